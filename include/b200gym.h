@@ -1,0 +1,126 @@
+/* b200gym — C ABI of the B200-native per-step tensor pipeline for legged_gym_dev.
+ *
+ * Drop-in boundary.  The reference has no native code: every entry point below
+ * replaces a group of Python/torch methods, cited as file:line of /root/reference.  All functions
+ *   - take raw device pointers + sizes + a cudaStream_t (as void*), never torch types,
+ *   - only ENQUEUE work on the stream (no host sync, CUDA-graph capturable),
+ *   - return 0 on success, <0 on error with a message in b200gym_last_error() (thread-local),
+ *   - never allocate or free tensor memory (PyTorch / PhysX own it).
+ * There is no CPU fallback.
+ */
+#ifndef B200GYM_H
+#define B200GYM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GYM_VERSION 100
+#define B200GYM_NUM_DOF 12
+#define B200GYM_NUM_FEET 4
+#define B200GYM_NUM_PEN 8
+#define B200GYM_MAX_TERM 4
+#define B200GYM_NUM_REWARD_TERMS 19 /* alphabetical _reward_* names, `termination` last (legged_robot.py:605-629) */
+#define B200GYM_MAX_POINTS 32
+
+int b200gym_version(void);
+const char* b200gym_last_error(void);
+/* sizeof() of the POD structs below, so a binding can verify its mirror of the layout */
+int b200gym_sizeof(const char* struct_name);
+
+/* ------------------------------------------------------------------------------------------------
+ * Group R — LeggedRobot / Anymal step pipeline
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct B200LeggedParams {
+    int32_t num_envs, num_obs, num_bodies, num_heights; /* num_heights = 0 unless cfg.terrain.measure_heights */
+    int32_t feet_idx[B200GYM_NUM_FEET], pen_idx[B200GYM_NUM_PEN], term_idx[B200GYM_MAX_TERM], num_term;
+    int32_t control_type; /* 0 P, 1 V, 2 T (legged_robot.py:402-412) */
+    float action_scale, sim_dt, dt, clip_actions, clip_obs;
+    float p_gains[B200GYM_NUM_DOF], d_gains[B200GYM_NUM_DOF], default_dof_pos[B200GYM_NUM_DOF];
+    float torque_limits[B200GYM_NUM_DOF], dof_pos_lo[B200GYM_NUM_DOF], dof_pos_hi[B200GYM_NUM_DOF];
+    float dof_vel_limits[B200GYM_NUM_DOF];
+    float obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel, obs_height;
+    int32_t add_noise;
+    float noise_lin_vel, noise_ang_vel, noise_gravity, noise_dof_pos, noise_dof_vel, noise_height;
+    int32_t heading_command, resample_steps;
+    float cmd_lo[4], cmd_span[4]; /* lin_vel_x, lin_vel_y, ang_vel_yaw, heading: lower and (upper - lower) */
+    int32_t push_robots, push_time;
+    float push_lo, push_span;
+    float max_episode_length, max_episode_length_s;
+    float reward_scale[B200GYM_NUM_REWARD_TERMS]; /* cfg scale * dt; 0 = term inactive */
+    int32_t sum_row[B200GYM_NUM_REWARD_TERMS];    /* row of episode_sums[K,N] or -1 */
+    int32_t num_sum_rows, only_positive;
+    float tracking_sigma, soft_dof_vel_limit, soft_torque_limit, base_height_target, max_contact_force;
+    int32_t mesh_plane, terrain_curriculum, terrain_rows, terrain_cols, max_terrain_level, terrain_num_cols;
+    float border_size, horizontal_scale, vertical_scale, half_env_length;
+    int32_t n_px, n_py;
+    float points_x[B200GYM_MAX_POINTS], points_y[B200GYM_MAX_POINTS];
+    int32_t custom_origins, zero_lstm_on_reset;
+    float base_init_state[13];
+    uint32_t seed_lo, seed_hi;
+} B200LeggedParams;
+
+typedef struct B200LeggedBuffers {
+    /* PhysX-owned, AoS as given (legged_robot.py:545-551) */
+    float* root_states;          /* [N,13]  pos3 quat4(xyzw) lin3 ang3; written on push / reset */
+    float* dof_state;            /* [N,12,2] (pos,vel); written on reset */
+    const float* contact_forces; /* [N,B,3] */
+    const float* actions;        /* [N,12] clipped */
+    const float* torques;        /* [N,12] */
+    /* env-owned state (legged_robot.py:561-581, base_task.py:70-79) */
+    float* last_actions;         /* [N,12] */
+    float* last_dof_vel;         /* [N,12] */
+    float* last_root_vel;        /* [N,6] */
+    float* commands;             /* [N,4] */
+    float* feet_air_time;        /* [N,4] */
+    uint8_t* last_contacts;      /* [N,4] bool */
+    int64_t* episode_length_buf; /* [N] */
+    uint8_t* reset_buf;          /* [N] bool (out) */
+    uint8_t* time_out_buf;       /* [N] bool (out) */
+    float* rew_buf;              /* [N] (out) */
+    float* episode_sums;         /* [K,N] rows = active reward terms, alphabetical */
+    float* obs_buf;              /* [N,O] (out, already clipped to +-clip_obs) */
+    float* base_lin_vel;         /* [N,3] (out) */
+    float* base_ang_vel;         /* [N,3] (out) */
+    float* projected_gravity;    /* [N,3] (out) */
+    float* measured_heights;     /* [N,H] (out) or NULL */
+    const int16_t* height_samples; /* [rows,cols] or NULL */
+    float* env_origins;          /* [N,3] */
+    int64_t* terrain_levels;     /* [N] or NULL */
+    const int64_t* terrain_types;  /* [N] or NULL */
+    const float* terrain_origins;  /* [max_level, num_cols, 3] or NULL */
+    float* lstm_h;               /* [2,N*12,8] or NULL: zeroed for reset envs (anymal.py:59-60) */
+    float* lstm_c;
+    /* extras["episode"] (legged_robot.py:175-182): [K] means / max_episode_length_s, [K] terrain_level mean,
+       [K+1] number of envs reset this step.  Entries are left untouched on steps without a reset (:156-157). */
+    float* extras_out;           /* [K+2] */
+    double* ws_sums;             /* [K+2] workspace, zero-initialised by the caller once */
+    uint32_t* ws_counter;        /* [1]   workspace, zero-initialised by the caller once */
+} B200LeggedBuffers;
+
+/* LeggedRobot._compute_torques (legged_robot.py:389-413), optionally fused with the action clip of
+ * LeggedRobot.step (:86-87): if actions_clipped != NULL the clipped actions are also written there.
+ * last_dof_vel is only read for control_type V. */
+int b200gym_pd_torques(const B200LeggedParams* p, const float* actions, float* actions_clipped, const float* dof_state,
+                       const float* last_dof_vel, float* torques, void* stream);
+
+/* Anymal._compute_torques, actuator-network branch (anymal.py:71-78) incl. the TorchScript LSTMsea forward.
+ * h, c: [2, N*12, 8], updated in place. */
+int b200gym_set_actuator_net(const float* w_ih0, const float* w_hh0, const float* b_ih0, const float* b_hh0,
+                             const float* w_ih1, const float* w_hh1, const float* b_ih1, const float* b_hh1,
+                             const float* w_lin, const float* b_lin, float in_scale0, float in_scale1, float out_scale);
+int b200gym_lstm_torques(const B200LeggedParams* p, const float* actions, float* actions_clipped, const float* dof_state,
+                         float* h, float* c, float* torques, void* stream);
+
+/* LeggedRobot.post_physics_step (legged_robot.py:106-134) + the obs clip of step() (:100-101), fused:
+ * counters, body-frame velocities, command resampling / heading, height scan, pushes, termination,
+ * all reward terms, in-place reset, observations + noise, last_* copies, extras["episode"] statistics.
+ * `step` is common_step_counter AFTER its increment (:115); env_id_offset = global id of local env 0. */
+int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedBuffers* b, uint64_t step, int64_t env_id_offset,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GYM_H */

@@ -1,0 +1,180 @@
+"""ctypes binding of libb200gym.so (the C ABI declared in include/b200gym.h).
+
+The library is built in-tree by `make` / `__graft_entry__.build()`.  There is NO fallback: if the shared
+object is missing or a call fails, a RuntimeError is raised (BASELINE.json north_star: "no CPU fallback").
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200gym.so")
+
+NUM_DOF, NUM_FEET, NUM_PEN, MAX_TERM, NUM_TERMS, MAX_POINTS = 12, 4, 8, 4, 19, 32
+
+f32, i32, u32 = C.c_float, C.c_int32, C.c_uint32
+vp = C.c_void_p
+
+
+class LeggedParamsPOD(C.Structure):
+    _fields_ = [
+        ("num_envs", i32), ("num_obs", i32), ("num_bodies", i32), ("num_heights", i32),
+        ("feet_idx", i32 * NUM_FEET), ("pen_idx", i32 * NUM_PEN), ("term_idx", i32 * MAX_TERM), ("num_term", i32),
+        ("control_type", i32),
+        ("action_scale", f32), ("sim_dt", f32), ("dt", f32), ("clip_actions", f32), ("clip_obs", f32),
+        ("p_gains", f32 * NUM_DOF), ("d_gains", f32 * NUM_DOF), ("default_dof_pos", f32 * NUM_DOF),
+        ("torque_limits", f32 * NUM_DOF), ("dof_pos_lo", f32 * NUM_DOF), ("dof_pos_hi", f32 * NUM_DOF),
+        ("dof_vel_limits", f32 * NUM_DOF),
+        ("obs_lin_vel", f32), ("obs_ang_vel", f32), ("obs_dof_pos", f32), ("obs_dof_vel", f32), ("obs_height", f32),
+        ("add_noise", i32),
+        ("noise_lin_vel", f32), ("noise_ang_vel", f32), ("noise_gravity", f32), ("noise_dof_pos", f32),
+        ("noise_dof_vel", f32), ("noise_height", f32),
+        ("heading_command", i32), ("resample_steps", i32),
+        ("cmd_lo", f32 * 4), ("cmd_span", f32 * 4),
+        ("push_robots", i32), ("push_time", i32), ("push_lo", f32), ("push_span", f32),
+        ("max_episode_length", f32), ("max_episode_length_s", f32),
+        ("reward_scale", f32 * NUM_TERMS), ("sum_row", i32 * NUM_TERMS),
+        ("num_sum_rows", i32), ("only_positive", i32),
+        ("tracking_sigma", f32), ("soft_dof_vel_limit", f32), ("soft_torque_limit", f32),
+        ("base_height_target", f32), ("max_contact_force", f32),
+        ("mesh_plane", i32), ("terrain_curriculum", i32), ("terrain_rows", i32), ("terrain_cols", i32),
+        ("max_terrain_level", i32), ("terrain_num_cols", i32),
+        ("border_size", f32), ("horizontal_scale", f32), ("vertical_scale", f32), ("half_env_length", f32),
+        ("n_px", i32), ("n_py", i32), ("points_x", f32 * MAX_POINTS), ("points_y", f32 * MAX_POINTS),
+        ("custom_origins", i32), ("zero_lstm_on_reset", i32),
+        ("base_init_state", f32 * 13),
+        ("seed_lo", u32), ("seed_hi", u32),
+    ]
+
+
+_BUF_FIELDS = ["root_states", "dof_state", "contact_forces", "actions", "torques", "last_actions", "last_dof_vel",
+               "last_root_vel", "commands", "feet_air_time", "last_contacts", "episode_length_buf", "reset_buf",
+               "time_out_buf", "rew_buf", "episode_sums", "obs_buf", "base_lin_vel", "base_ang_vel",
+               "projected_gravity", "measured_heights", "height_samples", "env_origins", "terrain_levels",
+               "terrain_types", "terrain_origins", "lstm_h", "lstm_c", "extras_out", "ws_sums", "ws_counter"]
+
+
+class LeggedBuffersPOD(C.Structure):
+    _fields_ = [(n, vp) for n in _BUF_FIELDS]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `make` or `python -c 'import __graft_entry__ as g; "
+                           f"g.build()'` — the b200gym path has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.b200gym_version.restype = C.c_int
+    L.b200gym_last_error.restype = C.c_char_p
+    L.b200gym_sizeof.restype = C.c_int
+    L.b200gym_sizeof.argtypes = [C.c_char_p]
+    pp = C.POINTER(LeggedParamsPOD)
+    L.b200gym_pd_torques.argtypes = [pp, vp, vp, vp, vp, vp, vp]
+    L.b200gym_set_actuator_net.argtypes = [vp] * 10 + [f32, f32, f32]
+    L.b200gym_lstm_torques.argtypes = [pp, vp, vp, vp, vp, vp, vp, vp]
+    L.b200gym_post_physics.argtypes = [pp, C.POINTER(LeggedBuffersPOD), C.c_uint64, C.c_int64, vp]
+    for name in ("b200gym_pd_torques", "b200gym_set_actuator_net", "b200gym_lstm_torques", "b200gym_post_physics"):
+        getattr(L, name).restype = C.c_int
+    for name, cls in (("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD)):
+        n = L.b200gym_sizeof(name.encode())
+        if n != C.sizeof(cls):
+            raise RuntimeError(f"ABI mismatch: sizeof({name}) is {n} in the library, {C.sizeof(cls)} in the binding")
+    _register_optional(L)
+    _lib = L
+    return L
+
+
+_OPTIONAL = []
+
+
+def _register_optional(L):
+    for fn in _OPTIONAL:
+        fn(L)
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().b200gym_last_error().decode(errors="replace")
+        raise RuntimeError(f"b200gym {what} failed ({rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"b200gym: `{name}` lives on {t.device}; the fused path runs on CUDA only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"b200gym: `{name}` must be contiguous")
+
+
+def fill_params(p, num_sum_rows, sum_row, zero_lstm_on_reset=False) -> LeggedParamsPOD:
+    """LeggedParams (legged_gym_dev_b200.params) -> POD struct.  Differences `hi - lo` are taken in double
+    here, exactly where the reference takes them in Python floats (helpers.py:129-130)."""
+    s = LeggedParamsPOD()
+    s.num_envs, s.num_obs, s.num_bodies, s.num_heights = p.num_envs, p.num_obs, p.num_bodies, p.num_height_points
+    if len(p.feet_indices) != NUM_FEET or len(p.penalised_indices) != NUM_PEN or p.num_dof != NUM_DOF:
+        raise ValueError("the fused step pipeline is specialised for 12 DOF / 4 feet / 8 penalised bodies (ANYmal-class)")
+    if not (1 <= len(p.termination_indices) <= MAX_TERM):
+        raise ValueError("1..4 termination bodies supported")
+    s.feet_idx[:] = p.feet_indices
+    s.pen_idx[:] = p.penalised_indices
+    for i, v in enumerate(p.termination_indices):
+        s.term_idx[i] = v
+    s.num_term = len(p.termination_indices)
+    s.control_type = p.control_type
+    s.action_scale, s.sim_dt, s.dt = p.action_scale, p.sim_dt, p.dt
+    s.clip_actions, s.clip_obs = p.clip_actions, p.clip_observations
+    s.p_gains[:], s.d_gains[:], s.default_dof_pos[:] = p.p_gains, p.d_gains, p.default_dof_pos
+    s.torque_limits[:], s.dof_vel_limits[:] = p.torque_limits, p.dof_vel_limits
+    s.dof_pos_lo[:] = [a for a, _ in p.dof_pos_limits]
+    s.dof_pos_hi[:] = [b for _, b in p.dof_pos_limits]
+    s.obs_lin_vel, s.obs_ang_vel, s.obs_dof_pos = p.obs_lin_vel, p.obs_ang_vel, p.obs_dof_pos
+    s.obs_dof_vel, s.obs_height = p.obs_dof_vel, p.obs_height
+    s.add_noise = int(p.add_noise)
+    s.noise_lin_vel, s.noise_ang_vel, s.noise_gravity = p.noise_lin_vel, p.noise_ang_vel, p.noise_gravity
+    s.noise_dof_pos, s.noise_dof_vel, s.noise_height = p.noise_dof_pos, p.noise_dof_vel, p.noise_height
+    s.heading_command, s.resample_steps = int(p.heading_command), p.resample_steps
+    for i, r in enumerate((p.cmd_lin_vel_x, p.cmd_lin_vel_y, p.cmd_ang_vel_yaw, p.cmd_heading)):
+        s.cmd_lo[i], s.cmd_span[i] = r[0], r[1] - r[0]
+    s.push_robots, s.push_time = int(p.push_robots), int(p.push_time)
+    s.push_lo, s.push_span = -p.max_push_vel, p.max_push_vel - (-p.max_push_vel)
+    s.max_episode_length, s.max_episode_length_s = p.max_episode_length, p.max_episode_length_s
+    s.reward_scale[:] = p.reward_scales
+    s.sum_row[:] = sum_row
+    s.num_sum_rows, s.only_positive = num_sum_rows, int(p.only_positive_rewards)
+    s.tracking_sigma, s.soft_dof_vel_limit, s.soft_torque_limit = p.tracking_sigma, p.soft_dof_vel_limit, p.soft_torque_limit
+    s.base_height_target, s.max_contact_force = p.base_height_target, p.max_contact_force
+    s.mesh_plane = int(p.mesh_type == "plane")
+    s.terrain_curriculum = int(p.terrain_curriculum)
+    s.terrain_rows, s.terrain_cols = p.terrain_rows, p.terrain_cols
+    s.max_terrain_level, s.terrain_num_cols = p.max_terrain_level, p.terrain_num_cols
+    s.border_size, s.horizontal_scale, s.vertical_scale = p.border_size, p.horizontal_scale, p.vertical_scale
+    s.half_env_length = p.terrain_length / 2
+    if p.measure_heights:
+        if len(p.measured_points_x) > MAX_POINTS or len(p.measured_points_y) > MAX_POINTS:
+            raise ValueError("at most 32 x 32 height points")
+        s.n_px, s.n_py = len(p.measured_points_x), len(p.measured_points_y)
+        for i, v in enumerate(p.measured_points_x):
+            s.points_x[i] = v
+        for i, v in enumerate(p.measured_points_y):
+            s.points_y[i] = v
+    s.custom_origins, s.zero_lstm_on_reset = int(p.custom_origins), int(zero_lstm_on_reset)
+    s.base_init_state[:] = p.base_init_state
+    s.seed_lo, s.seed_hi = p.seed & 0xFFFFFFFF, (p.seed >> 32) & 0xFFFFFFFF
+    return s

@@ -1,0 +1,146 @@
+"""Config objects with the attribute surface the step pipeline reads.
+
+The reference keeps nested-class configs (legged_gym/envs/base/legged_robot_config.py:34-279 and the
+anymal_c overrides).  The fused path is duck-typed: it accepts those very objects.  Because the reference
+cannot be imported on a box without Isaac Gym, this module builds equivalent attribute trees from compact
+tables, so `task_registry.make_env("anymal_c_flat")` works standalone.  Values follow the reference files
+cited per block; where the fork's shipped config is broken the two missing attributes
+are filled in and flagged.
+"""
+import copy
+
+
+class Cfg:
+    """Attribute tree; dict-valued leaves stay dicts (e.g. stiffness / default_joint_angles)."""
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+    def __repr__(self):
+        return "Cfg(" + ", ".join(f"{k}={v!r}" for k, v in vars(self).items()) + ")"
+
+
+def _tree(d):
+    return Cfg(**{k: _tree(v) if isinstance(v, dict) and k not in _DICT_LEAVES else copy.deepcopy(v) for k, v in d.items()})
+
+
+_DICT_LEAVES = {"default_joint_angles", "stiffness", "damping", "terrain_kwargs"}
+
+_GRID_X = [round(-0.8 + 0.1 * i, 1) for i in range(17)]      # legged_robot_config.py:55-57
+_GRID_Y = [round(-0.5 + 0.1 * i, 1) for i in range(11)]
+
+_BASE = {
+    "env": dict(num_envs=4096, num_observations=235, num_privileged_obs=None, num_actions=12, env_spacing=3.0,
+                send_timeouts=True, episode_length_s=20),                                       # :35-42
+    "terrain": dict(mesh_type="trimesh", horizontal_scale=0.1, vertical_scale=0.005, border_size=25, curriculum=True,
+                    static_friction=1.0, dynamic_friction=1.0, restitution=0.0, measure_heights=True,
+                    measured_points_x=_GRID_X, measured_points_y=_GRID_Y, selected=False, terrain_kwargs=None,
+                    max_init_terrain_level=5, terrain_length=8.0, terrain_width=8.0, num_rows=10, num_cols=20,
+                    terrain_proportions=[0.1, 0.1, 0.35, 0.25, 0.2], slope_treshold=0.75),      # :44-69
+    "commands": dict(num_commands=4, resampling_time=10.0, heading_command=True,
+                     ranges=dict(lin_vel_x=[-0.0, 0.0], lin_vel_y=[-0.0, 0.0], ang_vel_yaw=[-0, 0],
+                                 heading=[-0.0, 0.0])),                                         # :71-83
+    "init_state": dict(pos=[0.0, 0.0, 1.0], rot=[0.0, 0.0, 0.0, 1.0], lin_vel=[0.0, 0.0, 0.0], ang_vel=[0.0, 0.0, 0.0],
+                       default_joint_angles={"joint_a": 0.0, "joint_b": 0.0}),
+    "control": dict(control_type="P", stiffness={"joint_a": 10.0, "joint_b": 15.0}, damping={"joint_a": 1.0, "joint_b": 1.5},
+                    action_scale=0.5, decimation=4),
+    "asset": dict(file="", name="legged_robot", foot_name="None", penalize_contacts_on=[], terminate_after_contacts_on=[],
+                  self_collisions=0),
+    "domain_rand": dict(randomize_friction=True, friction_range=[0.5, 1.25], randomize_base_mass=False,
+                        added_mass_range=[-1.0, 1.0], push_robots=True, push_interval_s=15, max_push_vel_xy=1.0,
+                        max_push_vel=1.0),   # max_push_vel: read at legged_robot.py:827, missing in the fork
+    "rewards": dict(scales=dict(termination=-0.0), only_positive_rewards=True, tracking_sigma=0.25, soft_dof_pos_limit=1.0,
+                    soft_dof_vel_limit=1.0, soft_torque_limit=1.0, base_height_target=1.0, max_contact_force=100.0),
+    "curriculum": dict(use_curriculum=False, curriculum_steps=[100, 200], commands=[0.5, 0.75, 1],
+                       push=dict(magnitude=[0.1, 0.5, 1], time=[3, 2, 1])),   # use_curriculum: annotation-only in the fork
+    "normalization": dict(obs_scales=dict(lin_vel=2.0, ang_vel=0.25, dof_pos=1.0, dof_vel=0.05, height_measurements=5.0),
+                          clip_observations=100.0, clip_actions=100.0),
+    "noise": dict(add_noise=True, noise_level=1.0,
+                  noise_scales=dict(dof_pos=0.01, dof_vel=1.5, lin_vel=0.1, ang_vel=0.2, gravity=0.05,
+                                    height_measurements=0.1)),
+    "sim": dict(dt=0.005, substeps=1, gravity=[0.0, 0.0, -9.81], up_axis=1),
+}
+
+_PPO = {
+    "seed": 1, "runner_class_name": "OnPolicyRunner",
+    "policy": dict(init_noise_std=1.0, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128], activation="elu"),
+    "algorithm": dict(value_loss_coef=1.0, use_clipped_value_loss=True, clip_param=0.2, entropy_coef=0.01,
+                      num_learning_epochs=5, num_mini_batches=4, learning_rate=1.0e-3, schedule="adaptive", gamma=0.99,
+                      lam=0.95, desired_kl=0.01, max_grad_norm=1.0),                              # :249-261
+    "runner": dict(policy_class_name="ActorCritic", algorithm_class_name="PPO", num_steps_per_env=24, max_iterations=1500,
+                   save_interval=50, experiment_name="test", run_name="", resume=False, load_run=-1, checkpoint=-1,
+                   resume_path=None),
+}
+
+
+def _merge(base, over):
+    out = copy.deepcopy(base)
+    for k, v in over.items():
+        if isinstance(v, dict) and isinstance(out.get(k), dict) and k not in _DICT_LEAVES:
+            out[k] = _merge(out[k], v)
+        else:
+            out[k] = copy.deepcopy(v)
+    return out
+
+
+_ANYMAL_ROUGH = _merge(_BASE, {      # anymal_c/mixed_terrains/anymal_c_rough_config.py:32-86
+    "env": dict(num_envs=4096, num_actions=12),
+    "init_state": dict(pos=[0.0, 0.0, 0.6], default_joint_angles={
+        "LF_HAA": 0.0, "LH_HAA": 0.0, "RF_HAA": -0.0, "RH_HAA": -0.0, "LF_HFE": 0.4, "LH_HFE": -0.4, "RF_HFE": 0.4,
+        "RH_HFE": -0.4, "LF_KFE": -0.8, "LH_KFE": 0.8, "RF_KFE": -0.8, "RH_KFE": 0.8}),
+    "control": dict(stiffness={"HAA": 80.0, "HFE": 80.0, "KFE": 80.0}, damping={"HAA": 2.0, "HFE": 2.0, "KFE": 2.0},
+                    use_actuator_network=True,
+                    actuator_net_file="{LEGGED_GYM_ROOT_DIR}/resources/actuator_nets/anydrive_v3_lstm.pt"),
+    "asset": dict(file="{LEGGED_GYM_ROOT_DIR}/resources/robots/anymal_c/urdf/anymal_c.urdf", name="anymal_c", foot_name="FOOT",
+                  penalize_contacts_on=["SHANK", "THIGH"], terminate_after_contacts_on=["base"], self_collisions=1),
+    "domain_rand": dict(randomize_base_mass=True, added_mass_range=[-5.0, 5.0]),
+    "rewards": dict(base_height_target=0.5, max_contact_force=500.0, only_positive_rewards=True),
+})
+
+_ANYMAL_FLAT = _merge(_ANYMAL_ROUGH, {   # anymal_c/flat/anymal_c_flat_config.py:32-60
+    "env": dict(num_observations=48),
+    "terrain": dict(mesh_type="plane", measure_heights=False),
+    "asset": dict(self_collisions=0),
+    "rewards": dict(max_contact_force=350.0, scales=dict(orientation=-5.0, torques=-0.000025, feet_air_time=2.0)),
+    "commands": dict(heading_command=False, resampling_time=4.0, ranges=dict(ang_vel_yaw=[-1.5, 1.5])),
+    "domain_rand": dict(friction_range=[0.0, 1.5]),
+})
+
+# The upstream defaults the fork commented out (legged_robot_config.py:76-79,155-168): the throughput config
+# of SURVEY.md §8d cfg 2(b).
+UPSTREAM_REWARD_SCALES = dict(tracking_lin_vel=1.0, tracking_ang_vel=0.5, lin_vel_z=-2.0, ang_vel_xy=-0.05, torques=-0.00001,
+                              dof_acc=-2.5e-7, feet_air_time=1.0, collision=-1.0, action_rate=-0.01, termination=-0.0)
+UPSTREAM_COMMAND_RANGES = dict(lin_vel_x=[-1.0, 1.0], lin_vel_y=[-1.0, 1.0], ang_vel_yaw=[-1, 1], heading=[-3.14, 3.14])
+
+
+def anymal_c_rough_cfg():
+    return _tree(_ANYMAL_ROUGH)
+
+
+def anymal_c_flat_cfg():
+    return _tree(_ANYMAL_FLAT)
+
+
+def anymal_c_rough_cfg_ppo():
+    return _tree(_merge(_PPO, {"runner": dict(experiment_name="rough_anymal_c")}))
+
+
+def anymal_c_flat_cfg_ppo():
+    return _tree(_merge(_PPO, {"policy": dict(actor_hidden_dims=[128, 64, 32], critic_hidden_dims=[128, 64, 32]),
+                               "runner": dict(experiment_name="flat_anymal_c", max_iterations=300)}))
+
+
+def with_upstream_rewards(cfg, pd_control=True):
+    """cfg 2(b): upstream reward/command tables; PD branch of _compute_torques."""
+    cfg = cfg.clone()
+    for k, v in UPSTREAM_REWARD_SCALES.items():
+        setattr(cfg.rewards.scales, k, v)
+    for k, v in UPSTREAM_COMMAND_RANGES.items():
+        setattr(cfg.commands.ranges, k, list(v))
+    if pd_control:
+        cfg.control.use_actuator_network = False
+    return cfg

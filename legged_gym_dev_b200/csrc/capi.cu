@@ -1,0 +1,28 @@
+// Library-level entry points of the C ABI: version, error string, struct sizes.
+#include "common.cuh"
+#include "../../include/b200gym.h"
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void b200gym_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int b200gym_version(void) { return B200GYM_VERSION; }
+
+const char* b200gym_last_error(void) { return g_err; }
+
+int b200gym_sizeof(const char* name) {
+    if (!name) return -1;
+    if (!strcmp(name, "B200LeggedParams")) return (int)sizeof(B200LeggedParams);
+    if (!strcmp(name, "B200LeggedBuffers")) return (int)sizeof(B200LeggedBuffers);
+    return -1;
+}
+
+}  // extern "C"

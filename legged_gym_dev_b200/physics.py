@@ -1,0 +1,64 @@
+"""Physics stand-ins behind the LeggedRobot drop-in.
+
+The reference talks to PhysX through `self.gym` and three aliased state tensors
+(legged_robot.py:92-96,111-112,537-551).  PhysX is closed source and out of scope, so the env takes a
+`physics` object with the same three tensors and the same three moments of the step:
+
+    simulate(torques)   <- gym.set_dof_actuation_force_tensor + gym.simulate + gym.refresh_dof_state_tensor
+    refresh()           <- gym.refresh_actor_root_state_tensor + gym.refresh_net_contact_force_tensor
+    commit_resets()     <- gym.set_dof_state_tensor_indexed / set_actor_root_state_tensor_indexed (:428-430,452-454)
+
+`ReplayPhysics` replays a recorded / synthetic tape (legged_gym_dev_b200.synthetic).  An Isaac Gym
+adapter implementing the same three calls is sketched in INTEGRATION.md.
+"""
+import torch
+
+
+class ReplayPhysics:
+    """copy=True : frames are copied into persistent aliased buffers (what PhysX does; resets written by
+                   the kernels are overwritten by the next frame).  Used by parity tests.
+       copy=False: the aliased tensors are re-pointed at the tape frames (zero-copy replay; in-kernel
+                   resets then land in the tape).  Used by the throughput bench so that no
+                   device-to-device copy sits inside the timed region (SURVEY.md §8d cfg 2)."""
+
+    def __init__(self, tape, device="cuda", copy=True):
+        self.tape = tape
+        self.copy = copy
+        dev = torch.device(device)
+        self.root_frames = tape.root.to(dev)
+        self.dof_frames = tape.dof.to(dev)
+        self.contact_frames = tape.contact.to(dev).reshape(tape.frames, tape.num_envs * tape.contact.shape[2], 3)
+        self.num_envs, self.frames, self.decimation = tape.num_envs, tape.frames, tape.decimation
+        self.frame = 0
+        self.sub = 0
+        if copy:
+            self.root_states = self.root_frames[0].clone()
+            self.dof_state = self.dof_frames[0, 0].clone()
+            self.contact_forces = self.contact_frames[0].clone()
+        else:
+            self.root_states = self.root_frames[0]
+            self.dof_state = self.dof_frames[0, 0]
+            self.contact_forces = self.contact_frames[0]
+
+    def simulate(self, torques):
+        f = self.frame % self.frames
+        if self.copy:
+            self.dof_state.copy_(self.dof_frames[f, self.sub])
+        else:
+            self.dof_state = self.dof_frames[f, self.sub]
+        self.sub += 1
+
+    def refresh(self):
+        f = self.frame % self.frames
+        if self.copy:
+            self.root_states.copy_(self.root_frames[f])
+            self.contact_forces.copy_(self.contact_frames[f])
+        else:
+            self.root_states = self.root_frames[f]
+            self.contact_forces = self.contact_frames[f]
+        self.frame += 1
+        self.sub = 0
+
+    def commit_resets(self, reset_buf):
+        """PhysX would take over the reset rows of dof_state / root_states here; a replay has nothing to do."""
+        return None

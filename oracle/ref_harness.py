@@ -1,0 +1,436 @@
+"""Executes the UNMODIFIED reference (/root/reference) as the pinning oracle.  TEST INFRASTRUCTURE.
+
+Container-only: /root/reference does not exist on the GPU box, so nothing imported by `-m gpu`
+tests, smoke() or bench.py may import this module.  It is used by oracle/make_golden.py (to write
+tests/golden/*.npz) and by tests/test_oracle_cpu.py (to validate the travelling restatements in
+oracle/port_*.py), both `-m "not gpu"` and both skipped when /root/reference is absent.
+
+How: the absent heavy dependencies are replaced in sys.modules by mocks, except
+`isaacgym.torch_utils`, which is the restatement in oracle/isaacgym_restated.py; `Anymal.__init__` is
+bypassed and the attributes the asset loader would have produced are set by hand; `self.gym` is a stub
+whose simulate()/refresh_*() copy frames of a replay tape into the aliased state tensors.  The
+reference's own methods (`step`, `post_physics_step`, `_compute_torques`, `CustomSim.step`, ...) then
+run verbatim.  Randomness goes through oracle/rng_shim.py.
+"""
+import os
+import sys
+import types
+from types import SimpleNamespace
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+from . import philox as P
+from . import rng_shim, isaacgym_restated
+
+REF_ROOT = "/root/reference"
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF_ROOT, "legged_gym"))
+
+
+_imported = {}
+
+
+def import_reference():
+    """Stub-inject and import the reference packages once; returns a namespace of modules."""
+    if _imported:
+        return SimpleNamespace(**_imported)
+    if not reference_available():
+        raise RuntimeError("reference tree not present")
+    for name in ("casadi", "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "omegaconf", "hydra",
+                 "rsl_rl", "rsl_rl.env", "rsl_rl.runners", "pytorch3d", "pytorch3d.transforms", "wandb",
+                 "isaacgym.gymapi", "isaacgym.gymtorch", "isaacgym.gymutil", "isaacgym.terrain_utils"):
+        if name not in sys.modules:
+            sys.modules[name] = MagicMock()
+    if "isaacgym" not in sys.modules or isinstance(sys.modules["isaacgym"], MagicMock):
+        pkg = types.ModuleType("isaacgym")
+        pkg.__path__ = []
+        tu = types.ModuleType("isaacgym.torch_utils")
+        for k in ("to_torch", "get_axis_params", "normalize", "quat_apply", "quat_rotate_inverse", "torch_rand_float"):
+            setattr(tu, k, getattr(isaacgym_restated, k))
+        tu.torch = torch
+        tu.np = np
+        tu.__all__ = ["to_torch", "get_axis_params", "normalize", "quat_apply", "quat_rotate_inverse",
+                      "torch_rand_float", "torch", "np"]
+        pkg.torch_utils = tu
+        for sub in ("gymapi", "gymtorch", "gymutil", "terrain_utils"):
+            setattr(pkg, sub, sys.modules[f"isaacgym.{sub}"])
+        sys.modules["isaacgym"] = pkg
+        sys.modules["isaacgym.torch_utils"] = tu
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import legged_gym.envs as envs                                        # noqa: E402
+    import legged_gym.envs.base.legged_robot as legged_robot              # noqa: E402
+    import legged_gym.envs.anymal_c.anymal as anymal                      # noqa: E402
+    import trajopt.rom_dynamics as rom_dynamics                           # noqa: E402
+    import deep_tube_learning.utils as dtl_utils                          # noqa: E402
+    import deep_tube_learning.controllers as controllers                  # noqa: E402
+    import deep_tube_learning.custom_sim as custom_sim                    # noqa: E402
+    _imported.update(envs=envs, legged_robot=legged_robot, anymal=anymal, rom_dynamics=rom_dynamics,
+                     dtl_utils=dtl_utils, controllers=controllers, custom_sim=custom_sim)
+    return SimpleNamespace(**_imported)
+
+
+# --------------------------------------------------------------------------------------------
+# Group R: Anymal / LeggedRobot
+# --------------------------------------------------------------------------------------------
+UPSTREAM_REWARD_SCALES = dict(  # the commented-out upstream defaults, legged_robot_config.py:155-168
+    tracking_lin_vel=1.0, tracking_ang_vel=0.5, lin_vel_z=-2.0, ang_vel_xy=-0.05, torques=-1e-5,
+    dof_acc=-2.5e-7, feet_air_time=1.0, collision=-1.0, action_rate=-0.01, termination=-0.0)
+UPSTREAM_COMMAND_RANGES = dict(lin_vel_x=[-1.0, 1.0], lin_vel_y=[-1.0, 1.0], ang_vel_yaw=[-1, 1],
+                               heading=[-3.14, 3.14])     # legged_robot_config.py:76-79
+ALL_REWARD_SCALES = dict(       # every _reward_* term switched on (legged_robot.py:918-1015)
+    action_rate=-0.01, ang_vel_xy=-0.05, base_height=-1.0, collision=-1.0, dof_acc=-2.5e-7,
+    dof_pos_limits=-10.0, dof_vel=-1e-4, dof_vel_limits=-0.5, feet_air_time=1.0,
+    feet_contact_forces=-0.01, lin_vel_z=-2.0, orientation=-5.0, stand_still=-0.1, stumble=-0.3,
+    termination=-3.0, torque_limits=-0.02, torques=-1e-5, tracking_ang_vel=0.5, tracking_lin_vel=1.0)
+
+
+class _ReplayGym:
+    """Stands in for `self.gym`: simulate()/refresh_*() replay a tape into the aliased tensors."""
+
+    def __init__(self, env, tape):
+        self.env, self.tape = env, tape
+        self.frame = 0
+        self.sub = 0
+
+    def simulate(self, sim):
+        t = self.tape
+        self.env.dof_state.copy_(t.dof[self.frame % t.frames, self.sub])
+        self.sub += 1
+
+    def refresh_actor_root_state_tensor(self, sim):
+        t = self.tape
+        self.env.root_states.copy_(t.root[self.frame % t.frames])
+
+    def refresh_net_contact_force_tensor(self, sim):
+        t = self.tape
+        self.env.contact_forces.copy_(t.contact[self.frame % t.frames].reshape(self.env.contact_forces.shape))
+        self.frame += 1
+        self.sub = 0
+
+    def __getattr__(self, name):     # every other gym call is a no-op
+        return lambda *a, **k: None
+
+
+def make_reference_anymal(task, num_envs, tape, seed=0, reward_scales=None, command_ranges=None,
+                          use_actuator_network=None, heightfield=None, terrain_origins=None,
+                          episode_lengths=None, overrides=None):
+    """Build the reference's Anymal env for `task` in {"anymal_c_flat","anymal_c_rough"} without Isaac Gym."""
+    ref = import_reference()
+    from legged_gym_dev_b200 import synthetic as S
+    envs = ref.envs
+    cfg = envs.AnymalCFlatCfg() if task == "anymal_c_flat" else envs.AnymalCRoughCfg()
+    cfg.curriculum.use_curriculum = False          # annotation-only in the fork (legged_robot_config.py:179)
+    cfg.domain_rand.max_push_vel = 1.0             # read at legged_robot.py:827 but never defined
+    cfg.env.num_envs = num_envs
+    if reward_scales is not None:
+        for k, v in reward_scales.items():
+            setattr(cfg.rewards.scales, k, v)
+    if command_ranges is not None:
+        for k, v in command_ranges.items():
+            setattr(cfg.commands.ranges, k, list(v))
+    if use_actuator_network is not None:
+        cfg.control.use_actuator_network = use_actuator_network
+    for path, v in (overrides or {}).items():
+        obj = cfg
+        parts = path.split(".")
+        for p in parts[:-1]:
+            obj = getattr(obj, p)
+        setattr(obj, parts[-1], v)
+
+    Anymal = ref.anymal.Anymal
+    env = Anymal.__new__(Anymal)
+    env.cfg = cfg
+    env.sim_params = SimpleNamespace(dt=cfg.sim.dt, use_gpu_pipeline=False)
+    env.height_samples = None
+    env.debug_viz = False
+    env.init_done = False
+    env._parse_cfg(cfg)                                                   # reference code
+    # --- BaseTask.__init__ buffers (base_task.py:59-79) ---
+    env.device = "cpu"
+    env.headless = True
+    env.viewer = None
+    env.enable_viewer_sync = False
+    env.sim = None
+    env.num_envs, env.num_obs = cfg.env.num_envs, cfg.env.num_observations
+    env.num_privileged_obs, env.num_actions = cfg.env.num_privileged_obs, cfg.env.num_actions
+    env.obs_buf = torch.zeros(env.num_envs, env.num_obs, dtype=torch.float)
+    env.rew_buf = torch.zeros(env.num_envs, dtype=torch.float)
+    env.reset_buf = torch.ones(env.num_envs, dtype=torch.long)
+    env.episode_length_buf = torch.zeros(env.num_envs, dtype=torch.long)
+    env.time_out_buf = torch.zeros(env.num_envs, dtype=torch.bool)
+    env.privileged_obs_buf = None
+    env.extras = {}
+    # --- what create_sim/_create_envs would have produced (legged_robot.py:679-772) ---
+    env.up_axis_idx = 2
+    env.num_dof = env.num_dofs = S.NUM_DOF
+    env.num_bodies = S.NUM_BODIES
+    env.dof_names = list(S.DOF_NAMES)
+    env.feet_indices = torch.tensor(S.FEET_INDICES, dtype=torch.long)
+    env.penalised_contact_indices = torch.tensor(S.PENALISED_INDICES, dtype=torch.long)
+    env.termination_contact_indices = torch.tensor(S.TERMINATION_INDICES, dtype=torch.long)
+    lim = synthetic_dof_limits()
+    env.dof_pos_limits = lim["dof_pos_limits"].clone()
+    env.dof_vel_limits = lim["dof_vel_limits"].clone()
+    env.torque_limits = lim["torque_limits"].clone()
+    isl = cfg.init_state
+    env.base_init_state = torch.tensor(isl.pos + isl.rot + isl.lin_vel + isl.ang_vel, dtype=torch.float)
+    if cfg.terrain.mesh_type in ("heightfield", "trimesh"):
+        env.terrain = SimpleNamespace(cfg=cfg.terrain, env_length=cfg.terrain.terrain_length,
+                                      env_width=cfg.terrain.terrain_width,
+                                      env_origins=terrain_origins.numpy())
+        env.height_samples = heightfield
+        g = torch.Generator().manual_seed(seed + 31)
+        state = torch.get_rng_state()
+        torch.manual_seed(seed + 31)
+        env._get_env_origins()                                            # reference code (:790-817)
+        torch.set_rng_state(state)
+    else:
+        env._get_env_origins()
+    # --- aliased physics tensors (legged_robot.py:545-551): wrap_tensor returns ours, in order ---
+    root = tape.root[0].clone()
+    dof = tape.dof[0, 0].clone()
+    contact = tape.contact[0].reshape(num_envs * S.NUM_BODIES, 3).clone()
+    handed = iter([root, dof, contact])
+    ref.legged_robot.gymtorch.wrap_tensor = lambda _t: next(handed)
+    env.gym = MagicMock()
+    env._init_buffers()                                                   # reference code
+    env._prepare_reward_function()                                        # reference code
+    env.init_done = True
+    if cfg.control.use_actuator_network:
+        path = cfg.control.actuator_net_file.format(LEGGED_GYM_ROOT_DIR=REF_ROOT)
+        env.actuator_network = torch.jit.load(path)
+    env.gym = _ReplayGym(env, tape)
+    if episode_lengths is not None:
+        env.episode_length_buf[:] = episode_lengths
+    env._shim_seed = seed
+    _install_legged_wrappers(ref)
+    return env
+
+
+def synthetic_dof_limits():
+    """The URDF carries effort/velocity limits (80 N m, 20 rad/s: anymal_c.urdf:540) but no position
+    limits; synthetic +-(HAA 0.72, HFE/KFE 9.42*0.1...) style limits make the limit rewards non-trivial."""
+    lo = torch.tensor([-0.72, -1.2, -1.8] * 4, dtype=torch.float)
+    hi = torch.tensor([0.49, 1.2, 1.8] * 4, dtype=torch.float)
+    lo[3:6], hi[3:6] = torch.tensor([-0.49, -1.2, -1.8]), torch.tensor([0.72, 1.2, 1.8])
+    return dict(dof_pos_limits=torch.stack([lo, hi], dim=1),
+                dof_vel_limits=torch.full((12,), 20.0), torque_limits=torch.full((12,), 80.0))
+
+
+_wrapped = set()
+
+
+def _wrap(cls, name, make_ctx):
+    key = (cls, name)
+    if key in _wrapped:
+        return
+    _wrapped.add(key)
+    orig = getattr(cls, name)
+
+    def wrapper(self, *a, **k):
+        if not hasattr(self, "_shim_seed"):
+            return orig(self, *a, **k)
+        ctx = make_ctx(self, *a, **k)
+        if ctx is None:
+            return orig(self, *a, **k)
+        with rng_shim.draws(self._shim_seed, *ctx):
+            return orig(self, *a, **k)
+
+    wrapper.__wrapped__ = orig
+    setattr(cls, name, wrapper)
+
+
+def _install_legged_wrappers(ref):
+    LR = ref.legged_robot.LeggedRobot
+    rng_shim.install()
+    all_ids = lambda s: np.arange(s.num_envs)
+
+    def cmd_ctx(self, env_ids):
+        site = P.SITE_CMD_RESET if getattr(self, "_in_reset", False) else P.SITE_CMD_PERIODIC
+        return (env_ids, self.common_step_counter, [(site, 0), (site, 1), (site, 2)])
+
+    _wrap(LR, "_resample_commands", cmd_ctx)
+    _wrap(LR, "_push_robots", lambda s: (all_ids(s), s.common_step_counter, [(P.SITE_PUSH, 0)]))
+    _wrap(LR, "_update_terrain_curriculum",
+          lambda s, env_ids: (env_ids, s.common_step_counter, [(P.SITE_TERRAIN, 0)]))
+    _wrap(LR, "_reset_dofs", lambda s, env_ids: (env_ids, s.common_step_counter, [(P.SITE_RESET_DOF, 0)]))
+    _wrap(LR, "_reset_root_states",
+          lambda s, env_ids: (env_ids, s.common_step_counter,
+                              [(P.SITE_RESET_XY, 0), (P.SITE_RESET_VEL, 0)] if s.custom_origins
+                              else [(P.SITE_RESET_VEL, 0)]))
+    _wrap(LR, "compute_observations", lambda s: (all_ids(s), s.common_step_counter, [(P.SITE_OBS_NOISE, 0)]))
+    if (LR, "reset_idx") not in _wrapped:
+        _wrapped.add((LR, "reset_idx"))
+        orig = LR.reset_idx
+
+        def reset_idx(self, env_ids):
+            self._in_reset = True
+            try:
+                return orig(self, env_ids)
+            finally:
+                self._in_reset = False
+        LR.reset_idx = reset_idx
+
+
+# --------------------------------------------------------------------------------------------
+# Group M: CustomSim / TrajectoryGenerator / DoubleSingleTracking
+# --------------------------------------------------------------------------------------------
+def rom_config(num_envs, **over):
+    """Plain-namespace mirror of configs/data_generation/double_single_int.yaml:29-87 (+ default_custom.yaml)."""
+    pos = 1e9
+    d = dict(acc=0.5, vel=0.3, vel_rom=0.2, model_dt=0.05, rom_dt=0.1, N=10, dN=1, t_low=1, t_high=2,
+             freq_low=0.01, freq_high=2, prob_stationary=0.0005, max_rom_distance=[1.0, 1.0],
+             zero_rom_dist_llh=0.25, noise_lower=[0.0, 0.0, -0.1, -0.1], noise_upper=[0.0, 0.0, 0.1, 0.1],
+             weight_samp_cls="UniformWeightSamplerNoRamp", model_cls="DoubleInt2D", rom_cls="SingleInt2D",
+             randomize_rom_distance=True, Kp=10, Kd=10)
+    d.update(over)
+    ns = SimpleNamespace
+    cfg = ns(
+        env=ns(num_envs=num_envs, episode_length_s=20,
+               model=ns(dt=d["model_dt"], cls=d["model_cls"], z_min=[-pos, -pos, -d["vel"], -d["vel"]],
+                        z_max=[pos, pos, d["vel"], d["vel"]], v_min=[-d["acc"]] * 2, v_max=[d["acc"]] * 2)),
+        rom=ns(cls=d["rom_cls"], dt=d["rom_dt"], z_min=[-pos, -pos], z_max=[pos, pos],
+               v_min=[-d["vel_rom"]] * 2, v_max=[d["vel_rom"]] * 2),
+        trajectory_generator=ns(cls="TrajectoryGenerator", t_samp_cls="UniformSampleHoldDT",
+                                weight_samp_cls=d["weight_samp_cls"], N=d["N"], t_low=d["t_low"],
+                                t_high=d["t_high"], freq_low=d["freq_low"], freq_high=d["freq_high"], seed=0,
+                                prob_stationary=d["prob_stationary"], dN=d["dN"]),
+        noise=ns(add_noise=False),
+        domain_rand=ns(randomize_rom_distance=d["randomize_rom_distance"],
+                       max_rom_distance=d["max_rom_distance"], zero_rom_dist_llh=d["zero_rom_dist_llh"]),
+        init_state=ns(default_noise_lower=d["noise_lower"], default_noise_upper=d["noise_upper"]),
+        controller=ns(Kp=d["Kp"], Kd=d["Kd"]))
+    return cfg
+
+
+def make_reference_custom_sim(num_envs, seed=0, **over):
+    """The reference's CustomSim + DoubleSingleTracking on CPU, RNG through the shim."""
+    ref = import_reference()
+    cs, rd = ref.custom_sim, ref.rom_dynamics
+    cfg = rom_config(num_envs, **over)
+    # weight samplers default to device='cuda' and CustomSim passes no args (custom_sim.py:55, utils.py:52-79)
+    for name in ("UniformWeightSamplerNoRamp", "UniformWeightSamplerNoExtreme"):
+        base = getattr(ref.dtl_utils, name)
+        if not getattr(base, "_cpu_patched", False):
+            cpu_cls = type(name, (base,), {"__init__": (lambda b: lambda self, dim=4, seed=42, device="cpu":
+                                                        b.__init__(self, dim=dim, seed=seed, device="cpu"))(base),
+                                           "_cpu_patched": True})
+            setattr(cs, name, cpu_cls)
+    _install_rom_wrappers(ref)
+    holder = SimpleNamespace(seed=seed, ctr=np.zeros(num_envs, dtype=np.int64))
+    rd.TrajectoryGenerator._pending_holder = holder
+    try:
+        env = cs.CustomSim(cfg)
+    finally:
+        rd.TrajectoryGenerator._pending_holder = None
+    env._shim = holder
+    env.traj_gen._shim = holder
+    policy = ref.controllers.DoubleSingleTracking(cfg.controller.Kp, cfg.controller.Kd, env.model.clip_v_z)
+    return env, policy, cfg
+
+
+def _install_rom_wrappers(ref):
+    rd, cs = ref.rom_dynamics, ref.custom_sim
+    TG, CS = rd.TrajectoryGenerator, cs.CustomSim
+    rng_shim.install()
+    if (TG, "__init__") in _wrapped:
+        return
+    _wrapped.add((TG, "__init__"))
+
+    def take_events(holder, ids):
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        ev = holder.ctr[ids].copy()
+        holder.ctr[ids] += 1
+        return ev
+
+    tg_init = TG.__init__
+
+    def init(self, rom, *a, **k):
+        holder = getattr(TG, "_pending_holder", None)
+        if holder is None:
+            return tg_init(self, rom, *a, **k)
+        ids = np.arange(rom.n_robots)
+        with rng_shim.draws(holder.seed, ids, take_events(holder, ids), [(P.SITE_ROM_INIT, 0)]):
+            return tg_init(self, rom, *a, **k)
+    TG.__init__ = init
+
+    tg_resample = TG.resample
+
+    def resample(self, idx, z):
+        holder = getattr(self, "_shim", None)
+        if holder is None or len(idx) == 0:
+            return tg_resample(self, idx, z)
+        ids = idx.detach().cpu().numpy()
+        plan = [(s, 0) for s in (P.SITE_ROM_CONST, P.SITE_ROM_RAMP, P.SITE_ROM_EXTREME, P.SITE_ROM_SIN_MAG,
+                                 P.SITE_ROM_SIN_MEAN, P.SITE_ROM_SIN_FREQ, P.SITE_ROM_SIN_OFF,
+                                 P.SITE_ROM_TFINAL, P.SITE_ROM_WEIGHTS, P.SITE_ROM_STATIONARY)]
+        with rng_shim.draws(holder.seed, ids, take_events(holder, ids), plan):
+            return tg_resample(self, idx, z)
+    TG.resample = resample
+
+    cs_reset_idx = CS.reset_idx
+
+    def reset_idx(self, idx):
+        holder = getattr(self, "_shim", None)
+        if holder is None:
+            return cs_reset_idx(self, idx)
+        self._root_event = take_events(holder, idx.detach().cpu().numpy())
+        return cs_reset_idx(self, idx)
+    CS.reset_idx = reset_idx
+
+    # root draw happens inside reset_idx before reset_traj: give it its own one-call context by wrapping
+    # torch_rand_vec_float as seen from custom_sim's namespace.
+    vec = cs.torch_rand_vec_float
+
+    def torch_rand_vec_float(lower, upper, shape, device):
+        env = _current_sim[-1] if _current_sim else None
+        if env is None or getattr(env, "_root_event", None) is None:
+            return vec(lower, upper, shape, device)
+        ev, env._root_event = env._root_event, None
+        with rng_shim.draws(env._shim.seed, env._reset_ids, ev, [(P.SITE_ROM_ROOT, 0)]):
+            return vec(lower, upper, shape, device)
+    cs.torch_rand_vec_float = torch_rand_vec_float
+
+    inner_reset_idx = CS.reset_idx
+
+    def reset_idx_outer(self, idx):
+        self._reset_ids = idx.detach().cpu().numpy()
+        _current_sim.append(self)
+        try:
+            return inner_reset_idx(self, idx)
+        finally:
+            _current_sim.pop()
+    CS.reset_idx = reset_idx_outer
+
+    cs_reset_traj = CS.reset_traj
+
+    def reset_traj(self, env_ids):
+        holder = getattr(self, "_shim", None)
+        if holder is None:
+            return cs_reset_traj(self, env_ids)
+        ids = env_ids.detach().cpu().numpy()
+        ev = take_events(holder, ids)
+        llh = self.zero_rom_dist_llh
+
+        def lazy_ids(call, hist):
+            if call == 0:
+                return ids
+            return ids[(hist[0] > llh).numpy().reshape(-1)]
+
+        def lazy_ev(call, hist):
+            if call == 0:
+                return ev
+            return ev[(hist[0] > llh).numpy().reshape(-1)]
+
+        prev, self._root_event = getattr(self, "_root_event", None), None
+        with rng_shim.draws(holder.seed, lazy_ids, lazy_ev, [(P.SITE_ROM_DIST_MASK, 0), (P.SITE_ROM_DIST, 0)]):
+            return cs_reset_traj(self, env_ids)
+    CS.reset_traj = reset_traj
+
+
+_current_sim = []

@@ -1,0 +1,188 @@
+"""Builders shared by the Group-R parity tests: one *case* = task + reward table + control path."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from legged_gym_dev_b200 import configs, synthetic as S
+from legged_gym_dev_b200.params import flatten_legged_cfg
+
+ALL_REWARD_SCALES = dict(
+    action_rate=-0.01, ang_vel_xy=-0.05, base_height=-1.0, collision=-1.0, dof_acc=-2.5e-7, dof_pos_limits=-10.0,
+    dof_vel=-1e-4, dof_vel_limits=-0.5, feet_air_time=1.0, feet_contact_forces=-0.01, lin_vel_z=-2.0, orientation=-5.0,
+    stand_still=-0.1, stumble=-0.3, termination=-3.0, torque_limits=-0.02, torques=-1e-5, tracking_ang_vel=0.5,
+    tracking_lin_vel=1.0)
+
+# name -> (task, reward table, command table, use_actuator_network, extra overrides)
+CASES = {
+    "flat_pd_upstream": ("anymal_c_flat", configs.UPSTREAM_REWARD_SCALES, configs.UPSTREAM_COMMAND_RANGES, False, {}),
+    "flat_lstm_shipped": ("anymal_c_flat", None, None, True, {}),
+    "flat_allterms_v": ("anymal_c_flat", ALL_REWARD_SCALES, configs.UPSTREAM_COMMAND_RANGES, False,
+                        {"rewards.only_positive_rewards": False, "control.control_type": "V"}),
+    "flat_heading_nonoise": ("anymal_c_flat", configs.UPSTREAM_REWARD_SCALES, configs.UPSTREAM_COMMAND_RANGES, False,
+                             {"commands.heading_command": True, "noise.add_noise": False,
+                              "domain_rand.push_interval_s": 0.1}),
+    "rough_lstm_allterms": ("anymal_c_rough", ALL_REWARD_SCALES, configs.UPSTREAM_COMMAND_RANGES, True,
+                            {"rewards.only_positive_rewards": False, "domain_rand.push_interval_s": 0.1}),
+    "rough_pd_shipped": ("anymal_c_rough", None, None, False, {}),
+}
+
+
+def dof_limits():
+    lo = torch.tensor([-0.72, -1.2, -1.8] * 4, dtype=torch.float)
+    hi = torch.tensor([0.49, 1.2, 1.8] * 4, dtype=torch.float)
+    lo[3:6], hi[3:6] = torch.tensor([-0.49, -1.2, -1.8]), torch.tensor([0.72, 1.2, 1.8])
+    return dict(dof_pos_limits=torch.stack([lo, hi], dim=1), dof_vel_limits=torch.full((12,), 20.0),
+                torque_limits=torch.full((12,), 80.0))
+
+
+def apply_overrides(cfg, reward_scales, command_ranges, lstm, overrides):
+    if reward_scales is not None:
+        for k, v in reward_scales.items():
+            setattr(cfg.rewards.scales, k, v)
+    if command_ranges is not None:
+        for k, v in command_ranges.items():
+            setattr(cfg.commands.ranges, k, list(v))
+    cfg.control.use_actuator_network = lstm
+    for path, v in overrides.items():
+        obj = cfg
+        parts = path.split(".")
+        for q in parts[:-1]:
+            obj = getattr(obj, q)
+        setattr(obj, parts[-1], v)
+    return cfg
+
+
+def build_case(name, num_envs, frames=8, seed=5, tape_seed=1, base_contact_prob=0.02):
+    """Returns cfg + all inputs (CPU tensors) for the case."""
+    task, rs, cr, lstm, over = CASES[name]
+    rough = task == "anymal_c_rough"
+    cfg = configs.anymal_c_rough_cfg() if rough else configs.anymal_c_flat_cfg()
+    cfg = apply_overrides(cfg, rs, cr, lstm, over)
+    cfg.env.num_envs = num_envs
+    tape = S.make_state_tape(num_envs, frames=frames, seed=tape_seed, rough=rough, base_contact_prob=base_contact_prob)
+    ep = S.make_episode_lengths(num_envs, seed=tape_seed)
+    terrain = None
+    if rough:
+        hf = S.make_heightfield(seed=tape_seed)
+        to = S.make_terrain_origins(seed=tape_seed)
+        g = torch.Generator().manual_seed(tape_seed + 99)
+        levels = torch.randint(0, cfg.terrain.max_init_terrain_level + 1, (num_envs,), generator=g)
+        types = torch.div(torch.arange(num_envs), (num_envs / cfg.terrain.num_cols), rounding_mode="floor").to(torch.long)
+        terrain = dict(height_samples=hf, terrain_origins=to, terrain_levels=levels, terrain_types=types,
+                       env_origins=to[levels, types].clone())
+    return SimpleNamespace(name=name, task=task, rough=rough, lstm=lstm, cfg=cfg, tape=tape, ep=ep, terrain=terrain,
+                           seed=seed, num_envs=num_envs, limits=dof_limits())
+
+
+def make_params(case):
+    lim, t = case.limits, case.terrain
+    return flatten_legged_cfg(case.cfg, case.cfg.sim.dt, S.DOF_NAMES, num_envs=case.num_envs,
+                              dof_pos_limits=lim["dof_pos_limits"].tolist(), dof_vel_limits=lim["dof_vel_limits"].tolist(),
+                              torque_limits=lim["torque_limits"].tolist(),
+                              terrain_rows=t["height_samples"].shape[0] if t else 0,
+                              terrain_cols=t["height_samples"].shape[1] if t else 0, seed=case.seed)
+
+
+def make_port(case, rng="philox", env_id_offset=0):
+    from oracle.port_legged import LeggedPort, TapePhysics
+    p = make_params(case)
+    t = case.terrain or {}
+    w = None
+    if case.lstm:
+        import legged_gym_dev_b200
+        path = os.path.join(os.path.dirname(legged_gym_dev_b200.__file__), "resources", "anydrive_v3_lstm.npz")
+        w = dict(np.load(path))
+    clone = lambda x: x.clone() if x is not None else None
+    origins = clone(t.get("env_origins"))
+    if origins is None:                                               # legged_robot.py:808-817 (grid of robots)
+        N = case.num_envs
+        cols = np.floor(np.sqrt(N))
+        rows = np.ceil(N / cols)
+        xx, yy = torch.meshgrid(torch.arange(rows), torch.arange(cols), indexing="ij")
+        origins = torch.zeros(N, 3)
+        origins[:, 0] = case.cfg.env.env_spacing * xx.flatten()[:N]
+        origins[:, 1] = case.cfg.env.env_spacing * yy.flatten()[:N]
+    port = LeggedPort(p, case.tape.root[0].clone(), case.tape.dof[0, 0].clone(), case.tape.contact[0].clone(),
+                      env_origins=origins, height_samples=t.get("height_samples"),
+                      terrain_levels=clone(t.get("terrain_levels")), terrain_types=clone(t.get("terrain_types")),
+                      terrain_origins=clone(t.get("terrain_origins")), lstm=w, episode_length_buf=case.ep, rng=rng,
+                      env_id_offset=env_id_offset)
+    return port, TapePhysics(case.tape)
+
+
+def make_fused(case, device="cuda", copy=True, env_id_offset=0):
+    from legged_gym_dev_b200.legged_robot import Anymal
+    from legged_gym_dev_b200.physics import ReplayPhysics
+    phys = ReplayPhysics(case.tape, device=device, copy=copy)
+    lim = case.limits
+    asset = dict(dof_pos_limits=lim["dof_pos_limits"], dof_vel_limits=lim["dof_vel_limits"], torque_limits=lim["torque_limits"])
+    env = Anymal(case.cfg, SimpleNamespace(dt=case.cfg.sim.dt), None, device, True, physics=phys, asset=asset,
+                 seed=case.seed, terrain=case.terrain, env_id_offset=env_id_offset)
+    env.episode_length_buf.copy_(case.ep.to(device))
+    return env
+
+
+# quantities compared after every step: name -> (getter(port), getter(fused), kind, scale)
+def snapshot_port(port):
+    d = dict(obs=port.obs_buf, rew=port.rew_buf, reset=port.reset_buf, time_out=port.time_out_buf, torques=port.torques,
+             commands=port.commands, ep_len=port.episode_length_buf, feet_air_time=port.feet_air_time,
+             last_contacts=port.last_contacts, root=port.root_states, dof=port.dof_state, last_actions=port.last_actions,
+             last_dof_vel=port.last_dof_vel, last_root_vel=port.last_root_vel, base_lin_vel=port.base_lin_vel,
+             base_ang_vel=port.base_ang_vel, projected_gravity=port.projected_gravity)
+    for k, v in port.episode_sums.items():
+        d["sum_" + k] = v
+    if port.p.measure_heights:
+        d["heights"] = port.measured_heights
+    if port.p.terrain_curriculum:
+        d["terrain_levels"] = port.terrain_levels
+        d["env_origins"] = port.env_origins
+    if port.p.use_actuator_network:
+        d["lstm_h"], d["lstm_c"] = port.sea_hidden_state, port.sea_cell_state
+    for k, v in port.extras.get("episode", {}).items():
+        d["extras_" + k] = v
+    return {k: (v.detach().clone() if torch.is_tensor(v) else torch.as_tensor(v)) for k, v in d.items()}
+
+
+def snapshot_fused(env):
+    d = dict(obs=env.obs_buf, rew=env.rew_buf, reset=env.reset_buf, time_out=env.time_out_buf, torques=env.torques,
+             commands=env.commands, ep_len=env.episode_length_buf, feet_air_time=env.feet_air_time,
+             last_contacts=env.last_contacts, root=env.root_states, dof=env.dof_state, last_actions=env.last_actions,
+             last_dof_vel=env.last_dof_vel, last_root_vel=env.last_root_vel, base_lin_vel=env.base_lin_vel,
+             base_ang_vel=env.base_ang_vel, projected_gravity=env.projected_gravity)
+    for k, v in env.episode_sums.items():
+        d["sum_" + k] = v
+    if env.params.measure_heights:
+        d["heights"] = env.measured_heights
+    if env.params.terrain_curriculum:
+        d["terrain_levels"] = env.terrain_levels
+        d["env_origins"] = env.env_origins
+    if env.params.use_actuator_network:
+        d["lstm_h"], d["lstm_c"] = env.sea_hidden_state, env.sea_cell_state
+    for k, v in env.extras["episode"].items():
+        d["extras_" + k] = v
+    return {k: v.detach().cpu().clone() for k, v in d.items()}
+
+
+EXACT = {"reset", "time_out", "ep_len", "last_contacts", "terrain_levels"}
+SCALES = {"torques": 80.0, "heights": 1.0}
+
+
+def compare_snapshots(got, want, tag=""):
+    """Bit-exact for flags / counters / indices; |a-b| <= 1e-5*(|b| + S) otherwise (S=80 for torques, else 1).
+    Height cells are index work: compared exactly up to the (stated) vertical quantum."""
+    from oracle.compare import assert_close, assert_exact
+    worst = {}
+    for k, w in want.items():
+        if k not in got:
+            raise AssertionError(f"{tag}: fused path has no `{k}`")
+        g = got[k]
+        if k in EXACT:
+            assert_exact(g.to(w.dtype) if g.dtype != w.dtype else g, w, f"{tag}{k}")
+        elif k.startswith("extras_"):
+            # extras only change on steps with a reset; the port keeps stale values too
+            worst[k] = assert_close(g, w, 1.0, f"{tag}{k}")
+        else:
+            worst[k] = assert_close(g, w.to(g.dtype), SCALES.get(k, 1.0), f"{tag}{k}")
+    return worst

@@ -1,0 +1,99 @@
+"""Group R parity on the GPU: fused CUDA step pipeline (through the C ABI) vs the CPU oracle port.
+
+Same seeded inputs, same counter-based random numbers; compared after EVERY step so that stateful
+quantities (feet_air_time, LSTM h/c, episode sums, in-kernel resets) are checked along a trajectory.
+Tolerances: oracle/compare.py (bit-exact flags/indices; 1e-5 relative with stated scale otherwise)."""
+import pytest
+import torch
+
+import legged_case as LC
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(name, num_envs, steps, frames=8, big_action_step=3):
+    case = LC.build_case(name, num_envs, frames=frames)
+    port, phys = LC.make_port(case)
+    env = LC.make_fused(case)
+    worst = {}
+    resets = 0
+    for s in range(steps):
+        a = case.tape.actions[s % frames] * (150.0 if s == big_action_step else 1.0)   # exercises the action clip
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        w = LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} step {s}: ")
+        resets += int(port.reset_buf.sum())
+        for k, v in w.items():
+            worst[k] = max(worst.get(k, 0.0), v)
+    return worst, resets
+
+
+@pytest.mark.parametrize("name", list(LC.CASES))
+def test_step_parity_small(name):
+    worst, resets = _run(name, 256, 30)
+    assert resets > 0, "case never exercised the reset path"
+    print(name, "resets", resets, {k: f"{v:.1e}" for k, v in worst.items() if v > 0})
+
+
+@pytest.mark.parametrize("num_envs", [4, 60, 68, 1000])
+def test_ragged_sizes(num_envs):
+    """Tail tiles (num_envs not a multiple of the 64-env tile) take the non-TMA path."""
+    _run("flat_allterms_v", num_envs, 12)
+    _run("rough_lstm_allterms", num_envs, 6)
+
+
+def test_cfg2_size_4096():
+    """BASELINE config 2 size: anymal_c_flat, 4096 envs."""
+    worst, resets = _run("flat_pd_upstream", 4096, 12)
+    assert resets > 0
+
+
+def test_long_trajectory_timeouts():
+    """Episode counters start near the limit so time-outs (1001st step, legged_robot.py:144) fire."""
+    case = LC.build_case("flat_pd_upstream", 512, base_contact_prob=0.0)
+    case.ep[:] = torch.randint(990, 1001, (512,), generator=torch.Generator().manual_seed(3))
+    port, phys = LC.make_port(case)
+    env = LC.make_fused(case)
+    touts = 0
+    for s in range(16):
+        a = case.tape.actions[s % 8]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"timeouts step {s}: ")
+        touts += int(port.time_out_buf.sum())
+    assert touts > 0
+
+
+def test_shard_invariance():
+    """H6: per-env results do not depend on how envs are split over ranks (RNG keyed by global env id)."""
+    N = 512
+    case = LC.build_case("flat_pd_upstream", N)
+    env = LC.make_fused(case)
+    half = N // 2
+    shard = LC.build_case("flat_pd_upstream", half)
+    for k in ("root", "dof", "contact", "actions"):
+        t = getattr(case.tape, k)
+        if k == "dof":
+            setattr(shard.tape, k, t.view(t.shape[0], t.shape[1], N, 12, 2)[:, :, half:].reshape(t.shape[0], t.shape[1], half * 12, 2).contiguous())
+        else:
+            setattr(shard.tape, k, t[:, half:].contiguous())
+    shard.ep = case.ep[half:].clone()
+    env2 = LC.make_fused(shard, env_id_offset=half)
+    for s in range(10):
+        env.step(case.tape.actions[s % 8].cuda())
+        env2.step(shard.tape.actions[s % 8].cuda())
+        assert torch.equal(env.obs_buf[half:], env2.obs_buf)
+        assert torch.equal(env.rew_buf[half:], env2.rew_buf)
+        assert torch.equal(env.reset_buf[half:], env2.reset_buf)
+        assert torch.equal(env.commands[half:], env2.commands)
+
+
+def test_errors_are_loud():
+    from legged_gym_dev_b200 import _lib
+    case = LC.build_case("flat_pd_upstream", 64)
+    env = LC.make_fused(case)
+    with pytest.raises(RuntimeError):
+        env.step(torch.zeros(64, 12))          # CPU tensor: no fallback
+    env._pod.control_type = 7
+    with pytest.raises(RuntimeError, match="Unknown controller type"):
+        env.step(torch.zeros(64, 12, device="cuda"))

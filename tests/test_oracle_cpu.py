@@ -1,0 +1,131 @@
+"""CPU-side pinning of the oracle (runs without a GPU):
+  * Philox known-answer vectors (Random123 distribution),
+  * restated isaacgym.torch_utils vs scipy rotations,
+  * the oracle port vs the UNMODIFIED reference, step for step (only where /root/reference exists),
+  * the C-ABI library loads and exports every symbol include/b200gym.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import legged_case as LC
+from oracle import philox
+from oracle.compare import assert_close, assert_exact
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_philox_known_answers():
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, want in kat:
+        got = tuple(int(x) for x in philox.philox4x32(*c, *k))
+        assert got == want
+
+
+def test_philox_uniform_range_and_columns():
+    u = philox.uniform01(7, np.arange(1000), 3, philox.SITE_OBS_NOISE, 48)
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 0.01
+    # column j is independent of how many columns are requested
+    assert np.array_equal(u[:, :5], philox.uniform01(7, np.arange(1000), 3, philox.SITE_OBS_NOISE, 5))
+    r = philox.randint(7, np.arange(1000), 3, philox.SITE_TERRAIN, 1, 10)
+    assert r.min() >= 0 and r.max() <= 9
+
+
+def test_restated_quaternion_math_against_scipy():
+    from scipy.spatial.transform import Rotation
+    from oracle.isaacgym_restated import quat_apply, quat_rotate_inverse
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(200, 4, generator=g, dtype=torch.float64)
+    q = q / q.norm(dim=-1, keepdim=True)
+    v = torch.randn(200, 3, generator=g, dtype=torch.float64)
+    R = Rotation.from_quat(q.numpy())
+    assert np.allclose(quat_apply(q, v).numpy(), R.apply(v.numpy()), atol=1e-12)
+    assert np.allclose(quat_rotate_inverse(q, v).numpy(), R.inv().apply(v.numpy()), atol=1e-12)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200gym.h")).read()
+    names = set(re.findall(r"\b(b200gym_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 7
+    from legged_gym_dev_b200 import _lib
+    L = _lib.lib()                       # also checks struct sizes against the binding
+    for n in names:
+        assert hasattr(L, n), f"libb200gym.so does not export {n}"
+    assert L.b200gym_version() == 100
+
+
+def test_cfg_tables_match_reference_objects():
+    pytest.importorskip("torch")
+    if not os.path.isdir("/root/reference/legged_gym"):
+        pytest.skip("/root/reference not present")
+    import dataclasses
+    from oracle import ref_harness as H
+    from legged_gym_dev_b200 import configs, synthetic as S
+    from legged_gym_dev_b200.params import flatten_legged_cfg
+    ref = H.import_reference()
+    for mine, theirs in ((configs.anymal_c_flat_cfg(), ref.envs.AnymalCFlatCfg()),
+                         (configs.anymal_c_rough_cfg(), ref.envs.AnymalCRoughCfg())):
+        theirs.curriculum.use_curriculum = False
+        theirs.domain_rand.max_push_vel = 1.0
+        a = dataclasses.asdict(flatten_legged_cfg(theirs, 0.005, S.DOF_NAMES, terrain_rows=9, terrain_cols=9))
+        b = dataclasses.asdict(flatten_legged_cfg(mine, 0.005, S.DOF_NAMES, terrain_rows=9, terrain_cols=9))
+        assert a == b
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("name", ["flat_pd_upstream", "flat_lstm_shipped", "flat_allterms_v", "flat_heading_nonoise",
+                                  "rough_lstm_allterms", "rough_pd_shipped"])
+def test_port_tracks_unmodified_reference(name):
+    """The travelling restatement vs the reference's own code, every step, same Philox stream."""
+    from oracle import ref_harness as H
+    N, steps = 128, 24
+    case = LC.build_case(name, N)
+    task, rs, cr, lstm, over = LC.CASES[name]
+    env = H.make_reference_anymal(task, N, case.tape, seed=case.seed, reward_scales=rs, command_ranges=cr,
+                                  use_actuator_network=lstm,
+                                  heightfield=case.terrain["height_samples"] if case.rough else None,
+                                  terrain_origins=case.terrain["terrain_origins"] if case.rough else None,
+                                  episode_lengths=case.ep, overrides=over)
+    if case.rough:
+        env.terrain_levels[:] = case.terrain["terrain_levels"]
+        env.terrain_types[:] = case.terrain["terrain_types"]
+        env.env_origins[:] = case.terrain["env_origins"]
+    port, phys = LC.make_port(case)
+    resets = 0
+    for s in range(steps):
+        a = case.tape.actions[s % case.tape.frames] * (150.0 if s == 3 else 1.0)
+        o1, _, r1, d1, x1 = env.step(a.clone())
+        o2, _, r2, d2, x2 = port.step(a.clone(), phys)
+        resets += int(d1.sum())
+        tag = f"{name} step {s}: "
+        assert_exact(d2, d1, tag + "reset")
+        assert_exact(port.time_out_buf, env.time_out_buf, tag + "time_out")
+        assert_exact(port.episode_length_buf, env.episode_length_buf, tag + "ep_len")
+        assert_exact(port.last_contacts, env.last_contacts, tag + "last_contacts")
+        assert_close(o2, o1, 1.0, tag + "obs")
+        assert_close(r2, r1, 1.0, tag + "rew")
+        assert_close(port.torques, env.torques, 80.0, tag + "torques")
+        assert_close(port.commands, env.commands, 1.0, tag + "commands")
+        assert_close(port.root_states, env.root_states, 1.0, tag + "root")
+        assert_close(port.dof_state, env.dof_state, 1.0, tag + "dof")
+        assert_close(port.feet_air_time, env.feet_air_time, 1.0, tag + "feet_air_time")
+        for k in env.episode_sums:
+            assert_close(port.episode_sums[k], env.episode_sums[k], 1.0, tag + "sum_" + k)
+        if "episode" in x1:
+            assert list(x1["episode"]) == list(x2["episode"])
+            for k in x1["episode"]:
+                assert_close(x2["episode"][k], x1["episode"][k], 1.0, tag + "extras " + k)
+        if case.rough:
+            assert_exact(port.measured_heights, env.measured_heights, tag + "heights")
+            assert_exact(port.terrain_levels, env.terrain_levels, tag + "levels")
+        if lstm:
+            assert_close(port.sea_hidden_state, env.sea_hidden_state, 1.0, tag + "h")
+            assert_close(port.sea_cell_state, env.sea_cell_state, 1.0, tag + "c")
+    assert resets > 0
