@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Throughput bench of the fused step pipeline (contract: see the task statement / DESIGN.md §Measurement).
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): anymal_c_flat env step —
+4 x PD torques + the fused post-physics pass — upstream reward table (SURVEY.md §8d cfg 2b), on a replayed
+synthetic state tape, `--envs` environments per GPU (default 131072 = 1M envs on 8 GPUs).  One "step" = one
+`env.step(actions)` for every env.  `value` = env-steps/s with the tape resident in HBM; `e2e` = the same
+step driven through the public API from PINNED HOST buffers (H2D of the step's physics state + actions, D2H
+of obs/rew/reset inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl b200|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+METRIC = "env-steps/s of step pipeline (anymal_c_flat: 4x PD torques + fused post_physics_step)"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--envs", type=int, default=131072, help="environments per GPU")
+    ap.add_argument("--frames", type=int, default=8, help="frames of the replay tape")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-envs", type=int, default=16384, help="envs of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also report 4096..1M envs (extra keys, not the headline)")
+    return ap.parse_args()
+
+
+def workload_cfg(num_envs):
+    from legged_gym_dev_b200 import configs
+    cfg = configs.with_upstream_rewards(configs.anymal_c_flat_cfg(), pd_control=True)
+    cfg.env.num_envs = num_envs
+    return cfg
+
+
+def algorithmic_bytes(num_sum_rows, num_bodies=17):
+    """every API-visible tensor counted once per read and once per write, per env."""
+    K = num_sum_rows
+    rd = 52 + 96 + 12 * num_bodies + 48 + 48 + 48 + 48 + 16 + 16 + 4 + 8 + 4 * K
+    wr = 36 + 16 + 16 + 4 + 8 + 2 + 4 + 4 * K + 192 + 48 + 48 + 24
+    post = rd + wr
+    pd = 48 + 96 + 48
+    return dict(post_physics=post, pd_torques=pd, step=96 + 4 * pd + post)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def build_env(num_envs, frames, device, rank, copy=False, host=False):
+    from types import SimpleNamespace
+    from legged_gym_dev_b200 import synthetic as S
+    from legged_gym_dev_b200.legged_robot import Anymal
+    from legged_gym_dev_b200.physics import ReplayPhysics, HostReplayPhysics
+    import legged_case as LC
+    cfg = workload_cfg(num_envs)
+    tape = S.make_state_tape(num_envs, frames=frames, seed=100 + rank, device="cpu" if host else device)
+    phys = HostReplayPhysics(tape, device=device) if host else ReplayPhysics(tape, device=device, copy=copy)
+    lim = LC.dof_limits()
+    env = Anymal(cfg, SimpleNamespace(dt=cfg.sim.dt), None, device, True, physics=phys, asset=lim, seed=0,
+                 env_id_offset=rank * num_envs)
+    env.episode_length_buf.copy_(S.make_episode_lengths(num_envs, seed=rank, device=device))
+    return env, tape
+
+
+def time_steps(env, actions, steps, warmup, world, device):
+    import torch.distributed as dist
+    F = len(actions)
+    for s in range(warmup):
+        env.step(actions[s % F])
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(steps):
+        env.step(actions[(warmup + s) % F])
+    t1.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def kernel_time(env, actions, steps, device):
+    """Average duration of the dominant kernel (post_physics) and of pd_torques, CUDA events on the launch stream."""
+    F = len(actions)
+    env._timing = []
+    for s in range(steps):
+        env.step(actions[s % F])
+    torch.cuda.synchronize(device)
+    pp = [a.elapsed_time(b) for (k, a, b) in env._timing if k == "post_physics"]
+    pd = [a.elapsed_time(b) for (k, a, b) in env._timing if k == "torques"]
+    env._timing = None
+    return sum(pp) / len(pp), sum(pd) / len(pd)
+
+
+def e2e_run(num_envs, frames, steps, warmup, device, rank, world):
+    """Public-API step with HOST-resident inputs: every sub-step's dof_state, the root/contact frame and the
+    actions come from pinned host memory; obs/rew/reset are read back to pinned host memory every step."""
+    import torch.distributed as dist
+    env, tape = build_env(num_envs, frames, device, rank, host=True)
+    acts = [tape.actions[f].pin_memory() for f in range(frames)]
+    obs_h = torch.empty(num_envs, env.num_obs, pin_memory=True)
+    rew_h = torch.empty(num_envs, pin_memory=True)
+    rst_h = torch.empty(num_envs, dtype=torch.bool, pin_memory=True)
+    a_dev = torch.empty(num_envs, 12, device=device)
+
+    def one(s):
+        a_dev.copy_(acts[s % frames], non_blocking=True)
+        obs, _, rew, rst, _ = env.step(a_dev)
+        obs_h.copy_(obs, non_blocking=True)
+        rew_h.copy_(rew, non_blocking=True)
+        rst_h.copy_(rst, non_blocking=True)
+
+    for s in range(warmup):
+        one(s)
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(steps):
+        one(warmup + s)
+    torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    h2d = num_envs * (4 * 96 + 52 + 204 + 48)
+    d2h = num_envs * (env.num_obs * 4 + 4 + 1)
+    return dt, h2d, d2h
+
+
+def cpu_baseline(num_envs, steps):
+    """The oracle port (reference's torch ops, torch.rand like the reference) on the host cores."""
+    import legged_case as LC
+    torch.set_num_threads(os.cpu_count() or 1)
+    case = LC.build_case("flat_pd_upstream", num_envs, frames=4, base_contact_prob=0.002)
+    port, phys = LC.make_port(case, rng="torch")
+    for s in range(3):
+        port.step(case.tape.actions[s % 4], phys)
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps:
+        port.step(case.tape.actions[n % 4], phys)
+        n += 1
+        if time.perf_counter() - t0 > 30.0:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=num_envs * n / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"oracle/port_legged.py (torch CPU restatement of the reference), anymal_c_flat PD + upstream rewards, "
+                       f"{num_envs} envs x {n} steps, {dt:.2f} s", ms_per_step=1e3 * dt / n)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_baseline(args.cpu_envs, max(args.steps, 1) if args.steps < 100 else args.cpu_steps)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"anymal_c_flat env.step (4x PD torques + post_physics_step), upstream reward table, "
+                                       f"replayed synthetic state; reference's torch CPU path on a bounded sample of {args.cpu_envs} envs"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the b200gym path has no CPU fallback)")
+    import torch.distributed as dist
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from legged_gym_dev_b200 import _lib
+    _lib.lib()
+
+    N = args.envs
+    env, tape = build_env(N, args.frames, device, rank)
+    actions = [tape.actions[f].to(device) for f in range(args.frames)]
+    with ClockSampler(local_rank) as clk:
+        ms = time_steps(env, actions, args.steps, args.warmup, world, device)
+    t_pp, t_pd = kernel_time(env, actions, min(args.steps, 50), device)
+    value = world * N * args.steps / (ms * 1e-3)
+    ab = algorithmic_bytes(len(env.params.active_terms))
+    peak, peak_src = measured_peak()
+    ach = ab["post_physics"] * N / (t_pp * 1e-3) / 1e9
+    ach_pd = ab["pd_torques"] * N / (t_pd * 1e-3) / 1e9
+
+    e2e = None
+    if not args.no_e2e:
+        del env
+        torch.cuda.empty_cache()
+        esteps = max(5, min(args.steps, 30))
+        dt, h2d, d2h = e2e_run(N, min(args.frames, 4), esteps, 3, device, rank, world)
+        e2e = {"value": world * N * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": esteps, "note": "LeggedRobot.step through the C ABI with pinned-host physics frames + actions in, obs/rew/reset out"}
+
+    sweep = None
+    if args.sweep and world == 1:
+        sweep = {}
+        for n in (4096, 16384, 65536, 262144, 1048576):
+            e2, tp2 = build_env(n, 4, device, 0)
+            a2 = [tp2.actions[f].to(device) for f in range(4)]
+            m2 = time_steps(e2, a2, 100, 10, 1, device)
+            sweep[str(n)] = n * 100 / (m2 * 1e-3)
+            del e2, tp2, a2
+            torch.cuda.empty_cache()
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(args.cpu_envs, args.cpu_steps)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"anymal_c_flat env.step (4x PD torques + fused post_physics_step), upstream reward table "
+                                       f"(SURVEY 8d cfg 2b), {N} envs/GPU, {args.frames}-frame replay tape resident in HBM",
+                           "envs_per_gpu": N, "total_envs": world * N, "parallelism": f"env-sharded x{world}, no data-path collective",
+                           "cache": f"inputs larger than L2: {ab['step'] * N / 1e6:.0f} MB touched per step, tape cycles {args.frames} frames"},
+                "gpu_launches": args.steps * (env_launches()),
+                "roofline": {"bound": "hbm", "kernel": "post_physics_kernel<64,false>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                             "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_env": ab["post_physics"], "avg_launch_ms": t_pp,
+                             "pd_torques": {"achieved": ach_pd, "frac": ach_pd / peak, "avg_launch_ms": t_pd,
+                                            "algorithmic_bytes_per_env": ab["pd_torques"]},
+                             "step_frac": ab["step"] * N * args.steps / (ms * 1e-3) / 1e9 / peak},
+                "clocks": clk.summary()}
+        if e2e:
+            line["e2e"] = e2e
+        if cb:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if sweep:
+            line["sweep_env_steps_per_s"] = sweep
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def env_launches():
+    return 5   # 4 torque launches + 1 fused post-physics launch per env step
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,702 @@
+// post_physics_kernel — LeggedRobot.post_physics_step (legged_robot.py:106-134) and everything it calls,
+// plus the observation clip of step() (:100-101), as ONE pass over per-env state.
+//
+// Data movement.  Every API-visible tensor keeps the reference's row-major [N, k] layout (plain contiguous
+// torch tensors; PhysX-owned buffers consumed as given).  A CTA owns a tile of TILE consecutive envs, whose
+// rows form ONE contiguous byte range per tensor; each range moves HBM<->shared memory as a 1-D TMA bulk
+// copy (cp.async.bulk, SASS UBLKCP), issued by one thread and tracked by an mbarrier.  No thread ever
+// computes a global address for the streaming data, and every DRAM sector is touched exactly once.
+//
+// Work mapping (chosen from the ncu profile of the first version, profiles/r1_post_physics_v1.md: the kernel
+// was issue-bound because four lanes each repeated the per-env scalar work):
+//   phase H  (rough only) one warp per env: 187-point height scan           legged_robot.py:877-915
+//   phase W  4 lanes per env: per-DOF / per-foot / per-body terms, the DOF observation columns and all
+//            Philox noise draws; 2-step shuffle reductions leave per-env partial sums in shared memory
+//   phase S  1 thread per env: body-frame vectors, commands, termination, reward assembly, in-place reset,
+//            first 12 observation columns — scalar work executed exactly once per env
+//   phase H2 (rough only) one warp per env: height observations + noise    legged_robot.py:220-226
+#include "common.cuh"
+#include "philox.cuh"
+#include "../../include/b200gym.h"
+
+namespace {
+
+constexpr int LPE = 4;     // lanes per env in phase W
+constexpr int ND = B200GYM_NUM_DOF;
+constexpr int HPAD = 192;  // padded per-env stride of the raw height tile (>= 187)
+
+enum Term {
+    T_ACTION_RATE = 0, T_ANG_VEL_XY, T_BASE_HEIGHT, T_COLLISION, T_DOF_ACC, T_DOF_POS_LIMITS, T_DOF_VEL,
+    T_DOF_VEL_LIMITS, T_FEET_AIR_TIME, T_FEET_CONTACT_FORCES, T_LIN_VEL_Z, T_ORIENTATION, T_STAND_STILL,
+    T_STUMBLE, T_TORQUE_LIMITS, T_TORQUES, T_TRACKING_ANG_VEL, T_TRACKING_LIN_VEL, T_TERMINATION
+};
+// per-env partial sums handed from phase W to phase S
+enum Part { P_ACTION_RATE = 0, P_DOF_ACC, P_DOF_VEL, P_TORQUES, P_POS_LIM, P_VEL_LIM, P_TQ_LIM, P_STAND, P_AIR, P_STUMBLE, P_FCF,
+            P_COLL, P_TERM, NUM_PARTS };
+
+__device__ __forceinline__ void quat_rotate_inverse(float qx, float qy, float qz, float qw, float vx, float vy, float vz,
+                                                    float& rx, float& ry, float& rz) {
+    // isaacgym.torch_utils.quat_rotate_inverse: a = v*(2w^2-1); b = cross(q,v)*w*2; c = q*dot(q,v)*2; a - b + c
+    const float s = 2.0f * qw * qw - 1.0f;
+    const float cx = qy * vz - qz * vy, cy = qz * vx - qx * vz, cz = qx * vy - qy * vx;
+    const float dt2 = (qx * vx + qy * vy + qz * vz) * 2.0f, w2 = qw * 2.0f;
+    rx = vx * s - cx * w2 + qx * dt2;
+    ry = vy * s - cy * w2 + qy * dt2;
+    rz = vz * s - cz * w2 + qz * dt2;
+}
+
+// norms that feed a threshold compare keep torch's un-fused rounding
+__device__ __forceinline__ float norm2_rn(float x, float y) { return sqrtf(add_rn(mul_rn(x, x), mul_rn(y, y))); }
+__device__ __forceinline__ float norm3_rn(float x, float y, float z) {
+    return sqrtf(add_rn(add_rn(mul_rn(x, x), mul_rn(y, y)), mul_rn(z, z)));
+}
+
+__device__ __forceinline__ float wrap_to_pi(float a) {
+    // legged_gym/utils/math.py:45-48 on fp32 tensors: python-style remainder by fl32(2*pi), then -2*pi where > fl32(pi)
+    const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
+    float r = fmodf(a, two_pi);
+    if (r < 0.0f) r = add_rn(r, two_pi);
+    if (r > pi) r = sub_rn(r, two_pi);
+    return r;
+}
+
+__device__ __forceinline__ void resample_commands(const B200LeggedParams& p, const philox::Stream& rng, uint32_t site, float& c0,
+                                                  float& c1, float& c2, float& c3) {
+    // legged_robot.py:365-387
+    const uint4 w = rng.words(site, 0);
+    c0 = affine_rn(p.cmd_span[0], philox::u01(w.x), p.cmd_lo[0]);
+    c1 = affine_rn(p.cmd_span[1], philox::u01(w.y), p.cmd_lo[1]);
+    if (p.heading_command)
+        c3 = affine_rn(p.cmd_span[3], philox::u01(w.z), p.cmd_lo[3]);
+    else
+        c2 = affine_rn(p.cmd_span[2], philox::u01(w.z), p.cmd_lo[2]);
+    const float m = norm2_rn(c0, c1) > 0.2f ? 1.0f : 0.0f;
+    c0 *= m;
+    c1 *= m;
+}
+
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// noise term of legged_robot.py:226: (2u - 1) * scale, added to the observation
+__device__ __forceinline__ float add_noise(float v, float u, float scale) { return fmaf(fmaf(2.0f, u, -1.0f), scale, v); }
+
+struct Carver {
+    unsigned char* base;
+    size_t off;
+    template <typename T>
+    __device__ __host__ T* take(size_t n) {
+        T* r = reinterpret_cast<T*>(base + off);
+        off += (n * sizeof(T) + 15) & ~static_cast<size_t>(15);
+        return r;
+    }
+};
+
+struct TileSmem {
+    uint64_t* bar;
+    float *root, *dof, *contact, *act, *tq, *lact, *ldv, *cmd, *fat;
+    uint8_t* lc;
+    long long* ep;
+    float *sums, *obs, *blv, *bav, *pg, *lrv, *rew, *part;
+    uint8_t *reset, *tout;
+    int16_t* hraw;
+    float *bh, *zpost, *stage;
+    double* acc;
+    int* nreset;
+    size_t bytes;
+};
+
+template <int TILE, bool ROUGH>
+__device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K) {
+    Carver c{base, 0};
+    TileSmem s;
+    s.bar = c.take<uint64_t>(2);
+    s.root = c.take<float>(TILE * 13);
+    s.dof = c.take<float>(TILE * 24);
+    s.contact = c.take<float>(static_cast<size_t>(TILE) * B * 3);
+    s.act = c.take<float>(TILE * ND);
+    s.tq = c.take<float>(TILE * ND);
+    s.lact = c.take<float>(TILE * ND);
+    s.ldv = c.take<float>(TILE * ND);
+    s.cmd = c.take<float>(TILE * 4);
+    s.fat = c.take<float>(TILE * 4);
+    s.lc = c.take<uint8_t>(TILE * 4);
+    s.ep = c.take<long long>(TILE);
+    s.sums = c.take<float>(static_cast<size_t>(K > 0 ? K : 1) * TILE);
+    s.obs = c.take<float>(TILE * 48);
+    s.blv = c.take<float>(TILE * 3);
+    s.bav = c.take<float>(TILE * 3);
+    s.pg = c.take<float>(TILE * 3);
+    s.lrv = c.take<float>(TILE * 6);
+    s.rew = c.take<float>(TILE);
+    s.part = c.take<float>(NUM_PARTS * TILE);
+    s.reset = c.take<uint8_t>(TILE);
+    s.tout = c.take<uint8_t>(TILE);
+    s.acc = c.take<double>(B200GYM_NUM_REWARD_TERMS + 2);
+    s.nreset = c.take<int>(4);
+    if (ROUGH) {
+        s.hraw = c.take<int16_t>(TILE * HPAD);
+        s.bh = c.take<float>(TILE);
+        s.zpost = c.take<float>(TILE);
+        s.stage = c.take<float>((TILE * LPE / 32) * HPAD);
+    } else {
+        s.hraw = nullptr;
+        s.bh = s.zpost = s.stage = nullptr;
+    }
+    s.bytes = c.off;
+    return s;
+}
+
+template <typename T>
+__device__ __forceinline__ void coop_copy(T* dst, const T* src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+template <int TILE, bool ROUGH>
+__global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_constant__ B200LeggedParams p,
+                                                                 const __grid_constant__ B200LeggedBuffers b, uint64_t step,
+                                                                 long long env_off, int do_push) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int B = p.num_bodies, K = p.num_sum_rows, N = p.num_envs, O = p.num_obs;
+    const TileSmem s = carve_tile<TILE, ROUGH>(smem_raw, B, K);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile0 = blockIdx.x * TILE;
+    const int nvalid = min(TILE, N - tile0);
+    const bool full = (nvalid == TILE);
+    const float* rs = p.reward_scale;
+
+    if (tid == 0) {
+        mbar_init(s.bar, 1);
+        fence_mbar_init();
+        *s.nreset = 0;
+    }
+    if (tid < B200GYM_NUM_REWARD_TERMS + 2) s.acc[tid] = 0.0;
+    __syncthreads();
+
+    // ---- stage the tile: one bulk copy per tensor -------------------------------------------------
+    if (full) {
+        if (tid == 0) {
+            const uint32_t bytes = TILE * (13 + 24 + 3 * B + 4 * ND + 4 + 4) * 4 + TILE * 4 + TILE * 8 + K * TILE * 4;
+            mbar_expect_tx(s.bar, bytes);
+            bulk_g2s(s.root, b.root_states + static_cast<size_t>(tile0) * 13, TILE * 13 * 4, s.bar);
+            bulk_g2s(s.dof, b.dof_state + static_cast<size_t>(tile0) * 24, TILE * 24 * 4, s.bar);
+            bulk_g2s(s.contact, b.contact_forces + static_cast<size_t>(tile0) * B * 3, TILE * B * 3 * 4, s.bar);
+            bulk_g2s(s.act, b.actions + static_cast<size_t>(tile0) * ND, TILE * ND * 4, s.bar);
+            bulk_g2s(s.tq, b.torques + static_cast<size_t>(tile0) * ND, TILE * ND * 4, s.bar);
+            bulk_g2s(s.lact, b.last_actions + static_cast<size_t>(tile0) * ND, TILE * ND * 4, s.bar);
+            bulk_g2s(s.ldv, b.last_dof_vel + static_cast<size_t>(tile0) * ND, TILE * ND * 4, s.bar);
+            bulk_g2s(s.cmd, b.commands + static_cast<size_t>(tile0) * 4, TILE * 4 * 4, s.bar);
+            bulk_g2s(s.fat, b.feet_air_time + static_cast<size_t>(tile0) * 4, TILE * 4 * 4, s.bar);
+            bulk_g2s(s.lc, b.last_contacts + static_cast<size_t>(tile0) * 4, TILE * 4, s.bar);
+            bulk_g2s(s.ep, b.episode_length_buf + tile0, TILE * 8, s.bar);
+            for (int k = 0; k < K; ++k)
+                bulk_g2s(s.sums + k * TILE, b.episode_sums + static_cast<size_t>(k) * N + tile0, TILE * 4, s.bar);
+        }
+        mbar_wait(s.bar, 0);
+    } else {
+        coop_copy(s.root, b.root_states + static_cast<size_t>(tile0) * 13, nvalid * 13);
+        coop_copy(s.dof, b.dof_state + static_cast<size_t>(tile0) * 24, nvalid * 24);
+        coop_copy(s.contact, b.contact_forces + static_cast<size_t>(tile0) * B * 3, nvalid * B * 3);
+        coop_copy(s.act, b.actions + static_cast<size_t>(tile0) * ND, nvalid * ND);
+        coop_copy(s.tq, b.torques + static_cast<size_t>(tile0) * ND, nvalid * ND);
+        coop_copy(s.lact, b.last_actions + static_cast<size_t>(tile0) * ND, nvalid * ND);
+        coop_copy(s.ldv, b.last_dof_vel + static_cast<size_t>(tile0) * ND, nvalid * ND);
+        coop_copy(s.cmd, b.commands + static_cast<size_t>(tile0) * 4, nvalid * 4);
+        coop_copy(s.fat, b.feet_air_time + static_cast<size_t>(tile0) * 4, nvalid * 4);
+        coop_copy(s.lc, b.last_contacts + static_cast<size_t>(tile0) * 4, nvalid * 4);
+        coop_copy(s.ep, reinterpret_cast<const long long*>(b.episode_length_buf) + tile0, nvalid);
+        for (int k = 0; k < K; ++k) coop_copy(s.sums + k * TILE, b.episode_sums + static_cast<size_t>(k) * N + tile0, nvalid);
+        __syncthreads();
+    }
+
+    // ---- phase H: height scan, one warp per env (legged_robot.py:877-915, math.py:38-42) ----------
+    if (ROUGH) {
+        const int H = p.num_heights;
+        const int rows = p.terrain_rows, cols = p.terrain_cols;
+        for (int e = warp; e < nvalid; e += TILE * LPE / 32) {
+            const float* R = s.root + e * 13;
+            // quat_apply_yaw: zero x,y, renormalise, rotate — un-fused fp32 ops, the cell index depends on them (H2)
+            const float nq = fmaxf(sqrtf(add_rn(mul_rn(R[5], R[5]), mul_rn(R[6], R[6]))), 1e-9f);
+            const float qz = div_rn(R[5], nq), qw = div_rn(R[6], nq);
+            float part = 0.0f;
+            for (int pt = lane; pt < H; pt += 32) {
+                int raw = 0;
+                if (!p.mesh_plane) {
+                    const float hx = p.points_x[pt / p.n_py], hy = p.points_y[pt % p.n_py];
+                    const float tx = mul_rn(-mul_rn(qz, hy), 2.0f), ty = mul_rn(mul_rn(qz, hx), 2.0f);
+                    float wx = add_rn(add_rn(hx, mul_rn(qw, tx)), -mul_rn(qz, ty));
+                    float wy = add_rn(add_rn(hy, mul_rn(qw, ty)), mul_rn(qz, tx));
+                    wx = div_rn(add_rn(add_rn(wx, R[0]), p.border_size), p.horizontal_scale);
+                    wy = div_rn(add_rn(add_rn(wy, R[1]), p.border_size), p.horizontal_scale);
+                    long long ix = static_cast<long long>(wx), iy = static_cast<long long>(wy);
+                    ix = ix < 0 ? 0 : (ix > rows - 2 ? rows - 2 : ix);
+                    iy = iy < 0 ? 0 : (iy > cols - 2 ? cols - 2 : iy);
+                    const int16_t* hs = b.height_samples + ix * cols + iy;
+                    const int h1 = __ldg(hs), h2 = __ldg(hs + cols), h3 = __ldg(hs + 1);
+                    raw = min(min(h1, h2), h3);
+                }
+                s.hraw[e * HPAD + pt] = static_cast<int16_t>(raw);
+                const float mh = mul_rn(static_cast<float>(raw), p.vertical_scale);
+                b.measured_heights[static_cast<size_t>(tile0 + e) * H + pt] = mh;
+                part += R[2] - mh;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) s.bh[e] = part / static_cast<float>(H);
+        }
+    }
+
+    // ---- phase W: 4 lanes per env — per-DOF / per-foot / per-body work, DOF observations, all noise draws
+    {
+        const int e = tid >> 2, g = tid & 3;
+        const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
+        // uniforms for observation columns 0..35 = Philox blocks 0..8, exchanged through the obs tile
+        if (p.add_noise) {
+            float4* stage = reinterpret_cast<float4*>(s.obs + e * 48);
+            stage[g] = philox::u01(rng.words(philox::OBS_NOISE, g));
+            stage[g + 4] = philox::u01(rng.words(philox::OBS_NOISE, g + 4));
+            if (g == 0) stage[8] = philox::u01(rng.words(philox::OBS_NOISE, 8));
+        }
+        float pa_rate = 0.f, pd_acc = 0.f, pd_vel = 0.f, ptq = 0.f, ppos_lim = 0.f, pvel_lim = 0.f, ptq_lim = 0.f, pstand = 0.f;
+        float o_pos[3], o_vel[3], o_act[3];
+        const float inv_dt = 1.0f / p.dt;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int d = 3 * g + j;
+            const float a = s.act[e * ND + d], la = s.lact[e * ND + d], tq = s.tq[e * ND + d], ldv = s.ldv[e * ND + d];
+            const float2 qv = *reinterpret_cast<const float2*>(s.dof + e * 24 + 2 * d);
+            const float q = qv.x, qd = qv.y, q0 = p.default_dof_pos[d];
+            const float da = la - a, acc = (ldv - qd) * inv_dt;
+            pa_rate = fmaf(da, da, pa_rate);
+            pd_acc = fmaf(acc, acc, pd_acc);
+            pd_vel = fmaf(qd, qd, pd_vel);
+            ptq = fmaf(tq, tq, ptq);
+            if (rs[T_DOF_POS_LIMITS] != 0.f) ppos_lim += fmaxf(q - p.dof_pos_hi[d], 0.0f) - fminf(q - p.dof_pos_lo[d], 0.0f);
+            if (rs[T_DOF_VEL_LIMITS] != 0.f) pvel_lim += clampf(fabsf(qd) - p.dof_vel_limits[d] * p.soft_dof_vel_limit, 0.0f, 1.0f);
+            if (rs[T_TORQUE_LIMITS] != 0.f) ptq_lim += fmaxf(fabsf(tq) - p.torque_limits[d] * p.soft_torque_limit, 0.0f);
+            pstand += fabsf(q - q0);
+            o_pos[j] = (q - q0) * p.obs_dof_pos;
+            o_vel[j] = qd * p.obs_dof_vel;
+            o_act[j] = a;
+            s.ldv[e * ND + d] = qd;   // R12: last_dof_vel <- dof_vel (a reset env is fixed up in phase S)
+        }
+        // feet: lane g owns foot g (legged_robot.py:988-1015)
+        const float* Ff = s.contact + (e * B + p.feet_idx[g]) * 3;
+        const float fz = Ff[2];
+        float p_air = 0.f;
+        if (rs[T_FEET_AIR_TIME] != 0.0f) {   // the reference only mutates this state when the term is active
+            float fat = s.fat[e * 4 + g];
+            const bool contact = fz > 1.0f;
+            const bool filt = contact || (s.lc[e * 4 + g] != 0);
+            const bool first = (fat > 0.0f) && filt;
+            fat = add_rn(fat, p.dt);
+            p_air = first ? fat - 0.5f : 0.0f;
+            s.fat[e * 4 + g] = filt ? 0.0f : fat;
+            s.lc[e * 4 + g] = contact ? 1 : 0;
+        }
+        float p_stumble = 0.f, p_fcf = 0.f, p_coll = 0.f;
+        if (rs[T_STUMBLE] != 0.f) p_stumble = (norm2_rn(Ff[0], Ff[1]) > mul_rn(5.0f, fabsf(fz))) ? 1.0f : 0.0f;
+        if (rs[T_FEET_CONTACT_FORCES] != 0.f) p_fcf = fmaxf(norm3_rn(Ff[0], Ff[1], fz) - p.max_contact_force, 0.0f);
+        if (rs[T_COLLISION] != 0.f) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float* Fp = s.contact + (e * B + p.pen_idx[g + 4 * j]) * 3;
+                p_coll += (norm3_rn(Fp[0], Fp[1], Fp[2]) > 0.1f) ? 1.0f : 0.0f;
+            }
+        }
+        // R8 (contact part): lane t checks termination body t
+        float p_term = 0.f;
+        if (g < p.num_term) {
+            const float* F = s.contact + (e * B + p.term_idx[g]) * 3;
+            p_term = norm3_rn(F[0], F[1], F[2]) > 1.0f ? 1.0f : 0.0f;
+        }
+        // DOF observation columns 12..47 (+ noise), already clipped (legged_robot.py:100-101,208-226)
+        if (p.add_noise) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float u1 = s.obs[e * 48 + 12 + 3 * g + j], u2 = s.obs[e * 48 + 24 + 3 * g + j];
+                o_pos[j] = add_noise(o_pos[j], u1, p.noise_dof_pos);
+                o_vel[j] = add_noise(o_vel[j], u2, p.noise_dof_vel);
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            s.obs[e * 48 + 12 + 3 * g + j] = clampf(o_pos[j], -p.clip_obs, p.clip_obs);
+            s.obs[e * 48 + 24 + 3 * g + j] = clampf(o_vel[j], -p.clip_obs, p.clip_obs);
+            s.obs[e * 48 + 36 + 3 * g + j] = clampf(o_act[j], -p.clip_obs, p.clip_obs);
+        }
+        // quad reductions -> per-env partial sums
+        pa_rate = quad_sum(pa_rate), pd_acc = quad_sum(pd_acc), pd_vel = quad_sum(pd_vel), ptq = quad_sum(ptq);
+        pstand = quad_sum(pstand), p_air = quad_sum(p_air), p_coll = quad_sum(p_coll), p_term = quad_sum(p_term);
+        if (rs[T_DOF_POS_LIMITS] != 0.f) ppos_lim = quad_sum(ppos_lim);
+        if (rs[T_DOF_VEL_LIMITS] != 0.f) pvel_lim = quad_sum(pvel_lim);
+        if (rs[T_TORQUE_LIMITS] != 0.f) ptq_lim = quad_sum(ptq_lim);
+        if (rs[T_STUMBLE] != 0.f) p_stumble = quad_sum(p_stumble);
+        if (rs[T_FEET_CONTACT_FORCES] != 0.f) p_fcf = quad_sum(p_fcf);
+        float* P = s.part + e;
+        if (g == 0) {
+            P[P_ACTION_RATE * TILE] = pa_rate, P[P_DOF_ACC * TILE] = pd_acc, P[P_DOF_VEL * TILE] = pd_vel;
+            P[P_TORQUES * TILE] = ptq;
+        } else if (g == 1) {
+            P[P_POS_LIM * TILE] = ppos_lim, P[P_VEL_LIM * TILE] = pvel_lim, P[P_TQ_LIM * TILE] = ptq_lim;
+        } else if (g == 2) {
+            P[P_STAND * TILE] = pstand, P[P_AIR * TILE] = p_air, P[P_STUMBLE * TILE] = p_stumble;
+        } else {
+            P[P_FCF * TILE] = p_fcf, P[P_COLL * TILE] = p_coll, P[P_TERM * TILE] = p_term;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase S: one thread per env — everything that is scalar per env ---------------------------
+    if (tid < TILE) {
+        const int e = tid;
+        const bool valid = e < nvalid;
+        const size_t ge = static_cast<size_t>(tile0 + e);
+        const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
+        const float* R = s.root + e * 13;
+        const float* P = s.part + e;
+        const float qx = R[3], qy = R[4], qz = R[5], qw = R[6];
+
+        // R4: counters + body-frame vectors (legged_robot.py:114-121)
+        const long long ep = s.ep[e] + 1;
+        float blx, bly, blz, bax, bay, baz, pgx, pgy, pgz;
+        quat_rotate_inverse(qx, qy, qz, qw, R[7], R[8], R[9], blx, bly, blz);
+        quat_rotate_inverse(qx, qy, qz, qw, R[10], R[11], R[12], bax, bay, baz);
+        quat_rotate_inverse(qx, qy, qz, qw, 0.0f, 0.0f, -1.0f, pgx, pgy, pgz);
+
+        // R5: command resampling + heading (legged_robot.py:343-354)
+        const float4 cmd4 = *reinterpret_cast<const float4*>(s.cmd + e * 4);
+        float c0 = cmd4.x, c1 = cmd4.y, c2 = cmd4.z, c3 = cmd4.w;
+        if (static_cast<int>(ep) % p.resample_steps == 0) resample_commands(p, rng, philox::CMD_PERIODIC, c0, c1, c2, c3);
+        if (p.heading_command) {
+            // forward = quat_apply(q, [1,0,0]) (x,y only): t = 2*cross(q_xyz, [1,0,0]) = (0, 2qz, -2qy)
+            const float tyy = 2.0f * qz, tzz = -2.0f * qy;
+            const float fx = 1.0f + (qy * tzz - qz * tyy);
+            const float fy = qw * tyy + (-qx * tzz);
+            c2 = clampf(0.5f * wrap_to_pi(sub_rn(c3, atan2f(fy, fx))), -1.0f, 1.0f);
+        }
+
+        // R7: pushes (legged_robot.py:456-461)
+        float lrv[6] = {R[7], R[8], R[9], R[10], R[11], R[12]};
+        if (do_push) {
+            const uint4 w = rng.words(philox::PUSH, 0);
+            lrv[0] = affine_rn(p.push_span, philox::u01(w.x), p.push_lo);
+            lrv[1] = affine_rn(p.push_span, philox::u01(w.y), p.push_lo);
+        }
+
+        // R8: termination (legged_robot.py:139-145)
+        const bool time_out = static_cast<float>(ep) > p.max_episode_length;
+        const bool reset = (P[P_TERM * TILE] > 0.0f) | time_out;
+
+        // R9: reward assembly in the reference's (alphabetical) order (legged_robot.py:189-206)
+        const float cmd_norm = norm2_rn(c0, c1);
+        float rew = 0.0f;
+        float* sums = s.sums + e;
+        auto add_term = [&](int k, float val) {
+            const float r = val * rs[k];
+            rew += r;
+            sums[p.sum_row[k] * TILE] += r;
+        };
+        if (rs[T_ACTION_RATE] != 0.f) add_term(T_ACTION_RATE, P[P_ACTION_RATE * TILE]);
+        if (rs[T_ANG_VEL_XY] != 0.f) add_term(T_ANG_VEL_XY, bax * bax + bay * bay);
+        if (rs[T_BASE_HEIGHT] != 0.f) {
+            const float dh = (ROUGH ? s.bh[e] : R[2]) - p.base_height_target;
+            add_term(T_BASE_HEIGHT, dh * dh);
+        }
+        if (rs[T_COLLISION] != 0.f) add_term(T_COLLISION, P[P_COLL * TILE]);
+        if (rs[T_DOF_ACC] != 0.f) add_term(T_DOF_ACC, P[P_DOF_ACC * TILE]);
+        if (rs[T_DOF_POS_LIMITS] != 0.f) add_term(T_DOF_POS_LIMITS, P[P_POS_LIM * TILE]);
+        if (rs[T_DOF_VEL] != 0.f) add_term(T_DOF_VEL, P[P_DOF_VEL * TILE]);
+        if (rs[T_DOF_VEL_LIMITS] != 0.f) add_term(T_DOF_VEL_LIMITS, P[P_VEL_LIM * TILE]);
+        if (rs[T_FEET_AIR_TIME] != 0.f) add_term(T_FEET_AIR_TIME, P[P_AIR * TILE] * (cmd_norm > 0.1f ? 1.0f : 0.0f));
+        if (rs[T_FEET_CONTACT_FORCES] != 0.f) add_term(T_FEET_CONTACT_FORCES, P[P_FCF * TILE]);
+        if (rs[T_LIN_VEL_Z] != 0.f) add_term(T_LIN_VEL_Z, blz * blz);
+        if (rs[T_ORIENTATION] != 0.f) add_term(T_ORIENTATION, pgx * pgx + pgy * pgy);
+        if (rs[T_STAND_STILL] != 0.f) add_term(T_STAND_STILL, P[P_STAND * TILE] * (cmd_norm < 0.1f ? 1.0f : 0.0f));
+        if (rs[T_STUMBLE] != 0.f) add_term(T_STUMBLE, P[P_STUMBLE * TILE] > 0.0f ? 1.0f : 0.0f);
+        if (rs[T_TORQUE_LIMITS] != 0.f) add_term(T_TORQUE_LIMITS, P[P_TQ_LIM * TILE]);
+        if (rs[T_TORQUES] != 0.f) add_term(T_TORQUES, P[P_TORQUES * TILE]);
+        const float inv_sigma = 1.0f / p.tracking_sigma;
+        if (rs[T_TRACKING_ANG_VEL] != 0.f) {
+            const float er = c2 - baz;
+            add_term(T_TRACKING_ANG_VEL, expf(-(er * er) * inv_sigma));
+        }
+        if (rs[T_TRACKING_LIN_VEL] != 0.f) {
+            const float ex = c0 - blx, ey = c1 - bly;
+            add_term(T_TRACKING_LIN_VEL, expf(-(ex * ex + ey * ey) * inv_sigma));
+        }
+        if (p.only_positive) rew = fmaxf(rew, 0.0f);
+        if (rs[T_TERMINATION] != 0.f) add_term(T_TERMINATION, (reset && !time_out) ? 1.0f : 0.0f);
+
+        // R10: in-place reset (legged_robot.py:147-187, anymal.py:56-60) — a branch, not a host compaction (H7)
+        float zpost = R[2];
+        long long ep_out = ep, level = 0;
+        if (p.terrain_curriculum && valid) level = b.terrain_levels[ge];
+        if (reset && valid) {
+            float ox = b.env_origins[ge * 3 + 0], oy = b.env_origins[ge * 3 + 1], oz = b.env_origins[ge * 3 + 2];
+            if (p.terrain_curriculum) {   // legged_robot.py:463-486
+                const float dist = norm2_rn(sub_rn(R[0], ox), sub_rn(R[1], oy));
+                const bool up = dist > p.half_env_length;
+                const bool down = (dist < mul_rn(mul_rn(cmd_norm, p.max_episode_length_s), 0.5f)) && !up;
+                level += (up ? 1 : 0) - (down ? 1 : 0);
+                if (level >= p.max_terrain_level)
+                    level = philox::bounded(rng.words(philox::TERRAIN, 0).x, static_cast<uint32_t>(p.max_terrain_level));
+                else if (level < 0)
+                    level = 0;
+                const float* og = b.terrain_origins + (level * p.terrain_num_cols + b.terrain_types[ge]) * 3;
+                ox = og[0], oy = og[1], oz = og[2];
+                b.terrain_levels[ge] = level;
+                b.env_origins[ge * 3 + 0] = ox, b.env_origins[ge * 3 + 1] = oy, b.env_origins[ge * 3 + 2] = oz;
+            }
+            // dofs: q = q0 * U(0.5, 1.5), qd = 0 (legged_robot.py:423-425); fix up what phase W assumed
+            for (int blk = 0; blk < 3; ++blk) {
+                const uint4 w = rng.words(philox::RESET_DOF, blk);
+                const uint4 n1 = rng.words(philox::OBS_NOISE, 3 + blk), n2 = rng.words(philox::OBS_NOISE, 6 + blk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int d = 4 * blk + i;
+                    const float q0 = p.default_dof_pos[d];
+                    const float q = mul_rn(q0, affine_rn(1.0f, philox::u01(philox::word(w, i)), 0.5f));
+                    reinterpret_cast<float2*>(b.dof_state)[ge * ND + d] = make_float2(q, 0.0f);
+                    float op = (q - q0) * p.obs_dof_pos, ov = 0.0f;
+                    if (p.add_noise) {
+                        op = add_noise(op, philox::u01(philox::word(n1, i)), p.noise_dof_pos);
+                        ov = add_noise(ov, philox::u01(philox::word(n2, i)), p.noise_dof_vel);
+                    }
+                    s.obs[e * 48 + 12 + d] = clampf(op, -p.clip_obs, p.clip_obs);
+                    s.obs[e * 48 + 24 + d] = clampf(ov, -p.clip_obs, p.clip_obs);
+                    s.ldv[e * ND + d] = 0.0f;
+                }
+            }
+            // root (legged_robot.py:441-449)
+            float nr[13];
+#pragma unroll
+            for (int k = 0; k < 13; ++k) nr[k] = p.base_init_state[k];
+            nr[0] = add_rn(nr[0], ox), nr[1] = add_rn(nr[1], oy), nr[2] = add_rn(nr[2], oz);
+            if (p.custom_origins) {
+                const uint4 w = rng.words(philox::RESET_XY, 0);
+                nr[0] = add_rn(nr[0], affine_rn(2.0f, philox::u01(w.x), -1.0f));
+                nr[1] = add_rn(nr[1], affine_rn(2.0f, philox::u01(w.y), -1.0f));
+            }
+            const uint4 w0 = rng.words(philox::RESET_VEL, 0), w1 = rng.words(philox::RESET_VEL, 1);
+            nr[7] = affine_rn(1.0f, philox::u01(w0.x), -0.5f), nr[8] = affine_rn(1.0f, philox::u01(w0.y), -0.5f);
+            nr[9] = affine_rn(1.0f, philox::u01(w0.z), -0.5f), nr[10] = affine_rn(1.0f, philox::u01(w0.w), -0.5f);
+            nr[11] = affine_rn(1.0f, philox::u01(w1.x), -0.5f), nr[12] = affine_rn(1.0f, philox::u01(w1.y), -0.5f);
+            zpost = nr[2];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) lrv[k] = nr[7 + k];
+#pragma unroll
+            for (int k = 0; k < 13; ++k) b.root_states[ge * 13 + k] = nr[k];
+            resample_commands(p, rng, philox::CMD_RESET, c0, c1, c2, c3);
+            *reinterpret_cast<float4*>(s.fat + e * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            ep_out = 0;
+            // extras["episode"] statistics (legged_robot.py:175-179): per-CTA partials in shared memory
+            for (int k = 0; k < K; ++k) {
+                atomicAdd(&s.acc[k], static_cast<double>(sums[k * TILE]));
+                sums[k * TILE] = 0.0f;
+            }
+            atomicAdd(s.nreset, 1);
+            if (p.zero_lstm_on_reset) {   // h,c: [2, N*12, 8]; this env owns 2 x 96 floats per array
+                const size_t M8 = static_cast<size_t>(N) * ND * 8;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int l = 0; l < 2; ++l) {
+                    float4* hp = reinterpret_cast<float4*>(b.lstm_h + l * M8 + ge * ND * 8);
+                    float4* cp = reinterpret_cast<float4*>(b.lstm_c + l * M8 + ge * ND * 8);
+                    for (int k = 0; k < 24; ++k) hp[k] = z4, cp[k] = z4;
+                }
+            }
+        } else if (do_push && valid) {
+            b.root_states[ge * 13 + 7] = lrv[0];
+            b.root_states[ge * 13 + 8] = lrv[1];
+        }
+        if (p.terrain_curriculum && valid) atomicAdd(&s.acc[K], static_cast<double>(level));
+
+        // R11: first 12 observation columns (+ noise, clip); uniforms were staged by phase W
+        float o[12] = {blx * p.obs_lin_vel, bly * p.obs_lin_vel, blz * p.obs_lin_vel, bax * p.obs_ang_vel, bay * p.obs_ang_vel,
+                       baz * p.obs_ang_vel, pgx, pgy, pgz, c0 * p.obs_lin_vel, c1 * p.obs_lin_vel, c2 * p.obs_ang_vel};
+        float4* o4 = reinterpret_cast<float4*>(s.obs + e * 48);
+        if (p.add_noise) {
+            const float4 u0 = o4[0], u1 = o4[1], u2 = o4[2];
+            o[0] = add_noise(o[0], u0.x, p.noise_lin_vel), o[1] = add_noise(o[1], u0.y, p.noise_lin_vel);
+            o[2] = add_noise(o[2], u0.z, p.noise_lin_vel), o[3] = add_noise(o[3], u0.w, p.noise_ang_vel);
+            o[4] = add_noise(o[4], u1.x, p.noise_ang_vel), o[5] = add_noise(o[5], u1.y, p.noise_ang_vel);
+            o[6] = add_noise(o[6], u1.z, p.noise_gravity), o[7] = add_noise(o[7], u1.w, p.noise_gravity);
+            o[8] = add_noise(o[8], u2.x, p.noise_gravity);
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) o[k] = clampf(o[k], -p.clip_obs, p.clip_obs);
+        o4[0] = make_float4(o[0], o[1], o[2], o[3]);
+        o4[1] = make_float4(o[4], o[5], o[6], o[7]);
+        o4[2] = make_float4(o[8], o[9], o[10], o[11]);
+
+        // R12 + per-env outputs
+        s.blv[e * 3 + 0] = blx, s.blv[e * 3 + 1] = bly, s.blv[e * 3 + 2] = blz;
+        s.bav[e * 3 + 0] = bax, s.bav[e * 3 + 1] = bay, s.bav[e * 3 + 2] = baz;
+        s.pg[e * 3 + 0] = pgx, s.pg[e * 3 + 1] = pgy, s.pg[e * 3 + 2] = pgz;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s.lrv[e * 6 + k] = lrv[k];
+        *reinterpret_cast<float4*>(s.cmd + e * 4) = make_float4(c0, c1, c2, c3);
+        s.ep[e] = ep_out;
+        s.rew[e] = rew;
+        s.reset[e] = reset ? 1 : 0;
+        s.tout[e] = time_out ? 1 : 0;
+        if (ROUGH) s.zpost[e] = zpost;
+    }
+    fence_proxy_async();   // make the generic-proxy smem writes visible to the bulk-store engine
+    __syncthreads();
+
+    // ---- write the tile back ----------------------------------------------------------------------
+    const bool obs_bulk = full && (O == 48);
+    if (full) {
+        if (tid == 0) {
+            bulk_s2g(b.last_actions + static_cast<size_t>(tile0) * ND, s.act, TILE * ND * 4);
+            bulk_s2g(b.last_dof_vel + static_cast<size_t>(tile0) * ND, s.ldv, TILE * ND * 4);
+            bulk_s2g(b.last_root_vel + static_cast<size_t>(tile0) * 6, s.lrv, TILE * 6 * 4);
+            bulk_s2g(b.commands + static_cast<size_t>(tile0) * 4, s.cmd, TILE * 4 * 4);
+            bulk_s2g(b.feet_air_time + static_cast<size_t>(tile0) * 4, s.fat, TILE * 4 * 4);
+            bulk_s2g(b.last_contacts + static_cast<size_t>(tile0) * 4, s.lc, TILE * 4);
+            bulk_s2g(b.episode_length_buf + tile0, s.ep, TILE * 8);
+            bulk_s2g(b.reset_buf + tile0, s.reset, TILE);
+            bulk_s2g(b.time_out_buf + tile0, s.tout, TILE);
+            bulk_s2g(b.rew_buf + tile0, s.rew, TILE * 4);
+            bulk_s2g(b.base_lin_vel + static_cast<size_t>(tile0) * 3, s.blv, TILE * 3 * 4);
+            bulk_s2g(b.base_ang_vel + static_cast<size_t>(tile0) * 3, s.bav, TILE * 3 * 4);
+            bulk_s2g(b.projected_gravity + static_cast<size_t>(tile0) * 3, s.pg, TILE * 3 * 4);
+            for (int k = 0; k < K; ++k) bulk_s2g(b.episode_sums + static_cast<size_t>(k) * N + tile0, s.sums + k * TILE, TILE * 4);
+            if (obs_bulk) bulk_s2g(b.obs_buf + static_cast<size_t>(tile0) * 48, s.obs, TILE * 48 * 4);
+            bulk_commit();
+        }
+    } else {
+        coop_copy(b.last_actions + static_cast<size_t>(tile0) * ND, s.act, nvalid * ND);
+        coop_copy(b.last_dof_vel + static_cast<size_t>(tile0) * ND, s.ldv, nvalid * ND);
+        coop_copy(b.last_root_vel + static_cast<size_t>(tile0) * 6, s.lrv, nvalid * 6);
+        coop_copy(b.commands + static_cast<size_t>(tile0) * 4, s.cmd, nvalid * 4);
+        coop_copy(b.feet_air_time + static_cast<size_t>(tile0) * 4, s.fat, nvalid * 4);
+        coop_copy(b.last_contacts + static_cast<size_t>(tile0) * 4, s.lc, nvalid * 4);
+        coop_copy(reinterpret_cast<long long*>(b.episode_length_buf) + tile0, s.ep, nvalid);
+        coop_copy(b.reset_buf + tile0, s.reset, nvalid);
+        coop_copy(b.time_out_buf + tile0, s.tout, nvalid);
+        coop_copy(b.rew_buf + tile0, s.rew, nvalid);
+        coop_copy(b.base_lin_vel + static_cast<size_t>(tile0) * 3, s.blv, nvalid * 3);
+        coop_copy(b.base_ang_vel + static_cast<size_t>(tile0) * 3, s.bav, nvalid * 3);
+        coop_copy(b.projected_gravity + static_cast<size_t>(tile0) * 3, s.pg, nvalid * 3);
+        for (int k = 0; k < K; ++k) coop_copy(b.episode_sums + static_cast<size_t>(k) * N + tile0, s.sums + k * TILE, nvalid);
+    }
+    if (!obs_bulk) {
+        for (int i = tid; i < nvalid * 48; i += TILE * LPE) b.obs_buf[static_cast<size_t>(tile0 + i / 48) * O + (i % 48)] = s.obs[i];
+    }
+
+    // ---- phase H2: height observations, one warp per env (legged_robot.py:220-226) ----------------
+    if (ROUGH) {
+        const int H = p.num_heights;
+        float* stage = s.stage + warp * HPAD;
+        for (int e = warp; e < nvalid; e += TILE * LPE / 32) {
+            const float z = s.zpost[e] - 0.5f;
+            const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
+            for (int pb = lane; pb * 4 < H; pb += 32) {
+                float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+                if (p.add_noise) u = philox::u01(rng.words(philox::OBS_NOISE, 12 + pb));
+                const float uu[4] = {u.x, u.y, u.z, u.w};
+                float out[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int pt = 4 * pb + j;
+                    const float mh = mul_rn(static_cast<float>(pt < H ? s.hraw[e * HPAD + pt] : 0), p.vertical_scale);
+                    float v = clampf(z - mh, -1.0f, 1.0f) * p.obs_height;
+                    if (p.add_noise) v = add_noise(v, uu[j], p.noise_height);
+                    out[j] = clampf(v, -p.clip_obs, p.clip_obs);
+                }
+                *reinterpret_cast<float4*>(stage + 4 * pb) = make_float4(out[0], out[1], out[2], out[3]);
+            }
+            __syncwarp();
+            float* dst = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48;
+            for (int pt = lane; pt < H; pt += 32) dst[pt] = stage[pt];
+            __syncwarp();
+        }
+    }
+
+    // ---- extras["episode"]: cross-CTA reduction, finalised by the last CTA to arrive ---------------
+    __syncthreads();
+    const int nreset = *s.nreset;
+    if (nreset > 0 && tid < K) atomicAdd(&b.ws_sums[tid], s.acc[tid]);
+    if (p.terrain_curriculum && tid == K) atomicAdd(&b.ws_sums[K], s.acc[K]);
+    if (nreset > 0 && tid == K + 1) atomicAdd(&b.ws_sums[K + 1], static_cast<double>(nreset));
+    __threadfence();
+    __syncthreads();
+    __shared__ unsigned int s_ticket;
+    if (tid == 0) s_ticket = atomicAdd(b.ws_counter, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1) {
+        __threadfence();
+        volatile double* ws = b.ws_sums;
+        const double cnt = ws[K + 1];
+        if (tid < K && cnt > 0.0) b.extras_out[tid] = static_cast<float>(ws[tid] / cnt) / p.max_episode_length_s;
+        if (tid == K && cnt > 0.0) b.extras_out[K] = static_cast<float>(ws[K] / static_cast<double>(N));
+        if (tid == K + 1) b.extras_out[K + 1] = static_cast<float>(cnt);
+        __syncthreads();
+        if (tid < K + 2) b.ws_sums[tid] = 0.0;
+        if (tid == 0) *b.ws_counter = 0u;
+    }
+    if (full && tid == 0) bulk_wait_read0();   // shared memory must stay alive until the bulk stores have read it
+}
+
+template <int TILE, bool ROUGH>
+int launch_post_physics(const B200LeggedParams& p, const B200LeggedBuffers& b, uint64_t step, long long env_off, int do_push,
+                        cudaStream_t stream) {
+    const size_t smem = carve_tile<TILE, ROUGH>(nullptr, p.num_bodies, p.num_sum_rows).bytes;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(post_physics_kernel<TILE, ROUGH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "post_physics: cannot reserve %zu B of shared memory: %s", smem,
+                     cudaGetErrorString(e));
+        configured = smem;
+    }
+    const int grid = (p.num_envs + TILE - 1) / TILE;
+    post_physics_kernel<TILE, ROUGH><<<grid, TILE * LPE, smem, stream>>>(p, b, step, env_off, do_push);
+    B200_LAUNCH_CHECK("post_physics");
+    return B200GYM_OK;
+}
+
+}  // namespace
+
+extern "C" int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedBuffers* b, uint64_t step, int64_t env_id_offset,
+                                    void* stream) {
+    B200_REQUIRE(p && b, B200GYM_EINVAL, "post_physics: null argument");
+    B200_REQUIRE(p->num_envs > 0, B200GYM_EINVAL, "post_physics: num_envs must be positive (got %d)", p->num_envs);
+    B200_REQUIRE(p->num_bodies > 0 && p->num_bodies <= 64, B200GYM_EINVAL, "post_physics: num_bodies %d out of range", p->num_bodies);
+    B200_REQUIRE(p->num_sum_rows >= 0 && p->num_sum_rows <= B200GYM_NUM_REWARD_TERMS, B200GYM_EINVAL, "post_physics: bad num_sum_rows");
+    B200_REQUIRE(p->resample_steps > 0, B200GYM_EINVAL, "post_physics: resample_steps must be positive");
+    B200_REQUIRE(p->num_term >= 1 && p->num_term <= B200GYM_MAX_TERM, B200GYM_EINVAL, "post_physics: 1..4 termination bodies");
+    const bool rough = p->num_heights > 0;
+    B200_REQUIRE(p->num_obs == 48 + p->num_heights, B200GYM_EINVAL, "post_physics: num_obs %d != 48 + %d heights", p->num_obs,
+                 p->num_heights);
+    B200_REQUIRE(!rough || (p->num_heights <= HPAD && p->n_px * p->n_py == p->num_heights && p->n_px <= B200GYM_MAX_POINTS &&
+                            p->n_py <= B200GYM_MAX_POINTS),
+                 B200GYM_EINVAL, "post_physics: unsupported height grid %dx%d", p->n_px, p->n_py);
+    B200_REQUIRE(!rough || b->measured_heights, B200GYM_EINVAL, "post_physics: measured_heights buffer missing");
+    B200_REQUIRE(!rough || p->mesh_plane || (b->height_samples && p->terrain_rows >= 2 && p->terrain_cols >= 2), B200GYM_EINVAL,
+                 "post_physics: height_samples missing");
+    B200_REQUIRE(!p->terrain_curriculum || (b->terrain_levels && b->terrain_types && b->terrain_origins), B200GYM_EINVAL,
+                 "post_physics: terrain curriculum buffers missing");
+    B200_REQUIRE(!p->zero_lstm_on_reset || (b->lstm_h && b->lstm_c), B200GYM_EINVAL, "post_physics: LSTM state buffers missing");
+    const void* must[] = {b->root_states, b->dof_state, b->contact_forces, b->actions, b->torques, b->last_actions, b->last_dof_vel,
+                          b->last_root_vel, b->commands, b->feet_air_time, b->last_contacts, b->episode_length_buf, b->reset_buf,
+                          b->time_out_buf, b->rew_buf, b->obs_buf, b->base_lin_vel, b->base_ang_vel, b->projected_gravity,
+                          b->env_origins, b->extras_out, b->ws_sums, b->ws_counter};
+    for (const void* q : must) {
+        B200_REQUIRE(q != nullptr, B200GYM_EINVAL, "post_physics: null buffer");
+        B200_REQUIRE(b200_aligned16(q), B200GYM_EALIGN, "post_physics: buffers must be 16-byte aligned");
+    }
+    B200_REQUIRE(p->num_sum_rows == 0 || (b->episode_sums && b200_aligned16(b->episode_sums) && (p->num_envs % 4 == 0 || p->num_envs < 64)),
+                 B200GYM_EALIGN, "post_physics: episode_sums rows must be 16-byte aligned (num_envs %% 4 == 0)");
+    const int do_push = (p->push_robots && p->push_time > 0 && (step % static_cast<uint64_t>(p->push_time) == 0)) ? 1 : 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (rough) return launch_post_physics<64, true>(*p, *b, step, env_id_offset, do_push, st);
+    return launch_post_physics<64, false>(*p, *b, step, env_id_offset, do_push, st);
+}

@@ -43,6 +43,7 @@ class LeggedRobot:
         self.debug_viz = False
         self.init_done = False
         self.viewer = None
+        self._timing = None          # bench.py: list of (kind, start_event, end_event) when enabled
         asset = dict(asset or {})
         self.dof_names = list(asset.get("dof_names", S.DOF_NAMES))
         self.num_envs = int(cfg.env.num_envs)
@@ -214,7 +215,9 @@ class LeggedRobot:
             actions = actions.float()
         for i in range(self.params.decimation):
             # the first evaluation also writes the clipped actions (fuses legged_robot.py:86-87)
+            ev = self._event_start()
             self.torques = self._compute_torques(actions, write_clipped=(i == 0)).view(self.torques.shape)
+            self._event_end("torques", ev)
             self.physics.simulate(self.torques)
         self.post_physics_step()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
@@ -227,31 +230,54 @@ class LeggedRobot:
         return self.torques
 
     def _buffers(self):
-        b = _lib.LeggedBuffersPOD()
+        """POD of raw device pointers; built once, only the (re-pointable) physics tensors are refreshed per call."""
         ph = self.physics
-        t = dict(root_states=ph.root_states, dof_state=ph.dof_state, contact_forces=ph.contact_forces, actions=self.actions,
-                 torques=self.torques, last_actions=self.last_actions, last_dof_vel=self.last_dof_vel,
-                 last_root_vel=self.last_root_vel, commands=self.commands, feet_air_time=self.feet_air_time,
-                 last_contacts=self.last_contacts, episode_length_buf=self.episode_length_buf, reset_buf=self.reset_buf,
-                 time_out_buf=self.time_out_buf, rew_buf=self.rew_buf, episode_sums=self._sums, obs_buf=self.obs_buf,
-                 base_lin_vel=self.base_lin_vel, base_ang_vel=self.base_ang_vel, projected_gravity=self.projected_gravity,
-                 measured_heights=self.measured_heights if torch.is_tensor(self.measured_heights) else None,
-                 height_samples=self.height_samples, env_origins=self.env_origins, terrain_levels=self.terrain_levels,
-                 terrain_types=self.terrain_types, terrain_origins=self.terrain_origins,
-                 lstm_h=getattr(self, "sea_hidden_state", None), lstm_c=getattr(self, "sea_cell_state", None),
-                 extras_out=self._extras_out, ws_sums=self._ws_sums, ws_counter=self._ws_counter)
-        for k, v in t.items():
-            if v is not None:
-                _lib.require_cuda(v, k)
-                setattr(b, k, v.data_ptr())
+        b = getattr(self, "_buf_pod", None)
+        if b is None:
+            b = _lib.LeggedBuffersPOD()
+            t = dict(actions=self.actions, torques=self.torques, last_actions=self.last_actions,
+                     last_dof_vel=self.last_dof_vel, last_root_vel=self.last_root_vel, commands=self.commands,
+                     feet_air_time=self.feet_air_time, last_contacts=self.last_contacts,
+                     episode_length_buf=self.episode_length_buf, reset_buf=self.reset_buf, time_out_buf=self.time_out_buf,
+                     rew_buf=self.rew_buf, episode_sums=self._sums, obs_buf=self.obs_buf, base_lin_vel=self.base_lin_vel,
+                     base_ang_vel=self.base_ang_vel, projected_gravity=self.projected_gravity,
+                     measured_heights=self.measured_heights if torch.is_tensor(self.measured_heights) else None,
+                     height_samples=self.height_samples, env_origins=self.env_origins, terrain_levels=self.terrain_levels,
+                     terrain_types=self.terrain_types, terrain_origins=self.terrain_origins,
+                     lstm_h=getattr(self, "sea_hidden_state", None), lstm_c=getattr(self, "sea_cell_state", None),
+                     extras_out=self._extras_out, ws_sums=self._ws_sums, ws_counter=self._ws_counter)
+            for k, v in t.items():
+                if v is not None:
+                    _lib.require_cuda(v, k)
+                    setattr(b, k, v.data_ptr())
+            for k in ("root_states", "dof_state", "contact_forces"):
+                _lib.require_cuda(getattr(ph, k), k)
+            self._buf_pod = b
+        b.root_states, b.dof_state, b.contact_forces = ph.root_states.data_ptr(), ph.dof_state.data_ptr(), ph.contact_forces.data_ptr()
         return b
 
     def post_physics_step(self):                                          # legged_robot.py:106-134, fused
         self.physics.refresh()
         self.common_step_counter += 1
+        ev = self._event_start()
         _lib.check(self.lib.b200gym_post_physics(self._pod, self._buffers(), self.common_step_counter, self.env_id_offset,
                                                  _lib.stream_ptr(self.device)), "post_physics")
+        self._event_end("post_physics", ev)
         self.physics.commit_resets(self.reset_buf)
+
+    def _event_start(self):
+        if self._timing is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
+    def _event_end(self, kind, start):
+        if start is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        self._timing.append((kind, start, ev))
 
     # ------------------------------------------------------------------ API kept from BaseTask (base_task.py:101-119)
     def get_observations(self):

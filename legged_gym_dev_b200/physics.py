@@ -62,3 +62,32 @@ class ReplayPhysics:
     def commit_resets(self, reset_buf):
         """PhysX would take over the reset rows of dof_state / root_states here; a replay has nothing to do."""
         return None
+
+
+class HostReplayPhysics(ReplayPhysics):
+    """Frames live in PINNED HOST memory and are copied to the device inside simulate()/refresh(): the
+    end-to-end arm of bench.py (a physics engine that hands its state over from the host every sub-step)."""
+
+    def __init__(self, tape, device="cuda"):
+        self.tape, self.copy = tape, True
+        dev = torch.device(device)
+        self.root_frames = tape.root.pin_memory()
+        self.dof_frames = tape.dof.pin_memory()
+        self.contact_frames = tape.contact.reshape(tape.frames, tape.num_envs * tape.contact.shape[2], 3).pin_memory()
+        self.num_envs, self.frames, self.decimation = tape.num_envs, tape.frames, tape.decimation
+        self.frame = 0
+        self.sub = 0
+        self.root_states = self.root_frames[0].to(dev)
+        self.dof_state = self.dof_frames[0, 0].to(dev)
+        self.contact_forces = self.contact_frames[0].to(dev)
+
+    def simulate(self, torques):
+        self.dof_state.copy_(self.dof_frames[self.frame % self.frames, self.sub], non_blocking=True)
+        self.sub += 1
+
+    def refresh(self):
+        f = self.frame % self.frames
+        self.root_states.copy_(self.root_frames[f], non_blocking=True)
+        self.contact_forces.copy_(self.contact_frames[f], non_blocking=True)
+        self.frame += 1
+        self.sub = 0
