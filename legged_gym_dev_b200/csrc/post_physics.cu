@@ -15,6 +15,7 @@
 //   phase S  1 thread per env: body-frame vectors, commands, termination, reward assembly, in-place reset,
 //            first 12 observation columns — scalar work executed exactly once per env
 //   phase H2 (rough only) one warp per env: height observations + noise    legged_robot.py:220-226
+#include <stdlib.h>
 #include "common.cuh"
 #include "philox.cuh"
 #include "../../include/b200gym.h"
@@ -697,6 +698,15 @@ extern "C" int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedB
                  B200GYM_EALIGN, "post_physics: episode_sums rows must be 16-byte aligned (num_envs %% 4 == 0)");
     const int do_push = (p->push_robots && p->push_time > 0 && (step % static_cast<uint64_t>(p->push_time) == 0)) ? 1 : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static int tile = 0;   // tuning knob (profiles/): envs per CTA
+    if (tile == 0) {
+        const char* t = getenv("B200GYM_TILE");
+        tile = t ? atoi(t) : 32;
+    }
+    if (tile == 32) {
+        if (rough) return launch_post_physics<32, true>(*p, *b, step, env_id_offset, do_push, st);
+        return launch_post_physics<32, false>(*p, *b, step, env_id_offset, do_push, st);
+    }
     if (rough) return launch_post_physics<64, true>(*p, *b, step, env_id_offset, do_push, st);
     return launch_post_physics<64, false>(*p, *b, step, env_id_offset, do_push, st);
 }
