@@ -120,6 +120,65 @@ int b200gym_lstm_torques(const B200LeggedParams* p, const float* actions, float*
 int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedBuffers* b, uint64_t step, int64_t env_id_offset,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Group M — reduced-order-model rollout (trajopt/rom_dynamics.py, deep_tube_learning/custom_sim.py,
+ * deep_tube_learning/controllers.py, deep_tube_learning/data_collection_trajectory.py)
+ * ---------------------------------------------------------------------------------------------- */
+#define B200GYM_ROM_SINGLE_INT_2D 0 /* rom_dynamics.py:182-211  n=2 m=2 */
+#define B200GYM_ROM_DOUBLE_INT_2D 1 /* rom_dynamics.py:214-260  n=4 m=2 */
+#define B200GYM_ROM_MAX_WINDOW 32
+
+typedef struct B200RomParams {
+    int32_t num_envs, model_type, rom_type, window, dN, horizon; /* window = N*dN, horizon = N (rom_dynamics.py:485-486) */
+    float model_dt, rom_dt, dt_loop;
+    float model_z_min[4], model_z_max[4], model_v_min[2], model_v_max[2];
+    float rom_z_min[4], rom_z_max[4], rom_v_min[2], rom_v_max[2];
+    float t_low, t_span, freq_low, freq_high, prob_stationary; /* UniformSampleHoldDT (utils.py:27-43), :544,:520 */
+    int32_t weight_zero_col; /* -1 UniformWeightSampler, 1 ...NoRamp, 2 ...NoExtreme (utils.py:46-79) */
+    int32_t randomize_rom_distance;
+    float max_rom_distance[4], zero_rom_dist_llh, noise_lower[4], noise_upper[4]; /* custom_sim.py:32-35,80-91 */
+    float Kp, Kd; /* DoubleSingleTracking (controllers.py:80-92) */
+    uint32_t seed_lo, seed_hi;
+} B200RomParams;
+
+/* Generator + sim state; every tensor row-major [N, ...] fp32 with the reference's shapes (rom_dynamics.py:487-508,
+ * custom_sim.py:29-31) so the Python attributes traj_gen.{k,t,v,trajectory,v_trajectory,...} alias them directly. */
+typedef struct B200RomState {
+    float* root_states;  /* [N, model_n]                 CustomSim.root_states (may be NULL for generator-only use) */
+    float* trajectory;   /* [N, window+1, rom_n]         traj_gen.trajectory */
+    float* v_trajectory; /* [N, window, 2]               traj_gen.v_trajectory */
+    float* v;            /* [N, 2] */
+    float *t, *k, *t_final; /* [N] fp32 (rom_dynamics.py:488-490) */
+    float* weights;      /* [N, 4] */
+    float *sample_hold_input, *extreme_input, *ramp_v_start, *ramp_v_end; /* [N, 2] */
+    float* ramp_t_start; /* [N] */
+    float *sin_mag, *sin_freq, *sin_off, *sin_mean; /* [N, 2] */
+    uint8_t* stationary_inds; /* [N] bool */
+    int32_t* rng_ctr;    /* [N] per-env draw-event counter of the counter-based RNG */
+    float* env_trajectory; /* [N, horizon, rom_n]        CustomSim.trajectory (interpolated, custom_sim.py:74) or NULL */
+    float* obs;          /* [N, model_n + rom_n + 2]     CustomSim.get_observations (custom_sim.py:95-100) or NULL */
+} B200RomState;
+
+/* TrajectoryGenerator.__init__ draw of ramp_v_end (rom_dynamics.py:495); all other state must be zero-filled. */
+int b200gym_rom_init(const B200RomParams* p, const B200RomState* s, int64_t env_id_offset, void* stream);
+/* CustomSim.step (custom_sim.py:71-75) = model.f + TrajectoryGenerator.step (rom_dynamics.py:568-590) + get_trajectory
+ * (:607-612) + get_observations.  action == NULL: generator only (TrajectoryGenerator.step / step_idx).
+ * step_mask (uint8 [N]) == NULL: all envs (step_idx(arange)). */
+int b200gym_rom_step(const B200RomParams* p, const B200RomState* s, const float* action, const uint8_t* step_mask,
+                     int64_t env_id_offset, void* stream);
+/* CustomSim.reset_idx (custom_sim.py:80-93) incl. reset_traj and TrajectoryGenerator.reset_idx (rom_dynamics.py:595-605)
+ * and the trailing zero-action step of ALL envs.  reset_mask == NULL: CustomSim.reset(). */
+int b200gym_rom_reset(const B200RomParams* p, const B200RomState* s, const uint8_t* reset_mask, int64_t env_id_offset,
+                      void* stream);
+/* DoubleSingleTracking.__call__ (controllers.py:87-92) with DoubleInt2D.clip_v_z (rom_dynamics.py:234-250). */
+int b200gym_rom_tracking_policy(const B200RomParams* p, const float* obs, float* action, void* stream);
+/* One epoch of data_collection_trajectory.py:104-149 as ONE persistent launch: reset all envs, then T ROM steps of
+ * {policy -> CustomSim.step} with generator state in registers; logs x [N,T+1,model_n] (may be NULL), z, pz_x
+ * [N,T+1,rom_n], v [N,T,2], done [N,T] (bool).  obs_io [N,8]: in = observation the first action is computed from
+ * (the reference reuses the previous epoch's, :94,:111), out = last observation. */
+int b200gym_rom_rollout(const B200RomParams* p, const B200RomState* s, float* obs_io, int32_t T, float* x, float* z, float* pz_x,
+                        float* v, uint8_t* done, int64_t env_id_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,28 @@ class LeggedBuffersPOD(C.Structure):
     _fields_ = [(n, vp) for n in _BUF_FIELDS]
 
 
+class RomParamsPOD(C.Structure):
+    _fields_ = [
+        ("num_envs", i32), ("model_type", i32), ("rom_type", i32), ("window", i32), ("dN", i32), ("horizon", i32),
+        ("model_dt", f32), ("rom_dt", f32), ("dt_loop", f32),
+        ("model_z_min", f32 * 4), ("model_z_max", f32 * 4), ("model_v_min", f32 * 2), ("model_v_max", f32 * 2),
+        ("rom_z_min", f32 * 4), ("rom_z_max", f32 * 4), ("rom_v_min", f32 * 2), ("rom_v_max", f32 * 2),
+        ("t_low", f32), ("t_span", f32), ("freq_low", f32), ("freq_high", f32), ("prob_stationary", f32),
+        ("weight_zero_col", i32), ("randomize_rom_distance", i32),
+        ("max_rom_distance", f32 * 4), ("zero_rom_dist_llh", f32), ("noise_lower", f32 * 4), ("noise_upper", f32 * 4),
+        ("Kp", f32), ("Kd", f32), ("seed_lo", u32), ("seed_hi", u32),
+    ]
+
+
+_ROM_FIELDS = ["root_states", "trajectory", "v_trajectory", "v", "t", "k", "t_final", "weights", "sample_hold_input",
+               "extreme_input", "ramp_v_start", "ramp_v_end", "ramp_t_start", "sin_mag", "sin_freq", "sin_off", "sin_mean",
+               "stationary_inds", "rng_ctr", "env_trajectory", "obs"]
+
+
+class RomStatePOD(C.Structure):
+    _fields_ = [(n, vp) for n in _ROM_FIELDS]
+
+
 _lib = None
 
 
@@ -82,7 +104,16 @@ def lib():
     L.b200gym_post_physics.argtypes = [pp, C.POINTER(LeggedBuffersPOD), C.c_uint64, C.c_int64, vp]
     for name in ("b200gym_pd_torques", "b200gym_set_actuator_net", "b200gym_lstm_torques", "b200gym_post_physics"):
         getattr(L, name).restype = C.c_int
-    for name, cls in (("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD)):
+    rp, rs = C.POINTER(RomParamsPOD), C.POINTER(RomStatePOD)
+    L.b200gym_rom_init.argtypes = [rp, rs, C.c_int64, vp]
+    L.b200gym_rom_step.argtypes = [rp, rs, vp, vp, C.c_int64, vp]
+    L.b200gym_rom_reset.argtypes = [rp, rs, vp, C.c_int64, vp]
+    L.b200gym_rom_tracking_policy.argtypes = [rp, vp, vp, vp]
+    L.b200gym_rom_rollout.argtypes = [rp, rs, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int64, vp]
+    for name in ("b200gym_rom_init", "b200gym_rom_step", "b200gym_rom_reset", "b200gym_rom_tracking_policy", "b200gym_rom_rollout"):
+        getattr(L, name).restype = C.c_int
+    for name, cls in (("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
+                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD)):
         n = L.b200gym_sizeof(name.encode())
         if n != C.sizeof(cls):
             raise RuntimeError(f"ABI mismatch: sizeof({name}) is {n} in the library, {C.sizeof(cls)} in the binding")

@@ -144,3 +144,29 @@ def with_upstream_rewards(cfg, pd_control=True):
     if pd_control:
         cfg.control.use_actuator_network = False
     return cfg
+
+
+def double_single_int_cfg(num_envs=8192, seed=0, **over):
+    """deep_tube_learning/configs/data_generation/double_single_int.yaml:29-87 (+ default_custom.yaml:24-25 pos_max=1e9):
+    DoubleInt2D model (dt 0.05) tracked against a SingleInt2D ROM (dt 0.1), horizon N=10."""
+    d = dict(pos_max=1e9, vel_max=0.3, acc_max=0.5, vel_max_rom=0.2, model_dt=0.05, rom_dt=0.1, N=10, dN=1, t_low=1, t_high=2,
+             freq_low=0.01, freq_high=2, prob_stationary=0.0005, weight_samp_cls="UniformWeightSamplerNoRamp",
+             randomize_rom_distance=True, max_rom_distance=[1.0, 1.0], zero_rom_dist_llh=0.25,
+             noise_lower=[0.0, 0.0, -0.1, -0.1], noise_upper=[0.0, 0.0, 0.1, 0.1], Kp=10, Kd=10, episode_length_s=20)
+    d.update(over)
+    pm, vm, am, vr = d["pos_max"], d["vel_max"], d["acc_max"], d["vel_max_rom"]
+    return _tree({
+        "env": dict(num_envs=num_envs, episode_length_s=d["episode_length_s"], type="custom",
+                    model=dict(dt=d["model_dt"], cls="DoubleInt2D", z_min=[-pm, -pm, -vm, -vm], z_max=[pm, pm, vm, vm],
+                               v_min=[-am, -am], v_max=[am, am])),
+        "rom": dict(cls="SingleInt2D", dt=d["rom_dt"], z_min=[-pm, -pm], z_max=[pm, pm], v_min=[-vr, -vr], v_max=[vr, vr]),
+        "trajectory_generator": dict(cls="TrajectoryGenerator", t_samp_cls="UniformSampleHoldDT",
+                                     weight_samp_cls=d["weight_samp_cls"], N=d["N"], t_low=d["t_low"], t_high=d["t_high"],
+                                     freq_low=d["freq_low"], freq_high=d["freq_high"], seed=seed,
+                                     prob_stationary=d["prob_stationary"], dN=d["dN"]),
+        "noise": dict(add_noise=False),
+        "domain_rand": dict(randomize_rom_distance=d["randomize_rom_distance"], max_rom_distance=d["max_rom_distance"],
+                            zero_rom_dist_llh=d["zero_rom_dist_llh"]),
+        "init_state": dict(default_noise_lower=d["noise_lower"], default_noise_upper=d["noise_upper"]),
+        "controller": dict(Kp=d["Kp"], Kd=d["Kd"]),
+    })
