@@ -179,6 +179,47 @@ int b200gym_rom_tracking_policy(const B200RomParams* p, const float* obs, float*
 int b200gym_rom_rollout(const B200RomParams* p, const B200RomState* s, float* obs_io, int32_t T, float* x, float* z, float* pz_x,
                         float* v, uint8_t* done, int64_t env_id_offset, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Group G — rsl_rl rollout storage + PPO update (rsl_rl v1.0.2, a fork of which the reference imports at
+ * legged_gym/utils/task_registry.py:37-38; source NOT in /root/reference: arithmetic restated)
+ * ---------------------------------------------------------------------------------------------- */
+/* RolloutStorage.compute_returns (rsl_rl/storage/rollout_storage.py) as a per-env reverse scan over [T,N] tensors:
+ *   nt = 1 - done_t; delta = r_t + nt*gamma*V_{t+1} - V_t; A = delta + nt*gamma*lam*A; returns_t = A + V_t;
+ *   advantages_t = returns_t - V_t  (un-normalised).  If time_outs != NULL the time-out bootstrap of
+ *   PPO.process_env_step (rewards += gamma * values * time_outs) is applied first, in place.
+ * stats[0..2] (double, zeroed by the caller) receive sum(adv), sum(adv^2), count — all-reduce them across ranks
+ * before b200gym_adv_normalize when envs are sharded. */
+int b200gym_gae_returns(float* rewards, const float* values, const uint8_t* dones, const uint8_t* time_outs,
+                        const float* last_values, float* returns, float* advantages, double* stats, int32_t T, int32_t N,
+                        float gamma, float lam, void* stream);
+/* advantages = (advantages - mean) / (std_unbiased + 1e-8) from stats (rollout_storage.py, end of compute_returns). */
+int b200gym_adv_normalize(float* advantages, const double* stats, int64_t count, void* stream);
+/* RolloutStorage.mini_batch_generator gather: dst[k][i, :] = src[k][idx[i], :] for k < n_tensors; row_bytes[k] bytes per row. */
+int b200gym_gather_rows(void* const* dst, const void* const* src, const int32_t* row_bytes, int32_t n_tensors, const int64_t* idx,
+                        int64_t n_rows, void* stream);
+/* PPO.update loss (rsl_rl/algorithms/ppo.py) for one minibatch, forward AND gradient w.r.t. the network outputs:
+ * diagonal-Gaussian log-prob / entropy with the learned std[A], KL(old || new), clipped surrogate, clipped value
+ * loss, entropy bonus.  Writes d_mu [B,A], d_value [B] (already scaled by 1/B) and accumulates d_std [A] and
+ * scalars[0..3] = {sum kl, sum surrogate, sum value_loss, sum entropy} (double, zeroed by the caller). */
+typedef struct B200PpoLossParams {
+    int32_t batch, num_actions, use_clipped_value_loss, pad;
+    float clip_param, value_loss_coef, entropy_coef, inv_global_batch; /* 1 / (batch summed over ranks) */
+} B200PpoLossParams;
+int b200gym_ppo_loss(const B200PpoLossParams* p, const float* mu, const float* std, const float* value, const float* actions,
+                     const float* old_log_prob, const float* advantages, const float* returns, const float* old_values,
+                     const float* old_mu, const float* old_sigma, float* d_mu, float* d_value, float* d_std, double* scalars,
+                     void* stream);
+/* clip_grad_norm_(max_norm) + Adam.step over ONE flat fp32 parameter buffer: sumsq[0] (double, zeroed by the caller)
+ * is filled by b200gym_grad_sumsq (all-reduced gradients), then b200gym_clip_adam applies
+ * g *= min(1, max_norm / (sqrt(sumsq) + 1e-6)) and the bias-corrected Adam update with learning rate *lr (device). */
+int b200gym_grad_sumsq(const float* grad, int64_t n, float grad_scale, double* sumsq, void* stream);
+int b200gym_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
+                      const double* sumsq, float max_norm, const float* lr, float beta1, float beta2, float eps, int32_t step,
+                      void* stream);
+/* PPO.update adaptive schedule (ppo.py): kl_mean = *kl_sum / count; lr /= 1.5 if kl_mean > 2*desired_kl (floor 1e-5),
+ * lr *= 1.5 if 0 < kl_mean < desired_kl/2 (cap 1e-2).  lr lives on the device, so no host sync per minibatch. */
+int b200gym_adaptive_lr(const double* kl_sum, double count, float desired_kl, float* lr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,11 @@ class RomStatePOD(C.Structure):
     _fields_ = [(n, vp) for n in _ROM_FIELDS]
 
 
+class PpoLossParamsPOD(C.Structure):
+    _fields_ = [("batch", i32), ("num_actions", i32), ("use_clipped_value_loss", i32), ("pad", i32),
+                ("clip_param", f32), ("value_loss_coef", f32), ("entropy_coef", f32), ("inv_global_batch", f32)]
+
+
 _lib = None
 
 
@@ -112,7 +117,18 @@ def lib():
     L.b200gym_rom_rollout.argtypes = [rp, rs, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int64, vp]
     for name in ("b200gym_rom_init", "b200gym_rom_step", "b200gym_rom_reset", "b200gym_rom_tracking_policy", "b200gym_rom_rollout"):
         getattr(L, name).restype = C.c_int
-    for name, cls in (("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
+    f64 = C.c_double
+    L.b200gym_gae_returns.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, f32, f32, vp]
+    L.b200gym_adv_normalize.argtypes = [vp, vp, C.c_int64, vp]
+    L.b200gym_gather_rows.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.c_int32, vp, C.c_int64, vp]
+    L.b200gym_ppo_loss.argtypes = [C.POINTER(PpoLossParamsPOD)] + [vp] * 15
+    L.b200gym_grad_sumsq.argtypes = [vp, C.c_int64, f32, vp, vp]
+    L.b200gym_clip_adam.argtypes = [vp, vp, vp, vp, C.c_int64, f32, vp, f32, vp, f32, f32, f32, C.c_int32, vp]
+    L.b200gym_adaptive_lr.argtypes = [vp, f64, f32, vp, vp]
+    for name in ("b200gym_gae_returns", "b200gym_adv_normalize", "b200gym_gather_rows", "b200gym_ppo_loss", "b200gym_grad_sumsq",
+                 "b200gym_clip_adam", "b200gym_adaptive_lr"):
+        getattr(L, name).restype = C.c_int
+    for name, cls in (("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
                       ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD)):
         n = L.b200gym_sizeof(name.encode())
         if n != C.sizeof(cls):

@@ -106,7 +106,7 @@ class LeggedRobot:
         self.obs_buf = z(N, self.num_obs)
         self.rew_buf = z(N)
         self.reset_buf = torch.ones(N, dtype=torch.bool, device=dev)
-        self.episode_length_buf = z(N, dtype=torch.long)
+        self._episode_length_buf = z(N, dtype=torch.long)
         self.time_out_buf = z(N, dtype=torch.bool)
         self.privileged_obs_buf = z(N, self.num_privileged_obs) if self.num_privileged_obs is not None else None
         self.common_step_counter = 0
@@ -184,6 +184,15 @@ class LeggedRobot:
         return False
 
     # ------------------------------------------------------------------ aliased physics tensors (legged_robot.py:545-551)
+    @property
+    def episode_length_buf(self):
+        return self._episode_length_buf
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        # rsl_rl's runner REBINDS this attribute (init_at_random_ep_len); the kernels hold the buffer's address, so copy in place
+        self._episode_length_buf.copy_(value)
+
     @property
     def root_states(self):
         return self.physics.root_states

@@ -1,0 +1,399 @@
+"""rsl_rl-shaped rollout storage / PPO / runner whose storage arithmetic runs in the fused kernels (csrc/ppo.cu).
+
+Mirrors the surface of rsl_rl v1.0.2 the reference touches: `OnPolicyRunner(env, train_cfg_dict,
+log_dir, device=, wandb_callback=)`, `.learn(num_learning_iterations, init_at_random_ep_len)`, `.load/.save`,
+`.get_inference_policy(device)`, `.alg.actor_critic`, `.alg.optimizer`, checkpoint keys
+{'model_state_dict','optimizer_state_dict','iter','infos'} (deep_tube_learning/utils.py:305-308).
+
+What is fused: the time-out bootstrap + GAE reverse scan + advantage statistics (one launch), normalisation (one
+launch), the minibatch gather of all storage tensors (one launch), the whole PPO loss forward+gradient w.r.t. the
+network outputs (one launch), grad-norm + clip + Adam over ONE flat parameter buffer (two launches) and the
+KL-adaptive learning rate kept on the device — no host sync inside update().  Across GPUs (envs sharded, one process
+per GPU) the only collectives are one all-reduce of the 3 advantage statistics per iteration and one all-reduce of the
+flat gradient buffer (+ KL sum/count piggy-backed) per minibatch.
+The policy MLP contractions themselves still go through torch (cuBLAS); a tcgen05 MLP kernel is the next step
+(DESIGN.md §"what comes next").
+"""
+import ctypes as C
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _dist_ready():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class RolloutStorage:
+    """rsl_rl/storage/rollout_storage.py: [T, N, ...] tensors, same names."""
+
+    class Transition:
+        def __init__(self):
+            self.clear()
+
+        def clear(self):
+            self.observations = self.critic_observations = self.actions = self.rewards = self.dones = None
+            self.values = self.actions_log_prob = self.action_mean = self.action_sigma = self.hidden_states = None
+
+    def __init__(self, num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, actions_shape, device="cuda"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("the b200gym RolloutStorage runs on CUDA devices only (no CPU fallback)")
+        T, N, dev = num_transitions_per_env, num_envs, self.device
+        self.num_envs, self.num_transitions_per_env = N, T
+        self.obs_shape, self.privileged_obs_shape, self.actions_shape = obs_shape, privileged_obs_shape, actions_shape
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)
+        self.observations = z(T, N, *obs_shape)
+        self.privileged_observations = z(T, N, *privileged_obs_shape) if privileged_obs_shape[0] is not None else None
+        self.rewards, self.values, self.returns, self.advantages = z(T, N, 1), z(T, N, 1), z(T, N, 1), z(T, N, 1)
+        self.actions, self.mu, self.sigma = z(T, N, *actions_shape), z(T, N, *actions_shape), z(T, N, *actions_shape)
+        self.actions_log_prob = z(T, N, 1)
+        self.dones = z(T, N, 1, dtype=torch.uint8)
+        self.time_outs = z(T, N, dtype=torch.uint8)
+        self._stats = torch.zeros(4, dtype=torch.double, device=dev)
+        self.step = 0
+        self.lib = _lib.lib()
+
+    def add_transitions(self, tr):
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        s = self.step
+        self.observations[s].copy_(tr.observations)
+        if self.privileged_observations is not None:
+            self.privileged_observations[s].copy_(tr.critic_observations)
+        self.actions[s].copy_(tr.actions)
+        self.rewards[s].copy_(tr.rewards.view(-1, 1))
+        self.dones[s].copy_(tr.dones.view(-1, 1))
+        self.values[s].copy_(tr.values)
+        self.actions_log_prob[s].copy_(tr.actions_log_prob.view(-1, 1))
+        self.mu[s].copy_(tr.action_mean)
+        self.sigma[s].copy_(tr.action_sigma)
+        if getattr(tr, "time_outs", None) is not None:
+            self.time_outs[s].copy_(tr.time_outs)
+        else:
+            self.time_outs[s].zero_()
+        self.step += 1
+
+    def clear(self):
+        self.step = 0
+
+    def compute_returns(self, last_values, gamma, lam, bootstrap_time_outs=True):
+        """PPO.process_env_step's time-out bootstrap + RolloutStorage.compute_returns, fused; statistics all-reduced
+        across env shards before the normalisation."""
+        T, N, ptr, st = self.num_transitions_per_env, self.num_envs, _lib.ptr, _lib.stream_ptr(self.device)
+        self._stats.zero_()
+        last_values = last_values.contiguous()
+        _lib.check(self.lib.b200gym_gae_returns(ptr(self.rewards), ptr(self.values), ptr(self.dones),
+                                                ptr(self.time_outs) if bootstrap_time_outs else None, ptr(last_values),
+                                                ptr(self.returns), ptr(self.advantages), ptr(self._stats), T, N, gamma, lam, st),
+                   "gae_returns")
+        if _dist_ready():
+            import torch.distributed as dist
+            dist.all_reduce(self._stats)
+        _lib.check(self.lib.b200gym_adv_normalize(ptr(self.advantages), ptr(self._stats), T * N, st), "adv_normalize")
+
+    def get_statistics(self):
+        done = self.dones.clone()
+        done[-1] = 1
+        flat = done.permute(1, 0, 2).reshape(-1, 1)
+        ids = torch.cat((flat.new_tensor([-1], dtype=torch.int64), flat.nonzero(as_tuple=False)[:, 0]))
+        lengths = ids[1:] - ids[:-1]
+        return lengths.float().mean(), self.rewards.mean()
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8, generator=None, plan=None):
+        """Yields the same 11-tuple as rsl_rl; each minibatch is gathered by ONE kernel launch."""
+        T, N = self.num_transitions_per_env, self.num_envs
+        batch = T * N
+        mb = batch // num_mini_batches
+        if plan is None:
+            perm = torch.randperm(num_mini_batches * mb, device=self.device, generator=generator)
+            plan = [perm[i * mb:(i + 1) * mb] for _ in range(num_epochs) for i in range(num_mini_batches)]
+        crit = self.privileged_observations if self.privileged_observations is not None else self.observations
+        srcs = [self.observations, crit, self.actions, self.values, self.returns, self.actions_log_prob, self.advantages, self.mu,
+                self.sigma]
+        flat = [t.flatten(0, 1) for t in srcs]
+        n = len(flat)
+        row_bytes = (C.c_int32 * n)(*[f.shape[1] * f.element_size() if f.dim() > 1 else f.element_size() for f in flat])
+        src_ptrs = (C.c_void_p * n)(*[f.data_ptr() for f in flat])
+        for idx in plan:
+            idx = idx.to(self.device, torch.int64).contiguous()
+            outs = [torch.empty(idx.numel(), *f.shape[1:], dtype=f.dtype, device=self.device) for f in flat]
+            dst_ptrs = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+            _lib.check(self.lib.b200gym_gather_rows(dst_ptrs, src_ptrs, row_bytes, n, _lib.ptr(idx), idx.numel(),
+                                                    _lib.stream_ptr(self.device)), "gather_rows")
+            obs, cobs, act, val, ret, logp, adv, mu, sig = outs
+            yield obs, cobs, act, val, adv, ret, logp, mu, sig, (None, None), None
+
+
+class ActorCritic(nn.Module):
+    """rsl_rl/modules/actor_critic.py (non-recurrent): MLP actor/critic, ELU by default, learned std.  All parameters are
+    views of ONE flat fp32 buffer (and one flat gradient buffer) so that all-reduce / clip / Adam are single passes."""
+    is_recurrent = False
+
+    def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=(256, 256, 256),
+                 critic_hidden_dims=(256, 256, 256), activation="elu", init_noise_std=1.0, **kwargs):
+        super().__init__()
+        acts = {"elu": nn.ELU, "selu": nn.SELU, "relu": nn.ReLU, "lrelu": nn.LeakyReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}
+        if activation not in acts:
+            raise ValueError(f"invalid activation function {activation}")
+
+        def mlp(i, hs, o):
+            layers, d = [], i
+            for h in hs:
+                layers += [nn.Linear(d, h), acts[activation]()]
+                d = h
+            return nn.Sequential(*layers, nn.Linear(d, o))
+        self.actor = mlp(num_actor_obs, list(actor_hidden_dims), num_actions)
+        self.critic = mlp(num_critic_obs, list(critic_hidden_dims), 1)
+        self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+        self.distribution = None
+        self.flat_param = self.flat_grad = None
+
+    def flatten_parameters(self):
+        """Re-homes every parameter (and its .grad) into one contiguous buffer; 8 spare floats carry piggy-backed scalars."""
+        ps = list(self.parameters())
+        dev = ps[0].device
+        n = sum(p.numel() for p in ps)
+        self.flat_param = torch.empty(n, device=dev)
+        self.flat_grad = torch.zeros(n + 8, device=dev)
+        off = 0
+        self._slices = {}
+        for name, p in self.named_parameters():
+            k = p.numel()
+            self.flat_param[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + k].view_as(p)
+            p.grad = self.flat_grad[off:off + k].view_as(p)
+            self._slices[name] = (off, k)
+            off += k
+        self.num_flat = n
+        return self
+
+    def reset(self, dones=None):
+        pass
+
+    @property
+    def action_mean(self):
+        return self.distribution.mean
+
+    @property
+    def action_std(self):
+        return self.distribution.stddev
+
+    @property
+    def entropy(self):
+        return self.distribution.entropy().sum(dim=-1)
+
+    def update_distribution(self, observations):
+        mean = self.actor(observations)
+        self.distribution = torch.distributions.Normal(mean, mean * 0.0 + self.std)
+
+    def act(self, observations, **kwargs):
+        self.update_distribution(observations)
+        return self.distribution.sample()
+
+    def get_actions_log_prob(self, actions):
+        return self.distribution.log_prob(actions).sum(dim=-1)
+
+    def act_inference(self, observations):
+        return self.actor(observations)
+
+    def evaluate(self, critic_observations, **kwargs):
+        return self.critic(critic_observations)
+
+
+class PPO:
+    """rsl_rl/algorithms/ppo.py with the storage / loss / optimiser arithmetic in fused kernels."""
+
+    def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
+                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True,
+                 schedule="fixed", desired_kl=0.01, device="cuda"):
+        self.device = torch.device(device)
+        self.desired_kl, self.schedule, self.learning_rate = desired_kl, schedule, learning_rate
+        self.actor_critic = actor_critic.to(self.device)
+        if self.actor_critic.flat_param is None or self.actor_critic.flat_param.device != self.device:
+            self.actor_critic.flatten_parameters()
+        self.storage = None
+        self.optimizer = FlatAdam(self.actor_critic, lr=learning_rate)
+        self.transition = RolloutStorage.Transition()
+        self.clip_param, self.num_learning_epochs, self.num_mini_batches = clip_param, num_learning_epochs, num_mini_batches
+        self.value_loss_coef, self.entropy_coef, self.gamma, self.lam = value_loss_coef, entropy_coef, gamma, lam
+        self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
+        self.lib = _lib.lib()
+        self._scalars = torch.zeros(8, dtype=torch.double, device=self.device)
+        self._sumsq = torch.zeros(1, dtype=torch.double, device=self.device)
+        self._klsum = torch.zeros(2, dtype=torch.double, device=self.device)
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    def act(self, obs, critic_obs):
+        tr, ac = self.transition, self.actor_critic
+        tr.actions = ac.act(obs).detach()
+        tr.values = ac.evaluate(critic_obs).detach()
+        tr.actions_log_prob = ac.get_actions_log_prob(tr.actions).detach()
+        tr.action_mean, tr.action_sigma = ac.action_mean.detach(), ac.action_std.detach()
+        tr.observations, tr.critic_observations = obs, critic_obs
+        return tr.actions
+
+    def process_env_step(self, rewards, dones, infos):
+        """The time-out bootstrap (rewards += gamma * values * time_outs) is deferred into the GAE kernel: the storage keeps
+        the raw reward plus the time-out flag, and compute_returns applies it in place before the scan."""
+        tr = self.transition
+        tr.rewards, tr.dones = rewards.clone(), dones
+        tr.time_outs = infos["time_outs"] if "time_outs" in infos else None
+        self.storage.add_transitions(tr)
+        tr.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs):
+        last_values = self.actor_critic.evaluate(last_critic_obs).detach()
+        self.storage.compute_returns(last_values, self.gamma, self.lam)
+
+    def update(self, plan=None):
+        ac, ptr, st = self.actor_critic, _lib.ptr, _lib.stream_ptr(self.device)
+        world = 1
+        if _dist_ready():
+            import torch.distributed as dist
+            world = dist.get_world_size()
+        n_updates = 0
+        self._scalars.zero_()
+        A = ac.std.numel()
+        std_off, _ = ac._slices["std"]
+        lp = _lib.PpoLossParamsPOD()
+        lp.num_actions, lp.use_clipped_value_loss = A, int(self.use_clipped_value_loss)
+        lp.clip_param, lp.value_loss_coef, lp.entropy_coef = self.clip_param, self.value_loss_coef, self.entropy_coef
+        for (obs, cobs, act, old_v, adv, ret, old_logp, old_mu, old_sigma, _, _) in \
+                self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs, plan=plan):
+            B = obs.shape[0]
+            mu = ac.actor(obs)
+            value = ac.critic(cobs)
+            d_mu, d_value = torch.empty_like(mu), torch.empty(B, device=self.device)
+            ac.flat_grad.zero_()
+            lp.batch, lp.inv_global_batch = B, 1.0 / (B * world)
+            sc = self._scalars[4:8]
+            sc.zero_()
+            _lib.check(self.lib.b200gym_ppo_loss(lp, ptr(mu), ptr(ac.std), ptr(value), ptr(act), ptr(old_logp), ptr(adv), ptr(ret),
+                                                 ptr(old_v), ptr(old_mu), ptr(old_sigma), ptr(d_mu), ptr(d_value),
+                                                 C.c_void_p(ac.flat_grad.data_ptr() + 4 * std_off), ptr(sc), st), "ppo_loss")
+            torch.autograd.backward([mu, value], [d_mu, d_value.view(-1, 1)])
+            self._scalars[0:4] += sc
+            # one all-reduce: gradients + (sum kl, count) piggy-backed in the spare tail of the flat buffer
+            tail = ac.flat_grad[ac.num_flat:ac.num_flat + 2]
+            tail[0], tail[1] = sc[0].float(), float(B)
+            if world > 1:
+                dist.all_reduce(ac.flat_grad)
+            if self.desired_kl is not None and self.schedule == "adaptive":
+                self._klsum[0], self._klsum[1] = tail[0].double(), tail[1].double()
+                _lib.check(self.lib.b200gym_adaptive_lr(ptr(self._klsum), float(B * world), self.desired_kl, ptr(self.optimizer.lr), st),
+                           "adaptive_lr")
+            self.optimizer.step(self.max_grad_norm)
+            n_updates += 1
+        self.storage.clear()
+        s = (self._scalars[0:4] / (n_updates * (self.storage.num_envs * self.storage.num_transitions_per_env // self.num_mini_batches)))
+        self.learning_rate = self.optimizer.lr   # device scalar; float(self.learning_rate) syncs on demand
+        return s[2], s[1]   # mean_value_loss, mean_surrogate_loss (device scalars)
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (betas 0.9/0.999, eps 1e-8) over ActorCritic.flat_param, fused with clip_grad_norm_."""
+
+    def __init__(self, ac, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.ac, self.betas, self.eps = ac, betas, eps
+        dev = ac.flat_param.device
+        self.lr = torch.tensor([lr], dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(ac.flat_param)
+        self.exp_avg_sq = torch.zeros_like(ac.flat_param)
+        self.steps = 0
+        self._sumsq = torch.zeros(1, dtype=torch.double, device=dev)
+        self.lib = _lib.lib()
+
+    def step(self, max_grad_norm):
+        ac, ptr, st = self.ac, _lib.ptr, _lib.stream_ptr(self.ac.flat_param.device)
+        self.steps += 1
+        self._sumsq.zero_()
+        _lib.check(self.lib.b200gym_grad_sumsq(ptr(ac.flat_grad), ac.num_flat, 1.0, ptr(self._sumsq), st), "grad_sumsq")
+        _lib.check(self.lib.b200gym_clip_adam(ptr(ac.flat_param), ptr(ac.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), ac.num_flat,
+                                              1.0, ptr(self._sumsq), max_grad_norm, ptr(self.lr), self.betas[0], self.betas[1], self.eps,
+                                              self.steps, st), "clip_adam")
+
+    def grad_norm(self):
+        return torch.sqrt(self._sumsq[0])
+
+    def state_dict(self):
+        return dict(lr=self.lr.clone(), exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(), steps=self.steps)
+
+    def load_state_dict(self, sd):
+        self.lr.copy_(sd["lr"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.steps = sd["steps"]
+
+
+class OnPolicyRunner:
+    """rsl_rl/runners/on_policy_runner.py as the reference calls it (task_registry.py:148, scripts/train.py:44)."""
+
+    def __init__(self, env, train_cfg, log_dir=None, device="cuda", wandb_callback=None):
+        self.cfg, self.alg_cfg, self.policy_cfg = train_cfg["runner"], train_cfg["algorithm"], train_cfg["policy"]
+        self.device, self.env, self.log_dir, self.wandb_callback = torch.device(device), env, log_dir, wandb_callback
+        num_critic_obs = env.num_privileged_obs if env.num_privileged_obs is not None else env.num_obs
+        ac = ActorCritic(env.num_obs, num_critic_obs, env.num_actions, **self.policy_cfg).to(self.device)
+        self.alg = PPO(ac, device=self.device, **self.alg_cfg)
+        self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
+        self.alg.init_storage(env.num_envs, self.num_steps_per_env, [env.num_obs], [env.num_privileged_obs], [env.num_actions])
+        self.tot_timesteps, self.tot_time, self.current_learning_iteration = 0, 0, 0
+
+    def learn(self, num_learning_iterations, init_at_random_ep_len=False):
+        env = self.env
+        if init_at_random_ep_len:
+            env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
+        obs = env.get_observations()
+        priv = env.get_privileged_observations()
+        critic_obs = priv if priv is not None else obs
+        self.alg.actor_critic.train()
+        infos_out = []
+        for it in range(self.current_learning_iteration, self.current_learning_iteration + num_learning_iterations):
+            with torch.inference_mode():
+                for _ in range(self.num_steps_per_env):
+                    actions = self.alg.act(obs, critic_obs)
+                    obs, priv, rewards, dones, infos = env.step(actions)
+                    critic_obs = priv if priv is not None else obs
+                    self.alg.process_env_step(rewards, dones, infos)
+                self.alg.compute_returns(critic_obs)
+            mean_value_loss, mean_surrogate_loss = self.alg.update()
+            infos_out.append(dict(it=it, mean_value_loss=mean_value_loss, mean_surrogate_loss=mean_surrogate_loss))
+            if self.wandb_callback is not None:
+                self.wandb_callback(dict(mean_value_loss=float(mean_value_loss), mean_surrogate_loss=float(mean_surrogate_loss), it=it),
+                                    float(self.alg.learning_rate), self.alg.actor_critic.std.mean().item(),
+                                    self.alg.actor_critic.state_dict(), self.alg.optimizer.state_dict(), self.device, None)
+            if self.log_dir is not None and it % self.save_interval == 0:
+                self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
+        self.current_learning_iteration += num_learning_iterations
+        return infos_out
+
+    def save(self, path, infos=None):
+        torch.save({"model_state_dict": self.alg.actor_critic.state_dict(), "optimizer_state_dict": self.alg.optimizer.state_dict(),
+                    "iter": self.current_learning_iteration, "infos": infos}, path)
+
+    def load(self, path, load_optimizer=True):
+        d = torch.load(path, map_location=self.device)
+        self.alg.actor_critic.load_state_dict(d["model_state_dict"])
+        if load_optimizer:
+            self.alg.optimizer.load_state_dict(d["optimizer_state_dict"])
+        self.current_learning_iteration = d["iter"]
+        return d["infos"]
+
+    def get_inference_policy(self, device=None):
+        self.alg.actor_critic.eval()
+        if device is not None:
+            self.alg.actor_critic.to(device)
+        return self.alg.actor_critic.act_inference

@@ -60,3 +60,70 @@ def test_fused_matches_reference_golden(name):
         a = case.tape.actions[s % case.tape.frames] * (150.0 if s == 3 else 1.0)
         env.step(a.cuda())
         _check(LC.snapshot_fused(env), g, s, f"golden {name} step {s}: ")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Group M goldens (reference CustomSim + TrajectoryGenerator + DoubleSingleTracking)
+# ---------------------------------------------------------------------------------------------------
+ROM = sorted(os.path.basename(p)[len("rom_"):-4] for p in glob.glob(os.path.join(GOLD, "rom_*.npz")))
+ROM_OVER = {"default": {}, "fast_resample": dict(prob_stationary=0.05, t_low=0.2, t_high=0.5)}
+ROM_EXACT = {"t", "k", "stationary"}
+
+
+def _rom_check(get, g, s, tag):
+    for key in ("action", "obs", "root", "traj", "vtraj", "v", "t", "k", "t_final", "weights", "stationary", "env_trajectory"):
+        want = torch.from_numpy(g[f"s{s}_{key}"])
+        got = get(key)
+        if key in ROM_EXACT:
+            assert_exact(got.to(want.dtype), want, f"{tag}{key}")
+        else:
+            assert_close(got, want, 1.0, f"{tag}{key}")
+
+
+@pytest.mark.parametrize("name", ROM)
+def test_rom_port_matches_reference_golden(name):
+    from oracle.port_rom import RomPort, rom_params
+    g = np.load(os.path.join(GOLD, f"rom_{name}.npz"))
+    N, steps = int(g["num_envs"]), int(g["steps"])
+    port = RomPort(rom_params(N, seed=int(g["seed"]), **ROM_OVER[name]))
+    assert_close(port.ramp_v_end, torch.from_numpy(g["ramp_v_end0"]), 1.0, "ramp_v_end0")
+    obs, _ = port.reset()
+    keep = set(int(k) for k in g["keep"])
+    for s in range(steps):
+        if s == 60:
+            obs, _ = port.reset_idx(torch.arange(0, N, 3))
+        a = port.policy(obs)
+        obs, _ = port.step(a)
+        if s in keep:
+            view = dict(action=a, obs=obs, root=port.root_states, traj=port.traj, vtraj=port.v_traj, v=port.v, t=port.t, k=port.k,
+                        t_final=port.t_final, weights=port.weights, stationary=port.stationary, env_trajectory=port.trajectory)
+            _rom_check(lambda k: view[k], g, s, f"rom golden {name} step {s}: ")
+    assert np.array_equal(port.ctr, g["ctr"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ROM)
+def test_rom_fused_matches_reference_golden(name):
+    from legged_gym_dev_b200 import configs
+    from legged_gym_dev_b200.rom import CustomSim, DoubleSingleTracking
+    g = np.load(os.path.join(GOLD, f"rom_{name}.npz"))
+    N, steps = int(g["num_envs"]), int(g["steps"])
+    env = CustomSim(configs.double_single_int_cfg(N, seed=int(g["seed"]), **ROM_OVER[name]), device="cuda")
+    policy = DoubleSingleTracking(10, 10, env.model.clip_v_z)
+    assert_close(env.traj_gen.ramp_v_end.cpu(), torch.from_numpy(g["ramp_v_end0"]), 1.0, "ramp_v_end0")
+    env.reset()
+    obs = env.get_observations()
+    keep = set(int(k) for k in g["keep"])
+    for s in range(steps):
+        if s == 60:
+            env.reset_idx(torch.arange(0, N, 3, device="cuda"))
+            obs = env.get_observations()
+        a = policy(obs)
+        a_keep = a.clone()
+        obs, _, _, _, _ = env.step(a)
+        if s in keep:
+            tg = env.traj_gen
+            view = dict(action=a_keep, obs=obs, root=env.root_states, traj=tg.trajectory, vtraj=tg.v_trajectory, v=tg.v, t=tg.t, k=tg.k,
+                        t_final=tg.t_final, weights=tg.weights, stationary=tg.stationary_inds, env_trajectory=env.trajectory)
+            _rom_check(lambda k: view[k].detach().cpu(), g, s, f"rom golden {name} step {s}: ")
+    assert np.array_equal(env.traj_gen.rng_ctr.cpu().numpy().astype(np.int64), g["ctr"])

@@ -1,0 +1,66 @@
+"""N>1 host logic on CPU (gloo, world_size 2): env sharding keyed by GLOBAL env id, all-reduced statistics.
+The CUDA kernels cannot run here; the oracle port stands in for them so that the rank/offset/collective plumbing the
+GPU path uses (env_id_offset, shard ranges, (sum, sum^2, n) all-reduce) is exercised end to end."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from legged_gym_dev_b200.sharding import env_shard, combine_advantage_stats
+    from oracle.port_rom import RomPort, rom_params
+    N = 64
+    lo, hi = env_shard(rank, world, N)
+    port_ = RomPort(rom_params(hi - lo, seed=9), env_id_offset=lo)
+    log, _ = port_.collect_epoch(torch.zeros(hi - lo, 8), 6)
+    # advantage statistics: (sum, sum^2, n) all-reduced must reproduce the global mean / unbiased std
+    g = torch.Generator().manual_seed(0)
+    adv = torch.randn(N, generator=g)
+    mine = adv[lo:hi].double()
+    st = torch.stack([mine.sum(), (mine * mine).sum(), torch.tensor(float(hi - lo), dtype=torch.double)])
+    dist.all_reduce(st)
+    mean, std = combine_advantage_stats(st)
+    q.put((rank, lo, hi, log["z"], log["v"], float(mean), float(std), float(adv.mean()), float(adv.std())))
+    dist.destroy_process_group()
+
+
+def test_env_sharding_and_stats_over_gloo():
+    from oracle.port_rom import RomPort, rom_params
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = RomPort(rom_params(64, seed=9))
+    log, _ = full.collect_epoch(torch.zeros(64, 8), 6)
+    for rank, lo, hi, z, v, mean, std, gmean, gstd in out:
+        assert torch.equal(z, log["z"][lo:hi]) and torch.equal(v, log["v"][lo:hi]), "per-env results depend on the sharding"
+        assert abs(mean - gmean) < 1e-6 and abs(std - gstd) < 1e-6
+    assert sorted((o[1], o[2]) for o in out) == [(0, 32), (32, 64)]
+
+
+def test_env_shard_ranges():
+    from legged_gym_dev_b200.sharding import env_shard
+    for world in (1, 2, 4, 8):
+        for n in (8, 1000, 4096, 1 << 20):
+            spans = [env_shard(r, world, n) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 4 * world
+            if n // world >= 4:
+                assert all((h - l) % 4 == 0 for l, h in spans[:-1])

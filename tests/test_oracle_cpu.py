@@ -129,3 +129,40 @@ def test_port_tracks_unmodified_reference(name):
             assert_close(port.sea_hidden_state, env.sea_hidden_state, 1.0, tag + "h")
             assert_close(port.sea_cell_state, env.sea_cell_state, 1.0, tag + "c")
     assert resets > 0
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("over", [{}, dict(prob_stationary=0.05, t_low=0.2, t_high=0.5), dict(randomize_rom_distance=False)])
+def test_rom_port_tracks_unmodified_reference(over):
+    """oracle/port_rom.py vs the reference's CustomSim/TrajectoryGenerator/DoubleSingleTracking, every step."""
+    from oracle import ref_harness as H
+    from oracle.port_rom import RomPort, rom_params
+    N, steps = 96, 260
+    env, policy, cfg = H.make_reference_custom_sim(N, seed=3, **over)
+    port = RomPort(rom_params(N, seed=3, **over))
+    assert_exact(port.ramp_v_end, env.traj_gen.ramp_v_end, "ramp_v_end at construction")
+    env.reset()
+    o1 = env.get_observations()
+    o2, _ = port.reset()
+    for s in range(steps):
+        if s == 130:
+            ids = torch.arange(0, N, 3)
+            env.reset_idx(ids)
+            o1 = env.get_observations()
+            o2, _ = port.reset_idx(ids)
+        a1, a2 = policy(o1), port.policy(o2)
+        o1, _, _, d1, _ = env.step(a1)
+        o2, d2 = port.step(a2)
+        tg, tag = env.traj_gen, f"rom {over} step {s}: "
+        assert_exact(port.t, tg.t, tag + "t")
+        assert_exact(port.k, tg.k, tag + "k")
+        assert_exact(port.stationary, tg.stationary_inds, tag + "stationary")
+        assert_close(a2, a1, 1.0, tag + "action")
+        assert_close(o2, o1, 1.0, tag + "obs")
+        assert_close(port.traj, tg.trajectory, 1.0, tag + "trajectory")
+        assert_close(port.v_traj, tg.v_trajectory, 1.0, tag + "v_trajectory")
+        assert_close(port.v, tg.v, 1.0, tag + "v")
+        assert_close(port.weights, tg.weights, 1.0, tag + "weights")
+        assert_close(port.t_final, tg.t_final, 1.0, tag + "t_final")
+        assert_close(port.trajectory, env.trajectory, 1.0, tag + "CustomSim.trajectory")
+    assert np.array_equal(port.ctr, env._shim.ctr)

@@ -1,0 +1,149 @@
+"""Group G parity on the GPU: storage / PPO kernels vs the restated rsl_rl arithmetic (oracle/port_ppo.py; parity
+unpinned by the reference, see that file's header).  returns / advantages: 1e-5 (S = 1); update: 1e-3 as per
+SURVEY.md §8d cfg 5 (the MLP contraction is a library GEMM on both sides), identical LR-schedule decisions."""
+import copy
+
+import pytest
+import torch
+
+from oracle import port_ppo as O
+from oracle.compare import assert_close, assert_exact
+
+pytestmark = pytest.mark.gpu
+
+
+def make_storage_inputs(T, N, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    rewards = 0.02 + 0.05 * torch.randn(T, N, 1, generator=g)
+    values = 0.5 + 0.3 * torch.randn(T, N, 1, generator=g)
+    dones = torch.rand(T, N, 1, generator=g) < 0.005
+    time_outs = dones.squeeze(-1) & (torch.rand(T, N, generator=g) < 0.5)
+    last_values = 0.5 + 0.3 * torch.randn(N, 1, generator=g)
+    return rewards, values, dones, time_outs, last_values
+
+
+@pytest.mark.parametrize("T,N", [(24, 4096), (24, 1000), (1, 7), (50, 333)])
+def test_gae_returns_and_normalisation(T, N):
+    from legged_gym_dev_b200.ppo import RolloutStorage
+    rewards, values, dones, time_outs, last_values = make_storage_inputs(T, N)
+    st = RolloutStorage(N, T, [48], [None], [12])
+    st.rewards.copy_(rewards), st.values.copy_(values), st.dones.copy_(dones), st.time_outs.copy_(time_outs)
+    st.compute_returns(last_values.cuda(), 0.99, 0.95)
+    boot = torch.stack([O.process_env_step_bootstrap(rewards[t], values[t], time_outs[t], 0.99) for t in range(T)])
+    ret, adv_raw, adv = O.compute_returns(boot, values, dones, last_values, 0.99, 0.95)
+    assert_close(st.rewards.cpu(), boot, 1.0, "bootstrapped rewards")
+    assert_close(st.returns.cpu(), ret, 1.0, "returns")
+    if T * N > 1:
+        assert_close(st.advantages.cpu(), adv, 1.0, "normalised advantages", rtol=2e-5)
+
+
+def test_gather_rows_matches_indexing():
+    from legged_gym_dev_b200.ppo import RolloutStorage
+    T, N = 24, 512
+    st = RolloutStorage(N, T, [235], [None], [12])
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in (st.observations, st.actions, st.values, st.returns, st.actions_log_prob, st.advantages, st.mu, st.sigma):
+        t.copy_(torch.randn(t.shape, device="cuda", generator=g))
+    plan = [torch.randperm(T * N, device="cuda", generator=g)[:3000], torch.arange(5, device="cuda")]
+    flat = lambda t: t.flatten(0, 1)
+    for idx, mb in zip(plan, st.mini_batch_generator(4, 1, plan=plan)):
+        obs, cobs, act, val, adv, ret, logp, mu, sig, _, _ = mb
+        assert torch.equal(obs, flat(st.observations)[idx]) and torch.equal(cobs, obs)
+        assert torch.equal(act, flat(st.actions)[idx]) and torch.equal(val, flat(st.values)[idx])
+        assert torch.equal(adv, flat(st.advantages)[idx]) and torch.equal(ret, flat(st.returns)[idx])
+        assert torch.equal(logp, flat(st.actions_log_prob)[idx]) and torch.equal(mu, flat(st.mu)[idx])
+        assert torch.equal(sig, flat(st.sigma)[idx])
+
+
+def _oracle_and_fused(num_obs=48, hidden=(128, 64, 32), seed=1):
+    from legged_gym_dev_b200.ppo import ActorCritic, PPO
+    torch.manual_seed(seed)
+    ref = O.ActorCritic(num_obs, num_obs, 12, list(hidden), list(hidden), init_noise_std=1.0)
+    ac = ActorCritic(num_obs, num_obs, 12, actor_hidden_dims=hidden, critic_hidden_dims=hidden, init_noise_std=1.0)
+    ac.load_state_dict(copy.deepcopy(ref.state_dict()))
+    alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
+              entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
+              desired_kl=0.01, device="cuda")
+    return ref, alg
+
+
+def _fill(alg, ref, T, N, num_obs, seed=2):
+    """A rollout generated with the (shared) initial policy so that old_log_prob / mu / sigma are consistent."""
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(T, N, num_obs, generator=g)
+    with torch.no_grad():
+        d = ref.dist(obs)
+        actions = d.mean + d.stddev * torch.randn(T, N, 12, generator=g)
+        logp = d.log_prob(actions).sum(-1, keepdim=True)
+        values = ref.critic(obs)
+    rewards, _, dones, time_outs, last_values = make_storage_inputs(T, N, seed)
+    alg.init_storage(N, T, [num_obs], [None], [12])
+    st = alg.storage
+    for name, t in dict(observations=obs, actions=actions, actions_log_prob=logp, values=values, mu=d.mean, sigma=d.stddev,
+                        rewards=rewards, dones=dones, time_outs=time_outs).items():
+        getattr(st, name).copy_(t)
+    st.compute_returns(last_values.cuda(), 0.99, 0.95)
+    boot = torch.stack([O.process_env_step_bootstrap(rewards[t], values[t], time_outs[t], 0.99) for t in range(T)])
+    ret, _, adv = O.compute_returns(boot, values, dones, last_values, 0.99, 0.95)
+    f = lambda t: t.flatten(0, 1)
+    store = dict(obs=f(obs), critic_obs=f(obs), actions=f(actions), values=f(values), returns=f(ret), old_log_prob=f(logp),
+                 advantages=f(adv), old_mu=f(d.mean), old_sigma=f(d.stddev))
+    return store
+
+
+def test_ppo_loss_gradients_match_autograd():
+    from legged_gym_dev_b200 import _lib
+    ref, alg = _oracle_and_fused()
+    store = _fill(alg, ref, 8, 256, 48)
+    idx = torch.arange(0, 2048, 2)
+    batch = {k: v[idx] for k, v in store.items()}
+    # perturb the policy so ratios leave the clip range and the value clip engages
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    mu = ref.actor(batch["obs"]).detach().requires_grad_(True)
+    value = ref.critic(batch["critic_obs"]).detach().requires_grad_(True)
+    std = ref.std.detach().clone().requires_grad_(True)
+    d = torch.distributions.Normal(mu, mu * 0.0 + std)
+    logp = d.log_prob(batch["actions"]).sum(-1)
+    ent = d.entropy().sum(-1)
+    ratio = torch.exp(logp - batch["old_log_prob"].squeeze())
+    adv = batch["advantages"].squeeze()
+    surr = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+    vc = batch["values"] + (value - batch["values"]).clamp(-0.2, 0.2)
+    vl = torch.max((value - batch["returns"]).pow(2), (vc - batch["returns"]).pow(2)).mean()
+    loss = surr + 1.0 * vl - 0.01 * ent.mean()
+    loss.backward()
+    B = len(idx)
+    lp = _lib.PpoLossParamsPOD()
+    lp.batch, lp.num_actions, lp.use_clipped_value_loss = B, 12, 1
+    lp.clip_param, lp.value_loss_coef, lp.entropy_coef, lp.inv_global_batch = 0.2, 1.0, 0.01, 1.0 / B
+    c = lambda t: t.detach().cuda().contiguous()
+    d_mu, d_v, d_std = torch.empty(B, 12, device="cuda"), torch.empty(B, device="cuda"), torch.zeros(12, device="cuda")
+    sc = torch.zeros(4, dtype=torch.double, device="cuda")
+    args = [c(mu), c(std), c(value), c(batch["actions"]), c(batch["old_log_prob"]), c(batch["advantages"]), c(batch["returns"]),
+            c(batch["values"]), c(batch["old_mu"]), c(batch["old_sigma"])]
+    _lib.check(_lib.lib().b200gym_ppo_loss(lp, *[_lib.ptr(a) for a in args], _lib.ptr(d_mu), _lib.ptr(d_v), _lib.ptr(d_std), _lib.ptr(sc),
+                                           _lib.stream_ptr()), "ppo_loss")
+    assert_close(d_mu.cpu() * B, mu.grad * B, 1.0, "d loss / d mu", rtol=1e-4)
+    assert_close(d_v.cpu() * B, value.grad.squeeze() * B, 1.0, "d loss / d value", rtol=1e-4)
+    assert_close(d_std.cpu(), std.grad, 1.0, "d loss / d std", rtol=1e-4)
+    assert_close(sc[1].cpu() / B, surr.detach().double(), 1.0, "surrogate", rtol=1e-4)
+    assert_close(sc[2].cpu() / B, vl.detach().double(), 1.0, "value loss", rtol=1e-4)
+    assert_close(sc[3].cpu() / B, ent.mean().detach().double(), 1.0, "entropy", rtol=1e-4)
+
+
+def test_ppo_update_tracks_oracle():
+    """cfg 5 shape: flat nets [128,64,32], 4 minibatches; identical LR decisions, parameters within 1e-3."""
+    ref, alg = _oracle_and_fused()
+    T, N = 24, 512
+    store = _fill(alg, ref, T, N, 48)
+    plan = O.mini_batch_indices(T, N, 4, 2, generator=torch.Generator().manual_seed(3))
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    lr, stats = O.ppo_update(ref, opt, store, plan, 1e-3, desired_kl=0.01, max_grad_norm=1.0, schedule="adaptive", clip_param=0.2,
+                             value_loss_coef=1.0, entropy_coef=0.01, use_clipped_value_loss=True)
+    alg.update(plan=[p.cuda() for p in plan])
+    assert abs(float(alg.optimizer.lr) - lr) <= 1e-9 + 1e-6 * lr, (float(alg.optimizer.lr), lr, [s["lr"] for s in stats])
+    sd = alg.actor_critic.state_dict()
+    for k, v in ref.state_dict().items():
+        assert_close(sd[k].cpu(), v, 1.0, f"parameter {k} after update", rtol=1e-3)
