@@ -29,7 +29,7 @@ def test_gae_returns_and_normalisation(T, N):
     st = RolloutStorage(N, T, [48], [None], [12])
     st.rewards.copy_(rewards), st.values.copy_(values), st.dones.copy_(dones), st.time_outs.copy_(time_outs)
     st.compute_returns(last_values.cuda(), 0.99, 0.95)
-    boot = torch.stack([O.process_env_step_bootstrap(rewards[t], values[t], time_outs[t], 0.99) for t in range(T)])
+    boot = torch.stack([O.process_env_step_bootstrap(rewards[t, :, 0], values[t], time_outs[t], 0.99) for t in range(T)]).unsqueeze(-1)
     ret, adv_raw, adv = O.compute_returns(boot, values, dones, last_values, 0.99, 0.95)
     assert_close(st.rewards.cpu(), boot, 1.0, "bootstrapped rewards")
     assert_close(st.returns.cpu(), ret, 1.0, "returns")
@@ -83,7 +83,7 @@ def _fill(alg, ref, T, N, num_obs, seed=2):
                         rewards=rewards, dones=dones, time_outs=time_outs).items():
         getattr(st, name).copy_(t)
     st.compute_returns(last_values.cuda(), 0.99, 0.95)
-    boot = torch.stack([O.process_env_step_bootstrap(rewards[t], values[t], time_outs[t], 0.99) for t in range(T)])
+    boot = torch.stack([O.process_env_step_bootstrap(rewards[t, :, 0], values[t], time_outs[t], 0.99) for t in range(T)]).unsqueeze(-1)
     ret, _, adv = O.compute_returns(boot, values, dones, last_values, 0.99, 0.95)
     f = lambda t: t.flatten(0, 1)
     store = dict(obs=f(obs), critic_obs=f(obs), actions=f(actions), values=f(values), returns=f(ret), old_log_prob=f(logp),
