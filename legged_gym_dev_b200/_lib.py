@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200gym.so")
+LIB_PATH = os.environ.get("B200GYM_LIB") or os.path.join(_HERE, "libb200gym.so")   # env override: A/B of kernel variants
 
 NUM_DOF, NUM_FEET, NUM_PEN, MAX_TERM, NUM_TERMS, MAX_POINTS = 12, 4, 8, 4, 19, 32
 

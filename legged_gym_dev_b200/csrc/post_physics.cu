@@ -15,14 +15,31 @@
 //   phase S  1 thread per env: body-frame vectors, commands, termination, reward assembly, in-place reset,
 //            first 12 observation columns — scalar work executed exactly once per env
 //   phase H2 (rough only) one warp per env: height observations + noise    legged_robot.py:220-226
+#include <math.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "philox.cuh"
 #include "../../include/b200gym.h"
 
+#ifndef PP_SQNORM
+#define PP_SQNORM 1        // threshold compares on squared norms with exact (host-computed) constants instead of sqrtf
+#endif
+#ifndef PP_ALIAS_OBS
+#define PP_ALIAS_OBS 1     // the observation tile reuses the contact-force tile (dead after the contact pass of phase W)
+#endif
+#ifndef PP_MINBLOCKS
+#define PP_MINBLOCKS 9     // register cap so that 9 CTAs of 128 threads are resident per SM (A/B: profiles/r1_post_physics_ab.txt)
+#endif
+#ifndef PP_FINALIZE_KERNEL
+#define PP_FINALIZE_KERNEL 1   // extras["episode"] finalised by a 1-warp follow-up kernel instead of a last-CTA ticket
+#endif
+
 namespace {
 
 constexpr int LPE = 4;     // lanes per env in phase W
+
+// sqrtf(x) > t  <=>  x > gt(t);  sqrtf(x) < t  <=>  x < lt(t)   (exact in fp32; computed on the host by sq_thresholds())
+struct SqThr { float gt1, gt01, gt02, lt01; };
 constexpr int ND = B200GYM_NUM_DOF;
 constexpr int HPAD = 192;  // padded per-env stride of the raw height tile (>= 187)
 
@@ -52,6 +69,9 @@ __device__ __forceinline__ float norm3_rn(float x, float y, float z) {
     return sqrtf(add_rn(add_rn(mul_rn(x, x), mul_rn(y, y)), mul_rn(z, z)));
 }
 
+__device__ __forceinline__ float sq2_rn(float x, float y) { return add_rn(mul_rn(x, x), mul_rn(y, y)); }
+__device__ __forceinline__ float sq3_rn(float x, float y, float z) { return add_rn(add_rn(mul_rn(x, x), mul_rn(y, y)), mul_rn(z, z)); }
+
 __device__ __forceinline__ float wrap_to_pi(float a) {
     // legged_gym/utils/math.py:45-48 on fp32 tensors: python-style remainder by fl32(2*pi), then -2*pi where > fl32(pi)
     const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
@@ -61,8 +81,8 @@ __device__ __forceinline__ float wrap_to_pi(float a) {
     return r;
 }
 
-__device__ __forceinline__ void resample_commands(const B200LeggedParams& p, const philox::Stream& rng, uint32_t site, float& c0,
-                                                  float& c1, float& c2, float& c3) {
+__device__ __forceinline__ void resample_commands(const B200LeggedParams& p, const SqThr& thr, const philox::Stream& rng, uint32_t site,
+                                                  float& c0, float& c1, float& c2, float& c3) {
     // legged_robot.py:365-387
     const uint4 w = rng.words(site, 0);
     c0 = affine_rn(p.cmd_span[0], philox::u01(w.x), p.cmd_lo[0]);
@@ -71,7 +91,11 @@ __device__ __forceinline__ void resample_commands(const B200LeggedParams& p, con
         c3 = affine_rn(p.cmd_span[3], philox::u01(w.z), p.cmd_lo[3]);
     else
         c2 = affine_rn(p.cmd_span[2], philox::u01(w.z), p.cmd_lo[2]);
+#if PP_SQNORM
+    const float m = sq2_rn(c0, c1) > thr.gt02 ? 1.0f : 0.0f;
+#else
     const float m = norm2_rn(c0, c1) > 0.2f ? 1.0f : 0.0f;
+#endif
     c0 *= m;
     c1 *= m;
 }
@@ -127,7 +151,8 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
     s.lc = c.take<uint8_t>(TILE * 4);
     s.ep = c.take<long long>(TILE);
     s.sums = c.take<float>(static_cast<size_t>(K > 0 ? K : 1) * TILE);
-    s.obs = c.take<float>(TILE * 48);
+    // the obs tile reuses the contact tile when it fits (B*3 >= 48): contact forces are dead after phase W's contact pass
+    s.obs = (PP_ALIAS_OBS && B * 3 >= 48) ? s.contact : c.take<float>(TILE * 48);
     s.blv = c.take<float>(TILE * 3);
     s.bav = c.take<float>(TILE * 3);
     s.pg = c.take<float>(TILE * 3);
@@ -157,9 +182,10 @@ __device__ __forceinline__ void coop_copy(T* dst, const T* src, int n) {
 }
 
 template <int TILE, bool ROUGH>
-__global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_constant__ B200LeggedParams p,
-                                                                 const __grid_constant__ B200LeggedBuffers b, uint64_t step,
-                                                                 long long env_off, int do_push) {
+__global__ void __launch_bounds__(TILE* LPE, (PP_MINBLOCKS * TILE * LPE <= 2048 ? PP_MINBLOCKS : 2048 / (TILE * LPE))) post_physics_kernel(const __grid_constant__ B200LeggedParams p,
+                                                                               const __grid_constant__ B200LeggedBuffers b,
+                                                                               uint64_t step, long long env_off, int do_push,
+                                                                               const SqThr thr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int B = p.num_bodies, K = p.num_sum_rows, N = p.num_envs, O = p.num_obs;
     const TileSmem s = carve_tile<TILE, ROUGH>(smem_raw, B, K);
@@ -254,13 +280,6 @@ __global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_co
     {
         const int e = tid >> 2, g = tid & 3;
         const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
-        // uniforms for observation columns 0..35 = Philox blocks 0..8, exchanged through the obs tile
-        if (p.add_noise) {
-            float4* stage = reinterpret_cast<float4*>(s.obs + e * 48);
-            stage[g] = philox::u01(rng.words(philox::OBS_NOISE, g));
-            stage[g + 4] = philox::u01(rng.words(philox::OBS_NOISE, g + 4));
-            if (g == 0) stage[8] = philox::u01(rng.words(philox::OBS_NOISE, 8));
-        }
         float pa_rate = 0.f, pd_acc = 0.f, pd_vel = 0.f, ptq = 0.f, ppos_lim = 0.f, pvel_lim = 0.f, ptq_lim = 0.f, pstand = 0.f;
         float o_pos[3], o_vel[3], o_act[3];
         const float inv_dt = 1.0f / p.dt;
@@ -305,14 +324,32 @@ __global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const float* Fp = s.contact + (e * B + p.pen_idx[g + 4 * j]) * 3;
+#if PP_SQNORM
+                p_coll += (sq3_rn(Fp[0], Fp[1], Fp[2]) > thr.gt01) ? 1.0f : 0.0f;
+#else
                 p_coll += (norm3_rn(Fp[0], Fp[1], Fp[2]) > 0.1f) ? 1.0f : 0.0f;
+#endif
             }
         }
         // R8 (contact part): lane t checks termination body t
         float p_term = 0.f;
         if (g < p.num_term) {
             const float* F = s.contact + (e * B + p.term_idx[g]) * 3;
+#if PP_SQNORM
+            p_term = sq3_rn(F[0], F[1], F[2]) > thr.gt1 ? 1.0f : 0.0f;
+#else
             p_term = norm3_rn(F[0], F[1], F[2]) > 1.0f ? 1.0f : 0.0f;
+#endif
+        }
+#if PP_ALIAS_OBS
+        __syncthreads();   // every lane of the CTA is done with the contact tile: it becomes the obs tile
+#endif
+        // uniforms for observation columns 0..35 = Philox blocks 0..8, exchanged through the obs tile
+        if (p.add_noise) {
+            float4* stage = reinterpret_cast<float4*>(s.obs + e * 48);
+            stage[g] = philox::u01(rng.words(philox::OBS_NOISE, g));
+            stage[g + 4] = philox::u01(rng.words(philox::OBS_NOISE, g + 4));
+            if (g == 0) stage[8] = philox::u01(rng.words(philox::OBS_NOISE, 8));
         }
         // DOF observation columns 12..47 (+ noise), already clipped (legged_robot.py:100-101,208-226)
         if (p.add_noise) {
@@ -373,7 +410,7 @@ __global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_co
         // R5: command resampling + heading (legged_robot.py:343-354)
         const float4 cmd4 = *reinterpret_cast<const float4*>(s.cmd + e * 4);
         float c0 = cmd4.x, c1 = cmd4.y, c2 = cmd4.z, c3 = cmd4.w;
-        if (static_cast<int>(ep) % p.resample_steps == 0) resample_commands(p, rng, philox::CMD_PERIODIC, c0, c1, c2, c3);
+        if (static_cast<int>(ep) % p.resample_steps == 0) resample_commands(p, thr, rng, philox::CMD_PERIODIC, c0, c1, c2, c3);
         if (p.heading_command) {
             // forward = quat_apply(q, [1,0,0]) (x,y only): t = 2*cross(q_xyz, [1,0,0]) = (0, 2qz, -2qy)
             const float tyy = 2.0f * qz, tzz = -2.0f * qy;
@@ -395,7 +432,13 @@ __global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_co
         const bool reset = (P[P_TERM * TILE] > 0.0f) | time_out;
 
         // R9: reward assembly in the reference's (alphabetical) order (legged_robot.py:189-206)
+#if PP_SQNORM
+        const float cmd_sq = sq2_rn(c0, c1);
+        const bool cmd_gt01 = cmd_sq > thr.gt01, cmd_lt01 = cmd_sq < thr.lt01;
+#else
         const float cmd_norm = norm2_rn(c0, c1);
+        const bool cmd_gt01 = cmd_norm > 0.1f, cmd_lt01 = cmd_norm < 0.1f;
+#endif
         float rew = 0.0f;
         float* sums = s.sums + e;
         auto add_term = [&](int k, float val) {
@@ -414,11 +457,11 @@ __global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_co
         if (rs[T_DOF_POS_LIMITS] != 0.f) add_term(T_DOF_POS_LIMITS, P[P_POS_LIM * TILE]);
         if (rs[T_DOF_VEL] != 0.f) add_term(T_DOF_VEL, P[P_DOF_VEL * TILE]);
         if (rs[T_DOF_VEL_LIMITS] != 0.f) add_term(T_DOF_VEL_LIMITS, P[P_VEL_LIM * TILE]);
-        if (rs[T_FEET_AIR_TIME] != 0.f) add_term(T_FEET_AIR_TIME, P[P_AIR * TILE] * (cmd_norm > 0.1f ? 1.0f : 0.0f));
+        if (rs[T_FEET_AIR_TIME] != 0.f) add_term(T_FEET_AIR_TIME, P[P_AIR * TILE] * (cmd_gt01 ? 1.0f : 0.0f));
         if (rs[T_FEET_CONTACT_FORCES] != 0.f) add_term(T_FEET_CONTACT_FORCES, P[P_FCF * TILE]);
         if (rs[T_LIN_VEL_Z] != 0.f) add_term(T_LIN_VEL_Z, blz * blz);
         if (rs[T_ORIENTATION] != 0.f) add_term(T_ORIENTATION, pgx * pgx + pgy * pgy);
-        if (rs[T_STAND_STILL] != 0.f) add_term(T_STAND_STILL, P[P_STAND * TILE] * (cmd_norm < 0.1f ? 1.0f : 0.0f));
+        if (rs[T_STAND_STILL] != 0.f) add_term(T_STAND_STILL, P[P_STAND * TILE] * (cmd_lt01 ? 1.0f : 0.0f));
         if (rs[T_STUMBLE] != 0.f) add_term(T_STUMBLE, P[P_STUMBLE * TILE] > 0.0f ? 1.0f : 0.0f);
         if (rs[T_TORQUE_LIMITS] != 0.f) add_term(T_TORQUE_LIMITS, P[P_TQ_LIM * TILE]);
         if (rs[T_TORQUES] != 0.f) add_term(T_TORQUES, P[P_TORQUES * TILE]);
@@ -443,7 +486,7 @@ __global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_co
             if (p.terrain_curriculum) {   // legged_robot.py:463-486
                 const float dist = norm2_rn(sub_rn(R[0], ox), sub_rn(R[1], oy));
                 const bool up = dist > p.half_env_length;
-                const bool down = (dist < mul_rn(mul_rn(cmd_norm, p.max_episode_length_s), 0.5f)) && !up;
+                const bool down = (dist < mul_rn(mul_rn(norm2_rn(c0, c1), p.max_episode_length_s), 0.5f)) && !up;
                 level += (up ? 1 : 0) - (down ? 1 : 0);
                 if (level >= p.max_terrain_level)
                     level = philox::bounded(rng.words(philox::TERRAIN, 0).x, static_cast<uint32_t>(p.max_terrain_level));
@@ -493,7 +536,7 @@ __global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_co
             for (int k = 0; k < 6; ++k) lrv[k] = nr[7 + k];
 #pragma unroll
             for (int k = 0; k < 13; ++k) b.root_states[ge * 13 + k] = nr[k];
-            resample_commands(p, rng, philox::CMD_RESET, c0, c1, c2, c3);
+            resample_commands(p, thr, rng, philox::CMD_RESET, c0, c1, c2, c3);
             *reinterpret_cast<float4*>(s.fat + e * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             ep_out = 0;
             // extras["episode"] statistics (legged_robot.py:175-179): per-CTA partials in shared memory
@@ -627,6 +670,7 @@ __global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_co
     if (nreset > 0 && tid < K) atomicAdd(&b.ws_sums[tid], s.acc[tid]);
     if (p.terrain_curriculum && tid == K) atomicAdd(&b.ws_sums[K], s.acc[K]);
     if (nreset > 0 && tid == K + 1) atomicAdd(&b.ws_sums[K + 1], static_cast<double>(nreset));
+#if !PP_FINALIZE_KERNEL
     __threadfence();
     __syncthreads();
     __shared__ unsigned int s_ticket;
@@ -643,7 +687,36 @@ __global__ void __launch_bounds__(TILE* LPE) post_physics_kernel(const __grid_co
         if (tid < K + 2) b.ws_sums[tid] = 0.0;
         if (tid == 0) *b.ws_counter = 0u;
     }
+#endif
     if (full && tid == 0) bulk_wait_read0();   // shared memory must stay alive until the bulk stores have read it
+}
+
+#if PP_FINALIZE_KERNEL
+// legged_robot.py:175-182: mean over the reset envs / max_episode_length_s; untouched when nothing reset (:156-157)
+__global__ void extras_finalize_kernel(const __grid_constant__ B200LeggedParams p, const __grid_constant__ B200LeggedBuffers b) {
+    const int K = p.num_sum_rows, tid = threadIdx.x;
+    const double cnt = b.ws_sums[K + 1];
+    const double mine = tid < K + 2 ? b.ws_sums[tid] : 0.0;
+    __syncthreads();
+    if (tid < K && cnt > 0.0) b.extras_out[tid] = static_cast<float>(mine / cnt) / p.max_episode_length_s;
+    if (tid == K && cnt > 0.0) b.extras_out[K] = static_cast<float>(mine / static_cast<double>(p.num_envs));
+    if (tid == K + 1) b.extras_out[K + 1] = static_cast<float>(cnt);
+    if (tid < K + 2) b.ws_sums[tid] = 0.0;
+}
+#endif
+
+// largest y with sqrtf(y) <= t  (so sqrtf(x) > t <=> x > y) and smallest y with sqrtf(y) >= t (sqrtf(x) < t <=> x < y)
+static float sq_gt(float t) {
+    float y = t * t;
+    while (sqrtf(y) <= t) y = nextafterf(y, INFINITY);
+    while (sqrtf(y) > t) y = nextafterf(y, -INFINITY);
+    return y;
+}
+static float sq_lt(float t) {
+    float y = t * t;
+    while (sqrtf(y) >= t) y = nextafterf(y, -INFINITY);
+    while (sqrtf(y) < t) y = nextafterf(y, INFINITY);
+    return y;
 }
 
 template <int TILE, bool ROUGH>
@@ -659,8 +732,13 @@ int launch_post_physics(const B200LeggedParams& p, const B200LeggedBuffers& b, u
         configured = smem;
     }
     const int grid = (p.num_envs + TILE - 1) / TILE;
-    post_physics_kernel<TILE, ROUGH><<<grid, TILE * LPE, smem, stream>>>(p, b, step, env_off, do_push);
+    static const SqThr thr = {sq_gt(1.0f), sq_gt(0.1f), sq_gt(0.2f), sq_lt(0.1f)};
+    post_physics_kernel<TILE, ROUGH><<<grid, TILE * LPE, smem, stream>>>(p, b, step, env_off, do_push, thr);
     B200_LAUNCH_CHECK("post_physics");
+#if PP_FINALIZE_KERNEL
+    extras_finalize_kernel<<<1, 32, 0, stream>>>(p, b);
+    B200_LAUNCH_CHECK("extras_finalize");
+#endif
     return B200GYM_OK;
 }
 
@@ -706,6 +784,10 @@ extern "C" int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedB
     if (tile == 32) {
         if (rough) return launch_post_physics<32, true>(*p, *b, step, env_id_offset, do_push, st);
         return launch_post_physics<32, false>(*p, *b, step, env_id_offset, do_push, st);
+    }
+    if (tile == 16) {
+        if (rough) return launch_post_physics<16, true>(*p, *b, step, env_id_offset, do_push, st);
+        return launch_post_physics<16, false>(*p, *b, step, env_id_offset, do_push, st);
     }
     if (rough) return launch_post_physics<64, true>(*p, *b, step, env_id_offset, do_push, st);
     return launch_post_physics<64, false>(*p, *b, step, env_id_offset, do_push, st);
