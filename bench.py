@@ -37,10 +37,12 @@ def parse():
     ap.add_argument("--frames", type=int, default=8, help="frames of the replay tape")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-envs", type=int, default=16384, help="envs of the bounded CPU-baseline sample")
-    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also report 4096..1M envs (extra keys, not the headline)")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager Python API instead of CUDA-graph replays of tape cycles")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 4096..1M envs sweep (extra key, not the headline)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the timings of configs 1, 3, 4, 5 (extra key)")
     return ap.parse_args()
 
 
@@ -122,9 +124,34 @@ def build_env(num_envs, frames, device, rank, copy=False, host=False):
     return env, tape
 
 
-def time_steps(env, actions, steps, warmup, world, device):
+def time_steps(env, actions, steps, warmup, world, device, graphed=None):
+    """Times EXACTLY `steps` env steps.  graphed: GraphedReplay — whole tape cycles are replayed from one CUDA graph,
+    the remainder (steps % F) runs through the eager API at the end."""
     import torch.distributed as dist
     F = len(actions)
+    if graphed is not None:
+        for _ in range((warmup + F - 1) // F):
+            graphed.replay()
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps // F):
+            graphed.replay()
+        for s in range(steps % F):
+            env.step(actions[s])
+        t1.record()
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
     for s in range(warmup):
         env.step(actions[s % F])
     torch.cuda.synchronize(device)
@@ -197,20 +224,20 @@ def e2e_run(num_envs, frames, steps, warmup, device, rank, world):
     return dt, h2d, d2h
 
 
-def cpu_baseline(num_envs, steps):
+def cpu_baseline(num_envs, steps, warmup=3):
     """The oracle port (reference's torch ops, torch.rand like the reference) on the host cores."""
     import legged_case as LC
     torch.set_num_threads(os.cpu_count() or 1)
     case = LC.build_case("flat_pd_upstream", num_envs, frames=4, base_contact_prob=0.002)
     port, phys = LC.make_port(case, rng="torch")
-    for s in range(3):
+    for s in range(warmup):
         port.step(case.tape.actions[s % 4], phys)
     t0 = time.perf_counter()
     n = 0
     while n < steps:
         port.step(case.tape.actions[n % 4], phys)
         n += 1
-        if time.perf_counter() - t0 > 30.0:
+        if time.perf_counter() - t0 > 60.0:
             break
     dt = time.perf_counter() - t0
     return dict(value=num_envs * n / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
@@ -227,7 +254,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_baseline(args.cpu_envs, max(args.steps, 1) if args.steps < 100 else args.cpu_steps)
+        cb = cpu_baseline(args.cpu_envs, max(1, min(args.steps, 200)), warmup=max(3, min(args.warmup, 10)))
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -251,9 +278,14 @@ def main():
     N = args.envs
     env, tape = build_env(N, args.frames, device, rank)
     actions = [tape.actions[f].to(device) for f in range(args.frames)]
-    with ClockSampler(local_rank) as clk:
-        ms = time_steps(env, actions, args.steps, args.warmup, world, device)
+    ms_eager = time_steps(env, actions, args.steps, args.warmup, world, device)
     t_pp, t_pd = kernel_time(env, actions, min(args.steps, 50), device)
+    graphed = None
+    if not args.no_graph:
+        from legged_gym_dev_b200.graphs import GraphedReplay
+        graphed = GraphedReplay(env, actions)
+    with ClockSampler(local_rank) as clk:
+        ms = time_steps(env, actions, args.steps, args.warmup, world, device, graphed=graphed)
     value = world * N * args.steps / (ms * 1e-3)
     ab = algorithmic_bytes(len(env.params.active_terms))
     peak, peak_src = measured_peak()
@@ -270,15 +302,23 @@ def main():
                "steps": esteps, "note": "LeggedRobot.step through the C ABI with pinned-host physics frames + actions in, obs/rew/reset out"}
 
     sweep = None
-    if args.sweep and world == 1:
+    extra = None
+    if world == 1 and not args.no_sweep:
         sweep = {}
         for n in (4096, 16384, 65536, 262144, 1048576):
             e2, tp2 = build_env(n, 4, device, 0)
             a2 = [tp2.actions[f].to(device) for f in range(4)]
             m2 = time_steps(e2, a2, 100, 10, 1, device)
-            sweep[str(n)] = n * 100 / (m2 * 1e-3)
+            tpp, tpd = kernel_time(e2, a2, 30, device)
+            sweep[str(n)] = {"env_steps_per_s": n * 100 / (m2 * 1e-3), "ms_per_step": m2 / 100, "post_physics_ms": tpp,
+                             "post_physics_frac": ab["post_physics"] * n / (tpp * 1e-3) / 1e9 / peak,
+                             "pd_torques_ms": tpd, "pd_torques_frac": ab["pd_torques"] * n / (tpd * 1e-3) / 1e9 / peak}
             del e2, tp2, a2
             torch.cuda.empty_cache()
+    if world == 1 and not args.no_extra:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        extra = bench_configs.run_all(device=device, peak=peak)
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -291,9 +331,12 @@ def main():
                 "config": {"workload": f"anymal_c_flat env.step (4x PD torques + fused post_physics_step), upstream reward table "
                                        f"(SURVEY 8d cfg 2b), {N} envs/GPU, {args.frames}-frame replay tape resident in HBM",
                            "envs_per_gpu": N, "total_envs": world * N, "parallelism": f"env-sharded x{world}, no data-path collective",
+                           "launch": ("eager Python API (5 launches + finaliser per env step)" if graphed is None else
+                                      f"CUDA graph of one {args.frames}-step tape cycle replayed; step counter / RNG event in device memory"),
+                           "eager_ms_per_step": ms_eager / args.steps,
                            "cache": f"inputs larger than L2: {ab['step'] * N / 1e6:.0f} MB touched per step, tape cycles {args.frames} frames"},
                 "gpu_launches": args.steps * (env_launches()),
-                "roofline": {"bound": "hbm", "kernel": "post_physics_kernel<64,false>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "post_physics_kernel<32,false> (+ extras_finalize_kernel)", "achieved": ach, "peak": peak, "unit": "GB/s",
                              "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_env": ab["post_physics"], "avg_launch_ms": t_pp,
                              "pd_torques": {"achieved": ach_pd, "frac": ach_pd / peak, "avg_launch_ms": t_pd,
@@ -305,14 +348,16 @@ def main():
         if cb:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if sweep:
-            line["sweep_env_steps_per_s"] = sweep
+            line["sweep"] = sweep
+        if extra:
+            line["extra_configs"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def env_launches():
-    return 5   # 4 torque launches + 1 fused post-physics launch per env step
+    return 6   # 4 torque launches + fused post-physics + its 1-warp extras finaliser per env step
 
 
 if __name__ == "__main__":

@@ -97,6 +97,10 @@ typedef struct B200LeggedBuffers {
     float* extras_out;           /* [K+2] */
     double* ws_sums;             /* [K+2] workspace, zero-initialised by the caller once */
     uint32_t* ws_counter;        /* [1]   workspace, zero-initialised by the caller once */
+    /* optional device-resident step counter: when non-NULL the kernels read the step (RNG event, push schedule) from it
+       instead of the by-value argument and advance it after every step, which makes the launch sequence of whole env
+       steps CUDA-graph replayable.  It must hold common_step_counter of the NEXT post-physics pass. */
+    uint64_t* step_counter;
 } B200LeggedBuffers;
 
 /* LeggedRobot._compute_torques (legged_robot.py:389-413), optionally fused with the action clip of

@@ -52,7 +52,7 @@ _BUF_FIELDS = ["root_states", "dof_state", "contact_forces", "actions", "torques
                "last_root_vel", "commands", "feet_air_time", "last_contacts", "episode_length_buf", "reset_buf",
                "time_out_buf", "rew_buf", "episode_sums", "obs_buf", "base_lin_vel", "base_ang_vel",
                "projected_gravity", "measured_heights", "height_samples", "env_origins", "terrain_levels",
-               "terrain_types", "terrain_origins", "lstm_h", "lstm_c", "extras_out", "ws_sums", "ws_counter"]
+               "terrain_types", "terrain_origins", "lstm_h", "lstm_c", "extras_out", "ws_sums", "ws_counter", "step_counter"]
 
 
 class LeggedBuffersPOD(C.Structure):

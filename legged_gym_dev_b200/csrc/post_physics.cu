@@ -182,7 +182,7 @@ __device__ __forceinline__ void coop_copy(T* dst, const T* src, int n) {
 }
 
 template <int TILE, bool ROUGH>
-__global__ void __launch_bounds__(TILE* LPE, (PP_MINBLOCKS * TILE * LPE <= 2048 ? PP_MINBLOCKS : 2048 / (TILE * LPE))) post_physics_kernel(const __grid_constant__ B200LeggedParams p,
+__global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) post_physics_kernel(const __grid_constant__ B200LeggedParams p,
                                                                                const __grid_constant__ B200LeggedBuffers b,
                                                                                uint64_t step, long long env_off, int do_push,
                                                                                const SqThr thr) {
@@ -198,10 +198,17 @@ __global__ void __launch_bounds__(TILE* LPE, (PP_MINBLOCKS * TILE * LPE <= 2048 
     if (tid == 0) {
         mbar_init(s.bar, 1);
         fence_mbar_init();
-        *s.nreset = 0;
+        s.nreset[0] = 0;
+        s.nreset[1] = do_push;
+        if (b.step_counter) {   // graph-replayable mode: step and push schedule come from device memory
+            const unsigned long long sc = *b.step_counter;
+            s.nreset[1] = (p.push_robots && p.push_time > 0 && (sc % static_cast<unsigned long long>(p.push_time) == 0)) ? 1 : 0;
+        }
     }
+    if (b.step_counter) step = *b.step_counter;
     if (tid < B200GYM_NUM_REWARD_TERMS + 2) s.acc[tid] = 0.0;
     __syncthreads();
+    do_push = s.nreset[1];
 
     // ---- stage the tile: one bulk copy per tensor -------------------------------------------------
     if (full) {
@@ -702,6 +709,7 @@ __global__ void extras_finalize_kernel(const __grid_constant__ B200LeggedParams 
     if (tid == K && cnt > 0.0) b.extras_out[K] = static_cast<float>(mine / static_cast<double>(p.num_envs));
     if (tid == K + 1) b.extras_out[K + 1] = static_cast<float>(cnt);
     if (tid < K + 2) b.ws_sums[tid] = 0.0;
+    if (tid == 0 && b.step_counter) *b.step_counter += 1;
 }
 #endif
 

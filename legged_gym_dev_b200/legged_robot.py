@@ -172,6 +172,9 @@ class LeggedRobot:
         self._ws_sums = torch.zeros(K + 2, dtype=torch.double, device=self.device)
         self._ws_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         self._pod = _lib.fill_params(p, K, sum_row, zero_lstm_on_reset=self._has_actuator_state())
+        self._ptr_actions, self._ptr_torques = self.actions.data_ptr(), self.torques.data_ptr()
+        self._ptr_last_dof_vel = self.last_dof_vel.data_ptr()
+        self._stream = None
         ep = {"rew_" + n: self._extras_out[i] for i, n in enumerate(p.active_terms)}
         if p.terrain_curriculum:
             ep["terrain_level"] = self._extras_out[K]
@@ -222,20 +225,23 @@ class LeggedRobot:
         _lib.require_cuda(actions, "actions")
         if actions.dtype != torch.float32:
             actions = actions.float()
+        self._stream = torch.cuda.current_stream(self.device).cuda_stream    # looked up once per step
+        ph = self.physics
         for i in range(self.params.decimation):
             # the first evaluation also writes the clipped actions (fuses legged_robot.py:86-87)
             ev = self._event_start()
-            self.torques = self._compute_torques(actions, write_clipped=(i == 0)).view(self.torques.shape)
+            self._compute_torques(actions, write_clipped=(i == 0))
             self._event_end("torques", ev)
-            self.physics.simulate(self.torques)
+            ph.simulate(self.torques)
         self.post_physics_step()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def _compute_torques(self, actions, write_clipped=False):             # legged_robot.py:389-413
-        L, ptr = self.lib, _lib.ptr
-        _lib.check(L.b200gym_pd_torques(self._pod, ptr(actions), ptr(self.actions) if write_clipped else None,
-                                        ptr(self.physics.dof_state), ptr(self.last_dof_vel), ptr(self.torques),
-                                        _lib.stream_ptr(self.device)), "pd_torques")
+        rc = self.lib.b200gym_pd_torques(self._pod, actions.data_ptr(), self._ptr_actions if write_clipped else None,
+                                         self.physics.dof_state.data_ptr(), self._ptr_last_dof_vel, self._ptr_torques,
+                                         self._stream if self._stream is not None else torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "pd_torques")
         return self.torques
 
     def _buffers(self):
@@ -269,10 +275,21 @@ class LeggedRobot:
         self.physics.refresh()
         self.common_step_counter += 1
         ev = self._event_start()
-        _lib.check(self.lib.b200gym_post_physics(self._pod, self._buffers(), self.common_step_counter, self.env_id_offset,
-                                                 _lib.stream_ptr(self.device)), "post_physics")
+        st = self._stream if self._stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.b200gym_post_physics(self._pod, self._buffers(), self.common_step_counter, self.env_id_offset, st)
+        if rc:
+            _lib.check(rc, "post_physics")
         self._event_end("post_physics", ev)
         self.physics.commit_resets(self.reset_buf)
+
+    def use_device_step_counter(self):
+        """Keeps the step counter the kernels see in device memory (advanced by the kernels themselves), so that a
+        sequence of env steps can be captured in a CUDA graph and replayed (legged_gym_dev_b200.graphs)."""
+        if getattr(self, "_step_dev", None) is None:
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._step_dev.fill_(self.common_step_counter + 1)
+        self._buffers().step_counter = self._step_dev.data_ptr()
+        return self._step_dev
 
     def _event_start(self):
         if self._timing is None:
@@ -347,8 +364,10 @@ class Anymal(LeggedRobot):
     def _compute_torques(self, actions, write_clipped=False):             # anymal.py:71-78
         if not self.params.use_actuator_network:
             return super()._compute_torques(actions, write_clipped)
-        L, ptr = self.lib, _lib.ptr
-        _lib.check(L.b200gym_lstm_torques(self._pod, ptr(actions), ptr(self.actions) if write_clipped else None,
-                                          ptr(self.physics.dof_state), ptr(self.sea_hidden_state), ptr(self.sea_cell_state),
-                                          ptr(self.torques), _lib.stream_ptr(self.device)), "lstm_torques")
+        rc = self.lib.b200gym_lstm_torques(self._pod, actions.data_ptr(), self._ptr_actions if write_clipped else None,
+                                           self.physics.dof_state.data_ptr(), self.sea_hidden_state.data_ptr(),
+                                           self.sea_cell_state.data_ptr(), self._ptr_torques,
+                                           self._stream if self._stream is not None else torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "lstm_torques")
         return self.torques

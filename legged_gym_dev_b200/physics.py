@@ -31,31 +31,35 @@ class ReplayPhysics:
         self.num_envs, self.frames, self.decimation = tape.num_envs, tape.frames, tape.decimation
         self.frame = 0
         self.sub = 0
+        # per-frame views are built once: indexing a tensor costs microseconds of Python per call
+        self._root_v = [self.root_frames[f] for f in range(self.frames)]
+        self._contact_v = [self.contact_frames[f] for f in range(self.frames)]
+        self._dof_v = [[self.dof_frames[f, j] for j in range(self.decimation)] for f in range(self.frames)]
         if copy:
             self.root_states = self.root_frames[0].clone()
             self.dof_state = self.dof_frames[0, 0].clone()
             self.contact_forces = self.contact_frames[0].clone()
         else:
-            self.root_states = self.root_frames[0]
-            self.dof_state = self.dof_frames[0, 0]
-            self.contact_forces = self.contact_frames[0]
+            self.root_states = self._root_v[0]
+            self.dof_state = self._dof_v[0][0]
+            self.contact_forces = self._contact_v[0]
 
     def simulate(self, torques):
-        f = self.frame % self.frames
+        v = self._dof_v[self.frame % self.frames][self.sub]
         if self.copy:
-            self.dof_state.copy_(self.dof_frames[f, self.sub])
+            self.dof_state.copy_(v)
         else:
-            self.dof_state = self.dof_frames[f, self.sub]
+            self.dof_state = v
         self.sub += 1
 
     def refresh(self):
         f = self.frame % self.frames
         if self.copy:
-            self.root_states.copy_(self.root_frames[f])
-            self.contact_forces.copy_(self.contact_frames[f])
+            self.root_states.copy_(self._root_v[f])
+            self.contact_forces.copy_(self._contact_v[f])
         else:
-            self.root_states = self.root_frames[f]
-            self.contact_forces = self.contact_frames[f]
+            self.root_states = self._root_v[f]
+            self.contact_forces = self._contact_v[f]
         self.frame += 1
         self.sub = 0
 

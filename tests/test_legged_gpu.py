@@ -97,3 +97,31 @@ def test_errors_are_loud():
     env._pod.control_type = 7
     with pytest.raises(RuntimeError, match="Unknown controller type"):
         env.step(torch.zeros(64, 12, device="cuda"))
+
+
+def test_graph_replay_matches_eager():
+    """CUDA-graph replay of tape cycles (device-resident step counter) == the eager API, bit for bit, incl. fresh RNG."""
+    from legged_gym_dev_b200.graphs import GraphedReplay
+    F = 4
+    case = LC.build_case("flat_pd_upstream", 1024, frames=F)
+    a = LC.make_fused(case, copy=False)
+    case_b = LC.build_case("flat_pd_upstream", 1024, frames=F)
+    b = LC.make_fused(case_b, copy=False)
+    acts_a = [case.tape.actions[f].cuda() for f in range(F)]
+    acts_b = [case_b.tape.actions[f].cuda() for f in range(F)]
+    g = GraphedReplay(a, acts_a)           # runs one warm-up cycle eagerly
+    for f in range(F):
+        b.step(acts_b[f])
+    obs_prev = None
+    for cycle in range(3):
+        g.replay()
+        for f in range(F):
+            b.step(acts_b[f])
+        torch.cuda.synchronize()
+        assert a.common_step_counter == b.common_step_counter
+        for k in ("obs_buf", "rew_buf", "reset_buf", "commands", "episode_length_buf", "feet_air_time", "last_dof_vel"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), f"cycle {cycle}: {k}"
+        assert torch.equal(a._sums, b._sums)
+        if obs_prev is not None:
+            assert not torch.equal(obs_prev, a.obs_buf), "replays must draw fresh noise"
+        obs_prev = a.obs_buf.clone()

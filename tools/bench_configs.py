@@ -1,0 +1,189 @@
+"""Timings of the other BASELINE.json configs (1, 3, 4, 5) — the headline bench (config 2) lives in bench.py.
+Each function returns a small dict; bench.py attaches them under "extra_configs".  CUDA-event timing after warm-up."""
+import os
+import sys
+import time
+from types import SimpleNamespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+PEAK = None
+
+
+def _events():
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def rough_lstm(num_envs=16384, steps=50, warmup=5, device="cuda", peak=6535.7):
+    """cfg 3: anymal_c_rough, LSTM actuator net x4 + 187-point height scan + 235 observations."""
+    import legged_case as LC
+    from legged_gym_dev_b200 import synthetic as S
+    case = LC.build_case("rough_pd_shipped", 64)      # for cfg + terrain tables only
+    cfg = case.cfg
+    cfg.control.use_actuator_network = True
+    cfg.env.num_envs = num_envs
+    F = 4
+    tape = S.make_state_tape(num_envs, frames=F, seed=7, rough=True, device=device)
+    g = torch.Generator().manual_seed(3)
+    levels = torch.randint(0, cfg.terrain.max_init_terrain_level + 1, (num_envs,), generator=g)
+    types = torch.div(torch.arange(num_envs), (num_envs / cfg.terrain.num_cols), rounding_mode="floor").to(torch.long)
+    to = case.terrain["terrain_origins"]
+    terrain = dict(height_samples=case.terrain["height_samples"], terrain_origins=to, terrain_levels=levels, terrain_types=types,
+                   env_origins=to[levels, types].clone())
+    from legged_gym_dev_b200.legged_robot import Anymal
+    from legged_gym_dev_b200.physics import ReplayPhysics
+    env = Anymal(cfg, SimpleNamespace(dt=cfg.sim.dt), None, device, True, physics=ReplayPhysics(tape, device=device, copy=False),
+                 asset=LC.dof_limits(), seed=0, terrain=terrain)
+    env.episode_length_buf = S.make_episode_lengths(num_envs, seed=1, device=device)
+    acts = [tape.actions[f] for f in range(F)]
+    for s in range(warmup):
+        env.step(acts[s % F])
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    for s in range(steps):
+        env.step(acts[s % F])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    env._timing = []
+    for s in range(20):
+        env.step(acts[s % F])
+    torch.cuda.synchronize()
+    pp = [x.elapsed_time(y) for k, x, y in env._timing if k == "post_physics"]
+    tq = [x.elapsed_time(y) for k, x, y in env._timing if k == "torques"]
+    t_pp, t_tq = sum(pp) / len(pp), sum(tq) / len(tq)
+    K = len(env.params.active_terms)
+    pp_bytes = 986 + 8 * K + 748 + 748
+    return dict(config="anymal_c_rough: 4x LSTM actuator torques + post_physics with 187-pt height scan, 235 obs",
+                num_envs=num_envs, ms_per_step=ms, env_steps_per_s=num_envs / (ms * 1e-3),
+                lstm_torques=dict(avg_launch_ms=t_tq, algorithmic_bytes_per_env=3264 + 48,
+                                  achieved_gbs=(3264 + 48) * num_envs / (t_tq * 1e-3) / 1e9,
+                                  frac=(3264 + 48) * num_envs / (t_tq * 1e-3) / 1e9 / peak),
+                post_physics_rough=dict(avg_launch_ms=t_pp, algorithmic_bytes_per_env=pp_bytes,
+                                        achieved_gbs=pp_bytes * num_envs / (t_pp * 1e-3) / 1e9,
+                                        frac=pp_bytes * num_envs / (t_pp * 1e-3) / 1e9 / peak))
+
+
+def rom_per_call(num_envs=4096, loop_steps=1000, device="cuda", cpu=True):
+    """cfg 1: CustomSim.step + DoubleSingleTracking, 4096 envs x 1000 loop steps, call-per-step API; CPU port beside it."""
+    from legged_gym_dev_b200 import configs
+    from legged_gym_dev_b200.rom import CustomSim, DoubleSingleTracking
+    env = CustomSim(configs.double_single_int_cfg(num_envs, seed=0), device=device)
+    pol = DoubleSingleTracking(10, 10, env.model.clip_v_z)
+    env.reset()
+    obs = env.get_observations()
+    for _ in range(20):
+        obs, _, _, _, _ = env.step(pol(obs))
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    for _ in range(loop_steps):
+        obs, _, _, _, _ = env.step(pol(obs))
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    out = dict(config="DoubleInt2D model / SingleInt2D rom / DoubleSingleTracking, call-per-step API", num_envs=num_envs,
+               loop_steps=loop_steps, ms_total=ms, env_steps_per_s=num_envs * loop_steps / (ms * 1e-3),
+               note="2 launches per loop step: launch-latency bound at this size (SURVEY H5)")
+    if cpu:
+        from oracle.port_rom import RomPort, rom_params
+        torch.set_num_threads(os.cpu_count() or 1)
+        port = RomPort(rom_params(num_envs, seed=0), rng="torch")
+        o, _ = port.reset()
+        t0 = time.perf_counter()
+        for _ in range(loop_steps):
+            o, _ = port.step(port.policy(o))
+        dt = time.perf_counter() - t0
+        out["cpu_port"] = dict(env_steps_per_s=num_envs * loop_steps / dt, seconds=dt, cores=torch.get_num_threads())
+    return out
+
+
+def rom_rollout(num_envs=1 << 20, T=200, device="cuda", peak=6535.7, debug=False):
+    """cfg 4: one data-collection epoch (reset + T ROM steps = 2T loop steps) as ONE persistent launch."""
+    from legged_gym_dev_b200 import configs
+    from legged_gym_dev_b200.rom import CustomSim
+    env = CustomSim(configs.double_single_int_cfg(num_envs, seed=0), device=device)
+    obs = torch.zeros(num_envs, 8, device=device)
+    env.collect_epoch(obs, 8)
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    log = env.collect_epoch(obs, T, save_debugging_data=debug)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    loop_steps = 2 * T + 11
+    log_bytes = num_envs * ((T + 1) * 16 + T * 9 + ((T + 1) * 16 if debug else 0))
+    return dict(config="ROM tube data collection epoch, persistent rollout kernel", num_envs=num_envs, rom_steps=T,
+                ms_epoch=ms, env_loop_steps_per_s=num_envs * loop_steps / (ms * 1e-3), log_gb=log_bytes / 1e9,
+                log_gbs=log_bytes / (ms * 1e-3) / 1e9, frac_hbm=log_bytes / (ms * 1e-3) / 1e9 / peak,
+                note="ALU-bound (sinf, IEEE division, Philox); HBM traffic is only the materialised logs")
+
+
+def gae_update(num_envs=4096, T=24, device="cuda", peak=6535.7):
+    """cfg 5: GAE + advantage normalisation, and one PPO update iteration (5 epochs x 4 minibatches, flat nets)."""
+    from legged_gym_dev_b200.ppo import ActorCritic, PPO
+    ac = ActorCritic(48, 48, 12, actor_hidden_dims=[128, 64, 32], critic_hidden_dims=[128, 64, 32], init_noise_std=1.0)
+    alg = PPO(ac, num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
+              entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
+              desired_kl=0.01, device=device)
+    alg.init_storage(num_envs, T, [48], [None], [12])
+    st = alg.storage
+    g = torch.Generator(device=device).manual_seed(1)
+    st.observations.normal_(generator=g)
+    st.actions.normal_(generator=g)
+    st.mu.normal_(generator=g)
+    st.sigma.fill_(1.0)
+    st.rewards.normal_(0.02, 0.05, generator=g)
+    st.values.normal_(0.5, 0.3, generator=g)
+    st.actions_log_prob.normal_(-17.0, 2.0, generator=g)
+    st.dones.copy_(torch.rand(T, num_envs, 1, device=device, generator=g) < 0.005)
+    last = torch.randn(num_envs, 1, device=device, generator=g)
+    for _ in range(3):
+        st.compute_returns(last, 0.99, 0.95)
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    reps = 50
+    for _ in range(reps):
+        st.compute_returns(last, 0.99, 0.95)
+    b.record()
+    torch.cuda.synchronize()
+    ms_gae = a.elapsed_time(b) / reps
+    alg.update()
+    st.step = T
+    torch.cuda.synchronize()
+    a.record()
+    alg.update()
+    b.record()
+    torch.cuda.synchronize()
+    ms_upd = a.elapsed_time(b)
+    return dict(config="rollout storage GAE + normalisation; PPO update 5 epochs x 4 minibatches (nets 48-128-64-32)", num_envs=num_envs,
+                T=T, gae_ms=ms_gae, gae_env_steps_per_s=num_envs * T / (ms_gae * 1e-3),
+                gae_gbs=604 * num_envs / (ms_gae * 1e-3) / 1e9, gae_frac=604 * num_envs / (ms_gae * 1e-3) / 1e9 / peak,
+                update_ms=ms_upd, update_samples_per_s=5 * T * num_envs / (ms_upd * 1e-3),
+                note="GAE at 4096 envs moves 2.5 MB: launch-latency bound; MLP contractions are cuBLAS (tcgen05 kernel is next)")
+
+
+def run_all(device="cuda", peak=6535.7, quick=False):
+    out = {}
+    for name, fn, kw in (("cfg1_rom_per_call", rom_per_call, dict(device=device, loop_steps=200 if quick else 1000)),
+                         ("cfg3_rough_lstm", rough_lstm, dict(device=device, peak=peak)),
+                         ("cfg4_rom_rollout", rom_rollout, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20))),
+                         ("cfg5_gae_update", gae_update, dict(device=device, peak=peak))):
+        try:
+            out[name] = fn(**kw)
+        except Exception as e:   # an extra must never take the headline line down
+            out[name] = dict(error=f"{type(e).__name__}: {e}")
+        torch.cuda.empty_cache()
+    return out
+
+
+if __name__ == "__main__":
+    import json
+    print(json.dumps(run_all(quick="--quick" in sys.argv), indent=1))
