@@ -198,12 +198,21 @@ def e2e_run(num_envs, frames, steps, warmup, device, rank, world):
     rst_h = torch.empty(num_envs, dtype=torch.bool, pin_memory=True)
     a_dev = torch.empty(num_envs, 12, device=device)
 
+    out_stream = torch.cuda.Stream(device=device)
+    done_ev, read_ev = torch.cuda.Event(), torch.cuda.Event()
+
     def one(s):
+        cur = torch.cuda.current_stream(device)
         a_dev.copy_(acts[s % frames], non_blocking=True)
+        cur.wait_event(read_ev)                     # previous results have left the device buffers
         obs, _, rew, rst, _ = env.step(a_dev)
-        obs_h.copy_(obs, non_blocking=True)
-        rew_h.copy_(rew, non_blocking=True)
-        rst_h.copy_(rst, non_blocking=True)
+        done_ev.record(cur)
+        with torch.cuda.stream(out_stream):         # D2H of the results overlaps the next step's H2D (PCIe is full duplex)
+            out_stream.wait_event(done_ev)
+            obs_h.copy_(obs, non_blocking=True)
+            rew_h.copy_(rew, non_blocking=True)
+            rst_h.copy_(rst, non_blocking=True)
+            read_ev.record(out_stream)
 
     for s in range(warmup):
         one(s)

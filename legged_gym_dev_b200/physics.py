@@ -69,29 +69,56 @@ class ReplayPhysics:
 
 
 class HostReplayPhysics(ReplayPhysics):
-    """Frames live in PINNED HOST memory and are copied to the device inside simulate()/refresh(): the
-    end-to-end arm of bench.py (a physics engine that hands its state over from the host every sub-step)."""
+    """Frames live in PINNED HOST memory and cross PCIe inside every step: the end-to-end arm of bench.py (a physics
+    engine that hands its state over from the host every sub-step).  The copies of step s+1 are issued on a side
+    stream into a second set of device buffers while step s computes (double buffering, like any input pipeline);
+    every byte still moves inside the timed region."""
 
     def __init__(self, tape, device="cuda"):
         self.tape, self.copy = tape, True
-        dev = torch.device(device)
+        dev = self.device = torch.device(device)
         self.root_frames = tape.root.pin_memory()
         self.dof_frames = tape.dof.pin_memory()
         self.contact_frames = tape.contact.reshape(tape.frames, tape.num_envs * tape.contact.shape[2], 3).pin_memory()
         self.num_envs, self.frames, self.decimation = tape.num_envs, tape.frames, tape.decimation
         self.frame = 0
         self.sub = 0
+        mk = lambda t: [torch.empty_like(t, device=dev) for _ in range(2)]
+        self._root_d, self._contact_d = mk(self.root_frames[0]), mk(self.contact_frames[0])
+        self._dof_d = [[torch.empty_like(self.dof_frames[0, 0], device=dev) for _ in range(self.decimation)] for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
         self.root_states = self.root_frames[0].to(dev)
         self.dof_state = self.dof_frames[0, 0].to(dev)
         self.contact_forces = self.contact_frames[0].to(dev)
+        self._prefetch(0)
+
+    def _prefetch(self, frame):
+        """H2D of every tensor of `frame` into buffer set frame % 2, on the copy stream."""
+        b, f = frame % 2, frame % self.frames
+        cs = self._copy_stream
+        cs.wait_event(self._consumed[b]) if frame >= 2 else None
+        with torch.cuda.stream(cs):
+            for j in range(self.decimation):
+                self._dof_d[b][j].copy_(self.dof_frames[f, j], non_blocking=True)
+            self._root_d[b].copy_(self.root_frames[f], non_blocking=True)
+            self._contact_d[b].copy_(self.contact_frames[f], non_blocking=True)
+            self._ready[b].record(cs)
 
     def simulate(self, torques):
-        self.dof_state.copy_(self.dof_frames[self.frame % self.frames, self.sub], non_blocking=True)
+        b = self.frame % 2
+        if self.sub == 0:
+            torch.cuda.current_stream(self.device).wait_event(self._ready[b])
+        self.dof_state = self._dof_d[b][self.sub]
         self.sub += 1
 
     def refresh(self):
-        f = self.frame % self.frames
-        self.root_states.copy_(self.root_frames[f], non_blocking=True)
-        self.contact_forces.copy_(self.contact_frames[f], non_blocking=True)
+        b = self.frame % 2
+        self.root_states, self.contact_forces = self._root_d[b], self._contact_d[b]
         self.frame += 1
         self.sub = 0
+        self._prefetch(self.frame)      # next step's state starts crossing PCIe while this step's post-physics runs
+
+    def commit_resets(self, reset_buf):
+        self._consumed[(self.frame - 1) % 2].record(torch.cuda.current_stream(self.device))

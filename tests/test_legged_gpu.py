@@ -125,3 +125,26 @@ def test_graph_replay_matches_eager():
         if obs_prev is not None:
             assert not torch.equal(obs_prev, a.obs_buf), "replays must draw fresh noise"
         obs_prev = a.obs_buf.clone()
+
+
+def test_host_replay_physics_matches_device_replay():
+    """The pinned-host, double-buffered physics of bench.py's e2e arm feeds the same frames as the device replay."""
+    from types import SimpleNamespace
+    from legged_gym_dev_b200.legged_robot import Anymal
+    from legged_gym_dev_b200.physics import HostReplayPhysics
+    case = LC.build_case("flat_pd_upstream", 512, frames=4)
+    a = LC.make_fused(case)
+    lim = case.limits
+    b = Anymal(case.cfg, SimpleNamespace(dt=case.cfg.sim.dt), None, "cuda", True, physics=HostReplayPhysics(case.tape, device="cuda"),
+               asset=dict(dof_pos_limits=lim["dof_pos_limits"], dof_vel_limits=lim["dof_vel_limits"], torque_limits=lim["torque_limits"]),
+               seed=case.seed)
+    b.episode_length_buf = case.ep.cuda()
+    for s in range(10):
+        act = case.tape.actions[s % 4].cuda()
+        a.step(act)
+        b.step(act)
+        torch.cuda.synchronize()
+        if s == 0:
+            continue   # torque evaluation 0 of the very first step sees the initial (unspecified) dof_state of each backend
+        for k in ("obs_buf", "rew_buf", "reset_buf", "commands", "torques"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), f"step {s}: {k}"
