@@ -63,6 +63,16 @@ def algorithmic_bytes(num_sum_rows, num_bodies=17):
     return dict(post_physics=post, pd_torques=pd, step=96 + 4 * pd + post)
 
 
+def measured_traffic(num_envs):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, scaled per env (None if absent)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)["post_physics_kernel<32,false>"]
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["envs"] * num_envs
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -346,7 +356,9 @@ def main():
                            "cache": f"inputs larger than L2: {ab['step'] * N / 1e6:.0f} MB touched per step, tape cycles {args.frames} frames"},
                 "gpu_launches": args.steps * (env_launches()),
                 "roofline": {"bound": "hbm", "kernel": "post_physics_kernel<32,false> (+ extras_finalize_kernel)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                             "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": ach / peak, "traffic": measured_traffic(N),
+                             "traffic_note": "ncu dram read+write bytes of one launch at 1 048 576 envs, scaled per env (profiles/r1_traffic.json)",
+                             "peak_source": peak_src,
                              "algorithmic_bytes_per_env": ab["post_physics"], "avg_launch_ms": t_pp,
                              "pd_torques": {"achieved": ach_pd, "frac": ach_pd / peak, "avg_launch_ms": t_pd,
                                             "algorithmic_bytes_per_env": ab["pd_torques"]},

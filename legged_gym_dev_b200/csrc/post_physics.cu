@@ -72,6 +72,14 @@ __device__ __forceinline__ float norm3_rn(float x, float y, float z) {
 __device__ __forceinline__ float sq2_rn(float x, float y) { return add_rn(mul_rn(x, x), mul_rn(y, y)); }
 __device__ __forceinline__ float sq3_rn(float x, float y, float z) { return add_rn(add_rn(mul_rn(x, x), mul_rn(y, y)), mul_rn(z, z)); }
 
+// Correctly rounded x / d for a loop-invariant divisor with rcp = RN(1/d): q0 = RN(x*rcp); r = x - q0*d (exact, FMA);
+// q = RN(q0 + r*rcp) (Markstein).  Three instructions instead of the ~15 of the general IEEE division; the height-cell
+// index depends on the exact quotient, the parity tests compare the cells bit for bit.
+__device__ __forceinline__ float div_const_rn(float x, float d, float rcp) {
+    const float q0 = mul_rn(x, rcp);
+    return fmaf(fmaf(-q0, d, x), rcp, q0);
+}
+
 __device__ __forceinline__ float wrap_to_pi(float a) {
     // legged_gym/utils/math.py:45-48 on fp32 tensors: python-style remainder by fl32(2*pi), then -2*pi where > fl32(pi)
     const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
@@ -129,6 +137,7 @@ struct TileSmem {
     uint8_t *reset, *tout;
     int16_t* hraw;
     float *bh, *zpost, *stage;
+    float2* pts;
     double* acc;
     int* nreset;
     size_t bytes;
@@ -168,9 +177,11 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
         s.bh = c.take<float>(TILE);
         s.zpost = c.take<float>(TILE);
         s.stage = c.take<float>((TILE * LPE / 32) * HPAD);
+        s.pts = c.take<float2>(HPAD);
     } else {
         s.hraw = nullptr;
         s.bh = s.zpost = s.stage = nullptr;
+        s.pts = nullptr;
     }
     s.bytes = c.off;
     return s;
@@ -207,6 +218,9 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
     }
     if (b.step_counter) step = *b.step_counter;
     if (tid < B200GYM_NUM_REWARD_TERMS + 2) s.acc[tid] = 0.0;
+    if (ROUGH) {   // base-frame sample points (legged_robot.py:861-875), tabulated once per CTA
+        for (int pt = tid; pt < p.num_heights; pt += TILE * LPE) s.pts[pt] = make_float2(p.points_x[pt / p.n_py], p.points_y[pt % p.n_py]);
+    }
     __syncthreads();
     do_push = s.nreset[1];
 
@@ -250,32 +264,49 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
     if (ROUGH) {
         const int H = p.num_heights;
         const int rows = p.terrain_rows, cols = p.terrain_cols;
+        const float inv_hs = div_rn(1.0f, p.horizontal_scale);
         for (int e = warp; e < nvalid; e += TILE * LPE / 32) {
             const float* R = s.root + e * 13;
             // quat_apply_yaw: zero x,y, renormalise, rotate — un-fused fp32 ops, the cell index depends on them (H2)
             const float nq = fmaxf(sqrtf(add_rn(mul_rn(R[5], R[5]), mul_rn(R[6], R[6]))), 1e-9f);
             const float qz = div_rn(R[5], nq), qw = div_rn(R[6], nq);
             float part = 0.0f;
-            for (int pt = lane; pt < H; pt += 32) {
-                int raw = 0;
-                if (!p.mesh_plane) {
-                    const float hx = p.points_x[pt / p.n_py], hy = p.points_y[pt % p.n_py];
+            // all (<= 6 x 32) sample points of the env are indexed first and their 3 x 6 gathers issued together, so the
+            // L2 latency of the height field is paid once per env, not once per point
+            const int16_t* hs[HPAD / 32];
+#pragma unroll
+            for (int it = 0; it < HPAD / 32; ++it) {
+                const int pt = lane + 32 * it;
+                hs[it] = nullptr;
+                if (pt < H && !p.mesh_plane) {
+                    const float2 hp = s.pts[pt];
+                    const float hx = hp.x, hy = hp.y;
                     const float tx = mul_rn(-mul_rn(qz, hy), 2.0f), ty = mul_rn(mul_rn(qz, hx), 2.0f);
                     float wx = add_rn(add_rn(hx, mul_rn(qw, tx)), -mul_rn(qz, ty));
                     float wy = add_rn(add_rn(hy, mul_rn(qw, ty)), mul_rn(qz, tx));
-                    wx = div_rn(add_rn(add_rn(wx, R[0]), p.border_size), p.horizontal_scale);
-                    wy = div_rn(add_rn(add_rn(wy, R[1]), p.border_size), p.horizontal_scale);
-                    long long ix = static_cast<long long>(wx), iy = static_cast<long long>(wy);
-                    ix = ix < 0 ? 0 : (ix > rows - 2 ? rows - 2 : ix);
-                    iy = iy < 0 ? 0 : (iy > cols - 2 ? cols - 2 : iy);
-                    const int16_t* hs = b.height_samples + ix * cols + iy;
-                    const int h1 = __ldg(hs), h2 = __ldg(hs + cols), h3 = __ldg(hs + 1);
-                    raw = min(min(h1, h2), h3);
+                    wx = div_const_rn(add_rn(add_rn(wx, R[0]), p.border_size), p.horizontal_scale, inv_hs);
+                    wy = div_const_rn(add_rn(add_rn(wy, R[1]), p.border_size), p.horizontal_scale, inv_hs);
+                    // .long() truncation + clip (legged_robot.py:903-907); saturating conversion keeps huge values clipped
+                    const int ix = min(max(__float2int_rz(wx), 0), rows - 2), iy = min(max(__float2int_rz(wy), 0), cols - 2);
+                    hs[it] = b.height_samples + ix * cols + iy;
                 }
-                s.hraw[e * HPAD + pt] = static_cast<int16_t>(raw);
-                const float mh = mul_rn(static_cast<float>(raw), p.vertical_scale);
-                b.measured_heights[static_cast<size_t>(tile0 + e) * H + pt] = mh;
-                part += R[2] - mh;
+            }
+            int h1[HPAD / 32], h2[HPAD / 32], h3[HPAD / 32];
+#pragma unroll
+            for (int it = 0; it < HPAD / 32; ++it) {
+                h1[it] = h2[it] = h3[it] = 0;
+                if (hs[it]) h1[it] = __ldg(hs[it]), h2[it] = __ldg(hs[it] + cols), h3[it] = __ldg(hs[it] + 1);
+            }
+#pragma unroll
+            for (int it = 0; it < HPAD / 32; ++it) {
+                const int pt = lane + 32 * it;
+                if (pt < H) {
+                    const int raw = min(min(h1[it], h2[it]), h3[it]);
+                    s.hraw[e * HPAD + pt] = static_cast<int16_t>(raw);
+                    const float mh = mul_rn(static_cast<float>(raw), p.vertical_scale);
+                    b.measured_heights[static_cast<size_t>(tile0 + e) * H + pt] = mh;
+                    part += R[2] - mh;
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);

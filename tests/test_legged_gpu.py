@@ -148,3 +148,25 @@ def test_host_replay_physics_matches_device_replay():
             continue   # torque evaluation 0 of the very first step sees the initial (unspecified) dof_state of each backend
         for k in ("obs_buf", "rew_buf", "reset_buf", "commands", "torques"):
             assert torch.equal(getattr(a, k), getattr(b, k)), f"step {s}: {k}"
+
+
+def test_height_cells_exact_at_scale():
+    """3.7 M sample points: the truncated cell index (un-fused fp32 chain + exact division by horizontal_scale,
+    SURVEY.md fact 10) must agree with the reference arithmetic for every point."""
+    N = 20000
+    case = LC.build_case("rough_pd_shipped", N, frames=2)
+    # put a share of the robots exactly on cell boundaries and outside the field (clip path)
+    r = case.tape.root
+    r[:, : N // 4, 0] = torch.round(r[:, : N // 4, 0] * 10) / 10
+    r[:, N // 4: N // 2, 1] = torch.round(r[:, N // 4: N // 2, 1] * 10) / 10
+    r[:, -50:, 0] = -40.0
+    r[:, -100:-50, 1] = 400.0
+    port, phys = LC.make_port(case)
+    env = LC.make_fused(case)
+    for s in range(2):
+        a = case.tape.actions[s]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        got, want = env.measured_heights.cpu(), port.measured_heights
+        bad = (got != want)
+        assert not bad.any(), f"step {s}: {int(bad.sum())} of {bad.numel()} height samples differ"

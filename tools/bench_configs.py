@@ -174,6 +174,7 @@ def run_all(device="cuda", peak=6535.7, quick=False):
     out = {}
     for name, fn, kw in (("cfg1_rom_per_call", rom_per_call, dict(device=device, loop_steps=200 if quick else 1000)),
                          ("cfg3_rough_lstm", rough_lstm, dict(device=device, peak=peak)),
+                         ("cfg3_rough_lstm_262144", rough_lstm, dict(device=device, peak=peak, num_envs=16384 if quick else 262144, steps=20)),
                          ("cfg4_rom_rollout", rom_rollout, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20))),
                          ("cfg5_gae_update", gae_update, dict(device=device, peak=peak))):
         try:
