@@ -224,6 +224,18 @@ int b200gym_clip_adam(float* param, const float* grad, float* exp_avg, float* ex
  * lr *= 1.5 if 0 < kl_mean < desired_kl/2 (cap 1e-2).  lr lives on the device, so no host sync per minibatch. */
 int b200gym_adaptive_lr(const double* kl_sum, double count, float desired_kl, float* lr, void* stream);
 
+/* ActorCritic MLP forward (rsl_rl/modules/actor_critic.py: Linear + ELU stack, last layer linear) on the tcgen05 tensor
+ * cores (kind::tf32, fp32 accumulation in TMEM), one launch for the whole stack.  dims[0..num_layers] are the PADDED
+ * layer widths (K %% 8 == 0, N %% 16 == 0, N <= 256); wpacked holds, layer after layer, W_l [N_l x K_l] as
+ * [K_l/4][N_l][4] fp32 (zero padded); bias holds the padded biases back to back.  x: [batch, in_dim] with row stride
+ * in_stride (floats); out: [batch, out_dim] contiguous.  The padded weights must fit in shared memory (flat nets do). */
+#define B200GYM_MLP_MAX_LAYERS 6
+typedef struct B200MlpParams {
+    int32_t batch, num_layers, in_dim, in_stride, out_dim, pad;
+    int32_t dims[B200GYM_MLP_MAX_LAYERS + 1];
+} B200MlpParams;
+int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const float* wpacked, const float* bias, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

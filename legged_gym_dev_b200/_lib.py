@@ -81,6 +81,11 @@ class RomStatePOD(C.Structure):
     _fields_ = [(n, vp) for n in _ROM_FIELDS]
 
 
+class MlpParamsPOD(C.Structure):
+    _fields_ = [("batch", i32), ("num_layers", i32), ("in_dim", i32), ("in_stride", i32), ("out_dim", i32), ("pad", i32),
+                ("dims", i32 * 7)]
+
+
 class PpoLossParamsPOD(C.Structure):
     _fields_ = [("batch", i32), ("num_actions", i32), ("use_clipped_value_loss", i32), ("pad", i32),
                 ("clip_param", f32), ("value_loss_coef", f32), ("entropy_coef", f32), ("inv_global_batch", f32)]
@@ -128,7 +133,9 @@ def lib():
     for name in ("b200gym_gae_returns", "b200gym_adv_normalize", "b200gym_gather_rows", "b200gym_ppo_loss", "b200gym_grad_sumsq",
                  "b200gym_clip_adam", "b200gym_adaptive_lr"):
         getattr(L, name).restype = C.c_int
-    for name, cls in (("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
+    L.b200gym_mlp_forward.argtypes = [C.POINTER(MlpParamsPOD), vp, vp, vp, vp, vp]
+    L.b200gym_mlp_forward.restype = C.c_int
+    for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
                       ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD)):
         n = L.b200gym_sizeof(name.encode())
         if n != C.sizeof(cls):

@@ -22,6 +22,7 @@ int b200gym_sizeof(const char* name) {
     if (!name) return -1;
     if (!strcmp(name, "B200LeggedParams")) return (int)sizeof(B200LeggedParams);
     if (!strcmp(name, "B200LeggedBuffers")) return (int)sizeof(B200LeggedBuffers);
+    if (!strcmp(name, "B200MlpParams")) return (int)sizeof(B200MlpParams);
     if (!strcmp(name, "B200PpoLossParams")) return (int)sizeof(B200PpoLossParams);
     if (!strcmp(name, "B200RomParams")) return (int)sizeof(B200RomParams);
     if (!strcmp(name, "B200RomState")) return (int)sizeof(B200RomState);

@@ -1,0 +1,200 @@
+// mlp_forward_kernel — the policy / critic MLP of rsl_rl's ActorCritic (Linear+ELU stack) as ONE
+// launch on the 5th-generation tensor cores: tcgen05.mma (kind::tf32, M=128 rows per CTA tile, fp32 accumulators in
+// TMEM), operands in shared memory in the canonical K-major no-swizzle UMMA layout, bias + ELU epilogue straight out
+// of TMEM (tcgen05.ld), activations of layer l written back to shared memory as the A operand of layer l+1.  The
+// whole weight set of the flat nets (48-128-64-32-12: 67 KB in fp32) stays resident in shared memory; CTAs are
+// persistent over 128-row tiles.  Not under the 1e-5 contract (SURVEY.md §8d cfg 5: TF32 allowed for G4).
+//
+// Shared-memory operand layout (both A [rows x K] and B = W_l [N x K], K-major): 16-byte chunks of 4 consecutive k,
+// chunk-major:  byte(r, k) = (k/4) * R*16 + r*16 + (k%4)*4,  R = rows of the operand.  In UMMA terms the 8x16B core
+// matrices are contiguous (128 B), SBO (next 8 rows) = 128 B, LBO (next k-chunk) = R*16 B.
+#include "common.cuh"
+#include "../../include/b200gym.h"
+
+namespace {
+
+constexpr int TM = 128;   // rows (samples) per tile = UMMA M = TMEM lanes
+
+__device__ __forceinline__ uint64_t umma_desc(const void* smem, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout NONE [61,64)
+    return (static_cast<uint64_t>(smem_u32(smem) >> 4) & 0x3FFFull) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
+    // cute::UMMA::InstrDescriptor: c_format F32=1 [4,6), a/b_format TF32=2 [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(TM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(TM, 1) mlp_forward_kernel(const __grid_constant__ B200MlpParams p, const float* __restrict__ x,
+                                                            const float* __restrict__ wpacked, const float* __restrict__ bias,
+                                                            float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int L = p.num_layers, tid = threadIdx.x, warp = tid >> 5;
+    int kmax = 0, wtot = 0, btot = 0, nmax = 0;
+    for (int l = 0; l < L; ++l) {
+        kmax = max(kmax, p.dims[l]);
+        nmax = max(nmax, p.dims[l + 1]);
+        wtot += p.dims[l] * p.dims[l + 1];
+        btot += p.dims[l + 1];
+    }
+    float* sA = reinterpret_cast<float*>(smem);                 // [kmax/4][TM][4]
+    float* sW = sA + static_cast<size_t>(TM) * kmax;            // per layer [K/4][N][4]
+    float* sB = sW + wtot;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sB + ((btot + 3) & ~3));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    for (int i = tid * 4; i < wtot; i += TM * 4) *reinterpret_cast<float4*>(sW + i) = *reinterpret_cast<const float4*>(wpacked + i);
+    for (int i = tid; i < btot; i += TM) sB[i] = bias[i];
+    uint32_t ncols = 32;
+    while (ncols < static_cast<uint32_t>(nmax)) ncols <<= 1;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t my_taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    uint32_t phase = 0;
+
+    const int ntiles = (p.batch + TM - 1) / TM;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row = tile * TM + tid;
+        const bool live = row < p.batch;
+        // stage the input tile as the A operand (fp32 == tf32 container), zero-padded in rows and in k
+        const int K0 = p.dims[0];
+        for (int c = 0; c < K0 / 4; ++c) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                const float* src = x + static_cast<size_t>(row) * p.in_stride + 4 * c;
+                if (4 * c + 3 < p.in_dim && (p.in_stride & 3) == 0) v = *reinterpret_cast<const float4*>(src);
+                else {
+                    if (4 * c + 0 < p.in_dim) v.x = src[0];
+                    if (4 * c + 1 < p.in_dim) v.y = src[1];
+                    if (4 * c + 2 < p.in_dim) v.z = src[2];
+                    if (4 * c + 3 < p.in_dim) v.w = src[3];
+                }
+            }
+            *reinterpret_cast<float4*>(sA + (static_cast<size_t>(c) * TM + tid) * 4) = v;
+        }
+        int woff = 0, boff = 0;
+        for (int l = 0; l < L; ++l) {
+            const int K = p.dims[l], N = p.dims[l + 1];
+            fence_proxy_async();   // generic-proxy writes of the A operand -> visible to the tensor-core (async) proxy
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc_tf32(N);
+                for (int ks = 0; ks < K / 8; ++ks) {   // UMMA K = 8 tf32 = two 16-byte chunks
+                    const uint64_t da = umma_desc(sA + static_cast<size_t>(2 * ks) * TM * 4, TM * 16, 128);
+                    const uint64_t db = umma_desc(sW + woff + static_cast<size_t>(2 * ks) * N * 4, N * 16, 128);
+                    umma_tf32(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(bar);   // arrives on the mbarrier when every MMA above has completed (implies fence::before)
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+            const bool last = (l == L - 1);
+            for (int n0 = 0; n0 < N; n0 += 16) {
+                float v[16];
+                tmem_ld16(my_taddr + n0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float a = v[j] + sB[boff + n0 + j];
+                    if (!last) a = a > 0.0f ? a : expm1f(a);   // nn.ELU(alpha=1)
+                    v[j] = a;
+                }
+                if (!last) {   // next layer's A operand: k = n, chunk-major
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(sA + (static_cast<size_t>(n0 / 4 + q) * TM + tid) * 4) =
+                            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                } else if (live) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < p.out_dim) out[static_cast<size_t>(row) * p.out_dim + n0 + j] = v[j];
+                }
+            }
+            woff += K * N;
+            boff += N;
+        }
+        tc_fence_before();   // order this tile's tcgen05.ld before the next tile's MMAs overwrite the accumulator
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
+}
+
+}  // namespace
+
+extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const float* wpacked, const float* bias, float* out,
+                                   void* stream) {
+    B200_REQUIRE(p && x && wpacked && bias && out, B200GYM_EINVAL, "mlp_forward: null argument");
+    B200_REQUIRE(p->batch > 0 && p->num_layers >= 1 && p->num_layers <= B200GYM_MLP_MAX_LAYERS, B200GYM_EINVAL,
+                 "mlp_forward: batch > 0 and 1..%d layers", B200GYM_MLP_MAX_LAYERS);
+    B200_REQUIRE(b200_aligned16(x) && b200_aligned16(wpacked), B200GYM_EALIGN, "mlp_forward: x / weights must be 16-byte aligned");
+    size_t kmax = 0, wtot = 0, btot = 0;
+    for (int l = 0; l < p->num_layers; ++l) {
+        const int K = p->dims[l], N = p->dims[l + 1];
+        B200_REQUIRE(K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && N <= 256, B200GYM_EINVAL,
+                     "mlp_forward: layer %d is %d -> %d; need K %% 8 == 0, N %% 16 == 0, N <= 256 (pad with zeros)", l, K, N);
+        kmax = K > (int)kmax ? K : kmax;
+        wtot += static_cast<size_t>(K) * N;
+        btot += N;
+    }
+    B200_REQUIRE(p->in_dim > 0 && p->in_dim <= p->dims[0] && p->in_stride >= p->in_dim && p->out_dim > 0 &&
+                     p->out_dim <= p->dims[p->num_layers],
+                 B200GYM_EINVAL, "mlp_forward: inconsistent in_dim / out_dim");
+    const size_t smem = (TM * kmax + wtot + ((btot + 3) & ~size_t(3))) * 4 + 16;
+    B200_REQUIRE(smem <= 227 * 1024, B200GYM_EINVAL,
+                 "mlp_forward: %zu B of shared memory needed (weights must stay resident); this net is too large for the fused kernel", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "mlp_forward: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+        configured = smem;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int ntiles = (p->batch + TM - 1) / TM;
+    mlp_forward_kernel<<<ntiles < sms ? ntiles : sms, TM, smem, static_cast<cudaStream_t>(stream)>>>(*p, x, wpacked, bias, out);
+    B200_LAUNCH_CHECK("mlp_forward");
+    return B200GYM_OK;
+}

@@ -1,0 +1,59 @@
+"""Fused ActorCritic MLP forward on the tcgen05 tensor cores (csrc/mlp.cu): packing of nn.Sequential(Linear, ELU, ...)
+weights into the kernel's operand layout and the call wrapper.  Used for the no-grad forward passes of the rollout
+(`PPO.act`) and of `get_inference_policy`; the training forward/backward still goes through autograd."""
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _pad(n, m):
+    return (n + m - 1) // m * m
+
+
+class FusedMLP:
+    def __init__(self, seq: nn.Sequential):
+        self.linears = [m for m in seq if isinstance(m, nn.Linear)]
+        acts = [m for m in seq if not isinstance(m, nn.Linear)]
+        if not self.linears or not all(isinstance(a, nn.ELU) for a in acts) or len(acts) != len(self.linears) - 1:
+            raise ValueError("FusedMLP supports Linear/ELU stacks with a linear last layer")
+        if len(self.linears) > 6:
+            raise ValueError("at most 6 layers")
+        self.in_dim, self.out_dim = self.linears[0].in_features, self.linears[-1].out_features
+        self.dims = [_pad(self.in_dim, 8)] + [_pad(l.out_features, 16) for l in self.linears]
+        dev = self.linears[0].weight.device
+        wtot = sum(self.dims[i] * self.dims[i + 1] for i in range(len(self.linears)))
+        smem = (128 * max(self.dims[:-1]) + wtot + sum(self.dims[1:])) * 4 + 64
+        if max(self.dims[1:]) > 256 or smem > 227 * 1024:
+            raise ValueError("net too large for the weights-resident fused kernel")
+        self.wpacked = torch.zeros(wtot, device=dev)
+        self.bias = torch.zeros(_pad(sum(self.dims[1:]), 4), device=dev)
+        self.lib = _lib.lib()
+        self.repack()
+
+    @torch.no_grad()
+    def repack(self):
+        """W_l [N,K] -> [K/4][N][4] (zero padded), biases back to back.  Call after every optimiser step."""
+        woff = boff = 0
+        for i, lin in enumerate(self.linears):
+            K, N = self.dims[i], self.dims[i + 1]
+            W = torch.zeros(N, K, device=self.wpacked.device)
+            W[:lin.out_features, :lin.in_features] = lin.weight
+            self.wpacked[woff:woff + K * N].copy_(W.view(N, K // 4, 4).permute(1, 0, 2).reshape(-1))
+            self.bias[boff:boff + N].zero_()
+            self.bias[boff:boff + lin.out_features].copy_(lin.bias)
+            woff += K * N
+            boff += N
+
+    def __call__(self, x):
+        _lib.require_cuda(x, "x")
+        if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.in_dim or x.stride(1) != 1:
+            raise ValueError(f"expected a float32 [batch, {self.in_dim}] tensor with unit inner stride")
+        out = torch.empty(x.shape[0], self.out_dim, device=x.device)
+        p = _lib.MlpParamsPOD()
+        p.batch, p.num_layers, p.in_dim, p.in_stride, p.out_dim = x.shape[0], len(self.linears), self.in_dim, x.stride(0), self.out_dim
+        for i, d in enumerate(self.dims):
+            p.dims[i] = d
+        _lib.check(self.lib.b200gym_mlp_forward(p, x.data_ptr(), self.wpacked.data_ptr(), self.bias.data_ptr(), out.data_ptr(),
+                                                torch.cuda.current_stream(x.device).cuda_stream), "mlp_forward")
+        return out

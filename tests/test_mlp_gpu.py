@@ -1,0 +1,46 @@
+"""tcgen05 (TF32) fused MLP forward vs the plain fp32 torch forward of the same nn.Sequential.  TF32 keeps a 10-bit
+mantissa: tolerance 5e-3 absolute on O(1) outputs (SURVEY.md §8d cfg 5 allows TF32 for the G4 contraction)."""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(i, hs, o):
+    layers, d = [], i
+    for h in hs:
+        layers += [nn.Linear(d, h), nn.ELU()]
+        d = h
+    return nn.Sequential(*layers, nn.Linear(d, o)).cuda()
+
+
+@pytest.mark.parametrize("num_obs,hidden,out,batch", [(48, (128, 64, 32), 12, 4096), (48, (128, 64, 32), 1, 1000), (48, (128, 64, 32), 12, 7),
+                                                      (48, (128, 64, 32), 12, 24576), (30, (64, 48), 5, 300)])
+def test_fused_mlp_matches_torch(num_obs, hidden, out, batch):
+    from legged_gym_dev_b200.mlp import FusedMLP
+    torch.manual_seed(0)
+    net = _net(num_obs, hidden, out)
+    x = torch.randn(batch, num_obs, device="cuda")
+    with torch.no_grad():
+        want = net(x)
+    got = FusedMLP(net)(x)
+    torch.cuda.synchronize()
+    err = (got - want).abs().max().item()
+    assert got.shape == want.shape
+    assert err < 5e-3, f"max abs error {err}"
+    assert (got - want).abs().mean().item() < 1e-3
+    # repack after a weight change
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(0.5)
+    f = FusedMLP(net)
+    with torch.no_grad():
+        want2 = net(x)
+    assert (f(x) - want2).abs().max().item() < 5e-3
+
+
+def test_fused_mlp_rejects_large_nets():
+    from legged_gym_dev_b200.mlp import FusedMLP
+    with pytest.raises(ValueError):
+        FusedMLP(_net(235, (512, 256, 128), 12))
