@@ -11,8 +11,9 @@ network outputs (one launch), grad-norm + clip + Adam over ONE flat parameter bu
 KL-adaptive learning rate kept on the device — no host sync inside update().  Across GPUs (envs sharded, one process
 per GPU) the only collectives are one all-reduce of the 3 advantage statistics per iteration and one all-reduce of the
 flat gradient buffer (+ KL sum/count piggy-backed) per minibatch.
-The policy MLP contractions themselves still go through torch (cuBLAS); a tcgen05 MLP kernel is the next step
-(DESIGN.md §"what comes next").
+The no-grad MLP forward passes (rollout `act` / `evaluate`, `get_inference_policy`) run as one tcgen05 (TF32, TMEM)
+launch per net (legged_gym_dev_b200/mlp.py, csrc/mlp.cu); the training forward/backward still goes through autograd
+(cuBLAS) — a tcgen05 backward is the next step.
 """
 import ctypes as C
 import os
@@ -135,8 +136,10 @@ class ActorCritic(nn.Module):
     is_recurrent = False
 
     def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=(256, 256, 256),
-                 critic_hidden_dims=(256, 256, 256), activation="elu", init_noise_std=1.0, **kwargs):
+                 critic_hidden_dims=(256, 256, 256), activation="elu", init_noise_std=1.0, fused_inference=True, **kwargs):
         super().__init__()
+        self._want_fused = bool(fused_inference) and activation == "elu"
+        self._fused_actor = self._fused_critic = None
         acts = {"elu": nn.ELU, "selu": nn.SELU, "relu": nn.ReLU, "lrelu": nn.LeakyReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}
         if activation not in acts:
             raise ValueError(f"invalid activation function {activation}")
@@ -170,7 +173,30 @@ class ActorCritic(nn.Module):
             self._slices[name] = (off, k)
             off += k
         self.num_flat = n
+        self.enable_fused_inference()
         return self
+
+    def enable_fused_inference(self):
+        """No-grad forward passes (rollout `act`, `evaluate`, `act_inference`) run as ONE tcgen05 launch per net when the
+        net fits the weights-resident kernel (csrc/mlp.cu); the training forward stays on autograd."""
+        self._fused_actor = self._fused_critic = None
+        if not self._want_fused or next(self.parameters()).device.type != "cuda":
+            return
+        from .mlp import FusedMLP
+        try:
+            self._fused_actor, self._fused_critic = FusedMLP(self.actor), FusedMLP(self.critic)
+        except ValueError:
+            self._fused_actor = self._fused_critic = None
+
+    def repack_fused(self):
+        if self._fused_actor is not None:
+            self._fused_actor.repack()
+            self._fused_critic.repack()
+
+    def _forward(self, net, fused, x):
+        if fused is not None and not torch.is_grad_enabled() and x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1:
+            return fused(x)
+        return net(x)
 
     def reset(self, dones=None):
         pass
@@ -188,7 +214,7 @@ class ActorCritic(nn.Module):
         return self.distribution.entropy().sum(dim=-1)
 
     def update_distribution(self, observations):
-        mean = self.actor(observations)
+        mean = self._forward(self.actor, self._fused_actor, observations)
         self.distribution = torch.distributions.Normal(mean, mean * 0.0 + self.std)
 
     def act(self, observations, **kwargs):
@@ -199,10 +225,10 @@ class ActorCritic(nn.Module):
         return self.distribution.log_prob(actions).sum(dim=-1)
 
     def act_inference(self, observations):
-        return self.actor(observations)
+        return self._forward(self.actor, self._fused_actor, observations)
 
     def evaluate(self, critic_observations, **kwargs):
-        return self.critic(critic_observations)
+        return self._forward(self.critic, self._fused_critic, critic_observations)
 
 
 class PPO:
@@ -299,6 +325,7 @@ class PPO:
             self.optimizer.step(self.max_grad_norm)
             n_updates += 1
         self.storage.clear()
+        ac.repack_fused()
         s = (self._scalars[0:4] / (n_updates * (self.storage.num_envs * self.storage.num_transitions_per_env // self.num_mini_batches)))
         self.learning_rate = self.optimizer.lr   # device scalar; float(self.learning_rate) syncs on demand
         return s[2], s[1]   # mean_value_loss, mean_surrogate_loss (device scalars)
@@ -387,6 +414,7 @@ class OnPolicyRunner:
     def load(self, path, load_optimizer=True):
         d = torch.load(path, map_location=self.device)
         self.alg.actor_critic.load_state_dict(d["model_state_dict"])
+        self.alg.actor_critic.repack_fused()
         if load_optimizer:
             self.alg.optimizer.load_state_dict(d["optimizer_state_dict"])
         self.current_learning_iteration = d["iter"]

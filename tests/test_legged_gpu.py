@@ -170,3 +170,48 @@ def test_height_cells_exact_at_scale():
         got, want = env.measured_heights.cpu(), port.measured_heights
         bad = (got != want)
         assert not bad.any(), f"step {s}: {int(bad.sum())} of {bad.numel()} height samples differ"
+
+
+@pytest.mark.parametrize("name,prob,ep0", [("flat_allterms_v", 1.0, None), ("rough_lstm_allterms", 1.0, None),
+                                            ("flat_pd_upstream", 0.0, 0), ("rough_lstm_allterms", 0.0, 0)])
+def test_all_reset_and_no_reset(name, prob, ep0):
+    """Edge cases of SURVEY.md §4: every env resets every step (base contact on all envs) / no env ever resets
+    (extras['episode'] must then keep its previous values, legged_robot.py:156-157)."""
+    N = 200
+    case = LC.build_case(name, N, base_contact_prob=prob)
+    if prob == 1.0:
+        case.tape.contact[:, :, 0, 2] = 50.0     # make sure the base force exceeds the threshold everywhere
+    if ep0 is not None:
+        case.ep[:] = ep0
+    port, phys = LC.make_port(case)
+    env = LC.make_fused(case)
+    for s in range(8):
+        a = case.tape.actions[s % 8]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} p={prob} step {s}: ")
+        n = int(port.reset_buf.sum())
+        assert n == (N if prob == 1.0 else 0)
+        assert float(env.extras["num_resets"]) == (N if prob == 1.0 else 0.0)
+    if prob == 0.0:
+        assert all(float(v) == 0.0 for v in env.extras["episode"].values())
+
+
+def test_extreme_inputs_stay_finite():
+    """Huge actions / velocities / forces: clips must hold and nothing may turn into NaN (compared against the oracle)."""
+    N = 128
+    case = LC.build_case("flat_allterms_v", N)
+    case.tape.actions *= 1e4
+    case.tape.root[..., 7:13] *= 50.0
+    case.tape.contact *= 100.0
+    case.tape.dof[..., 1] *= 30.0
+    port, phys = LC.make_port(case)
+    env = LC.make_fused(case)
+    for s in range(6):
+        a = case.tape.actions[s % 8]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        snap = LC.snapshot_fused(env)
+        assert all(torch.isfinite(v.float()).all() for v in snap.values())
+        assert snap["obs"].abs().max() <= 100.0 and snap["torques"].abs().max() <= 80.0
+        LC.compare_snapshots(snap, LC.snapshot_port(port), tag=f"extreme step {s}: ")

@@ -44,3 +44,23 @@ def test_fused_mlp_rejects_large_nets():
     from legged_gym_dev_b200.mlp import FusedMLP
     with pytest.raises(ValueError):
         FusedMLP(_net(235, (512, 256, 128), 12))
+
+
+def test_actor_critic_uses_fused_forward_without_grad():
+    from legged_gym_dev_b200.ppo import ActorCritic, PPO
+    torch.manual_seed(1)
+    ac = ActorCritic(48, 48, 12, actor_hidden_dims=[128, 64, 32], critic_hidden_dims=[128, 64, 32])
+    alg = PPO(ac, device="cuda")
+    assert ac._fused_actor is not None
+    x = torch.randn(512, 48, device="cuda")
+    with torch.no_grad():
+        fused = ac.act_inference(x)
+        v_fused = ac.evaluate(x)
+    ref, v_ref = ac.actor(x), ac.critic(x)            # grad mode: autograd path
+    assert ref.requires_grad and not fused.requires_grad
+    assert (fused - ref).abs().max().item() < 5e-3 and (v_fused - v_ref).abs().max().item() < 5e-3
+    with torch.no_grad():
+        ac.flat_param.mul_(0.9)
+    ac.repack_fused()
+    with torch.no_grad():
+        assert (ac.act_inference(x) - ac.actor(x)).abs().max().item() < 5e-3

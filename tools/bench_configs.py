@@ -163,7 +163,31 @@ def gae_update(num_envs=4096, T=24, device="cuda", peak=6535.7):
     b.record()
     torch.cuda.synchronize()
     ms_upd = a.elapsed_time(b)
+    # policy forward: tcgen05 fused kernel vs torch (cuBLAS) on the rollout batch and on a minibatch-sized batch
+    mlp = {}
+    for B_ in (num_envs, T * num_envs // 4):
+        xb = torch.randn(B_, 48, device=device)
+        with torch.no_grad():
+            for _ in range(5):
+                ac._fused_actor(xb)
+                ac.actor(xb)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(50):
+                ac._fused_actor(xb)
+            b.record()
+            torch.cuda.synchronize()
+            t_f = a.elapsed_time(b) / 50
+            a.record()
+            for _ in range(50):
+                ac.actor(xb)
+            b.record()
+            torch.cuda.synchronize()
+            t_t = a.elapsed_time(b) / 50
+        flops = 2.0 * B_ * (48 * 128 + 128 * 64 + 64 * 32 + 32 * 12)
+        mlp[str(B_)] = dict(fused_tcgen05_ms=t_f, torch_ms=t_t, fused_tflops=flops / (t_f * 1e-3) / 1e12)
     return dict(config="rollout storage GAE + normalisation; PPO update 5 epochs x 4 minibatches (nets 48-128-64-32)", num_envs=num_envs,
+                actor_forward=mlp,
                 T=T, gae_ms=ms_gae, gae_env_steps_per_s=num_envs * T / (ms_gae * 1e-3),
                 gae_gbs=604 * num_envs / (ms_gae * 1e-3) / 1e9, gae_frac=604 * num_envs / (ms_gae * 1e-3) / 1e9 / peak,
                 update_ms=ms_upd, update_samples_per_s=5 * T * num_envs / (ms_upd * 1e-3),
