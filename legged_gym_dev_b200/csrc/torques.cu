@@ -9,6 +9,10 @@
 #include "philox.cuh"
 #include "../../include/b200gym.h"
 
+#ifndef LSTM_MINBLOCKS
+#define LSTM_MINBLOCKS 8
+#endif
+
 namespace {
 
 constexpr int ND = B200GYM_NUM_DOF;
@@ -57,33 +61,45 @@ __global__ void __launch_bounds__(256) pd_torques_kernel(const __grid_constant__
 // Actuator LSTM: one thread per actuator (env,dof).  969 weights live in constant memory, so every FFMA
 // takes its weight operand straight from the constant bank (all lanes read the same address).
 // ------------------------------------------------------------------------------------------------
+// Gate rows are stored in PAIRS (2p, 2p+1) so that one packed fp32 FMA (fma.rn.f32x2, SASS FFMA2 — Blackwell issues two
+// fp32 FMAs per lane per instruction) advances two gate pre-activations; the weight pair comes from the constant bank /
+// uniform registers and the input is the broadcast scalar operand, so no packing moves are needed.
 struct ActuatorNet {
-    float w_ih0[32][2], w_hh0[32][8], b0[32];   // b0 = b_ih0 (+ b_hh0 added separately to mirror ATen)
-    float bh0[32];
-    float w_ih1[32][8], w_hh1[32][8], b1[32], bh1[32];
+    float2 w_ih0[16][2], w_hh0[16][8], b0[16], bh0[16];   // b0 = b_ih, bh0 = b_hh (summed separately to mirror ATen)
+    float2 w_ih1[16][8], w_hh1[16][8], b1[16], bh1[16];
     float w_lin[8], b_lin, in0, in1, out_scale;
 };
 __constant__ ActuatorNet c_net;
 
-__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_acc(float x) {
-    // tanh(x) = 1 - 2/(exp(2x)+1); abs error ~1e-7, inside the 1e-5 contract
-    const float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, e + 1.0f);
+// MUFU-based activations without the denormal-handling prologues of __expf/__fdividef: ex2.approx.ftz (rel. error 2^-22)
+// and rcp.approx.ftz (1 ulp).  Saturation is exact: ex2 -> inf gives rcp -> 0, ex2 -> 0 (flushed) gives rcp(1) = 1.
+// Absolute error ~1e-7 on sigma/tanh, inside the 1e-5 * S contract (ATen's own two LSTM paths differ by 1.1e-5).
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_acc(float x) { return fmaf(-2.0f, rcp_ftz(ex2_ftz(2.8853900817779268f * x) + 1.0f), 1.0f); }
 
 template <int NIN>
-__device__ __forceinline__ void lstm_cell(const float (&w_ih)[32][NIN], const float (&w_hh)[32][8], const float (&bi)[32],
-                                          const float (&bh)[32], const float (&x)[NIN], float (&h)[8], float (&c)[8]) {
+__device__ __forceinline__ void lstm_cell(const float2 (&w_ih)[16][NIN], const float2 (&w_hh)[16][8], const float2 (&bi)[16],
+                                          const float2 (&bh)[16], const float (&x)[NIN], float (&h)[8], float (&c)[8]) {
     float gate[32];
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        float a = bi[r], bsum = bh[r];
+    for (int p = 0; p < 16; ++p) {
+        float2 a = bi[p], bsum = bh[p];
 #pragma unroll
-        for (int k = 0; k < NIN; ++k) a = fmaf(w_ih[r][k], x[k], a);
+        for (int k = 0; k < NIN; ++k) a = __ffma2_rn(w_ih[p][k], make_float2(x[k], x[k]), a);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) bsum = fmaf(w_hh[r][k], h[k], bsum);
-        gate[r] = a + bsum;
+        for (int k = 0; k < 8; ++k) bsum = __ffma2_rn(w_hh[p][k], make_float2(h[k], h[k]), bsum);
+        const float2 g = __fadd2_rn(a, bsum);
+        gate[2 * p] = g.x, gate[2 * p + 1] = g.y;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -94,7 +110,7 @@ __device__ __forceinline__ void lstm_cell(const float (&w_ih)[32][NIN], const fl
     }
 }
 
-__global__ void __launch_bounds__(128) lstm_torques_kernel(const __grid_constant__ B200LeggedParams p,
+__global__ void __launch_bounds__(128, LSTM_MINBLOCKS) lstm_torques_kernel(const __grid_constant__ B200LeggedParams p,
                                                            const float* __restrict__ actions,
                                                            float* __restrict__ actions_clipped,
                                                            const float2* __restrict__ dof_state, float* __restrict__ hbuf,
@@ -114,10 +130,12 @@ __global__ void __launch_bounds__(128) lstm_torques_kernel(const __grid_constant
     const float4* hp1 = reinterpret_cast<const float4*>(hbuf + l1 + static_cast<size_t>(i) * 8);
     const float4* cp1 = reinterpret_cast<const float4*>(cbuf + l1 + static_cast<size_t>(i) * 8);
     float4 v;
+    // each thread owns 32 contiguous bytes per state row: two 128-bit loads that share their sectors, so they must be
+    // allowed to allocate in L1 (a no-allocate streaming load would fetch every sector twice from L2)
 #define LD8(dst, src)                                                  \
-    v = ldg_stream4(src);                                              \
+    v = __ldg(src);                                                    \
     dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;            \
-    v = ldg_stream4(src + 1);                                          \
+    v = __ldg(src + 1);                                                \
     dst[4] = v.x, dst[5] = v.y, dst[6] = v.z, dst[7] = v.w;
     LD8(h0, hp) LD8(c0, cp) LD8(h1, hp1) LD8(c1, cp1)
 #undef LD8
@@ -166,10 +184,16 @@ int b200gym_set_actuator_net(const float* w_ih0, const float* w_hh0, const float
     B200_REQUIRE(w_ih0 && w_hh0 && b_ih0 && b_hh0 && w_ih1 && w_hh1 && b_ih1 && b_hh1 && w_lin && b_lin, B200GYM_EINVAL,
                  "set_actuator_net: null argument");
     ActuatorNet n;
-    for (int r = 0; r < 32; ++r) {
-        for (int k = 0; k < 2; ++k) n.w_ih0[r][k] = w_ih0[r * 2 + k];
-        for (int k = 0; k < 8; ++k) n.w_hh0[r][k] = w_hh0[r * 8 + k], n.w_ih1[r][k] = w_ih1[r * 8 + k], n.w_hh1[r][k] = w_hh1[r * 8 + k];
-        n.b0[r] = b_ih0[r], n.bh0[r] = b_hh0[r], n.b1[r] = b_ih1[r], n.bh1[r] = b_hh1[r];
+    for (int p = 0; p < 16; ++p) {   // rows 2p and 2p+1 side by side
+        const int r0 = 2 * p, r1 = 2 * p + 1;
+        for (int k = 0; k < 2; ++k) n.w_ih0[p][k] = make_float2(w_ih0[r0 * 2 + k], w_ih0[r1 * 2 + k]);
+        for (int k = 0; k < 8; ++k) {
+            n.w_hh0[p][k] = make_float2(w_hh0[r0 * 8 + k], w_hh0[r1 * 8 + k]);
+            n.w_ih1[p][k] = make_float2(w_ih1[r0 * 8 + k], w_ih1[r1 * 8 + k]);
+            n.w_hh1[p][k] = make_float2(w_hh1[r0 * 8 + k], w_hh1[r1 * 8 + k]);
+        }
+        n.b0[p] = make_float2(b_ih0[r0], b_ih0[r1]), n.bh0[p] = make_float2(b_hh0[r0], b_hh0[r1]);
+        n.b1[p] = make_float2(b_ih1[r0], b_ih1[r1]), n.bh1[p] = make_float2(b_hh1[r0], b_hh1[r1]);
     }
     for (int k = 0; k < 8; ++k) n.w_lin[k] = w_lin[k];
     n.b_lin = b_lin[0], n.in0 = in_scale0, n.in1 = in_scale1, n.out_scale = out_scale;
