@@ -9,12 +9,13 @@
 //
 // Work mapping (chosen from the ncu profile of the first version, profiles/r1_post_physics_v1.md: the kernel
 // was issue-bound because four lanes each repeated the per-env scalar work):
-//   phase H  (rough only) one warp per env: 187-point height scan           legged_robot.py:877-915
+//   phase H  (rough only) one warp per env: 187-point height scan + height observations (noise included)
+//                                                                            legged_robot.py:877-915,220-226
 //   phase W  4 lanes per env: per-DOF / per-foot / per-body terms, the DOF observation columns and all
 //            Philox noise draws; 2-step shuffle reductions leave per-env partial sums in shared memory
 //   phase S  1 thread per env: body-frame vectors, commands, termination, reward assembly, in-place reset,
 //            first 12 observation columns — scalar work executed exactly once per env
-//   phase H2 (rough only) one warp per env: height observations + noise    legged_robot.py:220-226
+//   phase H' (rough only) height observations redone for the (rare) envs that reset: they use the post-reset height
 #include <math.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -173,10 +174,10 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
     s.acc = c.take<double>(B200GYM_NUM_REWARD_TERMS + 2);
     s.nreset = c.take<int>(4);
     if (ROUGH) {
-        s.hraw = c.take<int16_t>(TILE * HPAD);
+        s.hraw = nullptr;
         s.bh = c.take<float>(TILE);
         s.zpost = c.take<float>(TILE);
-        s.stage = c.take<float>((TILE * LPE / 32) * HPAD);
+        s.stage = c.take<float>((TILE * LPE / 32) * 128);
         s.pts = c.take<float2>(HPAD);
     } else {
         s.hraw = nullptr;
@@ -260,53 +261,71 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         __syncthreads();
     }
 
-    // ---- phase H: height scan, one warp per env (legged_robot.py:877-915, math.py:38-42) ----------
+    // ---- phase H: height scan + height observations, one warp per env (legged_robot.py:877-915, math.py:38-42, :220-226)
+    // The observation needs the POST-reset base height; resets are rare, so the observation is produced here with the
+    // current height and redone after phase S only for the envs that did reset (phase H').
     if (ROUGH) {
         const int H = p.num_heights;
         const int rows = p.terrain_rows, cols = p.terrain_cols;
         const float inv_hs = div_rn(1.0f, p.horizontal_scale);
+        float* stage = s.stage + warp * 128;
         for (int e = warp; e < nvalid; e += TILE * LPE / 32) {
             const float* R = s.root + e * 13;
-            // quat_apply_yaw: zero x,y, renormalise, rotate — un-fused fp32 ops, the cell index depends on them (H2)
+            const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
+            // quat_apply_yaw: zero x,y, renormalise, rotate — un-fused fp32 ops, the cell index depends on them
             const float nq = fmaxf(sqrtf(add_rn(mul_rn(R[5], R[5]), mul_rn(R[6], R[6]))), 1e-9f);
             const float qz = div_rn(R[5], nq), qw = div_rn(R[6], nq);
+            const float z05 = sub_rn(R[2], 0.5f);
             float part = 0.0f;
-            // all (<= 6 x 32) sample points of the env are indexed first and their 3 x 6 gathers issued together, so the
-            // L2 latency of the height field is paid once per env, not once per point
-            const int16_t* hs[HPAD / 32];
-#pragma unroll
-            for (int it = 0; it < HPAD / 32; ++it) {
-                const int pt = lane + 32 * it;
-                hs[it] = nullptr;
-                if (pt < H && !p.mesh_plane) {
-                    const float2 hp = s.pts[pt];
-                    const float hx = hp.x, hy = hp.y;
-                    const float tx = mul_rn(-mul_rn(qz, hy), 2.0f), ty = mul_rn(mul_rn(qz, hx), 2.0f);
-                    float wx = add_rn(add_rn(hx, mul_rn(qw, tx)), -mul_rn(qz, ty));
-                    float wy = add_rn(add_rn(hy, mul_rn(qw, ty)), mul_rn(qz, tx));
-                    wx = div_const_rn(add_rn(add_rn(wx, R[0]), p.border_size), p.horizontal_scale, inv_hs);
-                    wy = div_const_rn(add_rn(add_rn(wy, R[1]), p.border_size), p.horizontal_scale, inv_hs);
-                    // .long() truncation + clip (legged_robot.py:903-907); saturating conversion keeps huge values clipped
-                    const int ix = min(max(__float2int_rz(wx), 0), rows - 2), iy = min(max(__float2int_rz(wy), 0), cols - 2);
-                    hs[it] = b.height_samples + ix * cols + iy;
+            float* mh_out = b.measured_heights + static_cast<size_t>(tile0 + e) * H;
+            float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48;
+            for (int c0 = 0; c0 < H; c0 += 128) {   // chunks of 128 points = 32 Philox blocks, one per lane
+                if (p.add_noise) {
+                    const int nb = (c0 >> 2) + lane;
+                    float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+                    if (4 * nb < H) u = philox::u01(rng.words(philox::OBS_NOISE, 12 + nb));
+                    *reinterpret_cast<float4*>(stage + 4 * lane) = u;
+                    __syncwarp();
                 }
-            }
-            int h1[HPAD / 32], h2[HPAD / 32], h3[HPAD / 32];
+                // index all 4 points of this lane first, then issue their 12 gathers together (one L2 latency per chunk)
+                const int16_t* hs[4];
 #pragma unroll
-            for (int it = 0; it < HPAD / 32; ++it) {
-                h1[it] = h2[it] = h3[it] = 0;
-                if (hs[it]) h1[it] = __ldg(hs[it]), h2[it] = __ldg(hs[it] + cols), h3[it] = __ldg(hs[it] + 1);
-            }
-#pragma unroll
-            for (int it = 0; it < HPAD / 32; ++it) {
-                const int pt = lane + 32 * it;
-                if (pt < H) {
-                    const int raw = min(min(h1[it], h2[it]), h3[it]);
-                    s.hraw[e * HPAD + pt] = static_cast<int16_t>(raw);
-                    const float mh = mul_rn(static_cast<float>(raw), p.vertical_scale);
-                    b.measured_heights[static_cast<size_t>(tile0 + e) * H + pt] = mh;
-                    part += R[2] - mh;
+                for (int j = 0; j < 4; ++j) {
+                    const int pt = c0 + 32 * j + lane;
+                    hs[j] = nullptr;
+                    if (pt < H && !p.mesh_plane) {
+                        const float2 hp = s.pts[pt];
+                        const float hx = hp.x, hy = hp.y;
+                        const float tx = mul_rn(-mul_rn(qz, hy), 2.0f), ty = mul_rn(mul_rn(qz, hx), 2.0f);
+                        float wx = add_rn(add_rn(hx, mul_rn(qw, tx)), -mul_rn(qz, ty));
+                        float wy = add_rn(add_rn(hy, mul_rn(qw, ty)), mul_rn(qz, tx));
+                        wx = div_const_rn(add_rn(add_rn(wx, R[0]), p.border_size), p.horizontal_scale, inv_hs);
+                        wy = div_const_rn(add_rn(add_rn(wy, R[1]), p.border_size), p.horizontal_scale, inv_hs);
+                        // .long() truncation + clip (legged_robot.py:903-907); the saturating conversion keeps huge values clipped
+                        const int ix = min(max(__float2int_rz(wx), 0), rows - 2), iy = min(max(__float2int_rz(wy), 0), cols - 2);
+                        hs[j] = b.height_samples + ix * cols + iy;
+                    }
                 }
+                int raw[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    raw[j] = 0;
+                    if (hs[j]) raw[j] = min(min(static_cast<int>(__ldg(hs[j])), static_cast<int>(__ldg(hs[j] + cols))),
+                                            static_cast<int>(__ldg(hs[j] + 1)));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int pt = c0 + 32 * j + lane;
+                    if (pt < H) {
+                        const float mh = mul_rn(static_cast<float>(raw[j]), p.vertical_scale);
+                        mh_out[pt] = mh;
+                        part += R[2] - mh;
+                        float v = clampf(sub_rn(z05, mh), -1.0f, 1.0f) * p.obs_height;
+                        if (p.add_noise) v = add_noise(v, stage[32 * j + lane], p.noise_height);
+                        ob_out[pt] = clampf(v, -p.clip_obs, p.clip_obs);
+                    }
+                }
+                __syncwarp();
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -596,7 +615,12 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
             b.root_states[ge * 13 + 7] = lrv[0];
             b.root_states[ge * 13 + 8] = lrv[1];
         }
-        if (p.terrain_curriculum && valid) atomicAdd(&s.acc[K], static_cast<double>(level));
+        if (p.terrain_curriculum) {   // sum of terrain levels of the tile: warp shuffle first, one shared atomic per warp
+            long long lv = valid ? level : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
+            if ((tid & 31) == 0) atomicAdd(&s.acc[K], static_cast<double>(lv));
+        }
 
         // R11: first 12 observation columns (+ noise, clip); uniforms were staged by phase W
         float o[12] = {blx * p.obs_lin_vel, bly * p.obs_lin_vel, blz * p.obs_lin_vel, bax * p.obs_ang_vel, bay * p.obs_ang_vel,
@@ -673,32 +697,35 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         for (int i = tid; i < nvalid * 48; i += TILE * LPE) b.obs_buf[static_cast<size_t>(tile0 + i / 48) * O + (i % 48)] = s.obs[i];
     }
 
-    // ---- phase H2: height observations, one warp per env (legged_robot.py:220-226) ----------------
+    // ---- phase H': height observations of the envs that reset this step, redone with the post-reset base height ----
     if (ROUGH) {
         const int H = p.num_heights;
-        float* stage = s.stage + warp * HPAD;
+        float* stage = s.stage + warp * 128;
         for (int e = warp; e < nvalid; e += TILE * LPE / 32) {
-            const float z = s.zpost[e] - 0.5f;
+            if (!s.reset[e]) continue;
+            const float z05 = sub_rn(s.zpost[e], 0.5f);
             const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
-            for (int pb = lane; pb * 4 < H; pb += 32) {
-                float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-                if (p.add_noise) u = philox::u01(rng.words(philox::OBS_NOISE, 12 + pb));
-                const float uu[4] = {u.x, u.y, u.z, u.w};
-                float out[4];
+            const float* mh_in = b.measured_heights + static_cast<size_t>(tile0 + e) * H;   // written by this CTA in phase H
+            float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48;
+            for (int c0 = 0; c0 < H; c0 += 128) {
+                if (p.add_noise) {
+                    const int nb = (c0 >> 2) + lane;
+                    float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+                    if (4 * nb < H) u = philox::u01(rng.words(philox::OBS_NOISE, 12 + nb));
+                    *reinterpret_cast<float4*>(stage + 4 * lane) = u;
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int pt = 4 * pb + j;
-                    const float mh = mul_rn(static_cast<float>(pt < H ? s.hraw[e * HPAD + pt] : 0), p.vertical_scale);
-                    float v = clampf(z - mh, -1.0f, 1.0f) * p.obs_height;
-                    if (p.add_noise) v = add_noise(v, uu[j], p.noise_height);
-                    out[j] = clampf(v, -p.clip_obs, p.clip_obs);
+                    const int pt = c0 + 32 * j + lane;
+                    if (pt < H) {
+                        float v = clampf(sub_rn(z05, mh_in[pt]), -1.0f, 1.0f) * p.obs_height;
+                        if (p.add_noise) v = add_noise(v, stage[32 * j + lane], p.noise_height);
+                        ob_out[pt] = clampf(v, -p.clip_obs, p.clip_obs);
+                    }
                 }
-                *reinterpret_cast<float4*>(stage + 4 * pb) = make_float4(out[0], out[1], out[2], out[3]);
+                __syncwarp();
             }
-            __syncwarp();
-            float* dst = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48;
-            for (int pt = lane; pt < H; pt += 32) dst[pt] = stage[pt];
-            __syncwarp();
         }
     }
 
