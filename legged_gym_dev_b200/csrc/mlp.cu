@@ -8,6 +8,7 @@
 // Shared-memory operand layout (both A [rows x K] and B = W_l [N x K], K-major): 16-byte chunks of 4 consecutive k,
 // chunk-major:  byte(r, k) = (k/4) * R*16 + r*16 + (k%4)*4,  R = rows of the operand.  In UMMA terms the 8x16B core
 // matrices are contiguous (128 B), SBO (next 8 rows) = 128 B, LBO (next k-chunk) = R*16 B.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/b200gym.h"
 
@@ -51,7 +52,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(TM, 1) mlp_forward_kernel(const __grid_constant__ B200MlpParams p, const float* __restrict__ x,
+__global__ void __launch_bounds__(TM, 1) mlp_forward_serial_kernel(const __grid_constant__ B200MlpParams p, const float* __restrict__ x,
                                                             const float* __restrict__ wpacked, const float* __restrict__ bias,
                                                             float* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -158,6 +159,223 @@ __global__ void __launch_bounds__(TM, 1) mlp_forward_kernel(const __grid_constan
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// mlp_forward_pipe_kernel — the same contraction as a warp-specialised, two-slot software pipeline (one persistent
+// 512-thread CTA per SM).  The serial kernel above spends its time in a 4-warp epilogue (expm1f, dependent chains,
+// nothing else resident on the SM: 25 us per 128-row tile, 146 GB/s); here
+//   * two tile slots alternate: while slot 0's warpgroup runs its bias+ELU epilogue on the FMA/MUFU pipes, slot 1's
+//     tcgen05.mma chain occupies the tensor pipe (and vice versa); each slot owns 128 TMEM columns and one operand buffer,
+//   * two loader warpgroups prefetch the NEXT input tile of their slot into registers (12 x 128-bit loads in flight per
+//     thread) and drop it into the slot's X region as soon as the layer that last reads that region has retired,
+//   * ELU = max(t, ex2(min(t,0)*log2e) - 1): 1 MUFU + 5 FP32 instructions per activation, no branch,
+//   * TMEM -> register loads are double-buffered against the epilogue arithmetic.
+// Shared memory: weights resident (67 KB for 48-128-64-32-16) + 2 operand buffers [chunks][128 rows][4].
+// Operand-buffer plan: layer l reads its A operand from chunks [0, K_l/4) (layer 0: the X region at chunk `x_off`) and
+// writes ELU(h) to chunks [0, N_l/4).  x_off is chosen past every hidden activation written after layer 1, so the next
+// tile's input can land while layers 2.. of the current tile are still running.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PIPE_THREADS = 512;   // warps 0-3 / 4-7: epilogue+MMA warpgroups of slot 0 / 1; warps 8-11 / 12-15: their loaders
+constexpr int CHUNK_BYTES = TM * 16;
+
+struct PipePlan {
+    int x_off;        // first chunk of the X region
+    int free_layer;   // the X region is free again once this layer's MMAs have completed
+    int buf_chunks;   // chunks per operand buffer
+    int wtot, btot;
+};
+
+__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// the registers are tied to the wait so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// nn.ELU(alpha=1): exp(t) - 1 >= t for every t, so elu(t) = max(t, exp(min(t, 0)) - 1)
+__device__ __forceinline__ float elu_fast(float t) { return fmaxf(t, ex2_approx(fminf(t, 0.0f) * 1.4426950408889634f) - 1.0f); }
+
+template <bool LAST>
+__device__ __forceinline__ void pipe_epilogue_chunk(const uint32_t (&r)[16], const float* __restrict__ sBl, int n0, float* __restrict__ hrow,
+                                                    float* __restrict__ orow, int out_dim, bool live) {
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sBl + n0 + 4 * q);   // same address in every lane: broadcast
+        v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
+        v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+        v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+        v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+    }
+    if (!LAST) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = elu_fast(v[j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)   // next layer's A operand, k = n: chunk (n0/4 + q), this thread's row
+            *reinterpret_cast<float4*>(hrow + static_cast<size_t>(n0 / 4 + q) * (TM * 4)) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else if (live) {
+        if ((out_dim & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (n0 + 4 * q < out_dim)
+                    *reinterpret_cast<float4*>(orow + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (n0 + j < out_dim) orow[n0 + j] = v[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PIPE_THREADS, 1) mlp_forward_pipe_kernel(const __grid_constant__ B200MlpParams p, const PipePlan plan,
+                                                                            const float* __restrict__ x, const float* __restrict__ wpacked,
+                                                                            const float* __restrict__ bias, float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int L = p.num_layers, tid = threadIdx.x, warp = tid >> 5;
+    const size_t buf_floats = static_cast<size_t>(plan.buf_chunks) * (TM * 4);
+    float* sH0 = reinterpret_cast<float*>(smem);
+    float* sW = sH0 + 2 * buf_floats;
+    float* sB = sW + plan.wtot;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + ((plan.btot + 3) & ~3));   // [0,1] full, [2,3] empty, [4,5] mma done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    for (int i = tid * 4; i < plan.wtot; i += PIPE_THREADS * 4)
+        *reinterpret_cast<float4*>(sW + i) = *reinterpret_cast<const float4*>(wpacked + i);
+    for (int i = tid; i < plan.btot; i += PIPE_THREADS) sB[i] = bias[i];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(bars + 0, TM), mbar_init(bars + 1, TM);   // full: every loader thread of the slot arrives
+        mbar_init(bars + 2, 1), mbar_init(bars + 3, 1);     // empty: one arrival by the slot's MMA thread
+        mbar_init(bars + 4, 1), mbar_init(bars + 5, 1);     // MMA completion (tcgen05.commit)
+        fence_mbar_init();
+    }
+    fence_proxy_async();   // the weight tile was written through the generic proxy, the tensor core reads it through the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int ntiles = (p.batch + TM - 1) / TM;
+    const int slot = (warp >> 2) & 1;               // warps 0-3, 8-11 -> slot 0; warps 4-7, 12-15 -> slot 1
+    const int t = tid & (TM - 1);                   // thread within its warpgroup = row within the tile
+    float* sH = sH0 + slot * buf_floats;
+    uint64_t *full = bars + slot, *empty = bars + 2 + slot, *mma_done = bars + 4 + slot;
+
+    if (warp >= 8) {
+        // ------------------------------ loader warpgroup of this slot ------------------------------
+        const int K0c = p.dims[0] / 4, in_c = p.in_dim / 4;
+        uint32_t ph = 1;   // the first wait on a fresh "empty" barrier falls through
+        for (int tile = blockIdx.x + slot * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
+            const int row = tile * TM + t;
+            const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * p.in_stride);
+            float4 v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < in_c && row < p.batch) v[c] = __ldg(src + c);   // L1-allocating: the two 16-B halves of a sector are read by consecutive loads
+            }
+            for (int c = 16; c < in_c; ++c) {   // wide inputs: beyond the register-prefetched part (waits for the buffer first)
+                if (c == 16) mbar_wait(empty, ph);
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < p.batch) w = __ldg(src + c);
+                *reinterpret_cast<float4*>(sH + (static_cast<size_t>(plan.x_off + c) * TM + t) * 4) = w;
+            }
+            if (in_c <= 16) mbar_wait(empty, ph);
+            ph ^= 1;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < K0c) *reinterpret_cast<float4*>(sH + (static_cast<size_t>(plan.x_off + c) * TM + t) * 4) = v[c];
+            for (int c = (in_c > 16 ? in_c : 16); c < K0c; ++c)
+                *reinterpret_cast<float4*>(sH + (static_cast<size_t>(plan.x_off + c) * TM + t) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            fence_proxy_async();
+            mbar_arrive(full);
+        }
+    } else {
+        // ------------------------------ MMA + epilogue warpgroup of this slot ------------------------------
+        const uint32_t tacc = tmem + static_cast<uint32_t>(slot * 128);                               // this slot's accumulator columns
+        const uint32_t my_taddr = tacc + (static_cast<uint32_t>((warp & 3) * 32) << 16);              // this warp's TMEM lane quadrant
+        float* hrow = sH + t * 4;
+        uint32_t ph_full = 0, ph_mma = 0;
+        for (int tile = blockIdx.x + slot * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
+            const int row = tile * TM + t;
+            const bool live = row < p.batch;
+            float* orow = out + static_cast<size_t>(row) * p.out_dim;
+            int woff = 0, boff = 0;
+            for (int l = 0; l < L; ++l) {
+                const int K = p.dims[l], N = p.dims[l + 1];
+                // everyone in the warpgroup has finished writing this layer's A operand and reading the accumulator
+                fence_proxy_async();
+                tc_fence_before();
+                bar_sync_named(1 + slot, TM);
+                if (t == 0) {
+                    if (l == 0) mbar_wait(full, ph_full);
+                    tc_fence_after();
+                    const uint32_t idesc = umma_idesc_tf32(N);
+                    const float* a0 = sH + (l == 0 ? static_cast<size_t>(plan.x_off) * (TM * 4) : 0);
+                    for (int ks = 0; ks < K / 8; ++ks) {
+                        const uint64_t da = umma_desc(a0 + static_cast<size_t>(2 * ks) * TM * 4, CHUNK_BYTES, 128);
+                        const uint64_t db = umma_desc(sW + woff + static_cast<size_t>(2 * ks) * N * 4, N * 16, 128);
+                        umma_tf32(tacc, da, db, idesc, ks > 0 ? 1u : 0u);
+                    }
+                    umma_commit(mma_done);
+                }
+                mbar_wait(mma_done, ph_mma);
+                ph_mma ^= 1;
+                tc_fence_after();
+                if (l == plan.free_layer && t == 0) mbar_arrive(empty);   // the X region may take the next tile's input
+                const float* sBl = sB + boff;
+                uint32_t ra[16], rb[16];
+                tmem_ld16_issue(my_taddr, ra);
+                if (l == L - 1) {
+                    for (int n0 = 0; n0 < N; n0 += 16) {
+                        tmem_ld16_wait(ra);
+                        pipe_epilogue_chunk<true>(ra, sBl, n0, hrow, orow, p.out_dim, live);
+                        if (n0 + 16 < N) tmem_ld16_issue(my_taddr + n0 + 16, ra);
+                    }
+                } else {
+                    for (int n0 = 0; n0 < N; n0 += 32) {
+                        tmem_ld16_wait(ra);
+                        if (n0 + 16 < N) tmem_ld16_issue(my_taddr + n0 + 16, rb);
+                        pipe_epilogue_chunk<false>(ra, sBl, n0, hrow, orow, p.out_dim, live);
+                        if (n0 + 16 < N) {
+                            tmem_ld16_wait(rb);
+                            if (n0 + 32 < N) tmem_ld16_issue(my_taddr + n0 + 32, ra);
+                            pipe_epilogue_chunk<false>(rb, sBl, n0 + 16, hrow, orow, p.out_dim, live);
+                        }
+                    }
+                }
+                woff += K * N;
+                boff += N;
+            }
+            ph_full ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
 }  // namespace
 
 extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const float* wpacked, const float* bias, float* out,
@@ -178,15 +396,6 @@ extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const
     B200_REQUIRE(p->in_dim > 0 && p->in_dim <= p->dims[0] && p->in_stride >= p->in_dim && p->out_dim > 0 &&
                      p->out_dim <= p->dims[p->num_layers],
                  B200GYM_EINVAL, "mlp_forward: inconsistent in_dim / out_dim");
-    const size_t smem = (TM * kmax + wtot + ((btot + 3) & ~size_t(3))) * 4 + 16;
-    B200_REQUIRE(smem <= 227 * 1024, B200GYM_EINVAL,
-                 "mlp_forward: %zu B of shared memory needed (weights must stay resident); this net is too large for the fused kernel", smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "mlp_forward: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-        configured = smem;
-    }
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -194,7 +403,48 @@ extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int ntiles = (p->batch + TM - 1) / TM;
-    mlp_forward_kernel<<<ntiles < sms ? ntiles : sms, TM, smem, static_cast<cudaStream_t>(stream)>>>(*p, x, wpacked, bias, out);
+    const int L = p->num_layers;
+    // ---- pipelined two-slot kernel whenever the shapes allow it --------------------------------------------------
+    {
+        PipePlan plan;
+        int nmax = 0, hidden_late = 0, hidden_all = 0;
+        for (int l = 0; l < L; ++l) nmax = p->dims[l + 1] > nmax ? p->dims[l + 1] : nmax;
+        for (int j = 1; j <= L - 1; ++j) hidden_all = p->dims[j] > hidden_all ? p->dims[j] : hidden_all;
+        for (int j = 2; j <= L - 1; ++j) hidden_late = p->dims[j] > hidden_late ? p->dims[j] : hidden_late;
+        plan.x_off = hidden_late / 4;
+        plan.free_layer = L - 1 < 1 ? L - 1 : 1;
+        plan.buf_chunks = hidden_all / 4 > plan.x_off + p->dims[0] / 4 ? hidden_all / 4 : plan.x_off + p->dims[0] / 4;
+        plan.wtot = static_cast<int>(wtot), plan.btot = static_cast<int>(btot);
+        const size_t smem_pipe = (2 * static_cast<size_t>(plan.buf_chunks) * TM * 4 + wtot + ((btot + 3) & ~size_t(3))) * 4 + 64;
+        static int force_serial = -1;
+        if (force_serial < 0) {
+            const char* e = getenv("B200GYM_MLP_SERIAL");
+            force_serial = (e && e[0] == '1') ? 1 : 0;
+        }
+        if (!force_serial && nmax <= 128 && (p->in_dim & 3) == 0 && (p->in_stride & 3) == 0 && smem_pipe <= 227 * 1024) {
+            static size_t configured_pipe = 0;
+            if (smem_pipe > configured_pipe) {
+                cudaError_t e = cudaFuncSetAttribute(mlp_forward_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_pipe));
+                B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "mlp_forward: cannot reserve %zu B of shared memory: %s", smem_pipe, cudaGetErrorString(e));
+                configured_pipe = smem_pipe;
+            }
+            mlp_forward_pipe_kernel<<<ntiles < sms ? ntiles : sms, PIPE_THREADS, smem_pipe, static_cast<cudaStream_t>(stream)>>>(*p, plan, x, wpacked,
+                                                                                                                            bias, out);
+            B200_LAUNCH_CHECK("mlp_forward (pipelined)");
+            return B200GYM_OK;
+        }
+    }
+    // ---- generic serial kernel (odd input widths, N up to 256) ---------------------------------------------------
+    const size_t smem = (TM * kmax + wtot + ((btot + 3) & ~size_t(3))) * 4 + 16;
+    B200_REQUIRE(smem <= 227 * 1024, B200GYM_EINVAL,
+                 "mlp_forward: %zu B of shared memory needed (weights must stay resident); this net is too large for the fused kernel", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_forward_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "mlp_forward: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+        configured = smem;
+    }
+    mlp_forward_serial_kernel<<<ntiles < sms ? ntiles : sms, TM, smem, static_cast<cudaStream_t>(stream)>>>(*p, x, wpacked, bias, out);
     B200_LAUNCH_CHECK("mlp_forward");
     return B200GYM_OK;
 }
