@@ -235,6 +235,9 @@ typedef struct B200MlpParams {
     int32_t dims[B200GYM_MLP_MAX_LAYERS + 1];
 } B200MlpParams;
 int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const float* wpacked, const float* bias, float* out, void* stream);
+/* Debug aid (tools/trace_mlp.py): buf = device buffer of 5*4096*2 uint64 that CTA 0 of the pipelined forward kernel fills
+ * with (event, clock64) pairs; NULL switches tracing off again (the default). */
+int b200gym_debug_mlp_trace(void* buf);
 
 #ifdef __cplusplus
 }

@@ -175,8 +175,22 @@ __global__ void __launch_bounds__(TM, 1) mlp_forward_serial_kernel(const __grid_
 // writes ELU(h) to chunks [0, N_l/4).  x_off is chosen past every hidden activation written after layer 1, so the next
 // tile's input can land while layers 2.. of the current tile are still running.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int PIPE_THREADS = 512;   // warps 0-3 / 4-7: epilogue+MMA warpgroups of slot 0 / 1; warps 8-11 / 12-15: their loaders
-constexpr int CHUNK_BYTES = TM * 16;
+// optional event trace (tools/trace_mlp.py): clock64 stamps of CTA 0, written only when a buffer has been registered
+__device__ unsigned long long* g_mlp_trace = nullptr;
+__device__ __forceinline__ void trace_ev(unsigned long long*& cur, int code) {
+    if (cur) {
+        cur[0] = static_cast<unsigned long long>(code);
+        cur[1] = clock64();
+        cur += 2;
+    }
+}
+constexpr int TRACE_EVENTS = 4096;   // per (slot, role) region, in (code, clock) pairs
+
+constexpr int PIPE_THREADS = 800;   // warps 0-7 / 8-15: epilogue groups of slot 0 / 1 (two warps per TMEM lane quadrant, each takes half of the
+                                    // columns); warps 16-19 / 20-23: loaders of slot 0 / 1; warp 24: MMA issue
+constexpr int EPI_THREADS = 256;
+constexpr int CHUNK_FLOATS = TM * 4 + 4;    // one k-chunk = 128 rows x 16 B, padded by 16 B: a row's chunks fall into different banks
+constexpr int CHUNK_BYTES = CHUNK_FLOATS * 4;
 
 struct PipePlan {
     int x_off;        // first chunk of the X region
@@ -229,7 +243,7 @@ __device__ __forceinline__ void pipe_epilogue_chunk(const uint32_t (&r)[16], con
         for (int j = 0; j < 16; ++j) v[j] = elu_fast(v[j]);
 #pragma unroll
         for (int q = 0; q < 4; ++q)   // next layer's A operand, k = n: chunk (n0/4 + q), this thread's row
-            *reinterpret_cast<float4*>(hrow + static_cast<size_t>(n0 / 4 + q) * (TM * 4)) =
+            *reinterpret_cast<float4*>(hrow + static_cast<size_t>(n0 / 4 + q) * CHUNK_FLOATS) =
                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     } else if (live) {
         if ((out_dim & 3) == 0) {
@@ -245,17 +259,67 @@ __device__ __forceinline__ void pipe_epilogue_chunk(const uint32_t (&r)[16], con
     }
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// long waits (a loader waits a whole tile time for its X region): poll with a back-off instead of hammering the barrier
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
+}
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking phase test
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
+struct LayerDesc {        // per layer, built once per CTA: everything the MMA warp needs
+    uint64_t da0, db0;    // descriptors of the first K step (slot 0); slot 1 adds buf_bytes >> 4 to da0
+    uint32_t idesc, ksteps, inc_b, pad;
+};
+
 __global__ void __launch_bounds__(PIPE_THREADS, 1) mlp_forward_pipe_kernel(const __grid_constant__ B200MlpParams p, const PipePlan plan,
                                                                             const float* __restrict__ x, const float* __restrict__ wpacked,
                                                                             const float* __restrict__ bias, float* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int L = p.num_layers, tid = threadIdx.x, warp = tid >> 5;
-    const size_t buf_floats = static_cast<size_t>(plan.buf_chunks) * (TM * 4);
+    const size_t buf_floats = static_cast<size_t>(plan.buf_chunks) * CHUNK_FLOATS;
     float* sH0 = reinterpret_cast<float*>(smem);
     float* sW = sH0 + 2 * buf_floats;
     float* sB = sW + plan.wtot;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + ((plan.btot + 3) & ~3));   // [0,1] full, [2,3] empty, [4,5] mma done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    // barriers: [0,1] full (loader -> MMA), [2,3] empty (commit -> loader), [4,5] mma done (commit -> epilogue), [6,7] ready (epilogue -> MMA)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + ((plan.btot + 3) & ~3));
+    LayerDesc* sL = reinterpret_cast<LayerDesc*>(bars + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sL + B200GYM_MLP_MAX_LAYERS);
 
     for (int i = tid * 4; i < plan.wtot; i += PIPE_THREADS * 4)
         *reinterpret_cast<float4*>(sW + i) = *reinterpret_cast<const float4*>(wpacked + i);
@@ -264,11 +328,26 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) mlp_forward_pipe_kernel(const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) {
+    if (tid == 32) {
         mbar_init(bars + 0, TM), mbar_init(bars + 1, TM);   // full: every loader thread of the slot arrives
-        mbar_init(bars + 2, 1), mbar_init(bars + 3, 1);     // empty: one arrival by the slot's MMA thread
+        mbar_init(bars + 2, 1), mbar_init(bars + 3, 1);     // empty: tcgen05.commit after the layer that last reads the X region
         mbar_init(bars + 4, 1), mbar_init(bars + 5, 1);     // MMA completion (tcgen05.commit)
+        mbar_init(bars + 6, EPI_THREADS), mbar_init(bars + 7, EPI_THREADS);   // ready: every epilogue thread of the slot arrives
         fence_mbar_init();
+    }
+    if (tid >= 64 && tid < 64 + L) {
+        const int l = tid - 64;
+        int woff = 0;
+        for (int j = 0; j < l; ++j) woff += p.dims[j] * p.dims[j + 1];
+        const int N = p.dims[l + 1];
+        LayerDesc d;
+        d.da0 = umma_desc(sH0 + (l == 0 ? static_cast<size_t>(plan.x_off) * CHUNK_FLOATS : 0), CHUNK_BYTES, 128);
+        d.db0 = umma_desc(sW + woff, N * 16, 128);
+        d.idesc = umma_idesc_tf32(N);
+        d.ksteps = p.dims[l] / 8;
+        d.inc_b = (2 * N * 16) >> 4;   // two 16-byte k-chunks per UMMA K step, in descriptor (16-byte) units
+        d.pad = 0;
+        sL[l] = d;
     }
     fence_proxy_async();   // the weight tile was written through the generic proxy, the tensor core reads it through the async proxy
     tc_fence_before();
@@ -277,98 +356,156 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) mlp_forward_pipe_kernel(const
     const uint32_t tmem = *tmem_slot;
 
     const int ntiles = (p.batch + TM - 1) / TM;
-    const int slot = (warp >> 2) & 1;               // warps 0-3, 8-11 -> slot 0; warps 4-7, 12-15 -> slot 1
-    const int t = tid & (TM - 1);                   // thread within its warpgroup = row within the tile
+    const int slot = warp < 16 ? (warp >> 3) : ((warp >> 2) & 1);   // epilogue warps 0-7 | 8-15, loader warps 16-19 | 20-23
+    const int t = tid & (TM - 1);                   // row within the tile (epilogue: TMEM lane = 32 * (warp % 4) + lane)
     float* sH = sH0 + slot * buf_floats;
-    uint64_t *full = bars + slot, *empty = bars + 2 + slot, *mma_done = bars + 4 + slot;
+    uint64_t *full = bars + slot, *empty = bars + 2 + slot, *mma_done = bars + 4 + slot, *ready = bars + 6 + slot;
 
-    if (warp >= 8) {
+    unsigned long long* tr = nullptr;
+    if (g_mlp_trace && blockIdx.x == 0 && (tid & 31) == 0 && (warp == 0 || warp == 8 || warp == 16 || warp == 20 || warp == 24))
+        tr = g_mlp_trace + static_cast<size_t>(warp == 0 ? 0 : warp == 8 ? 1 : warp == 16 ? 2 : warp == 20 ? 3 : 4) * TRACE_EVENTS * 2;
+    if (warp == 24) {
+        // ------------------------------ MMA warp: serves both slots, layer by layer ------------------------------
+        // Each slot's chain is MMA(l) -> epilogue(l) -> MMA(l+1) ...; the warp serves whichever slot has its operands ready.
+        // Slot 1 is held back until slot 0 has finished its first (longest) epilogue, so that the two slots run in
+        // anti-phase: one slot's epilogue (MUFU/FMA pipes) overlaps the other slot's MMAs instead of its epilogue.
+        const uint32_t buf_desc = static_cast<uint32_t>((buf_floats * 4) >> 4);
+        const uint32_t inc_a = (2 * CHUNK_BYTES) >> 4;
+        const int G = gridDim.x;
+        int lay[2] = {0, 0}, tile_of[2] = {static_cast<int>(blockIdx.x), static_cast<int>(blockIdx.x) + G};
+        uint32_t nstep[2] = {0, 0}, nfull[2] = {0, 0};
+        const uint32_t gate = L < 2 ? 1u : 2u;
+        while (tile_of[0] < ntiles || tile_of[1] < ntiles) {
+            bool progress = false;
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                if (tile_of[sl] >= ntiles) continue;
+                if (sl == 1 && tile_of[0] < ntiles && nstep[0] < gate) continue;
+                // operands ready: the previous epilogue of this slot has written h and drained the accumulator ...
+                if (nstep[sl] > 0 && !mbar_test(bars + 6 + sl, (nstep[sl] - 1) & 1)) continue;
+                // ... and, for the first layer, the loader has delivered the tile
+                if (lay[sl] == 0 && !mbar_test(bars + sl, nfull[sl] & 1)) continue;
+                const int l = lay[sl];
+                const LayerDesc d = sL[l];
+                tc_fence_after();
+                trace_ev(tr, 10 * l + sl);
+                if (elect_one()) {
+                    uint64_t da = d.da0 + (sl ? buf_desc : 0u), db = d.db0;
+                    const uint32_t tacc = tmem + static_cast<uint32_t>(sl * 128);
+                    for (uint32_t ks = 0; ks < d.ksteps; ++ks) {
+                        umma_tf32(tacc, da, db, d.idesc, ks > 0 ? 1u : 0u);
+                        da += inc_a;
+                        db += d.inc_b;
+                    }
+                    umma_commit(bars + 4 + sl);
+                    if (l == plan.free_layer) umma_commit(bars + 2 + sl);   // X region free once these MMAs have retired
+                }
+                __syncwarp();
+                trace_ev(tr, 10 * l + sl + 5);
+                progress = true;
+                ++nstep[sl];
+                if (++lay[sl] == L) {
+                    lay[sl] = 0;
+                    ++nfull[sl];
+                    tile_of[sl] += 2 * G;
+                }
+            }
+            if (!progress) __nanosleep(20);
+        }
+    } else if (warp >= 16) {
         // ------------------------------ loader warpgroup of this slot ------------------------------
+        // 16-byte piece q of the tile (row-major, in_c pieces per row) is loaded by thread q % 128: a warp reads 512 contiguous
+        // bytes per instruction; piece (r, c) lands at chunk c, row r of the X region (the padded chunk stride keeps the
+        // scattered 128-bit stores of a quarter-warp in different banks)
         const int K0c = p.dims[0] / 4, in_c = p.in_dim / 4;
+        const int pieces = TM * in_c;
+        constexpr int PRE = 12;   // 16-byte pieces per thread prefetched into registers (48 floats: the flat observation width)
+        float* xreg = sH + static_cast<size_t>(plan.x_off) * CHUNK_FLOATS;
+        const int r_first = t / in_c, c_first = t - r_first * in_c, dr = TM / in_c, dc = TM - dr * in_c;
         uint32_t ph = 1;   // the first wait on a fresh "empty" barrier falls through
         for (int tile = blockIdx.x + slot * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
-            const int row = tile * TM + t;
-            const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * p.in_stride);
-            float4 v[16];
+            const int row0 = tile * TM;
+            float4 v[PRE];
+            int r = r_first, c = c_first;   // (row, piece) of q = t + TM * j, advanced without divisions
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < in_c && row < p.batch) v[c] = __ldg(src + c);   // L1-allocating: the two 16-B halves of a sector are read by consecutive loads
+            for (int j = 0; j < PRE; ++j) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t + TM * j < pieces && row0 + r < p.batch)
+                    v[j] = ldg_stream4(reinterpret_cast<const float4*>(x + static_cast<size_t>(row0 + r) * p.in_stride) + c);
+                r += dr, c += dc;
+                if (c >= in_c) c -= in_c, ++r;
             }
-            for (int c = 16; c < in_c; ++c) {   // wide inputs: beyond the register-prefetched part (waits for the buffer first)
-                if (c == 16) mbar_wait(empty, ph);
-                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < p.batch) w = __ldg(src + c);
-                *reinterpret_cast<float4*>(sH + (static_cast<size_t>(plan.x_off + c) * TM + t) * 4) = w;
-            }
-            if (in_c <= 16) mbar_wait(empty, ph);
+            trace_ev(tr, 100);
+            mbar_wait_backoff(empty, ph);
             ph ^= 1;
+            trace_ev(tr, 101);
+            r = r_first, c = c_first;
 #pragma unroll
-            for (int c = 0; c < 16; ++c)
-                if (c < K0c) *reinterpret_cast<float4*>(sH + (static_cast<size_t>(plan.x_off + c) * TM + t) * 4) = v[c];
-            for (int c = (in_c > 16 ? in_c : 16); c < K0c; ++c)
-                *reinterpret_cast<float4*>(sH + (static_cast<size_t>(plan.x_off + c) * TM + t) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < PRE; ++j) {
+                if (t + TM * j < pieces) *reinterpret_cast<float4*>(xreg + static_cast<size_t>(c) * CHUNK_FLOATS + r * 4) = v[j];
+                r += dr, c += dc;
+                if (c >= in_c) c -= in_c, ++r;
+            }
+            for (int q = t + TM * PRE; q < pieces; q += TM) {   // inputs wider than 48 floats: the rest goes straight through
+                const int r = q / in_c, c = q - r * in_c;
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + r < p.batch) w = ldg_stream4(reinterpret_cast<const float4*>(x + static_cast<size_t>(row0 + r) * p.in_stride) + c);
+                *reinterpret_cast<float4*>(xreg + static_cast<size_t>(c) * CHUNK_FLOATS + r * 4) = w;
+            }
+            for (int c = in_c; c < K0c; ++c)   // zero padding of the k dimension
+                *reinterpret_cast<float4*>(xreg + static_cast<size_t>(c) * CHUNK_FLOATS + t * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             fence_proxy_async();
             mbar_arrive(full);
+            trace_ev(tr, 102);
         }
     } else {
-        // ------------------------------ MMA + epilogue warpgroup of this slot ------------------------------
-        const uint32_t tacc = tmem + static_cast<uint32_t>(slot * 128);                               // this slot's accumulator columns
-        const uint32_t my_taddr = tacc + (static_cast<uint32_t>((warp & 3) * 32) << 16);              // this warp's TMEM lane quadrant
+        // ------------------------------ epilogue warpgroup of this slot ------------------------------
+        const uint32_t my_taddr = tmem + static_cast<uint32_t>(slot * 128) + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         float* hrow = sH + t * 4;
-        uint32_t ph_full = 0, ph_mma = 0;
+        uint32_t ph_mma = 0;
         for (int tile = blockIdx.x + slot * gridDim.x; tile < ntiles; tile += 2 * gridDim.x) {
             const int row = tile * TM + t;
             const bool live = row < p.batch;
             float* orow = out + static_cast<size_t>(row) * p.out_dim;
-            int woff = 0, boff = 0;
+            int boff = 0;
             for (int l = 0; l < L; ++l) {
-                const int K = p.dims[l], N = p.dims[l + 1];
-                // everyone in the warpgroup has finished writing this layer's A operand and reading the accumulator
-                fence_proxy_async();
-                tc_fence_before();
-                bar_sync_named(1 + slot, TM);
-                if (t == 0) {
-                    if (l == 0) mbar_wait(full, ph_full);
-                    tc_fence_after();
-                    const uint32_t idesc = umma_idesc_tf32(N);
-                    const float* a0 = sH + (l == 0 ? static_cast<size_t>(plan.x_off) * (TM * 4) : 0);
-                    for (int ks = 0; ks < K / 8; ++ks) {
-                        const uint64_t da = umma_desc(a0 + static_cast<size_t>(2 * ks) * TM * 4, CHUNK_BYTES, 128);
-                        const uint64_t db = umma_desc(sW + woff + static_cast<size_t>(2 * ks) * N * 4, N * 16, 128);
-                        umma_tf32(tacc, da, db, idesc, ks > 0 ? 1u : 0u);
-                    }
-                    umma_commit(mma_done);
-                }
+                const int N = p.dims[l + 1];
+                trace_ev(tr, 10 * l + 0);
                 mbar_wait(mma_done, ph_mma);
                 ph_mma ^= 1;
                 tc_fence_after();
-                if (l == plan.free_layer && t == 0) mbar_arrive(empty);   // the X region may take the next tile's input
+                trace_ev(tr, 10 * l + 1);
                 const float* sBl = sB + boff;
+                // two warps share a TMEM lane quadrant: warp-group half h takes columns [h*N/2, (h+1)*N/2) (all 16 when N == 16)
+                const int half = (warp >> 2) & 1;
+                const int c_lo = N >= 32 ? half * (N / 2) : 0, c_hi = N >= 32 ? c_lo + N / 2 : (half == 0 ? N : 0);
                 uint32_t ra[16], rb[16];
-                tmem_ld16_issue(my_taddr, ra);
+                if (c_lo < c_hi) tmem_ld16_issue(my_taddr + c_lo, ra);
                 if (l == L - 1) {
-                    for (int n0 = 0; n0 < N; n0 += 16) {
+                    for (int n0 = c_lo; n0 < c_hi; n0 += 16) {
                         tmem_ld16_wait(ra);
                         pipe_epilogue_chunk<true>(ra, sBl, n0, hrow, orow, p.out_dim, live);
-                        if (n0 + 16 < N) tmem_ld16_issue(my_taddr + n0 + 16, ra);
+                        if (n0 + 16 < c_hi) tmem_ld16_issue(my_taddr + n0 + 16, ra);
                     }
                 } else {
-                    for (int n0 = 0; n0 < N; n0 += 32) {
+                    for (int n0 = c_lo; n0 < c_hi; n0 += 32) {
                         tmem_ld16_wait(ra);
-                        if (n0 + 16 < N) tmem_ld16_issue(my_taddr + n0 + 16, rb);
+                        if (n0 + 16 < c_hi) tmem_ld16_issue(my_taddr + n0 + 16, rb);
                         pipe_epilogue_chunk<false>(ra, sBl, n0, hrow, orow, p.out_dim, live);
-                        if (n0 + 16 < N) {
+                        if (n0 + 16 < c_hi) {
                             tmem_ld16_wait(rb);
-                            if (n0 + 32 < N) tmem_ld16_issue(my_taddr + n0 + 32, ra);
+                            if (n0 + 32 < c_hi) tmem_ld16_issue(my_taddr + n0 + 32, ra);
                             pipe_epilogue_chunk<false>(rb, sBl, n0 + 16, hrow, orow, p.out_dim, live);
                         }
                     }
                 }
-                woff += K * N;
                 boff += N;
+                // this thread's part of the next A operand is written and its accumulator reads are done
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(ready);
+                trace_ev(tr, 10 * l + 2);
             }
-            ph_full ^= 1;
         }
     }
     tc_fence_before();
@@ -377,6 +514,15 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) mlp_forward_pipe_kernel(const
 }
 
 }  // namespace
+
+/* debug: registers (or clears, with NULL) a device buffer of 5 * 4096 * 2 uint64 that CTA 0 of the pipelined kernel fills
+ * with (event code, clock64) pairs — tools/trace_mlp.py turns it into a per-phase cycle budget. */
+extern "C" int b200gym_debug_mlp_trace(void* buf) {
+    unsigned long long* p = static_cast<unsigned long long*>(buf);
+    cudaError_t e = cudaMemcpyToSymbol(g_mlp_trace, &p, sizeof(p));
+    B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "debug_mlp_trace: %s", cudaGetErrorString(e));
+    return B200GYM_OK;
+}
 
 extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const float* wpacked, const float* bias, float* out,
                                    void* stream) {
@@ -415,7 +561,8 @@ extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const
         plan.free_layer = L - 1 < 1 ? L - 1 : 1;
         plan.buf_chunks = hidden_all / 4 > plan.x_off + p->dims[0] / 4 ? hidden_all / 4 : plan.x_off + p->dims[0] / 4;
         plan.wtot = static_cast<int>(wtot), plan.btot = static_cast<int>(btot);
-        const size_t smem_pipe = (2 * static_cast<size_t>(plan.buf_chunks) * TM * 4 + wtot + ((btot + 3) & ~size_t(3))) * 4 + 64;
+        const size_t smem_pipe = (2 * static_cast<size_t>(plan.buf_chunks) * CHUNK_FLOATS + wtot + ((btot + 3) & ~size_t(3))) * 4 + 64 +
+                                 sizeof(LayerDesc) * B200GYM_MLP_MAX_LAYERS + 16;
         static int force_serial = -1;
         if (force_serial < 0) {
             const char* e = getenv("B200GYM_MLP_SERIAL");
