@@ -220,6 +220,14 @@ int b200gym_grad_sumsq(const float* grad, int64_t n, float grad_scale, double* s
 int b200gym_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
                       const double* sumsq, float max_norm, const float* lr, float beta1, float beta2, float eps, int32_t step,
                       void* stream);
+/* The same optimiser step with the Adam step count in DEVICE memory, so that a whole minibatch update (gather, forward,
+ * loss, backward, all-reduce, clip, Adam) can be captured once in a CUDA graph and replayed: b200gym_adam_prepare advances
+ * *step_dev and zeroes *sumsq (launch it before b200gym_grad_sumsq), b200gym_clip_adam_dev derives the bias corrections
+ * 1 - beta^step from *step_dev. */
+int b200gym_adam_prepare(int32_t* step_dev, double* sumsq, void* stream);
+int b200gym_clip_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
+                          const double* sumsq, float max_norm, const float* lr, float beta1, float beta2, float eps,
+                          const int32_t* step_dev, void* stream);
 /* PPO.update adaptive schedule (ppo.py): kl_mean = *kl_sum / count; lr /= 1.5 if kl_mean > 2*desired_kl (floor 1e-5),
  * lr *= 1.5 if 0 < kl_mean < desired_kl/2 (cap 1e-2).  lr lives on the device, so no host sync per minibatch. */
 int b200gym_adaptive_lr(const double* kl_sum, double count, float desired_kl, float* lr, void* stream);

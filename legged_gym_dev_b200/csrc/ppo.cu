@@ -222,6 +222,33 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
     }
 }
 
+// graph-replayable optimiser step: the step count lives in device memory; this 1-thread kernel advances it and zeroes the
+// gradient-norm accumulator in front of grad_sumsq, clip_adam_dev_kernel derives the bias corrections from it.
+__global__ void adam_prepare_kernel(int* __restrict__ step, double* __restrict__ sumsq) {
+    *step += 1;
+    *sumsq = 0.0;
+}
+
+__global__ void __launch_bounds__(256) clip_adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                            float* __restrict__ v, long long n, float scale,
+                                                            const double* __restrict__ sumsq, float max_norm,
+                                                            const float* __restrict__ lr, float b1, float b2, float eps,
+                                                            const int* __restrict__ step) {
+    const float st = static_cast<float>(*step);
+    const float bc1 = 1.0f - powf(b1, st), bc2_sqrt = sqrtf(1.0f - powf(b2, st));
+    const float total = static_cast<float>(sqrt(*sumsq));
+    const float coef = fminf(max_norm / (total + 1e-6f), 1.0f) * scale;   // clip_grad_norm_
+    const float step_size = *lr / bc1;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i] * coef;
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi, v[i] = vi;
+        p[i] -= step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+}
+
 __global__ void adaptive_lr_kernel(const double* __restrict__ kl_sum, double count, float desired_kl, float* __restrict__ lr) {
     const float kl_mean = static_cast<float>(*kl_sum / count);   // ppo.py: adaptive schedule
     float l = *lr;
@@ -304,6 +331,24 @@ int b200gym_clip_adam(float* param, const float* grad, float* exp_avg, float* ex
     clip_adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, grad_scale, sumsq, max_norm, lr,
                                                                         beta1, beta2, eps, bc1, bc2);
     B200_LAUNCH_CHECK("clip_adam");
+    return B200GYM_OK;
+}
+
+int b200gym_adam_prepare(int32_t* step_dev, double* sumsq, void* stream) {
+    B200_REQUIRE(step_dev && sumsq, B200GYM_EINVAL, "adam_prepare: null argument");
+    adam_prepare_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step_dev, sumsq);
+    B200_LAUNCH_CHECK("adam_prepare");
+    return B200GYM_OK;
+}
+
+int b200gym_clip_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
+                          const double* sumsq, float max_norm, const float* lr, float beta1, float beta2, float eps,
+                          const int32_t* step_dev, void* stream) {
+    B200_REQUIRE(param && grad && exp_avg && exp_avg_sq && sumsq && lr && step_dev && n > 0, B200GYM_EINVAL, "clip_adam_dev: bad argument");
+    const int grid = static_cast<int>((n + 1023) / 1024 > 148 * 8 ? 148 * 8 : (n + 1023) / 1024);
+    clip_adam_dev_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, grad_scale, sumsq, max_norm,
+                                                                            lr, beta1, beta2, eps, step_dev);
+    B200_LAUNCH_CHECK("clip_adam_dev");
     return B200GYM_OK;
 }
 

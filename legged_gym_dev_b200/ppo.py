@@ -252,6 +252,9 @@ class PPO:
         self._scalars = torch.zeros(8, dtype=torch.double, device=self.device)
         self._sumsq = torch.zeros(1, dtype=torch.double, device=self.device)
         self._klsum = torch.zeros(2, dtype=torch.double, device=self.device)
+        self._mb_cache = {}
+        self.use_graph = os.environ.get("B200GYM_PPO_GRAPH", "1") != "0"
+        self.tf32_matmul = os.environ.get("B200GYM_PPO_TF32", "1") != "0"
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
@@ -285,50 +288,128 @@ class PPO:
         last_values = self.actor_critic.evaluate(last_critic_obs).detach()
         self.storage.compute_returns(last_values, self.gamma, self.lam)
 
-    def update(self, plan=None):
+    def _minibatch_step(self, mb, world):
+        """One minibatch of PPO.update on the static buffers `mb` (gather target tensors): forward, fused loss + gradient,
+        backward, gradient all-reduce, KL-adaptive LR, clip + Adam.  No host synchronisation: capturable in a CUDA graph."""
         ac, ptr, st = self.actor_critic, _lib.ptr, _lib.stream_ptr(self.device)
+        obs, cobs, act, old_v, ret, old_logp, adv, old_mu, old_sigma = mb["tensors"]
+        B = obs.shape[0]
+        std_off, _ = ac._slices["std"]
+        lp = _lib.PpoLossParamsPOD()
+        lp.num_actions, lp.use_clipped_value_loss = ac.std.numel(), int(self.use_clipped_value_loss)
+        lp.clip_param, lp.value_loss_coef, lp.entropy_coef = self.clip_param, self.value_loss_coef, self.entropy_coef
+        lp.batch, lp.inv_global_batch = B, 1.0 / (B * world)
+        # the training contractions run on the tensor cores in TF32 (SURVEY.md §8a G4: not under the 1e-5 contract);
+        # the flag is read when the GEMMs are enqueued (forward here, backward below) and restored afterwards
+        tf32_was = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32_matmul
+        mu = ac.actor(obs)
+        value = ac.critic(cobs)
+        d_mu, d_value = mb["d_mu"], mb["d_value"]
+        ac.flat_grad.zero_()
+        sc = self._scalars[4:8]
+        sc.zero_()
+        _lib.check(self.lib.b200gym_ppo_loss(lp, ptr(mu), ptr(ac.std), ptr(value), ptr(act), ptr(old_logp), ptr(adv), ptr(ret),
+                                             ptr(old_v), ptr(old_mu), ptr(old_sigma), ptr(d_mu), ptr(d_value),
+                                             C.c_void_p(ac.flat_grad.data_ptr() + 4 * std_off), ptr(sc), st), "ppo_loss")
+        torch.autograd.backward([mu, value], [d_mu, d_value.view(-1, 1)])
+        torch.backends.cuda.matmul.allow_tf32 = tf32_was
+        self._scalars[0:4] += sc
+        # one all-reduce: gradients + (sum kl, count) piggy-backed in the spare tail of the flat buffer
+        tail = ac.flat_grad[ac.num_flat:ac.num_flat + 2]
+        tail[0:1].copy_(sc[0:1])
+        tail[1:2].fill_(float(B))
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ac.flat_grad)
+        if self.desired_kl is not None and self.schedule == "adaptive":
+            self._klsum.copy_(tail)
+            _lib.check(self.lib.b200gym_adaptive_lr(ptr(self._klsum), float(B * world), self.desired_kl, ptr(self.optimizer.lr), st),
+                       "adaptive_lr")
+        self.optimizer.step(self.max_grad_norm)
+
+    def _static_minibatch(self, B):
+        """Persistent gather targets of one minibatch + the captured CUDA graph of `_minibatch_step` on them."""
+        key = (B, self.storage.observations.data_ptr())
+        mb = self._mb_cache.get(key)
+        if mb is not None:
+            return mb
+        st, dev = self.storage, self.device
+        crit = st.privileged_observations if st.privileged_observations is not None else st.observations
+        srcs = [st.observations, crit, st.actions, st.values, st.returns, st.actions_log_prob, st.advantages, st.mu, st.sigma]
+        flat = [t.flatten(0, 1) for t in srcs]
+        n = len(flat)
+        mb = dict(tensors=[torch.empty(B, *f.shape[1:], dtype=f.dtype, device=dev) for f in flat],
+                  idx=torch.zeros(B, dtype=torch.int64, device=dev), d_mu=torch.empty(B, self.actor_critic.std.numel(), device=dev),
+                  d_value=torch.empty(B, device=dev), graph=None)
+        mb["row_bytes"] = (C.c_int32 * n)(*[f.shape[1] * f.element_size() for f in flat])
+        mb["src_ptrs"] = (C.c_void_p * n)(*[f.data_ptr() for f in flat])
+        mb["dst_ptrs"] = (C.c_void_p * n)(*[o.data_ptr() for o in mb["tensors"]])
+        mb["n"] = n
+        self._mb_cache = {key: mb}
+        return mb
+
+    def _gather(self, mb):
+        _lib.check(self.lib.b200gym_gather_rows(mb["dst_ptrs"], mb["src_ptrs"], mb["row_bytes"], mb["n"], _lib.ptr(mb["idx"]),
+                                                mb["idx"].numel(), _lib.stream_ptr(self.device)), "gather_rows")
+
+    def update(self, plan=None):
+        """rsl_rl PPO.update.  The body of one minibatch (gather -> forward -> loss -> backward -> all-reduce -> Adam) is
+        captured ONCE as a CUDA graph and replayed for every minibatch of every epoch; only the row indices change
+        (copied into a static index tensor).  B200GYM_PPO_GRAPH=0 runs the same body eagerly."""
+        ac = self.actor_critic
         world = 1
         if _dist_ready():
             import torch.distributed as dist
             world = dist.get_world_size()
-        n_updates = 0
+        T, N = self.storage.num_transitions_per_env, self.storage.num_envs
+        B = T * N // self.num_mini_batches
+        if plan is None:
+            perm = torch.randperm(self.num_mini_batches * B, device=self.device)
+            plan = [perm[i * B:(i + 1) * B] for _ in range(self.num_learning_epochs) for i in range(self.num_mini_batches)]
+        mb = self._static_minibatch(B)
         self._scalars.zero_()
-        A = ac.std.numel()
-        std_off, _ = ac._slices["std"]
-        lp = _lib.PpoLossParamsPOD()
-        lp.num_actions, lp.use_clipped_value_loss = A, int(self.use_clipped_value_loss)
-        lp.clip_param, lp.value_loss_coef, lp.entropy_coef = self.clip_param, self.value_loss_coef, self.entropy_coef
-        for (obs, cobs, act, old_v, adv, ret, old_logp, old_mu, old_sigma, _, _) in \
-                self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs, plan=plan):
-            B = obs.shape[0]
-            mu = ac.actor(obs)
-            value = ac.critic(cobs)
-            d_mu, d_value = torch.empty_like(mu), torch.empty(B, device=self.device)
-            ac.flat_grad.zero_()
-            lp.batch, lp.inv_global_batch = B, 1.0 / (B * world)
-            sc = self._scalars[4:8]
-            sc.zero_()
-            _lib.check(self.lib.b200gym_ppo_loss(lp, ptr(mu), ptr(ac.std), ptr(value), ptr(act), ptr(old_logp), ptr(adv), ptr(ret),
-                                                 ptr(old_v), ptr(old_mu), ptr(old_sigma), ptr(d_mu), ptr(d_value),
-                                                 C.c_void_p(ac.flat_grad.data_ptr() + 4 * std_off), ptr(sc), st), "ppo_loss")
-            torch.autograd.backward([mu, value], [d_mu, d_value.view(-1, 1)])
-            self._scalars[0:4] += sc
-            # one all-reduce: gradients + (sum kl, count) piggy-backed in the spare tail of the flat buffer
-            tail = ac.flat_grad[ac.num_flat:ac.num_flat + 2]
-            tail[0], tail[1] = sc[0].float(), float(B)
-            if world > 1:
-                dist.all_reduce(ac.flat_grad)
-            if self.desired_kl is not None and self.schedule == "adaptive":
-                self._klsum[0], self._klsum[1] = tail[0].double(), tail[1].double()
-                _lib.check(self.lib.b200gym_adaptive_lr(ptr(self._klsum), float(B * world), self.desired_kl, ptr(self.optimizer.lr), st),
-                           "adaptive_lr")
-            self.optimizer.step(self.max_grad_norm)
+        use_graph = self.use_graph and all(p.numel() == B for p in plan)
+        n_updates = 0
+        for idx in plan:
+            if idx.numel() != B:      # ragged plan (tests): fresh buffers, eager
+                mb = self._static_minibatch(idx.numel())
+            mb["idx"].copy_(idx, non_blocking=True)
+            if not use_graph:
+                self._gather(mb)
+                self._minibatch_step(mb, world)
+            else:
+                if mb["graph"] is None:
+                    self._capture(mb, world)
+                mb["graph"].replay()
+                self.optimizer.steps += 1
             n_updates += 1
         self.storage.clear()
         ac.repack_fused()
-        s = (self._scalars[0:4] / (n_updates * (self.storage.num_envs * self.storage.num_transitions_per_env // self.num_mini_batches)))
+        s = (self._scalars[0:4] / (n_updates * B))
         self.learning_rate = self.optimizer.lr   # device scalar; float(self.learning_rate) syncs on demand
         return s[2], s[1]   # mean_value_loss, mean_surrogate_loss (device scalars)
+
+    def _capture(self, mb, world):
+        """Warm-up on a side stream (cuBLAS workspaces, autograd buffers), restore the optimiser state, then capture."""
+        ac, opt = self.actor_critic, self.optimizer
+        keep = [t.clone() for t in (ac.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.lr, opt.step_dev, self._scalars)]
+        steps = opt.steps
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._gather(mb)
+                self._minibatch_step(mb, world)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._gather(mb)
+            self._minibatch_step(mb, world)
+        for t, k in zip((ac.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.lr, opt.step_dev, self._scalars), keep):
+            t.copy_(k)
+        opt.steps = steps
+        mb["graph"] = g
 
 
 class FlatAdam:
@@ -341,17 +422,19 @@ class FlatAdam:
         self.exp_avg = torch.zeros_like(ac.flat_param)
         self.exp_avg_sq = torch.zeros_like(ac.flat_param)
         self.steps = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._sumsq = torch.zeros(1, dtype=torch.double, device=dev)
         self.lib = _lib.lib()
 
     def step(self, max_grad_norm):
+        """clip_grad_norm_ + Adam; the step count is device-resident (CUDA-graph replayable), `steps` mirrors it on the host."""
         ac, ptr, st = self.ac, _lib.ptr, _lib.stream_ptr(self.ac.flat_param.device)
         self.steps += 1
-        self._sumsq.zero_()
+        _lib.check(self.lib.b200gym_adam_prepare(ptr(self.step_dev), ptr(self._sumsq), st), "adam_prepare")
         _lib.check(self.lib.b200gym_grad_sumsq(ptr(ac.flat_grad), ac.num_flat, 1.0, ptr(self._sumsq), st), "grad_sumsq")
-        _lib.check(self.lib.b200gym_clip_adam(ptr(ac.flat_param), ptr(ac.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), ac.num_flat,
-                                              1.0, ptr(self._sumsq), max_grad_norm, ptr(self.lr), self.betas[0], self.betas[1], self.eps,
-                                              self.steps, st), "clip_adam")
+        _lib.check(self.lib.b200gym_clip_adam_dev(ptr(ac.flat_param), ptr(ac.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                                  ac.num_flat, 1.0, ptr(self._sumsq), max_grad_norm, ptr(self.lr), self.betas[0],
+                                                  self.betas[1], self.eps, ptr(self.step_dev), st), "clip_adam_dev")
 
     def grad_norm(self):
         return torch.sqrt(self._sumsq[0])
@@ -364,6 +447,7 @@ class FlatAdam:
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.steps = sd["steps"]
+        self.step_dev.fill_(self.steps)
 
 
 class OnPolicyRunner:

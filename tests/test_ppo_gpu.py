@@ -77,7 +77,8 @@ def _fill(alg, ref, T, N, num_obs, seed=2):
         logp = d.log_prob(actions).sum(-1, keepdim=True)
         values = ref.critic(obs)
     rewards, _, dones, time_outs, last_values = make_storage_inputs(T, N, seed)
-    alg.init_storage(N, T, [num_obs], [None], [12])
+    if alg.storage is None or (alg.storage.num_envs, alg.storage.num_transitions_per_env) != (N, T):
+        alg.init_storage(N, T, [num_obs], [None], [12])
     st = alg.storage
     for name, t in dict(observations=obs, actions=actions, actions_log_prob=logp, values=values, mu=d.mean, sigma=d.stddev,
                         rewards=rewards, dones=dones, time_outs=time_outs).items():
@@ -133,9 +134,12 @@ def test_ppo_loss_gradients_match_autograd():
     assert_close(sc[3].cpu() / B, ent.mean().detach().double(), 1.0, "entropy", rtol=1e-4)
 
 
-def test_ppo_update_tracks_oracle():
-    """cfg 5 shape: flat nets [128,64,32], 4 minibatches; identical LR decisions, parameters within 1e-3."""
+@pytest.mark.parametrize("graph", [True, False])
+def test_ppo_update_tracks_oracle(graph):
+    """cfg 5 shape: flat nets [128,64,32], 4 minibatches; identical LR decisions, parameters within 1e-3.  graph=True: the
+    minibatch step replayed from one captured CUDA graph (the default), graph=False: the same body launched eagerly."""
     ref, alg = _oracle_and_fused()
+    alg.use_graph, alg.tf32_matmul = graph, False     # fp32 library GEMMs on both sides: parameter-level parity
     T, N = 24, 512
     store = _fill(alg, ref, T, N, 48)
     plan = O.mini_batch_indices(T, N, 4, 2, generator=torch.Generator().manual_seed(3))
@@ -143,7 +147,49 @@ def test_ppo_update_tracks_oracle():
     lr, stats = O.ppo_update(ref, opt, store, plan, 1e-3, desired_kl=0.01, max_grad_norm=1.0, schedule="adaptive", clip_param=0.2,
                              value_loss_coef=1.0, entropy_coef=0.01, use_clipped_value_loss=True)
     alg.update(plan=[p.cuda() for p in plan])
+    assert alg.optimizer.steps == len(plan) and int(alg.optimizer.step_dev) == len(plan)
     assert abs(float(alg.optimizer.lr) - lr) <= 1e-9 + 1e-6 * lr, (float(alg.optimizer.lr), lr, [s["lr"] for s in stats])
     sd = alg.actor_critic.state_dict()
     for k, v in ref.state_dict().items():
         assert_close(sd[k].cpu(), v, 1.0, f"parameter {k} after update", rtol=1e-3)
+
+
+def test_graph_and_eager_updates_agree_over_two_iterations():
+    """Second update() reuses the captured graph (new indices, advanced Adam step): must match the eager path closely."""
+    outs = []
+    for graph in (True, False):
+        ref, alg = _oracle_and_fused(seed=5)
+        alg.use_graph, alg.tf32_matmul = graph, False
+        T, N = 8, 256
+        for it in range(2):
+            _fill(alg, ref, T, N, 48, seed=7 + it)
+            plan = O.mini_batch_indices(T, N, 4, 2, generator=torch.Generator().manual_seed(11 + it))
+            alg.storage.step = T
+            alg.update(plan=[p.cuda() for p in plan])
+        outs.append((alg.actor_critic.flat_param.clone(), float(alg.optimizer.lr), alg.optimizer.steps))
+    assert outs[0][2] == outs[1][2] == 16
+    assert outs[0][1] == outs[1][1]
+    assert_close(outs[0][0].cpu(), outs[1][0].cpu(), 1.0, "flat parameters graph vs eager", rtol=2e-4)
+
+
+def test_ppo_update_tf32_contractions():
+    """Default mode: the training GEMMs run in TF32 on the tensor cores.  SURVEY.md §8d cfg 5 contract for that path:
+    losses to 1e-3 relative and identical LR-schedule decisions (Adam's sign-like first steps make a parameter-level
+    1e-3 bound meaningless at TF32: a flipped 1e-7 gradient moves a weight by 2 lr); parameters are checked at 5 lr."""
+    ref, alg = _oracle_and_fused()
+    assert alg.tf32_matmul and alg.use_graph
+    T, N = 24, 512
+    store = _fill(alg, ref, T, N, 48)
+    plan = O.mini_batch_indices(T, N, 4, 2, generator=torch.Generator().manual_seed(3))
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    lr, stats = O.ppo_update(ref, opt, store, plan, 1e-3, desired_kl=0.01, max_grad_norm=1.0, schedule="adaptive", clip_param=0.2,
+                             value_loss_coef=1.0, entropy_coef=0.01, use_clipped_value_loss=True)
+    v_loss, s_loss = alg.update(plan=[p.cuda() for p in plan])
+    assert abs(float(alg.optimizer.lr) - lr) <= 1e-9 + 1e-6 * lr, (float(alg.optimizer.lr), lr, [s["lr"] for s in stats])
+    want_v = sum(s["value_loss"] for s in stats) / len(stats)
+    want_s = sum(s["surrogate"] for s in stats) / len(stats)
+    assert abs(float(v_loss) - want_v) <= 1e-3 * abs(want_v) + 1e-6, (float(v_loss), want_v)
+    assert abs(float(s_loss) - want_s) <= 1e-3 * max(abs(want_s), 0.05), (float(s_loss), want_s)
+    sd = alg.actor_critic.state_dict()
+    worst = max((sd[k].cpu() - v).abs().max().item() for k, v in ref.state_dict().items())
+    assert worst <= 10 * max(s["lr"] for s in stats), worst
