@@ -3,7 +3,8 @@
 
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on): anymal_c_flat env step —
 4 x PD torques + the fused post-physics pass — upstream reward table (SURVEY.md §8d cfg 2b), on a replayed
-synthetic state tape, `--envs` environments per GPU (default 131072 = 1M envs on 8 GPUs).  One "step" = one
+synthetic state tape, `--envs` environments per GPU (default 1 048 576: the 1M-env end of the metric's range on ONE
+B200; the `sweep` key carries 4096 ... 1M including 131 072 = the per-GPU shard of 1M envs on 8 GPUs).  One "step" = one
 `env.step(actions)` for every env.  `value` = env-steps/s with the tape resident in HBM; `e2e` = the same
 step driven through the public API from PINNED HOST buffers (H2D of the step's physics state + actions, D2H
 of obs/rew/reset inside the timed region).
@@ -33,7 +34,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--envs", type=int, default=131072, help="environments per GPU")
+    ap.add_argument("--envs", type=int, default=1048576, help="environments per GPU")
     ap.add_argument("--frames", type=int, default=8, help="frames of the replay tape")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-envs", type=int, default=16384, help="envs of the bounded CPU-baseline sample")
@@ -125,7 +126,11 @@ def build_env(num_envs, frames, device, rank, copy=False, host=False):
     from legged_gym_dev_b200.physics import ReplayPhysics, HostReplayPhysics
     import legged_case as LC
     cfg = workload_cfg(num_envs)
-    tape = S.make_state_tape(num_envs, frames=frames, seed=100 + rank, device="cpu" if host else device)
+    tape = S.make_state_tape(num_envs, frames=frames, seed=100 + rank, device=device)
+    if host:   # generated on the device (fast), then moved to the host: the e2e arm replays it from pinned host memory
+        for k in ("root", "dof", "contact", "actions"):
+            setattr(tape, k, getattr(tape, k).cpu())
+        torch.cuda.empty_cache()
     phys = HostReplayPhysics(tape, device=device) if host else ReplayPhysics(tape, device=device, copy=copy)
     lim = LC.dof_limits()
     env = Anymal(cfg, SimpleNamespace(dt=cfg.sim.dt), None, device, True, physics=phys, asset=lim, seed=0,
@@ -315,8 +320,8 @@ def main():
     if not args.no_e2e:
         del env
         torch.cuda.empty_cache()
-        esteps = max(5, min(args.steps, 30))
-        dt, h2d, d2h = e2e_run(N, min(args.frames, 4), esteps, 3, device, rank, world)
+        esteps = max(5, min(args.steps, 30 if N <= 262144 else 12))
+        dt, h2d, d2h = e2e_run(N, 2 if N > 262144 else min(args.frames, 4), esteps, 3, device, rank, world)
         e2e = {"value": world * N * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": esteps, "note": "LeggedRobot.step through the C ABI with pinned-host physics frames + actions in, obs/rew/reset out"}
 
@@ -324,7 +329,7 @@ def main():
     extra = None
     if world == 1 and not args.no_sweep:
         sweep = {}
-        for n in (4096, 16384, 65536, 262144, 1048576):
+        for n in (4096, 16384, 65536, 131072, 262144, 1048576):
             e2, tp2 = build_env(n, 4, device, 0)
             a2 = [tp2.actions[f].to(device) for f in range(4)]
             m2 = time_steps(e2, a2, 100, 10, 1, device)
