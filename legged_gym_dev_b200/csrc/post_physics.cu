@@ -73,12 +73,29 @@ __device__ __forceinline__ float norm3_rn(float x, float y, float z) {
 __device__ __forceinline__ float sq2_rn(float x, float y) { return add_rn(mul_rn(x, x), mul_rn(y, y)); }
 __device__ __forceinline__ float sq3_rn(float x, float y, float z) { return add_rn(add_rn(mul_rn(x, x), mul_rn(y, y)), mul_rn(z, z)); }
 
-// Correctly rounded x / d for a loop-invariant divisor with rcp = RN(1/d): q0 = RN(x*rcp); r = x - q0*d (exact, FMA);
-// q = RN(q0 + r*rcp) (Markstein).  Three instructions instead of the ~15 of the general IEEE division; the height-cell
-// index depends on the exact quotient, the parity tests compare the cells bit for bit.
-__device__ __forceinline__ float div_const_rn(float x, float d, float rcp) {
-    const float q0 = mul_rn(x, rcp);
-    return fmaf(fmaf(-q0, d, x), rcp, q0);
+// Height-scan cell index of TWO sample points at once (legged_robot.py:896-907 with quat_apply_yaw, math.py:38-42), every
+// operation a separately rounded fp32 mul/add exactly as torch evaluates it, issued as packed f32x2 instructions:
+//   t = 2 * cross(q_yaw.xyz, p) = (-2 qz hy, 2 qz hx);  w = p + qw t + cross(q_yaw.xyz, t);  cell = trunc((w + base + border) / hs)
+struct HeightConsts { float2 border, neg_hs, rcp_hs; };
+__device__ __forceinline__ void height_cells2(float2 hx, float2 hy, float qz, float qw, float bx, float by, const HeightConsts& c,
+                                              int rows, int cols, int& off0, int& off1) {
+    const float2 qz2 = make_float2(qz, qz), nqz2 = make_float2(-qz, -qz), qw2 = make_float2(qw, qw);
+    const float2 tx = __fmul2_rn(__fmul2_rn(qz2, hy), make_float2(-2.0f, -2.0f));   // == (-(qz*hy)) * 2
+    const float2 ty = __fmul2_rn(__fmul2_rn(qz2, hx), make_float2(2.0f, 2.0f));
+    float2 wx = __fadd2_rn(__fadd2_rn(hx, __fmul2_rn(qw2, tx)), __fmul2_rn(nqz2, ty));   // (hx + qw*tx) + (-(qz*ty))
+    float2 wy = __fadd2_rn(__fadd2_rn(hy, __fmul2_rn(qw2, ty)), __fmul2_rn(qz2, tx));
+    wx = __fadd2_rn(__fadd2_rn(wx, make_float2(bx, bx)), c.border);
+    wy = __fadd2_rn(__fadd2_rn(wy, make_float2(by, by)), c.border);
+    // correctly rounded x / hs for the loop-invariant cell size with rcp = RN(1/hs): q0 = RN(x*rcp); r = x - q0*hs (exact, FMA);
+    // q = RN(q0 + r*rcp) (Markstein) — two lanes at a time; the parity tests compare the cells bit for bit
+    const float2 qx0 = __fmul2_rn(wx, c.rcp_hs), qy0 = __fmul2_rn(wy, c.rcp_hs);
+    wx = __ffma2_rn(__ffma2_rn(qx0, c.neg_hs, wx), c.rcp_hs, qx0);
+    wy = __ffma2_rn(__ffma2_rn(qy0, c.neg_hs, wy), c.rcp_hs, qy0);
+    // .long() truncation + clip (legged_robot.py:903-907); the saturating conversion keeps huge values clipped
+    const int ix0 = min(max(__float2int_rz(wx.x), 0), rows - 2), iy0 = min(max(__float2int_rz(wy.x), 0), cols - 2);
+    const int ix1 = min(max(__float2int_rz(wx.y), 0), rows - 2), iy1 = min(max(__float2int_rz(wy.y), 0), cols - 2);
+    off0 = ix0 * cols + iy0;
+    off1 = ix1 * cols + iy1;
 }
 
 __device__ __forceinline__ float wrap_to_pi(float a) {
@@ -137,15 +154,15 @@ struct TileSmem {
     float *sums, *obs, *blv, *bav, *pg, *lrv, *rew, *part;
     uint8_t *reset, *tout;
     int16_t* hraw;
-    float *bh, *zpost, *stage;
-    float2* pts;
+    float *bh, *zpost, *stage, *hpart;
+    float2 *pts, *yaw;
     double* acc;
     int* nreset;
     size_t bytes;
 };
 
 template <int TILE, bool ROUGH>
-__device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K) {
+__device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K, bool need_hpart) {
     Carver c{base, 0};
     TileSmem s;
     s.bar = c.take<uint64_t>(2);
@@ -175,14 +192,17 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
     s.nreset = c.take<int>(4);
     if (ROUGH) {
         s.hraw = nullptr;
-        s.bh = c.take<float>(TILE);
+        s.bh = nullptr;
         s.zpost = c.take<float>(TILE);
-        s.stage = c.take<float>((TILE * LPE / 32) * 128);
+        s.stage = nullptr;
+        s.yaw = c.take<float2>(TILE);
+        s.hpart = need_hpart ? c.take<float>(TILE * (HPAD / 4)) : nullptr;
         s.pts = c.take<float2>(HPAD);
     } else {
         s.hraw = nullptr;
-        s.bh = s.zpost = s.stage = nullptr;
+        s.bh = s.zpost = s.stage = s.hpart = nullptr;
         s.pts = nullptr;
+        s.yaw = nullptr;
     }
     s.bytes = c.off;
     return s;
@@ -200,8 +220,8 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
                                                                                const SqThr thr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int B = p.num_bodies, K = p.num_sum_rows, N = p.num_envs, O = p.num_obs;
-    const TileSmem s = carve_tile<TILE, ROUGH>(smem_raw, B, K);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileSmem s = carve_tile<TILE, ROUGH>(smem_raw, B, K, p.reward_scale[T_BASE_HEIGHT] != 0.0f);
+    const int tid = threadIdx.x;
     const int tile0 = blockIdx.x * TILE;
     const int nvalid = min(TILE, N - tile0);
     const bool full = (nvalid == TILE);
@@ -220,7 +240,8 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
     if (b.step_counter) step = *b.step_counter;
     if (tid < B200GYM_NUM_REWARD_TERMS + 2) s.acc[tid] = 0.0;
     if (ROUGH) {   // base-frame sample points (legged_robot.py:861-875), tabulated once per CTA
-        for (int pt = tid; pt < p.num_heights; pt += TILE * LPE) s.pts[pt] = make_float2(p.points_x[pt / p.n_py], p.points_y[pt % p.n_py]);
+        for (int pt = tid; pt < HPAD; pt += TILE * LPE)
+            s.pts[pt] = pt < p.num_heights ? make_float2(p.points_x[pt / p.n_py], p.points_y[pt % p.n_py]) : make_float2(0.f, 0.f);
     }
     __syncthreads();
     do_push = s.nreset[1];
@@ -261,75 +282,69 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         __syncthreads();
     }
 
-    // ---- phase H: height scan + height observations, one warp per env (legged_robot.py:877-915, math.py:38-42, :220-226)
-    // The observation needs the POST-reset base height; resets are rare, so the observation is produced here with the
-    // current height and redone after phase S only for the envs that did reset (phase H').
+    // ---- phase H: height scan + height observations (legged_robot.py:877-915, math.py:38-42, :220-226) ----------------
+    // Work item = (env, quad of 4 consecutive sample points); the (env, quad) pairs of the tile are flattened over the 128
+    // threads, so no lane idles on the 187 -> 192 padding and every item owns exactly one Philox block (the 4 noise
+    // draws of its 4 points): nothing is exchanged between lanes.  The index chain keeps torch's un-fused fp32 rounding
+    // (the cell index depends on it) but runs two points per instruction (mul/add/fma.rn.f32x2).
+    // The observation needs the POST-reset base height; resets are rare, so it is produced here with the current height
+    // and redone after phase S only for the envs that did reset (phase H').
+    // (A/B, profiles/r1_post_physics_rough.md: staging per-env terrain patches in shared memory for the gathers was slower
+    // than letting the 3 x 187 int16 gathers hit L1 — the patch of a robot is ~1 KB and stays L1-resident anyway.)
     if (ROUGH) {
-        const int H = p.num_heights;
+        if (tid < nvalid) {   // quat_apply_yaw: zero x,y, renormalise (un-fused fp32), once per env
+            const float* R = s.root + tid * 13;
+            const float nq = fmaxf(sqrtf(add_rn(mul_rn(R[5], R[5]), mul_rn(R[6], R[6]))), 1e-9f);
+            s.yaw[tid] = make_float2(div_rn(R[5], nq), div_rn(R[6], nq));
+        }
+        __syncthreads();
+        const int H = p.num_heights, Q = (H + 3) >> 2;
         const int rows = p.terrain_rows, cols = p.terrain_cols;
         const float inv_hs = div_rn(1.0f, p.horizontal_scale);
-        float* stage = s.stage + warp * 128;
-        for (int e = warp; e < nvalid; e += TILE * LPE / 32) {
+        const HeightConsts hc = {make_float2(p.border_size, p.border_size), make_float2(-p.horizontal_scale, -p.horizontal_scale),
+                                 make_float2(inv_hs, inv_hs)};
+        const int de = (TILE * LPE) / Q, dq = (TILE * LPE) - de * Q;
+        int e = tid / Q, q = tid - e * Q;
+        for (int i = tid; i < nvalid * Q; i += TILE * LPE) {
             const float* R = s.root + e * 13;
-            const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
-            // quat_apply_yaw: zero x,y, renormalise, rotate — un-fused fp32 ops, the cell index depends on them
-            const float nq = fmaxf(sqrtf(add_rn(mul_rn(R[5], R[5]), mul_rn(R[6], R[6]))), 1e-9f);
-            const float qz = div_rn(R[5], nq), qw = div_rn(R[6], nq);
-            const float z05 = sub_rn(R[2], 0.5f);
-            float part = 0.0f;
-            float* mh_out = b.measured_heights + static_cast<size_t>(tile0 + e) * H;
-            float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48;
-            for (int c0 = 0; c0 < H; c0 += 128) {   // chunks of 128 points = 32 Philox blocks, one per lane
-                if (p.add_noise) {
-                    const int nb = (c0 >> 2) + lane;
-                    float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-                    if (4 * nb < H) u = philox::u01(rng.words(philox::OBS_NOISE, 12 + nb));
-                    *reinterpret_cast<float4*>(stage + 4 * lane) = u;
-                    __syncwarp();
-                }
-                // index all 4 points of this lane first, then issue their 12 gathers together (one L2 latency per chunk)
-                const int16_t* hs[4];
+            const float2 yw = s.yaw[e];
+            const float rz = R[2], z05 = sub_rn(rz, 0.5f);
+            const int pt0 = 4 * q;
+            int raw[4] = {0, 0, 0, 0};
+            if (!p.mesh_plane) {
+                const float4 pa = *reinterpret_cast<const float4*>(s.pts + pt0), pb = *reinterpret_cast<const float4*>(s.pts + pt0 + 2);
+                int off[4];
+                height_cells2(make_float2(pa.x, pa.z), make_float2(pa.y, pa.w), yw.x, yw.y, R[0], R[1], hc, rows, cols, off[0], off[1]);
+                height_cells2(make_float2(pb.x, pb.z), make_float2(pb.y, pb.w), yw.x, yw.y, R[0], R[1], hc, rows, cols, off[2], off[3]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int pt = c0 + 32 * j + lane;
-                    hs[j] = nullptr;
-                    if (pt < H && !p.mesh_plane) {
-                        const float2 hp = s.pts[pt];
-                        const float hx = hp.x, hy = hp.y;
-                        const float tx = mul_rn(-mul_rn(qz, hy), 2.0f), ty = mul_rn(mul_rn(qz, hx), 2.0f);
-                        float wx = add_rn(add_rn(hx, mul_rn(qw, tx)), -mul_rn(qz, ty));
-                        float wy = add_rn(add_rn(hy, mul_rn(qw, ty)), mul_rn(qz, tx));
-                        wx = div_const_rn(add_rn(add_rn(wx, R[0]), p.border_size), p.horizontal_scale, inv_hs);
-                        wy = div_const_rn(add_rn(add_rn(wy, R[1]), p.border_size), p.horizontal_scale, inv_hs);
-                        // .long() truncation + clip (legged_robot.py:903-907); the saturating conversion keeps huge values clipped
-                        const int ix = min(max(__float2int_rz(wx), 0), rows - 2), iy = min(max(__float2int_rz(wy), 0), cols - 2);
-                        hs[j] = b.height_samples + ix * cols + iy;
-                    }
+                for (int j = 0; j < 4; ++j) {   // 12 gathers issued together; padding points read a valid (unused) cell
+                    const int16_t* h = b.height_samples + off[j];
+                    raw[j] = min(min(static_cast<int>(__ldg(h)), static_cast<int>(__ldg(h + cols))), static_cast<int>(__ldg(h + 1)));
                 }
-                int raw[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    raw[j] = 0;
-                    if (hs[j]) raw[j] = min(min(static_cast<int>(__ldg(hs[j])), static_cast<int>(__ldg(hs[j] + cols))),
-                                            static_cast<int>(__ldg(hs[j] + 1)));
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int pt = c0 + 32 * j + lane;
-                    if (pt < H) {
-                        const float mh = mul_rn(static_cast<float>(raw[j]), p.vertical_scale);
-                        mh_out[pt] = mh;
-                        part += R[2] - mh;
-                        float v = clampf(sub_rn(z05, mh), -1.0f, 1.0f) * p.obs_height;
-                        if (p.add_noise) v = add_noise(v, stage[32 * j + lane], p.noise_height);
-                        ob_out[pt] = clampf(v, -p.clip_obs, p.clip_obs);
-                    }
-                }
-                __syncwarp();
             }
+            float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+            if (p.add_noise) {
+                const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
+                u = philox::u01(rng.words(philox::OBS_NOISE, 12 + q));
+            }
+            const float un[4] = {u.x, u.y, u.z, u.w};
+            float* mh_out = b.measured_heights + static_cast<size_t>(tile0 + e) * H + pt0;
+            float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48 + pt0;
+            float part = 0.0f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if (lane == 0) s.bh[e] = part / static_cast<float>(H);
+            for (int j = 0; j < 4; ++j) {
+                if (pt0 + j < H) {
+                    const float mh = mul_rn(static_cast<float>(raw[j]), p.vertical_scale);
+                    mh_out[j] = mh;
+                    part += rz - mh;
+                    float v = clampf(sub_rn(z05, mh), -1.0f, 1.0f) * p.obs_height;
+                    if (p.add_noise) v = add_noise(v, un[j], p.noise_height);
+                    ob_out[j] = clampf(v, -p.clip_obs, p.clip_obs);
+                }
+            }
+            if (s.hpart) s.hpart[e * (HPAD / 4) + q] = part;
+            e += de, q += dq;
+            if (q >= Q) q -= Q, ++e;
         }
     }
 
@@ -506,7 +521,14 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         if (rs[T_ACTION_RATE] != 0.f) add_term(T_ACTION_RATE, P[P_ACTION_RATE * TILE]);
         if (rs[T_ANG_VEL_XY] != 0.f) add_term(T_ANG_VEL_XY, bax * bax + bay * bay);
         if (rs[T_BASE_HEIGHT] != 0.f) {
-            const float dh = (ROUGH ? s.bh[e] : R[2]) - p.base_height_target;
+            float bh = R[2];
+            if (ROUGH) {   // mean(root_z - measured_heights) (legged_robot.py:938-939): the quads' partial sums in a fixed order
+                const int Q = (p.num_heights + 3) >> 2;
+                float acc = 0.0f;
+                for (int q = 0; q < Q; ++q) acc += s.hpart[e * (HPAD / 4) + q];
+                bh = acc / static_cast<float>(p.num_heights);
+            }
+            const float dh = bh - p.base_height_target;
             add_term(T_BASE_HEIGHT, dh * dh);
         }
         if (rs[T_COLLISION] != 0.f) add_term(T_COLLISION, P[P_COLL * TILE]);
@@ -699,32 +721,34 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
 
     // ---- phase H': height observations of the envs that reset this step, redone with the post-reset base height ----
     if (ROUGH) {
-        const int H = p.num_heights;
-        float* stage = s.stage + warp * 128;
-        for (int e = warp; e < nvalid; e += TILE * LPE / 32) {
-            if (!s.reset[e]) continue;
-            const float z05 = sub_rn(s.zpost[e], 0.5f);
-            const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
-            const float* mh_in = b.measured_heights + static_cast<size_t>(tile0 + e) * H;   // written by this CTA in phase H
-            float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48;
-            for (int c0 = 0; c0 < H; c0 += 128) {
-                if (p.add_noise) {
-                    const int nb = (c0 >> 2) + lane;
+        __syncthreads();   // measured_heights written in phase H by other threads of this CTA
+        if (*s.nreset > 0) {
+            const int H = p.num_heights, Q = (H + 3) >> 2;
+            const int de = (TILE * LPE) / Q, dq = (TILE * LPE) - de * Q;
+            int e = tid / Q, q = tid - e * Q;
+            for (int i = tid; i < nvalid * Q; i += TILE * LPE) {
+                if (s.reset[e]) {
+                    const float z05 = sub_rn(s.zpost[e], 0.5f);
+                    const int pt0 = 4 * q;
                     float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-                    if (4 * nb < H) u = philox::u01(rng.words(philox::OBS_NOISE, 12 + nb));
-                    *reinterpret_cast<float4*>(stage + 4 * lane) = u;
-                    __syncwarp();
-                }
+                    if (p.add_noise) {
+                        const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
+                        u = philox::u01(rng.words(philox::OBS_NOISE, 12 + q));
+                    }
+                    const float un[4] = {u.x, u.y, u.z, u.w};
+                    const float* mh_in = b.measured_heights + static_cast<size_t>(tile0 + e) * H + pt0;
+                    float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48 + pt0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int pt = c0 + 32 * j + lane;
-                    if (pt < H) {
-                        float v = clampf(sub_rn(z05, mh_in[pt]), -1.0f, 1.0f) * p.obs_height;
-                        if (p.add_noise) v = add_noise(v, stage[32 * j + lane], p.noise_height);
-                        ob_out[pt] = clampf(v, -p.clip_obs, p.clip_obs);
+                    for (int j = 0; j < 4; ++j) {
+                        if (pt0 + j < H) {
+                            float v = clampf(sub_rn(z05, mh_in[j]), -1.0f, 1.0f) * p.obs_height;
+                            if (p.add_noise) v = add_noise(v, un[j], p.noise_height);
+                            ob_out[j] = clampf(v, -p.clip_obs, p.clip_obs);
+                        }
                     }
                 }
-                __syncwarp();
+                e += de, q += dq;
+                if (q >= Q) q -= Q, ++e;
             }
         }
     }
@@ -788,7 +812,7 @@ static float sq_lt(float t) {
 template <int TILE, bool ROUGH>
 int launch_post_physics(const B200LeggedParams& p, const B200LeggedBuffers& b, uint64_t step, long long env_off, int do_push,
                         cudaStream_t stream) {
-    const size_t smem = carve_tile<TILE, ROUGH>(nullptr, p.num_bodies, p.num_sum_rows).bytes;
+    const size_t smem = carve_tile<TILE, ROUGH>(nullptr, p.num_bodies, p.num_sum_rows, p.reward_scale[T_BASE_HEIGHT] != 0.0f).bytes;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(post_physics_kernel<TILE, ROUGH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
