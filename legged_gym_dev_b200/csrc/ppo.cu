@@ -55,24 +55,45 @@ __global__ void __launch_bounds__(256) gae_returns_kernel(float* __restrict__ re
     if (n < N) {
         float adv = 0.0f, next_v = last_values[n];
         const float gl = mul_rn(gamma, lam);
-        for (int t = T - 1; t >= 0; --t) {
-            const size_t i = static_cast<size_t>(t) * N + n;
-            const float v = values[i];
-            float r = rewards[i];
-            if (time_outs && time_outs[i]) {   // PPO.process_env_step: rewards += gamma * values * time_outs
-                r = add_rn(r, mul_rn(gamma, v));
-                rewards[i] = r;
+        // The recurrence is sequential in t, the memory traffic is not: the inputs of CH time steps are fetched together
+        // (CH independent loads in flight per thread) before the CH dependent updates run — at 4096 envs the kernel is a
+        // chain of DRAM round trips, not a bandwidth problem (profiles/r1_kernels_ncu.md).
+        constexpr int CH = 8;
+        for (int t1 = T; t1 > 0; t1 -= CH) {
+            const int cnt = t1 < CH ? t1 : CH;
+            float v[CH], r[CH];
+            unsigned char dn[CH], to[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                if (k < cnt) {
+                    const size_t i = static_cast<size_t>(t1 - 1 - k) * N + n;
+                    v[k] = values[i];
+                    r[k] = rewards[i];
+                    dn[k] = dones[i];
+                    to[k] = time_outs ? time_outs[i] : static_cast<unsigned char>(0);
+                }
             }
-            const float nt = dones[i] ? 0.0f : 1.0f;
-            const float delta = sub_rn(add_rn(r, mul_rn(mul_rn(nt, gamma), next_v)), v);
-            adv = add_rn(delta, mul_rn(mul_rn(nt, gl), adv));
-            const float ret = add_rn(adv, v);
-            returns[i] = ret;
-            const float a = sub_rn(ret, v);
-            advantages[i] = a;
-            acc[0] += a;
-            acc[1] += static_cast<double>(a) * a;
-            next_v = v;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                if (k < cnt) {
+                    const size_t i = static_cast<size_t>(t1 - 1 - k) * N + n;
+                    float rr = r[k];
+                    if (to[k]) {   // PPO.process_env_step: rewards += gamma * values * time_outs
+                        rr = add_rn(rr, mul_rn(gamma, v[k]));
+                        rewards[i] = rr;
+                    }
+                    const float nt = dn[k] ? 0.0f : 1.0f;
+                    const float delta = sub_rn(add_rn(rr, mul_rn(mul_rn(nt, gamma), next_v)), v[k]);
+                    adv = add_rn(delta, mul_rn(mul_rn(nt, gl), adv));
+                    const float ret = add_rn(adv, v[k]);
+                    returns[i] = ret;
+                    const float a = sub_rn(ret, v[k]);
+                    advantages[i] = a;
+                    acc[0] += a;
+                    acc[1] += static_cast<double>(a) * a;
+                    next_v = v[k];
+                }
+            }
         }
         acc[2] = T;
     }
@@ -266,8 +287,10 @@ int b200gym_gae_returns(float* rewards, const float* values, const uint8_t* done
                         float gamma, float lam, void* stream) {
     B200_REQUIRE(rewards && values && dones && last_values && returns && advantages && stats, B200GYM_EINVAL, "gae_returns: null argument");
     B200_REQUIRE(T > 0 && N > 0, B200GYM_EINVAL, "gae_returns: T and N must be positive (got %d, %d)", T, N);
-    gae_returns_kernel<<<(N + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(rewards, values, dones, time_outs, last_values,
-                                                                                     returns, advantages, stats, T, N, gamma, lam);
+    const int block = N <= 148 * 256 ? 64 : 256;   // small rollouts: spread the envs over as many SMs as possible
+    gae_returns_kernel<<<(N + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(rewards, values, dones, time_outs,
+                                                                                               last_values, returns, advantages, stats, T, N,
+                                                                                               gamma, lam);
     B200_LAUNCH_CHECK("gae_returns");
     return B200GYM_OK;
 }

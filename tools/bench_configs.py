@@ -148,13 +148,40 @@ def gae_update(num_envs=4096, T=24, device="cuda", peak=6535.7):
         st.compute_returns(last, 0.99, 0.95)
     torch.cuda.synchronize()
     a, b = _events()
+    # device time of the storage pass (zero stats + GAE scan + normalisation): replayed from a CUDA graph so that the host-side
+    # cost of three Python-issued launches does not hide it
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        st.compute_returns(last, 0.99, 0.95)
+    g.replay()
+    torch.cuda.synchronize()
     a.record()
     reps = 50
     for _ in range(reps):
-        st.compute_returns(last, 0.99, 0.95)
+        g.replay()
     b.record()
     torch.cuda.synchronize()
     ms_gae = a.elapsed_time(b) / reps
+    gae_sizes = {}
+    for n2 in (65536, 1048576):
+        st2 = type(st)(n2, T, [1], [None], [1], device)
+        st2.rewards.normal_(0.02, 0.05)
+        st2.values.normal_(0.5, 0.3)
+        l2 = torch.randn(n2, 1, device=device)
+        st2.compute_returns(l2, 0.99, 0.95)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            st2.compute_returns(l2, 0.99, 0.95)
+        g2.replay()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(20):
+            g2.replay()
+        b.record()
+        torch.cuda.synchronize()
+        m2 = a.elapsed_time(b) / 20
+        gae_sizes[str(n2)] = dict(ms=m2, gbs=604 * n2 / (m2 * 1e-3) / 1e9, frac=604 * n2 / (m2 * 1e-3) / 1e9 / peak)
+        del st2, g2
     alg.update()
     st.step = T
     torch.cuda.synchronize()
@@ -187,7 +214,7 @@ def gae_update(num_envs=4096, T=24, device="cuda", peak=6535.7):
         flops = 2.0 * B_ * (48 * 128 + 128 * 64 + 64 * 32 + 32 * 12)
         mlp[str(B_)] = dict(fused_tcgen05_ms=t_f, torch_ms=t_t, fused_tflops=flops / (t_f * 1e-3) / 1e12)
     return dict(config="rollout storage GAE + normalisation; PPO update 5 epochs x 4 minibatches (nets 48-128-64-32)", num_envs=num_envs,
-                actor_forward=mlp,
+                actor_forward=mlp, gae_sizes=gae_sizes,
                 T=T, gae_ms=ms_gae, gae_env_steps_per_s=num_envs * T / (ms_gae * 1e-3),
                 gae_gbs=604 * num_envs / (ms_gae * 1e-3) / 1e9, gae_frac=604 * num_envs / (ms_gae * 1e-3) / 1e9 / peak,
                 update_ms=ms_upd, update_samples_per_s=5 * T * num_envs / (ms_upd * 1e-3),
