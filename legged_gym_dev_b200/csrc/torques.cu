@@ -84,13 +84,23 @@ __device__ __forceinline__ float rcp_ftz(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float sigmoid_acc(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float tanh_acc(float x) { return fmaf(-2.0f, rcp_ftz(ex2_ftz(2.8853900817779268f * x) + 1.0f), 1.0f); }
+
+// Gate non-linearities of one PAIR of hidden units with shared reciprocals.  With E_x = exp(-x) (E_g, E_c: exp(-2x)):
+//   sigma(f) c + sigma(i) tanh(g) = [c (1+E_i)(1+E_g) + (1-E_g)(1+E_f)] / [(1+E_f)(1+E_i)(1+E_g)]        one rcp instead of three
+//   sigma(o) tanh(c')             = (1-E_c) / [(1+E_o)(1+E_c)]                                           one rcp instead of two
+// i.e. 7 MUFU ops per unit instead of 10 (the XU pipe was the busiest pipe of this kernel, profiles/r1_kernels_ncu.md);
+// the surrounding arithmetic runs two units per instruction (mul/add/fma.rn.f32x2).  The exponent arguments are capped at
+// 2^40 so that the triple product stays finite: sigma(x) for x < -27.7 becomes 9e-13 instead of a smaller number.
+__device__ __forceinline__ float2 ex2_pair_capped(float2 x, float scale) {
+    const float2 a = __fmul2_rn(x, make_float2(scale, scale));
+    return make_float2(ex2_ftz(fminf(a.x, 40.0f)), ex2_ftz(fminf(a.y, 40.0f)));
+}
+__device__ __forceinline__ float2 rcp_pair(float2 x) { return make_float2(rcp_ftz(x.x), rcp_ftz(x.y)); }
 
 template <int NIN>
 __device__ __forceinline__ void lstm_cell(const float2 (&w_ih)[16][NIN], const float2 (&w_hh)[16][8], const float2 (&bi)[16],
                                           const float2 (&bh)[16], const float (&x)[NIN], float (&h)[8], float (&c)[8]) {
-    float gate[32];
+    float2 gate[16];   // pair p = gate rows 2p, 2p+1: i (p 0-3), f (4-7), g (8-11), o (12-15) of hidden units 2(p%4), 2(p%4)+1
 #pragma unroll
     for (int p = 0; p < 16; ++p) {
         float2 a = bi[p], bsum = bh[p];
@@ -98,15 +108,23 @@ __device__ __forceinline__ void lstm_cell(const float2 (&w_ih)[16][NIN], const f
         for (int k = 0; k < NIN; ++k) a = __ffma2_rn(w_ih[p][k], make_float2(x[k], x[k]), a);
 #pragma unroll
         for (int k = 0; k < 8; ++k) bsum = __ffma2_rn(w_hh[p][k], make_float2(h[k], h[k]), bsum);
-        const float2 g = __fadd2_rn(a, bsum);
-        gate[2 * p] = g.x, gate[2 * p + 1] = g.y;
+        gate[p] = __fadd2_rn(a, bsum);
     }
+    const float L = 1.4426950408889634f;
+    const float2 one = make_float2(1.0f, 1.0f), mone = make_float2(-1.0f, -1.0f);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const float ig = sigmoid_acc(gate[u]), fg = sigmoid_acc(gate[8 + u]);
-        const float gg = tanh_acc(gate[16 + u]), og = sigmoid_acc(gate[24 + u]);
-        c[u] = fg * c[u] + ig * gg;
-        h[u] = og * tanh_acc(c[u]);
+    for (int k = 0; k < 4; ++k) {
+        const float2 Ei = ex2_pair_capped(gate[k], -L), Ef = ex2_pair_capped(gate[4 + k], -L);
+        const float2 Eg = ex2_pair_capped(gate[8 + k], -2.0f * L), Eo = ex2_pair_capped(gate[12 + k], -L);
+        const float2 D1 = __fadd2_rn(Ef, one), D2 = __fmul2_rn(__fadd2_rn(Ei, one), __fadd2_rn(Eg, one));
+        const float2 N2 = __ffma2_rn(Eg, mone, one);
+        const float2 cc = make_float2(c[2 * k], c[2 * k + 1]);
+        const float2 num = __ffma2_rn(N2, D1, __fmul2_rn(cc, D2));
+        const float2 cn = __fmul2_rn(num, rcp_pair(__fmul2_rn(D1, D2)));
+        const float2 Ec = ex2_pair_capped(cn, -2.0f * L);
+        const float2 hn = __fmul2_rn(__ffma2_rn(Ec, mone, one), rcp_pair(__fmul2_rn(__fadd2_rn(Eo, one), __fadd2_rn(Ec, one))));
+        c[2 * k] = cn.x, c[2 * k + 1] = cn.y;
+        h[2 * k] = hn.x, h[2 * k + 1] = hn.y;
     }
 }
 
