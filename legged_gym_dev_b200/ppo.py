@@ -369,7 +369,9 @@ class PPO:
             plan = [perm[i * B:(i + 1) * B] for _ in range(self.num_learning_epochs) for i in range(self.num_mini_batches)]
         mb = self._static_minibatch(B)
         self._scalars.zero_()
-        use_graph = self.use_graph and all(p.numel() == B for p in plan)
+        # Across ranks the minibatch body runs eagerly: it is GPU-bound either way (graph replay and eager launch measure the
+        # same), and keeping the NCCL all-reduce out of stream capture avoids depending on capture support in the process group.
+        use_graph = self.use_graph and world == 1 and all(p.numel() == B for p in plan)
         n_updates = 0
         for idx in plan:
             if idx.numel() != B:      # ragged plan (tests): fresh buffers, eager
