@@ -233,10 +233,12 @@ int b200gym_clip_adam_dev(float* param, const float* grad, float* exp_avg, float
 int b200gym_adaptive_lr(const double* kl_sum, double count, float desired_kl, float* lr, void* stream);
 
 /* ActorCritic MLP forward (rsl_rl/modules/actor_critic.py: Linear + ELU stack, last layer linear) on the tcgen05 tensor
- * cores (kind::tf32, fp32 accumulation in TMEM), one launch for the whole stack.  dims[0..num_layers] are the PADDED
- * layer widths (K %% 8 == 0, N %% 16 == 0, N <= 256); wpacked holds, layer after layer, W_l [N_l x K_l] as
- * [K_l/4][N_l][4] fp32 (zero padded); bias holds the padded biases back to back.  x: [batch, in_dim] with row stride
- * in_stride (floats); out: [batch, out_dim] contiguous.  The padded weights must fit in shared memory (flat nets do). */
+ * cores (fp32 accumulation in TMEM), one launch for the whole stack.  dims[0..num_layers] are the PADDED layer widths
+ * (K %% 16 == 0, N %% 16 == 0, N <= 256).  wpacked holds two sections back to back: (1) fp32, layer after layer, W_l [N_l x K_l]
+ * as [K_l/4][N_l][4] (zero padded) — operands of the kind::tf32 kernels; (2) fp16, layer after layer, W_l as [K_l/8][N_l][8]
+ * — operands of the kind::f16 four-slot kernel (used when every N_l <= 128 and in_dim %% 8 == 0).  bias holds the padded fp32
+ * biases back to back.  x: [batch, in_dim] with row stride in_stride (floats); out: [batch, out_dim] contiguous.  The padded
+ * weights must fit in shared memory (flat nets do). */
 #define B200GYM_MLP_MAX_LAYERS 6
 typedef struct B200MlpParams {
     int32_t batch, num_layers, in_dim, in_stride, out_dim, pad;

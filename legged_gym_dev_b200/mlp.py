@@ -20,26 +20,29 @@ class FusedMLP:
         if len(self.linears) > 6:
             raise ValueError("at most 6 layers")
         self.in_dim, self.out_dim = self.linears[0].in_features, self.linears[-1].out_features
-        self.dims = [_pad(self.in_dim, 8)] + [_pad(l.out_features, 16) for l in self.linears]
+        self.dims = [_pad(self.in_dim, 16)] + [_pad(l.out_features, 16) for l in self.linears]
         dev = self.linears[0].weight.device
         wtot = sum(self.dims[i] * self.dims[i + 1] for i in range(len(self.linears)))
         smem = (128 * max(self.dims[:-1]) + wtot + sum(self.dims[1:])) * 4 + 64
         if max(self.dims[1:]) > 256 or smem > 227 * 1024:
             raise ValueError("net too large for the weights-resident fused kernel")
-        self.wpacked = torch.zeros(wtot, device=dev)
+        self.wtot = wtot
+        self.wpacked = torch.zeros(wtot + (wtot + 1) // 2, device=dev)   # fp32 section, then the fp16 section (2 halves per float)
         self.bias = torch.zeros(_pad(sum(self.dims[1:]), 4), device=dev)
         self.lib = _lib.lib()
         self.repack()
 
     @torch.no_grad()
     def repack(self):
-        """W_l [N,K] -> [K/4][N][4] (zero padded), biases back to back.  Call after every optimiser step."""
+        """W_l [N,K] -> fp32 [K/4][N][4] and fp16 [K/8][N][8] (zero padded), biases back to back.  Call after every optimiser step."""
         woff = boff = 0
+        w16 = self.wpacked[self.wtot:].view(torch.float16)
         for i, lin in enumerate(self.linears):
             K, N = self.dims[i], self.dims[i + 1]
             W = torch.zeros(N, K, device=self.wpacked.device)
             W[:lin.out_features, :lin.in_features] = lin.weight
             self.wpacked[woff:woff + K * N].copy_(W.view(N, K // 4, 4).permute(1, 0, 2).reshape(-1))
+            w16[woff:woff + K * N].copy_(W.view(N, K // 8, 8).permute(1, 0, 2).reshape(-1))
             self.bias[boff:boff + N].zero_()
             self.bias[boff:boff + lin.out_features].copy_(lin.bias)
             woff += K * N
