@@ -249,6 +249,15 @@ int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const float* wpa
  * with (event, clock64) pairs; NULL switches tracing off again (the default). */
 int b200gym_debug_mlp_trace(void* buf);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tube-dataset construction from the rollout logs (deep_tube_learning/datasets.py:60-71,
+ * deep_tube_learning/evaluation/evaluate_tube_simple.py:28-46) — SURVEY.md §8f row 2
+ * ---------------------------------------------------------------------------------------------- */
+/* w[b,t] = || pz_x[b,t,:] - z[b,t,:] ||_2 for t < T; z, pz_x: [B, T1, n] logs of b200gym_rom_rollout (T1 = T + 1 there). */
+int b200gym_tube_error(const float* z, const float* pz_x, float* w, int64_t B, int32_t T, int32_t T1, int32_t n, void* stream);
+/* sliding_window(data, N, dN, m) (datasets.py:69-71): data [B,T,D] -> out [B,T,N*D], slice i = get_slice(data, i, dN, m). */
+int b200gym_sliding_window(const float* data, float* out, int64_t B, int32_t T, int32_t D, int32_t N, int32_t dN, int32_t m, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,6 +137,9 @@ def lib():
                  "b200gym_clip_adam", "b200gym_adaptive_lr", "b200gym_adam_prepare", "b200gym_clip_adam_dev", "b200gym_debug_mlp_trace"):
         getattr(L, name).restype = C.c_int
     L.b200gym_mlp_forward.argtypes = [C.POINTER(MlpParamsPOD), vp, vp, vp, vp, vp]
+    L.b200gym_tube_error.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.b200gym_sliding_window.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.b200gym_tube_error.restype = L.b200gym_sliding_window.restype = C.c_int
     L.b200gym_mlp_forward.restype = C.c_int
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
                       ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD)):

@@ -125,6 +125,35 @@ def rom_rollout(num_envs=1 << 20, T=200, device="cuda", peak=6535.7, debug=False
                 note="ALU-bound (sinf, IEEE division, Philox); HBM traffic is only the materialised logs")
 
 
+def tube_dataset(num_envs=262144, T=200, N=10, device="cuda", peak=6535.7):
+    """rollout logs -> tube error + N-deep sliding window, on the device (datasets.py:60-71)."""
+    from legged_gym_dev_b200 import _lib
+    L = _lib.lib()
+    z = torch.randn(num_envs, T + 1, 2, device=device)
+    pz = torch.randn(num_envs, T + 1, 2, device=device)
+    v = torch.randn(num_envs, T, 2, device=device)
+    w = torch.empty(num_envs, T, device=device)
+    data = torch.cat((w[:, :, None], v), dim=-1).contiguous()
+    out = torch.empty(num_envs, T, N * 3, device=device)
+    st = _lib.stream_ptr(z.device)
+
+    def run():
+        _lib.check(L.b200gym_tube_error(_lib.ptr(z), _lib.ptr(pz), _lib.ptr(w), num_envs, T, T + 1, 2, st))
+        _lib.check(L.b200gym_sliding_window(_lib.ptr(data), _lib.ptr(out), num_envs, T, 3, N, 1, 2, st))
+    run()
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    for _ in range(5):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    byt = num_envs * (2 * (T + 1) * 8 + T * 4 + T * 12 * (1 + N))
+    return dict(config="tube error + sliding window (N=10, dN=1) from rollout logs", num_envs=num_envs, T=T, ms=ms,
+                gbs=byt / (ms * 1e-3) / 1e9, frac=byt / (ms * 1e-3) / 1e9 / peak)
+
+
 def gae_update(num_envs=4096, T=24, device="cuda", peak=6535.7):
     """cfg 5: GAE + advantage normalisation, and one PPO update iteration (5 epochs x 4 minibatches, flat nets)."""
     from legged_gym_dev_b200.ppo import ActorCritic, PPO
@@ -228,6 +257,7 @@ def run_all(device="cuda", peak=6535.7, quick=False):
                          ("cfg3_rough_lstm", rough_lstm, dict(device=device, peak=peak)),
                          ("cfg3_rough_lstm_262144", rough_lstm, dict(device=device, peak=peak, num_envs=16384 if quick else 262144, steps=20)),
                          ("cfg4_rom_rollout", rom_rollout, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20))),
+                         ("cfg4b_tube_dataset", tube_dataset, dict(device=device, peak=peak, num_envs=16384 if quick else 262144)),
                          ("cfg5_gae_update", gae_update, dict(device=device, peak=peak))):
         try:
             out[name] = fn(**kw)
