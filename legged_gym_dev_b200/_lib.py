@@ -133,6 +133,8 @@ def lib():
     L.b200gym_adam_prepare.argtypes = [vp, vp, vp]
     L.b200gym_clip_adam_dev.argtypes = [vp, vp, vp, vp, C.c_int64, f32, vp, f32, vp, f32, f32, f32, vp, vp]
     L.b200gym_debug_mlp_trace.argtypes = [vp]
+    L.b200gym_debug_set_lstm_variant.argtypes = [C.c_int]
+    L.b200gym_debug_set_lstm_variant.restype = C.c_int
     for name in ("b200gym_gae_returns", "b200gym_adv_normalize", "b200gym_gather_rows", "b200gym_ppo_loss", "b200gym_grad_sumsq",
                  "b200gym_clip_adam", "b200gym_adaptive_lr", "b200gym_adam_prepare", "b200gym_clip_adam_dev", "b200gym_debug_mlp_trace"):
         getattr(L, name).restype = C.c_int

@@ -215,3 +215,22 @@ def test_extreme_inputs_stay_finite():
         assert all(torch.isfinite(v.float()).all() for v in snap.values())
         assert snap["obs"].abs().max() <= 100.0 and snap["torques"].abs().max() <= 80.0
         LC.compare_snapshots(snap, LC.snapshot_port(port), tag=f"extreme step {s}: ")
+
+
+def test_tensor_core_lstm_variant_meets_the_torque_contract():
+    """The actuator LSTM's gate mat-vecs on tcgen05 (3xTF32 operand split, fp32 accumulation): same 1e-5 (S = 80) parity
+    against the oracle as the default FFMA2 kernel."""
+    from legged_gym_dev_b200 import _lib
+    L = _lib.lib()
+    case = LC.build_case("flat_lstm_shipped", 1000)
+    port, phys = LC.make_port(case)
+    env = LC.make_fused(case)
+    assert L.b200gym_debug_set_lstm_variant(1) == 0
+    try:
+        for s in range(12):
+            a = case.tape.actions[s % 8]
+            port.step(a.clone(), phys)
+            env.step(a.cuda())
+            LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"tc lstm step {s}: ")
+    finally:
+        L.b200gym_debug_set_lstm_variant(0)
