@@ -21,7 +21,8 @@ cap gae_returns 'gae_returns_kernel' 2
 cap gather_rows 'gather_rows_kernel' 1
 cap ppo_loss 'ppo_loss_kernel' 1
 cap clip_adam 'clip_adam' 1
+cap sliding_window 'sliding_window_kernel' 1
 timeout 240 ncu --set full --clock-control none --import-source on -k "regex:post_physics_kernel" -s 4 -c 1 -f -o $O/prof_${R}_post_physics_flat $B > $O/ncu_${R}_pp_flat.log 2>&1
 timeout 240 ncu --set full --clock-control none --import-source on -k "regex:pd_torques_kernel" -s 8 -c 1 -f -o $O/prof_${R}_pd_torques $B > $O/ncu_${R}_pd.log 2>&1
-timeout 240 ncu --set full --clock-control none --import-source on -k "regex:mlp_forward_pipe" -s 2 -c 1 -f -o $O/prof_${R}_mlp_forward python tools/run_mlp_once.py 1048576 > $O/ncu_${R}_mlp.log 2>&1
+timeout 240 ncu --set full --clock-control none --import-source on -k "regex:mlp_forward_h4" -s 2 -c 1 -f -o $O/prof_${R}_mlp_forward python tools/run_mlp_once.py 1048576 > $O/ncu_${R}_mlp.log 2>&1
 ls -la $O | tail -20

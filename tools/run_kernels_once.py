@@ -11,3 +11,5 @@ r = B.rom_per_call(num_envs=65536, loop_steps=20, cpu=False)
 print("rom per call", r["ms_total"])
 r = B.gae_update(num_envs=65536, T=24)
 print("gae", r["gae_ms"], r["actor_forward"])
+r = B.tube_dataset(num_envs=65536)
+print("tube dataset", r["ms"])
