@@ -559,33 +559,39 @@ struct H4Plan {
 template <bool LAST>
 __device__ __forceinline__ void h4_epilogue_chunk(const uint32_t (&r)[16], const float* __restrict__ sBl, int n0, unsigned char* __restrict__ hrow,
                                                   float* __restrict__ orow, int out_dim, bool live) {
-    float v[16];
+    // bias add, the log2(e) scale and the "- 1" of the ELU run two activations per instruction (add/mul.rn.f32x2)
+    float2 v[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float4 b4 = *reinterpret_cast<const float4*>(sBl + n0 + 4 * q);   // same address in every lane: broadcast
-        v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
-        v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
-        v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
-        v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+        v[2 * q] = __fadd2_rn(make_float2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), make_float2(b4.x, b4.y));
+        v[2 * q + 1] = __fadd2_rn(make_float2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), make_float2(b4.z, b4.w));
     }
     if (!LAST) {
+        const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f), mone = make_float2(-1.0f, -1.0f);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = elu_fast(v[j]);
+        for (int j = 0; j < 8; ++j) {   // elu(t) = max(t, exp(min(t, 0)) - 1)
+            const float2 a = __fmul2_rn(make_float2(fminf(v[j].x, 0.0f), fminf(v[j].y, 0.0f)), l2e);
+            const float2 e = __fadd2_rn(make_float2(ex2_approx(a.x), ex2_approx(a.y)), mone);
+            v[j] = make_float2(fmaxf(v[j].x, e.x), fmaxf(v[j].y, e.y));
+        }
 #pragma unroll
         for (int q = 0; q < 2; ++q)   // next layer's A operand, k = n: chunk (n0/8 + q), this thread's row
             *reinterpret_cast<uint4*>(hrow + static_cast<size_t>(n0 / 8 + q) * CH16_BYTES) =
-                make_uint4(pack_h2(v[8 * q], v[8 * q + 1]), pack_h2(v[8 * q + 2], v[8 * q + 3]), pack_h2(v[8 * q + 4], v[8 * q + 5]),
-                           pack_h2(v[8 * q + 6], v[8 * q + 7]));
+                make_uint4(pack_h2(v[4 * q].x, v[4 * q].y), pack_h2(v[4 * q + 1].x, v[4 * q + 1].y), pack_h2(v[4 * q + 2].x, v[4 * q + 2].y),
+                           pack_h2(v[4 * q + 3].x, v[4 * q + 3].y));
     } else if (live) {
         if ((out_dim & 3) == 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 if (n0 + 4 * q < out_dim)
-                    *reinterpret_cast<float4*>(orow + n0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    *reinterpret_cast<float4*>(orow + n0 + 4 * q) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
         } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (n0 + j < out_dim) orow[n0 + j] = v[j];
+            for (int j = 0; j < 8; ++j) {
+                if (n0 + 2 * j < out_dim) orow[n0 + 2 * j] = v[j].x;
+                if (n0 + 2 * j + 1 < out_dim) orow[n0 + 2 * j + 1] = v[j].y;
+            }
         }
     }
 }
