@@ -90,6 +90,43 @@ def rom_per_call(num_envs=4096, loop_steps=1000, device="cuda", cpu=True):
     out = dict(config="DoubleInt2D model / SingleInt2D rom / DoubleSingleTracking, call-per-step API", num_envs=num_envs,
                loop_steps=loop_steps, ms_total=ms, env_steps_per_s=num_envs * loop_steps / (ms * 1e-3),
                note="2 launches per loop step: launch-latency bound at this size (SURVEY H5)")
+    # the same 4096 x 1000 loop steps as ONE launch of the persistent rollout kernel (collect_epoch: reset + 500 ROM steps
+    # = 1000 loop steps + 11 warm-up steps), and the call-per-step loop replayed from a CUDA graph (100 steps per replay)
+    env2 = CustomSim(configs.double_single_int_cfg(num_envs, seed=0), device=device)
+    o2 = torch.zeros(num_envs, 8, device=device)
+    env2.collect_epoch(o2, loop_steps // 2)
+    torch.cuda.synchronize()
+    a.record()
+    env2.collect_epoch(o2, loop_steps // 2)
+    b.record()
+    torch.cuda.synchronize()
+    ms_p = a.elapsed_time(b)
+    out["persistent_kernel"] = dict(ms_total=ms_p, env_steps_per_s=num_envs * loop_steps / (ms_p * 1e-3))
+    try:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                obs, _, _, _, _ = env.step(pol(obs))
+        torch.cuda.current_stream(device).wait_stream(side)
+        ob_static = obs.clone()
+        with torch.cuda.graph(g):
+            o = ob_static
+            for _ in range(100):
+                o, _, _, _, _ = env.step(pol(o))
+            ob_static.copy_(o)
+        g.replay()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(loop_steps // 100):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms_g = a.elapsed_time(b)
+        out["call_per_step_graph"] = dict(ms_total=ms_g, env_steps_per_s=num_envs * loop_steps / (ms_g * 1e-3))
+    except Exception as e:
+        out["call_per_step_graph"] = dict(error=f"{type(e).__name__}: {e}")
     if cpu:
         from oracle.port_rom import RomPort, rom_params
         torch.set_num_threads(os.cpu_count() or 1)
