@@ -338,7 +338,10 @@ def main():
             a2 = [tp2.actions[f].to(device) for f in range(4)]
             m2 = time_steps(e2, a2, 100, 10, 1, device)
             tpp, tpd = kernel_time(e2, a2, 30, device)
-            sweep[str(n)] = {"env_steps_per_s": n * 100 / (m2 * 1e-3), "ms_per_step": m2 / 100, "post_physics_ms": tpp,
+            from legged_gym_dev_b200.graphs import GraphedReplay
+            m3 = time_steps(e2, a2, 96, 8, 1, device, graphed=GraphedReplay(e2, a2))
+            sweep[str(n)] = {"env_steps_per_s": n * 100 / (m2 * 1e-3), "ms_per_step": m2 / 100, "graph_ms_per_step": m3 / 96,
+                             "graph_env_steps_per_s": n * 96 / (m3 * 1e-3), "post_physics_ms": tpp,
                              "post_physics_frac": ab["post_physics"] * n / (tpp * 1e-3) / 1e9 / peak,
                              "pd_torques_ms": tpd, "pd_torques_frac": ab["pd_torques"] * n / (tpd * 1e-3) / 1e9 / peak}
             del e2, tp2, a2

@@ -103,3 +103,39 @@ __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
 __device__ __forceinline__ void stg_stream4(float4* p, const float4& v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic Dependent Launch: the kernels of one env step form a dependent chain of short launches (at 4096 envs the
+// step is launch latency, not bandwidth).  Every kernel of the chain starts with pdl_wait() — it blocks until the previous
+// grid has completed and its writes are visible — and is launched with the programmatic-stream-serialization attribute,
+// so its CTAs are scheduled and run their prologue while the previous kernel drains.  pdl_launch_dependents() at the top of
+// a kernel lets the NEXT launch start being scheduled as soon as all of this kernel's CTAs are running.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#include <stdlib.h>
+#include <utility>
+// Measured (profiles/r1_pdl_ab.txt): PDL shortens the eagerly launched step by 13-15 % up to 262 144 envs, is neutral under
+// CUDA-graph replay at those sizes and costs 8 % at 1 M envs (early-resident dependents that only wait) — so it is on by
+// default for grids up to 262 144 envs; B200GYM_PDL=0 / 1 forces it off / on.
+static inline bool b200_pdl_enabled(long long units) {
+    static int mode = -2;
+    if (mode == -2) {
+        const char* e = getenv("B200GYM_PDL");
+        mode = e ? (e[0] == '0' ? 0 : 1) : -1;
+    }
+    return mode >= 0 ? mode != 0 : units <= 262144;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b200_launch_pdl(long long units, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                          Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = b200_pdl_enabled(units) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}

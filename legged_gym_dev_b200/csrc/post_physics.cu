@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
     const bool full = (nvalid == TILE);
     const float* rs = p.reward_scale;
 
+    pdl_launch_dependents();
+    pdl_wait();   // everything below reads what the torque kernels / the previous step wrote (incl. the device step counter)
     if (tid == 0) {
         mbar_init(s.bar, 1);
         fence_mbar_init();
@@ -784,6 +786,8 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
 // legged_robot.py:175-182: mean over the reset envs / max_episode_length_s; untouched when nothing reset (:156-157)
 __global__ void extras_finalize_kernel(const __grid_constant__ B200LeggedParams p, const __grid_constant__ B200LeggedBuffers b) {
     const int K = p.num_sum_rows, tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const double cnt = b.ws_sums[K + 1];
     const double mine = tid < K + 2 ? b.ws_sums[tid] : 0.0;
     __syncthreads();
@@ -823,10 +827,10 @@ int launch_post_physics(const B200LeggedParams& p, const B200LeggedBuffers& b, u
     }
     const int grid = (p.num_envs + TILE - 1) / TILE;
     static const SqThr thr = {sq_gt(1.0f), sq_gt(0.1f), sq_gt(0.2f), sq_lt(0.1f)};
-    post_physics_kernel<TILE, ROUGH><<<grid, TILE * LPE, smem, stream>>>(p, b, step, env_off, do_push, thr);
+    b200_launch_pdl(p.num_envs, post_physics_kernel<TILE, ROUGH>, dim3(grid), dim3(TILE * LPE), smem, stream, p, b, step, env_off, do_push, thr);
     B200_LAUNCH_CHECK("post_physics");
 #if PP_FINALIZE_KERNEL
-    extras_finalize_kernel<<<1, 32, 0, stream>>>(p, b);
+    b200_launch_pdl(p.num_envs, extras_finalize_kernel, dim3(1), dim3(32), 0, stream, p, b);
     B200_LAUNCH_CHECK("extras_finalize");
 #endif
     return B200GYM_OK;

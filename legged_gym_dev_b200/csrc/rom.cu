@@ -264,6 +264,8 @@ __global__ void __launch_bounds__(128) rom_step_kernel(const __grid_constant__ B
                                                        const float* __restrict__ action, const uint8_t* __restrict__ mask,
                                                        long long env_off) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (i >= p.num_envs) return;
     const int w = p.window, mn = p.model_type ? 4 : 2;
     Gen<RN, W> g;
@@ -355,6 +357,8 @@ __global__ void __launch_bounds__(128) rom_reset_kernel(const __grid_constant__ 
 
 __global__ void rom_policy_kernel(const __grid_constant__ B200RomParams p, const float* __restrict__ obs, float* __restrict__ action) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (i >= p.num_envs) return;
     const float4 a = *reinterpret_cast<const float4*>(obs + static_cast<size_t>(i) * 8);
     const float4 b = *reinterpret_cast<const float4*>(obs + static_cast<size_t>(i) * 8 + 4);
@@ -515,11 +519,11 @@ int b200gym_rom_step(const B200RomParams* p, const B200RomState* s, const float*
     const int grid = (p->num_envs + 127) / 128;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (p->rom_type == 0) {
-        if (p->window == 10 && p->dN == 1) rom_step_kernel<2, 10><<<grid, 128, 0, st>>>(*p, *s, action, step_mask, env_id_offset);
-        else rom_step_kernel<2, WMAXR><<<grid, 128, 0, st>>>(*p, *s, action, step_mask, env_id_offset);
+        if (p->window == 10 && p->dN == 1) b200_launch_pdl(p->num_envs, rom_step_kernel<2, 10>, dim3(grid), dim3(128), 0, st, *p, *s, action, step_mask, env_id_offset);
+        else b200_launch_pdl(p->num_envs, rom_step_kernel<2, WMAXR>, dim3(grid), dim3(128), 0, st, *p, *s, action, step_mask, env_id_offset);
     } else {
-        if (p->window == 10 && p->dN == 1) rom_step_kernel<4, 10><<<grid, 128, 0, st>>>(*p, *s, action, step_mask, env_id_offset);
-        else rom_step_kernel<4, WMAXR><<<grid, 128, 0, st>>>(*p, *s, action, step_mask, env_id_offset);
+        if (p->window == 10 && p->dN == 1) b200_launch_pdl(p->num_envs, rom_step_kernel<4, 10>, dim3(grid), dim3(128), 0, st, *p, *s, action, step_mask, env_id_offset);
+        else b200_launch_pdl(p->num_envs, rom_step_kernel<4, WMAXR>, dim3(grid), dim3(128), 0, st, *p, *s, action, step_mask, env_id_offset);
     }
     B200_LAUNCH_CHECK("rom_step");
     return B200GYM_OK;
@@ -542,7 +546,7 @@ int b200gym_rom_tracking_policy(const B200RomParams* p, const float* obs, float*
     B200_REQUIRE(p->num_envs > 0, B200GYM_EINVAL, "rom_tracking_policy: num_envs must be positive");
     B200_REQUIRE(p->model_type == 1, B200GYM_EINVAL, "rom_tracking_policy: DoubleSingleTracking needs a DoubleInt2D model");
     B200_REQUIRE(b200_aligned16(obs) && b200_aligned16(action), B200GYM_EALIGN, "rom_tracking_policy: pointers must be 16-byte aligned");
-    rom_policy_kernel<<<(p->num_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(*p, obs, action);
+    b200_launch_pdl(p->num_envs, rom_policy_kernel, dim3((p->num_envs + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), *p, obs, action);
     B200_LAUNCH_CHECK("rom_tracking_policy");
     return B200GYM_OK;
 }

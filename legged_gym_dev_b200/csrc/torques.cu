@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(256) pd_torques_kernel(const __grid_constant__
                                                          const float4* __restrict__ last_dof_vel,
                                                          float4* __restrict__ torques, int n4) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (i >= n4) return;
     float4 a4 = ldg_stream4(actions + i);
     const float4 s0 = ldg_stream4(dof_state + 2 * i), s1 = ldg_stream4(dof_state + 2 * i + 1);
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(128, LSTM_MINBLOCKS) lstm_torques_kernel(const
                                                            const float2* __restrict__ dof_state, float* __restrict__ hbuf,
                                                            float* __restrict__ cbuf, float* __restrict__ torques, int m) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (i >= m) return;
     const int d = i % ND;
     const float a = clampf(actions[i], -p.clip_actions, p.clip_actions);
@@ -267,6 +271,8 @@ __global__ void __launch_bounds__(128, LSTM_TC_BLOCKS) lstm_torques_tc_kernel(co
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = tid; i < (LSTM_K1 + LSTM_K2) * LSTM_NG; i += 128) sW[i] = g_lstm_wtc[i];
     if (tid < 2 * LSTM_NG) sBias[tid] = g_lstm_btc[tid];
     if (warp == 0) {
@@ -388,10 +394,10 @@ int b200gym_pd_torques(const B200LeggedParams* p, const float* actions, float* a
                      b200_aligned16(actions_clipped) && b200_aligned16(last_dof_vel),
                  B200GYM_EALIGN, "pd_torques: pointers must be 16-byte aligned");
     const int n4 = p->num_envs * ND / 4;
-    pd_torques_kernel<<<(n4 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        *p, reinterpret_cast<const float4*>(actions), reinterpret_cast<float4*>(actions_clipped),
-        reinterpret_cast<const float4*>(dof_state), reinterpret_cast<const float4*>(last_dof_vel),
-        reinterpret_cast<float4*>(torques), n4);
+    b200_launch_pdl(p->num_envs, pd_torques_kernel, dim3((n4 + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), *p,
+                    reinterpret_cast<const float4*>(actions), reinterpret_cast<float4*>(actions_clipped),
+                    reinterpret_cast<const float4*>(dof_state), reinterpret_cast<const float4*>(last_dof_vel),
+                    reinterpret_cast<float4*>(torques), n4);
     B200_LAUNCH_CHECK("pd_torques");
     return B200GYM_OK;
 }
@@ -475,13 +481,13 @@ int b200gym_lstm_torques(const B200LeggedParams* p, const float* actions, float*
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         }
         const int ntiles = (m + 127) / 128, cap = sms * LSTM_TC_BLOCKS;
-        lstm_torques_tc_kernel<<<ntiles < cap ? ntiles : cap, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-            *p, actions, actions_clipped, reinterpret_cast<const float2*>(dof_state), h, c, torques, m);
+        b200_launch_pdl(p->num_envs, lstm_torques_tc_kernel, dim3(ntiles < cap ? ntiles : cap), dim3(128), 0, static_cast<cudaStream_t>(stream), *p, actions,
+                        actions_clipped, reinterpret_cast<const float2*>(dof_state), h, c, torques, m);
         B200_LAUNCH_CHECK("lstm_torques (tcgen05)");
         return B200GYM_OK;
     }
-    lstm_torques_kernel<<<(m + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        *p, actions, actions_clipped, reinterpret_cast<const float2*>(dof_state), h, c, torques, m);
+    b200_launch_pdl(p->num_envs, lstm_torques_kernel, dim3((m + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), *p, actions, actions_clipped,
+                    reinterpret_cast<const float2*>(dof_state), h, c, torques, m);
     B200_LAUNCH_CHECK("lstm_torques");
     return B200GYM_OK;
 }
