@@ -124,7 +124,6 @@ def build_env(num_envs, frames, device, rank, copy=False, host=False):
     from legged_gym_dev_b200 import synthetic as S
     from legged_gym_dev_b200.legged_robot import Anymal
     from legged_gym_dev_b200.physics import ReplayPhysics, HostReplayPhysics
-    import legged_case as LC
     cfg = workload_cfg(num_envs)
     tape = S.make_state_tape(num_envs, frames=frames, seed=100 + rank, device=device)
     if host:   # generated on the device (fast), then moved to the host: the e2e arm replays it from pinned host memory
@@ -132,7 +131,7 @@ def build_env(num_envs, frames, device, rank, copy=False, host=False):
             setattr(tape, k, getattr(tape, k).cpu())
         torch.cuda.empty_cache()
     phys = HostReplayPhysics(tape, device=device) if host else ReplayPhysics(tape, device=device, copy=copy)
-    lim = LC.dof_limits()
+    lim = S.anymal_dof_limits()
     env = Anymal(cfg, SimpleNamespace(dt=cfg.sim.dt), None, device, True, physics=phys, asset=lim, seed=0,
                  env_id_offset=rank * num_envs)
     env.episode_length_buf.copy_(S.make_episode_lengths(num_envs, seed=rank, device=device))

@@ -21,6 +21,16 @@ DOF_NAMES = tuple(f"{leg}_{j}" for leg in ("LF", "LH", "RF", "RH") for j in ("HA
 DEFAULT_DOF_POS = (0.0, 0.4, -0.8, 0.0, -0.4, 0.8, 0.0, 0.4, -0.8, 0.0, -0.4, 0.8)
 
 
+def anymal_dof_limits():
+    """Soft joint limits / velocity / effort limits of the collapsed ANYmal-C asset (what LeggedRobot reads from the URDF through
+    `gym.get_asset_dof_properties`, legged_robot.py:264-283): synthetic stand-in used wherever no Isaac Gym asset is loaded."""
+    lo = torch.tensor([-0.72, -1.2, -1.8] * 4, dtype=torch.float)
+    hi = torch.tensor([0.49, 1.2, 1.8] * 4, dtype=torch.float)
+    lo[3:6], hi[3:6] = torch.tensor([-0.49, -1.2, -1.8]), torch.tensor([0.72, 1.2, 1.8])
+    return dict(dof_pos_limits=torch.stack([lo, hi], dim=1), dof_vel_limits=torch.full((12,), 20.0),
+                torque_limits=torch.full((12,), 80.0))
+
+
 def _gen(seed, device):
     g = torch.Generator(device=device)
     g.manual_seed(int(seed))

@@ -30,11 +30,7 @@ CASES = {
 
 
 def dof_limits():
-    lo = torch.tensor([-0.72, -1.2, -1.8] * 4, dtype=torch.float)
-    hi = torch.tensor([0.49, 1.2, 1.8] * 4, dtype=torch.float)
-    lo[3:6], hi[3:6] = torch.tensor([-0.49, -1.2, -1.8]), torch.tensor([0.72, 1.2, 1.8])
-    return dict(dof_pos_limits=torch.stack([lo, hi], dim=1), dof_vel_limits=torch.full((12,), 20.0),
-                torque_limits=torch.full((12,), 80.0))
+    return S.anymal_dof_limits()
 
 
 def apply_overrides(cfg, reward_scales, command_ranges, lstm, overrides):

@@ -20,10 +20,8 @@ def _events():
 
 def rough_lstm(num_envs=16384, steps=50, warmup=5, device="cuda", peak=6535.7):
     """cfg 3: anymal_c_rough, LSTM actuator net x4 + 187-point height scan + 235 observations."""
-    import legged_case as LC
-    from legged_gym_dev_b200 import synthetic as S
-    case = LC.build_case("rough_pd_shipped", 64)      # for cfg + terrain tables only
-    cfg = case.cfg
+    from legged_gym_dev_b200 import configs, synthetic as S
+    cfg = configs.anymal_c_rough_cfg()                # shipped reward table, trimesh terrain with curriculum, heading commands
     cfg.control.use_actuator_network = True
     cfg.env.num_envs = num_envs
     F = 4
@@ -31,13 +29,13 @@ def rough_lstm(num_envs=16384, steps=50, warmup=5, device="cuda", peak=6535.7):
     g = torch.Generator().manual_seed(3)
     levels = torch.randint(0, cfg.terrain.max_init_terrain_level + 1, (num_envs,), generator=g)
     types = torch.div(torch.arange(num_envs), (num_envs / cfg.terrain.num_cols), rounding_mode="floor").to(torch.long)
-    to = case.terrain["terrain_origins"]
-    terrain = dict(height_samples=case.terrain["height_samples"], terrain_origins=to, terrain_levels=levels, terrain_types=types,
+    to = S.make_terrain_origins(seed=1)
+    terrain = dict(height_samples=S.make_heightfield(seed=1), terrain_origins=to, terrain_levels=levels, terrain_types=types,
                    env_origins=to[levels, types].clone())
     from legged_gym_dev_b200.legged_robot import Anymal
     from legged_gym_dev_b200.physics import ReplayPhysics
     env = Anymal(cfg, SimpleNamespace(dt=cfg.sim.dt), None, device, True, physics=ReplayPhysics(tape, device=device, copy=False),
-                 asset=LC.dof_limits(), seed=0, terrain=terrain)
+                 asset=S.anymal_dof_limits(), seed=0, terrain=terrain)
     env.episode_length_buf = S.make_episode_lengths(num_envs, seed=1, device=device)
     acts = [tape.actions[f] for f in range(F)]
     for s in range(warmup):
