@@ -30,7 +30,8 @@ def _worker(rank, world, port, q):
     st = torch.stack([mine.sum(), (mine * mine).sum(), torch.tensor(float(hi - lo), dtype=torch.double)])
     dist.all_reduce(st)
     mean, std = combine_advantage_stats(st)
-    q.put((rank, lo, hi, log["z"], log["v"], float(mean), float(std), float(adv.mean()), float(adv.std())))
+    # numpy copies: torch tensors travel through a Queue as fd-shared storage, which breaks if this process exits first
+    q.put((rank, lo, hi, log["z"].numpy().copy(), log["v"].numpy().copy(), float(mean), float(std), float(adv.mean()), float(adv.std())))
     dist.destroy_process_group()
 
 
@@ -49,7 +50,7 @@ def test_env_sharding_and_stats_over_gloo():
     full = RomPort(rom_params(64, seed=9))
     log, _ = full.collect_epoch(torch.zeros(64, 8), 6)
     for rank, lo, hi, z, v, mean, std, gmean, gstd in out:
-        assert torch.equal(z, log["z"][lo:hi]) and torch.equal(v, log["v"][lo:hi]), "per-env results depend on the sharding"
+        assert torch.equal(torch.from_numpy(z), log["z"][lo:hi]) and torch.equal(torch.from_numpy(v), log["v"][lo:hi]), "per-env results depend on the sharding"
         assert abs(mean - gmean) < 1e-6 and abs(std - gstd) < 1e-6
     assert sorted((o[1], o[2]) for o in out) == [(0, 32), (32, 64)]
 
