@@ -154,7 +154,7 @@ struct TileSmem {
     float *sums, *obs, *blv, *bav, *pg, *lrv, *rew, *part;
     uint8_t *reset, *tout;
     int16_t* hraw;
-    float *bh, *zpost, *stage, *hpart;
+    float *bh, *zpost, *stage, *hsum, *unoise;
     float2 *pts, *yaw;
     double* acc;
     int* nreset;
@@ -196,11 +196,12 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
         s.zpost = c.take<float>(TILE);
         s.stage = nullptr;
         s.yaw = c.take<float2>(TILE);
-        s.hpart = need_hpart ? c.take<float>(TILE * (HPAD / 4)) : nullptr;
+        s.hsum = need_hpart ? c.take<float>(TILE) : nullptr;
+        s.unoise = c.take<float>(static_cast<size_t>(TILE * LPE / 32) * 2 * HPAD);   // per warp: noise uniforms of an env pair
         s.pts = c.take<float2>(HPAD);
     } else {
         s.hraw = nullptr;
-        s.bh = s.zpost = s.stage = s.hpart = nullptr;
+        s.bh = s.zpost = s.stage = s.hsum = s.unoise = nullptr;
         s.pts = nullptr;
         s.yaw = nullptr;
     }
@@ -305,48 +306,69 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         const float inv_hs = div_rn(1.0f, p.horizontal_scale);
         const HeightConsts hc = {make_float2(p.border_size, p.border_size), make_float2(-p.horizontal_scale, -p.horizontal_scale),
                                  make_float2(inv_hs, inv_hs)};
-        const int de = (TILE * LPE) / Q, dq = (TILE * LPE) - de * Q;
-        int e = tid / Q, q = tid - e * Q;
-        for (int i = tid; i < nvalid * Q; i += TILE * LPE) {
-            const float* R = s.root + e * 13;
-            const float2 yw = s.yaw[e];
-            const float rz = R[2], z05 = sub_rn(rz, 0.5f);
-            const int pt0 = 4 * q;
-            int raw[4] = {0, 0, 0, 0};
-            if (!p.mesh_plane) {
-                const float4 pa = *reinterpret_cast<const float4*>(s.pts + pt0), pb = *reinterpret_cast<const float4*>(s.pts + pt0 + 2);
-                int off[4];
-                height_cells2(make_float2(pa.x, pa.z), make_float2(pa.y, pa.w), yw.x, yw.y, R[0], R[1], hc, rows, cols, off[0], off[1]);
-                height_cells2(make_float2(pb.x, pb.z), make_float2(pb.y, pb.w), yw.x, yw.y, R[0], R[1], hc, rows, cols, off[2], off[3]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {   // 12 gathers issued together; padding points read a valid (unused) cell
-                    const int16_t* h = b.height_samples + off[j];
-                    raw[j] = min(min(static_cast<int>(__ldg(h)), static_cast<int>(__ldg(h + cols))), static_cast<int>(__ldg(h + 1)));
-                }
-            }
-            float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+        constexpr int NW = TILE * LPE / 32, RND = HPAD / 32;
+        const int warp = tid >> 5, lane = tid & 31;
+        float* un = s.unoise + warp * 2 * HPAD;
+        for (int e0 = 2 * warp; e0 < nvalid; e0 += 2 * NW) {
+            const int ne = min(2, nvalid - e0);
             if (p.add_noise) {
-                const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
-                u = philox::u01(rng.words(philox::OBS_NOISE, 12 + q));
+                // the Q (= 47) Philox blocks of an env hold the noise of its 4Q points: lane L draws block L of both envs, then
+                // the tails (blocks 32..Q-1) of the two envs share one more round (lanes 0-15 / 16-31); uniforms go through a
+                // per-warp scratch so that a lane can pick up the draws of ITS points
+                for (int k = 0; k < ne; ++k) {
+                    const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e0 + k), step);
+                    if (lane < Q) *reinterpret_cast<float4*>(un + k * HPAD + 4 * lane) = philox::u01(rng.words(philox::OBS_NOISE, 12 + lane));
+                }
+                const int k = lane >> 4, blk = 32 + (lane & 15);
+                if (k < ne && blk < Q) {
+                    const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e0 + k), step);
+                    *reinterpret_cast<float4*>(un + k * HPAD + 4 * blk) = philox::u01(rng.words(philox::OBS_NOISE, 12 + blk));
+                }
+                __syncwarp();
             }
-            const float un[4] = {u.x, u.y, u.z, u.w};
-            float* mh_out = b.measured_heights + static_cast<size_t>(tile0 + e) * H + pt0;
-            float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48 + pt0;
-            float part = 0.0f;
+            for (int k = 0; k < ne; ++k) {
+                const int e = e0 + k;
+                const float* R = s.root + e * 13;
+                const float2 yw = s.yaw[e];
+                const float rz = R[2], z05 = sub_rn(rz, 0.5f);
+                int raw[RND];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (pt0 + j < H) {
-                    const float mh = mul_rn(static_cast<float>(raw[j]), p.vertical_scale);
-                    mh_out[j] = mh;
-                    part += rz - mh;
-                    float v = clampf(sub_rn(z05, mh), -1.0f, 1.0f) * p.obs_height;
-                    if (p.add_noise) v = add_noise(v, un[j], p.noise_height);
-                    ob_out[j] = clampf(v, -p.clip_obs, p.clip_obs);
+                for (int r = 0; r < RND; ++r) raw[r] = 0;
+                if (!p.mesh_plane) {
+                    int off[RND];
+#pragma unroll
+                    for (int r = 0; r < RND; r += 2) {   // two points (rounds r, r+1) per packed instruction
+                        const float2 pa = s.pts[32 * r + lane], pb = s.pts[32 * (r + 1) + lane];
+                        height_cells2(make_float2(pa.x, pb.x), make_float2(pa.y, pb.y), yw.x, yw.y, R[0], R[1], hc, rows, cols, off[r], off[r + 1]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < RND; ++r) {   // 18 gathers issued together; padding points read a valid (unused) cell
+                        const int16_t* h = b.height_samples + off[r];
+                        raw[r] = min(min(static_cast<int>(__ldg(h)), static_cast<int>(__ldg(h + cols))), static_cast<int>(__ldg(h + 1)));
+                    }
+                }
+                float* mh_out = b.measured_heights + static_cast<size_t>(tile0 + e) * H + lane;
+                float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48 + lane;
+                const float* ue = un + k * HPAD + lane;
+                float part = 0.0f;
+#pragma unroll
+                for (int r = 0; r < RND; ++r) {
+                    if (32 * r + lane < H) {
+                        const float mh = mul_rn(static_cast<float>(raw[r]), p.vertical_scale);
+                        mh_out[32 * r] = mh;
+                        part += rz - mh;
+                        float v = clampf(sub_rn(z05, mh), -1.0f, 1.0f) * p.obs_height;
+                        if (p.add_noise) v = add_noise(v, ue[32 * r], p.noise_height);
+                        ob_out[32 * r] = clampf(v, -p.clip_obs, p.clip_obs);
+                    }
+                }
+                if (s.hsum) {
+#pragma unroll
+                    for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+                    if (lane == 0) s.hsum[e] = part;
                 }
             }
-            if (s.hpart) s.hpart[e * (HPAD / 4) + q] = part;
-            e += de, q += dq;
-            if (q >= Q) q -= Q, ++e;
+            __syncwarp();   // the scratch is rewritten by the next env pair
         }
     }
 
@@ -524,12 +546,8 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         if (rs[T_ANG_VEL_XY] != 0.f) add_term(T_ANG_VEL_XY, bax * bax + bay * bay);
         if (rs[T_BASE_HEIGHT] != 0.f) {
             float bh = R[2];
-            if (ROUGH) {   // mean(root_z - measured_heights) (legged_robot.py:938-939): the quads' partial sums in a fixed order
-                const int Q = (p.num_heights + 3) >> 2;
-                float acc = 0.0f;
-                for (int q = 0; q < Q; ++q) acc += s.hpart[e * (HPAD / 4) + q];
-                bh = acc / static_cast<float>(p.num_heights);
-            }
+            if (ROUGH)   // mean(root_z - measured_heights) (legged_robot.py:938-939): phase H's warp-reduced sum (fixed order)
+                bh = s.hsum[e] / static_cast<float>(p.num_heights);
             const float dh = bh - p.base_height_target;
             add_term(T_BASE_HEIGHT, dh * dh);
         }
