@@ -9,7 +9,8 @@
 //
 // Work mapping (chosen from the ncu profile of the first version, profiles/r1_post_physics_v1.md: the kernel
 // was issue-bound because four lanes each repeated the per-env scalar work):
-//   phase H  (rough only) one warp per env: 187-point height scan + height observations (noise included)
+//   phase H  (rough only) one warp per env pair, one lane per sample point: 187-point height scan + height
+//            observations (noise included)
 //                                                                            legged_robot.py:877-915,220-226
 //   phase W  4 lanes per env: per-DOF / per-foot / per-body terms, the DOF observation columns and all
 //            Philox noise draws; 2-step shuffle reductions leave per-env partial sums in shared memory
@@ -286,14 +287,14 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
     }
 
     // ---- phase H: height scan + height observations (legged_robot.py:877-915, math.py:38-42, :220-226) ----------------
-    // Work item = (env, quad of 4 consecutive sample points); the (env, quad) pairs of the tile are flattened over the 128
-    // threads, so no lane idles on the 187 -> 192 padding and every item owns exactly one Philox block (the 4 noise
-    // draws of its 4 points): nothing is exchanged between lanes.  The index chain keeps torch's un-fused fp32 rounding
-    // (the cell index depends on it) but runs two points per instruction (mul/add/fma.rn.f32x2).
-    // The observation needs the POST-reset base height; resets are rare, so it is produced here with the current height
-    // and redone after phase S only for the envs that did reset (phase H').
-    // (A/B, profiles/r1_post_physics_rough.md: staging per-env terrain patches in shared memory for the gathers was slower
-    // than letting the 3 x 187 int16 gathers hit L1 — the patch of a robot is ~1 KB and stays L1-resident anyway.)
+    // A warp takes two envs at a time; a lane owns the sample points {lane, lane+32, ...} of the env, so one gather instruction
+    // covers 32 CONSECUTIVE points (~3 columns of the 17 x 11 grid = few heightfield rows) and the measured_heights / height
+    // observation stores are 128-B coalesced.  (The previous mapping, one lane per quad of points, spread every gather over
+    // ~14 cache lines and was bound by the L1 tag rate: profiles/r1_post_physics_rough.md.)  The index chain keeps torch's
+    // un-fused fp32 rounding (the cell index depends on it) but runs two points per instruction (f32x2).
+    // Noise: Philox block q holds the draws of points 4q..4q+3, so lanes draw whole blocks and hand the uniforms over
+    // through a per-warp scratch.  The observation needs the POST-reset base height; resets are rare, so it is produced
+    // here with the current height and redone after phase S only for the envs that did reset (phase H').
     if (ROUGH) {
         if (tid < nvalid) {   // quat_apply_yaw: zero x,y, renormalise (un-fused fp32), once per env
             const float* R = s.root + tid * 13;
