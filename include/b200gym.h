@@ -21,7 +21,9 @@ extern "C" {
 #define B200GYM_NUM_FEET 4
 #define B200GYM_NUM_PEN 8
 #define B200GYM_MAX_TERM 4
-#define B200GYM_NUM_REWARD_TERMS 19 /* alphabetical _reward_* names, `termination` last (legged_robot.py:605-629) */
+#define B200GYM_NUM_REWARD_TERMS 21 /* alphabetical _reward_* names of LeggedRobot + LeggedRobotTrajectory, `termination` last
+                                       (legged_robot.py:605-629, legged_robot_trajectory.py:663-687) */
+#define B200GYM_TRAJ_WIDTH 20 /* trajectory observation block: N = 10 knots of a 2-state rom (legged_robot_trajectory.py:277-283) */
 #define B200GYM_MAX_POINTS 32
 
 int b200gym_version(void);
@@ -59,6 +61,14 @@ typedef struct B200LeggedParams {
     int32_t custom_origins, zero_lstm_on_reset;
     float base_init_state[13];
     uint32_t seed_lo, seed_hi;
+    /* LeggedRobotTrajectory (legged_gym/envs/base/legged_robot_trajectory.py): traj_mode != 0 selects its step semantics —
+       no command resampling (:405-417), per-env push timers (:169-178), rewards tracking_rom (:1060-1069) and
+       differential_error (:1100-1110), prev_error on reset (:233), trajectory observation block (:274-287). */
+    int32_t traj_mode, traj_n, traj_horizon;
+    float traj_scale[4];  /* normalization.obs_scales.trajectory, per rom state */
+    float traj_weight[4]; /* rom.get_weighting_vector(cfg.rewards.reward_weighting) (rom_dynamics.py:209-211) */
+    float diff_neg_slope, diff_pos_slope; /* cfg.rewards.differential_error */
+    float push_t_lo, push_t_span;         /* cfg.domain_rand.time_between_pushes: lower, upper - lower */
 } B200LeggedParams;
 
 typedef struct B200LeggedBuffers {
@@ -101,6 +111,10 @@ typedef struct B200LeggedBuffers {
        instead of the by-value argument and advance it after every step, which makes the launch sequence of whole env
        steps CUDA-graph replayable.  It must hold common_step_counter of the NEXT post-physics pass. */
     uint64_t* step_counter;
+    /* traj_mode only */
+    const float* trajectory;     /* [N, horizon, n] self.trajectory = traj_gen.get_trajectory() of this step (:410) */
+    float* prev_error;           /* [N, n] */
+    float* time_until_next_push; /* [N] */
 } B200LeggedBuffers;
 
 /* LeggedRobot._compute_torques (legged_robot.py:389-413), optionally fused with the action clip of
@@ -178,6 +192,13 @@ int b200gym_rom_step(const B200RomParams* p, const B200RomState* s, const float*
  * and the trailing zero-action step of ALL envs.  reset_mask == NULL: CustomSim.reset(). */
 int b200gym_rom_reset(const B200RomParams* p, const B200RomState* s, const uint8_t* reset_mask, int64_t env_id_offset,
                       void* stream);
+/* LeggedRobotTrajectory.reset_traj (legged_robot_trajectory.py:248-253) + TrajectoryGenerator.reset_idx (rom_dynamics.py:595-605)
+ * for the envs flagged in reset_mask: p_zx = proj_z(root) read from root [N, root_stride] (SingleInt2D: first two columns),
+ * optional random offset, generator reset and N*dN warm-up steps.  any_reset (device float, e.g. extras_out[K+1] of
+ * b200gym_post_physics, or NULL): when it reads 0 the call does nothing, as reset_idx returns early on an empty id list (:217-218).
+ * The interpolated env_trajectory is NOT refreshed (the reference keeps the pre-reset clone until the next step, :410). */
+int b200gym_rom_reset_from_root(const B200RomParams* p, const B200RomState* s, const uint8_t* reset_mask, const float* root,
+                                int32_t root_stride, const float* any_reset, int64_t env_id_offset, void* stream);
 /* DoubleSingleTracking.__call__ (controllers.py:87-92) with DoubleInt2D.clip_v_z (rom_dynamics.py:234-250). */
 int b200gym_rom_tracking_policy(const B200RomParams* p, const float* obs, float* action, void* stream);
 /* One epoch of data_collection_trajectory.py:104-149 as ONE persistent launch: reset all envs, then T ROM steps of

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200GYM_LIB") or os.path.join(_HERE, "libb200gym.so")   # env override: A/B of kernel variants
 
-NUM_DOF, NUM_FEET, NUM_PEN, MAX_TERM, NUM_TERMS, MAX_POINTS = 12, 4, 8, 4, 19, 32
+NUM_DOF, NUM_FEET, NUM_PEN, MAX_TERM, NUM_TERMS, MAX_POINTS = 12, 4, 8, 4, 21, 32
 
 f32, i32, u32 = C.c_float, C.c_int32, C.c_uint32
 vp = C.c_void_p
@@ -45,6 +45,9 @@ class LeggedParamsPOD(C.Structure):
         ("custom_origins", i32), ("zero_lstm_on_reset", i32),
         ("base_init_state", f32 * 13),
         ("seed_lo", u32), ("seed_hi", u32),
+        ("traj_mode", i32), ("traj_n", i32), ("traj_horizon", i32),
+        ("traj_scale", f32 * 4), ("traj_weight", f32 * 4),
+        ("diff_neg_slope", f32), ("diff_pos_slope", f32), ("push_t_lo", f32), ("push_t_span", f32),
     ]
 
 
@@ -52,7 +55,8 @@ _BUF_FIELDS = ["root_states", "dof_state", "contact_forces", "actions", "torques
                "last_root_vel", "commands", "feet_air_time", "last_contacts", "episode_length_buf", "reset_buf",
                "time_out_buf", "rew_buf", "episode_sums", "obs_buf", "base_lin_vel", "base_ang_vel",
                "projected_gravity", "measured_heights", "height_samples", "env_origins", "terrain_levels",
-               "terrain_types", "terrain_origins", "lstm_h", "lstm_c", "extras_out", "ws_sums", "ws_counter", "step_counter"]
+               "terrain_types", "terrain_origins", "lstm_h", "lstm_c", "extras_out", "ws_sums", "ws_counter", "step_counter",
+               "trajectory", "prev_error", "time_until_next_push"]
 
 
 class LeggedBuffersPOD(C.Structure):
@@ -118,9 +122,11 @@ def lib():
     L.b200gym_rom_init.argtypes = [rp, rs, C.c_int64, vp]
     L.b200gym_rom_step.argtypes = [rp, rs, vp, vp, C.c_int64, vp]
     L.b200gym_rom_reset.argtypes = [rp, rs, vp, C.c_int64, vp]
+    L.b200gym_rom_reset_from_root.argtypes = [rp, rs, vp, vp, C.c_int32, vp, C.c_int64, vp]
     L.b200gym_rom_tracking_policy.argtypes = [rp, vp, vp, vp]
     L.b200gym_rom_rollout.argtypes = [rp, rs, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int64, vp]
-    for name in ("b200gym_rom_init", "b200gym_rom_step", "b200gym_rom_reset", "b200gym_rom_tracking_policy", "b200gym_rom_rollout"):
+    for name in ("b200gym_rom_init", "b200gym_rom_step", "b200gym_rom_reset", "b200gym_rom_reset_from_root", "b200gym_rom_tracking_policy",
+                 "b200gym_rom_rollout"):
         getattr(L, name).restype = C.c_int
     f64 = C.c_double
     L.b200gym_gae_returns.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, f32, f32, vp]
@@ -239,4 +245,8 @@ def fill_params(p, num_sum_rows, sum_row, zero_lstm_on_reset=False) -> LeggedPar
     s.custom_origins, s.zero_lstm_on_reset = int(p.custom_origins), int(zero_lstm_on_reset)
     s.base_init_state[:] = p.base_init_state
     s.seed_lo, s.seed_hi = p.seed & 0xFFFFFFFF, (p.seed >> 32) & 0xFFFFFFFF
+    s.traj_mode, s.traj_n, s.traj_horizon = int(p.traj_mode), p.traj_n, p.traj_horizon
+    s.traj_scale[:], s.traj_weight[:] = p.traj_scale, p.traj_weight
+    s.diff_neg_slope, s.diff_pos_slope = p.diff_neg_slope, p.diff_pos_slope
+    s.push_t_lo, s.push_t_span = p.time_between_pushes[0], p.time_between_pushes[1] - p.time_between_pushes[0]
     return s

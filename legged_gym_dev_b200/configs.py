@@ -117,6 +117,82 @@ UPSTREAM_REWARD_SCALES = dict(tracking_lin_vel=1.0, tracking_ang_vel=0.5, lin_ve
 UPSTREAM_COMMAND_RANGES = dict(lin_vel_x=[-1.0, 1.0], lin_vel_y=[-1.0, 1.0], ang_vel_yaw=[-1, 1], heading=[-3.14, 3.14])
 
 
+# ---- LeggedRobotTrajectoryCfg family (legged_gym/envs/base/legged_robot_trajectory_config.py:33-231 and the anymal_c
+# *_trajectory overrides).  The fork's anymal trajectory configs do not carry every attribute LeggedRobotTrajectory reads
+# (they were moved on to the hopper configs): `rewards.tracking_sigma`, `domain_rand.{randomize_rom_distance, max_rom_dist,
+# zero_rom_distance_likelihood}`, `curriculum.*`, `trajectory_generator.{dN, prob_stationary}` and an existing weight-sampler
+# class are filled in from legged_gym/envs/hopper/flat_trajectory/hopper_trajectory_config.py:113-260 and flagged here.
+_TRAJ_BASE = {
+    "env": dict(num_envs=4096, num_observations=240, num_privileged_obs=None, num_actions=12, env_spacing=3.0,
+                send_timeouts=True, episode_length_s=20),
+    "terrain": dict(_BASE["terrain"], slope_threshold=0.75),
+    "rom": dict(cls="SingleInt2D", dt=0.1, z_min=[-1e9, -1e9], z_max=[1e9, 1e9], v_min=[-0.35, -0.35], v_max=[0.35, 0.35],
+                prob_stationary=1e-4, stationary_duration=1.0),                                    # :71-88
+    "trajectory_generator": dict(cls="TrajectoryGenerator", t_samp_cls="UniformSampleHoldDT",
+                                 weight_samp_cls="UniformWeightSampler",   # shipped name 'WeightSamplerSampleAndHold' does not exist
+                                 N=10, t_low=1, t_high=2, freq_low=0.01, freq_high=2, seed=42, DN=1,
+                                 dN=1, prob_stationary=1e-4),                                      # :90-100 (+ dN, prob_stationary)
+    "init_state": _BASE["init_state"],
+    "control": _BASE["control"],
+    "asset": _BASE["asset"],
+    "domain_rand": dict(randomize_friction=True, friction_range=[0.5, 1.25], randomize_base_mass=False,
+                        added_mass_range=[-1.0, 1.0], push_robots=True, push_interval_s=15, max_push_vel_xy=1.0,
+                        max_push_vel=[0.25, 0.25, 0.25, 0.75, 0.75, 0.75], time_between_pushes=[0.5, 10.0],   # :149-158
+                        randomize_rom_distance=True, max_rom_dist=[1.0, 1.0], zero_rom_distance_likelihood=0.25),  # filled in
+    "rewards": dict(scales=dict(termination=-0.5), only_positive_rewards=False, soft_dof_pos_limit=1.0, soft_dof_vel_limit=1.0,
+                    soft_torque_limit=1.0, base_height_target=1.0, max_contact_force=100.0,
+                    differential_error=dict(neg_slope=1.0, pos_slope=4.0),
+                    reward_weighting=dict(position=1.0, velocity=1.0, orientation=0.3, angular_velocity=0.2, v_perp=0.4),
+                    tracking_sigma=0.25),                                                          # :160-194 (+ tracking_sigma)
+    "curriculum": dict(use_curriculum=False, curriculum_steps=[2500, 5000]),                       # filled in
+    "normalization": dict(obs_scales=dict(lin_vel=2.0, ang_vel=0.25, dof_pos=1.0, dof_vel=0.05, height_measurements=5.0,
+                                          trajectory=[1.0, 1.0]), clip_observations=100.0, clip_actions=100.0),
+    "noise": _BASE["noise"],
+    "sim": _BASE["sim"],
+}
+
+_ANYMAL_ROUGH_TRAJ = _merge(_TRAJ_BASE, {   # anymal_c/mixed_terrains_trajectory/anymal_c_rough_trajectory_config.py:32-86
+    "env": dict(num_envs=4096, num_actions=12, num_observations=65 + 187),
+    "terrain": dict(mesh_type="trimesh", curriculum=False),   # the terrain curriculum needs self.commands (:508): off
+    "init_state": _ANYMAL_ROUGH["init_state"],
+    "control": _ANYMAL_ROUGH["control"],
+    "asset": _ANYMAL_ROUGH["asset"],
+    "domain_rand": dict(randomize_base_mass=True, added_mass_range=[-5.0, 5.0]),
+    "rewards": dict(base_height_target=0.5, max_contact_force=500.0, only_positive_rewards=False),
+})
+
+_ANYMAL_FLAT_TRAJ = _merge(_ANYMAL_ROUGH_TRAJ, {   # anymal_c/flat_trajectory/anymal_c_flat_trajectory_config.py:32-52
+    "env": dict(num_observations=65),
+    "terrain": dict(mesh_type="plane", measure_heights=False),
+    "asset": dict(self_collisions=0),
+    "rewards": dict(max_contact_force=350.0, scales=dict(orientation=-5.0, torques=-0.000025, feet_air_time=0.5)),
+    "domain_rand": dict(friction_range=[0.0, 1.5]),
+})
+
+# every reward term LeggedRobotTrajectory defines (legged_robot_trajectory.py:1000-1110) except stand_still (reads self.commands)
+TRAJECTORY_ALL_REWARD_SCALES = dict(
+    action_rate=-0.01, ang_vel_xy=-0.05, base_height=-1.0, collision=-1.0, differential_error=2.0, dof_acc=-2.5e-7,
+    dof_pos_limits=-10.0, dof_vel=-1e-4, dof_vel_limits=-0.5, feet_air_time=1.0, feet_contact_forces=-0.01, lin_vel_z=-2.0,
+    orientation=-5.0, stumble=-0.3, termination=-3.0, torque_limits=-0.02, torques=-1e-5, tracking_rom=6.0)
+
+
+def anymal_c_rough_trajectory_cfg():
+    return _tree(_ANYMAL_ROUGH_TRAJ)
+
+
+def anymal_c_flat_trajectory_cfg():
+    return _tree(_ANYMAL_FLAT_TRAJ)
+
+
+def anymal_c_flat_trajectory_cfg_ppo():
+    return _tree(_merge(_PPO, {"policy": dict(actor_hidden_dims=[128, 64, 32], critic_hidden_dims=[128, 64, 32]),
+                               "runner": dict(experiment_name="flat_anymal_c_trajectory", max_iterations=300)}))
+
+
+def anymal_c_rough_trajectory_cfg_ppo():
+    return _tree(_merge(_PPO, {"runner": dict(experiment_name="rough_anymal_trajectory_c")}))
+
+
 def anymal_c_rough_cfg():
     return _tree(_ANYMAL_ROUGH)
 

@@ -8,7 +8,7 @@
 namespace philox {
 
 enum Site : uint32_t {
-    CMD_PERIODIC = 1, PUSH = 2, TERRAIN = 3, RESET_DOF = 4, RESET_XY = 5, RESET_VEL = 6, CMD_RESET = 7, OBS_NOISE = 8,
+    CMD_PERIODIC = 1, PUSH = 2, TERRAIN = 3, RESET_DOF = 4, RESET_XY = 5, RESET_VEL = 6, CMD_RESET = 7, OBS_NOISE = 8, PUSH_TIMER = 9,
     ROM_INIT = 16, ROM_ROOT = 17, ROM_DIST_MASK = 18, ROM_DIST = 19, ROM_CONST = 20, ROM_RAMP = 21, ROM_EXTREME = 22,
     ROM_SIN_MAG = 23, ROM_SIN_MEAN = 24, ROM_SIN_FREQ = 25, ROM_SIN_OFF = 26, ROM_TFINAL = 27, ROM_WEIGHTS = 28,
     ROM_STATIONARY = 29

@@ -44,11 +44,20 @@ constexpr int LPE = 4;     // lanes per env in phase W
 struct SqThr { float gt1, gt01, gt02, lt01; };
 constexpr int ND = B200GYM_NUM_DOF;
 constexpr int HPAD = 192;  // padded per-env stride of the raw height tile (>= 187)
+// LeggedRobotTrajectory (legged_robot_trajectory.py:274-287): the 3 command columns become the N x rom.n trajectory block
+constexpr int TRAJ_W = B200GYM_TRAJ_WIDTH;
+template <bool TRAJ> struct ObsLayout {
+    static constexpr int CW = TRAJ ? TRAJ_W : 3;       // command / trajectory block
+    static constexpr int DOF = 9 + CW;                  // first dof_pos column
+    static constexpr int OW = DOF + 3 * ND;             // columns before the height block (48 | 65)
+    static constexpr int NB = (DOF + 2 * ND + 3) / 4;   // Philox blocks covering the noisy columns [0, DOF + 24)
+    static constexpr int HB0 = OW / 4, HSH = OW % 4;    // height column j -> block HB0 + (j + HSH) / 4, word (j + HSH) % 4
+};
 
 enum Term {
-    T_ACTION_RATE = 0, T_ANG_VEL_XY, T_BASE_HEIGHT, T_COLLISION, T_DOF_ACC, T_DOF_POS_LIMITS, T_DOF_VEL,
+    T_ACTION_RATE = 0, T_ANG_VEL_XY, T_BASE_HEIGHT, T_COLLISION, T_DIFFERENTIAL_ERROR, T_DOF_ACC, T_DOF_POS_LIMITS, T_DOF_VEL,
     T_DOF_VEL_LIMITS, T_FEET_AIR_TIME, T_FEET_CONTACT_FORCES, T_LIN_VEL_Z, T_ORIENTATION, T_STAND_STILL,
-    T_STUMBLE, T_TORQUE_LIMITS, T_TORQUES, T_TRACKING_ANG_VEL, T_TRACKING_LIN_VEL, T_TERMINATION
+    T_STUMBLE, T_TORQUE_LIMITS, T_TORQUES, T_TRACKING_ANG_VEL, T_TRACKING_LIN_VEL, T_TRACKING_ROM, T_TERMINATION
 };
 // per-env partial sums handed from phase W to phase S
 enum Part { P_ACTION_RATE = 0, P_DOF_ACC, P_DOF_VEL, P_TORQUES, P_POS_LIM, P_VEL_LIM, P_TQ_LIM, P_STAND, P_AIR, P_STUMBLE, P_FCF,
@@ -156,13 +165,14 @@ struct TileSmem {
     uint8_t *reset, *tout;
     int16_t* hraw;
     float *bh, *zpost, *stage, *hsum, *unoise;
+    float *traj, *perr, *tpush;
     float2 *pts, *yaw;
     double* acc;
     int* nreset;
     size_t bytes;
 };
 
-template <int TILE, bool ROUGH>
+template <int TILE, bool ROUGH, bool TRAJ>
 __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K, bool need_hpart) {
     Carver c{base, 0};
     TileSmem s;
@@ -179,8 +189,12 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
     s.lc = c.take<uint8_t>(TILE * 4);
     s.ep = c.take<long long>(TILE);
     s.sums = c.take<float>(static_cast<size_t>(K > 0 ? K : 1) * TILE);
-    // the obs tile reuses the contact tile when it fits (B*3 >= 48): contact forces are dead after phase W's contact pass
-    s.obs = (PP_ALIAS_OBS && B * 3 >= 48) ? s.contact : c.take<float>(TILE * 48);
+    // the obs tile reuses the contact tile when it fits (B*3 >= OW): contact forces are dead after phase W's contact pass
+    constexpr int OW = ObsLayout<TRAJ>::OW;
+    s.obs = (PP_ALIAS_OBS && B * 3 >= OW) ? s.contact : c.take<float>(TILE * OW);
+    s.traj = TRAJ ? c.take<float>(TILE * TRAJ_W) : nullptr;
+    s.perr = TRAJ ? c.take<float>(TILE * 2) : nullptr;
+    s.tpush = TRAJ ? c.take<float>(TILE) : nullptr;
     s.blv = c.take<float>(TILE * 3);
     s.bav = c.take<float>(TILE * 3);
     s.pg = c.take<float>(TILE * 3);
@@ -215,19 +229,21 @@ __device__ __forceinline__ void coop_copy(T* dst, const T* src, int n) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
-template <int TILE, bool ROUGH>
+template <int TILE, bool ROUGH, bool TRAJ>
 __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) post_physics_kernel(const __grid_constant__ B200LeggedParams p,
                                                                                const __grid_constant__ B200LeggedBuffers b,
                                                                                uint64_t step, long long env_off, int do_push,
                                                                                const SqThr thr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int B = p.num_bodies, K = p.num_sum_rows, N = p.num_envs, O = p.num_obs;
-    const TileSmem s = carve_tile<TILE, ROUGH>(smem_raw, B, K, p.reward_scale[T_BASE_HEIGHT] != 0.0f);
+    const TileSmem s = carve_tile<TILE, ROUGH, TRAJ>(smem_raw, B, K, p.reward_scale[T_BASE_HEIGHT] != 0.0f);
     const int tid = threadIdx.x;
     const int tile0 = blockIdx.x * TILE;
     const int nvalid = min(TILE, N - tile0);
     const bool full = (nvalid == TILE);
     const float* rs = p.reward_scale;
+    using OL = ObsLayout<TRAJ>;
+    constexpr int OW = OL::OW;
 
     pdl_launch_dependents();
     pdl_wait();   // everything below reads what the torque kernels / the previous step wrote (incl. the device step counter)
@@ -253,7 +269,8 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
     // ---- stage the tile: one bulk copy per tensor -------------------------------------------------
     if (full) {
         if (tid == 0) {
-            const uint32_t bytes = TILE * (13 + 24 + 3 * B + 4 * ND + 4 + 4) * 4 + TILE * 4 + TILE * 8 + K * TILE * 4;
+            const uint32_t bytes = TILE * (13 + 24 + 3 * B + 4 * ND + 4 + 4) * 4 + TILE * 4 + TILE * 8 + K * TILE * 4 +
+                                   (TRAJ ? TILE * (TRAJ_W + 2 + 1) * 4 : 0);
             mbar_expect_tx(s.bar, bytes);
             bulk_g2s(s.root, b.root_states + static_cast<size_t>(tile0) * 13, TILE * 13 * 4, s.bar);
             bulk_g2s(s.dof, b.dof_state + static_cast<size_t>(tile0) * 24, TILE * 24 * 4, s.bar);
@@ -266,6 +283,11 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
             bulk_g2s(s.fat, b.feet_air_time + static_cast<size_t>(tile0) * 4, TILE * 4 * 4, s.bar);
             bulk_g2s(s.lc, b.last_contacts + static_cast<size_t>(tile0) * 4, TILE * 4, s.bar);
             bulk_g2s(s.ep, b.episode_length_buf + tile0, TILE * 8, s.bar);
+            if (TRAJ) {
+                bulk_g2s(s.traj, b.trajectory + static_cast<size_t>(tile0) * TRAJ_W, TILE * TRAJ_W * 4, s.bar);
+                bulk_g2s(s.perr, b.prev_error + static_cast<size_t>(tile0) * 2, TILE * 2 * 4, s.bar);
+                bulk_g2s(s.tpush, b.time_until_next_push + tile0, TILE * 4, s.bar);
+            }
             for (int k = 0; k < K; ++k)
                 bulk_g2s(s.sums + k * TILE, b.episode_sums + static_cast<size_t>(k) * N + tile0, TILE * 4, s.bar);
         }
@@ -282,6 +304,11 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         coop_copy(s.fat, b.feet_air_time + static_cast<size_t>(tile0) * 4, nvalid * 4);
         coop_copy(s.lc, b.last_contacts + static_cast<size_t>(tile0) * 4, nvalid * 4);
         coop_copy(s.ep, reinterpret_cast<const long long*>(b.episode_length_buf) + tile0, nvalid);
+        if (TRAJ) {
+            coop_copy(s.traj, b.trajectory + static_cast<size_t>(tile0) * TRAJ_W, nvalid * TRAJ_W);
+            coop_copy(s.perr, b.prev_error + static_cast<size_t>(tile0) * 2, nvalid * 2);
+            coop_copy(s.tpush, b.time_until_next_push + tile0, nvalid);
+        }
         for (int k = 0; k < K; ++k) coop_copy(s.sums + k * TILE, b.episode_sums + static_cast<size_t>(k) * N + tile0, nvalid);
         __syncthreads();
     }
@@ -302,7 +329,7 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
             s.yaw[tid] = make_float2(div_rn(R[5], nq), div_rn(R[6], nq));
         }
         __syncthreads();
-        const int H = p.num_heights, Q = (H + 3) >> 2;
+        const int H = p.num_heights, Q = (H + OL::HSH + 3) >> 2;   // Philox blocks holding the height-noise draws
         const int rows = p.terrain_rows, cols = p.terrain_cols;
         const float inv_hs = div_rn(1.0f, p.horizontal_scale);
         const HeightConsts hc = {make_float2(p.border_size, p.border_size), make_float2(-p.horizontal_scale, -p.horizontal_scale),
@@ -318,12 +345,12 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
                 // per-warp scratch so that a lane can pick up the draws of ITS points
                 for (int k = 0; k < ne; ++k) {
                     const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e0 + k), step);
-                    if (lane < Q) *reinterpret_cast<float4*>(un + k * HPAD + 4 * lane) = philox::u01(rng.words(philox::OBS_NOISE, 12 + lane));
+                    if (lane < Q) *reinterpret_cast<float4*>(un + k * HPAD + 4 * lane) = philox::u01(rng.words(philox::OBS_NOISE, OL::HB0 + lane));
                 }
                 const int k = lane >> 4, blk = 32 + (lane & 15);
                 if (k < ne && blk < Q) {
                     const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e0 + k), step);
-                    *reinterpret_cast<float4*>(un + k * HPAD + 4 * blk) = philox::u01(rng.words(philox::OBS_NOISE, 12 + blk));
+                    *reinterpret_cast<float4*>(un + k * HPAD + 4 * blk) = philox::u01(rng.words(philox::OBS_NOISE, OL::HB0 + blk));
                 }
                 __syncwarp();
             }
@@ -349,8 +376,8 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
                     }
                 }
                 float* mh_out = b.measured_heights + static_cast<size_t>(tile0 + e) * H + lane;
-                float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48 + lane;
-                const float* ue = un + k * HPAD + lane;
+                float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + OW + lane;
+                const float* ue = un + k * HPAD + lane + OL::HSH;
                 float part = 0.0f;
 #pragma unroll
                 for (int r = 0; r < RND; ++r) {
@@ -441,19 +468,32 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
 #if PP_ALIAS_OBS
         __syncthreads();   // every lane of the CTA is done with the contact tile: it becomes the obs tile
 #endif
-        // uniforms for observation columns 0..35 = Philox blocks 0..8, exchanged through the obs tile
+        // uniforms for the noisy observation columns (0..35 = Philox blocks 0..8; trajectory layout: 0..52 = blocks 0..13),
+        // exchanged through the obs tile
         if (p.add_noise) {
-            float4* stage = reinterpret_cast<float4*>(s.obs + e * 48);
-            stage[g] = philox::u01(rng.words(philox::OBS_NOISE, g));
-            stage[g + 4] = philox::u01(rng.words(philox::OBS_NOISE, g + 4));
-            if (g == 0) stage[8] = philox::u01(rng.words(philox::OBS_NOISE, 8));
+            if (!TRAJ) {
+                float4* stage = reinterpret_cast<float4*>(s.obs + e * OW);
+                stage[g] = philox::u01(rng.words(philox::OBS_NOISE, g));
+                stage[g + 4] = philox::u01(rng.words(philox::OBS_NOISE, g + 4));
+                if (g == 0) stage[8] = philox::u01(rng.words(philox::OBS_NOISE, 8));
+            } else {   // rows of 65 floats are not 16-byte aligned: scalar stores
+#pragma unroll
+                for (int r = 0; r < (OL::NB + 3) / 4; ++r) {
+                    const int blk = g + 4 * r;
+                    if (blk < OL::NB) {
+                        const float4 u = philox::u01(rng.words(philox::OBS_NOISE, blk));
+                        float* st = s.obs + e * OW + 4 * blk;
+                        st[0] = u.x, st[1] = u.y, st[2] = u.z, st[3] = u.w;
+                    }
+                }
+            }
         }
         // DOF observation columns 12..47 (+ noise), already clipped (legged_robot.py:100-101,208-226)
         if (p.add_noise) {
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const float u1 = s.obs[e * 48 + 12 + 3 * g + j], u2 = s.obs[e * 48 + 24 + 3 * g + j];
+                const float u1 = s.obs[e * OW + OL::DOF + 3 * g + j], u2 = s.obs[e * OW + OL::DOF + ND + 3 * g + j];
                 o_pos[j] = add_noise(o_pos[j], u1, p.noise_dof_pos);
                 o_vel[j] = add_noise(o_vel[j], u2, p.noise_dof_vel);
             }
@@ -461,9 +501,9 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         }
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            s.obs[e * 48 + 12 + 3 * g + j] = clampf(o_pos[j], -p.clip_obs, p.clip_obs);
-            s.obs[e * 48 + 24 + 3 * g + j] = clampf(o_vel[j], -p.clip_obs, p.clip_obs);
-            s.obs[e * 48 + 36 + 3 * g + j] = clampf(o_act[j], -p.clip_obs, p.clip_obs);
+            s.obs[e * OW + OL::DOF + 3 * g + j] = clampf(o_pos[j], -p.clip_obs, p.clip_obs);
+            s.obs[e * OW + OL::DOF + ND + 3 * g + j] = clampf(o_vel[j], -p.clip_obs, p.clip_obs);
+            s.obs[e * OW + OL::DOF + 2 * ND + 3 * g + j] = clampf(o_act[j], -p.clip_obs, p.clip_obs);
         }
         // quad reductions -> per-env partial sums
         pa_rate = quad_sum(pa_rate), pd_acc = quad_sum(pd_acc), pd_vel = quad_sum(pd_vel), ptq = quad_sum(ptq);
@@ -507,8 +547,9 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         // R5: command resampling + heading (legged_robot.py:343-354)
         const float4 cmd4 = *reinterpret_cast<const float4*>(s.cmd + e * 4);
         float c0 = cmd4.x, c1 = cmd4.y, c2 = cmd4.z, c3 = cmd4.w;
-        if (static_cast<int>(ep) % p.resample_steps == 0) resample_commands(p, thr, rng, philox::CMD_PERIODIC, c0, c1, c2, c3);
-        if (p.heading_command) {
+        // (LeggedRobotTrajectory has no command resampling: legged_robot_trajectory.py:405-417)
+        if (!TRAJ && static_cast<int>(ep) % p.resample_steps == 0) resample_commands(p, thr, rng, philox::CMD_PERIODIC, c0, c1, c2, c3);
+        if (!TRAJ && p.heading_command) {
             // forward = quat_apply(q, [1,0,0]) (x,y only): t = 2*cross(q_xyz, [1,0,0]) = (0, 2qz, -2qy)
             const float tyy = 2.0f * qz, tzz = -2.0f * qy;
             const float fx = 1.0f + (qy * tzz - qz * tyy);
@@ -518,11 +559,19 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
 
         // R7: pushes (legged_robot.py:456-461)
         float lrv[6] = {R[7], R[8], R[9], R[10], R[11], R[12]};
-        if (do_push) {
+        bool pushed = do_push != 0;
+        float tpush = 0.0f;
+        if (TRAJ) {   // per-env push timers (legged_robot_trajectory.py:169-178)
+            tpush = sub_rn(s.tpush[e], p.dt);
+            pushed = tpush <= 0.0f;
+        }
+        if (pushed) {
             const uint4 w = rng.words(philox::PUSH, 0);
             lrv[0] = affine_rn(p.push_span, philox::u01(w.x), p.push_lo);
             lrv[1] = affine_rn(p.push_span, philox::u01(w.y), p.push_lo);
+            if (TRAJ) tpush = affine_rn(p.push_t_span, philox::u01(rng.words(philox::PUSH_TIMER, 0).x), p.push_t_lo);
         }
+        if (TRAJ) s.tpush[e] = tpush;
 
         // R8: termination (legged_robot.py:139-145)
         const bool time_out = static_cast<float>(ep) > p.max_episode_length;
@@ -553,11 +602,21 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
             add_term(T_BASE_HEIGHT, dh * dh);
         }
         if (rs[T_COLLISION] != 0.f) add_term(T_COLLISION, P[P_COLL * TILE]);
+        float te0 = 0.0f, te1 = 0.0f;   // square(proj_z(root) - trajectory[:, 0]) (legged_robot_trajectory.py:1064-1066, :1101-1103)
+        if (TRAJ) {
+            const float d0 = R[0] - s.traj[e * TRAJ_W], d1 = R[1] - s.traj[e * TRAJ_W + 1];
+            te0 = d0 * d0, te1 = d1 * d1;
+            if (rs[T_DIFFERENTIAL_ERROR] != 0.f) {   // :1100-1110
+                const float pe0 = s.perr[e * 2], pe1 = s.perr[e * 2 + 1];
+                const float de = sqrtf(te0 * te0 + te1 * te1) - sqrtf(pe0 * pe0 + pe1 * pe1);
+                add_term(T_DIFFERENTIAL_ERROR, (de < 0.0f ? p.diff_neg_slope : p.diff_pos_slope) * de);
+            }
+        }
         if (rs[T_DOF_ACC] != 0.f) add_term(T_DOF_ACC, P[P_DOF_ACC * TILE]);
         if (rs[T_DOF_POS_LIMITS] != 0.f) add_term(T_DOF_POS_LIMITS, P[P_POS_LIM * TILE]);
         if (rs[T_DOF_VEL] != 0.f) add_term(T_DOF_VEL, P[P_DOF_VEL * TILE]);
         if (rs[T_DOF_VEL_LIMITS] != 0.f) add_term(T_DOF_VEL_LIMITS, P[P_VEL_LIM * TILE]);
-        if (rs[T_FEET_AIR_TIME] != 0.f) add_term(T_FEET_AIR_TIME, P[P_AIR * TILE] * (cmd_gt01 ? 1.0f : 0.0f));
+        if (rs[T_FEET_AIR_TIME] != 0.f) add_term(T_FEET_AIR_TIME, TRAJ ? P[P_AIR * TILE] : P[P_AIR * TILE] * (cmd_gt01 ? 1.0f : 0.0f));
         if (rs[T_FEET_CONTACT_FORCES] != 0.f) add_term(T_FEET_CONTACT_FORCES, P[P_FCF * TILE]);
         if (rs[T_LIN_VEL_Z] != 0.f) add_term(T_LIN_VEL_Z, blz * blz);
         if (rs[T_ORIENTATION] != 0.f) add_term(T_ORIENTATION, pgx * pgx + pgy * pgy);
@@ -574,11 +633,13 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
             const float ex = c0 - blx, ey = c1 - bly;
             add_term(T_TRACKING_LIN_VEL, expf(-(ex * ex + ey * ey) * inv_sigma));
         }
+        if (TRAJ && rs[T_TRACKING_ROM] != 0.f)   // exp(-inner(err^2, weighting) / sigma), legged_robot_trajectory.py:1060-1069
+            add_term(T_TRACKING_ROM, expf(-(te0 * p.traj_weight[0] + te1 * p.traj_weight[1]) / p.tracking_sigma));
         if (p.only_positive) rew = fmaxf(rew, 0.0f);
         if (rs[T_TERMINATION] != 0.f) add_term(T_TERMINATION, (reset && !time_out) ? 1.0f : 0.0f);
 
         // R10: in-place reset (legged_robot.py:147-187, anymal.py:56-60) — a branch, not a host compaction (H7)
-        float zpost = R[2];
+        float zpost = R[2], xpost = R[0], ypost = R[1];
         long long ep_out = ep, level = 0;
         if (p.terrain_curriculum && valid) level = b.terrain_levels[ge];
         if (reset && valid) {
@@ -598,23 +659,47 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
                 b.env_origins[ge * 3 + 0] = ox, b.env_origins[ge * 3 + 1] = oy, b.env_origins[ge * 3 + 2] = oz;
             }
             // dofs: q = q0 * U(0.5, 1.5), qd = 0 (legged_robot.py:423-425); fix up what phase W assumed
-            for (int blk = 0; blk < 3; ++blk) {
-                const uint4 w = rng.words(philox::RESET_DOF, blk);
-                const uint4 n1 = rng.words(philox::OBS_NOISE, 3 + blk), n2 = rng.words(philox::OBS_NOISE, 6 + blk);
+            if (!TRAJ) {
+                for (int blk = 0; blk < 3; ++blk) {
+                    const uint4 w = rng.words(philox::RESET_DOF, blk);
+                    const uint4 n1 = rng.words(philox::OBS_NOISE, 3 + blk), n2 = rng.words(philox::OBS_NOISE, 6 + blk);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int d = 4 * blk + i;
-                    const float q0 = p.default_dof_pos[d];
-                    const float q = mul_rn(q0, affine_rn(1.0f, philox::u01(philox::word(w, i)), 0.5f));
-                    reinterpret_cast<float2*>(b.dof_state)[ge * ND + d] = make_float2(q, 0.0f);
-                    float op = (q - q0) * p.obs_dof_pos, ov = 0.0f;
-                    if (p.add_noise) {
-                        op = add_noise(op, philox::u01(philox::word(n1, i)), p.noise_dof_pos);
-                        ov = add_noise(ov, philox::u01(philox::word(n2, i)), p.noise_dof_vel);
+                    for (int i = 0; i < 4; ++i) {
+                        const int d = 4 * blk + i;
+                        const float q0 = p.default_dof_pos[d];
+                        const float q = mul_rn(q0, affine_rn(1.0f, philox::u01(philox::word(w, i)), 0.5f));
+                        reinterpret_cast<float2*>(b.dof_state)[ge * ND + d] = make_float2(q, 0.0f);
+                        float op = (q - q0) * p.obs_dof_pos, ov = 0.0f;
+                        if (p.add_noise) {
+                            op = add_noise(op, philox::u01(philox::word(n1, i)), p.noise_dof_pos);
+                            ov = add_noise(ov, philox::u01(philox::word(n2, i)), p.noise_dof_vel);
+                        }
+                        s.obs[e * OW + OL::DOF + d] = clampf(op, -p.clip_obs, p.clip_obs);
+                        s.obs[e * OW + OL::DOF + ND + d] = clampf(ov, -p.clip_obs, p.clip_obs);
+                        s.ldv[e * ND + d] = 0.0f;
                     }
-                    s.obs[e * 48 + 12 + d] = clampf(op, -p.clip_obs, p.clip_obs);
-                    s.obs[e * 48 + 24 + d] = clampf(ov, -p.clip_obs, p.clip_obs);
-                    s.ldv[e * ND + d] = 0.0f;
+                }
+            } else {   // dof columns 29.. are not Philox-block aligned: (column >> 2, column & 3) per element (rare path)
+                for (int blk = 0; blk < 3; ++blk) {
+                    const uint4 w = rng.words(philox::RESET_DOF, blk);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int d = 4 * blk + i;
+                        const float q0 = p.default_dof_pos[d];
+                        const float q = mul_rn(q0, affine_rn(1.0f, philox::u01(philox::word(w, i)), 0.5f));
+                        reinterpret_cast<float2*>(b.dof_state)[ge * ND + d] = make_float2(q, 0.0f);
+                        float op = (q - q0) * p.obs_dof_pos, ov = 0.0f;
+                        if (p.add_noise) {
+                            const int c1 = OL::DOF + d, c2 = OL::DOF + ND + d;
+                            const uint4 n1 = rng.words(philox::OBS_NOISE, c1 >> 2), n2 = rng.words(philox::OBS_NOISE, c2 >> 2);
+                            const int k1 = c1 & 3, k2 = c2 & 3;
+                            op = add_noise(op, philox::u01(k1 == 0 ? n1.x : k1 == 1 ? n1.y : k1 == 2 ? n1.z : n1.w), p.noise_dof_pos);
+                            ov = add_noise(ov, philox::u01(k2 == 0 ? n2.x : k2 == 1 ? n2.y : k2 == 2 ? n2.z : n2.w), p.noise_dof_vel);
+                        }
+                        s.obs[e * OW + OL::DOF + d] = clampf(op, -p.clip_obs, p.clip_obs);
+                        s.obs[e * OW + OL::DOF + ND + d] = clampf(ov, -p.clip_obs, p.clip_obs);
+                        s.ldv[e * ND + d] = 0.0f;
+                    }
                 }
             }
             // root (legged_robot.py:441-449)
@@ -631,12 +716,16 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
             nr[7] = affine_rn(1.0f, philox::u01(w0.x), -0.5f), nr[8] = affine_rn(1.0f, philox::u01(w0.y), -0.5f);
             nr[9] = affine_rn(1.0f, philox::u01(w0.z), -0.5f), nr[10] = affine_rn(1.0f, philox::u01(w0.w), -0.5f);
             nr[11] = affine_rn(1.0f, philox::u01(w1.x), -0.5f), nr[12] = affine_rn(1.0f, philox::u01(w1.y), -0.5f);
-            zpost = nr[2];
+            zpost = nr[2], xpost = nr[0], ypost = nr[1];
 #pragma unroll
             for (int k = 0; k < 6; ++k) lrv[k] = nr[7 + k];
 #pragma unroll
             for (int k = 0; k < 13; ++k) b.root_states[ge * 13 + k] = nr[k];
-            resample_commands(p, thr, rng, philox::CMD_RESET, c0, c1, c2, c3);
+            if (!TRAJ) resample_commands(p, thr, rng, philox::CMD_RESET, c0, c1, c2, c3);
+            if (TRAJ) {   // prev_error from the (stale) trajectory and the NEW root position (legged_robot_trajectory.py:233)
+                const float d0 = s.traj[e * TRAJ_W] - nr[0], d1 = s.traj[e * TRAJ_W + 1] - nr[1];
+                s.perr[e * 2] = d0 * d0, s.perr[e * 2 + 1] = d1 * d1;
+            }
             *reinterpret_cast<float4*>(s.fat + e * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             ep_out = 0;
             // extras["episode"] statistics (legged_robot.py:175-179): per-CTA partials in shared memory
@@ -654,7 +743,7 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
                     for (int k = 0; k < 24; ++k) hp[k] = z4, cp[k] = z4;
                 }
             }
-        } else if (do_push && valid) {
+        } else if (pushed && valid) {
             b.root_states[ge * 13 + 7] = lrv[0];
             b.root_states[ge * 13 + 8] = lrv[1];
         }
@@ -668,9 +757,12 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         // R11: first 12 observation columns (+ noise, clip); uniforms were staged by phase W
         float o[12] = {blx * p.obs_lin_vel, bly * p.obs_lin_vel, blz * p.obs_lin_vel, bax * p.obs_ang_vel, bay * p.obs_ang_vel,
                        baz * p.obs_ang_vel, pgx, pgy, pgz, c0 * p.obs_lin_vel, c1 * p.obs_lin_vel, c2 * p.obs_ang_vel};
-        float4* o4 = reinterpret_cast<float4*>(s.obs + e * 48);
+        float4* o4 = reinterpret_cast<float4*>(s.obs + e * OW);
+        float* orow = s.obs + e * OW;
         if (p.add_noise) {
-            const float4 u0 = o4[0], u1 = o4[1], u2 = o4[2];
+            float4 u0, u1, u2;
+            if (!TRAJ) u0 = o4[0], u1 = o4[1], u2 = o4[2];
+            else u0 = make_float4(orow[0], orow[1], orow[2], orow[3]), u1 = make_float4(orow[4], orow[5], orow[6], orow[7]), u2.x = orow[8];
             o[0] = add_noise(o[0], u0.x, p.noise_lin_vel), o[1] = add_noise(o[1], u0.y, p.noise_lin_vel);
             o[2] = add_noise(o[2], u0.z, p.noise_lin_vel), o[3] = add_noise(o[3], u0.w, p.noise_ang_vel);
             o[4] = add_noise(o[4], u1.x, p.noise_ang_vel), o[5] = add_noise(o[5], u1.y, p.noise_ang_vel);
@@ -679,9 +771,19 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         }
 #pragma unroll
         for (int k = 0; k < 12; ++k) o[k] = clampf(o[k], -p.clip_obs, p.clip_obs);
-        o4[0] = make_float4(o[0], o[1], o[2], o[3]);
-        o4[1] = make_float4(o[4], o[5], o[6], o[7]);
-        o4[2] = make_float4(o[8], o[9], o[10], o[11]);
+        if (!TRAJ) {
+            o4[0] = make_float4(o[0], o[1], o[2], o[3]);
+            o4[1] = make_float4(o[4], o[5], o[6], o[7]);
+            o4[2] = make_float4(o[8], o[9], o[10], o[11]);
+        } else {   // (trajectory - proj_z(root)) * trajectory_scale, no noise (legged_robot_trajectory.py:277-283, :573)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) orow[k] = o[k];
+#pragma unroll
+            for (int k = 0; k < TRAJ_W; k += 2) {
+                orow[9 + k] = clampf((s.traj[e * TRAJ_W + k] - xpost) * p.traj_scale[0], -p.clip_obs, p.clip_obs);
+                orow[10 + k] = clampf((s.traj[e * TRAJ_W + k + 1] - ypost) * p.traj_scale[1], -p.clip_obs, p.clip_obs);
+            }
+        }
 
         // R12 + per-env outputs
         s.blv[e * 3 + 0] = blx, s.blv[e * 3 + 1] = bly, s.blv[e * 3 + 2] = blz;
@@ -700,7 +802,7 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
     __syncthreads();
 
     // ---- write the tile back ----------------------------------------------------------------------
-    const bool obs_bulk = full && (O == 48);
+    const bool obs_bulk = full && (O == OW);
     if (full) {
         if (tid == 0) {
             bulk_s2g(b.last_actions + static_cast<size_t>(tile0) * ND, s.act, TILE * ND * 4);
@@ -717,7 +819,11 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
             bulk_s2g(b.base_ang_vel + static_cast<size_t>(tile0) * 3, s.bav, TILE * 3 * 4);
             bulk_s2g(b.projected_gravity + static_cast<size_t>(tile0) * 3, s.pg, TILE * 3 * 4);
             for (int k = 0; k < K; ++k) bulk_s2g(b.episode_sums + static_cast<size_t>(k) * N + tile0, s.sums + k * TILE, TILE * 4);
-            if (obs_bulk) bulk_s2g(b.obs_buf + static_cast<size_t>(tile0) * 48, s.obs, TILE * 48 * 4);
+            if (obs_bulk) bulk_s2g(b.obs_buf + static_cast<size_t>(tile0) * OW, s.obs, TILE * OW * 4);
+            if (TRAJ) {
+                bulk_s2g(b.prev_error + static_cast<size_t>(tile0) * 2, s.perr, TILE * 2 * 4);
+                bulk_s2g(b.time_until_next_push + tile0, s.tpush, TILE * 4);
+            }
             bulk_commit();
         }
     } else {
@@ -735,9 +841,13 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         coop_copy(b.base_ang_vel + static_cast<size_t>(tile0) * 3, s.bav, nvalid * 3);
         coop_copy(b.projected_gravity + static_cast<size_t>(tile0) * 3, s.pg, nvalid * 3);
         for (int k = 0; k < K; ++k) coop_copy(b.episode_sums + static_cast<size_t>(k) * N + tile0, s.sums + k * TILE, nvalid);
+        if (TRAJ) {
+            coop_copy(b.prev_error + static_cast<size_t>(tile0) * 2, s.perr, nvalid * 2);
+            coop_copy(b.time_until_next_push + tile0, s.tpush, nvalid);
+        }
     }
     if (!obs_bulk) {
-        for (int i = tid; i < nvalid * 48; i += TILE * LPE) b.obs_buf[static_cast<size_t>(tile0 + i / 48) * O + (i % 48)] = s.obs[i];
+        for (int i = tid; i < nvalid * OW; i += TILE * LPE) b.obs_buf[static_cast<size_t>(tile0 + i / OW) * O + (i % OW)] = s.obs[i];
     }
 
     // ---- phase H': height observations of the envs that reset this step, redone with the post-reset base height ----
@@ -751,14 +861,17 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
                 if (s.reset[e]) {
                     const float z05 = sub_rn(s.zpost[e], 0.5f);
                     const int pt0 = 4 * q;
-                    float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-                    if (p.add_noise) {
+                    float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+                    if (p.add_noise) {   // height column j sits in Philox block HB0 + (j + HSH) / 4, word (j + HSH) % 4
                         const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
-                        u = philox::u01(rng.words(philox::OBS_NOISE, 12 + q));
+                        const float4 ua = philox::u01(rng.words(philox::OBS_NOISE, OL::HB0 + q));
+                        const float4 ub = OL::HSH ? philox::u01(rng.words(philox::OBS_NOISE, OL::HB0 + q + 1)) : ua;
+                        const float u8[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) un[j] = u8[j + OL::HSH];
                     }
-                    const float un[4] = {u.x, u.y, u.z, u.w};
                     const float* mh_in = b.measured_heights + static_cast<size_t>(tile0 + e) * H + pt0;
-                    float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + 48 + pt0;
+                    float* ob_out = b.obs_buf + static_cast<size_t>(tile0 + e) * O + OW + pt0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (pt0 + j < H) {
@@ -832,13 +945,13 @@ static float sq_lt(float t) {
     return y;
 }
 
-template <int TILE, bool ROUGH>
+template <int TILE, bool ROUGH, bool TRAJ = false>
 int launch_post_physics(const B200LeggedParams& p, const B200LeggedBuffers& b, uint64_t step, long long env_off, int do_push,
                         cudaStream_t stream) {
-    const size_t smem = carve_tile<TILE, ROUGH>(nullptr, p.num_bodies, p.num_sum_rows, p.reward_scale[T_BASE_HEIGHT] != 0.0f).bytes;
+    const size_t smem = carve_tile<TILE, ROUGH, TRAJ>(nullptr, p.num_bodies, p.num_sum_rows, p.reward_scale[T_BASE_HEIGHT] != 0.0f).bytes;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(post_physics_kernel<TILE, ROUGH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(post_physics_kernel<TILE, ROUGH, TRAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
         B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "post_physics: cannot reserve %zu B of shared memory: %s", smem,
                      cudaGetErrorString(e));
@@ -846,7 +959,7 @@ int launch_post_physics(const B200LeggedParams& p, const B200LeggedBuffers& b, u
     }
     const int grid = (p.num_envs + TILE - 1) / TILE;
     static const SqThr thr = {sq_gt(1.0f), sq_gt(0.1f), sq_gt(0.2f), sq_lt(0.1f)};
-    b200_launch_pdl(p.num_envs, post_physics_kernel<TILE, ROUGH>, dim3(grid), dim3(TILE * LPE), smem, stream, p, b, step, env_off, do_push, thr);
+    b200_launch_pdl(p.num_envs, post_physics_kernel<TILE, ROUGH, TRAJ>, dim3(grid), dim3(TILE * LPE), smem, stream, p, b, step, env_off, do_push, thr);
     B200_LAUNCH_CHECK("post_physics");
 #if PP_FINALIZE_KERNEL
     b200_launch_pdl(p.num_envs, extras_finalize_kernel, dim3(1), dim3(32), 0, stream, p, b);
@@ -866,8 +979,22 @@ extern "C" int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedB
     B200_REQUIRE(p->resample_steps > 0, B200GYM_EINVAL, "post_physics: resample_steps must be positive");
     B200_REQUIRE(p->num_term >= 1 && p->num_term <= B200GYM_MAX_TERM, B200GYM_EINVAL, "post_physics: 1..4 termination bodies");
     const bool rough = p->num_heights > 0;
-    B200_REQUIRE(p->num_obs == 48 + p->num_heights, B200GYM_EINVAL, "post_physics: num_obs %d != 48 + %d heights", p->num_obs,
+    const bool traj = p->traj_mode != 0;
+    const int ow = traj ? ObsLayout<true>::OW : ObsLayout<false>::OW;
+    B200_REQUIRE(p->num_obs == ow + p->num_heights, B200GYM_EINVAL, "post_physics: num_obs %d != %d + %d heights", p->num_obs, ow,
                  p->num_heights);
+    B200_REQUIRE(!traj || (p->traj_n == 2 && p->traj_horizon * p->traj_n == TRAJ_W), B200GYM_EINVAL,
+                 "post_physics: trajectory block must be %d columns of a 2-state rom (got N=%d, n=%d)", TRAJ_W, p->traj_horizon, p->traj_n);
+    B200_REQUIRE(!traj || (b->trajectory && b->prev_error && b->time_until_next_push && b200_aligned16(b->trajectory) &&
+                           b200_aligned16(b->prev_error) && b200_aligned16(b->time_until_next_push)),
+                 B200GYM_EINVAL, "post_physics: trajectory / prev_error / time_until_next_push buffers missing or misaligned");
+    B200_REQUIRE(!traj || !p->terrain_curriculum, B200GYM_EINVAL,
+                 "post_physics: the trajectory env has no commands for the terrain curriculum (legged_robot_trajectory.py:508)");
+    B200_REQUIRE(!traj || (p->reward_scale[T_STAND_STILL] == 0.f && p->reward_scale[T_TRACKING_ANG_VEL] == 0.f &&
+                           p->reward_scale[T_TRACKING_LIN_VEL] == 0.f),
+                 B200GYM_EINVAL, "post_physics: command-based reward terms do not exist in the trajectory env");
+    B200_REQUIRE(traj || (p->reward_scale[T_TRACKING_ROM] == 0.f && p->reward_scale[T_DIFFERENTIAL_ERROR] == 0.f), B200GYM_EINVAL,
+                 "post_physics: tracking_rom / differential_error need traj_mode");
     B200_REQUIRE(!rough || (p->num_heights <= HPAD && p->n_px * p->n_py == p->num_heights && p->n_px <= B200GYM_MAX_POINTS &&
                             p->n_py <= B200GYM_MAX_POINTS),
                  B200GYM_EINVAL, "post_physics: unsupported height grid %dx%d", p->n_px, p->n_py);
@@ -893,6 +1020,10 @@ extern "C" int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedB
     if (tile == 0) {
         const char* t = getenv("B200GYM_TILE");
         tile = t ? atoi(t) : 32;
+    }
+    if (traj) {
+        if (rough) return launch_post_physics<32, true, true>(*p, *b, step, env_id_offset, 0, st);
+        return launch_post_physics<32, false, true>(*p, *b, step, env_id_offset, 0, st);
     }
     if (tile == 32) {
         if (rough) return launch_post_physics<32, true>(*p, *b, step, env_id_offset, do_push, st);

@@ -284,25 +284,12 @@ __global__ void __launch_bounds__(128) rom_step_kernel(const __grid_constant__ B
     write_views(p, s, i, g, action ? root : nullptr, mn);
 }
 
-// CustomSim.reset_idx body for one env held in registers; `in_idx` = env is being reset
+// reset_traj + TrajectoryGenerator.reset_idx for one env held in registers (custom_sim.py:80-85 == legged_robot_trajectory.py:248-253,
+// rom_dynamics.py:595-605); pz = proj_z of the (new) root state; `in_idx` = env is being reset
 template <int RN, int W>
-__device__ __forceinline__ void sim_reset(const B200RomParams& p, Gen<RN, W>& g, float* root, int mn, int w, uint64_t genv, bool in_idx) {
+__device__ __forceinline__ void traj_reset(const B200RomParams& p, Gen<RN, W>& g, float* pz, int w, uint64_t genv, bool in_idx) {
     if (W != WMAXR) w = W;
     if (in_idx) {
-        {   // root_states[idx] = U(lower, upper), custom_sim.py:88-91
-            const philox::Stream rng(p.seed_lo, p.seed_hi, genv, g.ctr);
-            const float4 ur = philox::u01(rng.words(philox::ROM_ROOT, 0));
-            root[0] = affine_rn(sub_rn(p.noise_upper[0], p.noise_lower[0]), ur.x, p.noise_lower[0]);
-            root[1] = affine_rn(sub_rn(p.noise_upper[1], p.noise_lower[1]), ur.y, p.noise_lower[1]);
-            if (mn == 4) {
-                root[2] = affine_rn(sub_rn(p.noise_upper[2], p.noise_lower[2]), ur.z, p.noise_lower[2]);
-                root[3] = affine_rn(sub_rn(p.noise_upper[3], p.noise_lower[3]), ur.w, p.noise_lower[3]);
-            }
-            g.ctr += 1;
-        }
-        float pz[RN];   // reset_traj, custom_sim.py:80-85 (proj_z of SingleInt2D = first two model states)
-#pragma unroll
-        for (int c = 0; c < RN; ++c) pz[c] = c < 2 ? root[c] : 0.0f;
         {
             const philox::Stream rng(p.seed_lo, p.seed_hi, genv, g.ctr);
             if (p.randomize_rom_distance && philox::u01(rng.words(philox::ROM_DIST_MASK, 0).x) > p.zero_rom_dist_llh) {
@@ -330,6 +317,54 @@ __device__ __forceinline__ void sim_reset(const B200RomParams& p, Gen<RN, W>& g,
         get_input(p, g, w, genv);
         if (in_idx) advance(p, g, w, true);
     }
+}
+
+// CustomSim.reset_idx body for one env held in registers; `in_idx` = env is being reset
+template <int RN, int W>
+__device__ __forceinline__ void sim_reset(const B200RomParams& p, Gen<RN, W>& g, float* root, int mn, int w, uint64_t genv, bool in_idx) {
+    float pz[RN];
+#pragma unroll
+    for (int c = 0; c < RN; ++c) pz[c] = 0.0f;
+    if (in_idx) {
+        {   // root_states[idx] = U(lower, upper), custom_sim.py:88-91
+            const philox::Stream rng(p.seed_lo, p.seed_hi, genv, g.ctr);
+            const float4 ur = philox::u01(rng.words(philox::ROM_ROOT, 0));
+            root[0] = affine_rn(sub_rn(p.noise_upper[0], p.noise_lower[0]), ur.x, p.noise_lower[0]);
+            root[1] = affine_rn(sub_rn(p.noise_upper[1], p.noise_lower[1]), ur.y, p.noise_lower[1]);
+            if (mn == 4) {
+                root[2] = affine_rn(sub_rn(p.noise_upper[2], p.noise_lower[2]), ur.z, p.noise_lower[2]);
+                root[3] = affine_rn(sub_rn(p.noise_upper[3], p.noise_lower[3]), ur.w, p.noise_lower[3]);
+            }
+            g.ctr += 1;
+        }
+        // reset_traj, custom_sim.py:80-85 (proj_z of SingleInt2D = first two model states)
+#pragma unroll
+        for (int c = 0; c < RN; ++c) pz[c] = c < 2 ? root[c] : 0.0f;
+    }
+    traj_reset(p, g, pz, w, genv, in_idx);
+}
+
+// LeggedRobotTrajectory.reset_traj (legged_robot_trajectory.py:248-253): generator-only reset of the envs flagged in `mask`, p_zx read
+// from the robot's root_states [N, stride] (SingleInt2D.proj_z = first two columns).  The reference returns from reset_idx before
+// touching the generator when no env resets (:217-218), so nothing happens when *any_reset == 0; otherwise the warm-up evaluates the
+// input (incl. due resamples) of EVERY env, as the reference's step_rom_idx does (rom_dynamics.py:577-580).
+template <int RN, int W>
+__global__ void __launch_bounds__(128) rom_reset_root_kernel(const __grid_constant__ B200RomParams p, const __grid_constant__ B200RomState s,
+                                                             const uint8_t* __restrict__ mask, const float* __restrict__ root, int stride,
+                                                             const float* __restrict__ any_reset, long long env_off) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (i >= p.num_envs) return;
+    if (any_reset && *any_reset == 0.0f) return;
+    const int w = p.window;
+    Gen<RN, W> g;
+    load_gen(s, i, w, g);
+    float pz[RN];
+#pragma unroll
+    for (int c = 0; c < RN; ++c) pz[c] = root[static_cast<size_t>(i) * stride + c];
+    traj_reset(p, g, pz, w, static_cast<uint64_t>(env_off + i), mask[i] != 0);
+    store_gen(s, i, w, g);
 }
 
 template <int RN, int W>
@@ -538,6 +573,21 @@ int b200gym_rom_reset(const B200RomParams* p, const B200RomState* s, const uint8
     if (p->window == 10 && p->dN == 1) rom_reset_kernel<2, 10><<<grid, 128, 0, st>>>(*p, *s, reset_mask, env_id_offset);
     else rom_reset_kernel<2, WMAXR><<<grid, 128, 0, st>>>(*p, *s, reset_mask, env_id_offset);
     B200_LAUNCH_CHECK("rom_reset");
+    return B200GYM_OK;
+}
+
+int b200gym_rom_reset_from_root(const B200RomParams* p, const B200RomState* s, const uint8_t* reset_mask, const float* root,
+                                int32_t root_stride, const float* any_reset, int64_t env_id_offset, void* stream) {
+    if (int rc = check_rom(p, s, "rom_reset_from_root", false)) return rc;
+    B200_REQUIRE(reset_mask && root && root_stride >= 2, B200GYM_EINVAL, "rom_reset_from_root: reset_mask / root missing");
+    B200_REQUIRE(p->rom_type == 0, B200GYM_EINVAL, "rom_reset_from_root: proj_z is implemented for SingleInt2D (first two root columns)");
+    const int grid = (p->num_envs + 127) / 128;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->window == 10 && p->dN == 1)
+        b200_launch_pdl(p->num_envs, rom_reset_root_kernel<2, 10>, dim3(grid), dim3(128), 0, st, *p, *s, reset_mask, root, root_stride, any_reset, env_id_offset);
+    else
+        b200_launch_pdl(p->num_envs, rom_reset_root_kernel<2, WMAXR>, dim3(grid), dim3(128), 0, st, *p, *s, reset_mask, root, root_stride, any_reset, env_id_offset);
+    B200_LAUNCH_CHECK("rom_reset_from_root");
     return B200GYM_OK;
 }
 

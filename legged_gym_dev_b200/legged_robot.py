@@ -331,11 +331,11 @@ class LeggedRobot:
 
 
 def cfg_num_commands(cfg):
-    return int(getattr(cfg.commands, "num_commands", 4))
+    return int(getattr(getattr(cfg, "commands", None), "num_commands", 4))
 
 
-class Anymal(LeggedRobot):
-    """anymal.py:46-80: adds the actuator-network torque path and its per-(env,dof) LSTM state."""
+class ActuatorNetMixin:
+    """anymal.py:46-80 / anymal_trajectory.py:46-80: the actuator-network torque path and its per-(env,dof) LSTM state."""
 
     def _has_actuator_state(self):
         return bool(self.params.use_actuator_network)
@@ -371,3 +371,7 @@ class Anymal(LeggedRobot):
         if rc:
             _lib.check(rc, "lstm_torques")
         return self.torques
+
+
+class Anymal(ActuatorNetMixin, LeggedRobot):
+    """legged_gym/envs/anymal_c/anymal.py:46-80."""

@@ -13,10 +13,16 @@ import numpy as np
 
 # Reward terms in the order the reference evaluates them: `class_to_dict` walks `dir()` (helpers.py:111-126),
 # i.e. alphabetical; `termination` is kept out of the loop and added after clipping (legged_robot.py:203-206).
-REWARD_TERMS = ("action_rate", "ang_vel_xy", "base_height", "collision", "dof_acc", "dof_pos_limits", "dof_vel",
-                "dof_vel_limits", "feet_air_time", "feet_contact_forces", "lin_vel_z", "orientation",
+# The table is the union of LeggedRobot's terms (legged_robot.py:918-1015) and LeggedRobotTrajectory's
+# (legged_robot_trajectory.py:1000-1110: + differential_error, tracking_rom; - tracking_lin_vel/ang_vel).
+REWARD_TERMS = ("action_rate", "ang_vel_xy", "base_height", "collision", "differential_error", "dof_acc", "dof_pos_limits",
+                "dof_vel", "dof_vel_limits", "feet_air_time", "feet_contact_forces", "lin_vel_z", "orientation",
                 "stand_still", "stumble", "torque_limits", "torques", "tracking_ang_vel", "tracking_lin_vel",
-                "termination")
+                "tracking_rom", "termination")
+TRAJ_ONLY_TERMS = ("differential_error", "tracking_rom")
+# _reward_tracking_lin_vel/_ang_vel do not exist in LeggedRobotTrajectory; _reward_stand_still reads self.commands,
+# which that class never creates (legged_robot_trajectory.py:621-622, :1090-1093)
+NON_TRAJ_TERMS = ("tracking_lin_vel", "tracking_ang_vel", "stand_still")
 TERM_ID = {n: i for i, n in enumerate(REWARD_TERMS)}
 NUM_TERMS = len(REWARD_TERMS)
 CONTROL_TYPES = {"P": 0, "V": 1, "T": 2}
@@ -115,6 +121,20 @@ class LeggedParams:
     base_init_state: List[float] = field(default_factory=lambda: [0, 0, 1.0, 0, 0, 0, 1.0, 0, 0, 0, 0, 0, 0])
     send_timeouts: bool = True
     seed: int = 0
+    # LeggedRobotTrajectory (legged_robot_trajectory.py)
+    traj_mode: bool = False
+    traj_n: int = 0
+    traj_horizon: int = 0
+    traj_scale: List[float] = field(default_factory=lambda: [1.0, 1.0, 1.0, 1.0])
+    traj_weight: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.0, 0.0])
+    diff_neg_slope: float = 1.0
+    diff_pos_slope: float = 4.0
+    time_between_pushes: List[float] = field(default_factory=lambda: [0.5, 10.0])
+
+    @property
+    def obs_width(self):
+        """Columns before the height block: 48, or 45 + N * rom.n in the trajectory env (legged_robot_trajectory.py:277-287)."""
+        return 45 + self.traj_horizon * self.traj_n if self.traj_mode else 48
 
     @property
     def num_height_points(self):
@@ -128,7 +148,7 @@ class LeggedParams:
 
 def flatten_legged_cfg(cfg, sim_dt, dof_names, num_envs=None, feet_indices=None, penalised_indices=None,
                        termination_indices=None, dof_pos_limits=None, dof_vel_limits=None, torque_limits=None,
-                       custom_origins=None, terrain_rows=0, terrain_cols=0, seed=0) -> LeggedParams:
+                       custom_origins=None, terrain_rows=0, terrain_cols=0, seed=0, trajectory=False) -> LeggedParams:
     """cfg: an (instantiated) LeggedRobotCfg-shaped object.  Mirrors _parse_cfg / _init_buffers /
     _prepare_reward_function / _get_noise_scale_vec of the reference (citations in the module docstring)."""
     p = LeggedParams()
@@ -181,27 +201,41 @@ def flatten_legged_cfg(cfg, sim_dt, dof_names, num_envs=None, feet_indices=None,
     p.noise_dof_pos = n.dof_pos * lvl * s.dof_pos
     p.noise_dof_vel = n.dof_vel * lvl * s.dof_vel
     p.noise_height = n.height_measurements * lvl * s.height_measurements
-    c = cfg.commands
-    p.heading_command = bool(c.heading_command)
-    p.resample_steps = int(c.resampling_time / p.dt)                  # :348
-    r = c.ranges
-    p.cmd_lin_vel_x, p.cmd_lin_vel_y = [float(v) for v in r.lin_vel_x], [float(v) for v in r.lin_vel_y]
-    p.cmd_ang_vel_yaw, p.cmd_heading = [float(v) for v in r.ang_vel_yaw], [float(v) for v in r.heading]
     d = cfg.domain_rand
     p.push_robots = bool(d.push_robots)
     p.push_time = int(np.ceil(d.push_interval_s / p.dt))              # :826
-    p.max_push_vel = float(getattr(d, "max_push_vel", getattr(d, "max_push_vel_xy", 1.0)))
+    if not trajectory:
+        c = cfg.commands
+        p.heading_command = bool(c.heading_command)
+        p.resample_steps = int(c.resampling_time / p.dt)                  # :348
+        r = c.ranges
+        p.cmd_lin_vel_x, p.cmd_lin_vel_y = [float(v) for v in r.lin_vel_x], [float(v) for v in r.lin_vel_y]
+        p.cmd_ang_vel_yaw, p.cmd_heading = [float(v) for v in r.ang_vel_yaw], [float(v) for v in r.heading]
+        p.max_push_vel = float(getattr(d, "max_push_vel", getattr(d, "max_push_vel_xy", 1.0)))
+    else:   # LeggedRobotTrajectoryCfg has no `commands`; pushes use max_push_vel_xy and per-env timers
+        p.traj_mode = True
+        p.heading_command, p.resample_steps = False, 1
+        p.max_push_vel = float(d.max_push_vel_xy)                      # legged_robot_trajectory.py:489
+        p.time_between_pushes = [float(v) for v in d.time_between_pushes]   # :85-88, :175-178
     rw = cfg.rewards
     scales = cfg_to_dict(rw.scales)
     p.reward_scales = [0.0] * NUM_TERMS
+    cls_name = "LeggedRobotTrajectory" if trajectory else "LeggedRobot"
     for name, v in scales.items():                                    # :610-615
-        if name not in TERM_ID:
+        missing = name not in TERM_ID or name in (NON_TRAJ_TERMS[:2] if trajectory else TRAJ_ONLY_TERMS)
+        if missing:
             if v != 0:
-                raise AttributeError(f"'LeggedRobot' object has no attribute '_reward_{name}'")
+                raise AttributeError(f"'{cls_name}' object has no attribute '_reward_{name}'")
             continue
+        if trajectory and name == "stand_still" and v != 0:
+            raise AttributeError(f"'{cls_name}' object has no attribute 'commands'")
         p.reward_scales[TERM_ID[name]] = float(v) * p.dt if v != 0 else 0.0
     p.only_positive_rewards = bool(rw.only_positive_rewards)
     p.tracking_sigma = float(rw.tracking_sigma)
+    if trajectory:
+        de = rw.differential_error
+        p.diff_neg_slope, p.diff_pos_slope = float(de.neg_slope), float(de.pos_slope)       # :1107-1108
+        p.traj_scale = [float(v) for v in s.trajectory] + [1.0] * (4 - len(s.trajectory))   # :626-630
     p.soft_dof_vel_limit, p.soft_torque_limit = float(rw.soft_dof_vel_limit), float(rw.soft_torque_limit)
     p.base_height_target, p.max_contact_force = float(rw.base_height_target), float(rw.max_contact_force)
     t = cfg.terrain
@@ -220,6 +254,6 @@ def flatten_legged_cfg(cfg, sim_dt, dof_names, num_envs=None, feet_indices=None,
     isl = cfg.init_state
     p.base_init_state = [float(v) for v in (list(isl.pos) + list(isl.rot) + list(isl.lin_vel) + list(isl.ang_vel))]
     p.send_timeouts = bool(cfg.env.send_timeouts)
-    if p.measure_heights and p.num_obs != 48 + p.num_height_points:
+    if not trajectory and p.measure_heights and p.num_obs != 48 + p.num_height_points:
         raise ValueError(f"num_observations {p.num_obs} != 48 + {p.num_height_points} height points")
     return p

@@ -66,6 +66,11 @@ def _register_defaults():
     from .legged_robot import Anymal
     task_registry.register("anymal_c_rough_b200", Anymal, configs.anymal_c_rough_cfg(), configs.anymal_c_rough_cfg_ppo())
     task_registry.register("anymal_c_flat_b200", Anymal, configs.anymal_c_flat_cfg(), configs.anymal_c_flat_cfg_ppo())
+    from .legged_robot_trajectory import AnymalTrajectory                # legged_gym/envs/__init__.py registrations
+    task_registry.register("anymal_c_rough_trajectory_b200", AnymalTrajectory, configs.anymal_c_rough_trajectory_cfg(),
+                           configs.anymal_c_rough_trajectory_cfg_ppo())
+    task_registry.register("anymal_c_flat_trajectory_b200", AnymalTrajectory, configs.anymal_c_flat_trajectory_cfg(),
+                           configs.anymal_c_flat_trajectory_cfg_ppo())
 
 
 _register_defaults()

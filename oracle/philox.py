@@ -77,6 +77,7 @@ SITE_RESET_XY = 5         # cols 0,1                                           (
 SITE_RESET_VEL = 6        # cols 0..5                                          (legged_robot.py:449)
 SITE_CMD_RESET = 7        # cols 0,1,2                                         (legged_robot.py:371-384 via :166)
 SITE_OBS_NOISE = 8        # cols 0..num_obs-1                                  (legged_robot.py:226)
+SITE_PUSH_TIMER = 9       # col 0: time_until_next_push redraw                  (legged_robot_trajectory.py:175-178)
 # ROM generator, event = per-env draw-event counter
 SITE_ROM_INIT = 16        # ramp_v_end at construction                         (rom_dynamics.py:495)
 SITE_ROM_ROOT = 17        # CustomSim.reset_idx root state                     (custom_sim.py:88-91)

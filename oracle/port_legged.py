@@ -20,9 +20,10 @@ import torch
 from . import philox as P
 from .isaacgym_restated import quat_apply, quat_rotate_inverse, normalize
 
-TERMS = ("action_rate", "ang_vel_xy", "base_height", "collision", "dof_acc", "dof_pos_limits", "dof_vel",
+# union of the LeggedRobot and LeggedRobotTrajectory terms, alphabetical, `termination` last (== params.REWARD_TERMS)
+TERMS = ("action_rate", "ang_vel_xy", "base_height", "collision", "differential_error", "dof_acc", "dof_pos_limits", "dof_vel",
          "dof_vel_limits", "feet_air_time", "feet_contact_forces", "lin_vel_z", "orientation", "stand_still",
-         "stumble", "torque_limits", "torques", "tracking_ang_vel", "tracking_lin_vel", "termination")
+         "stumble", "torque_limits", "torques", "tracking_ang_vel", "tracking_lin_vel", "tracking_rom", "termination")
 
 
 class LeggedPort:

@@ -226,7 +226,12 @@ class RomPort:
         p = self.p
         ev = self._events(idx)
         self.root_states[idx, :] = self._uniform(self.noise_lower, self.noise_upper, P.SITE_ROM_ROOT, idx, ev, self.model.n)
-        p_zx = self.rom.proj_z(self.root_states.clone())
+        self.reset_traj(idx, self.rom.proj_z(self.root_states.clone()))
+        return self.step(torch.zeros(self.N, self.model.m))
+
+    def reset_traj(self, idx, p_zx):
+        """reset_traj: custom_sim.py:80-85 == legged_robot_trajectory.py:248-253 (p_zx = proj_z of the root states)."""
+        p = self.p
         if p.randomize_rom_distance:
             ev2 = self._events(idx)
             m = self._u(P.SITE_ROM_DIST_MASK, idx, ev2, 1).squeeze(1) > p.zero_rom_dist_llh
@@ -238,7 +243,6 @@ class RomPort:
         elif self.rng == "philox":
             self._events(idx)     # the harness takes the event whether or not the branch draws
         self.gen_reset_idx(idx, p_zx)
-        return self.step(torch.zeros(self.N, self.model.m))
 
     def reset(self):
         return self.reset_idx(torch.arange(self.N))

@@ -212,6 +212,180 @@ def make_reference_anymal(task, num_envs, tape, seed=0, reward_scales=None, comm
     return env
 
 
+# --------------------------------------------------------------------------------------------
+# AnymalTrajectory / LeggedRobotTrajectory
+# --------------------------------------------------------------------------------------------
+TRAJECTORY_ALL_REWARD_SCALES = dict(   # every _reward_* of legged_robot_trajectory.py:1000-1110 except stand_still (reads self.commands)
+    action_rate=-0.01, ang_vel_xy=-0.05, base_height=-1.0, collision=-1.0, differential_error=2.0, dof_acc=-2.5e-7,
+    dof_pos_limits=-10.0, dof_vel=-1e-4, dof_vel_limits=-0.5, feet_air_time=1.0, feet_contact_forces=-0.01, lin_vel_z=-2.0,
+    orientation=-5.0, stumble=-0.3, termination=-3.0, torque_limits=-0.02, torques=-1e-5, tracking_rom=6.0)
+
+
+def complete_trajectory_cfg(cfg):
+    """The fork's anymal *_trajectory configs lack attributes LeggedRobotTrajectory reads (they live on in the hopper
+    configs, hopper_trajectory_config.py:113-260).  Filled in here — and identically in legged_gym_dev_b200/configs.py."""
+    cfg.rewards.tracking_sigma = 0.25                                  # read at legged_robot_trajectory.py:892
+    cfg.domain_rand.randomize_rom_distance = True                      # :250
+    cfg.domain_rand.max_rom_dist = [1.0, 1.0]                          # :887
+    cfg.domain_rand.zero_rom_distance_likelihood = 0.25                # :888
+    cfg.curriculum = SimpleNamespace(use_curriculum=False, curriculum_steps=[2500, 5000])   # :82, :414
+    tg = cfg.trajectory_generator
+    tg.weight_samp_cls = "UniformWeightSampler"                        # 'WeightSamplerSampleAndHold' does not exist
+    tg.dN = 1                                                          # :122 reads dN, the cfg defines DN
+    tg.prob_stationary = cfg.rom.prob_stationary                       # :121 reads it from the generator cfg
+    cfg.terrain.curriculum = False                                     # _update_terrain_curriculum needs self.commands (:508)
+    return cfg
+
+
+def make_reference_anymal_trajectory(task, num_envs, tape, seed=0, reward_scales=None, use_actuator_network=None,
+                                     heightfield=None, terrain_origins=None, episode_lengths=None,
+                                     time_until_next_push=None, overrides=None):
+    """The reference's AnymalTrajectory for `task` in {"anymal_c_flat_trajectory","anymal_c_rough_trajectory"}."""
+    ref = import_reference()
+    from legged_gym_dev_b200 import synthetic as S
+    envs = ref.envs
+    import legged_gym.envs.base.legged_robot_trajectory as ltmod
+    cfg = envs.AnymalCFlatTrajectoryCfg() if task == "anymal_c_flat_trajectory" else envs.AnymalCRoughTrajectoryCfg()
+    complete_trajectory_cfg(cfg)
+    cfg.env.num_envs = num_envs
+    if task != "anymal_c_flat_trajectory":
+        cfg.env.num_observations = 65 + 187
+    if reward_scales is not None:
+        for k, v in reward_scales.items():
+            setattr(cfg.rewards.scales, k, v)
+    if use_actuator_network is not None:
+        cfg.control.use_actuator_network = use_actuator_network
+    for path, v in (overrides or {}).items():
+        obj = cfg
+        parts = path.split(".")
+        for p in parts[:-1]:
+            obj = getattr(obj, p)
+        setattr(obj, parts[-1], v)
+
+    AT = envs.AnymalTrajectory
+    env = AT.__new__(AT)
+    env.cfg = cfg
+    env.sim_params = SimpleNamespace(dt=cfg.sim.dt, use_gpu_pipeline=False)
+    env.height_samples = None
+    env.debug_viz = False
+    env.init_done = False
+    env._parse_cfg(cfg)                                                   # reference code (:877-902)
+    env.device = "cpu"
+    env.headless = True
+    env.viewer = None
+    env.enable_viewer_sync = False
+    env.sim = None
+    env.num_envs, env.num_obs = cfg.env.num_envs, cfg.env.num_observations
+    env.num_privileged_obs, env.num_actions = cfg.env.num_privileged_obs, cfg.env.num_actions
+    env.obs_buf = torch.zeros(env.num_envs, env.num_obs, dtype=torch.float)
+    env.rew_buf = torch.zeros(env.num_envs, dtype=torch.float)
+    env.reset_buf = torch.ones(env.num_envs, dtype=torch.long)
+    env.episode_length_buf = torch.zeros(env.num_envs, dtype=torch.long)
+    env.time_out_buf = torch.zeros(env.num_envs, dtype=torch.bool)
+    env.privileged_obs_buf = None
+    env.extras = {}
+    env.up_axis_idx = 2
+    env.num_dof = env.num_dofs = S.NUM_DOF
+    env.num_bodies = S.NUM_BODIES
+    env.dof_names = list(S.DOF_NAMES)
+    env.feet_indices = torch.tensor(S.FEET_INDICES, dtype=torch.long)
+    env.penalised_contact_indices = torch.tensor(S.PENALISED_INDICES, dtype=torch.long)
+    env.termination_contact_indices = torch.tensor(S.TERMINATION_INDICES, dtype=torch.long)
+    lim = synthetic_dof_limits()
+    env.dof_pos_limits = lim["dof_pos_limits"].clone()
+    env.dof_vel_limits = lim["dof_vel_limits"].clone()
+    env.torque_limits = lim["torque_limits"].clone()
+    isl = cfg.init_state
+    env.base_init_state = torch.tensor(isl.pos + isl.rot + isl.lin_vel + isl.ang_vel, dtype=torch.float)
+    if cfg.terrain.mesh_type in ("heightfield", "trimesh"):
+        env.terrain = SimpleNamespace(cfg=cfg.terrain, env_length=cfg.terrain.terrain_length,
+                                      env_width=cfg.terrain.terrain_width, env_origins=terrain_origins.numpy())
+        env.height_samples = heightfield
+        state = torch.get_rng_state()
+        torch.manual_seed(seed + 31)
+        env._get_env_origins()                                            # reference code
+        torch.set_rng_state(state)
+    else:
+        env._get_env_origins()
+    # --- the tail of LeggedRobotTrajectory.__init__ (:72-88), in its order ---
+    env.max_rom_distance = torch.tensor(env.nominal_max_rom_distance)
+    env.zero_rom_dist_llh = env.nominal_zero_rom_distance_likelihood
+    # (UniformWeightSampler.sample hard-codes device='cuda' in torch.rand; under the shim that call returns CPU numbers)
+    for name in ("UniformWeightSamplerNoRamp", "UniformWeightSamplerNoExtreme"):
+        base = getattr(ref.dtl_utils, name)     # default device='cuda' and the env passes no args (:109)
+        cpu_cls = type(name, (base,), {"__init__": (lambda b: lambda self, dim=4, seed=42, device="cpu":
+                                                    b.__init__(self, dim=dim, seed=seed, device="cpu"))(base)})
+        setattr(ltmod, name, cpu_cls)
+    _install_rom_wrappers(ref)
+    holder = SimpleNamespace(seed=int(cfg.trajectory_generator.seed), ctr=np.zeros(num_envs, dtype=np.int64))
+    env._init_rom()                                                       # reference code
+    ref.rom_dynamics.TrajectoryGenerator._pending_holder = holder
+    try:
+        env._init_trajectory_generator()                                  # reference code
+    finally:
+        ref.rom_dynamics.TrajectoryGenerator._pending_holder = None
+    env.traj_gen._shim = holder
+    env._traj_shim = holder
+    root = tape.root[0].clone()
+    dof = tape.dof[0, 0].clone()
+    contact = tape.contact[0].reshape(num_envs * S.NUM_BODIES, 3).clone()
+    handed = iter([root, dof, contact])
+    ltmod.gymtorch.wrap_tensor = lambda _t: next(handed)
+    env.gym = MagicMock()
+    env._init_buffers()                                                   # reference code
+    env._prepare_reward_function()                                        # reference code
+    env.init_done = True
+    if cfg.control.use_actuator_network:
+        path = cfg.control.actuator_net_file.format(LEGGED_GYM_ROOT_DIR=REF_ROOT)
+        env.actuator_network = torch.jit.load(path)
+    if time_until_next_push is not None:                                  # the torch_rand_float draw of :85-88 as an input
+        env.time_until_next_push = time_until_next_push.clone().reshape(num_envs, 1)
+    env.gym = _ReplayGym(env, tape)
+    if episode_lengths is not None:
+        env.episode_length_buf[:] = episode_lengths
+    env._shim_seed = seed
+    _install_trajectory_wrappers(ref, ltmod)
+    return env
+
+
+def _install_trajectory_wrappers(ref, ltmod):
+    LT = ltmod.LeggedRobotTrajectory
+    rng_shim.install()
+    all_ids = lambda s: np.arange(s.num_envs)
+    _wrap(LT, "_push_robots", lambda s, push_idx: (push_idx.nonzero().flatten(), s.common_step_counter, [(P.SITE_PUSH, 0)]))
+    _wrap(LT, "_reset_dofs", lambda s, env_ids: (env_ids, s.common_step_counter, [(P.SITE_RESET_DOF, 0)]))
+    _wrap(LT, "_reset_root_states",
+          lambda s, env_ids: (env_ids, s.common_step_counter,
+                              [(P.SITE_RESET_XY, 0), (P.SITE_RESET_VEL, 0)] if s.custom_origins
+                              else [(P.SITE_RESET_VEL, 0)]))
+    _wrap(LT, "compute_observations", lambda s: (all_ids(s), s.common_step_counter, [(P.SITE_OBS_NOISE, 0)]))
+
+    # the push-timer redraw is inline in post_physics_step (:175-178): an outer context resolved at draw time
+    def pps_ctx(self):
+        ids = lambda call, hist: (self.time_until_next_push <= 0).reshape(-1).nonzero().flatten().numpy()
+        ev = lambda call, hist: self.common_step_counter
+        return (ids, ev, [(P.SITE_PUSH_TIMER, 0)])
+    _wrap(LT, "post_physics_step", pps_ctx)
+
+    if (LT, "reset_traj") not in _wrapped:
+        _wrapped.add((LT, "reset_traj"))
+        orig = LT.reset_traj
+
+        def reset_traj(self, env_ids):
+            holder = getattr(self, "_traj_shim", None)
+            if holder is None:
+                return orig(self, env_ids)
+            ids = env_ids.detach().cpu().numpy()
+            ev = holder.ctr[ids].copy()
+            holder.ctr[ids] += 1
+            llh = self.zero_rom_dist_llh
+            lazy_ids = lambda call, hist: ids if call == 0 else ids[(hist[0] > llh).numpy().reshape(-1)]
+            lazy_ev = lambda call, hist: ev if call == 0 else ev[(hist[0] > llh).numpy().reshape(-1)]
+            with rng_shim.draws(holder.seed, lazy_ids, lazy_ev, [(P.SITE_ROM_DIST_MASK, 0), (P.SITE_ROM_DIST, 0)]):
+                return orig(self, env_ids)
+        LT.reset_traj = reset_traj
+
+
 def synthetic_dof_limits():
     """The URDF carries effort/velocity limits (80 N m, 20 rad/s: anymal_c.urdf:540) but no position
     limits; synthetic +-(HAA 0.72, HFE/KFE 9.42*0.1...) style limits make the limit rewards non-trivial."""

@@ -26,7 +26,18 @@ CASES = {
     "rough_lstm_allterms": ("anymal_c_rough", ALL_REWARD_SCALES, configs.UPSTREAM_COMMAND_RANGES, True,
                             {"rewards.only_positive_rewards": False, "domain_rand.push_interval_s": 0.1}),
     "rough_pd_shipped": ("anymal_c_rough", None, None, False, {}),
+    # AnymalTrajectory (legged_robot_trajectory.py); frequent per-env pushes so the timers fire in a short test
+    "traj_flat_allterms": ("anymal_c_flat_trajectory", configs.TRAJECTORY_ALL_REWARD_SCALES, None, False,
+                           {"domain_rand.time_between_pushes": [0.05, 0.3]}),
+    "traj_flat_lstm_shipped": ("anymal_c_flat_trajectory", None, None, True, {}),
+    "traj_flat_nonoise_norand": ("anymal_c_flat_trajectory", configs.TRAJECTORY_ALL_REWARD_SCALES, None, False,
+                                 {"noise.add_noise": False, "domain_rand.randomize_rom_distance": False,
+                                  "trajectory_generator.weight_samp_cls": "UniformWeightSamplerNoRamp",
+                                  "trajectory_generator.t_low": 0.1, "trajectory_generator.t_high": 0.3}),
+    "traj_rough_lstm_allterms": ("anymal_c_rough_trajectory", configs.TRAJECTORY_ALL_REWARD_SCALES, None, True,
+                                 {"domain_rand.time_between_pushes": [0.05, 0.3]}),
 }
+TRAJ_TASKS = ("anymal_c_flat_trajectory", "anymal_c_rough_trajectory")
 
 
 def dof_limits():
@@ -53,12 +64,23 @@ def apply_overrides(cfg, reward_scales, command_ranges, lstm, overrides):
 def build_case(name, num_envs, frames=8, seed=5, tape_seed=1, base_contact_prob=0.02):
     """Returns cfg + all inputs (CPU tensors) for the case."""
     task, rs, cr, lstm, over = CASES[name]
-    rough = task == "anymal_c_rough"
-    cfg = configs.anymal_c_rough_cfg() if rough else configs.anymal_c_flat_cfg()
+    traj = task in TRAJ_TASKS
+    rough = task in ("anymal_c_rough", "anymal_c_rough_trajectory")
+    if traj:
+        cfg = configs.anymal_c_rough_trajectory_cfg() if rough else configs.anymal_c_flat_trajectory_cfg()
+    else:
+        cfg = configs.anymal_c_rough_cfg() if rough else configs.anymal_c_flat_cfg()
     cfg = apply_overrides(cfg, rs, cr, lstm, over)
     cfg.env.num_envs = num_envs
     tape = S.make_state_tape(num_envs, frames=frames, seed=tape_seed, rough=rough, base_contact_prob=base_contact_prob)
     ep = S.make_episode_lengths(num_envs, seed=tape_seed)
+    tpush = None
+    if traj:
+        keep = ep[::8].clone()
+        ep[:] = 1001          # most envs time out on the first step: their generators are reset next to the robots
+        ep[::8] = keep
+        g = torch.Generator().manual_seed(tape_seed + 7)
+        tpush = 0.4 * torch.rand(num_envs, 1, generator=g)   # stands in for the construction-time draw (legged_robot_trajectory.py:85-88)
     terrain = None
     if rough:
         hf = S.make_heightfield(seed=tape_seed)
@@ -68,8 +90,18 @@ def build_case(name, num_envs, frames=8, seed=5, tape_seed=1, base_contact_prob=
         types = torch.div(torch.arange(num_envs), (num_envs / cfg.terrain.num_cols), rounding_mode="floor").to(torch.long)
         terrain = dict(height_samples=hf, terrain_origins=to, terrain_levels=levels, terrain_types=types,
                        env_origins=to[levels, types].clone())
+    if traj:   # keep the replayed robots near their env origins, where the generators start (tracking errors of O(0.3 m))
+        if terrain is not None:
+            o = terrain["env_origins"]
+        else:
+            cols = np.floor(np.sqrt(num_envs))
+            rows = np.ceil(num_envs / cols)
+            xx, yy = torch.meshgrid(torch.arange(rows), torch.arange(cols), indexing="ij")
+            o = torch.stack([cfg.env.env_spacing * xx.flatten()[:num_envs], cfg.env.env_spacing * yy.flatten()[:num_envs]], dim=1)
+        g = torch.Generator().manual_seed(tape_seed + 8)
+        tape.root[:, :, 0:2] = o[None, :, :2].float() + 0.3 * torch.randn(tape.root.shape[0], num_envs, 2, generator=g)
     return SimpleNamespace(name=name, task=task, rough=rough, lstm=lstm, cfg=cfg, tape=tape, ep=ep, terrain=terrain,
-                           seed=seed, num_envs=num_envs, limits=dof_limits())
+                           seed=seed, num_envs=num_envs, limits=dof_limits(), traj=traj, tpush=tpush)
 
 
 def make_params(case):
@@ -78,12 +110,25 @@ def make_params(case):
                               dof_pos_limits=lim["dof_pos_limits"].tolist(), dof_vel_limits=lim["dof_vel_limits"].tolist(),
                               torque_limits=lim["torque_limits"].tolist(),
                               terrain_rows=t["height_samples"].shape[0] if t else 0,
-                              terrain_cols=t["height_samples"].shape[1] if t else 0, seed=case.seed)
+                              terrain_cols=t["height_samples"].shape[1] if t else 0, seed=case.seed, trajectory=case.traj)
+
+
+def generator_cfg(cfg):
+    """trajectory_generator / rom / domain_rand numbers of a trajectory cfg, as oracle.port_legged_traj wants them."""
+    tg, rom, d = cfg.trajectory_generator, cfg.rom, cfg.domain_rand
+    return dict(rom_dt=rom.dt, vel_max_rom=rom.v_max[0], N=tg.N, dN=tg.dN, t_low=tg.t_low, t_high=tg.t_high, freq_low=tg.freq_low,
+                freq_high=tg.freq_high, prob_stationary=tg.prob_stationary, weight_sampler=tg.weight_samp_cls, seed=tg.seed,
+                randomize_rom_distance=d.randomize_rom_distance, max_rom_distance=d.max_rom_dist,
+                zero_rom_dist_llh=d.zero_rom_distance_likelihood)
 
 
 def make_port(case, rng="philox", env_id_offset=0):
     from oracle.port_legged import LeggedPort, TapePhysics
     p = make_params(case)
+    if case.traj:
+        p.traj_n, p.traj_horizon = 2, case.cfg.trajectory_generator.N
+        rw = case.cfg.rewards.reward_weighting
+        p.traj_weight = [float(rw.position), float(rw.position), 0.0, 0.0]      # SingleInt2D.get_weighting_vector
     t = case.terrain or {}
     w = None
     if case.lstm:
@@ -100,6 +145,10 @@ def make_port(case, rng="philox", env_id_offset=0):
         origins = torch.zeros(N, 3)
         origins[:, 0] = case.cfg.env.env_spacing * xx.flatten()[:N]
         origins[:, 1] = case.cfg.env.env_spacing * yy.flatten()[:N]
+    kw = {}
+    if case.traj:
+        from oracle.port_legged_traj import LeggedTrajPort
+        LeggedPort = lambda p_, r, d, c, **k: LeggedTrajPort(p_, generator_cfg(case.cfg), r, d, c, case.tpush, **k)   # noqa: F811
     port = LeggedPort(p, case.tape.root[0].clone(), case.tape.dof[0, 0].clone(), case.tape.contact[0].clone(),
                       env_origins=origins, height_samples=t.get("height_samples"),
                       terrain_levels=clone(t.get("terrain_levels")), terrain_types=clone(t.get("terrain_types")),
@@ -111,22 +160,43 @@ def make_port(case, rng="philox", env_id_offset=0):
 def make_fused(case, device="cuda", copy=True, env_id_offset=0):
     from legged_gym_dev_b200.legged_robot import Anymal
     from legged_gym_dev_b200.physics import ReplayPhysics
+    if case.traj:
+        from legged_gym_dev_b200.legged_robot_trajectory import AnymalTrajectory as Anymal   # noqa: F811
     phys = ReplayPhysics(case.tape, device=device, copy=copy)
     lim = case.limits
     asset = dict(dof_pos_limits=lim["dof_pos_limits"], dof_vel_limits=lim["dof_vel_limits"], torque_limits=lim["torque_limits"])
     env = Anymal(case.cfg, SimpleNamespace(dt=case.cfg.sim.dt), None, device, True, physics=phys, asset=asset,
                  seed=case.seed, terrain=case.terrain, env_id_offset=env_id_offset)
     env.episode_length_buf.copy_(case.ep.to(device))
+    if case.traj:
+        env.time_until_next_push.copy_(case.tpush.to(device))
     return env
 
 
 # quantities compared after every step: name -> (getter(port), getter(fused), kind, scale)
+def _gen_port(d, g):
+    d.update(gen_trajectory=g.traj, gen_v_trajectory=g.v_traj, gen_t=g.t, gen_k=g.k, gen_t_final=g.t_final, gen_weights=g.weights,
+             gen_stationary=g.stationary, gen_ramp_v_end=g.ramp_v_end, gen_sin_freq=g.sin_freq,
+             gen_ctr=torch.from_numpy(g.ctr.astype("int64")))
+
+
+def _gen_fused(d, g):
+    d.update(gen_trajectory=g.trajectory, gen_v_trajectory=g.v_trajectory, gen_t=g.t, gen_k=g.k, gen_t_final=g.t_final,
+             gen_weights=g.weights, gen_stationary=g.stationary_inds, gen_ramp_v_end=g.ramp_v_end, gen_sin_freq=g.sin_freq,
+             gen_ctr=g.rng_ctr.long())
+
+
 def snapshot_port(port):
     d = dict(obs=port.obs_buf, rew=port.rew_buf, reset=port.reset_buf, time_out=port.time_out_buf, torques=port.torques,
-             commands=port.commands, ep_len=port.episode_length_buf, feet_air_time=port.feet_air_time,
+             ep_len=port.episode_length_buf, feet_air_time=port.feet_air_time,
              last_contacts=port.last_contacts, root=port.root_states, dof=port.dof_state, last_actions=port.last_actions,
              last_dof_vel=port.last_dof_vel, last_root_vel=port.last_root_vel, base_lin_vel=port.base_lin_vel,
              base_ang_vel=port.base_ang_vel, projected_gravity=port.projected_gravity)
+    if hasattr(port, "gen"):
+        d.update(trajectory=port.trajectory, prev_error=port.prev_error, time_until_next_push=port.time_until_next_push)
+        _gen_port(d, port.gen)
+    else:
+        d["commands"] = port.commands
     for k, v in port.episode_sums.items():
         d["sum_" + k] = v
     if port.p.measure_heights:
@@ -143,10 +213,15 @@ def snapshot_port(port):
 
 def snapshot_fused(env):
     d = dict(obs=env.obs_buf, rew=env.rew_buf, reset=env.reset_buf, time_out=env.time_out_buf, torques=env.torques,
-             commands=env.commands, ep_len=env.episode_length_buf, feet_air_time=env.feet_air_time,
+             ep_len=env.episode_length_buf, feet_air_time=env.feet_air_time,
              last_contacts=env.last_contacts, root=env.root_states, dof=env.dof_state, last_actions=env.last_actions,
              last_dof_vel=env.last_dof_vel, last_root_vel=env.last_root_vel, base_lin_vel=env.base_lin_vel,
              base_ang_vel=env.base_ang_vel, projected_gravity=env.projected_gravity)
+    if hasattr(env, "traj_gen"):
+        d.update(trajectory=env.trajectory, prev_error=env.prev_error, time_until_next_push=env.time_until_next_push)
+        _gen_fused(d, env.traj_gen)
+    else:
+        d["commands"] = env.commands
     for k, v in env.episode_sums.items():
         d["sum_" + k] = v
     if env.params.measure_heights:
@@ -161,7 +236,7 @@ def snapshot_fused(env):
     return {k: v.detach().cpu().clone() for k, v in d.items()}
 
 
-EXACT = {"reset", "time_out", "ep_len", "last_contacts", "terrain_levels"}
+EXACT = {"reset", "time_out", "ep_len", "last_contacts", "terrain_levels", "gen_k", "gen_stationary", "gen_ctr"}
 SCALES = {"torques": 80.0, "heights": 1.0}
 
 

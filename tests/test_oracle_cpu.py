@@ -166,3 +166,72 @@ def test_rom_port_tracks_unmodified_reference(over):
         assert_close(port.t_final, tg.t_final, 1.0, tag + "t_final")
         assert_close(port.trajectory, env.trajectory, 1.0, tag + "CustomSim.trajectory")
     assert np.array_equal(port.ctr, env._shim.ctr)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("name", ["traj_flat_allterms", "traj_flat_lstm_shipped", "traj_flat_nonoise_norand", "traj_rough_lstm_allterms"])
+def test_trajectory_port_tracks_unmodified_reference(name):
+    """oracle/port_legged_traj.py vs the reference's own AnymalTrajectory / LeggedRobotTrajectory
+    (legged_robot_trajectory.py), every step, same Philox stream (env draws keyed by step, generator draws by event counter)."""
+    from oracle import ref_harness as H
+    N, steps = 96, 40
+    case = LC.build_case(name, N)
+    task, rs, _, lstm, over = LC.CASES[name]
+    env = H.make_reference_anymal_trajectory(task, N, case.tape, seed=case.seed, reward_scales=rs, use_actuator_network=lstm,
+                                             heightfield=case.terrain["height_samples"] if case.rough else None,
+                                             terrain_origins=case.terrain["terrain_origins"] if case.rough else None,
+                                             episode_lengths=case.ep, time_until_next_push=case.tpush, overrides=over)
+    if case.rough:
+        env.env_origins[:] = case.terrain["env_origins"]
+    port, phys = LC.make_port(case)
+    assert_exact(port.gen.ramp_v_end, env.traj_gen.ramp_v_end, "ramp_v_end at construction")
+    assert_close(port.noise_scale_vec, env.noise_scale_vec, 1.0, "noise_scale_vec")
+    assert_close(port.reward_weighting, env.reward_weighting, 1.0, "reward_weighting")
+    assert sorted(port.episode_sums) == sorted(env.episode_sums)
+    # a never-reset generator divides 0/0 (rom_dynamics.py:552 with t_final == ramp_t_start == 0): start, as reset() does, from
+    # generators reset at the robots' positions
+    env.reset_traj(torch.arange(N))
+    port.gen.reset_traj(torch.arange(N), port.proj_z())
+    resets = pushes = 0
+    for s in range(steps):
+        a = case.tape.actions[s % case.tape.frames] * (150.0 if s == 3 else 1.0)
+        t_before = env.time_until_next_push.clone()
+        o1, _, r1, d1, x1 = env.step(a.clone())
+        o2, _, r2, d2, x2 = port.step(a.clone(), phys)
+        resets += int(d1.sum())
+        pushes += int((t_before - 0.02 <= 0).sum())
+        tag = f"{name} step {s}: "
+        tg, g = env.traj_gen, port.gen
+        assert_exact(d2, d1, tag + "reset")
+        assert_exact(port.time_out_buf, env.time_out_buf, tag + "time_out")
+        assert_exact(port.episode_length_buf, env.episode_length_buf, tag + "ep_len")
+        assert_exact(port.last_contacts, env.last_contacts, tag + "last_contacts")
+        assert_exact(g.k, tg.k, tag + "gen k")
+        assert_exact(g.t, tg.t, tag + "gen t")
+        assert_exact(g.stationary, tg.stationary_inds, tag + "gen stationary")
+        assert_close(o2, o1, 1.0, tag + "obs")
+        assert_close(r2, r1, 1.0, tag + "rew")
+        assert_close(port.torques, env.torques, 80.0, tag + "torques")
+        assert_close(port.root_states, env.root_states, 1.0, tag + "root")
+        assert_close(port.dof_state, env.dof_state, 1.0, tag + "dof")
+        assert_close(port.feet_air_time, env.feet_air_time, 1.0, tag + "feet_air_time")
+        assert_close(port.trajectory, env.trajectory, 1.0, tag + "trajectory")
+        assert_close(port.prev_error, env.prev_error, 1.0, tag + "prev_error")
+        assert_close(port.time_until_next_push, env.time_until_next_push, 1.0, tag + "time_until_next_push")
+        assert_close(g.traj, tg.trajectory, 1.0, tag + "gen trajectory")
+        assert_close(g.v_traj, tg.v_trajectory, 1.0, tag + "gen v_trajectory")
+        assert_close(g.weights, tg.weights, 1.0, tag + "gen weights")
+        assert_close(g.t_final, tg.t_final, 1.0, tag + "gen t_final")
+        for k in env.episode_sums:
+            assert_close(port.episode_sums[k], env.episode_sums[k], 1.0, tag + "sum_" + k)
+        if "episode" in x1:
+            assert list(x1["episode"]) == list(x2["episode"])
+            for k in x1["episode"]:
+                assert_close(x2["episode"][k], x1["episode"][k], 1.0, tag + "extras " + k)
+        if case.rough:
+            assert_exact(port.measured_heights, env.measured_heights, tag + "heights")
+        if lstm:
+            assert_close(port.sea_hidden_state, env.sea_hidden_state, 1.0, tag + "h")
+            assert_close(port.sea_cell_state, env.sea_cell_state, 1.0, tag + "c")
+    assert np.array_equal(port.gen.ctr, env._traj_shim.ctr)
+    assert resets > N // 2 and pushes > 0
