@@ -251,6 +251,16 @@ def compare_snapshots(got, want, tag=""):
         g = got[k]
         if k in EXACT:
             assert_exact(g.to(w.dtype) if g.dtype != w.dtype else g, w, f"{tag}{k}")
+        elif k == "obs" and "trajectory" in want:
+            # columns 9..28 are (trajectory - root_xy) * scale (legged_robot_trajectory.py:277-283): a difference of two positions
+            # of O(|origin|) metres.  The 1e-5 contract holds for the operands (trajectory is compared on its own below), so
+            # the difference is compared at the operands' magnitude; every other column at S = 1.
+            tw = want["trajectory"].shape[1] * want["trajectory"].shape[2]
+            mag = float(want["trajectory"].abs().max()) + 1.0
+            cols = torch.ones(w.shape[1], dtype=torch.bool)
+            cols[9:9 + tw] = False
+            worst[k] = assert_close(g[:, cols], w[:, cols].to(g.dtype), 1.0, f"{tag}{k}")
+            worst[k + "_traj"] = assert_close(g[:, ~cols], w[:, ~cols].to(g.dtype), mag, f"{tag}{k}[trajectory block]")
         elif k.startswith("extras_"):
             # extras only change on steps with a reset; the port keeps stale values too
             worst[k] = assert_close(g, w, 1.0, f"{tag}{k}")

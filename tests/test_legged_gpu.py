@@ -15,6 +15,9 @@ def _run(name, num_envs, steps, frames=8, big_action_step=3):
     case = LC.build_case(name, num_envs, frames=frames)
     port, phys = LC.make_port(case)
     env = LC.make_fused(case)
+    if case.traj:   # as reset() does: generators reset at the robots' positions (a never-reset generator divides 0/0 in the reference)
+        port.gen.reset_traj(torch.arange(num_envs), port.proj_z())
+        env.reset_traj(torch.arange(num_envs, device="cuda"))
     worst = {}
     resets = 0
     for s in range(steps):
@@ -40,6 +43,8 @@ def test_ragged_sizes(num_envs):
     """Tail tiles (num_envs not a multiple of the 64-env tile) take the non-TMA path."""
     _run("flat_allterms_v", num_envs, 12)
     _run("rough_lstm_allterms", num_envs, 6)
+    _run("traj_flat_allterms", num_envs, 8)
+    _run("traj_rough_lstm_allterms", num_envs, 6)
 
 
 def test_cfg2_size_4096():
