@@ -29,32 +29,54 @@ def legged_golden(name, num_envs=32, frames=4, steps=8):
         case.terrain["height_samples"] = hf
         case.tape.root[..., 0] = case.tape.root[..., 0] / 80.0 * 20.0 - 26.0
         case.tape.root[..., 1] = case.tape.root[..., 1] / 160.0 * 30.0 - 26.0
-    env = H.make_reference_anymal(task, num_envs, case.tape, seed=case.seed, reward_scales=rs, command_ranges=cr,
-                                  use_actuator_network=lstm, heightfield=case.terrain["height_samples"] if case.rough else None,
-                                  terrain_origins=case.terrain["terrain_origins"] if case.rough else None,
-                                  episode_lengths=case.ep, overrides=over)
+        if case.traj:   # robots stay next to their origins: move the origins the same way
+            case.terrain["env_origins"][:, 0] = case.terrain["env_origins"][:, 0] / 80.0 * 20.0 - 26.0
+            case.terrain["env_origins"][:, 1] = case.terrain["env_origins"][:, 1] / 160.0 * 30.0 - 26.0
+    if case.traj:
+        env = H.make_reference_anymal_trajectory(task, num_envs, case.tape, seed=case.seed, reward_scales=rs, use_actuator_network=lstm,
+                                                 heightfield=case.terrain["height_samples"] if case.rough else None,
+                                                 terrain_origins=case.terrain["terrain_origins"] if case.rough else None,
+                                                 episode_lengths=case.ep, time_until_next_push=case.tpush, overrides=over)
+    else:
+        env = H.make_reference_anymal(task, num_envs, case.tape, seed=case.seed, reward_scales=rs, command_ranges=cr,
+                                      use_actuator_network=lstm, heightfield=case.terrain["height_samples"] if case.rough else None,
+                                      terrain_origins=case.terrain["terrain_origins"] if case.rough else None,
+                                      episode_lengths=case.ep, overrides=over)
     if case.rough:
-        env.terrain_levels[:] = case.terrain["terrain_levels"]
-        env.terrain_types[:] = case.terrain["terrain_types"]
+        if not case.traj:
+            env.terrain_levels[:] = case.terrain["terrain_levels"]
+            env.terrain_types[:] = case.terrain["terrain_types"]
         env.env_origins[:] = case.terrain["env_origins"]
+    if case.traj:
+        env.reset_traj(torch.arange(num_envs))     # as reset() does (see tests/test_oracle_cpu.py)
     out = dict(tape_root=case.tape.root.numpy(), tape_dof=case.tape.dof.numpy(), tape_contact=case.tape.contact.numpy(),
                tape_actions=case.tape.actions.numpy(), ep=case.ep.numpy(), seed=np.int64(case.seed),
                num_envs=np.int64(num_envs), frames=np.int64(frames), steps=np.int64(steps))
     if case.rough:
         for k, v in case.terrain.items():
             out["terrain_" + k] = v.numpy()
+    if case.traj:
+        out["tpush"] = case.tpush.numpy()
     for s in range(steps):
         a = case.tape.actions[s % frames] * (150.0 if s == 3 else 1.0)
         env.step(a.clone())
         snap = dict(obs=env.obs_buf, rew=env.rew_buf, reset=env.reset_buf, time_out=env.time_out_buf, torques=env.torques,
-                    commands=env.commands, ep_len=env.episode_length_buf, feet_air_time=env.feet_air_time,
+                    ep_len=env.episode_length_buf, feet_air_time=env.feet_air_time,
                     last_contacts=env.last_contacts, root=env.root_states, dof=env.dof_state,
                     last_dof_vel=env.last_dof_vel, last_root_vel=env.last_root_vel, base_lin_vel=env.base_lin_vel)
+        if case.traj:
+            tg = env.traj_gen
+            snap.update(trajectory=env.trajectory, prev_error=env.prev_error, time_until_next_push=env.time_until_next_push,
+                        gen_trajectory=tg.trajectory, gen_v_trajectory=tg.v_trajectory, gen_t=tg.t, gen_k=tg.k,
+                        gen_t_final=tg.t_final, gen_weights=tg.weights, gen_stationary=tg.stationary_inds)
+        else:
+            snap["commands"] = env.commands
         for k, v in env.episode_sums.items():
             snap["sum_" + k] = v
         if case.rough:
             snap["heights"] = env.measured_heights
-            snap["terrain_levels"] = env.terrain_levels
+            if not case.traj:
+                snap["terrain_levels"] = env.terrain_levels
         if lstm:
             snap["lstm_h"], snap["lstm_c"] = env.sea_hidden_state, env.sea_cell_state
         for k, v in env.extras.get("episode", {}).items():
@@ -69,8 +91,13 @@ def legged_golden(name, num_envs=32, frames=4, steps=8):
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    for name in ("flat_pd_upstream", "flat_lstm_shipped", "flat_allterms_v", "rough_lstm_allterms"):
-        legged_golden(name)
+    only = sys.argv[1:]
+    for name in ("flat_pd_upstream", "flat_lstm_shipped", "flat_allterms_v", "rough_lstm_allterms",
+                 "traj_flat_allterms", "traj_flat_lstm_shipped", "traj_rough_lstm_allterms"):
+        if not only or name in only:
+            legged_golden(name, steps=12 if name.startswith("traj") else 8)
+    if only:
+        return
     try:
         from oracle.make_golden_rom import main as rom_main
         rom_main()

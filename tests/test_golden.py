@@ -24,6 +24,8 @@ def _load_case(name):
     case.tape.contact = torch.from_numpy(g["tape_contact"])
     case.tape.actions = torch.from_numpy(g["tape_actions"])
     case.ep = torch.from_numpy(g["ep"])
+    if case.traj:
+        case.tpush = torch.from_numpy(g["tpush"])
     if case.rough:
         case.terrain = {k[len("terrain_"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("terrain_")}
     return case, g
@@ -37,6 +39,9 @@ def _check(snap, g, s, tag):
         got = snap[k]
         if k in LC.EXACT:
             assert_exact(got.to(want.dtype), want, f"{tag}{k}")
+        elif k == "obs" and "trajectory" in snap:     # the trajectory block is a difference of positions: see LC.compare_snapshots
+            LC.compare_snapshots(dict(obs=got, trajectory=snap["trajectory"]),
+                                 dict(obs=want, trajectory=torch.from_numpy(g[f"s{s}_trajectory"])), tag)
         else:
             assert_close(got.reshape(want.shape), want, LC.SCALES.get(k, 1.0), f"{tag}{k}")
 
@@ -45,6 +50,8 @@ def _check(snap, g, s, tag):
 def test_port_matches_reference_golden(name):
     case, g = _load_case(name)
     port, phys = LC.make_port(case)
+    if case.traj:
+        port.gen.reset_traj(torch.arange(case.num_envs), port.proj_z())
     for s in range(int(g["steps"])):
         a = case.tape.actions[s % case.tape.frames] * (150.0 if s == 3 else 1.0)
         port.step(a.clone(), phys)
@@ -56,6 +63,8 @@ def test_port_matches_reference_golden(name):
 def test_fused_matches_reference_golden(name):
     case, g = _load_case(name)
     env = LC.make_fused(case)
+    if case.traj:
+        env.reset_traj(torch.arange(case.num_envs, device="cuda"))
     for s in range(int(g["steps"])):
         a = case.tape.actions[s % case.tape.frames] * (150.0 if s == 3 else 1.0)
         env.step(a.cuda())

@@ -239,3 +239,44 @@ def test_tensor_core_lstm_variant_meets_the_torque_contract():
             LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"tc lstm step {s}: ")
     finally:
         L.b200gym_debug_set_lstm_variant(0)
+
+
+def test_trajectory_env_reset_then_steps_are_finite():
+    """AnymalTrajectory.reset() (BaseTask.reset: reset all, one zero-action step) followed by steps never produces NaNs — the
+    generators are reset before the first generator step (a never-reset generator evaluates 0/0, rom_dynamics.py:552)."""
+    case = LC.build_case("traj_flat_allterms", 512)
+    env = LC.make_fused(case)
+    obs, _ = env.reset()
+    assert torch.isfinite(obs).all() and bool(env.reset_buf.all())
+    for s in range(12):
+        obs, _, rew, dones, extras = env.step(case.tape.actions[s % 8].cuda())
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert torch.isfinite(env.prev_error).all() and torch.isfinite(env.trajectory).all()
+    assert float(env.traj_gen.k.min()) >= 0
+
+
+def test_trajectory_env_shard_invariance():
+    """Per-env results of the trajectory env do not depend on the split over ranks (env and generator draws keyed by global id)."""
+    N, half = 256, 128
+    case = LC.build_case("traj_flat_allterms", N)
+    env = LC.make_fused(case)
+    shard = LC.build_case("traj_flat_allterms", half)
+    for k in ("root", "dof", "contact", "actions"):
+        t = getattr(case.tape, k)
+        if k == "dof":
+            setattr(shard.tape, k, t.view(t.shape[0], t.shape[1], N, 12, 2)[:, :, half:].reshape(t.shape[0], t.shape[1], half * 12, 2).contiguous())
+        else:
+            setattr(shard.tape, k, t[:, half:].contiguous())
+    shard.ep, shard.tpush = case.ep[half:].clone(), case.tpush[half:].clone()
+    env2 = LC.make_fused(shard, env_id_offset=half)
+    # the flat env origins are a grid over the LOCAL env count: give the shard the rows of the full grid
+    env2.env_origins.copy_(env.env_origins[half:])
+    env.reset_traj(torch.arange(N, device="cuda"))
+    env2.reset_traj(torch.arange(half, device="cuda"))
+    for s in range(16):
+        env.step(case.tape.actions[s % 8].cuda())
+        env2.step(shard.tape.actions[s % 8].cuda())
+        for name in ("obs_buf", "rew_buf", "reset_buf", "prev_error", "time_until_next_push", "trajectory"):
+            a, b = getattr(env, name)[half:], getattr(env2, name)
+            assert torch.equal(a, b), f"step {s}: {name} depends on the sharding"
+        assert torch.equal(env.traj_gen.trajectory[half:], env2.traj_gen.trajectory)

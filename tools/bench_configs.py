@@ -67,6 +67,53 @@ def rough_lstm(num_envs=16384, steps=50, warmup=5, device="cuda", peak=6535.7):
                                         frac=pp_bytes * num_envs / (t_pp * 1e-3) / 1e9 / peak))
 
 
+def trajectory_env(num_envs=4096, steps=50, warmup=5, device="cuda", peak=6535.7):
+    """anymal_c_flat_trajectory env step = 4x PD torques + generator step + fused post-physics (traj_mode, 65 obs,
+    all reward terms of the class) + generator reset.  Algorithmic bytes of the fused kernel: the flat figure with 65 obs columns
+    + trajectory [10,2] read + prev_error / push timer read+write."""
+    from legged_gym_dev_b200 import configs, synthetic as S
+    from legged_gym_dev_b200.legged_robot_trajectory import AnymalTrajectory
+    from legged_gym_dev_b200.physics import ReplayPhysics
+    cfg = configs.anymal_c_flat_trajectory_cfg()
+    for k, v in configs.TRAJECTORY_ALL_REWARD_SCALES.items():
+        setattr(cfg.rewards.scales, k, v)
+    cfg.control.use_actuator_network = False
+    cfg.env.num_envs = num_envs
+    F = 4
+    tape = S.make_state_tape(num_envs, frames=F, seed=7, device=device)
+    env = AnymalTrajectory(cfg, SimpleNamespace(dt=cfg.sim.dt), None, device, True, physics=ReplayPhysics(tape, device=device, copy=False),
+                           asset=S.anymal_dof_limits(), seed=0)
+    env.episode_length_buf = S.make_episode_lengths(num_envs, seed=1, device=device)
+    env.reset_traj(torch.arange(num_envs, device=device))
+    acts = [tape.actions[f] for f in range(F)]
+    for s in range(warmup):
+        env.step(acts[s % F])
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    for s in range(steps):
+        env.step(acts[s % F])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    env._timing = []
+    for s in range(20):
+        env.step(acts[s % F])
+    torch.cuda.synchronize()
+    pp = [x.elapsed_time(y) for k, x, y in env._timing if k == "post_physics"]
+    t_pp = sum(pp) / len(pp)
+    K = len(env.params.active_terms)
+    pp_bytes = 986 + 8 * K + (65 - 48) * 4 + 80 + 2 * 8 + 2 * 4          # fused kernel only
+    gen_bytes = 2 * (88 + 80 + 4 * 4 + 16 + 9 * 8 + 4 + 1 + 4) + 80         # generator step: state read + written, window out
+    finite = bool(torch.isfinite(env.rew_buf).all()) and bool(torch.isfinite(env.obs_buf).all())
+    return dict(config="anymal_c_flat_trajectory (AnymalTrajectory): 4x PD torques + generator step + fused post-physics (65 obs, 18 reward "
+                       "terms) + generator reset",
+                num_envs=num_envs, ms_per_step=ms, env_steps_per_s=num_envs / (ms * 1e-3), finite=finite,
+                generator_plus_post_physics=dict(avg_launch_ms=t_pp, algorithmic_bytes_per_env=pp_bytes + gen_bytes,
+                                                 achieved_gbs=(pp_bytes + gen_bytes) * num_envs / (t_pp * 1e-3) / 1e9,
+                                                 frac=(pp_bytes + gen_bytes) * num_envs / (t_pp * 1e-3) / 1e9 / peak))
+
+
 def rom_per_call(num_envs=4096, loop_steps=1000, device="cuda", cpu=True):
     """cfg 1: CustomSim.step + DoubleSingleTracking, 4096 envs x 1000 loop steps, call-per-step API; CPU port beside it."""
     from legged_gym_dev_b200 import configs
@@ -293,6 +340,8 @@ def run_all(device="cuda", peak=6535.7, quick=False):
     for name, fn, kw in (("cfg1_rom_per_call", rom_per_call, dict(device=device, loop_steps=200 if quick else 1000)),
                          ("cfg3_rough_lstm", rough_lstm, dict(device=device, peak=peak)),
                          ("cfg3_rough_lstm_262144", rough_lstm, dict(device=device, peak=peak, num_envs=16384 if quick else 262144, steps=20)),
+                         ("next1_trajectory_env_4096", trajectory_env, dict(device=device, peak=peak)),
+                         ("next1_trajectory_env_262144", trajectory_env, dict(device=device, peak=peak, num_envs=16384 if quick else 262144, steps=20)),
                          ("cfg4_rom_rollout", rom_rollout, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20))),
                          ("cfg4b_tube_dataset", tube_dataset, dict(device=device, peak=peak, num_envs=16384 if quick else 262144)),
                          ("cfg5_gae_update", gae_update, dict(device=device, peak=peak))):
