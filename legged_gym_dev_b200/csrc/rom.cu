@@ -170,11 +170,13 @@ __device__ __forceinline__ void tracking_policy(const B200RomParams& p, const fl
 }
 
 // ---- state <-> registers ---------------------------------------------------------------------------
-template <int RN, int W>
+template <int RN, int W, bool WINDOWS = true>
 __device__ __forceinline__ void load_gen(const B200RomState& s, size_t i, int w, Gen<RN, W>& g) {
     const float* tr = s.trajectory + i * (w + 1) * RN;
     const float* vt = s.v_trajectory + i * w * 2;
-    if (W == WMAXR) {
+    if (!WINDOWS) {
+        // generator parameters only (the caller neither reads nor advances the horizon windows)
+    } else if (W == WMAXR) {
         for (int c = 0; c < (w + 1) * RN; ++c) g.traj[c] = tr[c];
         for (int c = 0; c < w * 2; ++c) g.vtraj[c] = vt[c];
     } else {
@@ -198,11 +200,12 @@ __device__ __forceinline__ void load_gen(const B200RomState& s, size_t i, int w,
     g.ctr = static_cast<uint32_t>(s.rng_ctr[i]);
 }
 
-template <int RN, int W>
+template <int RN, int W, bool WINDOWS = true>
 __device__ __forceinline__ void store_gen(const B200RomState& s, size_t i, int w, const Gen<RN, W>& g) {
     float* tr = s.trajectory + i * (w + 1) * RN;
     float* vt = s.v_trajectory + i * w * 2;
-    if (W == WMAXR) {
+    if (!WINDOWS) {
+    } else if (W == WMAXR) {
         for (int c = 0; c < (w + 1) * RN; ++c) tr[c] = g.traj[c];
         for (int c = 0; c < w * 2; ++c) vt[c] = g.vtraj[c];
     } else {
@@ -358,13 +361,33 @@ __global__ void __launch_bounds__(128) rom_reset_root_kernel(const __grid_consta
     if (i >= p.num_envs) return;
     if (any_reset && *any_reset == 0.0f) return;
     const int w = p.window;
+    const uint64_t genv = static_cast<uint64_t>(env_off + i);
     Gen<RN, W> g;
-    load_gen(s, i, w, g);
-    float pz[RN];
+    if (mask[i] != 0) {
+        load_gen(s, i, w, g);
+        float pz[RN];
 #pragma unroll
-    for (int c = 0; c < RN; ++c) pz[c] = root[static_cast<size_t>(i) * stride + c];
-    traj_reset(p, g, pz, w, static_cast<uint64_t>(env_off + i), mask[i] != 0);
-    store_gen(s, i, w, g);
+        for (int c = 0; c < RN; ++c) pz[c] = root[static_cast<size_t>(i) * stride + c];
+        traj_reset(p, g, pz, w, genv, true);
+        store_gen(s, i, w, g);
+        return;
+    }
+    // An env that does not reset only takes part in the warm-up's input evaluations (rom_dynamics.py:577-580): resamples that are
+    // due, then v.  Its clock does not move, so once t <= t_final every further evaluation repeats the same v; the horizon windows
+    // are neither read (SingleInt2D bounds are state-independent) nor written: ~110 B instead of ~600 B of traffic for such an env.
+    static_assert(RN == 2, "state-independent input bounds assumed");
+#pragma unroll
+    for (int c = 0; c < (W + 1) * RN; ++c) g.traj[c] = 0.0f;
+    load_gen<RN, W, false>(s, i, w, g);
+    const uint32_t ctr0 = g.ctr;
+    int it = 0;
+    while (it < w && g.t > g.t_final) {
+        get_input(p, g, w, genv);
+        ++it;
+    }
+    if (it < w) get_input(p, g, w, genv);
+    if (g.ctr != ctr0) store_gen<RN, W, false>(s, i, w, g);
+    else *reinterpret_cast<float2*>(s.v + static_cast<size_t>(i) * 2) = make_float2(g.v[0], g.v[1]);
 }
 
 template <int RN, int W>
