@@ -749,8 +749,10 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         }
         if (p.terrain_curriculum) {   // sum of terrain levels of the tile: warp shuffle first, one shared atomic per warp
             long long lv = valid ? level : 0;
+            constexpr int SW = TILE < 32 ? TILE : 32;                              // phase S runs on the first TILE threads only
+            constexpr unsigned SMASK = TILE < 32 ? ((1u << SW) - 1u) : 0xffffffffu;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
+            for (int o = SW / 2; o > 0; o >>= 1) lv += __shfl_xor_sync(SMASK, lv, o);
             if ((tid & 31) == 0) atomicAdd(&s.acc[K], static_cast<double>(lv));
         }
 
