@@ -280,3 +280,29 @@ def test_trajectory_env_shard_invariance():
             a, b = getattr(env, name)[half:], getattr(env2, name)
             assert torch.equal(a, b), f"step {s}: {name} depends on the sharding"
         assert torch.equal(env.traj_gen.trajectory[half:], env2.traj_gen.trajectory)
+
+
+def test_trajectory_env_graph_replay_matches_eager():
+    """The three-kernel trajectory step (generator step, fused post-physics, gated generator reset) has no host branch: a captured
+    tape cycle replays bit-identically to the eager API, generator state included."""
+    from legged_gym_dev_b200.graphs import GraphedReplay
+    F = 4
+    ca, cb = LC.build_case("traj_flat_allterms", 1024, frames=F), LC.build_case("traj_flat_allterms", 1024, frames=F)
+    a, b = LC.make_fused(ca, copy=False), LC.make_fused(cb, copy=False)
+    ids = torch.arange(1024, device="cuda")
+    a.reset_traj(ids)
+    b.reset_traj(ids)
+    acts_a = [ca.tape.actions[f].cuda() for f in range(F)]
+    acts_b = [cb.tape.actions[f].cuda() for f in range(F)]
+    g = GraphedReplay(a, acts_a)           # runs one warm-up cycle eagerly
+    for f in range(F):
+        b.step(acts_b[f])
+    for cycle in range(3):
+        g.replay()
+        for f in range(F):
+            b.step(acts_b[f])
+        torch.cuda.synchronize()
+        for k in ("obs_buf", "rew_buf", "reset_buf", "prev_error", "time_until_next_push", "trajectory", "episode_length_buf"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), f"cycle {cycle}: {k}"
+        for k in ("trajectory", "k", "t", "t_final", "weights", "rng_ctr"):
+            assert torch.equal(getattr(a.traj_gen, k), getattr(b.traj_gen, k)), f"cycle {cycle}: traj_gen.{k}"

@@ -106,7 +106,27 @@ def trajectory_env(num_envs=4096, steps=50, warmup=5, device="cuda", peak=6535.7
     pp_bytes = 986 + 8 * K + (65 - 48) * 4 + 80 + 2 * 8 + 2 * 4          # fused kernel only
     gen_bytes = 2 * (88 + 80 + 4 * 4 + 16 + 9 * 8 + 4 + 1 + 4) + 80         # generator step: state read + written, window out
     finite = bool(torch.isfinite(env.rew_buf).all()) and bool(torch.isfinite(env.obs_buf).all())
-    return dict(config="anymal_c_flat_trajectory (AnymalTrajectory): 4x PD torques + generator step + fused post-physics (65 obs, 18 reward "
+    graph_ms = None
+    try:   # the same loop as CUDA-graph replays of whole tape cycles (no host branch in the trajectory step)
+        from legged_gym_dev_b200.graphs import GraphedReplay
+        env._timing = None
+        g = GraphedReplay(env, acts)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        a, b = _events()
+        a.record()
+        reps = max(1, steps // F)
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        graph_ms = a.elapsed_time(b) / (reps * F)
+    except Exception as e:
+        graph_ms = f"{type(e).__name__}: {e}"
+    return dict(graph_ms_per_step=graph_ms,
+                graph_env_steps_per_s=(num_envs / (graph_ms * 1e-3) if isinstance(graph_ms, float) else None),
+                config="anymal_c_flat_trajectory (AnymalTrajectory): 4x PD torques + generator step + fused post-physics (65 obs, 18 reward "
                        "terms) + generator reset",
                 num_envs=num_envs, ms_per_step=ms, env_steps_per_s=num_envs / (ms * 1e-3), finite=finite,
                 generator_plus_post_physics=dict(avg_launch_ms=t_pp, algorithmic_bytes_per_env=pp_bytes + gen_bytes,
