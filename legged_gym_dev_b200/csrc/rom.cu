@@ -282,8 +282,19 @@ __global__ void __launch_bounds__(128) rom_step_kernel(const __grid_constant__ B
         else int2d_f<2>(p.model_dt, x, u, root);
         for (int c = 0; c < mn; ++c) s.root_states[static_cast<size_t>(i) * mn + c] = root[c];
     }
+    const uint32_t ctr0 = g.ctr;
+    const float k0 = g.k;
     gen_step(p, g, w, static_cast<uint64_t>(env_off + i), mask ? mask[i] != 0 : true);
-    store_gen(s, i, w, g);
+    // The ROM clock is slower than the loop (rom.dt / dt_loop loop steps per knot) and resamples are rarer still: write back only
+    // what this call changed — the horizon windows when a knot was appended, the parameters when a resample fired, else t and v.
+    if (g.k != k0) {
+        store_gen(s, i, w, g);
+    } else if (g.ctr != ctr0) {
+        store_gen<RN, W, false>(s, i, w, g);
+    } else {
+        s.t[i] = g.t;
+        *reinterpret_cast<float2*>(s.v + static_cast<size_t>(i) * 2) = make_float2(g.v[0], g.v[1]);
+    }
     write_views(p, s, i, g, action ? root : nullptr, mn);
 }
 
