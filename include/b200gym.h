@@ -253,6 +253,18 @@ int b200gym_adam_prepare(int32_t* step_dev, double* sumsq, void* stream);
 int b200gym_clip_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
                           const double* sumsq, float max_norm, const float* lr, float beta1, float beta2, float eps,
                           const int32_t* step_dev, void* stream);
+/* Data-parallel PPO.update: out[i] = sum over ranks r (in rank order) of peers->ptr[r][i], i < n_total, where
+ * ptr[r] is rank r's flat gradient buffer mapped into this process (peer / symmetric memory over NVLink; ptr[own rank] is the
+ * local buffer); sumsq (double, zeroed by the caller) += sum_{i < n_params} out[i]^2, the clip_grad_norm_ input.  Replaces the
+ * NCCL all-reduce + b200gym_grad_sumsq pair with one graph-capturable launch; every rank computes bit-identical sums.  The caller
+ * synchronises the ranks before (all gradients written) and after (no buffer overwritten while peers read) the call. */
+#define B200GYM_MAX_PEERS 16
+typedef struct B200PeerPtrs {
+    const float* ptr[B200GYM_MAX_PEERS];
+} B200PeerPtrs;
+int b200gym_grad_reduce_peers(const B200PeerPtrs* peers, int32_t world, float* out, int64_t n_total, int64_t n_params, double* sumsq,
+                              void* stream);
+
 /* PPO.update adaptive schedule (ppo.py): kl_mean = *kl_sum / count; lr /= 1.5 if kl_mean > 2*desired_kl (floor 1e-5),
  * lr *= 1.5 if 0 < kl_mean < desired_kl/2 (cap 1e-2).  lr lives on the device, so no host sync per minibatch. */
 int b200gym_adaptive_lr(const double* kl_sum, double count, float desired_kl, float* lr, void* stream);

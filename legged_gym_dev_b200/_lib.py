@@ -95,6 +95,10 @@ class PpoLossParamsPOD(C.Structure):
                 ("clip_param", f32), ("value_loss_coef", f32), ("entropy_coef", f32), ("inv_global_batch", f32)]
 
 
+class PeerPtrsPOD(C.Structure):
+    _fields_ = [("ptr", vp * 16)]
+
+
 _lib = None
 
 
@@ -136,6 +140,8 @@ def lib():
     L.b200gym_grad_sumsq.argtypes = [vp, C.c_int64, f32, vp, vp]
     L.b200gym_clip_adam.argtypes = [vp, vp, vp, vp, C.c_int64, f32, vp, f32, vp, f32, f32, f32, C.c_int32, vp]
     L.b200gym_adaptive_lr.argtypes = [vp, f64, f32, vp, vp]
+    L.b200gym_grad_reduce_peers.argtypes = [C.POINTER(PeerPtrsPOD), C.c_int32, vp, C.c_int64, C.c_int64, vp, vp]
+    L.b200gym_grad_reduce_peers.restype = C.c_int
     L.b200gym_adam_prepare.argtypes = [vp, vp, vp]
     L.b200gym_clip_adam_dev.argtypes = [vp, vp, vp, vp, C.c_int64, f32, vp, f32, vp, f32, f32, f32, vp, vp]
     L.b200gym_debug_mlp_trace.argtypes = [vp]
@@ -150,7 +156,7 @@ def lib():
     L.b200gym_tube_error.restype = L.b200gym_sliding_window.restype = C.c_int
     L.b200gym_mlp_forward.restype = C.c_int
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
-                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD)):
+                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD)):
         n = L.b200gym_sizeof(name.encode())
         if n != C.sizeof(cls):
             raise RuntimeError(f"ABI mismatch: sizeof({name}) is {n} in the library, {C.sizeof(cls)} in the binding")

@@ -226,6 +226,24 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict
     block_accumulate<1>(acc, out);
 }
 
+// Data-parallel PPO: the ranks' flat gradient buffers live in peer-mapped (symmetric) memory; every rank sums them
+// ITSELF with P2P loads over NVLink, in rank order, so all ranks obtain bit-identical sums without a ring; the squared norm that
+// clip_grad_norm_ needs is accumulated in the same pass.  One launch replaces NCCL all-reduce + grad_sumsq (the buffers are
+// 135 KB - 2.3 MB: a latency problem, not a bandwidth one) and — unlike a process-group collective — it is a plain kernel that a
+// CUDA graph captures.  The caller brackets it with a cross-rank barrier (gradients complete / nobody overwrites while peers read).
+__global__ void __launch_bounds__(256) grad_reduce_peers_kernel(const B200PeerPtrs peers, int world, float* __restrict__ out, long long n_total,
+                                                                long long n_params, double* __restrict__ sumsq) {
+    double acc[1] = {0.0};
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float g = 0.0f;
+        for (int r = 0; r < world; ++r) g = add_rn(g, __ldcv(peers.ptr[r] + i));   // volatile-class load: peers wrote it
+        out[i] = g;
+        if (i < n_params) acc[0] += static_cast<double>(g) * g;
+    }
+    block_accumulate<1>(acc, sumsq);
+}
+
 __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, long long n, float scale, const double* __restrict__ sumsq,
                                                         float max_norm, const float* __restrict__ lr, float b1, float b2, float eps,
@@ -341,6 +359,17 @@ int b200gym_grad_sumsq(const float* grad, int64_t n, float grad_scale, double* s
     const int grid = static_cast<int>((n + 2047) / 2048 > 148 * 8 ? 148 * 8 : (n + 2047) / 2048);
     grad_sumsq_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad, n, grad_scale, sumsq);
     B200_LAUNCH_CHECK("grad_sumsq");
+    return B200GYM_OK;
+}
+
+int b200gym_grad_reduce_peers(const B200PeerPtrs* peers, int32_t world, float* out, int64_t n_total, int64_t n_params, double* sumsq,
+                              void* stream) {
+    B200_REQUIRE(peers && out && sumsq && n_total > 0 && n_params >= 0 && n_params <= n_total, B200GYM_EINVAL, "grad_reduce_peers: bad argument");
+    B200_REQUIRE(world >= 1 && world <= B200GYM_MAX_PEERS, B200GYM_EINVAL, "grad_reduce_peers: 1..%d ranks (got %d)", B200GYM_MAX_PEERS, world);
+    for (int r = 0; r < world; ++r) B200_REQUIRE(peers->ptr[r] != nullptr, B200GYM_EINVAL, "grad_reduce_peers: peer %d has no buffer", r);
+    const int grid = static_cast<int>((n_total + 255) / 256 > 148 * 4 ? 148 * 4 : (n_total + 255) / 256);
+    grad_reduce_peers_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*peers, world, out, n_total, n_params, sumsq);
+    B200_LAUNCH_CHECK("grad_reduce_peers");
     return B200GYM_OK;
 }
 

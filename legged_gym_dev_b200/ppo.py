@@ -156,13 +156,14 @@ class ActorCritic(nn.Module):
         self.distribution = None
         self.flat_param = self.flat_grad = None
 
-    def flatten_parameters(self):
-        """Re-homes every parameter (and its .grad) into one contiguous buffer; 8 spare floats carry piggy-backed scalars."""
+    def flatten_parameters(self, grad_buffer=None):
+        """Re-homes every parameter (and its .grad) into one contiguous buffer; 8 spare floats carry piggy-backed scalars.
+        grad_buffer: optional pre-allocated [n + 8] tensor for the gradients (peer-mapped memory in the multi-GPU update)."""
         ps = list(self.parameters())
         dev = ps[0].device
         n = sum(p.numel() for p in ps)
         self.flat_param = torch.empty(n, device=dev)
-        self.flat_grad = torch.zeros(n + 8, device=dev)
+        self.flat_grad = torch.zeros(n + 8, device=dev) if grad_buffer is None else grad_buffer
         off = 0
         self._slices = {}
         for name, p in self.named_parameters():
@@ -243,6 +244,17 @@ class PPO:
         if self.actor_critic.flat_param is None or self.actor_critic.flat_param.device != self.device:
             self.actor_critic.flatten_parameters()
         self.storage = None
+        # multi-GPU: gradients in peer-mapped memory, summed by our own kernel over NVLink (peer_reduce.py); B200GYM_P2P_GRADS=0 or a
+        # failed rendezvous falls back to the NCCL all-reduce of the same flat buffer
+        self._peer = None
+        if _dist_ready() and os.environ.get("B200GYM_P2P_GRADS", "1") != "0":
+            try:
+                from .peer_reduce import PeerGradReducer
+                self._peer = PeerGradReducer(self.actor_critic.num_flat + 8, self.device)
+                self.actor_critic.flatten_parameters(grad_buffer=self._peer.buf)
+            except Exception as e:   # noqa: BLE001 — symmetric memory needs NVLink/P2P between the ranks
+                print(f"[b200gym] peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+                self._peer = None
         self.optimizer = FlatAdam(self.actor_critic, lr=learning_rate)
         self.transition = RolloutStorage.Transition()
         self.clip_param, self.num_learning_epochs, self.num_mini_batches = clip_param, num_learning_epochs, num_mini_batches
@@ -319,14 +331,20 @@ class PPO:
         tail = ac.flat_grad[ac.num_flat:ac.num_flat + 2]
         tail[0:1].copy_(sc[0:1])
         tail[1:2].fill_(float(B))
-        if world > 1:
+        grad = None
+        if world > 1 and self._peer is not None:
+            # ONE kernel over peer-mapped memory: rank-ordered sum of all ranks' buffers + squared norm (graph-capturable)
+            self.optimizer.prepare()
+            grad = self._peer.reduce(ac.num_flat, self.optimizer._sumsq)
+            tail = grad[ac.num_flat:ac.num_flat + 2]
+        elif world > 1:
             import torch.distributed as dist
             dist.all_reduce(ac.flat_grad)
         if self.desired_kl is not None and self.schedule == "adaptive":
             self._klsum.copy_(tail)
             _lib.check(self.lib.b200gym_adaptive_lr(ptr(self._klsum), float(B * world), self.desired_kl, ptr(self.optimizer.lr), st),
                        "adaptive_lr")
-        self.optimizer.step(self.max_grad_norm)
+        self.optimizer.step(self.max_grad_norm, grad=grad)
 
     def _static_minibatch(self, B):
         """Persistent gather targets of one minibatch + the captured CUDA graph of `_minibatch_step` on them."""
@@ -371,7 +389,7 @@ class PPO:
         self._scalars.zero_()
         # Across ranks the minibatch body runs eagerly: it is GPU-bound either way (graph replay and eager launch measure the
         # same), and keeping the NCCL all-reduce out of stream capture avoids depending on capture support in the process group.
-        use_graph = self.use_graph and world == 1 and all(p.numel() == B for p in plan)
+        use_graph = self.use_graph and (world == 1 or self._peer is not None) and all(p.numel() == B for p in plan)
         n_updates = 0
         for idx in plan:
             if idx.numel() != B:      # ragged plan (tests): fresh buffers, eager
@@ -428,13 +446,22 @@ class FlatAdam:
         self._sumsq = torch.zeros(1, dtype=torch.double, device=dev)
         self.lib = _lib.lib()
 
-    def step(self, max_grad_norm):
-        """clip_grad_norm_ + Adam; the step count is device-resident (CUDA-graph replayable), `steps` mirrors it on the host."""
+    def prepare(self):
+        """Advances the device-resident step count and zeroes the squared-norm accumulator."""
+        _lib.check(self.lib.b200gym_adam_prepare(_lib.ptr(self.step_dev), _lib.ptr(self._sumsq), _lib.stream_ptr(self.ac.flat_param.device)),
+                   "adam_prepare")
+
+    def step(self, max_grad_norm, grad=None):
+        """clip_grad_norm_ + Adam; the step count is device-resident (CUDA-graph replayable), `steps` mirrors it on the host.
+        grad: already reduced gradients whose squared norm sits in `_sumsq` (peer-memory path: `prepare()` was called before the
+        reduction); default = the local flat gradient buffer."""
         ac, ptr, st = self.ac, _lib.ptr, _lib.stream_ptr(self.ac.flat_param.device)
         self.steps += 1
-        _lib.check(self.lib.b200gym_adam_prepare(ptr(self.step_dev), ptr(self._sumsq), st), "adam_prepare")
-        _lib.check(self.lib.b200gym_grad_sumsq(ptr(ac.flat_grad), ac.num_flat, 1.0, ptr(self._sumsq), st), "grad_sumsq")
-        _lib.check(self.lib.b200gym_clip_adam_dev(ptr(ac.flat_param), ptr(ac.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+        if grad is None:
+            self.prepare()
+            _lib.check(self.lib.b200gym_grad_sumsq(ptr(ac.flat_grad), ac.num_flat, 1.0, ptr(self._sumsq), st), "grad_sumsq")
+            grad = ac.flat_grad
+        _lib.check(self.lib.b200gym_clip_adam_dev(ptr(ac.flat_param), ptr(grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                                                   ac.num_flat, 1.0, ptr(self._sumsq), max_grad_norm, ptr(self.lr), self.betas[0],
                                                   self.betas[1], self.eps, ptr(self.step_dev), st), "clip_adam_dev")
 

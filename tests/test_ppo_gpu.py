@@ -193,3 +193,28 @@ def test_ppo_update_tf32_contractions():
     sd = alg.actor_critic.state_dict()
     worst = max((sd[k].cpu() - v).abs().max().item() for k, v in ref.state_dict().items())
     assert worst <= 10 * max(s["lr"] for s in stats), worst
+
+
+@pytest.mark.parametrize("world", [1, 2, 5, 8])
+def test_grad_reduce_peers_kernel(world):
+    """b200gym_grad_reduce_peers on ONE GPU with local tensors standing in for the peer-mapped buffers: rank-ordered fp32 sum of
+    all buffers + squared norm of the parameter part (the multi-rank wiring is checked by tools/ddp_train_check.py on 2+ GPUs)."""
+    from legged_gym_dev_b200 import _lib
+    L = _lib.lib()
+    n, n_params = 33657 + 8, 33657
+    g = torch.Generator(device="cuda").manual_seed(world)
+    bufs = [torch.randn(n, generator=g, device="cuda") for _ in range(world)]
+    peers = _lib.PeerPtrsPOD()
+    for r, b in enumerate(bufs):
+        peers.ptr[r] = b.data_ptr()
+    out = torch.empty(n, device="cuda")
+    sumsq = torch.zeros(1, dtype=torch.double, device="cuda")
+    _lib.check(L.b200gym_grad_reduce_peers(peers, world, _lib.ptr(out), n, n_params, _lib.ptr(sumsq), _lib.stream_ptr("cuda")))
+    want = torch.zeros(n, device="cuda")
+    for b in bufs:                                   # same order, same fp32 rounding
+        want = want + b
+    assert torch.equal(out, want)
+    ref = float((want[:n_params].double() ** 2).sum())
+    assert abs(float(sumsq) - ref) <= 1e-12 * ref
+    with pytest.raises(RuntimeError):
+        _lib.check(L.b200gym_grad_reduce_peers(peers, 17, _lib.ptr(out), n, n_params, _lib.ptr(sumsq), _lib.stream_ptr("cuda")))
