@@ -306,3 +306,28 @@ def test_trajectory_env_graph_replay_matches_eager():
             assert torch.equal(getattr(a, k), getattr(b, k)), f"cycle {cycle}: {k}"
         for k in ("trajectory", "k", "t", "t_final", "weights", "rng_ctr"):
             assert torch.equal(getattr(a.traj_gen, k), getattr(b.traj_gen, k)), f"cycle {cycle}: traj_gen.{k}"
+
+
+def test_trajectory_env_error_paths():
+    """Same failures as the reference class: the terrain curriculum reads self.commands (legged_robot_trajectory.py:508) ->
+    AttributeError; rom / generator classes outside the fused set are refused loudly; a wrong num_observations is refused."""
+    case = LC.build_case("traj_flat_allterms", 64)
+    case.cfg.terrain.mesh_type, case.cfg.terrain.curriculum = "trimesh", True
+    with pytest.raises(AttributeError, match="commands"):
+        LC.make_fused(case)
+    case = LC.build_case("traj_flat_allterms", 64)
+    case.cfg.rom.cls = "Unicycle"
+    with pytest.raises(NotImplementedError):
+        LC.make_fused(case)
+    case = LC.build_case("traj_flat_allterms", 64)
+    case.cfg.trajectory_generator.cls = "CircleTrajectoryGenerator"
+    with pytest.raises(NotImplementedError):
+        LC.make_fused(case)
+    case = LC.build_case("traj_flat_allterms", 64)
+    case.cfg.env.num_observations = 48
+    with pytest.raises(ValueError, match="num_observations"):
+        LC.make_fused(case)
+    env = LC.make_fused(LC.build_case("traj_flat_allterms", 64))
+    assert not hasattr(env, "commands") and env.trajectory.shape == (64, 10, 2) and env.obs_buf.shape == (64, 65)
+    with pytest.raises(RuntimeError):
+        env.step(torch.zeros(64, 12))          # CPU tensor: no fallback

@@ -235,3 +235,47 @@ def test_trajectory_port_tracks_unmodified_reference(name):
             assert_close(port.sea_cell_state, env.sea_cell_state, 1.0, tag + "c")
     assert np.array_equal(port.gen.ctr, env._traj_shim.ctr)
     assert resets > N // 2 and pushes > 0
+
+
+def test_trajectory_cfg_tables_match_reference_objects():
+    """configs.py's anymal trajectory tables == the reference's cfg classes (+ the documented completion) after flattening."""
+    if not os.path.isdir("/root/reference/legged_gym"):
+        pytest.skip("/root/reference not present")
+    import dataclasses
+    from oracle import ref_harness as H
+    from legged_gym_dev_b200 import configs, synthetic as S
+    from legged_gym_dev_b200.params import flatten_legged_cfg
+    ref = H.import_reference()
+    for mine, theirs in ((configs.anymal_c_flat_trajectory_cfg(), ref.envs.AnymalCFlatTrajectoryCfg()),
+                         (configs.anymal_c_rough_trajectory_cfg(), ref.envs.AnymalCRoughTrajectoryCfg())):
+        H.complete_trajectory_cfg(theirs)
+        theirs.env.num_observations = mine.env.num_observations      # the shipped 240 matches no rom (legged_robot_trajectory_config.py:36)
+        a = dataclasses.asdict(flatten_legged_cfg(theirs, 0.005, S.DOF_NAMES, terrain_rows=9, terrain_cols=9, trajectory=True))
+        b = dataclasses.asdict(flatten_legged_cfg(mine, 0.005, S.DOF_NAMES, terrain_rows=9, terrain_cols=9, trajectory=True))
+        assert a == b
+        for sec in ("rom", "trajectory_generator"):
+            ta, tb = getattr(theirs, sec), getattr(mine, sec)
+            for k in ("cls", "dt", "z_min", "z_max", "v_min", "v_max") if sec == "rom" else \
+                    ("cls", "t_samp_cls", "weight_samp_cls", "N", "dN", "t_low", "t_high", "freq_low", "freq_high", "seed", "prob_stationary"):
+                assert getattr(ta, k) == getattr(tb, k), (sec, k)
+        for k in ("randomize_rom_distance", "max_rom_dist", "zero_rom_distance_likelihood", "time_between_pushes", "max_push_vel_xy"):
+            assert getattr(theirs.domain_rand, k) == getattr(mine.domain_rand, k), k
+
+
+def test_trajectory_env_rejects_what_the_reference_class_cannot_run():
+    """LeggedRobotTrajectory has no commands (legged_robot_trajectory.py:621-622): the terms that need them raise AttributeError in the
+    reference (missing _reward_* / missing self.commands) and in the flattening; tracking_rom / differential_error need the class."""
+    from legged_gym_dev_b200 import configs, synthetic as S
+    from legged_gym_dev_b200.params import flatten_legged_cfg
+    for term in ("tracking_lin_vel", "tracking_ang_vel", "stand_still"):
+        cfg = configs.anymal_c_flat_trajectory_cfg()
+        setattr(cfg.rewards.scales, term, 1.0)
+        with pytest.raises(AttributeError):
+            flatten_legged_cfg(cfg, 0.005, S.DOF_NAMES, trajectory=True)
+    for term in ("tracking_rom", "differential_error"):
+        cfg = configs.anymal_c_flat_cfg()
+        setattr(cfg.rewards.scales, term, 1.0)
+        with pytest.raises(AttributeError):
+            flatten_legged_cfg(cfg, 0.005, S.DOF_NAMES)
+    p = flatten_legged_cfg(configs.anymal_c_flat_trajectory_cfg(), 0.005, S.DOF_NAMES, trajectory=True)
+    assert p.traj_mode and p.time_between_pushes == [0.5, 10.0] and p.max_push_vel == 1.0
