@@ -65,3 +65,57 @@ def test_env_shard_ranges():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 4 * world
             if n // world >= 4:
                 assert all((h - l) % 4 == 0 for l, h in spans[:-1])
+
+
+def _traj_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import legged_case as LC
+    from legged_gym_dev_b200.sharding import env_shard
+    N = 64
+    lo, hi = env_shard(rank, world, N)
+    full = LC.build_case("traj_flat_allterms", N)
+    case = LC.build_case("traj_flat_allterms", hi - lo)
+    t = full.tape
+    case.tape.root, case.tape.contact, case.tape.actions = t.root[:, lo:hi].contiguous(), t.contact[:, lo:hi].contiguous(), t.actions[:, lo:hi].contiguous()
+    case.tape.dof = t.dof.view(t.dof.shape[0], t.dof.shape[1], N, 12, 2)[:, :, lo:hi].reshape(t.dof.shape[0], t.dof.shape[1], (hi - lo) * 12, 2).contiguous()
+    case.ep, case.tpush = full.ep[lo:hi].clone(), full.tpush[lo:hi].clone()
+    port_, phys = LC.make_port(case, env_id_offset=lo)
+    fport, _ = LC.make_port(full)
+    port_.env_origins.copy_(fport.env_origins[lo:hi])          # the grid of origins is laid out over the GLOBAL env count
+    port_.gen.reset_traj(torch.arange(hi - lo), port_.proj_z())
+    rew_sum = torch.zeros(1, dtype=torch.double)
+    for s in range(10):
+        port_.step(case.tape.actions[s % 8].clone(), phys)
+        rew_sum += port_.rew_buf.double().sum()
+    dist.all_reduce(rew_sum)                                   # reward statistics: the one cross-rank quantity of the env step
+    q.put((rank, lo, hi, port_.obs_buf.numpy().copy(), port_.gen.traj.numpy().copy(), port_.prev_error.numpy().copy(), float(rew_sum)))
+    dist.destroy_process_group()
+
+
+def test_trajectory_env_sharding_over_gloo():
+    """SURVEY 8f row 1 across ranks: env draws keyed by global env id, generator draws by (global env id, event counter)."""
+    import legged_case as LC
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_traj_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = LC.build_case("traj_flat_allterms", 64)
+    fport, phys = LC.make_port(full)
+    fport.gen.reset_traj(torch.arange(64), fport.proj_z())
+    total = 0.0
+    for s in range(10):
+        fport.step(full.tape.actions[s % 8].clone(), phys)
+        total += float(fport.rew_buf.double().sum())
+    for rank, lo, hi, obs, traj, perr, rew_sum in out:
+        assert torch.equal(torch.from_numpy(obs), fport.obs_buf[lo:hi]), "observations depend on the sharding"
+        assert torch.equal(torch.from_numpy(traj), fport.gen.traj[lo:hi]) and torch.equal(torch.from_numpy(perr), fport.prev_error[lo:hi])
+        assert abs(rew_sum - total) <= 1e-9 * max(1.0, abs(total))

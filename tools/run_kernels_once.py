@@ -13,3 +13,5 @@ r = B.gae_update(num_envs=65536, T=24)
 print("gae", r["gae_ms"], r["actor_forward"])
 r = B.tube_dataset(num_envs=65536)
 print("tube dataset", r["ms"])
+r = B.trajectory_env(num_envs=262144, steps=3, warmup=2)
+print("trajectory env", r["ms_per_step"])
