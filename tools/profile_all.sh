@@ -13,8 +13,8 @@ $K > $O/${R}_kernels_plain.log 2>&1 || exit 1
 cap() {  # name regex [skip]
   timeout 240 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s ${3:-1} -c 1 -f -o $O/prof_${R}_$1 $K > $O/ncu_${R}_$1.log 2>&1
 }
-cap post_physics_rough 'post_physics_kernel<32, 1, 0>' 2
-cap post_physics_traj 'post_physics_kernel<32, 0, 1>' 2
+cap post_physics_rough 'post_physics_kernel<\(int\)32, \(bool\)1, \(bool\)0>' 2
+cap post_physics_traj 'post_physics_kernel<\(int\)32, \(bool\)0, \(bool\)1>' 2
 cap rom_reset_root 'rom_reset_root_kernel' 2
 cap lstm_torques 'lstm_torques_kernel' 4
 cap rom_rollout 'rom_rollout_kernel' 1
