@@ -149,6 +149,12 @@ int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedBuffers* b, 
 #define B200GYM_ROM_SINGLE_INT_2D 0 /* rom_dynamics.py:182-211  n=2 m=2 */
 #define B200GYM_ROM_DOUBLE_INT_2D 1 /* rom_dynamics.py:214-260  n=4 m=2 */
 #define B200GYM_ROM_MAX_WINDOW 32
+/* trajectory generator classes (rom_dynamics.py): the random TrajectoryGenerator :441-615 and its deterministic subclasses
+ * ZeroTrajectoryGenerator :618-624, SquareTrajectoryGenerator :627-675, CircleTrajectoryGenerator :678-698 (SingleInt2D rom) */
+#define B200GYM_GEN_RANDOM 0
+#define B200GYM_GEN_ZERO 1
+#define B200GYM_GEN_SQUARE 2
+#define B200GYM_GEN_CIRCLE 3
 
 typedef struct B200RomParams {
     int32_t num_envs, model_type, rom_type, window, dN, horizon; /* window = N*dN, horizon = N (rom_dynamics.py:485-486) */
@@ -161,6 +167,9 @@ typedef struct B200RomParams {
     float max_rom_distance[4], zero_rom_dist_llh, noise_lower[4], noise_upper[4]; /* custom_sim.py:32-35,80-91 */
     float Kp, Kd; /* DoubleSingleTracking (controllers.py:80-92) */
     uint32_t seed_lo, seed_hi;
+    int32_t gen_kind;  /* B200GYM_GEN_* */
+    float gen_c[4];    /* Square: leg boundaries c1..c4 (rom_dynamics.py:633-636), computed by the host in fp32 like the reference */
+    float gen_v[4];    /* Square: v_max[1]/2, v_max[0], v_min[1]/2, v_min[1] (:637-640, incl. its v_min[1] quirk); Circle: [0] = speed (:692) */
 } B200RomParams;
 
 /* Generator + sim state; every tensor row-major [N, ...] fp32 with the reference's shapes (rom_dynamics.py:487-508,
@@ -179,6 +188,7 @@ typedef struct B200RomState {
     int32_t* rng_ctr;    /* [N] per-env draw-event counter of the counter-based RNG */
     float* env_trajectory; /* [N, horizon, rom_n]        CustomSim.trajectory (interpolated, custom_sim.py:74) or NULL */
     float* obs;          /* [N, model_n + rom_n + 2]     CustomSim.get_observations (custom_sim.py:95-100) or NULL */
+    float* center;       /* [N, 2]                       CircleTrajectoryGenerator.center or NULL */
 } B200RomState;
 
 /* TrajectoryGenerator.__init__ draw of ramp_v_end (rom_dynamics.py:495); all other state must be zero-filled. */

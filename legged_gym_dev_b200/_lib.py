@@ -73,12 +73,13 @@ class RomParamsPOD(C.Structure):
         ("weight_zero_col", i32), ("randomize_rom_distance", i32),
         ("max_rom_distance", f32 * 4), ("zero_rom_dist_llh", f32), ("noise_lower", f32 * 4), ("noise_upper", f32 * 4),
         ("Kp", f32), ("Kd", f32), ("seed_lo", u32), ("seed_hi", u32),
+        ("gen_kind", i32), ("gen_c", f32 * 4), ("gen_v", f32 * 4),
     ]
 
 
 _ROM_FIELDS = ["root_states", "trajectory", "v_trajectory", "v", "t", "k", "t_final", "weights", "sample_hold_input",
                "extreme_input", "ramp_v_start", "ramp_v_end", "ramp_t_start", "sin_mag", "sin_freq", "sin_off", "sin_mean",
-               "stationary_inds", "rng_ctr", "env_trajectory", "obs"]
+               "stationary_inds", "rng_ctr", "env_trajectory", "obs", "center"]
 
 
 class RomStatePOD(C.Structure):

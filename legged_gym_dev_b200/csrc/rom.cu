@@ -27,6 +27,7 @@ template <int RN, int W>   // RN = rom state dim (2|4), W = window capacity
 struct Gen {
     float traj[(W + 1) * RN], vtraj[W * 2];
     float w[4], t_final, t, k, hold[2], ext[2], ramp_t0, rv0[2], rv1[2], smag[2], sfreq[2], soff[2], smean[2], v[2];
+    float cen[2];   // CircleTrajectoryGenerator.center (rom_dynamics.py:680-683)
     bool stat;
     uint32_t ctr;
 };
@@ -89,6 +90,29 @@ __device__ __forceinline__ void get_input(const B200RomParams& p, Gen<RN, W>& g,
     // TrajectoryGenerator.get_input_t, rom_dynamics.py:550-566 (+ v[stationary] = 0 of :580)
     if (W != WMAXR) w = W;
     const float* z = g.traj + w * RN;
+    if (p.gen_kind != B200GYM_GEN_RANDOM) {
+        // Zero / Square / Circle generators override get_input_t (rom_dynamics.py:618-698): no resampling, no clip_v_z, no draws
+        float v0 = 0.0f, v1 = 0.0f;
+        if (p.gen_kind == B200GYM_GEN_SQUARE) {   // :630-640 (SingleInt2D): four legs selected by the env's own clock
+            const float t = g.t;
+            if (0.0f <= t && t < p.gen_c[0]) v1 = p.gen_v[0];
+            if (p.gen_c[0] <= t && t < p.gen_c[1]) v0 = p.gen_v[1];
+            if (p.gen_c[1] <= t && t < p.gen_c[2]) v1 = p.gen_v[2];
+            if (p.gen_c[2] <= t && t < p.gen_c[3]) v0 = p.gen_v[3];
+        } else if (p.gen_kind == B200GYM_GEN_CIRCLE) {   // :686-692 (SingleInt2D)
+            const float e0 = sub_rn(z[0], g.cen[0]), e1 = sub_rn(z[1], g.cen[1]);
+            float a0 = -e1, a1 = e0;
+            const float n1 = sqrtf(add_rn(mul_rn(a0, a0), mul_rn(a1, a1)));
+            a0 = add_rn(a0, -sub_rn(e0, div_rn(mul_rn(0.5f, e0), n1)));
+            a1 = add_rn(a1, -sub_rn(e1, div_rn(mul_rn(0.5f, e1), n1)));
+            const float n2 = sqrtf(add_rn(mul_rn(a0, a0), mul_rn(a1, a1)));
+            v0 = mul_rn(div_rn(a0, n2), p.gen_v[0]);
+            v1 = mul_rn(div_rn(a1, n2), p.gen_v[0]);
+        }
+        g.v[0] = g.stat ? 0.0f : v0;
+        g.v[1] = g.stat ? 0.0f : v1;
+        return;
+    }
     if (g.t > g.t_final) resample(p, g, z, genv);
     float lo[2], hi[2];
     rom_bounds<RN>(p, z, lo, hi);
@@ -198,6 +222,11 @@ __device__ __forceinline__ void load_gen(const B200RomState& s, size_t i, int w,
 #undef LD2
     g.stat = s.stationary_inds[i] != 0;
     g.ctr = static_cast<uint32_t>(s.rng_ctr[i]);
+    g.cen[0] = g.cen[1] = 0.0f;
+    if (s.center) {
+        const float2 c = *reinterpret_cast<const float2*>(s.center + i * 2);
+        g.cen[0] = c.x, g.cen[1] = c.y;
+    }
 }
 
 template <int RN, int W, bool WINDOWS = true>
@@ -222,6 +251,7 @@ __device__ __forceinline__ void store_gen(const B200RomState& s, size_t i, int w
 #undef ST2
     s.stationary_inds[i] = g.stat ? 1 : 0;
     s.rng_ctr[i] = static_cast<int32_t>(g.ctr);
+    if (s.center) *reinterpret_cast<float2*>(s.center + i * 2) = make_float2(g.cen[0], g.cen[1]);
 }
 
 // writes CustomSim.trajectory (interpolated window, custom_sim.py:74) and the observation (custom_sim.py:95-100)
@@ -324,7 +354,12 @@ __device__ __forceinline__ void traj_reset(const B200RomParams& p, Gen<RN, W>& g
         g.k = -static_cast<float>(w);
         g.t = mul_rn(g.k, p.rom_dt);
         g.t_final = g.t;
-        resample(p, g, pz, genv);
+        if (p.gen_kind == B200GYM_GEN_RANDOM) resample(p, g, pz, genv);
+        else if (p.gen_kind == B200GYM_GEN_ZERO) g.stat = true;                    // ZeroTrajectoryGenerator.resample, :619-620
+    }
+    if (p.gen_kind == B200GYM_GEN_CIRCLE) {   // CircleTrajectoryGenerator.resample re-centres EVERY env from z (:680-683), reset or not
+        g.cen[0] = sub_rn(pz[0], 0.5f);
+        g.cen[1] = pz[1];
     }
     // warm-up, :604-605: the input is evaluated for every env, only reset envs advance (with the ROM clock)
     for (int it = 0; it < w; ++it) {
@@ -390,6 +425,13 @@ __global__ void __launch_bounds__(128) rom_reset_root_kernel(const __grid_consta
 #pragma unroll
     for (int c = 0; c < (W + 1) * RN; ++c) g.traj[c] = 0.0f;
     load_gen<RN, W, false>(s, i, w, g);
+    if (p.gen_kind == B200GYM_GEN_CIRCLE) {   // re-centred from this env's own root position (no offset: it does not reset), :680-683
+#pragma unroll
+        for (int c = 0; c < RN; ++c) g.traj[(W != WMAXR ? W : w) * RN + c] = s.trajectory[(static_cast<size_t>(i) * (w + 1) + w) * RN + c];
+        g.cen[0] = sub_rn(root[static_cast<size_t>(i) * stride], 0.5f);
+        g.cen[1] = root[static_cast<size_t>(i) * stride + 1];
+        *reinterpret_cast<float2*>(s.center + static_cast<size_t>(i) * 2) = make_float2(g.cen[0], g.cen[1]);
+    }
     const uint32_t ctr0 = g.ctr;
     int it = 0;
     while (it < w && g.t > g.t_final) {
@@ -567,6 +609,10 @@ int check_rom(const B200RomParams* p, const B200RomState* s, const char* what, b
         B200_REQUIRE(b200_aligned16(q), B200GYM_EALIGN, "%s: state tensors must be 16-byte aligned", what);
     }
     B200_REQUIRE(!need_root || s->root_states, B200GYM_EINVAL, "%s: root_states missing", what);
+    B200_REQUIRE(p->gen_kind >= B200GYM_GEN_RANDOM && p->gen_kind <= B200GYM_GEN_CIRCLE, B200GYM_EINVAL, "%s: unknown gen_kind %d", what, p->gen_kind);
+    B200_REQUIRE(p->gen_kind == B200GYM_GEN_RANDOM || p->rom_type == 0, B200GYM_EINVAL,
+                 "%s: the Zero / Square / Circle generators are implemented for a SingleInt2D rom", what);
+    B200_REQUIRE(p->gen_kind != B200GYM_GEN_CIRCLE || (s->center && b200_aligned16(s->center)), B200GYM_EINVAL, "%s: circle centres missing", what);
     return B200GYM_OK;
 }
 
@@ -601,6 +647,7 @@ int b200gym_rom_step(const B200RomParams* p, const B200RomState* s, const float*
 int b200gym_rom_reset(const B200RomParams* p, const B200RomState* s, const uint8_t* reset_mask, int64_t env_id_offset,
                       void* stream) {
     if (int rc = check_rom(p, s, "rom_reset", true)) return rc;
+    B200_REQUIRE(p->gen_kind == B200GYM_GEN_RANDOM, B200GYM_EINVAL, "rom_reset: CustomSim only knows the random TrajectoryGenerator (custom_sim.py:1,53)");
     B200_REQUIRE(p->rom_type == 0, B200GYM_EINVAL, "rom_reset: CustomSim needs a SingleInt2D rom (proj_z of the model state)");
     const int grid = (p->num_envs + 127) / 128;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -638,6 +685,7 @@ int b200gym_rom_tracking_policy(const B200RomParams* p, const float* obs, float*
 int b200gym_rom_rollout(const B200RomParams* p, const B200RomState* s, float* obs_io, int32_t T, float* x, float* z, float* pz_x,
                         float* v, uint8_t* done, int64_t env_id_offset, void* stream) {
     if (int rc = check_rom(p, s, "rom_rollout", true)) return rc;
+    B200_REQUIRE(p->gen_kind == B200GYM_GEN_RANDOM, B200GYM_EINVAL, "rom_rollout: CustomSim only knows the random TrajectoryGenerator (custom_sim.py:1,53)");
     B200_REQUIRE(p->rom_type == 0 && p->model_type == 1, B200GYM_EINVAL,
                  "rom_rollout: built for the double_single_int configuration (DoubleInt2D model, SingleInt2D rom)");
     B200_REQUIRE(obs_io && z && pz_x && T >= 0 && (T == 0 || (v && done)), B200GYM_EINVAL, "rom_rollout: null log buffer or negative T");

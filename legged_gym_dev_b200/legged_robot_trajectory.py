@@ -100,9 +100,11 @@ class LeggedRobotTrajectory(LeggedRobot):
 
     def _init_trajectory_generator(self):                                 # legged_robot_trajectory.py:105-123
         tc = self.cfg.trajectory_generator
-        if tc.cls != "TrajectoryGenerator":
-            raise NotImplementedError(f"{tc.cls}: only the random TrajectoryGenerator is fused (SURVEY.md §8f-4)")
-        self.traj_gen = R.TrajectoryGenerator(
+        classes = {"TrajectoryGenerator": R.TrajectoryGenerator, "ZeroTrajectoryGenerator": R.ZeroTrajectoryGenerator,
+                   "SquareTrajectoryGenerator": R.SquareTrajectoryGenerator, "CircleTrajectoryGenerator": R.CircleTrajectoryGenerator}
+        if tc.cls not in classes:
+            raise NotImplementedError(f"{tc.cls}: not a fused trajectory generator class")
+        self.traj_gen = classes[tc.cls](
             self.rom, _T_SAMPLERS[tc.t_samp_cls](tc.t_low, tc.t_high, backend="torch", device=self.device),
             _W_SAMPLERS[tc.weight_samp_cls](), dt_loop=self.dt, N=tc.N, freq_low=tc.freq_low, freq_high=tc.freq_high,
             seed=tc.seed, backend="torch", device=self.device, prob_stationary=tc.prob_stationary, dN=tc.dN,

@@ -132,6 +132,7 @@ def _pad4(v):
 
 class TrajectoryGenerator:
     """rom_dynamics.py:441-615 with the torch backend; state tensors have the reference's names and shapes."""
+    kind = 0   # B200GYM_GEN_RANDOM; the deterministic subclasses below override it
 
     def __init__(self, rom, t_sampler, weight_sampler, dt_loop=0.02, N=4, freq_low=0.01, freq_high=10, seed=42,
                  backend="torch", device="cuda", prob_stationary=.01, dN=1, env_id_offset=0, model=None):
@@ -156,6 +157,9 @@ class TrajectoryGenerator:
         self.v = z(n, rom.m)
         self.stationary_inds = torch.zeros(n, dtype=torch.bool, device=dev)
         self.rng_ctr = torch.zeros(n, dtype=torch.int32, device=dev)
+        if self.kind != 0 and rom.kind != SINGLE_INT_2D:
+            raise ValueError("Only SingleInt2D is fused for the Zero / Square / Circle generators")
+        self.center = z(n, 2) if self.kind == 3 else None
         self._model = model
         self._sim = None
         self._build_pod()
@@ -179,6 +183,17 @@ class TrajectoryGenerator:
         p.freq_low, p.freq_high, p.prob_stationary = self.freq_low, self.freq_high, self.prob_stationary
         p.weight_zero_col = getattr(self.weight_sampler, "zero_col", -1)
         p.seed_lo, p.seed_hi = self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF
+        p.gen_kind = self.kind
+        if self.kind == 2:      # rom_dynamics.py:633-640, evaluated in fp32 tensors exactly as written there
+            vmax, vmin = rom.v_max.cpu(), rom.v_min.cpu()
+            c1 = 2 / vmax[1]
+            c2 = c1 + 1 / vmax[0]
+            c3 = c2 + 2 / abs(vmin[1])
+            c4 = c3 + 1 / abs(vmin[0])
+            p.gen_c[:] = [float(c1), float(c2), float(c3), float(c4)]
+            p.gen_v[:] = [float(vmax[1] / 2), float(vmax[0]), float(vmin[1] / 2), float(vmin[1])]
+        elif self.kind == 3:    # :692
+            p.gen_v[0] = float(torch.min(torch.minimum(rom.v_max, torch.abs(rom.v_min))))
         if sim is not None:
             p.randomize_rom_distance = int(sim.randomize_rom_distance)
             p.max_rom_distance[:] = _pad4(sim.max_rom_distance.tolist())
@@ -192,6 +207,8 @@ class TrajectoryGenerator:
             t = getattr(self, name)
             _lib.require_cuda(t, name)
             setattr(s, name, t.data_ptr())
+        if self.center is not None:
+            s.center = self.center.data_ptr()
         if sim is not None:
             s.root_states, s.env_trajectory, s.obs = sim.root_states.data_ptr(), sim.trajectory.data_ptr(), sim.obs_buf.data_ptr()
         self._p, self._s, self._sim = p, s, sim
@@ -228,6 +245,21 @@ class TrajectoryGenerator:
 
     def reset(self, z):
         raise NotImplementedError("stand-alone TrajectoryGenerator.reset is driven through CustomSim.reset / reset_idx")
+
+
+class ZeroTrajectoryGenerator(TrajectoryGenerator):
+    """rom_dynamics.py:618-624: zero input, reset envs become stationary."""
+    kind = 1
+
+
+class SquareTrajectoryGenerator(TrajectoryGenerator):
+    """rom_dynamics.py:627-675 (SingleInt2D legs :630-640; the leg boundaries are computed here in fp32, as the reference does)."""
+    kind = 2
+
+
+class CircleTrajectoryGenerator(TrajectoryGenerator):
+    """rom_dynamics.py:678-698 (SingleInt2D :686-692); `center` is re-taken from z for EVERY env whenever any env resets (:680-683)."""
+    kind = 3
 
 
 class CustomSim:

@@ -25,7 +25,8 @@ def generator_params(p, tg):
              t_high=float(tg["t_high"]), freq_low=tg["freq_low"], freq_high=tg["freq_high"], prob_stationary=tg["prob_stationary"],
              weight_sampler=tg["weight_sampler"], randomize_rom_distance=tg["randomize_rom_distance"],
              max_rom_distance=list(tg["max_rom_distance"]), zero_rom_dist_llh=tg["zero_rom_dist_llh"],
-             noise_lower=[0.0, 0.0], noise_upper=[0.0, 0.0], Kp=0.0, Kd=0.0, seed=tg["seed"], episode_length_s=20)
+             noise_lower=[0.0, 0.0], noise_upper=[0.0, 0.0], Kp=0.0, Kd=0.0, seed=tg["seed"], episode_length_s=20,
+             generator=tg.get("generator", "TrajectoryGenerator"))
     return SimpleNamespace(**d)
 
 

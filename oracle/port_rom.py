@@ -23,7 +23,7 @@ def rom_params(num_envs, **over):
              vel_max=0.3, acc_max=0.5, vel_max_rom=0.2, N=10, dN=1, t_low=1.0, t_high=2.0, freq_low=0.01, freq_high=2.0,
              prob_stationary=0.0005, weight_sampler="UniformWeightSamplerNoRamp", randomize_rom_distance=True,
              max_rom_distance=[1.0, 1.0], zero_rom_dist_llh=0.25, noise_lower=[0.0, 0.0, -0.1, -0.1],
-             noise_upper=[0.0, 0.0, 0.1, 0.1], Kp=10.0, Kd=10.0, seed=0, episode_length_s=20)
+             noise_upper=[0.0, 0.0, 0.1, 0.1], Kp=10.0, Kd=10.0, seed=0, episode_length_s=20, generator="TrajectoryGenerator")
     d.update(over)
     return SimpleNamespace(**d)
 
@@ -131,6 +131,16 @@ class RomPort:
 
     # ---- TrajectoryGenerator ------------------------------------------------------------------
     def resample(self, idx, z):                                           # rom_dynamics.py:510-545
+        kind = getattr(self.p, "generator", "TrajectoryGenerator")
+        if kind == "ZeroTrajectoryGenerator":                             # :619-620
+            self.stationary[idx] = True
+            return
+        if kind == "SquareTrajectoryGenerator":                           # :629-630
+            return
+        if kind == "CircleTrajectoryGenerator":                           # :680-683: every env is re-centred from z
+            self.center = z.detach().clone()[:, :2]
+            self.center[:, 0] -= 0.5
+            return
         if len(idx) == 0:
             return
         p, rom = self.p, self.rom
@@ -165,6 +175,27 @@ class RomPort:
 
     def get_input_t(self, t, z):                                          # rom_dynamics.py:550-566
         rom = self.rom
+        kind = getattr(self.p, "generator", "TrajectoryGenerator")
+        if kind != "TrajectoryGenerator":                                 # the subclasses override get_input_t: no resample, no clip
+            v = torch.zeros(self.N, rom.m)
+            if rom.cls != "SingleInt2D":
+                raise ValueError("port: Zero / Square / Circle generators restated for SingleInt2D")
+            if kind == "SquareTrajectoryGenerator":                       # :630-640
+                c1 = 2 / rom.v_max[1]
+                c2 = c1 + 1 / rom.v_max[0]
+                c3 = c2 + 2 / abs(rom.v_min[1])
+                c4 = c3 + 1 / abs(rom.v_min[0])
+                v[(0 <= t) & (t < c1), 1] = rom.v_max[1] / 2
+                v[(c1 <= t) & (t < c2), 0] = rom.v_max[0]
+                v[(c2 <= t) & (t < c3), 1] = rom.v_min[1] / 2
+                v[(c3 <= t) & (t < c4), 0] = rom.v_min[1]
+            elif kind == "CircleTrajectoryGenerator":                     # :686-692
+                e = z - self.center
+                v[:, 0] = -e[:, 1]
+                v[:, 1] = e[:, 0]
+                v += -(e - 0.5 * e / torch.linalg.norm(v, dim=-1, keepdim=True))
+                v = v / torch.linalg.norm(v, dim=-1, keepdim=True) * torch.min(torch.minimum(rom.v_max, torch.abs(rom.v_min)))
+            return v
         idx = torch.nonzero(t > self.t_final).reshape((-1,))
         self.resample(idx, z)
         ramp = self.ramp_v_start + (self.ramp_v_end - self.ramp_v_start) * \
@@ -197,6 +228,8 @@ class RomPort:
 
     def gen_reset_idx(self, idx, z):                                      # rom_dynamics.py:595-605
         rom, W = self.rom, self.W
+        if getattr(self.p, "generator", "") == "SquareTrajectoryGenerator":   # :673-675
+            z[:, rom.vel_inds] = 0
         self.traj[idx, :, :] = 0.0
         self.v_traj[idx, :, :] = 0.0
         self.traj[idx, -1, :] = z[idx, :]

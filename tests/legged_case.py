@@ -34,6 +34,13 @@ CASES = {
                                  {"noise.add_noise": False, "domain_rand.randomize_rom_distance": False,
                                   "trajectory_generator.weight_samp_cls": "UniformWeightSamplerNoRamp",
                                   "trajectory_generator.t_low": 0.1, "trajectory_generator.t_high": 0.3}),
+    # SURVEY 8f row 4 (generators): the deterministic TrajectoryGenerator subclasses (rom_dynamics.py:618-698)
+    "traj_flat_zero_gen": ("anymal_c_flat_trajectory", configs.TRAJECTORY_ALL_REWARD_SCALES, None, False,
+                           {"trajectory_generator.cls": "ZeroTrajectoryGenerator"}),
+    "traj_flat_square_gen": ("anymal_c_flat_trajectory", configs.TRAJECTORY_ALL_REWARD_SCALES, None, False,
+                             {"trajectory_generator.cls": "SquareTrajectoryGenerator", "domain_rand.time_between_pushes": [0.05, 0.3]}),
+    "traj_flat_circle_gen": ("anymal_c_flat_trajectory", configs.TRAJECTORY_ALL_REWARD_SCALES, None, False,
+                             {"trajectory_generator.cls": "CircleTrajectoryGenerator"}),
     "traj_rough_lstm_allterms": ("anymal_c_rough_trajectory", configs.TRAJECTORY_ALL_REWARD_SCALES, None, True,
                                  {"domain_rand.time_between_pushes": [0.05, 0.3]}),
 }
@@ -118,6 +125,7 @@ def generator_cfg(cfg):
     tg, rom, d = cfg.trajectory_generator, cfg.rom, cfg.domain_rand
     return dict(rom_dt=rom.dt, vel_max_rom=rom.v_max[0], N=tg.N, dN=tg.dN, t_low=tg.t_low, t_high=tg.t_high, freq_low=tg.freq_low,
                 freq_high=tg.freq_high, prob_stationary=tg.prob_stationary, weight_sampler=tg.weight_samp_cls, seed=tg.seed,
+                generator=tg.cls,
                 randomize_rom_distance=d.randomize_rom_distance, max_rom_distance=d.max_rom_dist,
                 zero_rom_dist_llh=d.zero_rom_distance_likelihood)
 
@@ -178,12 +186,16 @@ def _gen_port(d, g):
     d.update(gen_trajectory=g.traj, gen_v_trajectory=g.v_traj, gen_t=g.t, gen_k=g.k, gen_t_final=g.t_final, gen_weights=g.weights,
              gen_stationary=g.stationary, gen_ramp_v_end=g.ramp_v_end, gen_sin_freq=g.sin_freq,
              gen_ctr=torch.from_numpy(g.ctr.astype("int64")))
+    if hasattr(g, "center"):
+        d["gen_center"] = g.center
 
 
 def _gen_fused(d, g):
     d.update(gen_trajectory=g.trajectory, gen_v_trajectory=g.v_trajectory, gen_t=g.t, gen_k=g.k, gen_t_final=g.t_final,
              gen_weights=g.weights, gen_stationary=g.stationary_inds, gen_ramp_v_end=g.ramp_v_end, gen_sin_freq=g.sin_freq,
              gen_ctr=g.rng_ctr.long())
+    if g.center is not None:
+        d["gen_center"] = g.center
 
 
 def snapshot_port(port):

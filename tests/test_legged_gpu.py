@@ -320,7 +320,7 @@ def test_trajectory_env_error_paths():
     with pytest.raises(NotImplementedError):
         LC.make_fused(case)
     case = LC.build_case("traj_flat_allterms", 64)
-    case.cfg.trajectory_generator.cls = "CircleTrajectoryGenerator"
+    case.cfg.trajectory_generator.cls = "SpiralTrajectoryGenerator"        # not a class of rom_dynamics.py
     with pytest.raises(NotImplementedError):
         LC.make_fused(case)
     case = LC.build_case("traj_flat_allterms", 64)

@@ -169,7 +169,8 @@ def test_rom_port_tracks_unmodified_reference(over):
 
 
 @pytest.mark.reference
-@pytest.mark.parametrize("name", ["traj_flat_allterms", "traj_flat_lstm_shipped", "traj_flat_nonoise_norand", "traj_rough_lstm_allterms"])
+@pytest.mark.parametrize("name", ["traj_flat_allterms", "traj_flat_lstm_shipped", "traj_flat_nonoise_norand", "traj_rough_lstm_allterms",
+                                  "traj_flat_zero_gen", "traj_flat_square_gen", "traj_flat_circle_gen"])
 def test_trajectory_port_tracks_unmodified_reference(name):
     """oracle/port_legged_traj.py vs the reference's own AnymalTrajectory / LeggedRobotTrajectory
     (legged_robot_trajectory.py), every step, same Philox stream (env draws keyed by step, generator draws by event counter)."""
@@ -222,6 +223,9 @@ def test_trajectory_port_tracks_unmodified_reference(name):
         assert_close(g.v_traj, tg.v_trajectory, 1.0, tag + "gen v_trajectory")
         assert_close(g.weights, tg.weights, 1.0, tag + "gen weights")
         assert_close(g.t_final, tg.t_final, 1.0, tag + "gen t_final")
+        assert_close(g.v, tg.v, 1.0, tag + "gen v")
+        if hasattr(tg, "center"):
+            assert_close(g.center, tg.center, 1.0, tag + "gen center")
         for k in env.episode_sums:
             assert_close(port.episode_sums[k], env.episode_sums[k], 1.0, tag + "sum_" + k)
         if "episode" in x1:
