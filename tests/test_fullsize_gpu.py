@@ -98,3 +98,67 @@ def test_sliding_window_at_scale_matches_torch_gather():
     for i in (0, 1, 5, 9):
         want = torch.cat((start.expand(B, i, D), data[:, :T - i, :]), dim=1)       # dN == 1: slice i is the log shifted by i
         assert torch.equal(got[:, :, i * D:(i + 1) * D], want), i
+
+
+def test_trajectory_env_at_1m_envs_shard_invariance_and_identities():
+    """SURVEY 8f row 1 at 1 048 576 envs: the upper half stepped on its own (global ids) is bit-identical, generator state included;
+    flags, counters, push timers and prev_error obey the identities of legged_robot_trajectory.py:150-246."""
+    from legged_gym_dev_b200 import configs, synthetic as S
+    from legged_gym_dev_b200.legged_robot_trajectory import AnymalTrajectory
+    from legged_gym_dev_b200.physics import ReplayPhysics
+    import legged_case as LC
+    N, F = N_FULL, 2
+    tape = S.make_state_tape(N, frames=F, seed=12, device="cuda")
+    ep = S.make_episode_lengths(N, seed=4, device="cuda")
+    tpush = 0.1 * torch.rand(N, 1, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+
+    def make(n, tp, e, tp_push, offset, origins=None):
+        cfg = configs.anymal_c_flat_trajectory_cfg()
+        for k, v in configs.TRAJECTORY_ALL_REWARD_SCALES.items():
+            setattr(cfg.rewards.scales, k, v)
+        cfg.control.use_actuator_network = False
+        cfg.env.num_envs = n
+        env = AnymalTrajectory(cfg, SimpleNamespace(dt=cfg.sim.dt), None, "cuda", True, physics=ReplayPhysics(tp, device="cuda", copy=True),
+                               asset=LC.dof_limits(), seed=0, env_id_offset=offset)
+        env.episode_length_buf.copy_(e)
+        env.time_until_next_push.copy_(tp_push)
+        if origins is not None:
+            env.env_origins.copy_(origins)
+        env.reset_traj(torch.arange(n, device="cuda"))
+        return env
+
+    full = make(N, tape, ep, tpush, 0)
+    lo = N // 2
+    part = make(N - lo, _half(tape, lo, N), ep[lo:], tpush[lo:], lo, origins=full.env_origins[lo:])
+    for s in range(3):
+        ep_before, tp_before = full.episode_length_buf.clone(), full.time_until_next_push.clone()
+        traj_prev_gen = full.traj_gen.k.clone()
+        a = tape.actions[s % F]
+        obs, _, rew, rst, extras = full.step(a)
+        obs2, _, rew2, rst2, _ = part.step(a[lo:])
+        assert torch.equal(obs[lo:], obs2) and torch.equal(rew[lo:], rew2) and torch.equal(rst[lo:], rst2)
+        for name in ("trajectory", "prev_error", "time_until_next_push"):
+            assert torch.equal(getattr(full, name)[lo:], getattr(part, name)), name
+        for name in ("trajectory", "k", "t", "t_final", "weights", "rng_ctr", "stationary_inds"):
+            assert torch.equal(getattr(full.traj_gen, name)[lo:], getattr(part.traj_gen, name)), "traj_gen." + name
+        f = s % F
+        term = torch.norm(tape.contact[f][:, 0, :], dim=-1) > 1.0
+        tout = (ep_before + 1).float() > full.max_episode_length
+        assert torch.equal(rst, term | tout) and torch.equal(extras["time_outs"], tout)
+        assert torch.equal(full.episode_length_buf, torch.where(rst, torch.zeros_like(ep_before), ep_before + 1))
+        # push timers: decremented by dt; the ones that fired were redrawn inside [0.5, 10) s
+        dec = tp_before - 0.02
+        fired = (dec <= 0).reshape(-1)
+        assert torch.equal(full.time_until_next_push[~fired], dec[~fired])
+        tf = full.time_until_next_push[fired]
+        assert bool((tf >= 0.5).all()) and bool((tf < 10.0).all()) and int(fired.sum()) > 0
+        # prev_error only changes for envs that reset, where it is (stale trajectory knot - new root position)^2
+        want = torch.square(full.trajectory[rst, 0, :] - full.root_states[rst, :2])
+        assert torch.allclose(full.prev_error[rst], want, rtol=1e-5, atol=1e-6)
+        # generators of reset envs restart at k = 0 after their N warm-up knots; the others advance by at most one knot
+        assert bool((full.traj_gen.k[rst] == 0).all())
+        dk = full.traj_gen.k[~rst] - traj_prev_gen[~rst]
+        assert bool(((dk == 0) | (dk == 1)).all())
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert float(obs.abs().max()) <= full.cfg.normalization.clip_observations
+    assert int(full.reset_buf.sum()) > 0
