@@ -191,7 +191,10 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
     s.sums = c.take<float>(static_cast<size_t>(K > 0 ? K : 1) * TILE);
     // the obs tile reuses the contact tile when it fits (B*3 >= OW): contact forces are dead after phase W's contact pass
     constexpr int OW = ObsLayout<TRAJ>::OW;
-    s.obs = (PP_ALIAS_OBS && B * 3 >= OW) ? s.contact : c.take<float>(TILE * OW);
+    // (trajectory layout, 65 columns: the dof tile sits right in front of the contact tile and is dead at the same barrier, so the
+    //  pair [dof | contact] = 24 + 3B floats per env hosts the observation tile)
+    static_assert((TILE * 24 * sizeof(float)) % 16 == 0, "dof and contact tiles must be contiguous");
+    s.obs = (PP_ALIAS_OBS && B * 3 >= OW) ? s.contact : (PP_ALIAS_OBS && TRAJ && 24 + B * 3 >= OW) ? s.dof : c.take<float>(TILE * OW);
     s.traj = TRAJ ? c.take<float>(TILE * TRAJ_W) : nullptr;
     s.perr = TRAJ ? c.take<float>(TILE * 2) : nullptr;
     s.tpush = TRAJ ? c.take<float>(TILE) : nullptr;

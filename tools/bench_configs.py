@@ -362,6 +362,7 @@ def run_all(device="cuda", peak=6535.7, quick=False):
                          ("cfg3_rough_lstm_262144", rough_lstm, dict(device=device, peak=peak, num_envs=16384 if quick else 262144, steps=20)),
                          ("next1_trajectory_env_4096", trajectory_env, dict(device=device, peak=peak)),
                          ("next1_trajectory_env_262144", trajectory_env, dict(device=device, peak=peak, num_envs=16384 if quick else 262144, steps=20)),
+                         ("next1_trajectory_env_1048576", trajectory_env, dict(device=device, peak=peak, num_envs=16384 if quick else (1 << 20), steps=20)),
                          ("cfg4_rom_rollout", rom_rollout, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20))),
                          ("cfg4b_tube_dataset", tube_dataset, dict(device=device, peak=peak, num_envs=16384 if quick else 262144)),
                          ("cfg5_gae_update", gae_update, dict(device=device, peak=peak))):
