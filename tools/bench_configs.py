@@ -355,6 +355,29 @@ def gae_update(num_envs=4096, T=24, device="cuda", peak=6535.7):
                      "(fused gather/loss/clip+Adam kernels + TF32 cuBLAS GEMMs for the training forward/backward)")
 
 
+def cpu_port_baselines(quick=False):
+    """The reference's torch CPU path beside cfg 3 and the trajectory env (measured N only, no extrapolation): the oracle
+    ports (torch.rand like the reference) on all host cores.  The only function of this file, with rom_per_call, that touches oracle/."""
+    import legged_case as LC
+    torch.set_num_threads(os.cpu_count() or 1)
+    out = {}
+    for key, case_name, n, steps in (("cfg3_rough_lstm_cpu_port", "rough_lstm_allterms", 4096 if quick else 16384, 5),
+                                     ("next1_trajectory_env_cpu_port", "traj_flat_allterms", 4096, 20)):
+        case = LC.build_case(case_name, n, frames=4)
+        port, phys = LC.make_port(case, rng="torch")
+        if case.traj:
+            port.gen.reset_traj(torch.arange(n), port.proj_z())
+        for s in range(2):
+            port.step(case.tape.actions[s % 4], phys)
+        t0 = time.perf_counter()
+        for s in range(steps):
+            port.step(case.tape.actions[s % 4], phys)
+        dt = time.perf_counter() - t0
+        out[key] = dict(num_envs=n, steps=steps, ms_per_step=1e3 * dt / steps, env_steps_per_s=n * steps / dt, cores=torch.get_num_threads(),
+                        kind="port", sample=f"oracle port of case {case_name}, {n} envs x {steps} steps, {dt:.2f} s")
+    return out
+
+
 def run_all(device="cuda", peak=6535.7, quick=False):
     out = {}
     for name, fn, kw in (("cfg1_rom_per_call", rom_per_call, dict(device=device, loop_steps=200 if quick else 1000)),
@@ -371,6 +394,10 @@ def run_all(device="cuda", peak=6535.7, quick=False):
         except Exception as e:   # an extra must never take the headline line down
             out[name] = dict(error=f"{type(e).__name__}: {e}")
         torch.cuda.empty_cache()
+    try:
+        out.update(cpu_port_baselines(quick=quick))
+    except Exception as e:
+        out["cpu_port_baselines"] = dict(error=f"{type(e).__name__}: {e}")
     return out
 
 
