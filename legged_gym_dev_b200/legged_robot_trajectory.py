@@ -18,14 +18,13 @@ with no host synchronisation: the reference's `torch.any(need_push)`, `nonzero` 
   * pushes are per-env timers decremented by dt every step (:169-178).
 There is no CPU path.
 """
+import numpy as np
 import torch
 
 from . import _lib
-from .legged_robot import LeggedRobot, ActuatorNetMixin
-from .params import flatten_legged_cfg
 from . import rom as R
-
-import numpy as np
+from .legged_robot import LeggedRobot, ActuatorNetMixin
+from .params import flatten_legged_cfg, TERM_ID
 
 _ROM_CLASSES = {"SingleInt2D": R.SingleInt2D, "DoubleInt2D": R.DoubleInt2D}
 _T_SAMPLERS = {"UniformSampleHoldDT": R.UniformSampleHoldDT}
@@ -205,7 +204,6 @@ class LeggedRobotTrajectory(LeggedRobot):
         for key in list(self.reward_scales.keys()):
             self.reward_scales[key] = getattr(self.cfg.rewards.scales, key) * getattr(cur.rewards, key)[ind] * self.dt
         # push the new numbers into the POD structs the kernels read
-        from .params import TERM_ID
         for key, v in self.reward_scales.items():
             self._pod.reward_scale[TERM_ID[key]] = v
         self._pod.tracking_sigma = p.tracking_sigma

@@ -331,3 +331,50 @@ def test_trajectory_env_error_paths():
     assert not hasattr(env, "commands") and env.trajectory.shape == (64, 10, 2) and env.obs_buf.shape == (64, 65)
     with pytest.raises(RuntimeError):
         env.step(torch.zeros(64, 12))          # CPU tensor: no fallback
+
+
+def test_trajectory_env_curriculum_rewrites_the_kernel_parameters():
+    """update_command_curriculum (legged_robot_trajectory.py:519-555) is a host-side rewrite of the numbers the kernels read: an env
+    moved to curriculum stage 1 must equal, bit for bit, an env built from the stage-1 values directly; the stage advances when
+    common_step_counter hits curriculum_steps[stage] (:414-417)."""
+    from legged_gym_dev_b200.configs import Cfg
+    ca, cb = LC.build_case("traj_flat_allterms", 512), LC.build_case("traj_flat_allterms", 512)
+    keys = [k for k, v in vars(ca.cfg.rewards.scales).items() if v != 0]
+    ca.cfg.curriculum = Cfg(use_curriculum=True, curriculum_steps=[10 ** 9, 10 ** 9], push=Cfg(magnitude=[0.1, 0.5], time=[3, 2]),
+                            max_rom_distance=[0.5, 0.8], zero_rom_distance_likelihood=[1.0, 1.0], rom=Cfg(z=[1, 1], v=[0.5, 0.75]),
+                            trajectory_generator=Cfg(t_low=[3, 2], t_high=[3, 2]), sigma=Cfg(tracking_rom=[1.0, 0.8]),
+                            rewards=Cfg(**{k: [1.0, 0.8] for k in keys}))
+    b = cb.cfg
+    b.rom.v_min, b.rom.v_max = [v * 0.75 for v in b.rom.v_min], [v * 0.75 for v in b.rom.v_max]
+    b.trajectory_generator.t_low, b.trajectory_generator.t_high = b.trajectory_generator.t_low * 2, b.trajectory_generator.t_high * 2
+    b.rewards.tracking_sigma = b.rewards.tracking_sigma * 0.8
+    b.domain_rand.max_rom_dist = [v * 0.8 for v in b.domain_rand.max_rom_dist]
+    for k in keys:
+        setattr(b.rewards.scales, k, getattr(b.rewards.scales, k) * 0.8)
+    ea, eb = LC.make_fused(ca), LC.make_fused(cb)
+    assert ea.curriculum_state == 0 and abs(ea._pod.tracking_sigma - 0.25) < 1e-7
+    ea.curriculum_state = 1
+    ea.update_command_curriculum()
+    assert abs(ea._pod.tracking_sigma - 0.2) < 1e-7
+    ids = torch.arange(512, device="cuda")
+    # the construction-time generator draw used the stage-0 bounds in A: give both the same ramp end points
+    ea.traj_gen.ramp_v_end.copy_(eb.traj_gen.ramp_v_end)
+    ea.reset_traj(ids)
+    eb.reset_traj(ids)
+    for s in range(10):
+        a = ca.tape.actions[s % 8].cuda()
+        ea.step(a)
+        eb.step(a)
+        for name in ("obs_buf", "rew_buf", "reset_buf", "prev_error", "trajectory"):
+            assert torch.equal(getattr(ea, name), getattr(eb, name)), f"step {s}: {name}"
+        assert torch.equal(ea.traj_gen.trajectory, eb.traj_gen.trajectory) and torch.equal(ea._sums, eb._sums)
+    # the trigger itself
+    cc = LC.build_case("traj_flat_allterms", 64)
+    cc.cfg.curriculum = ca.cfg.curriculum.clone()
+    cc.cfg.curriculum.curriculum_steps = [3, 10 ** 9]
+    ec = LC.make_fused(cc)
+    ec.reset_traj(torch.arange(64, device="cuda"))
+    for s in range(4):
+        ec.step(cc.tape.actions[s].cuda())
+        assert ec.curriculum_state == (1 if s >= 2 else 0)
+    assert abs(ec._pod.tracking_sigma - 0.2) < 1e-7
