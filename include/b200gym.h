@@ -211,6 +211,11 @@ int b200gym_rom_reset_from_root(const B200RomParams* p, const B200RomState* s, c
                                 int32_t root_stride, const float* any_reset, int64_t env_id_offset, void* stream);
 /* DoubleSingleTracking.__call__ (controllers.py:87-92) with DoubleInt2D.clip_v_z (rom_dynamics.py:234-250). */
 int b200gym_rom_tracking_policy(const B200RomParams* p, const float* obs, float* action, void* stream);
+/* RaibertHeuristic.raibert_policy (deep_tube_learning/controllers.py:38-73, the hopper's tracking controller — SURVEY 8f row 3):
+ * obs [n, obs_stride >= 10] = (pos err x, y, vel err x, y, desired vel x, y, quat xyzw) -> action [n, 4] = desired orientation
+ * quaternion (w, x, y, z) = omega_to_quat(clamped pitch, clamped roll, current yaw). */
+int b200gym_raibert_policy(const float* obs, int32_t obs_stride, int64_t n, float Kp, float Kv, float Kff, float clip_pos, float clip_vel,
+                           float clip_ang, float* action, void* stream);
 /* One epoch of data_collection_trajectory.py:104-149 as ONE persistent launch: reset all envs, then T ROM steps of
  * {policy -> CustomSim.step} with generator state in registers; logs x [N,T+1,model_n] (may be NULL), z, pz_x
  * [N,T+1,rom_n], v [N,T,2], done [N,T] (bool).  obs_io [N,8]: in = observation the first action is computed from

@@ -129,6 +129,8 @@ def lib():
     L.b200gym_rom_reset.argtypes = [rp, rs, vp, C.c_int64, vp]
     L.b200gym_rom_reset_from_root.argtypes = [rp, rs, vp, vp, C.c_int32, vp, C.c_int64, vp]
     L.b200gym_rom_tracking_policy.argtypes = [rp, vp, vp, vp]
+    L.b200gym_raibert_policy.argtypes = [vp, C.c_int32, C.c_int64, f32, f32, f32, f32, f32, f32, vp, vp]
+    L.b200gym_raibert_policy.restype = C.c_int
     L.b200gym_rom_rollout.argtypes = [rp, rs, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int64, vp]
     for name in ("b200gym_rom_init", "b200gym_rom_step", "b200gym_rom_reset", "b200gym_rom_reset_from_root", "b200gym_rom_tracking_policy",
                  "b200gym_rom_rollout"):

@@ -479,6 +479,32 @@ __global__ void rom_policy_kernel(const __grid_constant__ B200RomParams p, const
     *reinterpret_cast<float2*>(action + static_cast<size_t>(i) * 2) = make_float2(u[0], u[1]);
 }
 
+// RaibertHeuristic.raibert_policy (deep_tube_learning/controllers.py:38-73): position / velocity errors -> clamped pitch and roll
+// commands -> desired orientation quaternion (w, x, y, z) at the robot's current yaw.  One thread per env; pure elementwise.
+__global__ void raibert_policy_kernel(const float* __restrict__ obs, int stride, long long n, float Kp, float Kv, float Kff, float clip_pos,
+                                      float clip_vel, float clip_ang, float* __restrict__ action) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (i >= n) return;
+    const float* o = obs + i * stride;
+    const float pex = o[0], pey = -o[1], evx = -o[2], evy = o[3], dvx = o[4], dvy = -o[5];
+    const float pitch_pos = clampf(mul_rn(-Kp, pex), -clip_pos, clip_pos), roll_pos = clampf(mul_rn(-Kp, pey), -clip_pos, clip_pos);
+    const float vx = clampf(add_rn(mul_rn(-Kv, evx), mul_rn(Kff, dvx)), -clip_vel, clip_vel);
+    const float vy = clampf(add_rn(mul_rn(-Kv, evy), mul_rn(Kff, dvy)), -clip_vel, clip_vel);
+    const float pitch = clampf(add_rn(pitch_pos, vx), -clip_ang, clip_ang), roll = clampf(add_rn(roll_pos, vy), -clip_ang, clip_ang);
+    const float qx = o[6], qy = o[7], qz = o[8], qw = o[9];                                    // quat_to_yaw, :75-81
+    const float yaw = atan2f(mul_rn(2.0f, add_rn(mul_rn(qw, qz), mul_rn(qx, qy))),
+                             sub_rn(1.0f, mul_rn(2.0f, add_rn(mul_rn(qy, qy), mul_rn(qz, qz)))));
+    const float cy = cosf(yaw * 0.5f), sy = sinf(yaw * 0.5f), cp = cosf(pitch * 0.5f), sp = sinf(pitch * 0.5f);   // omega_to_quat, :23-36
+    const float cr = cosf(roll * 0.5f), sr = sinf(roll * 0.5f);
+    const float w = add_rn(mul_rn(mul_rn(cr, cp), cy), mul_rn(mul_rn(sr, sp), sy));
+    const float x = sub_rn(mul_rn(mul_rn(sr, cp), cy), mul_rn(mul_rn(cr, sp), sy));
+    const float y = add_rn(mul_rn(mul_rn(cr, sp), cy), mul_rn(mul_rn(sr, cp), sy));
+    const float z = sub_rn(mul_rn(mul_rn(cr, cp), sy), mul_rn(mul_rn(sr, sp), cy));
+    *reinterpret_cast<float4*>(action + i * 4) = make_float4(w, x, y, z);
+}
+
 // ---- persistent rollout: one data-collection epoch ---------------------------------------------------
 constexpr int RB = 128;   // envs (threads) per CTA
 constexpr int TB = 8;     // timesteps staged per flush
@@ -679,6 +705,16 @@ int b200gym_rom_tracking_policy(const B200RomParams* p, const float* obs, float*
     B200_REQUIRE(b200_aligned16(obs) && b200_aligned16(action), B200GYM_EALIGN, "rom_tracking_policy: pointers must be 16-byte aligned");
     b200_launch_pdl(p->num_envs, rom_policy_kernel, dim3((p->num_envs + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), *p, obs, action);
     B200_LAUNCH_CHECK("rom_tracking_policy");
+    return B200GYM_OK;
+}
+
+int b200gym_raibert_policy(const float* obs, int32_t obs_stride, int64_t n, float Kp, float Kv, float Kff, float clip_pos, float clip_vel,
+                           float clip_ang, float* action, void* stream) {
+    B200_REQUIRE(obs && action && n > 0 && obs_stride >= 10, B200GYM_EINVAL, "raibert_policy: need obs [n, >= 10] and an action buffer");
+    B200_REQUIRE(b200_aligned16(action), B200GYM_EALIGN, "raibert_policy: action must be 16-byte aligned");
+    b200_launch_pdl(static_cast<int>(n < (1 << 30) ? n : (1 << 30)), raibert_policy_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0,
+                    static_cast<cudaStream_t>(stream), obs, obs_stride, n, Kp, Kv, Kff, clip_pos, clip_vel, clip_ang, action);
+    B200_LAUNCH_CHECK("raibert_policy");
     return B200GYM_OK;
 }
 

@@ -370,3 +370,32 @@ class DoubleSingleTracking:
         _lib.check(self.lib.b200gym_rom_tracking_policy(self._p, _lib.ptr(obs), _lib.ptr(self._action),
                                                         _lib.stream_ptr(obs.device)), "rom_tracking_policy")
         return self._action
+
+
+class RaibertHeuristic:
+    """deep_tube_learning/controllers.py:4-81 (the hopper's tracking controller): same constructor (`cfg.controller.{K_p, K_v, K_ff,
+    clip_value_pos, clip_value_vel, clip_value_total}`), `get_inference_policy(device)` and static `raibert_policy(...)`; the policy
+    is one launch of `b200gym_raibert_policy`."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        c = cfg.controller
+        self.K_p, self.K_v, self.K_ff = c.K_p, c.K_v, c.K_ff
+        self.clip_value_pos, self.clip_value_vel, self.clip_value_total = c.clip_value_pos, c.clip_value_vel, c.clip_value_total
+
+    def get_inference_policy(self, device):
+        def policy(obs):
+            return RaibertHeuristic.raibert_policy(obs, self.K_p, self.K_v, self.K_ff, self.clip_value_pos, self.clip_value_vel,
+                                                   self.clip_value_total)
+        return policy
+
+    @staticmethod
+    def raibert_policy(obs, Kp, Kv, K_ff, clip_pos, clip_vel, clip_ang):
+        _lib.require_cuda(obs, "obs")
+        if obs.dim() != 2 or obs.shape[1] < 10 or obs.dtype != torch.float32:
+            raise ValueError("raibert_policy: obs must be a float32 [n, >= 10] tensor")
+        out = torch.empty(obs.shape[0], 4, device=obs.device)
+        _lib.check(_lib.lib().b200gym_raibert_policy(_lib.ptr(obs), obs.shape[1], obs.shape[0], float(Kp), float(Kv), float(K_ff),
+                                                     float(clip_pos), float(clip_vel), float(clip_ang), _lib.ptr(out),
+                                                     _lib.stream_ptr(obs.device)), "raibert_policy")
+        return out
