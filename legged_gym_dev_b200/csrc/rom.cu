@@ -416,8 +416,24 @@ __global__ void __launch_bounds__(128) rom_reset_root_kernel(const __grid_consta
         for (int c = 0; c < RN; ++c) pz[c] = root[static_cast<size_t>(i) * stride + c];
         traj_reset(p, g, pz, w, genv, true);
         store_gen(s, i, w, g);
-        return;
     }
+}
+
+// The envs that do NOT reset (the other half of the call above, as its own kernel: without the horizon windows in registers it needs
+// a quarter of the registers and runs at full occupancy).
+template <int RN, int W>
+__global__ void __launch_bounds__(256, 4) rom_reset_root_others_kernel(const __grid_constant__ B200RomParams p, const __grid_constant__ B200RomState s,
+                                                                    const uint8_t* __restrict__ mask, const float* __restrict__ root, int stride,
+                                                                    const float* __restrict__ any_reset, long long env_off) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (i >= p.num_envs) return;
+    if (any_reset && *any_reset == 0.0f) return;
+    if (mask[i] != 0) return;
+    const int w = p.window;
+    const uint64_t genv = static_cast<uint64_t>(env_off + i);
+    Gen<RN, W> g;
     // An env that does not reset only takes part in the warm-up's input evaluations (rom_dynamics.py:577-580): resamples that are
     // due, then v.  Its clock does not move, so once t <= t_final every further evaluation repeats the same v; the horizon windows
     // are neither read (SingleInt2D bounds are state-independent) nor written: ~110 B instead of ~600 B of traffic for such an env.
@@ -690,10 +706,14 @@ int b200gym_rom_reset_from_root(const B200RomParams* p, const B200RomState* s, c
     B200_REQUIRE(p->rom_type == 0, B200GYM_EINVAL, "rom_reset_from_root: proj_z is implemented for SingleInt2D (first two root columns)");
     const int grid = (p->num_envs + 127) / 128;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (p->window == 10 && p->dN == 1)
+    const int grid2 = (p->num_envs + 255) / 256;
+    if (p->window == 10 && p->dN == 1) {
+        b200_launch_pdl(p->num_envs, rom_reset_root_others_kernel<2, 10>, dim3(grid2), dim3(256), 0, st, *p, *s, reset_mask, root, root_stride, any_reset, env_id_offset);
         b200_launch_pdl(p->num_envs, rom_reset_root_kernel<2, 10>, dim3(grid), dim3(128), 0, st, *p, *s, reset_mask, root, root_stride, any_reset, env_id_offset);
-    else
+    } else {
+        b200_launch_pdl(p->num_envs, rom_reset_root_others_kernel<2, WMAXR>, dim3(grid2), dim3(256), 0, st, *p, *s, reset_mask, root, root_stride, any_reset, env_id_offset);
         b200_launch_pdl(p->num_envs, rom_reset_root_kernel<2, WMAXR>, dim3(grid), dim3(128), 0, st, *p, *s, reset_mask, root, root_stride, any_reset, env_id_offset);
+    }
     B200_LAUNCH_CHECK("rom_reset_from_root");
     return B200GYM_OK;
 }
