@@ -251,7 +251,8 @@ class LeggedRobot:
         if b is None:
             b = _lib.LeggedBuffersPOD()
             t = dict(actions=self.actions, torques=self.torques, last_actions=self.last_actions,
-                     last_dof_vel=self.last_dof_vel, last_root_vel=self.last_root_vel, commands=self.commands,
+                     last_dof_vel=self.last_dof_vel, last_root_vel=self.last_root_vel,
+                     commands=getattr(self, "commands", getattr(self, "_commands_unused", None)),
                      feet_air_time=self.feet_air_time, last_contacts=self.last_contacts,
                      episode_length_buf=self.episode_length_buf, reset_buf=self.reset_buf, time_out_buf=self.time_out_buf,
                      rew_buf=self.rew_buf, episode_sums=self._sums, obs_buf=self.obs_buf, base_lin_vel=self.base_lin_vel,

@@ -126,7 +126,9 @@ class LeggedRobotTrajectory(LeggedRobot):
         if p.measure_heights:
             nv[45 + ts:] = p.noise_height
         self.noise_scale_vec = nv
-        del self.commands, self.commands_scale                           # :621-622
+        # :621-622: the class has no commands; the fused launcher still wants a valid pointer in that (ignored) slot
+        self._commands_unused = self.commands
+        del self.commands, self.commands_scale
         # the generator writes its interpolated window (get_trajectory, :410) straight into self.trajectory
         g = self.traj_gen
         g._s.env_trajectory = self.trajectory.data_ptr()
@@ -136,12 +138,8 @@ class LeggedRobotTrajectory(LeggedRobot):
 
     def _buffers(self):
         first = getattr(self, "_buf_pod", None) is None
-        if first:
-            # the fused kernel ignores `commands` in traj_mode, but the launcher wants a valid pointer for every slot
-            self.commands = torch.zeros(self.num_envs, 4, device=self.device)
         b = super()._buffers()
         if first:
-            del self.commands
             b.trajectory, b.prev_error = self.trajectory.data_ptr(), self.prev_error.data_ptr()
             b.time_until_next_push = self.time_until_next_push.data_ptr()
         return b

@@ -12,7 +12,7 @@ from types import SimpleNamespace
 import torch
 
 from . import philox as P
-from .port_legged import LeggedPort, TERMS
+from .port_legged import LeggedPort
 from .port_rom import RomPort
 
 

@@ -153,11 +153,11 @@ def make_port(case, rng="philox", env_id_offset=0):
         origins = torch.zeros(N, 3)
         origins[:, 0] = case.cfg.env.env_spacing * xx.flatten()[:N]
         origins[:, 1] = case.cfg.env.env_spacing * yy.flatten()[:N]
-    kw = {}
+    make = LeggedPort
     if case.traj:
         from oracle.port_legged_traj import LeggedTrajPort
-        LeggedPort = lambda p_, r, d, c, **k: LeggedTrajPort(p_, generator_cfg(case.cfg), r, d, c, case.tpush, **k)   # noqa: F811
-    port = LeggedPort(p, case.tape.root[0].clone(), case.tape.dof[0, 0].clone(), case.tape.contact[0].clone(),
+        make = lambda p_, r, d, c, **k: LeggedTrajPort(p_, generator_cfg(case.cfg), r, d, c, case.tpush, **k)
+    port = make(p, case.tape.root[0].clone(), case.tape.dof[0, 0].clone(), case.tape.contact[0].clone(),
                       env_origins=origins, height_samples=t.get("height_samples"),
                       terrain_levels=clone(t.get("terrain_levels")), terrain_types=clone(t.get("terrain_types")),
                       terrain_origins=clone(t.get("terrain_origins")), lstm=w, episode_length_buf=case.ep, rng=rng,
