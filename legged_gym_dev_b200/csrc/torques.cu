@@ -11,6 +11,9 @@
 #include "philox.cuh"
 #include "../../include/b200gym.h"
 
+#ifndef PD_MAX_CTAS
+#define PD_MAX_CTAS 0      // 0 = one CTA per 256 float4 chunks (no cap); see profiles/ for the A/B of capped grids
+#endif
 #ifndef LSTM_MINBLOCKS
 #define LSTM_MINBLOCKS 8
 #endif
@@ -28,7 +31,7 @@ __global__ void __launch_bounds__(256) pd_torques_kernel(const __grid_constant__
                                                          const float4* __restrict__ dof_state,
                                                          const float4* __restrict__ last_dof_vel,
                                                          float4* __restrict__ torques, int n4) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     // Per-dof constants as float4 rows for the three dof quads {0-3, 4-7, 8-11}: a thread's quad is i % 3, i.e. lane-dependent.
     // Indexing the __grid_constant__ arrays with it costs 16 constant-bank loads per thread, each replayed for the 3 distinct
     // addresses of a warp (the kernel was MIO-throttled at 79 % of HBM); four 128-bit shared-memory reads replace them.
@@ -41,7 +44,8 @@ __global__ void __launch_bounds__(256) pd_torques_kernel(const __grid_constant__
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
-    if (i >= n4) return;
+    // grid-stride: large problems run on a capped grid (PD_MAX_CTAS) of long-lived CTAs instead of ~50 000 64-byte-per-thread CTAs
+    for (int i = i0; i < n4; i += gridDim.x * blockDim.x) {
     float4 a4 = ldg_stream4(actions + i);
     const float4 s0 = ldg_stream4(dof_state + 2 * i), s1 = ldg_stream4(dof_state + 2 * i + 1);
     float a[4] = {a4.x, a4.y, a4.z, a4.w};
@@ -71,6 +75,7 @@ __global__ void __launch_bounds__(256) pd_torques_kernel(const __grid_constant__
     }
     stg_stream4(torques + i, make_float4(t[0], t[1], t[2], t[3]));
     if (actions_clipped) actions_clipped[i] = make_float4(a[0], a[1], a[2], a[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -406,7 +411,13 @@ int b200gym_pd_torques(const B200LeggedParams* p, const float* actions, float* a
                      b200_aligned16(actions_clipped) && b200_aligned16(last_dof_vel),
                  B200GYM_EALIGN, "pd_torques: pointers must be 16-byte aligned");
     const int n4 = p->num_envs * ND / 4;
-    b200_launch_pdl(p->num_envs, pd_torques_kernel, dim3((n4 + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), *p,
+    static int max_ctas = -1;
+    if (max_ctas < 0) {
+        const char* e = getenv("B200GYM_PD_MAX_CTAS");
+        max_ctas = e ? atoi(e) : PD_MAX_CTAS;
+    }
+    const int want = (n4 + 255) / 256, grid = (max_ctas > 0 && want > max_ctas) ? max_ctas : want;
+    b200_launch_pdl(p->num_envs, pd_torques_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), *p,
                     reinterpret_cast<const float4*>(actions), reinterpret_cast<float4*>(actions_clipped),
                     reinterpret_cast<const float4*>(dof_state), reinterpret_cast<const float4*>(last_dof_vel),
                     reinterpret_cast<float4*>(torques), n4);
