@@ -224,6 +224,54 @@ int b200gym_rom_rollout(const B200RomParams* p, const B200RomState* s, float* ob
                         float* v, uint8_t* done, int64_t env_id_offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Group M, SURVEY 8f row 4 — the whole RomDynamics family (trajopt/rom_dynamics.py:182-438) behind one generic generator.
+ * The kernels above are the register-resident fast path of the shipped data-generation configs (SingleInt2D / DoubleInt2D,
+ * 2 inputs); the entry points below cover every rom class — state dimension up to 6, up to 3 inputs — with the same
+ * state tensors (B200RomState, [N, m] / [N, window+1, n] with the class's own n and m), the same draw events and, for
+ * rom types 0 / 1, bit-identical results to the kernels above.
+ * ---------------------------------------------------------------------------------------------- */
+#define B200GYM_ROM_UNICYCLE 2                  /* rom_dynamics.py:263-305  n=3 m=2  [x, y, theta] / [v, omega] */
+#define B200GYM_ROM_LATERAL_UNICYCLE 3          /* rom_dynamics.py:307-333  n=3 m=3  [x, y, theta] / [v, v_perp, omega] */
+#define B200GYM_ROM_EXTENDED_UNICYCLE 4         /* rom_dynamics.py:336-394  n=5 m=2  [x, y, theta, v, omega] / [a, alpha] */
+#define B200GYM_ROM_EXTENDED_LATERAL_UNICYCLE 5 /* rom_dynamics.py:397-438  n=6 m=3  [x, y, theta, v, v_perp, omega] / [a, a_perp, alpha] */
+#define B200GYM_ROM_NUM_TYPES 6
+
+typedef struct B200RomFamilyParams {
+    int32_t num_envs, rom_type, window, dN; /* window = N*dN (rom_dynamics.py:485-486) */
+    float rom_dt, dt_loop;
+    float z_min[8], z_max[8], v_min[4], v_max[4]; /* RomDynamics.__init__ bounds (:16-33), first n / m entries used */
+    float t_low, t_span, freq_low, freq_high, prob_stationary;
+    int32_t weight_zero_col; /* as in B200RomParams */
+    uint32_t seed_lo, seed_hi;
+} B200RomFamilyParams;
+
+/* RomDynamics.f (:192,:224,:273-278,:311-316,:345-352,:406-414): z [n_rows, n], v [n_rows, m] -> z_next [n_rows, n]. */
+int b200gym_romfam_f(int32_t rom_type, float dt, const float* z, const float* v, float* z_next, int64_t n_rows, void* stream);
+/* RomDynamics.des_pose_vel (:198,:230,:286-290,:318-322,:354-358,:416-420; incl. LateralUnicycle's om = v[:, 1]):
+ * pose [n_rows, 3] = (x, y, yaw), vel [n_rows, 3] = (xdot, ydot, yawdot). */
+int b200gym_romfam_des_pose_vel(int32_t rom_type, const float* z, const float* v, float* pose, float* vel, int64_t n_rows, void* stream);
+/* RomDynamics.compute_state_dependent_input_bounds (:106-107,:234-246,:367-379) and, when v != NULL, clip_v_z (:201,:248-250,
+ * :292,:381-383): v_lo / v_hi [n_rows, m] (either may be NULL), v_clipped [n_rows, m].  Uses p->rom_type, rom_dt, z_*, v_*. */
+int b200gym_romfam_input_bounds(const B200RomFamilyParams* p, const float* z, const float* v, float* v_lo, float* v_hi, float* v_clipped,
+                                int64_t n_rows, void* stream);
+/* RomDynamics.proj_z (:195,:227,:280-284,:360-365,:422-427): x [n_rows, 13] = (pos 3, quat xyzw 4, lin vel 3, ang vel 3) ->
+ * z [n_rows, n]; yaw = last angle of scipy's Rotation.as_euler('xyz'), evaluated on the device in fp32. */
+int b200gym_romfam_proj_z(int32_t rom_type, const float* x, float* z, int64_t n_rows, void* stream);
+/* TrajectoryGenerator.__init__ draw of ramp_v_end (:495) for m inputs. */
+int b200gym_romfam_gen_init(const B200RomFamilyParams* p, const B200RomState* s, int64_t env_id_offset, void* stream);
+/* TrajectoryGenerator.reset_idx(idx, z) (:595-605): z [N, n]; reset_mask uint8 [N] or NULL = reset(z).  Envs outside the mask
+ * take part in the warm-up's input evaluations (resamples that are due, self.v), as in step_rom_idx (:577-580). */
+int b200gym_romfam_gen_reset(const B200RomFamilyParams* p, const B200RomState* s, const float* z, const uint8_t* reset_mask,
+                             int64_t env_id_offset, void* stream);
+/* TrajectoryGenerator.step_idx(idx) (:571-590); step_mask uint8 [N] or NULL = step(). */
+int b200gym_romfam_gen_step(const B200RomFamilyParams* p, const B200RomState* s, const uint8_t* step_mask, int64_t env_id_offset,
+                            void* stream);
+/* TrajectoryGenerator.get_input_t(t, z) (:560-566) with caller-supplied clocks t [N] and states z [N, n] (the open-loop use of
+ * trajopt/trajectory_gen.py:35-41): resamples the envs with t > t_final, returns the weighted clipped input in v_out [N, m]. */
+int b200gym_romfam_gen_input(const B200RomFamilyParams* p, const B200RomState* s, const float* t, const float* z, float* v_out,
+                             int64_t env_id_offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Group G — rsl_rl rollout storage + PPO update (rsl_rl v1.0.2, a fork of which the reference imports at
  * legged_gym/utils/task_registry.py:37-38; source NOT in /root/reference: arithmetic restated)
  * ---------------------------------------------------------------------------------------------- */

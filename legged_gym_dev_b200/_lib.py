@@ -77,6 +77,15 @@ class RomParamsPOD(C.Structure):
     ]
 
 
+class RomFamilyParamsPOD(C.Structure):
+    _fields_ = [
+        ("num_envs", i32), ("rom_type", i32), ("window", i32), ("dN", i32), ("rom_dt", f32), ("dt_loop", f32),
+        ("z_min", f32 * 8), ("z_max", f32 * 8), ("v_min", f32 * 4), ("v_max", f32 * 4),
+        ("t_low", f32), ("t_span", f32), ("freq_low", f32), ("freq_high", f32), ("prob_stationary", f32),
+        ("weight_zero_col", i32), ("seed_lo", u32), ("seed_hi", u32),
+    ]
+
+
 _ROM_FIELDS = ["root_states", "trajectory", "v_trajectory", "v", "t", "k", "t_final", "weights", "sample_hold_input",
                "extreme_input", "ramp_v_start", "ramp_v_end", "ramp_t_start", "sin_mag", "sin_freq", "sin_off", "sin_mean",
                "stationary_inds", "rng_ctr", "env_trajectory", "obs", "center"]
@@ -135,6 +144,18 @@ def lib():
     for name in ("b200gym_rom_init", "b200gym_rom_step", "b200gym_rom_reset", "b200gym_rom_reset_from_root", "b200gym_rom_tracking_policy",
                  "b200gym_rom_rollout"):
         getattr(L, name).restype = C.c_int
+    fp = C.POINTER(RomFamilyParamsPOD)
+    L.b200gym_romfam_f.argtypes = [C.c_int32, f32, vp, vp, vp, C.c_int64, vp]
+    L.b200gym_romfam_des_pose_vel.argtypes = [C.c_int32, vp, vp, vp, vp, C.c_int64, vp]
+    L.b200gym_romfam_input_bounds.argtypes = [fp, vp, vp, vp, vp, vp, C.c_int64, vp]
+    L.b200gym_romfam_proj_z.argtypes = [C.c_int32, vp, vp, C.c_int64, vp]
+    L.b200gym_romfam_gen_init.argtypes = [fp, rs, C.c_int64, vp]
+    L.b200gym_romfam_gen_reset.argtypes = [fp, rs, vp, vp, C.c_int64, vp]
+    L.b200gym_romfam_gen_step.argtypes = [fp, rs, vp, C.c_int64, vp]
+    L.b200gym_romfam_gen_input.argtypes = [fp, rs, vp, vp, vp, C.c_int64, vp]
+    for name in ("b200gym_romfam_f", "b200gym_romfam_des_pose_vel", "b200gym_romfam_input_bounds", "b200gym_romfam_proj_z",
+                 "b200gym_romfam_gen_init", "b200gym_romfam_gen_reset", "b200gym_romfam_gen_step", "b200gym_romfam_gen_input"):
+        getattr(L, name).restype = C.c_int
     f64 = C.c_double
     L.b200gym_gae_returns.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, f32, f32, vp]
     L.b200gym_adv_normalize.argtypes = [vp, vp, C.c_int64, vp]
@@ -159,7 +180,8 @@ def lib():
     L.b200gym_tube_error.restype = L.b200gym_sliding_window.restype = C.c_int
     L.b200gym_mlp_forward.restype = C.c_int
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
-                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD)):
+                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD),
+                      ("B200RomFamilyParams", RomFamilyParamsPOD)):
         n = L.b200gym_sizeof(name.encode())
         if n != C.sizeof(cls):
             raise RuntimeError(f"ABI mismatch: sizeof({name}) is {n} in the library, {C.sizeof(cls)} in the binding")

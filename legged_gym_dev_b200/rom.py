@@ -9,8 +9,12 @@ Reference surface kept (SURVEY.md §1, §8b iii):
                                                                                               deep_tube_learning/custom_sim.py:5-103
   DoubleSingleTracking(Kp, Kd, state_dependent_input_bound)(obs)                             deep_tube_learning/controllers.py:80-92
 plus `collect_epoch`, the loop body of deep_tube_learning/data_collection_trajectory.py:104-149 as one launch.
-The small algebraic helpers (f / proj_z / clip_v_z ...) stay torch expressions on the device — they are API, not
-the hot loop; the hot loop (`step`, `reset`, the controller, the epoch rollout) goes through the C ABI.
+The small algebraic helpers (f / proj_z / clip_v_z ...) of the two integrator classes stay torch expressions on the device — they
+are API, not the hot loop; the hot loop (`step`, `reset`, the controller, the epoch rollout) goes through the C ABI.
+The unicycle family (Unicycle :263, LateralUnicycle :307, ExtendedUnicycle :336, ExtendedLateralUnicycle :397 — SURVEY 8f row 4)
+runs entirely through the generic kernels of csrc/rom_family.cu: its algebra (one launch per call, incl. proj_z, which the
+reference evaluates with scipy on the host) and a stand-alone TrajectoryGenerator over any rom class
+(`reset(z)`, `reset_idx(idx, z)`, `step()`, `step_idx(idx)`, `get_input_t(t, z)`).
 """
 import ctypes as C
 import math
@@ -19,7 +23,7 @@ import torch
 
 from . import _lib
 
-SINGLE_INT_2D, DOUBLE_INT_2D = 0, 1
+SINGLE_INT_2D, DOUBLE_INT_2D, UNICYCLE, LATERAL_UNICYCLE, EXTENDED_UNICYCLE, EXTENDED_LATERAL_UNICYCLE = range(6)
 
 
 class RomDynamics:
@@ -103,6 +107,118 @@ class DoubleInt2D(RomDynamics):
         return torch.tensor([rw.position, rw.position, rw.velocity, rw.velocity], dtype=torch.float32, device=self.device)
 
 
+def _pad(v, n):
+    v = [float(x) for x in v]
+    return v + [0.0] * (n - len(v))
+
+
+def _family_pod(rom):
+    p = _lib.RomFamilyParamsPOD()
+    p.num_envs, p.rom_type, p.window, p.dN = rom.n_robots, rom.kind, 2, 1
+    p.rom_dt, p.dt_loop = rom.dt, rom.dt
+    p.z_min[:], p.z_max[:] = _pad(rom.z_min.tolist(), 8), _pad(rom.z_max.tolist(), 8)
+    p.v_min[:], p.v_max[:] = _pad(rom.v_min.tolist(), 4), _pad(rom.v_max.tolist(), 4)
+    return p
+
+
+class Unicycle(RomDynamics):
+    """rom_dynamics.py:263-305; f / des_pose_vel / proj_z / clip_v_z are single launches of the b200gym_romfam_* entry points.
+    Unlike the reference (whose f() fills a [n_robots, n] buffer, :270) any number of rows is accepted."""
+    n, m, kind = 3, 2, UNICYCLE
+    _vel_inds = (False, False, False)
+
+    def __init__(self, dt, z_min, z_max, v_min, v_max, n_robots=1, backend="torch", device="cuda"):
+        super().__init__(dt, z_min, z_max, v_min, v_max, n_robots, backend, device)
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("the b200gym unicycle-family ROMs run on CUDA devices only (no CPU fallback)")
+        if len(self.z_min) != self.n or len(self.z_max) != self.n or len(self.v_min) != self.m or len(self.v_max) != self.m:
+            raise ValueError(f"{type(self).__name__}: z bounds need {self.n} entries, v bounds {self.m}")
+        self.vel_inds = torch.tensor(self._vel_inds, device=device)
+        self._fp = _family_pod(self)
+        self.lib = _lib.lib()
+
+    def _rows(self, t, width, name):
+        _lib.require_cuda(t, name)
+        if t.dim() != 2 or t.shape[1] != width or t.dtype != torch.float32:
+            raise ValueError(f"{type(self).__name__}: `{name}` must be a float32 [rows, {width}] tensor (got {tuple(t.shape)}, {t.dtype})")
+        return t.contiguous()
+
+    def f(self, x, u):
+        x, u = self._rows(x, self.n, "x"), self._rows(u, self.m, "u")
+        out = torch.empty_like(x)
+        if x.shape[0]:
+            _lib.check(self.lib.b200gym_romfam_f(self.kind, self.dt, _lib.ptr(x), _lib.ptr(u), _lib.ptr(out), x.shape[0],
+                                                 _lib.stream_ptr(x.device)), "romfam_f")
+        return out
+
+    def des_pose_vel(self, z, v):
+        z, v = self._rows(z, self.n, "z"), self._rows(v, self.m, "v")
+        pose, vel = torch.empty(z.shape[0], 3, device=z.device), torch.empty(z.shape[0], 3, device=z.device)
+        if z.shape[0]:
+            _lib.check(self.lib.b200gym_romfam_des_pose_vel(self.kind, _lib.ptr(z), _lib.ptr(v), _lib.ptr(pose), _lib.ptr(vel), z.shape[0],
+                                                            _lib.stream_ptr(z.device)), "romfam_des_pose_vel")
+        return pose, vel
+
+    def proj_z(self, x):
+        x = self._rows(x, 13, "x")
+        z = torch.empty(x.shape[0], self.n, device=x.device)
+        if x.shape[0]:
+            _lib.check(self.lib.b200gym_romfam_proj_z(self.kind, _lib.ptr(x), _lib.ptr(z), x.shape[0], _lib.stream_ptr(x.device)), "romfam_proj_z")
+        return z
+
+    def compute_state_dependent_input_bounds(self, z):
+        z = self._rows(z, self.n, "z")
+        lo, hi = torch.empty(z.shape[0], self.m, device=z.device), torch.empty(z.shape[0], self.m, device=z.device)
+        if z.shape[0]:
+            _lib.check(self.lib.b200gym_romfam_input_bounds(self._fp, _lib.ptr(z), None, _lib.ptr(lo), _lib.ptr(hi), None, z.shape[0],
+                                                            _lib.stream_ptr(z.device)), "romfam_input_bounds")
+        return lo, hi
+
+    def clip_v_z(self, z, v):
+        z, v = self._rows(z, self.n, "z"), self._rows(v, self.m, "v")
+        out = torch.empty_like(v)
+        if z.shape[0]:
+            _lib.check(self.lib.b200gym_romfam_input_bounds(self._fp, _lib.ptr(z), _lib.ptr(v), None, None, _lib.ptr(out), z.shape[0],
+                                                            _lib.stream_ptr(z.device)), "romfam_input_bounds")
+        return out
+
+    def get_weighting_vector(self, rw):                                   # :302-304
+        return torch.tensor([rw.position, rw.position, rw.orientation], dtype=torch.float32, device=self.device)
+
+
+class LateralUnicycle(Unicycle):
+    """rom_dynamics.py:307-333 (des_pose_vel keeps the reference's om = v[:, 1], :321)."""
+    n, m, kind = 3, 3, LATERAL_UNICYCLE
+
+    def get_weighting_vector(self, rw):                                   # :329-333
+        return torch.tensor([rw.position, rw.position, rw.orientation, rw.velocity, rw.velocity, rw.angular_velocity], dtype=torch.float32,
+                            device=self.device)
+
+
+class ExtendedUnicycle(Unicycle):
+    """rom_dynamics.py:336-394."""
+    n, m, kind = 5, 2, EXTENDED_UNICYCLE
+    _vel_inds = (False, False, False, True, True)
+
+    def get_weighting_vector(self, rw):                                   # :390-394
+        return torch.tensor([rw.position, rw.position, rw.orientation, rw.velocity, rw.angular_velocity], dtype=torch.float32,
+                            device=self.device)
+
+
+class ExtendedLateralUnicycle(ExtendedUnicycle):
+    """rom_dynamics.py:397-438.  proj_z: the reference's (:422-427) raises on both of its array backends (torch.squeeze of a numpy
+    array); built as ExtendedUnicycle's with both local velocity components, the evident intent."""
+    n, m, kind = 6, 3, EXTENDED_LATERAL_UNICYCLE
+    _vel_inds = (False, False, False, True, True, True)
+
+    def get_weighting_vector(self, rw):                                   # :434-438
+        return torch.tensor([rw.position, rw.position, rw.orientation, rw.velocity, rw.velocity, rw.angular_velocity], dtype=torch.float32,
+                            device=self.device)
+
+
+ROM_CLASSES = {c.__name__: c for c in (SingleInt2D, DoubleInt2D, Unicycle, LateralUnicycle, ExtendedUnicycle, ExtendedLateralUnicycle)}
+
+
 class UniformSampleHoldDT:
     """utils.py:27-43: only the bounds matter to the fused generator (the draw itself happens in-kernel)."""
 
@@ -135,7 +251,7 @@ class TrajectoryGenerator:
     kind = 0   # B200GYM_GEN_RANDOM; the deterministic subclasses below override it
 
     def __init__(self, rom, t_sampler, weight_sampler, dt_loop=0.02, N=4, freq_low=0.01, freq_high=10, seed=42,
-                 backend="torch", device="cuda", prob_stationary=.01, dN=1, env_id_offset=0, model=None):
+                 backend="torch", device="cuda", prob_stationary=.01, dN=1, env_id_offset=0, model=None, generic_kernels=False):
         if backend != "torch":
             raise ValueError("backend must be 'torch'")
         self.device = torch.device(device)
@@ -162,10 +278,43 @@ class TrajectoryGenerator:
         self.center = z(n, 2) if self.kind == 3 else None
         self._model = model
         self._sim = None
+        # the unicycle-family classes are served only by the generic kernels (csrc/rom_family.cu); `generic_kernels=True` routes the
+        # integrator classes through them too (step / step_idx; reset / get_input_t always are) — the two paths agree bit for bit
+        self._family = rom.kind > DOUBLE_INT_2D or bool(generic_kernels)
+        if self._family and (self.kind != 0 or model is not None):
+            raise ValueError("the generic rom-family kernels serve the stand-alone random TrajectoryGenerator only")
+        self._build_family_pod()
+        if self._family:
+            self._p = None
+            _lib.check(self.lib.b200gym_romfam_gen_init(self._fp, self._s, self.env_id_offset, _lib.stream_ptr(dev)), "romfam_gen_init")
+            return
         self._build_pod()
         _lib.check(self.lib.b200gym_rom_init(self._p, self._s, self.env_id_offset, _lib.stream_ptr(dev)), "rom_init")
 
     # ---- POD structs ----------------------------------------------------------------------------
+    def _state_pod(self):
+        s = _lib.RomStatePOD()
+        for name in ("trajectory", "v_trajectory", "v", "t", "k", "t_final", "weights", "sample_hold_input", "extreme_input",
+                     "ramp_v_start", "ramp_v_end", "ramp_t_start", "sin_mag", "sin_freq", "sin_off", "sin_mean",
+                     "stationary_inds", "rng_ctr"):
+            t = getattr(self, name)
+            _lib.require_cuda(t, name)
+            setattr(s, name, t.data_ptr())
+        return s
+
+    def _build_family_pod(self):
+        """B200RomFamilyParams of the generic generator kernels (any rom class; the stand-alone reset(z) / get_input_t path)."""
+        rom = self.rom
+        p = _family_pod(rom)
+        p.window, p.dN, p.dt_loop = self.N * self.dN, self.dN, self.dt_loop
+        p.t_low, p.t_span = self.t_sampler.t_low, self.t_sampler.t_high - self.t_sampler.t_low
+        p.freq_low, p.freq_high, p.prob_stationary = self.freq_low, self.freq_high, self.prob_stationary
+        p.weight_zero_col = getattr(self.weight_sampler, "zero_col", -1)
+        p.seed_lo, p.seed_hi = self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF
+        self._fp = p
+        if self._family:
+            self._s = self._state_pod()
+
     def _build_pod(self, sim=None):
         rom, model = self.rom, self._model
         p = _lib.RomParamsPOD()
@@ -200,13 +349,7 @@ class TrajectoryGenerator:
             p.zero_rom_dist_llh = sim.zero_rom_dist_llh
             p.noise_lower[:], p.noise_upper[:] = _pad4(sim.root_state_noise_lower.tolist()), _pad4(sim.root_state_noise_upper.tolist())
             p.Kp, p.Kd = sim.Kp, sim.Kd
-        s = _lib.RomStatePOD()
-        for name in ("trajectory", "v_trajectory", "v", "t", "k", "t_final", "weights", "sample_hold_input", "extreme_input",
-                     "ramp_v_start", "ramp_v_end", "ramp_t_start", "sin_mag", "sin_freq", "sin_off", "sin_mean",
-                     "stationary_inds", "rng_ctr"):
-            t = getattr(self, name)
-            _lib.require_cuda(t, name)
-            setattr(s, name, t.data_ptr())
+        s = self._state_pod()
         if self.center is not None:
             s.center = self.center.data_ptr()
         if sim is not None:
@@ -233,6 +376,10 @@ class TrajectoryGenerator:
 
     def step_idx(self, idx):
         m, mp = self._mask_ptr(idx)
+        if self._family:
+            _lib.check(self.lib.b200gym_romfam_gen_step(self._fp, self._s, mp, self.env_id_offset, _lib.stream_ptr(self.device)),
+                       "romfam_gen_step")
+            return
         _lib.check(self.lib.b200gym_rom_step(self._p, self._s, None, mp, self.env_id_offset, _lib.stream_ptr(self.device)), "rom_step")
 
     def get_trajectory(self):                                             # rom_dynamics.py:607-612
@@ -243,8 +390,37 @@ class TrajectoryGenerator:
     def get_v_trajectory(self):
         return self.v_trajectory[:, ::self.dN, :]
 
-    def reset(self, z):
-        raise NotImplementedError("stand-alone TrajectoryGenerator.reset is driven through CustomSim.reset / reset_idx")
+    def _z_rows(self, z):
+        _lib.require_cuda(z, "z")
+        if tuple(z.shape) != (self.rom.n_robots, self.rom.n) or z.dtype != torch.float32:
+            raise ValueError(f"z must be a float32 [{self.rom.n_robots}, {self.rom.n}] tensor (got {tuple(z.shape)}, {z.dtype})")
+        return z.contiguous()
+
+    def reset(self, z):                                                   # rom_dynamics.py:592-593
+        self.reset_idx(None, z)
+
+    def reset_idx(self, idx, z):
+        """rom_dynamics.py:595-605 for the random generator over any rom class (one launch: the W warm-up knots are written in place).
+        The Zero / Square / Circle generators are reset through the trajectory env / CustomSim paths only."""
+        if self.kind != 0:
+            raise NotImplementedError("stand-alone reset of the Zero / Square / Circle generators is driven through the env's reset path")
+        z = self._z_rows(z)
+        m, mp = self._mask_ptr(idx)
+        _lib.check(self.lib.b200gym_romfam_gen_reset(self._fp, self._s, _lib.ptr(z), mp, self.env_id_offset, _lib.stream_ptr(self.device)),
+                   "romfam_gen_reset")
+
+    def get_input_t(self, t, z):
+        """rom_dynamics.py:560-566 with caller-supplied clock(s) `t` (scalar or [n_robots]) and states z: resamples the envs with
+        t > t_final, returns the weighted, clipped input [n_robots, m] (the open-loop use of trajopt/trajectory_gen.py:35-41)."""
+        if self.kind != 0:
+            raise NotImplementedError("get_input_t is fused for the random TrajectoryGenerator")
+        z = self._z_rows(z)
+        n = self.rom.n_robots
+        tt = torch.as_tensor(t, dtype=torch.float32, device=self.device).expand(n).contiguous()
+        v = torch.empty(n, self.rom.m, device=self.device)
+        _lib.check(self.lib.b200gym_romfam_gen_input(self._fp, self._s, _lib.ptr(tt), _lib.ptr(z), _lib.ptr(v), self.env_id_offset,
+                                                     _lib.stream_ptr(self.device)), "romfam_gen_input")
+        return v
 
 
 class ZeroTrajectoryGenerator(TrajectoryGenerator):

@@ -28,15 +28,23 @@ def rom_params(num_envs, **over):
     return SimpleNamespace(**d)
 
 
+# the unicycle family, rom_dynamics.py:263-438: class -> (n, m, first velocity state)
+FAMILY = {"Unicycle": (3, 2, 3), "LateralUnicycle": (3, 3, 3), "ExtendedUnicycle": (5, 2, 3), "ExtendedLateralUnicycle": (6, 3, 3)}
+
+
 class Rom:
-    """SingleInt2D / DoubleInt2D with the torch backend (rom_dynamics.py:182-260)."""
+    """The RomDynamics classes with the torch backend (rom_dynamics.py:182-438)."""
 
     def __init__(self, cls, dt, z_min, z_max, v_min, v_max):
         t = lambda v: torch.tensor(v, dtype=torch.float32)
         self.cls, self.dt = cls, dt
         self.z_min, self.z_max, self.v_min, self.v_max = t(z_min), t(z_max), t(v_min), t(v_max)
         self.m = 2
-        if cls == "SingleInt2D":
+        if cls in FAMILY:
+            self.n, self.m, vs = FAMILY[cls]
+            self.vs = vs
+            self.vel_inds = torch.tensor([c >= vs for c in range(self.n)])
+        elif cls == "SingleInt2D":
             self.n = 2
             self.A = t([[1.0, 0], [0, 1.0]])
             self.B = t([[dt, 0], [0, dt]])
@@ -50,15 +58,69 @@ class Rom:
             raise ValueError(cls)
 
     def f(self, x, u):
+        if self.cls in FAMILY:
+            # Unicycle.f :273-278, LateralUnicycle.f :311-316, ExtendedUnicycle.f :345-352, ExtendedLateralUnicycle.f :406-414
+            gu = torch.zeros(x.shape[0], self.n)
+            c, s = torch.cos(x[:, 2]), torch.sin(x[:, 2])
+            if self.cls == "Unicycle":
+                gu[:, 0], gu[:, 1], gu[:, 2] = u[:, 0] * c, u[:, 0] * s, u[:, 1]
+            elif self.cls == "LateralUnicycle":
+                gu[:, 0] = u[:, 0] * c - u[:, 1] * s
+                gu[:, 1] = u[:, 0] * s + u[:, 1] * c
+                gu[:, 2] = u[:, 2]
+            elif self.cls == "ExtendedUnicycle":
+                gu[:, 0], gu[:, 1], gu[:, 2] = x[:, 3] * c, x[:, 3] * s, x[:, 4]
+                gu[:, 3], gu[:, 4] = u[:, 0], u[:, 1]
+            else:
+                gu[:, 0] = x[:, 3] * c - x[:, 4] * s
+                gu[:, 1] = x[:, 3] * s + x[:, 4] * c
+                gu[:, 2] = x[:, 5]
+                gu[:, 3], gu[:, 4], gu[:, 5] = u[:, 0], u[:, 1], u[:, 2]
+            return x + self.dt * gu
         return (self.A @ x.T).T + (self.B @ u.T).T
+
+    def des_pose_vel(self, z, v):
+        """:198-199, :230-232, :286-290, :318-322 (om = v[:, 1] as written there), :354-358, :416-420."""
+        zero = torch.zeros((v.shape[0], 1))
+        if self.cls == "SingleInt2D":
+            return torch.hstack((z, torch.arctan2(v[:, 1], v[:, 0])[:, None])), torch.hstack((v, zero))
+        if self.cls == "DoubleInt2D":
+            return torch.hstack((z[:, :2], torch.arctan2(z[:, 3], z[:, 2])[:, None])), torch.hstack((z[:, 2:], zero))
+        c, s = torch.cos(z[:, 2]), torch.sin(z[:, 2])
+        if self.cls == "Unicycle":
+            vx, vy, om = v[:, 0] * c, v[:, 0] * s, v[:, 1]
+        elif self.cls == "LateralUnicycle":
+            vx, vy, om = v[:, 0] * c - v[:, 1] * s, v[:, 0] * s + v[:, 1] * c, v[:, 1]
+        elif self.cls == "ExtendedUnicycle":
+            vx, vy, om = z[:, 3] * c, z[:, 3] * s, z[:, 4]
+        else:
+            vx, vy, om = z[:, 3] * c - z[:, 4] * s, z[:, 3] * s + z[:, 4] * c, z[:, 5]
+        return z[:, :3], torch.hstack((vx[:, None], vy[:, None], om[:, None]))
 
     def proj_z(self, x):
         if self.cls == "SingleInt2D":
             return x[..., :2]
-        return torch.hstack((x[..., :2], x[..., 7:9]))
+        if self.cls == "DoubleInt2D":
+            return torch.hstack((x[..., :2], x[..., 7:9]))
+        # :280-284, :360-365, :422-427 — the reference runs these on numpy arrays (scipy Rotation, fp64 euler angles)
+        from scipy.spatial.transform import Rotation
+        xn = x.numpy() if torch.is_tensor(x) else np.asarray(x)
+        yaw = Rotation.from_quat(xn[:, 3:7]).as_euler("xyz", degrees=False)[..., -1]
+        cols = [xn[..., :2], yaw[:, None]]
+        if self.cls in ("ExtendedUnicycle", "ExtendedLateralUnicycle"):
+            y2r = np.zeros((yaw.shape[0], 2, 2))                          # yaw2rot, deep_tube_learning/utils.py:88-96
+            y2r[:, 0, 0] = y2r[:, 1, 1] = np.cos(yaw)
+            y2r[:, 0, 1], y2r[:, 1, 0] = np.sin(yaw), -np.sin(yaw)
+            vl = np.squeeze(y2r @ xn[:, 7:9][:, :, None], axis=-1)
+            cols += [vl[:, :1] if self.cls == "ExtendedUnicycle" else vl, xn[:, -1][:, None]]
+        return np.hstack(cols)
 
     def bounds(self, z):
-        if self.cls == "SingleInt2D":
+        if self.cls in FAMILY and self.vs < self.n:                       # :367-379
+            v_max_z = torch.min(self.v_max, (self.z_max[self.vs:] - z[:, self.vs:]) / self.dt)
+            v_min_z = torch.max(self.v_min, (self.z_min[self.vs:] - z[:, self.vs:]) / self.dt)
+            return v_min_z, v_max_z
+        if self.cls == "SingleInt2D" or self.cls in FAMILY:
             n = z.shape[0]
             return (torch.repeat_interleave(self.v_min[None, :], n, dim=0),
                     torch.repeat_interleave(self.v_max[None, :], n, dim=0))
@@ -67,7 +129,7 @@ class Rom:
         return v_min_z, v_max_z
 
     def clip_v_z(self, z, v):
-        if self.cls == "SingleInt2D":
+        if self.cls == "SingleInt2D" or (self.cls in FAMILY and self.vs == self.n):   # :201, :292
             return v
         lo, hi = self.bounds(z)
         return torch.max(torch.min(v, hi), lo)
@@ -310,3 +372,47 @@ class RomPort:
             z[done[:, t], t + 1, :] = proj[done[:, t], :]
             pz_x[:, t + 1, :] = proj
         return dict(x=x, z=z, pz_x=pz_x, v=v, done=done), obs
+
+
+def gen_params(num_envs, rom_cls, **over):
+    """A stand-alone TrajectoryGenerator over any rom class (the shape of trajopt/trajectory_gen.py:13-19,72-98)."""
+    n, m, _ = FAMILY.get(rom_cls, (2 if rom_cls == "SingleInt2D" else 4, 2, 0))
+    vel = {"SingleInt2D": [1.0, 1.0], "DoubleInt2D": [1.0, 1.0], "Unicycle": [1.0, 2.0], "LateralUnicycle": [1.0, 0.5, 2.0],
+           "ExtendedUnicycle": [1.0, 4.0], "ExtendedLateralUnicycle": [1.0, 0.6, 4.0]}[rom_cls]
+    zmax = {"SingleInt2D": [1e9, 1e9], "DoubleInt2D": [1e9, 1e9, 0.6, 0.6], "Unicycle": [1e9, 1e9, 1e9], "LateralUnicycle": [1e9, 1e9, 1e9],
+            "ExtendedUnicycle": [1e9, 1e9, 1e9, 1.0, 2.0], "ExtendedLateralUnicycle": [1e9, 1e9, 1e9, 1.0, 0.5, 2.0]}[rom_cls]
+    d = dict(num_envs=num_envs, rom_cls=rom_cls, rom_dt=0.1, dt_loop=0.02, z_min=[-a for a in zmax], z_max=zmax, v_min=[-a for a in vel],
+             v_max=vel, N=6, dN=1, t_low=0.3, t_high=1.2, freq_low=0.01, freq_high=3.0, prob_stationary=0.05,
+             weight_sampler="UniformWeightSampler", seed=0, generator="TrajectoryGenerator")
+    d.update(over)
+    d["model_dt"] = d["dt_loop"]
+    return SimpleNamespace(**d)
+
+
+class GenPort(RomPort):
+    """TrajectoryGenerator alone (rom_dynamics.py:441-615) over any rom class: reset(z) / reset_idx / step / step_idx /
+    get_input_t / get_trajectory, with RomPort's restatement of the generator underneath."""
+
+    def __init__(self, p, rng="philox", env_id_offset=0):
+        self.p, self.rng, self.off = p, rng, env_id_offset
+        N = self.N = p.num_envs
+        rom = self.rom = Rom(p.rom_cls, p.rom_dt, p.z_min, p.z_max, p.v_min, p.v_max)
+        self.W = p.N * p.dN
+        self.ctr = np.zeros(N, dtype=np.int64)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32)
+        self.weights, self.t_final, self.t, self.k = z(N, 4), z(N), z(N), z(N)
+        self.sample_hold_input, self.extreme_input = z(N, rom.m), z(N, rom.m)
+        self.ramp_t_start, self.ramp_v_start = z(N), z(N, rom.m)
+        ids = torch.arange(N)
+        self.ramp_v_end = self._uniform(rom.v_min, rom.v_max, P.SITE_ROM_INIT, ids, self._events(ids), rom.m)
+        self.sin_mag, self.sin_freq, self.sin_off, self.sin_mean = z(N, rom.m), z(N, rom.m), z(N, rom.m), z(N, rom.m)
+        self.traj = z(N, self.W + 1, rom.n)
+        self.v_traj = z(N, self.W, rom.m)
+        self.v = z(N, rom.m)
+        self.stationary = torch.zeros(N, dtype=torch.bool)
+
+    def reset(self, z):
+        self.gen_reset_idx(torch.arange(self.N), z)
+
+    def step(self):
+        self.gen_step_idx(torch.arange(self.N))

@@ -508,6 +508,27 @@ def make_reference_custom_sim(num_envs, seed=0, **over):
     return env, policy, cfg
 
 
+def make_reference_generator(p, seed=0):
+    """The reference's rom class `p.rom_cls` (torch backend on CPU) under a stand-alone TrajectoryGenerator (rom_dynamics.py:441-615),
+    RNG through the shim.  `p` = oracle.port_rom.gen_params(...)."""
+    ref = import_reference()
+    rd, du = ref.rom_dynamics, ref.dtl_utils
+    _install_rom_wrappers(ref)
+    t = lambda v: torch.tensor(v, dtype=torch.float32)
+    rom = getattr(rd, p.rom_cls)(p.rom_dt, t(p.z_min), t(p.z_max), t(p.v_min), t(p.v_max), n_robots=p.num_envs, backend="torch", device="cpu")
+    t_samp = du.UniformSampleHoldDT(p.t_low, p.t_high, backend="torch", device="cpu")
+    w_samp = getattr(du, p.weight_sampler)()
+    holder = SimpleNamespace(seed=seed, ctr=np.zeros(p.num_envs, dtype=np.int64))
+    rd.TrajectoryGenerator._pending_holder = holder
+    try:
+        tg = rd.TrajectoryGenerator(rom, t_samp, w_samp, dt_loop=p.dt_loop, N=p.N, freq_low=p.freq_low, freq_high=p.freq_high, seed=seed,
+                                    backend="torch", device="cpu", prob_stationary=p.prob_stationary, dN=p.dN)
+    finally:
+        rd.TrajectoryGenerator._pending_holder = None
+    tg._shim = holder
+    return tg, rom
+
+
 def _install_rom_wrappers(ref):
     rd, cs = ref.rom_dynamics, ref.custom_sim
     TG, CS = rd.TrajectoryGenerator, cs.CustomSim
