@@ -310,6 +310,94 @@ __global__ void __launch_bounds__(128) fam_step_kernel(const __grid_constant__ B
     for (int c = 0; c < M; ++c) s.v[i * M + c] = g.v[c];
 }
 
+// The same step with the CTA's horizon windows staged through shared memory.  The windows of 128 consecutive envs are ONE contiguous
+// block of HBM ([N, W+1, n] row-major), so a CTA whose envs are due moves them with two 1-D bulk copies (TMA) each way instead of 128
+// strided per-thread streams; each thread then shifts its own row in shared memory.  ROM clocks run in lock-step unless step_idx is
+// used with partial masks, so `due` is CTA-uniform in practice: on the calls between knots (rom.dt / dt_loop - 1 of every rom.dt /
+// dt_loop) no window is touched beyond the last knot.  A partial tail CTA whose block is not a multiple of 16 bytes takes the per-thread
+// path of fam_step_kernel.
+constexpr int FT = 128;   // envs (threads) per CTA
+
+template <int T>
+__global__ void __launch_bounds__(FT) fam_step_tile_kernel(const __grid_constant__ B200RomFamilyParams p, const __grid_constant__ B200RomState s,
+                                                           const uint8_t* __restrict__ mask, long long env_off) {
+    constexpr int RN = Rom<T>::n, M = Rom<T>::m;
+    extern __shared__ __align__(128) float fam_smem[];
+    __shared__ uint64_t bar;
+    const int w = p.window;
+    const int rl = (w + 1) * RN, vl = w * M;   // floats per env in the two windows
+    float* s_tr = fam_smem;
+    float* s_vt = fam_smem + FT * rl;
+    const int env0 = blockIdx.x * FT;
+    const int nenv = min(FT, p.num_envs - env0);
+    const int e = threadIdx.x;
+    const bool valid = e < nenv;
+    const size_t i = static_cast<size_t>(env0) + (valid ? e : 0);
+    const uint64_t genv = static_cast<uint64_t>(env_off) + i;
+    pdl_launch_dependents();
+    pdl_wait();
+    float* g_tr = s.trajectory + static_cast<size_t>(env0) * rl;
+    float* g_vt = s.v_trajectory + static_cast<size_t>(env0) * vl;
+    GenP<M> g;
+    load_params(s, i, g);
+    const bool in_idx = valid && (mask == nullptr || mask[i] != 0);
+    const bool due = in_idx && (g.t >= sub_rn(mul_rn(g.k, p.rom_dt), 1e-5f));
+    const uint32_t bytes_tr = static_cast<uint32_t>(nenv) * rl * 4u, bytes_vt = static_cast<uint32_t>(nenv) * vl * 4u;
+    const bool tile_ok = ((bytes_tr | bytes_vt) & 15u) == 0 && ((reinterpret_cast<uintptr_t>(g_tr) | reinterpret_cast<uintptr_t>(g_vt)) & 15u) == 0;
+    const bool staged = __syncthreads_or(due) != 0 && tile_ok;
+    if (staged) {
+        if (e == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (e == 0) {
+            mbar_expect_tx(&bar, bytes_tr + bytes_vt);
+            bulk_g2s(s_tr, g_tr, bytes_tr, &bar);
+            bulk_g2s(s_vt, g_vt, bytes_vt, &bar);
+        }
+        mbar_wait(&bar, 0);
+    }
+    float* tr = staged ? s_tr + e * rl : s.trajectory + i * rl;
+    float* vt = staged ? s_vt + e * vl : s.v_trajectory + i * vl;
+    const uint32_t ctr0 = g.ctr;
+    if (valid) {
+        float z[RN];
+#pragma unroll
+        for (int c = 0; c < RN; ++c) z[c] = tr[w * RN + c];
+        eval_v<T>(p, g, z, genv);
+        if (due) {   // :581-588
+            float zn[RN];
+            next_knot<T>(p, g, z, zn);
+            for (int c = 0; c < w * RN; ++c) tr[c] = tr[c + RN];
+#pragma unroll
+            for (int c = 0; c < RN; ++c) tr[w * RN + c] = zn[c];
+            for (int c = 0; c < (w - 1) * M; ++c) vt[c] = vt[c + M];
+#pragma unroll
+            for (int c = 0; c < M; ++c) vt[(w - 1) * M + c] = g.v[c];
+            g.k = add_rn(g.k, 1.0f);
+            s.k[i] = g.k;
+        }
+        if (in_idx) {
+            g.t = add_rn(g.t, p.dt_loop);
+            s.t[i] = g.t;
+        }
+        if (g.ctr != ctr0) store_params(s, i, g);
+#pragma unroll
+        for (int c = 0; c < M; ++c) s.v[i * M + c] = g.v[c];
+    }
+    if (staged) {
+        fence_proxy_async();
+        __syncthreads();
+        if (e == 0) {
+            bulk_s2g(g_tr, s_tr, bytes_tr);
+            bulk_s2g(g_vt, s_vt, bytes_vt);
+            bulk_commit();
+            bulk_wait0();
+        }
+    }
+}
+
 template <int T>
 __global__ void __launch_bounds__(128) fam_input_kernel(const __grid_constant__ B200RomFamilyParams p, const __grid_constant__ B200RomState s,
                                                         const float* __restrict__ t_in, const float* __restrict__ z_in, float* __restrict__ v_out,
@@ -529,7 +617,18 @@ int b200gym_romfam_gen_step(const B200RomFamilyParams* p, const B200RomState* s,
     if (int rc = check_fam(p, s, "romfam_gen_step")) return rc;
     const int grid = (p->num_envs + 127) / 128;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    FAM_DISPATCH(p->rom_type, (b200_launch_pdl(p->num_envs, fam_step_kernel<T>, dim3(grid), dim3(128), 0, st, *p, *s, step_mask, (long long)env_id_offset)));
+    // windows staged through shared memory (TMA bulk tiles) unless they do not fit or B200GYM_ROMFAM_TILE=0 asks for the per-thread kernel
+    static const bool tile_on = []() { const char* e = getenv("B200GYM_ROMFAM_TILE"); return !(e && e[0] == '0'); }();
+    const int n_of[B200GYM_ROM_NUM_TYPES] = {2, 4, 3, 3, 5, 6}, m_of[B200GYM_ROM_NUM_TYPES] = {2, 2, 2, 3, 2, 3};
+    const size_t smem = static_cast<size_t>(FT) * ((p->window + 1) * n_of[p->rom_type] + p->window * m_of[p->rom_type]) * sizeof(float);
+    if (tile_on && smem <= 200 * 1024) {
+        FAM_DISPATCH(p->rom_type, {
+            if (smem + 1024 > 48 * 1024) cudaFuncSetAttribute(fam_step_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            b200_launch_pdl(p->num_envs, fam_step_tile_kernel<T>, dim3(grid), dim3(FT), smem, st, *p, *s, step_mask, (long long)env_id_offset);
+        });
+    } else {
+        FAM_DISPATCH(p->rom_type, (b200_launch_pdl(p->num_envs, fam_step_kernel<T>, dim3(grid), dim3(128), 0, st, *p, *s, step_mask, (long long)env_id_offset)));
+    }
     B200_LAUNCH_CHECK("romfam_gen_step");
     return B200GYM_OK;
 }

@@ -103,6 +103,7 @@ def test_algebra_rejects_bad_input():
     ("Unicycle", 300, {}), ("LateralUnicycle", 77, dict(weight_sampler="UniformWeightSamplerNoRamp")),
     ("ExtendedUnicycle", 1000, dict(t_low=0.05, t_high=0.3, prob_stationary=0.2)), ("ExtendedLateralUnicycle", 513, dict(N=4, dN=3)),
     ("ExtendedLateralUnicycle", 130, dict(dt_loop=0.1, weight_sampler="UniformWeightSamplerNoExtreme")),
+    ("ExtendedLateralUnicycle", 260, dict(N=10)), ("ExtendedLateralUnicycle", 140, dict(N=16, dN=2)),     # 48 KB / 150 KB of staged windows per CTA
     ("SingleInt2D", 200, {}), ("DoubleInt2D", 200, dict(N=10, dt_loop=0.05))])
 def test_generator_stepwise_parity(cls, N, over):
     """reset(z), steps with dt_loop < rom.dt (envs only advance when their ROM clock is due), a partial reset_idx whose warm-up re-evaluates
@@ -115,6 +116,7 @@ def test_generator_stepwise_parity(cls, N, over):
     port.reset(z0.clone())
     gen.reset(z0.cuda())
     compare(port, gen, f"{cls} after reset: ")
+    seen_stationary = 0
     for s in range(240):
         if s == 100:
             ids = torch.arange(0, N, 3)
@@ -130,7 +132,8 @@ def test_generator_stepwise_parity(cls, N, over):
             port.step()
             gen.step()
         compare(port, gen, f"{cls} step {s}: ")
-    assert port.ctr.max() > 4 and bool(port.stationary.any()) and not bool(port.stationary.all())
+        seen_stationary += int(port.stationary.sum())
+    assert port.ctr.max() > 4 and seen_stationary > 0 and not bool(port.stationary.all())
     # open-loop use (trajopt/trajectory_gen.py:35-41): the caller owns clock and state
     for tq in (float(port.t.max()) + 0.05, float(port.t.max()) + 2.5):
         zq = torch.randn(N, port.rom.n, generator=rng) * 0.4
