@@ -272,6 +272,35 @@ int b200gym_romfam_gen_input(const B200RomFamilyParams* p, const B200RomState* s
                              int64_t env_id_offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SURVEY 8f row 3 (part) — the Hopper's torque law, Hopper._compute_torques (legged_gym/envs/hopper/hopper.py:168-237), for the control
+ * types the reference method can run: "orientation" and "orientation_spindown" (hopper_config.py:62-63).  4 DOF: foot slide (dof 0) +
+ * three reaction wheels (dofs 1-3); actions = desired base orientation, a raw (w, x, y, z) quaternion.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct B200HopperTorqueParams {
+    int32_t num_envs, num_bodies, foot_body, spindown; /* contact = contact_forces[:, foot_body, 2] > 0.1 (:184); spindown: :204-206 */
+    float action_scale, torque_speed_bound_ratio;      /* cfg.control.action_scale, cfg.asset.torque_speed_bound_ratio (:68) */
+    float p_gains[4], d_gains[4];                      /* LeggedRobot._init_buffers' per-dof gains (hopper_config.py:35-48) */
+    float kd_spindown[3], wheel_speed_limits[3];       /* hopper.py:390-403 */
+    float torque_limits[4];                            /* asset effort limits */
+    float rot_actuator[9];                             /* cfg.asset.rot_actuator, row-major; tau = local_tau @ R (pytorch3d Rotate, :67,:221) */
+} B200HopperTorqueParams;
+
+typedef struct B200HopperTorqueBuffers {
+    const float* actions;        /* [N, 4] */
+    const float* dof_state;      /* [N, 4, 2] (pos, vel) */
+    const float* contact_forces; /* [N, num_bodies, 3] */
+    const float* root_states;    /* [N, 13]; quaternion xyzw in columns 3-6 */
+    const float* base_ang_vel;   /* [N, 3] */
+    const float *p_gain_random, *d_gain_random, *torque_limit_random; /* [N, 4] multipliers (:362-378) */
+    const float* wheel_limit_random;                                  /* [N, 3] (:380-382) */
+    const float *spring_stiffness, *spring_damping, *foot_pos_des, *torque_speed_bound_ratio_random; /* [N] ([N, 1] in the reference) */
+    float* torques;              /* [N, 4] self.torques: after the torque-speed clip, before the torque-limit clip (:236) */
+    float* torques_clipped;      /* [N, 4] the return value (:237) */
+} B200HopperTorqueBuffers;
+
+int b200gym_hopper_torques(const B200HopperTorqueParams* p, const B200HopperTorqueBuffers* b, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Group G — rsl_rl rollout storage + PPO update (rsl_rl v1.0.2, a fork of which the reference imports at
  * legged_gym/utils/task_registry.py:37-38; source NOT in /root/reference: arithmetic restated)
  * ---------------------------------------------------------------------------------------------- */

@@ -86,6 +86,21 @@ class RomFamilyParamsPOD(C.Structure):
     ]
 
 
+class HopperTorqueParamsPOD(C.Structure):
+    _fields_ = [("num_envs", i32), ("num_bodies", i32), ("foot_body", i32), ("spindown", i32), ("action_scale", f32),
+                ("torque_speed_bound_ratio", f32), ("p_gains", f32 * 4), ("d_gains", f32 * 4), ("kd_spindown", f32 * 3),
+                ("wheel_speed_limits", f32 * 3), ("torque_limits", f32 * 4), ("rot_actuator", f32 * 9)]
+
+
+_HOPPER_FIELDS = ["actions", "dof_state", "contact_forces", "root_states", "base_ang_vel", "p_gain_random", "d_gain_random", "torque_limit_random",
+                  "wheel_limit_random", "spring_stiffness", "spring_damping", "foot_pos_des", "torque_speed_bound_ratio_random", "torques",
+                  "torques_clipped"]
+
+
+class HopperTorqueBuffersPOD(C.Structure):
+    _fields_ = [(n, vp) for n in _HOPPER_FIELDS]
+
+
 _ROM_FIELDS = ["root_states", "trajectory", "v_trajectory", "v", "t", "k", "t_final", "weights", "sample_hold_input",
                "extreme_input", "ramp_v_start", "ramp_v_end", "ramp_t_start", "sin_mag", "sin_freq", "sin_off", "sin_mean",
                "stationary_inds", "rng_ctr", "env_trajectory", "obs", "center"]
@@ -144,6 +159,8 @@ def lib():
     for name in ("b200gym_rom_init", "b200gym_rom_step", "b200gym_rom_reset", "b200gym_rom_reset_from_root", "b200gym_rom_tracking_policy",
                  "b200gym_rom_rollout"):
         getattr(L, name).restype = C.c_int
+    L.b200gym_hopper_torques.argtypes = [C.POINTER(HopperTorqueParamsPOD), C.POINTER(HopperTorqueBuffersPOD), vp]
+    L.b200gym_hopper_torques.restype = C.c_int
     fp = C.POINTER(RomFamilyParamsPOD)
     L.b200gym_romfam_f.argtypes = [C.c_int32, f32, vp, vp, vp, C.c_int64, vp]
     L.b200gym_romfam_des_pose_vel.argtypes = [C.c_int32, vp, vp, vp, vp, C.c_int64, vp]
@@ -181,7 +198,8 @@ def lib():
     L.b200gym_mlp_forward.restype = C.c_int
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
                       ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD),
-                      ("B200RomFamilyParams", RomFamilyParamsPOD)):
+                      ("B200RomFamilyParams", RomFamilyParamsPOD), ("B200HopperTorqueParams", HopperTorqueParamsPOD),
+                      ("B200HopperTorqueBuffers", HopperTorqueBuffersPOD)):
         n = L.b200gym_sizeof(name.encode())
         if n != C.sizeof(cls):
             raise RuntimeError(f"ABI mismatch: sizeof({name}) is {n} in the library, {C.sizeof(cls)} in the binding")

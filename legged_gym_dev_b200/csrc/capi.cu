@@ -27,6 +27,8 @@ int b200gym_sizeof(const char* name) {
     if (!strcmp(name, "B200RomParams")) return (int)sizeof(B200RomParams);
     if (!strcmp(name, "B200RomState")) return (int)sizeof(B200RomState);
     if (!strcmp(name, "B200RomFamilyParams")) return (int)sizeof(B200RomFamilyParams);
+    if (!strcmp(name, "B200HopperTorqueParams")) return (int)sizeof(B200HopperTorqueParams);
+    if (!strcmp(name, "B200HopperTorqueBuffers")) return (int)sizeof(B200HopperTorqueBuffers);
     if (!strcmp(name, "B200PeerPtrs")) return (int)sizeof(B200PeerPtrs);
     return -1;
 }

@@ -1,0 +1,129 @@
+// the Hopper's torque law, Hopper._compute_torques (legged_gym/envs/hopper/hopper.py:168-237).
+//
+// One thread per env, one pass: the foot's contact-switched spring / PD torque, the reaction wheels' orientation control
+// (quaternion error -> rotation matrix -> so3 log map -> PD in the body frame -> actuator rotation) or spin-down damping in contact,
+// the torque-speed envelope and the torque limits, with the per-env randomised gain / limit multipliers.  The quaternion / so3 steps
+// follow pytorch3d.transforms (quaternion_invert, quaternion_multiply, quaternion_to_matrix, so3_log_map with its linear acos
+// continuation, Rotate.transform_points) operation by operation in fp32 round-to-nearest — the log map is ill-conditioned near
+// 0 and pi, where the reference's own result depends on that order.
+//
+// Algorithmic bytes per env: actions 16 + dof_state 32 + foot contact z 4 + quaternion 16 + base_ang_vel 12 + multipliers 76 +
+// two torque tensors 32 = 188 B; the contact read touches one 32 B sector of the [N, bodies, 3] tensor.
+#include <math.h>
+
+#include "common.cuh"
+#include "../../include/b200gym.h"
+
+namespace {
+
+struct AcosExtrap {   // acos_linear_extrapolation(x, (-1 + 1e-4, 1 - 1e-4)), pytorch3d/transforms/math.py, constants formed in double on the host
+    float lo, hi, slope_lo, slope_hi, acos_lo, acos_hi;
+};
+
+__global__ void __launch_bounds__(256) hopper_torques_kernel(const __grid_constant__ B200HopperTorqueParams p,
+                                                             const __grid_constant__ B200HopperTorqueBuffers b,
+                                                             const __grid_constant__ AcosExtrap ax) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (e >= p.num_envs) return;
+    const size_t i = static_cast<size_t>(e);
+    const float4 act = *reinterpret_cast<const float4*>(b.actions + i * 4);
+    const float4 ds0 = *reinterpret_cast<const float4*>(b.dof_state + i * 8), ds1 = *reinterpret_cast<const float4*>(b.dof_state + i * 8 + 4);
+    const float foot_pos = ds0.x, foot_vel = ds0.y, wv[3] = {ds0.w, ds1.y, ds1.w};
+    const bool contact = b.contact_forces[(i * p.num_bodies + p.foot_body) * 3 + 2] > 0.1f;                      // :184
+    const float4 pr = *reinterpret_cast<const float4*>(b.p_gain_random + i * 4), dr = *reinterpret_cast<const float4*>(b.d_gain_random + i * 4);
+    const float pg[4] = {mul_rn(p.p_gains[0], pr.x), mul_rn(p.p_gains[1], pr.y), mul_rn(p.p_gains[2], pr.z), mul_rn(p.p_gains[3], pr.w)};   // :191
+    const float drv[4] = {dr.x, dr.y, dr.z, dr.w};
+    const float dg[4] = {mul_rn(p.d_gains[0], dr.x), mul_rn(p.d_gains[1], dr.y), mul_rn(p.d_gains[2], dr.z), mul_rn(p.d_gains[3], dr.w)};   // :192
+    float tq[4];
+
+    // foot: zero + spring in contact, PD towards foot_pos_des in flight (:198-201)
+    if (contact) {
+        tq[0] = add_rn(0.0f, sub_rn(mul_rn(-b.spring_stiffness[i], foot_pos), mul_rn(b.spring_damping[i], foot_vel)));
+    } else {
+        tq[0] = sub_rn(mul_rn(-pg[0], sub_rn(foot_pos, b.foot_pos_des[i])), mul_rn(dg[0], foot_vel));
+    }
+
+    if (p.spindown && contact) {                                                                              // :204-205
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tq[1 + j] = mul_rn(-mul_rn(p.kd_spindown[j], drv[1 + j]), wv[j]);          // kd_spindown * d_gain_random (:193)
+    } else {                                                                                                  // :212-222
+        const float a[4] = {mul_rn(act.x, p.action_scale), mul_rn(act.y, p.action_scale), mul_rn(act.z, p.action_scale), mul_rn(act.w, p.action_scale)};
+        const float nrm = sqrtf(add_rn(add_rn(add_rn(mul_rn(a[0], a[0]), mul_rn(a[1], a[1])), mul_rn(a[2], a[2])), mul_rn(a[3], a[3])));
+        // quaternion_invert(quat_des): (w, -x, -y, -z)
+        const float aw = div_rn(a[0], nrm), ax_ = -div_rn(a[1], nrm), ay = -div_rn(a[2], nrm), az = -div_rn(a[3], nrm);
+        const float* rs = b.root_states + i * 13;
+        const float bw = rs[6], bx = rs[3], by = rs[4], bz = rs[5];                                            // wxyz_quat_inds = [6, 3, 4, 5] (:62)
+        // quaternion_raw_multiply + standardize_quaternion
+        float r = sub_rn(sub_rn(sub_rn(mul_rn(aw, bw), mul_rn(ax_, bx)), mul_rn(ay, by)), mul_rn(az, bz));
+        float qi = sub_rn(add_rn(add_rn(mul_rn(aw, bx), mul_rn(ax_, bw)), mul_rn(ay, bz)), mul_rn(az, by));
+        float qj = add_rn(add_rn(sub_rn(mul_rn(aw, by), mul_rn(ax_, bz)), mul_rn(ay, bw)), mul_rn(az, bx));
+        float qk = add_rn(sub_rn(add_rn(mul_rn(aw, bz), mul_rn(ax_, by)), mul_rn(ay, bx)), mul_rn(az, bw));
+        if (r < 0.0f) r = -r, qi = -qi, qj = -qj, qk = -qk;
+        // quaternion_to_matrix
+        const float two_s = div_rn(2.0f, add_rn(add_rn(add_rn(mul_rn(r, r), mul_rn(qi, qi)), mul_rn(qj, qj)), mul_rn(qk, qk)));
+        const float R00 = sub_rn(1.0f, mul_rn(two_s, add_rn(mul_rn(qj, qj), mul_rn(qk, qk))));
+        const float R01 = mul_rn(two_s, sub_rn(mul_rn(qi, qj), mul_rn(qk, r)));
+        const float R02 = mul_rn(two_s, add_rn(mul_rn(qi, qk), mul_rn(qj, r)));
+        const float R10 = mul_rn(two_s, add_rn(mul_rn(qi, qj), mul_rn(qk, r)));
+        const float R11 = sub_rn(1.0f, mul_rn(two_s, add_rn(mul_rn(qi, qi), mul_rn(qk, qk))));
+        const float R12 = mul_rn(two_s, sub_rn(mul_rn(qj, qk), mul_rn(qi, r)));
+        const float R20 = mul_rn(two_s, sub_rn(mul_rn(qi, qk), mul_rn(qj, r)));
+        const float R21 = mul_rn(two_s, add_rn(mul_rn(qj, qk), mul_rn(qi, r)));
+        const float R22 = sub_rn(1.0f, mul_rn(two_s, add_rn(mul_rn(qi, qi), mul_rn(qj, qj))));
+        // so3_rotation_angle + so3_log_map + hat_inv
+        const float phi_cos = mul_rn(sub_rn(add_rn(add_rn(R00, R11), R22), 1.0f), 0.5f);
+        float phi;
+        if (phi_cos >= ax.hi) phi = add_rn(mul_rn(sub_rn(phi_cos, ax.hi), ax.slope_hi), ax.acos_hi);
+        else if (phi_cos <= ax.lo) phi = add_rn(mul_rn(sub_rn(phi_cos, ax.lo), ax.slope_lo), ax.acos_lo);
+        else phi = acosf(phi_cos);
+        const float phi_sin = sinf(phi);
+        const float factor = fabsf(phi_sin) > 5e-5f ? div_rn(phi, mul_rn(2.0f, phi_sin)) : add_rn(0.5f, mul_rn(mul_rn(phi, phi), 1.0f / 12));
+        const float lg[3] = {mul_rn(factor, sub_rn(R21, R12)), mul_rn(factor, sub_rn(R02, R20)), mul_rn(factor, sub_rn(R10, R01))};
+        float lt[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) lt[j] = sub_rn(mul_rn(-pg[1 + j], lg[j]), mul_rn(dg[1 + j], b.base_ang_vel[i * 3 + j]));   // :219
+        // Rotate(rot_actuator).transform_points: row vector times matrix
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tq[1 + j] = fmaf(lt[2], p.rot_actuator[6 + j], fmaf(lt[1], p.rot_actuator[3 + j], mul_rn(lt[0], p.rot_actuator[j])));
+    }
+
+    // torque-speed envelope (:231-236), then the torque limits (:237)
+    const float ts = mul_rn(p.torque_speed_bound_ratio, b.torque_speed_bound_ratio_random[i]);
+    const float4 tl = *reinterpret_cast<const float4*>(b.torque_limit_random + i * 4);
+    const float tb[4] = {mul_rn(p.torque_limits[0], tl.x), mul_rn(p.torque_limits[1], tl.y), mul_rn(p.torque_limits[2], tl.z), mul_rn(p.torque_limits[3], tl.w)};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float wb = mul_rn(p.wheel_speed_limits[j], b.wheel_limit_random[i * 3 + j]);
+        const float k = div_rn(mul_rn(-ts, tb[1 + j]), wb);
+        const float upper = mul_rn(k, sub_rn(wv[j], wb)), lower = mul_rn(k, add_rn(wv[j], wb));
+        tq[1 + j] = fminf(fmaxf(tq[1 + j], lower), upper);
+    }
+    *reinterpret_cast<float4*>(b.torques + i * 4) = make_float4(tq[0], tq[1], tq[2], tq[3]);
+    *reinterpret_cast<float4*>(b.torques_clipped + i * 4) = make_float4(fminf(fmaxf(tq[0], -tb[0]), tb[0]), fminf(fmaxf(tq[1], -tb[1]), tb[1]),
+                                                                        fminf(fmaxf(tq[2], -tb[2]), tb[2]), fminf(fmaxf(tq[3], -tb[3]), tb[3]));
+}
+
+}  // namespace
+
+extern "C" int b200gym_hopper_torques(const B200HopperTorqueParams* p, const B200HopperTorqueBuffers* b, void* stream) {
+    B200_REQUIRE(p && b, B200GYM_EINVAL, "hopper_torques: null argument");
+    B200_REQUIRE(p->num_envs > 0, B200GYM_EINVAL, "hopper_torques: num_envs must be positive (got %d)", p->num_envs);
+    B200_REQUIRE(p->num_bodies > 0 && p->foot_body >= 0 && p->foot_body < p->num_bodies, B200GYM_EINVAL, "hopper_torques: foot_body %d outside [0, %d)",
+                 p->foot_body, p->num_bodies);
+    const void* must[] = {b->actions, b->dof_state, b->contact_forces, b->root_states, b->base_ang_vel, b->p_gain_random, b->d_gain_random,
+                          b->torque_limit_random, b->wheel_limit_random, b->spring_stiffness, b->spring_damping, b->foot_pos_des,
+                          b->torque_speed_bound_ratio_random, b->torques, b->torques_clipped};
+    for (const void* q : must) B200_REQUIRE(q != nullptr, B200GYM_EINVAL, "hopper_torques: null buffer");
+    const void* vec[] = {b->actions, b->dof_state, b->p_gain_random, b->d_gain_random, b->torque_limit_random, b->torques, b->torques_clipped};
+    for (const void* q : vec) B200_REQUIRE(b200_aligned16(q), B200GYM_EALIGN, "hopper_torques: [N, 4] tensors must be 16-byte aligned");
+    const double lo = -1.0 + 1e-4, hi = 1.0 - 1e-4;   // so3_log_map's default cos_bound
+    AcosExtrap ax;
+    ax.lo = static_cast<float>(lo), ax.hi = static_cast<float>(hi);
+    ax.slope_lo = static_cast<float>(-1.0 / sqrt(1.0 - lo * lo)), ax.slope_hi = static_cast<float>(-1.0 / sqrt(1.0 - hi * hi));
+    ax.acos_lo = static_cast<float>(acos(lo)), ax.acos_hi = static_cast<float>(acos(hi));
+    b200_launch_pdl(p->num_envs, hopper_torques_kernel, dim3((p->num_envs + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), *p, *b, ax);
+    B200_LAUNCH_CHECK("hopper_torques");
+    return B200GYM_OK;
+}

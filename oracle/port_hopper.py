@@ -1,0 +1,89 @@
+"""CPU restatement (torch, fp32) of the Hopper's torque law, Hopper._compute_torques (legged_gym/envs/hopper/hopper.py:168-237):
+contact-switched foot spring / PD, quaternion-log orientation control of the three reaction wheels through the actuator rotation,
+spin-down in contact, torque-speed and torque-limit clipping, with the per-env randomised gain / limit multipliers (:343-382).
+TEST INFRASTRUCTURE.  Pinned by tests/test_hopper_cpu.py against the unmodified method (oracle/ref_harness.reference_hopper_torques,
+with pytorch3d.transforms = oracle/pytorch3d_restated — see that module's header for what that pin does and does not cover) and by
+tests/golden/hopper_torques_reference.npz.
+
+Control types: "orientation_spindown" (shipped, hopper_config.py:63) and "orientation" — the two the reference method can run.
+Its "w_foot" branch (:195-196) subtracts a [num_envs] from a [num_envs, 1] tensor and fails to assign for num_envs > 1; its "V" / "T"
+branches (:223-227) index actions with a [num_envs] against a [3] index tensor and only run when num_envs == 3: not restated
+(tests/test_hopper_cpu.py shows the reference raising on them).
+"""
+import torch
+
+from . import pytorch3d_restated as P3
+
+# hopper_config.py:35-55,76-89 (+ LeggedRobot._init_buffers' per-dof gain vectors; wheel3 has no stiffness / damping entry -> 0)
+DEFAULTS = dict(action_scale=1.0, p_gains=[900.0, 15.0, 15.0, 0.0], d_gains=[60.0, 3.0, 3.0, 0.0], kd_spindown=[0.1, 0.1, 0.1],
+                foot_pos_des=0.021, spring_stiffness=7000.0, spring_damping=4.0, torque_speed_bound_ratio=6.0,
+                rot_actuator=[[-0.8165, 0.2511, 0.2511], [-0.0, -0.7643, 0.7643], [-0.5773, -0.5939, -0.5939]],
+                wheel_speed_limits=[600.0, 600.0, 600.0], torque_limits=[300.0, 1.5, 1.5, 1.5])
+
+
+def hopper_case(num_envs, seed=0, control_type="orientation_spindown", max_angle=2.6, num_bodies=5, foot_body=4, **over):
+    """Seeded synthetic state of the Hopper's shape: 4 DOF (foot slide + 3 wheels), quaternion actions, contact on ~half of the envs,
+    randomised multipliers in the ranges of hopper_config.py:144-175.  The orientation error angle is drawn in [0, max_angle]."""
+    g = torch.Generator().manual_seed(seed)
+    N = num_envs
+    rn = lambda *s: torch.randn(*s, generator=g)
+    ru = lambda lo, hi, *s: (hi - lo) * torch.rand(*s, generator=g) + lo
+    d = dict(DEFAULTS)
+    d.update(over)
+    unit = lambda q: q / torch.linalg.norm(q, dim=-1, keepdim=True)
+    q_act = unit(rn(N, 4))                                        # wxyz
+    axis = unit(rn(N, 3))
+    ang = ru(0.0, max_angle, N, 1)
+    dq = torch.cat((torch.cos(ang / 2), torch.sin(ang / 2) * axis), dim=1)
+    q_des = P3.quaternion_raw_multiply(q_act, dq) * ru(0.5, 2.0, N, 1)      # the policy's raw (un-normalised) quaternion action
+    root = rn(N, 13)
+    root[:, 3:7] = q_act[:, [1, 2, 3, 0]]                          # xyzw in root_states
+    dof_state = torch.stack((torch.cat((ru(-0.03, 0.05, N, 1), rn(N, 3)), 1), torch.cat((rn(N, 1) * 0.5, rn(N, 3) * 200.0), 1)), dim=-1)
+    cf = rn(N, num_bodies, 3)
+    cf[:, foot_body, 2] = torch.where(torch.rand(N, generator=g) < 0.5, ru(1.0, 300.0, N), torch.zeros(N))
+    case = dict(num_envs=N, control_type=control_type, foot_body=foot_body, action_scale=d["action_scale"],
+                torque_speed_bound_ratio=d["torque_speed_bound_ratio"], rot_actuator=d["rot_actuator"],
+                dof_state=dof_state, contact_forces=cf, root_states=root, base_ang_vel=rn(N, 3) * 2.0,
+                p_gains=torch.tensor(d["p_gains"]), d_gains=torch.tensor(d["d_gains"]), kd_spindown=torch.tensor(d["kd_spindown"]),
+                torque_limits=torch.tensor(d["torque_limits"]), wheel_speed_limits=torch.tensor(d["wheel_speed_limits"]),
+                p_gain_random=ru(0.9, 1.1, N, 4), d_gain_random=ru(0.9, 1.1, N, 4),
+                spring_stiffness=ru(0.9, 1.1, N, 1) * d["spring_stiffness"], spring_damping=ru(0.9, 1.1, N, 1) * d["spring_damping"],
+                foot_pos_des=ru(0.75, 1.25, N, 1) * d["foot_pos_des"], torque_speed_bound_ratio_random=ru(0.9, 1.1, N, 1),
+                torque_limit_random=ru(0.9, 1.1, N, 4), wheel_limit_random=ru(0.9, 1.1, N, 3))
+    return case, q_des
+
+
+def hopper_torques(case, actions):
+    """hopper.py:179-237 per env, masks instead of index lists."""
+    c = case
+    ct = c["control_type"]
+    if ct not in ("orientation", "orientation_spindown"):
+        raise ValueError(f"control_type {ct!r}: the reference method runs 'orientation' and 'orientation_spindown' only")
+    a = actions * c["action_scale"]
+    dof_pos, dof_vel = c["dof_state"][..., 0], c["dof_state"][..., 1]
+    foot_pos, foot_vel, wheel_vel = dof_pos[:, 0], dof_vel[:, 0], dof_vel[:, 1:4]
+    contact = c["contact_forces"][:, c["foot_body"], 2] > 0.1
+    p_gains = c["p_gains"] * c["p_gain_random"]
+    d_gains = c["d_gains"] * c["d_gain_random"]
+    kd_spin = c["kd_spindown"] * c["d_gain_random"][:, 1:4]
+    tq = torch.zeros(c["num_envs"], 4)
+    foot = torch.where(contact, torch.zeros_like(foot_pos),                                       # :198-199
+                       -p_gains[:, 0] * (foot_pos - c["foot_pos_des"][:, 0]) - d_gains[:, 0] * foot_vel)
+    spring = -c["spring_stiffness"][:, 0] * foot_pos - c["spring_damping"][:, 0] * foot_vel      # :201
+    tq[:, 0] = torch.where(contact, foot + spring, foot)
+    quat_des = a / torch.linalg.norm(a, dim=-1, keepdim=True)                                     # :213
+    quat_act = c["root_states"][:, [6, 3, 4, 5]]
+    err = P3.quaternion_multiply(P3.quaternion_invert(quat_des), quat_act)
+    log_err = P3.so3_log_map(P3.quaternion_to_matrix(err))
+    local_tau = -p_gains[:, 1:4] * log_err - d_gains[:, 1:4] * c["base_ang_vel"]                  # :219
+    tau = P3.Rotate(torch.tensor(c["rot_actuator"])).transform_points(local_tau)                  # :221
+    if "spindown" in ct:                                                                          # :204-206
+        tau = torch.where(contact[:, None], -kd_spin * wheel_vel, tau)
+    tq[:, 1:4] = tau
+    ts_ratio = c["torque_speed_bound_ratio"] * c["torque_speed_bound_ratio_random"]               # :231-237
+    t_bound = c["torque_limits"] * c["torque_limit_random"]
+    w_bound = c["wheel_speed_limits"] * c["wheel_limit_random"]
+    upper = -ts_ratio * t_bound[:, 1:4] / w_bound * (wheel_vel - w_bound)
+    lower = -ts_ratio * t_bound[:, 1:4] / w_bound * (wheel_vel + w_bound)
+    tq[:, 1:4] = torch.clip(tq[:, 1:4], lower, upper)
+    return torch.clip(tq, -t_bound, t_bound), tq

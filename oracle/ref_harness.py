@@ -45,6 +45,11 @@ def import_reference():
                  "isaacgym.gymapi", "isaacgym.gymtorch", "isaacgym.gymutil", "isaacgym.terrain_utils"):
         if name not in sys.modules:
             sys.modules[name] = MagicMock()
+    if isinstance(sys.modules["pytorch3d.transforms"], MagicMock):
+        # the Hopper's torque law really calls these (hopper.py:38,213-221): restated, not mocked
+        from . import pytorch3d_restated
+        sys.modules["pytorch3d.transforms"] = pytorch3d_restated
+        sys.modules["pytorch3d"].transforms = pytorch3d_restated
     if "isaacgym" not in sys.modules or isinstance(sys.modules["isaacgym"], MagicMock):
         pkg = types.ModuleType("isaacgym")
         pkg.__path__ = []
@@ -69,6 +74,8 @@ def import_reference():
     import deep_tube_learning.utils as dtl_utils                          # noqa: E402
     import deep_tube_learning.controllers as controllers                  # noqa: E402
     import deep_tube_learning.custom_sim as custom_sim                    # noqa: E402
+    import legged_gym.envs.hopper.hopper as hopper                        # noqa: E402
+    _imported["hopper"] = hopper
     _imported.update(envs=envs, legged_robot=legged_robot, anymal=anymal, rom_dynamics=rom_dynamics,
                      dtl_utils=dtl_utils, controllers=controllers, custom_sim=custom_sim)
     return SimpleNamespace(**_imported)
@@ -629,3 +636,28 @@ def _install_rom_wrappers(ref):
 
 
 _current_sim = []
+
+
+# --------------------------------------------------------------------------------------------
+# Hopper._compute_torques
+# --------------------------------------------------------------------------------------------
+def reference_hopper_torques(case, actions):
+    """Runs the UNMODIFIED Hopper._compute_torques (legged_gym/envs/hopper/hopper.py:168-237) on a stub `self` that carries exactly the
+    attributes the method reads, built from `case` (oracle.port_hopper.hopper_case).  pytorch3d.transforms = oracle/pytorch3d_restated."""
+    ref = import_reference()
+    N = case["num_envs"]
+    t = lambda k: case[k].clone()
+    dof_state = t("dof_state")                                   # [N, 4, 2], as gymtorch hands it out (hopper uses .view(N, num_dof, 2))
+    stub = SimpleNamespace(
+        cfg=SimpleNamespace(control=SimpleNamespace(control_type=case["control_type"], action_scale=case["action_scale"])),
+        num_envs=N, device="cpu", dof_pos=dof_state[..., 0], dof_vel=dof_state[..., 1], contact_forces=t("contact_forces"),
+        feet_indices=torch.tensor([case["foot_body"]]), foot_joint_index=torch.tensor([0]), wheel_joint_indices=torch.tensor([1, 2, 3]),
+        wxyz_quat_inds=torch.tensor([6, 3, 4, 5]), root_states=t("root_states"), base_ang_vel=t("base_ang_vel"),
+        p_gains=t("p_gains"), d_gains=t("d_gains"), p_gain_random=t("p_gain_random"), d_gain_random=t("d_gain_random"),
+        kd_spindown=t("kd_spindown"), spring_stiffness=t("spring_stiffness"), spring_damping=t("spring_damping"), foot_pos_des=t("foot_pos_des"),
+        torque_speed_bound_ratio=case["torque_speed_bound_ratio"], torque_speed_bound_ratio_random=t("torque_speed_bound_ratio_random"),
+        torque_limits=t("torque_limits"), torque_limit_random=t("torque_limit_random"), wheel_speed_limits=t("wheel_speed_limits"),
+        wheel_limit_random=t("wheel_limit_random"), torques=torch.zeros(N, 4), last_dof_vel=torch.zeros(N, 4), sim_params=SimpleNamespace(dt=0.005),
+        actuator_transform=sys.modules["pytorch3d.transforms"].Rotate(torch.tensor(case["rot_actuator"]), device="cpu"))
+    out = ref.hopper.Hopper._compute_torques(stub, actions.clone())
+    return out, stub.torques

@@ -1,0 +1,85 @@
+"""SURVEY 8f row 3 (part), CPU side: the restated pytorch3d functions against scipy, the oracle port of Hopper._compute_torques against the
+UNMODIFIED reference method (build container) and against the reference-generated fixture (everywhere)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pytorch3d_restated as P3
+from oracle.compare import assert_close, assert_exact
+from oracle.make_golden_hopper import CASES
+from oracle.port_hopper import hopper_case, hopper_torques
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hopper_torques_reference.npz")
+
+
+def test_restated_pytorch3d_against_scipy():
+    from scipy.spatial.transform import Rotation
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(500, 4, generator=g, dtype=torch.float64), torch.randn(500, 4, generator=g, dtype=torch.float64)
+    a, b = a / a.norm(dim=1, keepdim=True), b / b.norm(dim=1, keepdim=True)
+    to_scipy = lambda q: Rotation.from_quat(q[:, [1, 2, 3, 0]].numpy())          # scipy is scalar-last
+    prod = P3.quaternion_multiply(P3.quaternion_invert(a), b)
+    want = to_scipy(a).inv() * to_scipy(b)
+    assert bool((prod[:, 0] >= 0).all())
+    R = P3.quaternion_to_matrix(prod)
+    assert np.allclose(R.numpy(), want.as_matrix(), atol=1e-12)
+    keep = torch.from_numpy(want.magnitude() < 3.0)                               # away from pi the log map is well conditioned
+    assert np.allclose(P3.so3_log_map(R)[keep].numpy(), want.as_rotvec()[keep.numpy()], atol=1e-7)
+    M = Rotation.from_euler("xyz", [0.3, -0.2, 1.1]).as_matrix()
+    pts = torch.randn(50, 3, generator=g, dtype=torch.float64)
+    assert np.allclose(P3.Rotate(torch.tensor(M), dtype=torch.float64).transform_points(pts).numpy(), pts.numpy() @ M, atol=1e-12)
+    # the linear continuation of acos: continuous and first-order exact at the bounds
+    x = torch.tensor([1 - 1e-4, 1 - 0.5e-4, 1.0, -1 + 1e-4, -1.0], dtype=torch.float64)
+    y = P3.acos_linear_extrapolation(x, (-1 + 1e-4, 1 - 1e-4))
+    assert abs(float(y[0]) - np.arccos(1 - 1e-4)) < 1e-12 and abs(float(y[3]) - np.arccos(-1 + 1e-4)) < 1e-12
+    assert float(y[1]) < float(y[0]) and float(y[2]) < float(y[1]) and float(y[4]) > float(y[3])
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_port_matches_reference_golden(name):
+    g = np.load(GOLD)
+    N, seed, ct, ang, over = CASES[name]
+    case, act = hopper_case(N, seed=seed, control_type=ct, max_angle=ang, **over)
+    clipped, torques = hopper_torques(case, act)
+    assert_close(clipped, g[f"{name}_clipped"], 1.0, f"{name}: clipped torques")
+    assert_close(torques, g[f"{name}_torques"], 1.0, f"{name}: self.torques")
+
+
+def test_cases_exercise_every_branch():
+    """The fixtures are only worth something if the clips are not always active and both contact states occur."""
+    for name, (N, seed, ct, ang, over) in CASES.items():
+        case, act = hopper_case(N, seed=seed, control_type=ct, max_angle=ang, **over)
+        clipped, torques = hopper_torques(case, act)
+        contact = case["contact_forces"][:, case["foot_body"], 2] > 0.1
+        assert 0.25 < float(contact.float().mean()) < 0.75
+        tb = case["torque_limits"] * case["torque_limit_random"]
+        inside = (clipped.abs() < tb)[:, 1:]
+        if name != "shipped":
+            assert float(inside.float().mean()) > 0.3, f"{name}: wheel torques saturate everywhere"
+        assert bool(torch.isfinite(clipped).all())
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("ct", ["orientation_spindown", "orientation"])
+@pytest.mark.parametrize("seed,N,ang", [(1, 257, 3.1), (2, 64, 0.01), (3, 500, 1.5)])
+def test_port_equals_unmodified_reference_method(ct, seed, N, ang):
+    from oracle import ref_harness as H
+    case, act = hopper_case(N, seed=seed, control_type=ct, max_angle=ang, torque_limits=[9000.0, 80.0, 80.0, 80.0])
+    want, want_t = H.reference_hopper_torques(case, act)
+    got, got_t = hopper_torques(case, act)
+    assert_exact(got, want, "returned torques")
+    assert_exact(got_t, want_t, "self.torques")
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("ct", ["orientation_w_foot", "V", "T_spindown"])
+def test_reference_cannot_run_the_other_control_types(ct):
+    """Why the port / kernel reject them: the reference method itself raises (shape errors at hopper.py:196 / :224 / :227)."""
+    from oracle import ref_harness as H
+    case, act = hopper_case(16, seed=1, control_type=ct)
+    with pytest.raises((RuntimeError, IndexError)):
+        H.reference_hopper_torques(case, act)
+    with pytest.raises(ValueError):
+        hopper_torques(case, act)
