@@ -119,3 +119,47 @@ def test_trajectory_env_sharding_over_gloo():
         assert torch.equal(torch.from_numpy(obs), fport.obs_buf[lo:hi]), "observations depend on the sharding"
         assert torch.equal(torch.from_numpy(traj), fport.gen.traj[lo:hi]) and torch.equal(torch.from_numpy(perr), fport.prev_error[lo:hi])
         assert abs(rew_sum - total) <= 1e-9 * max(1.0, abs(total))
+
+
+def _family_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from legged_gym_dev_b200.sharding import env_shard
+    from oracle.port_rom import GenPort, gen_params
+    N, cls = 64, "ExtendedLateralUnicycle"
+    lo, hi = env_shard(rank, world, N)
+    gen = GenPort(gen_params(hi - lo, cls, seed=13), env_id_offset=lo)
+    z0 = torch.randn(N, 6, generator=torch.Generator().manual_seed(4)) * 0.3
+    gen.reset(z0[lo:hi].clone())
+    for _ in range(60):
+        gen.step()
+    # the only cross-env quantity a rollout of this generator reports: how many envs are stationary (sum over ranks)
+    st = torch.tensor([float(gen.stationary.sum()), float(hi - lo)], dtype=torch.double)
+    dist.all_reduce(st)
+    q.put((rank, lo, hi, gen.traj.numpy().copy(), gen.v_traj.numpy().copy(), gen.ctr.copy(), st.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_rom_family_generator_sharding_over_gloo():
+    """SURVEY 8f row 4 shards like every other env-indexed path: contiguous env ranges, RNG keyed by the GLOBAL env id, no data-path collective."""
+    from oracle.port_rom import GenPort, gen_params
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_family_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = GenPort(gen_params(64, "ExtendedLateralUnicycle", seed=13))
+    full.reset(torch.randn(64, 6, generator=torch.Generator().manual_seed(4)) * 0.3)
+    for _ in range(60):
+        full.step()
+    for rank, lo, hi, traj, vtraj, ctr, st in out:
+        assert torch.equal(torch.from_numpy(traj), full.traj[lo:hi]) and torch.equal(torch.from_numpy(vtraj), full.v_traj[lo:hi])
+        assert (ctr == full.ctr[lo:hi]).all()
+        assert st[0] == float(full.stationary.sum()) and st[1] == 64

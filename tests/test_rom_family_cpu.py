@@ -114,3 +114,21 @@ def test_extended_lateral_proj_z_extends_extended_unicycle():
     v = x.numpy()[:, 7:9].astype(np.float64)
     assert np.allclose(b[:, 3] ** 2 + b[:, 4] ** 2, (v ** 2).sum(1), rtol=1e-12)            # a rotation of (vx, vy)
     assert np.allclose(np.cos(yaw) * b[:, 3] - np.sin(yaw) * b[:, 4], v[:, 0], atol=1e-12)   # back in the world frame
+
+
+def test_product_classes_fail_loudly_without_cuda():
+    """No CPU fallback: the host mirrors of the family refuse CPU devices / CPU tensors instead of computing something else."""
+    from legged_gym_dev_b200 import rom as R
+    from legged_gym_dev_b200.hopper import HopperActuation
+    for cls in ("Unicycle", "LateralUnicycle", "ExtendedUnicycle", "ExtendedLateralUnicycle"):
+        n, m, _ = FAMILY[cls]
+        assert (R.ROM_CLASSES[cls].n, R.ROM_CLASSES[cls].m) == (n, m)
+        with pytest.raises(RuntimeError, match="CUDA devices only"):
+            R.ROM_CLASSES[cls](0.1, [0.0] * n, [1.0] * n, [0.0] * m, [1.0] * m, device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        R.TrajectoryGenerator(R.SingleInt2D(0.1, [0, 0], [1, 1], [0, 0], [1, 1], device="cpu"), R.UniformSampleHoldDT(1, 2), R.UniformWeightSampler(),
+                              device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        HopperActuation(4, device="cpu")
+    with pytest.raises(NameError, match="Unknown controller type"):
+        HopperActuation(4, control_type="V")

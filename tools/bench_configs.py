@@ -378,6 +378,53 @@ def cpu_port_baselines(quick=False):
     return out
 
 
+def rom_family_step(num_envs=1 << 20, cls="ExtendedLateralUnicycle", steps=100, device="cuda", peak=6535.7):
+    """stand-alone TrajectoryGenerator.step over the 6-state / 3-input rom class through the generic kernels (W = 10 knots,
+    dt_loop 0.02 / rom.dt 0.1: one call in five appends a knot).  Algorithmic bytes per env and call: 4 (P + n + 1 + m) + 8 ((W+1) n + W m) / 5."""
+    from legged_gym_dev_b200 import rom as R
+    zmax, vmax = {"ExtendedLateralUnicycle": ([1e9, 1e9, 1e9, 1.0, 0.5, 2.0], [1.0, 0.6, 4.0]), "Unicycle": ([1e9] * 3, [1.0, 2.0])}[cls]
+    rom = R.ROM_CLASSES[cls](0.1, [-a for a in zmax], zmax, [-a for a in vmax], vmax, n_robots=num_envs, device=device)
+    gen = R.TrajectoryGenerator(rom, R.UniformSampleHoldDT(1.0, 2.0), R.UniformWeightSampler(), dt_loop=0.02, N=10, freq_low=0.01, freq_high=2.0, seed=1,
+                                device=device, prob_stationary=0.0005)
+    gen.reset(torch.randn(num_envs, rom.n, device=device) * 0.3)
+    for _ in range(10):
+        gen.step()
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    for _ in range(steps):
+        gen.step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    n, m, W = rom.n, rom.m, 10
+    per = 4 * (9 * m + 6 + n + 1 + m) + 8 * ((W + 1) * n + W * m) / 5
+    return dict(workload=f"TrajectoryGenerator.step over {cls}, {num_envs} envs", ms_per_step=ms, env_steps_per_s=num_envs / ms * 1e3,
+                algorithmic_bytes_per_env=per, achieved_gbs=per * num_envs / ms / 1e6, frac=per * num_envs / ms / 1e6 / peak)
+
+
+def hopper_torques(num_envs=1 << 20, steps=50, device="cuda", peak=6535.7):
+    """Hopper._compute_torques, 188 algorithmic bytes per env (csrc/hopper.cu)."""
+    from legged_gym_dev_b200.hopper import HopperActuation
+    env = HopperActuation(num_envs, device=device, torque_limits=[9000.0, 80.0, 80.0, 80.0])
+    g = torch.Generator(device=device).manual_seed(1)
+    for t in (env.dof_state, env.root_states, env.base_ang_vel, env.contact_forces):
+        t.normal_(generator=g)
+    act = torch.randn(num_envs, 4, device=device, generator=g)
+    for _ in range(5):
+        env._compute_torques(act)
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    for _ in range(steps):
+        env._compute_torques(act)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return dict(workload=f"Hopper._compute_torques, {num_envs} envs", ms_per_call=ms, env_calls_per_s=num_envs / ms * 1e3,
+                algorithmic_bytes_per_env=188, achieved_gbs=188 * num_envs / ms / 1e6, frac=188 * num_envs / ms / 1e6 / peak)
+
+
 def run_all(device="cuda", peak=6535.7, quick=False):
     out = {}
     for name, fn, kw in (("cfg1_rom_per_call", rom_per_call, dict(device=device, loop_steps=200 if quick else 1000)),
@@ -388,7 +435,9 @@ def run_all(device="cuda", peak=6535.7, quick=False):
                          ("next1_trajectory_env_1048576", trajectory_env, dict(device=device, peak=peak, num_envs=16384 if quick else (1 << 20), steps=20)),
                          ("cfg4_rom_rollout", rom_rollout, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20))),
                          ("cfg4b_tube_dataset", tube_dataset, dict(device=device, peak=peak, num_envs=16384 if quick else 262144)),
-                         ("cfg5_gae_update", gae_update, dict(device=device, peak=peak))):
+                         ("cfg5_gae_update", gae_update, dict(device=device, peak=peak)),
+                         ("next4_rom_family_step", rom_family_step, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20))),
+                         ("next3_hopper_torques", hopper_torques, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20)))):
         try:
             out[name] = fn(**kw)
         except Exception as e:   # an extra must never take the headline line down
