@@ -375,6 +375,27 @@ def cpu_port_baselines(quick=False):
         dt = time.perf_counter() - t0
         out[key] = dict(num_envs=n, steps=steps, ms_per_step=1e3 * dt / steps, env_steps_per_s=n * steps / dt, cores=torch.get_num_threads(),
                         kind="port", sample=f"oracle port of case {case_name}, {n} envs x {steps} steps, {dt:.2f} s")
+    # the generator step over the 6-state rom class and the Hopper torque law, torch on the host cores
+    from oracle.port_rom import GenPort, gen_params
+    from oracle.port_hopper import hopper_case, hopper_torques as port_hopper_torques
+    n, steps = 16384 if quick else 65536, 50
+    gen = GenPort(gen_params(n, "ExtendedLateralUnicycle", N=10, t_low=1.0, t_high=2.0, freq_high=2.0, prob_stationary=0.0005), rng="torch")
+    gen.reset(torch.randn(n, 6) * 0.3)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        gen.step()
+    dt = time.perf_counter() - t0
+    out["next4_rom_family_step_cpu_port"] = dict(num_envs=n, steps=steps, ms_per_step=1e3 * dt / steps, env_steps_per_s=n * steps / dt,
+                                                 cores=torch.get_num_threads(), kind="port",
+                                                 sample=f"oracle GenPort over ExtendedLateralUnicycle, {n} envs x {steps} steps, {dt:.2f} s")
+    case, act = hopper_case(n, seed=1, torque_limits=[9000.0, 80.0, 80.0, 80.0])
+    port_hopper_torques(case, act)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        port_hopper_torques(case, act)
+    dt = time.perf_counter() - t0
+    out["next3_hopper_torques_cpu_port"] = dict(num_envs=n, calls=20, ms_per_call=1e3 * dt / 20, env_calls_per_s=n * 20 / dt, cores=torch.get_num_threads(),
+                                                kind="port", sample=f"oracle port of Hopper._compute_torques, {n} envs x 20 calls, {dt:.2f} s")
     return out
 
 
