@@ -300,6 +300,26 @@ typedef struct B200HopperTorqueBuffers {
 
 int b200gym_hopper_torques(const B200HopperTorqueParams* p, const B200HopperTorqueBuffers* b, void* stream);
 
+/* Hopper.compute_observations (hopper.py:239-258, cfg.terrain.measure_heights = False as shipped, hopper_config.py:13) + the observation
+ * clip of Hopper.step (:116-117): obs [N, 21] = (z * z_pos, base_quat xyzw, base_lin_vel * lin_vel, base_ang_vel * ang_vel,
+ * wheel dof_vel * dof_vel, commands[:3] * commands_scale, actions / |actions| with qw >= 0) + (2u - 1) * noise_scale_vec, u = the
+ * Philox uniforms of (seed, global env id, event, site OBS_NOISE, column) — event = common_step_counter, as in b200gym_post_physics. */
+#define B200GYM_HOPPER_NUM_OBS 21
+typedef struct B200HopperObsParams {
+    int32_t num_envs, add_noise;
+    float z_pos_scale, lin_vel_scale, ang_vel_scale, dof_vel_scale, clip_observations; /* cfg.normalization (hopper_config.py:92-100) */
+    float commands_scale[3];                     /* LeggedRobot._init_buffers: (lin_vel, lin_vel, ang_vel) */
+    float noise_scale_vec[B200GYM_HOPPER_NUM_OBS]; /* Hopper._get_noise_scale_vec (:407-430) */
+    uint32_t seed_lo, seed_hi;
+} B200HopperObsParams;
+int b200gym_hopper_observations(const B200HopperObsParams* p, const float* root_states, const float* base_lin_vel, const float* base_ang_vel,
+                                const float* dof_state, const float* commands, const float* actions, float* obs, uint64_t event,
+                                int64_t env_id_offset, void* stream);
+/* The Hopper's own reward terms (hopper.py:448-458), raw (before scale * dt): out [N, 3] = (_reward_torque_limits = sum |wheel torques|,
+ * _reward_dof_acc = sum ((last_dof_vel - dof_vel) / dt)^2 over the wheels, _reward_unit_quat = (1 - |actions|)^2). */
+int b200gym_hopper_reward_terms(int32_t num_envs, float dt, const float* torques, const float* dof_state, const float* last_dof_vel,
+                                const float* actions, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Group G — rsl_rl rollout storage + PPO update (rsl_rl v1.0.2, a fork of which the reference imports at
  * legged_gym/utils/task_registry.py:37-38; source NOT in /root/reference: arithmetic restated)

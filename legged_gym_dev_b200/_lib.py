@@ -92,6 +92,11 @@ class HopperTorqueParamsPOD(C.Structure):
                 ("wheel_speed_limits", f32 * 3), ("torque_limits", f32 * 4), ("rot_actuator", f32 * 9)]
 
 
+class HopperObsParamsPOD(C.Structure):
+    _fields_ = [("num_envs", i32), ("add_noise", i32), ("z_pos_scale", f32), ("lin_vel_scale", f32), ("ang_vel_scale", f32), ("dof_vel_scale", f32),
+                ("clip_observations", f32), ("commands_scale", f32 * 3), ("noise_scale_vec", f32 * 21), ("seed_lo", u32), ("seed_hi", u32)]
+
+
 _HOPPER_FIELDS = ["actions", "dof_state", "contact_forces", "root_states", "base_ang_vel", "p_gain_random", "d_gain_random", "torque_limit_random",
                   "wheel_limit_random", "spring_stiffness", "spring_damping", "foot_pos_des", "torque_speed_bound_ratio_random", "torques",
                   "torques_clipped"]
@@ -161,6 +166,10 @@ def lib():
         getattr(L, name).restype = C.c_int
     L.b200gym_hopper_torques.argtypes = [C.POINTER(HopperTorqueParamsPOD), C.POINTER(HopperTorqueBuffersPOD), vp]
     L.b200gym_hopper_torques.restype = C.c_int
+    L.b200gym_hopper_observations.argtypes = [C.POINTER(HopperObsParamsPOD), vp, vp, vp, vp, vp, vp, vp, C.c_uint64, C.c_int64, vp]
+    L.b200gym_hopper_observations.restype = C.c_int
+    L.b200gym_hopper_reward_terms.argtypes = [C.c_int32, f32, vp, vp, vp, vp, vp, vp]
+    L.b200gym_hopper_reward_terms.restype = C.c_int
     fp = C.POINTER(RomFamilyParamsPOD)
     L.b200gym_romfam_f.argtypes = [C.c_int32, f32, vp, vp, vp, C.c_int64, vp]
     L.b200gym_romfam_des_pose_vel.argtypes = [C.c_int32, vp, vp, vp, vp, C.c_int64, vp]
@@ -199,7 +208,7 @@ def lib():
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
                       ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD),
                       ("B200RomFamilyParams", RomFamilyParamsPOD), ("B200HopperTorqueParams", HopperTorqueParamsPOD),
-                      ("B200HopperTorqueBuffers", HopperTorqueBuffersPOD)):
+                      ("B200HopperTorqueBuffers", HopperTorqueBuffersPOD), ("B200HopperObsParams", HopperObsParamsPOD)):
         n = L.b200gym_sizeof(name.encode())
         if n != C.sizeof(cls):
             raise RuntimeError(f"ABI mismatch: sizeof({name}) is {n} in the library, {C.sizeof(cls)} in the binding")

@@ -12,6 +12,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "../../include/b200gym.h"
 
 namespace {
@@ -105,7 +106,107 @@ __global__ void __launch_bounds__(256) hopper_torques_kernel(const __grid_consta
                                                                         fminf(fmaxf(tq[2], -tb[2]), tb[2]), fminf(fmaxf(tq[3], -tb[3]), tb[3]));
 }
 
+// Hopper.compute_observations (hopper.py:239-258) + the clip of Hopper.step (:116-117).  One thread per env computes the 21 columns; the
+// [128, 21] tile of a CTA is one contiguous 10.75 KB block of the output, staged in shared memory (row stride 21: conflict-free) and
+// written out with coalesced 128-bit stores.  96 B read + 84 B written per env.
+constexpr int HOBS = B200GYM_HOPPER_NUM_OBS, HT = 128;
+
+__global__ void __launch_bounds__(HT) hopper_obs_kernel(const __grid_constant__ B200HopperObsParams p, const float* __restrict__ root,
+                                                        const float* __restrict__ lin_vel, const float* __restrict__ ang_vel,
+                                                        const float* __restrict__ dof_state, const float* __restrict__ commands,
+                                                        const float* __restrict__ actions, float* __restrict__ obs, unsigned long long event,
+                                                        long long env_off) {
+    __shared__ __align__(16) float tile[HT * HOBS];
+    const int env0 = blockIdx.x * HT, e = threadIdx.x;
+    const int nenv = min(HT, p.num_envs - env0);
+    pdl_launch_dependents();
+    pdl_wait();
+    if (e < nenv) {
+        const size_t i = static_cast<size_t>(env0 + e);
+        float o[HOBS];
+        const float* r = root + i * 13;
+        o[0] = mul_rn(r[2], p.z_pos_scale);
+        o[1] = r[3], o[2] = r[4], o[3] = r[5], o[4] = r[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            o[5 + c] = mul_rn(lin_vel[i * 3 + c], p.lin_vel_scale);
+            o[8 + c] = mul_rn(ang_vel[i * 3 + c], p.ang_vel_scale);
+            o[11 + c] = mul_rn(dof_state[i * 8 + 2 * (1 + c) + 1], p.dof_vel_scale);
+            o[14 + c] = mul_rn(commands[i * 4 + c], p.commands_scale[c]);
+        }
+        const float4 a = *reinterpret_cast<const float4*>(actions + i * 4);   // normalised action quaternion, qw >= 0 (:242-244)
+        const float nrm = sqrtf(add_rn(add_rn(add_rn(mul_rn(a.x, a.x), mul_rn(a.y, a.y)), mul_rn(a.z, a.z)), mul_rn(a.w, a.w)));
+        const float sgn = div_rn(a.x, nrm) < 0.0f ? -1.0f : 1.0f;
+        o[17] = mul_rn(div_rn(a.x, nrm), sgn), o[18] = mul_rn(div_rn(a.y, nrm), sgn), o[19] = mul_rn(div_rn(a.z, nrm), sgn), o[20] = mul_rn(div_rn(a.w, nrm), sgn);
+        if (p.add_noise) {   // obs += (2 * rand_like(obs) - 1) * noise_scale_vec (:257-258); columns 14-20 carry zero scales: no draw needed
+            const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off) + i, event);
+#pragma unroll
+            for (int blk = 0; blk < 4; ++blk) {
+                const uint4 w = rng.words(philox::OBS_NOISE, blk);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = 4 * blk + k;
+                    o[c] = add_rn(o[c], mul_rn(sub_rn(mul_rn(2.0f, philox::u01(philox::word(w, k))), 1.0f), p.noise_scale_vec[c]));
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < HOBS; ++c) tile[e * HOBS + c] = fminf(fmaxf(o[c], -p.clip_observations), p.clip_observations);
+    }
+    __syncthreads();
+    float* dst = obs + static_cast<size_t>(env0) * HOBS;   // 128 * 21 * 4 B per full tile: 16-byte aligned whenever obs is
+    const int total = nenv * HOBS;
+    if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        for (int q = e; q < total / 4; q += HT) reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(tile)[q];
+    } else {
+        for (int q = e; q < total; q += HT) dst[q] = tile[q];
+    }
+}
+
+__global__ void __launch_bounds__(256) hopper_reward_terms_kernel(int n, float dt, const float* __restrict__ torques, const float* __restrict__ dof_state,
+                                                                  const float* __restrict__ last_dof_vel, const float* __restrict__ actions,
+                                                                  float* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (e >= n) return;
+    const size_t i = static_cast<size_t>(e);
+    const float4 tq = *reinterpret_cast<const float4*>(torques + i * 4), lv = *reinterpret_cast<const float4*>(last_dof_vel + i * 4);
+    const float4 a = *reinterpret_cast<const float4*>(actions + i * 4);
+    const float4 d0 = *reinterpret_cast<const float4*>(dof_state + i * 8), d1 = *reinterpret_cast<const float4*>(dof_state + i * 8 + 4);
+    const float tl = add_rn(add_rn(fabsf(tq.y), fabsf(tq.z)), fabsf(tq.w));                                   // :448-450
+    const float q1 = div_rn(sub_rn(lv.y, d0.w), dt), q2 = div_rn(sub_rn(lv.z, d1.y), dt), q3 = div_rn(sub_rn(lv.w, d1.w), dt);
+    const float acc = add_rn(add_rn(mul_rn(q1, q1), mul_rn(q2, q2)), mul_rn(q3, q3));                         // :452-454
+    const float nrm = sqrtf(add_rn(add_rn(add_rn(mul_rn(a.x, a.x), mul_rn(a.y, a.y)), mul_rn(a.z, a.z)), mul_rn(a.w, a.w)));
+    const float uq = sub_rn(1.0f, nrm);                                                                       // :456-458
+    out[i * 3 + 0] = tl, out[i * 3 + 1] = acc, out[i * 3 + 2] = mul_rn(uq, uq);
+}
+
 }  // namespace
+
+extern "C" int b200gym_hopper_observations(const B200HopperObsParams* p, const float* root_states, const float* base_lin_vel, const float* base_ang_vel,
+                                           const float* dof_state, const float* commands, const float* actions, float* obs, uint64_t event,
+                                           int64_t env_id_offset, void* stream) {
+    B200_REQUIRE(p && root_states && base_lin_vel && base_ang_vel && dof_state && commands && actions && obs, B200GYM_EINVAL, "hopper_observations: null argument");
+    B200_REQUIRE(p->num_envs > 0, B200GYM_EINVAL, "hopper_observations: num_envs must be positive (got %d)", p->num_envs);
+    B200_REQUIRE(b200_aligned16(actions), B200GYM_EALIGN, "hopper_observations: actions must be 16-byte aligned");
+    b200_launch_pdl(p->num_envs, hopper_obs_kernel, dim3((p->num_envs + HT - 1) / HT), dim3(HT), 0, static_cast<cudaStream_t>(stream), *p, root_states,
+                    base_lin_vel, base_ang_vel, dof_state, commands, actions, obs, static_cast<unsigned long long>(event), static_cast<long long>(env_id_offset));
+    B200_LAUNCH_CHECK("hopper_observations");
+    return B200GYM_OK;
+}
+
+extern "C" int b200gym_hopper_reward_terms(int32_t num_envs, float dt, const float* torques, const float* dof_state, const float* last_dof_vel,
+                                           const float* actions, float* out, void* stream) {
+    B200_REQUIRE(torques && dof_state && last_dof_vel && actions && out, B200GYM_EINVAL, "hopper_reward_terms: null argument");
+    B200_REQUIRE(num_envs > 0 && dt > 0.0f, B200GYM_EINVAL, "hopper_reward_terms: num_envs and dt must be positive");
+    const void* vec[] = {torques, dof_state, last_dof_vel, actions};
+    for (const void* q : vec) B200_REQUIRE(b200_aligned16(q), B200GYM_EALIGN, "hopper_reward_terms: [N, 4] tensors must be 16-byte aligned");
+    b200_launch_pdl(num_envs, hopper_reward_terms_kernel, dim3((num_envs + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<int>(num_envs), dt,
+                    torques, dof_state, last_dof_vel, actions, out);
+    B200_LAUNCH_CHECK("hopper_reward_terms");
+    return B200GYM_OK;
+}
 
 extern "C" int b200gym_hopper_torques(const B200HopperTorqueParams* p, const B200HopperTorqueBuffers* b, void* stream) {
     B200_REQUIRE(p && b, B200GYM_EINVAL, "hopper_torques: null argument");

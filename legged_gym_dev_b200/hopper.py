@@ -1,11 +1,14 @@
 """The Hopper's torque law behind the reference's own method name (first part).
 
-`HopperActuation` carries the tensors Hopper._compute_torques reads, under the names the reference class gives them
+`HopperActuation` carries the tensors Hopper._compute_torques, compute_observations and the Hopper's own reward terms read, under the names the reference class gives them
 (legged_gym/envs/hopper/hopper.py:44-69,343-403): dof_pos / dof_vel views of dof_state, contact_forces, root_states, base_ang_vel,
 p_gains / d_gains and their per-env random multipliers, spring_stiffness / spring_damping / foot_pos_des, kd_spindown, the torque and
 wheel-speed limits with their multipliers, torques.  `_compute_torques(actions)` (hopper.py:168-237) is ONE launch of
 b200gym_hopper_torques and returns the limit-clipped torques, leaving `self.torques` as the reference does (clipped to the
-torque-speed envelope only).  The rest of the Hopper env (observations, rewards, resets, hopper_trajectory.py) is not built yet.
+torque-speed envelope only).  `compute_observations()` (hopper.py:239-258 + the clip of step, :116-117; noise uniforms = Philox keyed by
+(seed, global env id, common_step_counter)) and `_reward_torque_limits / _reward_dof_acc / _reward_unit_quat` (:448-458) are one launch
+each.  The rest of the Hopper env (post_physics_step's callback / push timers, the inherited reward terms and reward assembly, reset_idx with
+its domain-randomisation draws, hopper_trajectory.py) is not built yet.
 
 Control types: "orientation_spindown" (shipped, hopper_config.py:63) and "orientation".  The reference's "w_foot" branch (:195-196)
 fails on a [num_envs, 1] vs [num_envs] broadcast and its "V" / "T" branches (:223-227) on a [num_envs] vs [3] index broadcast, so
@@ -16,6 +19,9 @@ import torch
 from . import _lib
 
 # hopper_config.py:35-55,62-63,76-89; asset effort limits from the hopper URDF are an input (torque_limits)
+# hopper_config.py:92-112 (normalization + noise); 21 observations (hopper_config.py:6), measure_heights False (:13)
+DEFAULT_OBS_CFG = dict(z_pos=1.0, lin_vel=0.5, ang_vel=0.25, dof_vel=0.01, clip_observations=100.0, add_noise=True, noise_level=1.0,
+                       noise_scales=dict(z_pos=0.02, quat=0.05, lin_vel=0.1, ang_vel=0.2, dof_vel=1.5))
 DEFAULT_CFG = dict(control_type="orientation_spindown", action_scale=1.0, p_gains=[900.0, 15.0, 15.0, 0.0], d_gains=[60.0, 3.0, 3.0, 0.0],
                    kd_spindown=[0.1, 0.1, 0.1], foot_pos_des=0.021, spring_stiffness=7000.0, spring_damping=4.0, torque_speed_bound_ratio=6.0,
                    rot_actuator=[[-0.8165, 0.2511, 0.2511], [-0.0, -0.7643, 0.7643], [-0.5773, -0.5939, -0.5939]],
@@ -25,7 +31,7 @@ DEFAULT_CFG = dict(control_type="orientation_spindown", action_scale=1.0, p_gain
 class HopperActuation:
     num_dof = num_actions = 4
 
-    def __init__(self, num_envs, num_bodies=5, foot_body=4, device="cuda", **cfg):
+    def __init__(self, num_envs, num_bodies=5, foot_body=4, device="cuda", obs_cfg=None, seed=0, env_id_offset=0, dt=0.02, **cfg):
         c = dict(DEFAULT_CFG)
         unknown = set(cfg) - set(c)
         if unknown:
@@ -64,6 +70,48 @@ class HopperActuation:
         p.wheel_speed_limits[:], p.torque_limits[:] = c["wheel_speed_limits"], c["torque_limits"]
         p.rot_actuator[:] = [float(x) for row in c["rot_actuator"] for x in row]
         self._p = p
+        # observations + reward terms (hopper.py:239-258,407-430,448-458)
+        oc = dict(DEFAULT_OBS_CFG)
+        oc.update(obs_cfg or {})
+        self.obs_cfg, self.dt, self.seed, self.env_id_offset, self.common_step_counter = oc, float(dt), int(seed), int(env_id_offset), 0
+        self.add_noise = bool(oc["add_noise"])
+        self.base_lin_vel, self.commands, self.actions, self.last_dof_vel = zeros(N, 3), zeros(N, 4), zeros(N, 4), zeros(N, 4)
+        self.obs_buf, self._terms = zeros(N, 21), zeros(N, 3)
+        self.commands_scale = f([oc["lin_vel"], oc["lin_vel"], oc["ang_vel"]])
+        ns, lv = oc["noise_scales"], oc["noise_level"]
+        nv = [ns["z_pos"] * lv * oc["z_pos"]] + [ns["quat"] * lv] * 4 + [ns["lin_vel"] * lv * oc["lin_vel"]] * 3 + [ns["ang_vel"] * lv * oc["ang_vel"]] * 3 \
+            + [ns["dof_vel"] * lv * oc["dof_vel"]] * 3 + [0.0] * 7                                       # _get_noise_scale_vec, :407-430
+        self.noise_scale_vec = f(nv)
+        op = _lib.HopperObsParamsPOD()
+        op.num_envs, op.add_noise = N, int(self.add_noise)
+        op.z_pos_scale, op.lin_vel_scale, op.ang_vel_scale, op.dof_vel_scale = oc["z_pos"], oc["lin_vel"], oc["ang_vel"], oc["dof_vel"]
+        op.clip_observations = oc["clip_observations"]
+        op.commands_scale[:] = [oc["lin_vel"], oc["lin_vel"], oc["ang_vel"]]
+        op.noise_scale_vec[:] = self.noise_scale_vec.tolist()
+        op.seed_lo, op.seed_hi = self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF
+        self._op = op
+
+    def compute_observations(self):
+        """hopper.py:239-258 (+ the clip of :116-117) into self.obs_buf; the noise event is self.common_step_counter, as in the legged env."""
+        _lib.check(self.lib.b200gym_hopper_observations(self._op, _lib.ptr(self.root_states), _lib.ptr(self.base_lin_vel), _lib.ptr(self.base_ang_vel),
+                                                        _lib.ptr(self.dof_state), _lib.ptr(self.commands), _lib.ptr(self.actions), _lib.ptr(self.obs_buf),
+                                                        int(self.common_step_counter), self.env_id_offset, _lib.stream_ptr(self.device)),
+                   "hopper_observations")
+        return self.obs_buf
+
+    def _reward_terms(self):
+        _lib.check(self.lib.b200gym_hopper_reward_terms(self.num_envs, self.dt, _lib.ptr(self.torques), _lib.ptr(self.dof_state), _lib.ptr(self.last_dof_vel),
+                                                        _lib.ptr(self.actions), _lib.ptr(self._terms), _lib.stream_ptr(self.device)), "hopper_reward_terms")
+        return self._terms
+
+    def _reward_torque_limits(self):                                      # hopper.py:448-450
+        return self._reward_terms()[:, 0]
+
+    def _reward_dof_acc(self):                                            # :452-454
+        return self._reward_terms()[:, 1]
+
+    def _reward_unit_quat(self):                                          # :456-458
+        return self._reward_terms()[:, 2]
 
     def load(self, **tensors):
         """Copies state / randomised-property tensors in by the reference's attribute names (shapes checked)."""

@@ -22,6 +22,12 @@ def main():
         case, act = hopper_case(N, seed=seed, control_type=ct, max_angle=ang, **over)
         clipped, torques = H.reference_hopper_torques(case, act)
         out[f"{name}_clipped"], out[f"{name}_torques"] = clipped.numpy(), torques.numpy()
+    # observations (with / without noise) and the Hopper's own reward terms, from the unmodified methods (hopper.py:239-258,407-430,448-458)
+    from oracle.port_hopper import OBS_CFG, obs_case
+    case = obs_case(160, seed=9)
+    for tag, cfg in (("noise", OBS_CFG), ("plain", dict(OBS_CFG, add_noise=False, clip_observations=1.5))):
+        obs, nv, terms = H.reference_hopper_observations(case, cfg, seed=5, event=7)
+        out[f"obs_{tag}"], out["noise_scale_vec"], out["reward_terms"] = obs.numpy(), nv.numpy(), terms.numpy()
     path = os.path.join(ROOT, "tests", "golden", "hopper_torques_reference.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

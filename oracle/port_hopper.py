@@ -87,3 +87,56 @@ def hopper_torques(case, actions):
     lower = -ts_ratio * t_bound[:, 1:4] / w_bound * (wheel_vel + w_bound)
     tq[:, 1:4] = torch.clip(tq[:, 1:4], lower, upper)
     return torch.clip(tq, -t_bound, t_bound), tq
+
+
+# ---- observations + the Hopper's own reward terms (hopper.py:239-258, 407-430, 448-458) -------------------------------------------
+OBS_CFG = dict(z_pos=1.0, lin_vel=0.5, ang_vel=0.25, dof_vel=0.01, clip_observations=100.0, add_noise=True, noise_level=1.0,
+               noise_scales=dict(z_pos=0.02, quat=0.05, lin_vel=0.1, ang_vel=0.2, dof_vel=1.5))      # hopper_config.py:92-112
+
+
+def noise_scale_vec(cfg=OBS_CFG):
+    """Hopper._get_noise_scale_vec, :407-430 (measure_heights False)."""
+    ns, lv = cfg["noise_scales"], cfg["noise_level"]
+    v = torch.zeros(21)
+    v[0] = ns["z_pos"] * lv * cfg["z_pos"]
+    v[1:5] = ns["quat"] * lv
+    v[5:8] = ns["lin_vel"] * lv * cfg["lin_vel"]
+    v[8:11] = ns["ang_vel"] * lv * cfg["ang_vel"]
+    v[11:14] = ns["dof_vel"] * lv * cfg["dof_vel"]
+    return v
+
+
+def obs_case(num_envs, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    root = rn(num_envs, 13)
+    root[:, 3:7] = root[:, 3:7] / torch.linalg.norm(root[:, 3:7], dim=1, keepdim=True)
+    return dict(num_envs=num_envs, root_states=root, base_lin_vel=rn(num_envs, 3), base_ang_vel=rn(num_envs, 3) * 3.0,
+                dof_state=torch.stack((rn(num_envs, 4), rn(num_envs, 4) * 150.0), dim=-1), commands=rn(num_envs, 4) * 0.3,
+                actions=rn(num_envs, 4) * torch.rand(num_envs, 1, generator=g) * 2.0, last_dof_vel=rn(num_envs, 4) * 150.0, torques=rn(num_envs, 4) * 2.0)
+
+
+def hopper_observations(case, cfg=OBS_CFG, seed=0, event=1, env_id_offset=0):
+    """compute_observations :239-258 followed by the clip of step :116-117; noise uniforms = Philox (seed, env, event, OBS_NOISE, column)."""
+    from . import philox as PH
+    c = case
+    a = c["actions"].clone()
+    a /= torch.linalg.norm(a, dim=-1, keepdim=True)
+    a[a[:, 0] < 0, :] *= -1
+    scale = torch.tensor([cfg["lin_vel"], cfg["lin_vel"], cfg["ang_vel"]])
+    obs = torch.cat((c["root_states"][:, 2][:, None] * cfg["z_pos"], c["root_states"][:, 3:7], c["base_lin_vel"] * cfg["lin_vel"],
+                     c["base_ang_vel"] * cfg["ang_vel"], c["dof_state"][:, 1:4, 1] * cfg["dof_vel"], c["commands"][:, :3] * scale, a), dim=-1)
+    if cfg["add_noise"]:
+        import numpy as np
+        u = torch.from_numpy(PH.uniform01(seed, np.arange(c["num_envs"]) + env_id_offset, event, PH.SITE_OBS_NOISE, 21))
+        obs += (2 * u - 1) * noise_scale_vec(cfg)
+    return torch.clip(obs, -cfg["clip_observations"], cfg["clip_observations"])
+
+
+def hopper_reward_terms(case, dt):
+    """_reward_torque_limits, _reward_dof_acc, _reward_unit_quat (:448-458), raw."""
+    c = case
+    tl = torch.sum(torch.abs(c["torques"][:, 1:4]), dim=1)
+    acc = torch.sum(torch.square((c["last_dof_vel"][:, 1:4] - c["dof_state"][:, 1:4, 1]) / dt), dim=1)
+    uq = torch.square(1 - torch.linalg.norm(c["actions"], dim=-1))
+    return torch.stack((tl, acc, uq), dim=1)

@@ -661,3 +661,29 @@ def reference_hopper_torques(case, actions):
         actuator_transform=sys.modules["pytorch3d.transforms"].Rotate(torch.tensor(case["rot_actuator"]), device="cpu"))
     out = ref.hopper.Hopper._compute_torques(stub, actions.clone())
     return out, stub.torques
+
+
+def reference_hopper_observations(case, cfg, seed=0, event=1):
+    """The UNMODIFIED Hopper._get_noise_scale_vec + Hopper.compute_observations (hopper.py:407-430, 239-258) + the clip of step (:116-117)
+    on a stub `self`; torch.rand_like goes through the shim (site OBS_NOISE, event = common_step_counter)."""
+    ref = import_reference()
+    rng_shim.install()
+    N = case["num_envs"]
+    ns = SimpleNamespace
+    t = lambda k: case[k].clone()
+    dof_state = t("dof_state")
+    hcfg = ns(noise=ns(add_noise=cfg["add_noise"], noise_level=cfg["noise_level"], noise_scales=ns(**cfg["noise_scales"])),
+              terrain=ns(measure_heights=False), normalization=ns(clip_observations=cfg["clip_observations"]))
+    obs_scales = ns(z_pos=cfg["z_pos"], lin_vel=cfg["lin_vel"], ang_vel=cfg["ang_vel"], dof_vel=cfg["dof_vel"], height_measurements=5.0)
+    stub = ns(cfg=hcfg, obs_scales=obs_scales, obs_buf=torch.zeros(N, 21), actions=t("actions"), root_states=t("root_states"),
+              base_quat=t("root_states")[:, 3:7], base_lin_vel=t("base_lin_vel"), base_ang_vel=t("base_ang_vel"), dof_vel=dof_state[..., 1],
+              wheel_joint_indices=torch.tensor([1, 2, 3]), commands=t("commands"),
+              commands_scale=torch.tensor([cfg["lin_vel"], cfg["lin_vel"], cfg["ang_vel"]]), last_dof_vel=t("last_dof_vel"), torques=t("torques"),
+              dt=case.get("dt", 0.02))
+    H = ref.hopper.Hopper
+    stub.noise_scale_vec = H._get_noise_scale_vec(stub, hcfg)
+    with rng_shim.draws(seed, np.arange(N), event, [(P.SITE_OBS_NOISE, 0)]):
+        H.compute_observations(stub)
+    obs = torch.clip(stub.obs_buf, -cfg["clip_observations"], cfg["clip_observations"])
+    terms = torch.stack((H._reward_torque_limits(stub), H._reward_dof_acc(stub), H._reward_unit_quat(stub)), dim=1)
+    return obs, stub.noise_scale_vec, terms

@@ -83,3 +83,29 @@ def test_reference_cannot_run_the_other_control_types(ct):
         H.reference_hopper_torques(case, act)
     with pytest.raises(ValueError):
         hopper_torques(case, act)
+
+
+# ---- observations + the Hopper's own reward terms ---------------------------------------------------------------------------------
+def test_observation_port_matches_reference_golden():
+    from oracle.port_hopper import OBS_CFG, hopper_observations, hopper_reward_terms, noise_scale_vec, obs_case
+    g = np.load(GOLD)
+    case = obs_case(160, seed=9)
+    assert_exact(noise_scale_vec(), g["noise_scale_vec"], "noise_scale_vec")
+    assert_close(hopper_observations(case, OBS_CFG, seed=5, event=7), g["obs_noise"], 1.0, "observations with noise")
+    plain = hopper_observations(case, dict(OBS_CFG, add_noise=False, clip_observations=1.5), seed=5, event=7)
+    assert_close(plain, g["obs_plain"], 1.0, "observations, no noise, clipped at 1.5")
+    assert float(plain.abs().max()) == 1.5 and bool((plain[:, 17] >= 0).all())       # the clip bites; qw >= 0 convention
+    assert_close(hopper_reward_terms(case, 0.02), g["reward_terms"], 1.0, "reward terms")
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("N,seed", [(200, 1), (33, 2)])
+def test_observation_port_equals_unmodified_reference_methods(N, seed):
+    from oracle import ref_harness as H
+    from oracle.port_hopper import OBS_CFG, hopper_observations, hopper_reward_terms, noise_scale_vec, obs_case
+    case = obs_case(N, seed)
+    for cfg in (OBS_CFG, dict(OBS_CFG, add_noise=False), dict(OBS_CFG, noise_level=3.0, clip_observations=2.0)):
+        want, nv, terms = H.reference_hopper_observations(case, cfg, seed=5, event=7)
+        assert_exact(noise_scale_vec(cfg), nv, "noise_scale_vec")
+        assert_exact(hopper_observations(case, cfg, seed=5, event=7), want, "observations")
+        assert_exact(hopper_reward_terms(case, 0.02), terms, "reward terms")

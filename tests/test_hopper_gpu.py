@@ -99,3 +99,54 @@ def test_full_size_properties_1m():
     for sl in (slice(0, half), slice(half, N)):
         sub = dict(case, num_envs=half, **{k: case[k][sl] for k in STATE})
         assert torch.equal(make_env(sub)._compute_torques(act[sl].cuda()), out[sl])
+
+
+# ---- observations + the Hopper's own reward terms ---------------------------------------------------------------------------------
+OBS_STATE = ("root_states", "base_lin_vel", "base_ang_vel", "dof_state", "commands", "actions", "last_dof_vel", "torques")
+
+
+def make_obs_env(case, cfg, seed=5, env_id_offset=0):
+    env = HopperActuation(case["num_envs"], device="cuda", obs_cfg=cfg, seed=seed, env_id_offset=env_id_offset, dt=0.02)
+    env.load(**{k: case[k] for k in OBS_STATE})
+    env.common_step_counter = 7
+    return env
+
+
+def test_observations_match_reference_golden():
+    from oracle.port_hopper import OBS_CFG, obs_case
+    g = np.load(GOLD)
+    case = obs_case(160, seed=9)
+    env = make_obs_env(case, OBS_CFG)
+    assert_close(env.noise_scale_vec, g["noise_scale_vec"], 1.0, "noise_scale_vec")
+    assert_close(env.compute_observations(), g["obs_noise"], 1.0, "observations with noise")
+    assert_close(make_obs_env(case, dict(OBS_CFG, add_noise=False, clip_observations=1.5)).compute_observations(), g["obs_plain"], 1.0, "plain observations")
+    for j, name in enumerate(("_reward_torque_limits", "_reward_dof_acc", "_reward_unit_quat")):
+        assert_close(getattr(env, name)(), g["reward_terms"][:, j], 1.0, name)
+
+
+@pytest.mark.parametrize("N", [1, 127, 128, 1000, 4099])
+def test_observations_parity_ragged(N):
+    from oracle.port_hopper import OBS_CFG, hopper_observations, hopper_reward_terms, obs_case
+    case = obs_case(N, seed=N)
+    for cfg in (OBS_CFG, dict(OBS_CFG, add_noise=False), dict(OBS_CFG, noise_level=3.0, clip_observations=2.0)):
+        env = make_obs_env(case, cfg)
+        assert_close(env.compute_observations(), hopper_observations(case, cfg, seed=5, event=7), 1.0, f"observations {N}")
+        assert_close(env._reward_terms(), hopper_reward_terms(case, 0.02), 1.0, f"reward terms {N}")
+
+
+def test_observations_shard_invariance_1m():
+    """1 048 576 envs: two half-size launches with global env ids equal the whole (noise keyed by global id); without noise the clipped
+    observation is a pure function of the env's own row; the action block is a unit quaternion with qw >= 0."""
+    from oracle.port_hopper import OBS_CFG, obs_case
+    N = 1 << 20
+    case = obs_case(N, seed=3)
+    whole = make_obs_env(case, OBS_CFG).compute_observations().clone()
+    half = N // 2
+    for lo in (0, half):
+        sub = dict(case, num_envs=half, **{k: case[k][lo:lo + half] for k in OBS_STATE})
+        assert torch.equal(make_obs_env(sub, OBS_CFG, env_id_offset=lo).compute_observations(), whole[lo:lo + half])
+    q = whole[:, 17:21]
+    assert bool((q[:, 0] >= 0).all()) and float((q.norm(dim=1) - 1).abs().max()) < 1e-5
+    plain = make_obs_env(case, dict(OBS_CFG, add_noise=False)).compute_observations()
+    assert torch.equal(plain[:, 1:5], case["root_states"][:, 3:7].cuda()) and torch.equal(plain[:, 14:], whole[:, 14:])
+    assert float((whole - plain)[:, :14].abs().max()) <= 0.0501 and float((whole - plain)[:, :14].abs().max()) > 0.04
