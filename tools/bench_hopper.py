@@ -32,4 +32,17 @@ for N in (4096, 65536, 1 << 20, 1 << 22):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
     out["sizes"][N] = dict(ms=ms, gbs=188 * N / ms / 1e6, frac=188 * N / ms / 1e6 / PEAK, env_calls_per_s=N / ms * 1e3)
+    # compute_observations: 96 B read + 84 B written per env
+    env.base_lin_vel.normal_(generator=g)
+    env.actions.copy_(act)
+    for _ in range(5):
+        env.compute_observations()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        env.compute_observations()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    out["sizes"][N]["observations"] = dict(ms=ms, gbs=180 * N / ms / 1e6, frac=180 * N / ms / 1e6 / PEAK)
 print(json.dumps(out))
