@@ -623,7 +623,11 @@ int b200gym_romfam_gen_step(const B200RomFamilyParams* p, const B200RomState* s,
     const size_t smem = static_cast<size_t>(FT) * ((p->window + 1) * n_of[p->rom_type] + p->window * m_of[p->rom_type]) * sizeof(float);
     if (tile_on && smem <= 200 * 1024) {
         FAM_DISPATCH(p->rom_type, {
-            if (smem + 1024 > 48 * 1024) cudaFuncSetAttribute(fam_step_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            static size_t granted = 0;   // per rom class: raise the dynamic shared-memory limit once per size, not on every call
+            if (smem + 1024 > 48 * 1024 && smem > granted) {
+                cudaFuncSetAttribute(fam_step_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                granted = smem;
+            }
             b200_launch_pdl(p->num_envs, fam_step_tile_kernel<T>, dim3(grid), dim3(FT), smem, st, *p, *s, step_mask, (long long)env_id_offset);
         });
     } else {
