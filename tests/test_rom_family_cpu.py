@@ -132,3 +132,30 @@ def test_product_classes_fail_loudly_without_cuda():
         HopperActuation(4, device="cpu")
     with pytest.raises(NameError, match="Unknown controller type"):
         HopperActuation(4, control_type="V")
+
+
+def test_c_abi_argument_checks_need_no_gpu():
+    """The argument validation of the new entry points runs before any CUDA call: wrong rom types / null buffers / bad windows come back as
+    B200GYM_EINVAL with a message, on a machine without a GPU too."""
+    import ctypes as C
+    from legged_gym_dev_b200 import _lib
+    L = _lib.lib()
+    err = lambda: L.b200gym_last_error().decode()
+    one = C.c_void_p(16)       # never dereferenced: the checks reject the call first
+    assert L.b200gym_romfam_f(9, 0.1, one, one, one, 4, None) == -1 and "unknown rom_type 9" in err()
+    assert L.b200gym_romfam_f(2, 0.1, None, one, one, 4, None) == -1 and "null argument" in err()
+    assert L.b200gym_romfam_proj_z(3, one, one, 0, None) == -1 and "n_rows" in err()
+    p = _lib.RomFamilyParamsPOD()
+    s = _lib.RomStatePOD()
+    p.num_envs, p.rom_type, p.window, p.dN, p.rom_dt = 8, 5, 1, 1, 0.1
+    assert L.b200gym_romfam_gen_step(p, s, None, 0, None) == -1 and "window" in err()
+    p.window = 6
+    assert L.b200gym_romfam_gen_step(p, s, None, 0, None) == -1 and "null state tensor" in err()
+    p.rom_dt = 0.0
+    assert L.b200gym_romfam_input_bounds(p, one, None, one, one, None, 4, None) == -1 and "rom_dt" in err()
+    hp, hb = _lib.HopperTorqueParamsPOD(), _lib.HopperTorqueBuffersPOD()
+    hp.num_envs, hp.num_bodies, hp.foot_body = 8, 5, 7
+    assert L.b200gym_hopper_torques(hp, hb, None) == -1 and "foot_body" in err()
+    hp.foot_body = 4
+    assert L.b200gym_hopper_torques(hp, hb, None) == -1 and "null buffer" in err()
+    assert L.b200gym_hopper_reward_terms(8, 0.0, one, one, one, one, one, None) == -1 and "positive" in err()

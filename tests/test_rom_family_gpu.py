@@ -1,7 +1,6 @@
 """SURVEY 8f row 4 on the GPU: the generic rom-family kernels (csrc/rom_family.cu, through the C ABI) against the CPU oracle port and the
 reference-generated fixture.  Masks / clocks / counters (t, k, stationary flags, draw-event counters) bit-exact; fp32 state within 1e-5
 (S = 1).  For the integrator classes the generic kernels must equal the register-resident ones of csrc/rom.cu bit for bit."""
-import os
 
 import numpy as np
 import pytest
