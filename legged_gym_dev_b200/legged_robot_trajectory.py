@@ -107,7 +107,7 @@ class LeggedRobotTrajectory(LeggedRobot):
             self.rom, _T_SAMPLERS[tc.t_samp_cls](tc.t_low, tc.t_high, backend="torch", device=self.device),
             _W_SAMPLERS[tc.weight_samp_cls](), dt_loop=self.dt, N=tc.N, freq_low=tc.freq_low, freq_high=tc.freq_high,
             seed=tc.seed, backend="torch", device=self.device, prob_stationary=tc.prob_stationary, dN=tc.dN,
-            env_id_offset=self.env_id_offset)
+            env_id_offset=self.env_id_offset, generic_kernels=False)   # the env drives b200gym_rom_step itself (views, gen_kind)
 
     # ------------------------------------------------------------------ buffers (legged_robot_trajectory.py:584-661)
     def _init_buffers(self):

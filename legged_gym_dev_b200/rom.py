@@ -251,7 +251,7 @@ class TrajectoryGenerator:
     kind = 0   # B200GYM_GEN_RANDOM; the deterministic subclasses below override it
 
     def __init__(self, rom, t_sampler, weight_sampler, dt_loop=0.02, N=4, freq_low=0.01, freq_high=10, seed=42,
-                 backend="torch", device="cuda", prob_stationary=.01, dN=1, env_id_offset=0, model=None, generic_kernels=False):
+                 backend="torch", device="cuda", prob_stationary=.01, dN=1, env_id_offset=0, model=None, generic_kernels=None):
         if backend != "torch":
             raise ValueError("backend must be 'torch'")
         self.device = torch.device(device)
@@ -278,17 +278,22 @@ class TrajectoryGenerator:
         self.center = z(n, 2) if self.kind == 3 else None
         self._model = model
         self._sim = None
-        # the unicycle-family classes are served only by the generic kernels (csrc/rom_family.cu); `generic_kernels=True` routes the
-        # integrator classes through them too (step / step_idx; reset / get_input_t always are) — the two paths agree bit for bit
+        # the unicycle-family classes are served only by the generic kernels (csrc/rom_family.cu).  For the integrator classes both kernel
+        # sets exist and agree bit for bit (tests/test_rom_family_gpu.py); `generic_kernels` picks the one behind step / step_idx (reset(z) /
+        # get_input_t always use the generic ones): None = the generic, window-staging kernels for a stand-alone random generator (measured
+        # 1.4-1.6x the register-resident ones at 1 M envs, profiles/r1_rom_family_hopper.md), the register-resident ones of csrc/rom.cu as soon
+        # as a model / CustomSim / trajectory env is attached (they also refresh the env's interpolated trajectory and observation views).
+        if generic_kernels is None:
+            generic_kernels = self.kind == 0 and model is None
         self._family = rom.kind > DOUBLE_INT_2D or bool(generic_kernels)
         if self._family and (self.kind != 0 or model is not None):
             raise ValueError("the generic rom-family kernels serve the stand-alone random TrajectoryGenerator only")
         self._build_family_pod()
-        if self._family:
+        if rom.kind > DOUBLE_INT_2D:
             self._p = None
             _lib.check(self.lib.b200gym_romfam_gen_init(self._fp, self._s, self.env_id_offset, _lib.stream_ptr(dev)), "romfam_gen_init")
             return
-        self._build_pod()
+        self._build_pod()      # the integrator classes always carry both parameter blocks; `_family` only selects the step kernels
         _lib.check(self.lib.b200gym_rom_init(self._p, self._s, self.env_id_offset, _lib.stream_ptr(dev)), "rom_init")
 
     # ---- POD structs ----------------------------------------------------------------------------
@@ -312,11 +317,13 @@ class TrajectoryGenerator:
         p.weight_zero_col = getattr(self.weight_sampler, "zero_col", -1)
         p.seed_lo, p.seed_hi = self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF
         self._fp = p
-        if self._family:
+        if rom.kind > DOUBLE_INT_2D:
             self._s = self._state_pod()
 
     def _build_pod(self, sim=None):
         rom, model = self.rom, self._model
+        if sim is not None and rom.kind <= DOUBLE_INT_2D:
+            self._family = False      # an attached env needs its views refreshed by rom_step
         p = _lib.RomParamsPOD()
         p.num_envs, p.rom_type = rom.n_robots, rom.kind
         p.model_type = model.kind if model is not None else rom.kind
@@ -376,7 +383,7 @@ class TrajectoryGenerator:
 
     def step_idx(self, idx):
         m, mp = self._mask_ptr(idx)
-        if self._family:
+        if self._family and not (self._s.env_trajectory or self._s.obs):     # attached views are refreshed by b200gym_rom_step only
             _lib.check(self.lib.b200gym_romfam_gen_step(self._fp, self._s, mp, self.env_id_offset, _lib.stream_ptr(self.device)),
                        "romfam_gen_step")
             return

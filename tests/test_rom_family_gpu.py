@@ -149,7 +149,8 @@ def test_generic_kernels_equal_register_kernels_bitwise(cls, over):
     registers) and through b200gym_romfam_gen_step (horizon in HBM) — every tensor identical, every step."""
     N = 777
     p = gen_params(N, cls, seed=4, **over)
-    a, b = make_gen(p), make_gen(p, generic_kernels=True)
+    a, b = make_gen(p, generic_kernels=False), make_gen(p, generic_kernels=True)
+    assert not a._family and b._family and make_gen(p)._family      # stand-alone generators default to the window-staging kernels
     z0 = (torch.randn(N, a.rom.n, generator=torch.Generator().manual_seed(2)) * 0.4).cuda()
     a.reset(z0)
     b.reset(z0)

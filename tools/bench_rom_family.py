@@ -62,7 +62,7 @@ for cls, (zmax, vmax) in SPEC.items():
     rec["step"] = dict(ms=ms, gbs=per * N / ms / 1e6, frac=per * N / ms / 1e6 / PEAK, bytes_per_env=per, env_steps_per_s=N / ms * 1e3)
     if cls in ("SingleInt2D", "DoubleInt2D"):      # the register-resident kernels of csrc/rom.cu on the same state
         ref = R.TrajectoryGenerator(rom, R.UniformSampleHoldDT(1.0, 2.0), R.UniformWeightSampler(), dt_loop=dt_loop, N=Wn, freq_low=0.01, freq_high=2.0,
-                                    seed=1, device="cuda", prob_stationary=0.0005)
+                                    seed=1, device="cuda", prob_stationary=0.0005, generic_kernels=False)
         ref.reset(z0)
         for _ in range(10):
             ref.step()
