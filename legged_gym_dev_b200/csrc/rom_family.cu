@@ -212,21 +212,16 @@ __global__ void fam_init_kernel(const __grid_constant__ B200RomFamilyParams p, c
     s.rng_ctr[i] = static_cast<int32_t>(ctr + 1);
 }
 
+// TrajectoryGenerator.reset_idx for one env (rom_dynamics.py:595-605); tr / vt = this env's horizon windows (HBM or a shared-memory tile)
 template <int T>
-__global__ void __launch_bounds__(128) fam_reset_kernel(const __grid_constant__ B200RomFamilyParams p, const __grid_constant__ B200RomState s,
-                                                        const float* __restrict__ z_in, const uint8_t* __restrict__ mask, long long env_off) {
+__device__ __forceinline__ void reset_env(const B200RomFamilyParams& p, const B200RomState& s, size_t i, uint64_t genv, const float* __restrict__ z_in,
+                                          bool in_idx, float* tr, float* vt) {
     constexpr int RN = Rom<T>::n, M = Rom<T>::m;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= p.num_envs) return;
-    const size_t i = static_cast<size_t>(e);
-    const uint64_t genv = static_cast<uint64_t>(env_off) + i;
     const int w = p.window;
-    float* tr = s.trajectory + i * (w + 1) * RN;
-    float* vt = s.v_trajectory + i * w * M;
     GenP<M> g;
     load_params(s, i, g);
     float z[RN];
-    if (mask == nullptr || mask[i] != 0) {
+    if (in_idx) {
         // reset_idx, :596-602: windows cleared, last knot = z, clocks rewound to -W knots, parameters resampled from z
 #pragma unroll
         for (int c = 0; c < RN; ++c) z[c] = z_in[i * RN + c];
@@ -264,6 +259,16 @@ __global__ void __launch_bounds__(128) fam_reset_kernel(const __grid_constant__ 
     store_params(s, i, g);
 #pragma unroll
     for (int c = 0; c < M; ++c) s.v[i * M + c] = g.v[c];
+}
+
+template <int T>
+__global__ void __launch_bounds__(128) fam_reset_kernel(const __grid_constant__ B200RomFamilyParams p, const __grid_constant__ B200RomState s,
+                                                        const float* __restrict__ z_in, const uint8_t* __restrict__ mask, long long env_off) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.num_envs) return;
+    const size_t i = static_cast<size_t>(e);
+    reset_env<T>(p, s, i, static_cast<uint64_t>(env_off) + i, z_in, mask == nullptr || mask[i] != 0,
+                 s.trajectory + i * (p.window + 1) * Rom<T>::n, s.v_trajectory + i * p.window * Rom<T>::m);
 }
 
 template <int T>
@@ -386,6 +391,58 @@ __global__ void __launch_bounds__(FT) fam_step_tile_kernel(const __grid_constant
 #pragma unroll
         for (int c = 0; c < M; ++c) s.v[i * M + c] = g.v[c];
     }
+    if (staged) {
+        fence_proxy_async();
+        __syncthreads();
+        if (e == 0) {
+            bulk_s2g(g_tr, s_tr, bytes_tr);
+            bulk_s2g(g_vt, s_vt, bytes_vt);
+            bulk_commit();
+            bulk_wait0();
+        }
+    }
+}
+
+// reset_idx with the same staging.  Per-thread, every env streams its own W+1 rows to HBM (ncu at 1 M envs, n = 6: 26 sectors per store
+// request, 603 MB written for 403 MB of windows, L2 at 66 %); staged, the CTA's block leaves as two bulk stores.  With a partial mask the
+// block is fetched first so that the other envs' windows survive; reset() of every env overwrites all of it.
+template <int T>
+__global__ void __launch_bounds__(FT) fam_reset_tile_kernel(const __grid_constant__ B200RomFamilyParams p, const __grid_constant__ B200RomState s,
+                                                            const float* __restrict__ z_in, const uint8_t* __restrict__ mask, long long env_off) {
+    constexpr int RN = Rom<T>::n, M = Rom<T>::m;
+    extern __shared__ __align__(128) float fam_smem[];
+    __shared__ uint64_t bar;
+    const int w = p.window;
+    const int rl = (w + 1) * RN, vl = w * M;
+    float* s_tr = fam_smem;
+    float* s_vt = fam_smem + FT * rl;
+    const int env0 = blockIdx.x * FT;
+    const int nenv = min(FT, p.num_envs - env0);
+    const int e = threadIdx.x;
+    const bool valid = e < nenv;
+    const size_t i = static_cast<size_t>(env0) + (valid ? e : 0);
+    float* g_tr = s.trajectory + static_cast<size_t>(env0) * rl;
+    float* g_vt = s.v_trajectory + static_cast<size_t>(env0) * vl;
+    const uint32_t bytes_tr = static_cast<uint32_t>(nenv) * rl * 4u, bytes_vt = static_cast<uint32_t>(nenv) * vl * 4u;
+    const bool staged = ((bytes_tr | bytes_vt) & 15u) == 0 && ((reinterpret_cast<uintptr_t>(g_tr) | reinterpret_cast<uintptr_t>(g_vt)) & 15u) == 0;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (staged && mask != nullptr) {
+        if (e == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (e == 0) {
+            mbar_expect_tx(&bar, bytes_tr + bytes_vt);
+            bulk_g2s(s_tr, g_tr, bytes_tr, &bar);
+            bulk_g2s(s_vt, g_vt, bytes_vt, &bar);
+        }
+        mbar_wait(&bar, 0);
+    }
+    if (valid)
+        reset_env<T>(p, s, i, static_cast<uint64_t>(env_off) + i, z_in, mask == nullptr || mask[i] != 0, staged ? s_tr + e * rl : s.trajectory + i * rl,
+                     staged ? s_vt + e * vl : s.v_trajectory + i * vl);
     if (staged) {
         fence_proxy_async();
         __syncthreads();
@@ -544,6 +601,15 @@ int check_fam(const B200RomFamilyParams* p, const B200RomState* s, const char* w
         default: { constexpr int T = 5; CALL; } break;                \
     }
 
+bool fam_tile_enabled() {
+    static const bool on = []() { const char* e = getenv("B200GYM_ROMFAM_TILE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+size_t fam_tile_bytes(const B200RomFamilyParams* p) {   // both horizon windows of a CTA's 128 envs
+    const int n_of[B200GYM_ROM_NUM_TYPES] = {2, 4, 3, 3, 5, 6}, m_of[B200GYM_ROM_NUM_TYPES] = {2, 2, 2, 3, 2, 3};
+    return static_cast<size_t>(128) * ((p->window + 1) * n_of[p->rom_type] + p->window * m_of[p->rom_type]) * sizeof(float);
+}
+
 int check_rows(int32_t rom_type, int64_t n_rows, const char* what) {
     B200_REQUIRE(rom_type >= 0 && rom_type < B200GYM_ROM_NUM_TYPES, B200GYM_EINVAL, "%s: unknown rom_type %d", what, rom_type);
     B200_REQUIRE(n_rows > 0 && n_rows < (1ll << 31) * 256, B200GYM_EINVAL, "%s: n_rows out of range", what);
@@ -607,7 +673,20 @@ int b200gym_romfam_gen_reset(const B200RomFamilyParams* p, const B200RomState* s
     if (int rc = check_fam(p, s, "romfam_gen_reset")) return rc;
     B200_REQUIRE(z, B200GYM_EINVAL, "romfam_gen_reset: z missing");
     const int grid = (p->num_envs + 127) / 128;
-    FAM_DISPATCH(p->rom_type, (fam_reset_kernel<T><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p, *s, z, reset_mask, env_id_offset)));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = fam_tile_bytes(p);
+    if (fam_tile_enabled() && smem <= 200 * 1024) {
+        FAM_DISPATCH(p->rom_type, {
+            static size_t granted = 0;
+            if (smem + 1024 > 48 * 1024 && smem > granted) {
+                cudaFuncSetAttribute(fam_reset_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                granted = smem;
+            }
+            b200_launch_pdl(p->num_envs, fam_reset_tile_kernel<T>, dim3(grid), dim3(FT), smem, st, *p, *s, z, reset_mask, (long long)env_id_offset);
+        });
+    } else {
+        FAM_DISPATCH(p->rom_type, (fam_reset_kernel<T><<<grid, 128, 0, st>>>(*p, *s, z, reset_mask, env_id_offset)));
+    }
     B200_LAUNCH_CHECK("romfam_gen_reset");
     return B200GYM_OK;
 }
@@ -618,10 +697,8 @@ int b200gym_romfam_gen_step(const B200RomFamilyParams* p, const B200RomState* s,
     const int grid = (p->num_envs + 127) / 128;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // windows staged through shared memory (TMA bulk tiles) unless they do not fit or B200GYM_ROMFAM_TILE=0 asks for the per-thread kernel
-    static const bool tile_on = []() { const char* e = getenv("B200GYM_ROMFAM_TILE"); return !(e && e[0] == '0'); }();
-    const int n_of[B200GYM_ROM_NUM_TYPES] = {2, 4, 3, 3, 5, 6}, m_of[B200GYM_ROM_NUM_TYPES] = {2, 2, 2, 3, 2, 3};
-    const size_t smem = static_cast<size_t>(FT) * ((p->window + 1) * n_of[p->rom_type] + p->window * m_of[p->rom_type]) * sizeof(float);
-    if (tile_on && smem <= 200 * 1024) {
+    const size_t smem = fam_tile_bytes(p);
+    if (fam_tile_enabled() && smem <= 200 * 1024) {
         FAM_DISPATCH(p->rom_type, {
             static size_t granted = 0;   // per rom class: raise the dynamic shared-memory limit once per size, not on every call
             if (smem + 1024 > 48 * 1024 && smem > granted) {

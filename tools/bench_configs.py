@@ -407,11 +407,20 @@ def rom_family_step(num_envs=1 << 20, cls="ExtendedLateralUnicycle", steps=100, 
     rom = R.ROM_CLASSES[cls](0.1, [-a for a in zmax], zmax, [-a for a in vmax], vmax, n_robots=num_envs, device=device)
     gen = R.TrajectoryGenerator(rom, R.UniformSampleHoldDT(1.0, 2.0), R.UniformWeightSampler(), dt_loop=0.02, N=10, freq_low=0.01, freq_high=2.0, seed=1,
                                 device=device, prob_stationary=0.0005)
-    gen.reset(torch.randn(num_envs, rom.n, device=device) * 0.3)
+    z0 = torch.randn(num_envs, rom.n, device=device) * 0.3
+    for _ in range(3):
+        gen.reset(z0)
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    for _ in range(5):
+        gen.reset(z0)
+    b.record()
+    torch.cuda.synchronize()
+    reset_ms = a.elapsed_time(b) / 5
     for _ in range(10):
         gen.step()
     torch.cuda.synchronize()
-    a, b = _events()
     a.record()
     for _ in range(steps):
         gen.step()
@@ -421,7 +430,9 @@ def rom_family_step(num_envs=1 << 20, cls="ExtendedLateralUnicycle", steps=100, 
     n, m, W = rom.n, rom.m, 10
     per = 4 * (9 * m + 6 + n + 1 + m) + 8 * ((W + 1) * n + W * m) / 5
     return dict(workload=f"TrajectoryGenerator.step over {cls}, {num_envs} envs", ms_per_step=ms, env_steps_per_s=num_envs / ms * 1e3,
-                algorithmic_bytes_per_env=per, achieved_gbs=per * num_envs / ms / 1e6, frac=per * num_envs / ms / 1e6 / peak)
+                algorithmic_bytes_per_env=per, achieved_gbs=per * num_envs / ms / 1e6, frac=per * num_envs / ms / 1e6 / peak,
+                reset_ms=reset_ms, reset_bytes_per_env=4 * (n + 2 * (9 * m + 6) + (W + 1) * n + W * m),
+                reset_frac=4 * (n + 2 * (9 * m + 6) + (W + 1) * n + W * m) * num_envs / reset_ms / 1e6 / peak)
 
 
 def hopper_torques(num_envs=1 << 20, steps=50, device="cuda", peak=6535.7):
