@@ -109,3 +109,27 @@ def test_observation_port_equals_unmodified_reference_methods(N, seed):
         assert_exact(noise_scale_vec(cfg), nv, "noise_scale_vec")
         assert_exact(hopper_observations(case, cfg, seed=5, event=7), want, "observations")
         assert_exact(hopper_reward_terms(case, 0.02), terms, "reward terms")
+
+
+@pytest.mark.reference
+def test_reference_hopper_reset_path_is_not_runnable_as_shipped():
+    """Why the Hopper slice stops at torques / observations / reward terms: `Hopper._reset_dofs`, `_reset_root_states` and `_push_robots`
+    (hopper.py:270-341) use torch_rand_vec_float, matrix_to_quaternion, euler_angles_to_matrix and `push_idx`, none of which hopper.py
+    imports or defines — they raise NameError on the first reset.  The class that can run is HopperTrajectory (hopper_trajectory.py imports
+    them, :38-40); the remaining Hopper rows have to be pinned on that file."""
+    from types import SimpleNamespace
+    from oracle import ref_harness as H
+    hop = H.import_reference().hopper
+    for name in ("torch_rand_vec_float", "matrix_to_quaternion", "euler_angles_to_matrix"):
+        assert not hasattr(hop, name), f"hopper.py now defines {name}: the reset path may have become runnable"
+    ids = torch.arange(4)
+    stub = SimpleNamespace(dof_pos=torch.zeros(4, 4), dof_vel=torch.zeros(4, 4), default_dof_pos=torch.zeros(1, 4), num_dof=4, device="cpu",
+                           default_dof_pos_noise_lower=torch.zeros(4), default_dof_pos_noise_upper=torch.ones(4),
+                           default_dof_vel_noise_lower=torch.zeros(4), default_dof_vel_noise_upper=torch.ones(4))
+    with pytest.raises(NameError, match="torch_rand_vec_float"):
+        hop.Hopper._reset_dofs(stub, ids)
+    with pytest.raises(NameError, match="not defined"):      # torch_rand_vec_float again, then the undefined push_idx / env_ids_int32 (:336-341)
+        hop.Hopper._push_robots(SimpleNamespace(max_vel=torch.ones(6), device="cpu"), ids)
+    import inspect
+    src = inspect.getsource(hop.Hopper._push_robots)
+    assert "push_idx" in src and "push_inds" in src and "env_ids_int32" in src
