@@ -641,7 +641,7 @@ _current_sim = []
 # --------------------------------------------------------------------------------------------
 # Hopper._compute_torques
 # --------------------------------------------------------------------------------------------
-def reference_hopper_torques(case, actions):
+def reference_hopper_torques(case, actions, cls="Hopper"):
     """Runs the UNMODIFIED Hopper._compute_torques (legged_gym/envs/hopper/hopper.py:168-237) on a stub `self` that carries exactly the
     attributes the method reads, built from `case` (oracle.port_hopper.hopper_case).  pytorch3d.transforms = oracle/pytorch3d_restated."""
     ref = import_reference()
@@ -659,7 +659,11 @@ def reference_hopper_torques(case, actions):
         torque_limits=t("torque_limits"), torque_limit_random=t("torque_limit_random"), wheel_speed_limits=t("wheel_speed_limits"),
         wheel_limit_random=t("wheel_limit_random"), torques=torch.zeros(N, 4), last_dof_vel=torch.zeros(N, 4), sim_params=SimpleNamespace(dt=0.005),
         actuator_transform=sys.modules["pytorch3d.transforms"].Rotate(torch.tensor(case["rot_actuator"]), device="cpu"))
-    out = ref.hopper.Hopper._compute_torques(stub, actions.clone())
+    if cls == "HopperTrajectory":       # the class of this fork that can run a full step (hopper_trajectory.py:184-253)
+        import legged_gym.envs.hopper.hopper_trajectory as ht
+        out = ht.HopperTrajectory._compute_torques(stub, actions.clone())
+    else:
+        out = ref.hopper.Hopper._compute_torques(stub, actions.clone())
     return out, stub.torques
 
 

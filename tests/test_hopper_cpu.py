@@ -74,6 +74,20 @@ def test_port_equals_unmodified_reference_method(ct, seed, N, ang):
 
 
 @pytest.mark.reference
+@pytest.mark.parametrize("ct", ["orientation_spindown", "orientation"])
+def test_port_equals_hopper_trajectory_torque_law_too(ct):
+    """HopperTrajectory carries its own copy of the torque law (hopper_trajectory.py:184-253, restructured index handling, same arithmetic):
+    the port — and so the kernel — serves both classes."""
+    from oracle import ref_harness as H
+    for seed, N, ang in ((1, 257, 3.1), (4, 96, 0.3)):
+        case, act = hopper_case(N, seed=seed, control_type=ct, max_angle=ang, torque_limits=[9000.0, 80.0, 80.0, 80.0])
+        want, want_t = H.reference_hopper_torques(case, act, cls="HopperTrajectory")
+        got, got_t = hopper_torques(case, act)
+        assert_exact(got, want, "returned torques")
+        assert_exact(got_t, want_t, "self.torques")
+
+
+@pytest.mark.reference
 @pytest.mark.parametrize("ct", ["orientation_w_foot", "V", "T_spindown"])
 def test_reference_cannot_run_the_other_control_types(ct):
     """Why the port / kernel reject them: the reference method itself raises (shape errors at hopper.py:196 / :224 / :227)."""
