@@ -140,3 +140,43 @@ def hopper_reward_terms(case, dt):
     acc = torch.sum(torch.square((c["last_dof_vel"][:, 1:4] - c["dof_state"][:, 1:4, 1]) / dt), dim=1)
     uq = torch.square(1 - torch.linalg.norm(c["actions"], dim=-1))
     return torch.stack((tl, acc, uq), dim=1)
+
+
+# ---- HopperTrajectory (hopper_trajectory.py), groundwork for the remaining Hopper rows: oracle only, no kernel yet ---------------------
+def hopper_traj_noise_scale_vec(traj_size, cfg=OBS_CFG):
+    """HopperTrajectory._get_noise_scale_vec, hopper_trajectory.py:439-468 (measure_heights False): the trajectory block replaces the 3 command
+    columns; everything after the wheel velocities carries zero noise."""
+    v = torch.zeros(14 + traj_size + 4)
+    v[:14] = noise_scale_vec(cfg)[:14]
+    return v
+
+
+def hopper_traj_observations(case, trajectory, trajectory_scale, cfg=OBS_CFG, seed=0, event=1, env_id_offset=0):
+    """HopperTrajectory.compute_observations, hopper_trajectory.py:255-282, for a SingleInt2D rom (proj_z = root xy) + the clip of step."""
+    from . import philox as PH
+    import numpy as np
+    c = case
+    a = c["actions"].clone()
+    a /= torch.linalg.norm(a, dim=-1, keepdim=True)
+    a[a[:, 0] < 0, :] *= -1
+    mod = trajectory.clone()
+    mod[:, :, :2] -= c["root_states"][:, :2][:, None, :2]
+    obs = torch.cat((c["root_states"][:, 2][:, None] * cfg["z_pos"], c["root_states"][:, 3:7], c["base_lin_vel"] * cfg["lin_vel"],
+                     c["base_ang_vel"] * cfg["ang_vel"], c["dof_state"][:, 1:4, 1] * cfg["dof_vel"],
+                     (mod * trajectory_scale).reshape(c["num_envs"], -1), a), dim=-1)
+    if cfg["add_noise"]:
+        u = torch.from_numpy(PH.uniform01(seed, np.arange(c["num_envs"]) + env_id_offset, event, PH.SITE_OBS_NOISE, obs.shape[1]))
+        obs += (2 * u - 1) * hopper_traj_noise_scale_vec(trajectory.shape[1] * trajectory.shape[2], cfg)
+    return torch.clip(obs, -cfg["clip_observations"], cfg["clip_observations"])
+
+
+def hopper_reward_raibert(case, desired_position, desired_velocity, gains):
+    """HopperTrajectory._reward_raibert, hopper_trajectory.py:482-505 (SingleInt2D rom): squared distance between the policy's quaternion action
+    and the Raibert heuristic's (deep_tube_learning/controllers.py:38-73, oracle/port_controllers.py)."""
+    from .isaacgym_restated import quat_rotate_inverse
+    from .port_controllers import raibert_policy
+    rs = case["root_states"]
+    cur_v = quat_rotate_inverse(rs[:, 3:7], rs[:, 7:10])[:, :2]
+    rh_obs = torch.cat((desired_position - rs[:, :2], cur_v, desired_velocity, rs[:, 3:7]), dim=1)
+    rh = raibert_policy(rh_obs, gains["Kp"], gains["Kv"], gains["K_ff"], gains["clip_pos"], gains["clip_vel"], gains["clip_ang"])
+    return torch.sum(torch.square(case["actions"] - rh), dim=1)

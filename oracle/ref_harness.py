@@ -691,3 +691,32 @@ def reference_hopper_observations(case, cfg, seed=0, event=1):
     obs = torch.clip(stub.obs_buf, -cfg["clip_observations"], cfg["clip_observations"])
     terms = torch.stack((H._reward_torque_limits(stub), H._reward_dof_acc(stub), H._reward_unit_quat(stub)), dim=1)
     return obs, stub.noise_scale_vec, terms
+
+
+def reference_hopper_trajectory_observations(case, cfg, trajectory, trajectory_scale, gains, desired_velocity, seed=0, event=1):
+    """The UNMODIFIED HopperTrajectory._get_noise_scale_vec / compute_observations / _reward_raibert (hopper_trajectory.py:439-468, 255-282,
+    482-505) on a stub `self` with a SingleInt2D rom; `traj_gen.get_trajectory()` returns `trajectory`, `traj_gen.v` = desired_velocity."""
+    ref = import_reference()
+    rng_shim.install()
+    import legged_gym.envs.hopper.hopper_trajectory as ht
+    N = case["num_envs"]
+    ns = SimpleNamespace
+    t = lambda k: case[k].clone()
+    rom = ref.rom_dynamics.SingleInt2D(0.1, torch.tensor([-1e9, -1e9]), torch.tensor([1e9, 1e9]), torch.tensor([-1.0, -1.0]), torch.tensor([1.0, 1.0]),
+                                       n_robots=N, backend="torch", device="cpu")
+    hcfg = ns(noise=ns(add_noise=cfg["add_noise"], noise_level=cfg["noise_level"], noise_scales=ns(**cfg["noise_scales"])),
+              terrain=ns(measure_heights=False))
+    obs_scales = ns(z_pos=cfg["z_pos"], lin_vel=cfg["lin_vel"], ang_vel=cfg["ang_vel"], dof_vel=cfg["dof_vel"], height_measurements=5.0)
+    W, n = trajectory.shape[1], trajectory.shape[2]
+    traj_gen = ns(N=W, rom=rom, v=desired_velocity.clone(), get_trajectory=lambda: trajectory.clone())
+    stub = ns(cfg=hcfg, obs_scales=obs_scales, obs_buf=torch.zeros(N, 14 + W * n + 4), actions=t("actions"), root_states=t("root_states"),
+              base_quat=t("root_states")[:, 3:7], base_lin_vel=t("base_lin_vel"), base_ang_vel=t("base_ang_vel"), dof_vel=t("dof_state")[..., 1],
+              wheel_joint_indices=torch.tensor([1, 2, 3]), trajectory=trajectory.clone(), trajectory_scale=trajectory_scale.clone(), rom=rom,
+              traj_gen=traj_gen, num_envs=N, raibert_Kp=gains["Kp"], raibert_Kv=gains["Kv"], raibert_Kff=gains["K_ff"],
+              raibert_clip_pos=gains["clip_pos"], raibert_clip_vel=gains["clip_vel"], raibert_clip_ang=gains["clip_ang"])
+    H = ht.HopperTrajectory
+    stub.noise_scale_vec = H._get_noise_scale_vec(stub, hcfg)
+    with rng_shim.draws(seed, np.arange(N), event, [(P.SITE_OBS_NOISE, 0)]):
+        H.compute_observations(stub)
+    obs = torch.clip(stub.obs_buf, -cfg["clip_observations"], cfg["clip_observations"])
+    return obs, stub.noise_scale_vec, H._reward_raibert(stub)

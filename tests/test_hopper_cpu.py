@@ -147,3 +147,24 @@ def test_reference_hopper_reset_path_is_not_runnable_as_shipped():
     import inspect
     src = inspect.getsource(hop.Hopper._push_robots)
     assert "push_idx" in src and "push_inds" in src and "env_ids_int32" in src
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("add_noise", [True, False])
+def test_hopper_trajectory_observation_and_raibert_ports_equal_reference(add_noise):
+    """Oracle groundwork for the remaining Hopper rows (no kernel yet): HopperTrajectory.compute_observations with its trajectory block,
+    its noise vector and _reward_raibert, against the unmodified methods."""
+    from oracle import ref_harness as H
+    from oracle.port_controllers import GAINS
+    from oracle.port_hopper import OBS_CFG, hopper_reward_raibert, hopper_traj_noise_scale_vec, hopper_traj_observations, obs_case
+    N, W = 120, 10
+    case = obs_case(N, seed=6)
+    g = torch.Generator().manual_seed(2)
+    traj = torch.randn(N, W, 2, generator=g) * 0.5 + case["root_states"][:, None, :2]
+    scale = torch.tensor([2.0, 2.0])[None, :].repeat(W, 1)
+    vdes = torch.randn(N, 2, generator=g) * 0.2
+    cfg = dict(OBS_CFG, add_noise=add_noise)
+    want, nv, raib = H.reference_hopper_trajectory_observations(case, cfg, traj, scale, GAINS, vdes, seed=5, event=7)
+    assert_exact(hopper_traj_noise_scale_vec(W * 2, cfg), nv, "noise_scale_vec")
+    assert_exact(hopper_traj_observations(case, traj, scale, cfg, seed=5, event=7), want, "observations")
+    assert_exact(hopper_reward_raibert(case, traj[:, 0], vdes, GAINS), raib, "_reward_raibert")
