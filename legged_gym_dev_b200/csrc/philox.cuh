@@ -11,7 +11,9 @@ enum Site : uint32_t {
     CMD_PERIODIC = 1, PUSH = 2, TERRAIN = 3, RESET_DOF = 4, RESET_XY = 5, RESET_VEL = 6, CMD_RESET = 7, OBS_NOISE = 8, PUSH_TIMER = 9,
     ROM_INIT = 16, ROM_ROOT = 17, ROM_DIST_MASK = 18, ROM_DIST = 19, ROM_CONST = 20, ROM_RAMP = 21, ROM_EXTREME = 22,
     ROM_SIN_MAG = 23, ROM_SIN_MEAN = 24, ROM_SIN_FREQ = 25, ROM_SIN_OFF = 26, ROM_TFINAL = 27, ROM_WEIGHTS = 28,
-    ROM_STATIONARY = 29
+    ROM_STATIONARY = 29,
+    // HopperTrajectory reset / push (oracle/philox.py; reserved, no kernel draws from them yet)
+    HOP_DOF_POS = 32, HOP_DOF_VEL = 33, HOP_ROOT_POS = 34, HOP_YAW = 35, HOP_ROOT_VEL = 36, HOP_PUSH = 37
 };
 
 __device__ __forceinline__ uint4 block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {

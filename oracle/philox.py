@@ -93,3 +93,10 @@ SITE_ROM_SIN_OFF = 26
 SITE_ROM_TFINAL = 27
 SITE_ROM_WEIGHTS = 28
 SITE_ROM_STATIONARY = 29
+# HopperTrajectory reset / push, event = common_step_counter (oracle groundwork; no kernel consumes these yet)
+SITE_HOP_DOF_POS = 32     # cols 0..3                                          (hopper_trajectory.py:306-309)
+SITE_HOP_DOF_VEL = 33     # cols 0..3                                          (hopper_trajectory.py:310-313)
+SITE_HOP_ROOT_POS = 34    # cols 0..4 = z, qx, qy, qz, qw offsets              (hopper_trajectory.py:338-341)
+SITE_HOP_YAW = 35         # col 0                                              (hopper_trajectory.py:343)
+SITE_HOP_ROOT_VEL = 36    # cols 0..5                                          (hopper_trajectory.py:351-354)
+SITE_HOP_PUSH = 37        # cols 0..5                                          (hopper_trajectory.py:366-367)

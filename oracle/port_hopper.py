@@ -180,3 +180,49 @@ def hopper_reward_raibert(case, desired_position, desired_velocity, gains):
     rh_obs = torch.cat((desired_position - rs[:, :2], cur_v, desired_velocity, rs[:, 3:7]), dim=1)
     rh = raibert_policy(rh_obs, gains["Kp"], gains["Kv"], gains["K_ff"], gains["clip_pos"], gains["clip_vel"], gains["clip_ang"])
     return torch.sum(torch.square(case["actions"] - rh), dim=1)
+
+
+# hopper_config.py:15-31 / hopper_trajectory_config (init_state)
+RESET_CFG = dict(base_init_state=[0.0, 0.0, 0.5, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0], default_dof_pos=[0.021, 0.0, 0.0, 0.0],
+                 dof_pos_noise=([-0.02, 0, 0, 0], [0.02, 0, 0, 0]), dof_vel_noise=([-0.1, 100, 100, 100], [0.1, 100, 100, 100]),
+                 root_pos_noise=([-0.0, -0.0, -0.05, -0.03, -0.03, -0.03, -0.03], [0.0, 0.0, 0.05, 0.03, 0.03, 0.03, 0.03]),
+                 root_vel_noise=([-0.05, -0.05, -0.05, -0.2, -0.2, -0.2], [0.05, 0.05, 0.05, 0.2, 0.2, 0.2]), randomize_yaw=True,
+                 zero_action=[1.0, 0.0, 0.0, 0.0], max_push_vel=[0.5, 0.5, 0.2, 0.3, 0.3, 0.3])
+
+
+def hopper_traj_reset(state, env_ids, env_origins, cfg=RESET_CFG, seed=0, event=1, env_id_offset=0):
+    """HopperTrajectory._reset_dofs + _reset_root_states (hopper_trajectory.py:298-358, the custom_origins == False branch — the other one
+    adds a [n, 2] draw to 7 columns and cannot run).  `state` = dict(dof_state [N,4,2], root_states [N,13], actions [N,4]), modified in place."""
+    import math
+    import numpy as np
+    from . import philox as PH
+    t = lambda v: torch.tensor(v, dtype=torch.float32)
+    ids = np.asarray(env_ids) + env_id_offset
+    u = lambda site, ncols: torch.from_numpy(PH.uniform01(seed, ids, event, site, ncols))
+    lo, hi = (t(v) for v in cfg["dof_pos_noise"])
+    state["dof_state"][env_ids, :, 0] = t(cfg["default_dof_pos"]) + ((hi - lo) * u(PH.SITE_HOP_DOF_POS, 4) + lo)
+    lo, hi = (t(v) for v in cfg["dof_vel_noise"])
+    state["dof_state"][env_ids, :, 1] = (hi - lo) * u(PH.SITE_HOP_DOF_VEL, 4) + lo
+    state["actions"][env_ids, :] = t(cfg["zero_action"])
+    rs = state["root_states"]
+    rs[env_ids] = t(cfg["base_init_state"])
+    rs[env_ids, :3] += env_origins[env_ids]
+    lo, hi = (t(v)[2:] for v in cfg["root_pos_noise"])
+    rs[env_ids, 2:7] += (hi - lo) * u(PH.SITE_HOP_ROOT_POS, 5) + lo
+    rs[env_ids, 3:7] /= torch.linalg.norm(rs[env_ids, 3:7], dim=-1, keepdim=True)
+    if cfg["randomize_yaw"]:
+        yaw = (math.pi - (-math.pi)) * u(PH.SITE_HOP_YAW, 1) + (-math.pi)
+        quat_yaw = P3.matrix_to_quaternion(P3.euler_angles_to_matrix(torch.cat([torch.zeros(len(env_ids), 2), yaw], dim=-1), "XYZ"))
+        q_new = P3.quaternion_multiply(rs[:, [6, 3, 4, 5]][env_ids, :], quat_yaw)
+        rs[env_ids, 3:7] = q_new[:, [1, 2, 3, 0]]
+    lo, hi = (t(v) for v in cfg["root_vel_noise"])
+    rs[env_ids, 7:13] = (hi - lo) * u(PH.SITE_HOP_ROOT_VEL, 6) + lo
+
+
+def hopper_traj_push(state, push_idx, cfg=RESET_CFG, seed=0, event=1, env_id_offset=0):
+    """HopperTrajectory._push_robots, hopper_trajectory.py:362-367."""
+    import numpy as np
+    from . import philox as PH
+    mv = torch.tensor(cfg["max_push_vel"], dtype=torch.float32)
+    u = torch.from_numpy(PH.uniform01(seed, np.asarray(push_idx) + env_id_offset, event, PH.SITE_HOP_PUSH, 6))
+    state["root_states"][push_idx, 7:13] = (mv - (-mv)) * u + (-mv)

@@ -1,5 +1,6 @@
-"""Restatement of the five pytorch3d.transforms functions the Hopper's torque law imports (legged_gym/envs/hopper/hopper.py:38):
-quaternion_invert, quaternion_multiply, quaternion_to_matrix, so3_log_map, Rotate(...).transform_points.  TEST INFRASTRUCTURE.
+"""Restatement of the pytorch3d.transforms functions the Hopper classes import (legged_gym/envs/hopper/hopper.py:38, hopper_trajectory.py:39-40):
+quaternion_invert, quaternion_multiply, quaternion_to_matrix, so3_log_map, Rotate(...).transform_points (torque law), euler_angles_to_matrix,
+matrix_to_quaternion (yaw randomisation of the reset).  TEST INFRASTRUCTURE.
 
 pytorch3d is a third-party dependency that is absent from this image and from /root/reference, and the reference pins no version of it
 (no requirements entry, README silent).  What follows restates the published algorithm of pytorch3d v0.7.x
@@ -138,9 +139,60 @@ class Rotate:
         return points_out
 
 
+def _axis_angle_rotation(axis, angle):
+    cos, sin = torch.cos(angle), torch.sin(angle)
+    one, zero = torch.ones_like(angle), torch.zeros_like(angle)
+    if axis == "X":
+        flat = (one, zero, zero, zero, cos, -sin, zero, sin, cos)
+    elif axis == "Y":
+        flat = (cos, zero, sin, zero, one, zero, -sin, zero, cos)
+    elif axis == "Z":
+        flat = (cos, -sin, zero, sin, cos, zero, zero, zero, one)
+    else:
+        raise ValueError("letter must be either X, Y or Z.")
+    return torch.stack(flat, -1).reshape(angle.shape + (3, 3))
+
+
+def euler_angles_to_matrix(euler_angles, convention):
+    """rotation_conversions.py: product of the three axis rotations in the order of `convention` (used by the Hopper's yaw randomisation,
+    hopper_trajectory.py:344)."""
+    if euler_angles.dim() == 0 or euler_angles.shape[-1] != 3:
+        raise ValueError("Invalid input euler angles.")
+    if len(convention) != 3:
+        raise ValueError("Convention must have 3 letters.")
+    matrices = [_axis_angle_rotation(c, e) for c, e in zip(convention, torch.unbind(euler_angles, -1))]
+    return torch.matmul(torch.matmul(matrices[0], matrices[1]), matrices[2])
+
+
+def _sqrt_positive_part(x):
+    ret = torch.zeros_like(x)
+    positive_mask = x > 0
+    ret[positive_mask] = torch.sqrt(x[positive_mask])
+    return ret
+
+
+def matrix_to_quaternion(matrix):
+    """rotation_conversions.py (v0.7.x): four candidate quaternions, the one with the largest denominator wins; real part first.  Later
+    releases standardise the sign (w >= 0), earlier ones do not — irrelevant where the reference uses it: the result is only ever the right
+    factor of a quaternion_multiply, which standardises its own product."""
+    if matrix.size(-1) != 3 or matrix.size(-2) != 3:
+        raise ValueError(f"Invalid rotation matrix shape {matrix.shape}.")
+    batch_dim = matrix.shape[:-2]
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = torch.unbind(matrix.reshape(batch_dim + (9,)), dim=-1)
+    q_abs = _sqrt_positive_part(torch.stack([1.0 + m00 + m11 + m22, 1.0 + m00 - m11 - m22, 1.0 - m00 + m11 - m22, 1.0 - m00 - m11 + m22], dim=-1))
+    quat_by_rijk = torch.stack([
+        torch.stack([q_abs[..., 0] ** 2, m21 - m12, m02 - m20, m10 - m01], dim=-1),
+        torch.stack([m21 - m12, q_abs[..., 1] ** 2, m10 + m01, m02 + m20], dim=-1),
+        torch.stack([m02 - m20, m10 + m01, q_abs[..., 2] ** 2, m12 + m21], dim=-1),
+        torch.stack([m10 - m01, m20 + m02, m21 + m12, q_abs[..., 3] ** 2], dim=-1)], dim=-2)
+    flr = torch.tensor(0.1).to(dtype=q_abs.dtype, device=q_abs.device)
+    quat_candidates = quat_by_rijk / (2.0 * q_abs[..., None].max(flr))
+    out = quat_candidates[torch.nn.functional.one_hot(q_abs.argmax(dim=-1), num_classes=4) > 0.5, :].reshape(batch_dim + (4,))
+    return standardize_quaternion(out)
+
+
 def __getattr__(name):
-    """Names other modules of the reference import from pytorch3d.transforms but this path never calls (hopper_trajectory.py:39-40:
-    euler_angles_to_matrix, matrix_to_quaternion): importable, loud when used."""
+    """Anything else a module of the reference may import from pytorch3d.transforms: importable, loud when used."""
     if name.startswith("__"):
         raise AttributeError(name)
 

@@ -720,3 +720,33 @@ def reference_hopper_trajectory_observations(case, cfg, trajectory, trajectory_s
         H.compute_observations(stub)
     obs = torch.clip(stub.obs_buf, -cfg["clip_observations"], cfg["clip_observations"])
     return obs, stub.noise_scale_vec, H._reward_raibert(stub)
+
+
+def reference_hopper_trajectory_reset(state, env_ids, env_origins, cfg, seed=0, event=1, push_idx=None):
+    """The UNMODIFIED HopperTrajectory._reset_dofs / _reset_root_states / _push_robots (hopper_trajectory.py:298-372) on a stub `self` whose
+    gym calls are no-ops; draws through the shim at the HOP_* sites.  `state` tensors are modified in place."""
+    import_reference()
+    rng_shim.install()
+    import legged_gym.envs.hopper.hopper_trajectory as ht
+    ns = SimpleNamespace
+    t = lambda v: torch.tensor(v, dtype=torch.float32)
+    N = state["root_states"].shape[0]
+    ds = state["dof_state"]
+    stub = ns(dof_pos=ds[..., 0], dof_vel=ds[..., 1], dof_state=ds, root_states=state["root_states"], actions=state["actions"], num_dof=4, device="cpu",
+              default_dof_pos=t(cfg["default_dof_pos"])[None, :], zero_action=t(cfg["zero_action"])[None, :].repeat(N, 1),
+              default_dof_pos_noise_lower=t(cfg["dof_pos_noise"][0]), default_dof_pos_noise_upper=t(cfg["dof_pos_noise"][1]),
+              default_dof_vel_noise_lower=t(cfg["dof_vel_noise"][0]), default_dof_vel_noise_upper=t(cfg["dof_vel_noise"][1]),
+              default_root_pos_noise_lower=t(cfg["root_pos_noise"][0]), default_root_pos_noise_upper=t(cfg["root_pos_noise"][1]),
+              default_root_vel_noise_lower=t(cfg["root_vel_noise"][0]), default_root_vel_noise_upper=t(cfg["root_vel_noise"][1]),
+              custom_origins=False, base_init_state=t(cfg["base_init_state"]), env_origins=env_origins, wxyz_quat_inds=torch.tensor([6, 3, 4, 5]),
+              cfg=ns(init_state=ns(randomize_yaw=cfg["randomize_yaw"])), max_vel=t(cfg["max_push_vel"]), gym=MagicMock(), sim=None)
+    ids = env_ids.numpy()
+    H = ht.HopperTrajectory
+    with rng_shim.draws(seed, ids, event, [(P.SITE_HOP_DOF_POS, 0), (P.SITE_HOP_DOF_VEL, 0)]):
+        H._reset_dofs(stub, env_ids)
+    plan = [(P.SITE_HOP_ROOT_POS, 0)] + ([(P.SITE_HOP_YAW, 0)] if cfg["randomize_yaw"] else []) + [(P.SITE_HOP_ROOT_VEL, 0)]
+    with rng_shim.draws(seed, ids, event, plan):
+        H._reset_root_states(stub, env_ids)
+    if push_idx is not None:
+        with rng_shim.draws(seed, push_idx.numpy(), event, [(P.SITE_HOP_PUSH, 0)]):
+            H._push_robots(stub, push_idx)

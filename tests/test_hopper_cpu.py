@@ -168,3 +168,43 @@ def test_hopper_trajectory_observation_and_raibert_ports_equal_reference(add_noi
     assert_exact(hopper_traj_noise_scale_vec(W * 2, cfg), nv, "noise_scale_vec")
     assert_exact(hopper_traj_observations(case, traj, scale, cfg, seed=5, event=7), want, "observations")
     assert_exact(hopper_reward_raibert(case, traj[:, 0], vdes, GAINS), raib, "_reward_raibert")
+
+
+def test_restated_euler_and_matrix_to_quaternion_against_scipy():
+    from scipy.spatial.transform import Rotation
+    g = torch.Generator().manual_seed(3)
+    eul = (torch.rand(400, 3, generator=g, dtype=torch.float64) - 0.5) * 6.0
+    R = P3.euler_angles_to_matrix(eul, "XYZ")
+    assert np.allclose(R.numpy(), Rotation.from_euler("XYZ", eul.numpy()).as_matrix(), atol=1e-12)     # intrinsic X-Y-Z
+    q = P3.matrix_to_quaternion(R)
+    want = Rotation.from_matrix(R.numpy()).as_quat()[:, [3, 0, 1, 2]]
+    want = np.where(want[:, :1] < 0, -want, want)
+    assert bool((q[:, 0] >= 0).all()) and np.allclose(q.numpy(), want, atol=1e-9)
+    yaw = torch.linspace(-3.1, 3.1, 50, dtype=torch.float64)          # the only use in the reference: pure yaw (hopper_trajectory.py:344)
+    qy = P3.matrix_to_quaternion(P3.euler_angles_to_matrix(torch.stack((torch.zeros_like(yaw), torch.zeros_like(yaw), yaw), -1), "XYZ"))
+    y = yaw.numpy()
+    assert np.allclose(qy.numpy(), np.stack((np.cos(y / 2), 0 * y, 0 * y, np.sin(y / 2)), -1), atol=1e-12)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("randomize_yaw", [True, False])
+def test_hopper_trajectory_reset_and_push_ports_equal_reference(randomize_yaw):
+    """Oracle groundwork (no kernel yet): HopperTrajectory._reset_dofs / _reset_root_states / _push_robots against the unmodified methods."""
+    from oracle import ref_harness as H
+    from oracle.port_hopper import RESET_CFG, hopper_traj_push, hopper_traj_reset
+    N = 90
+    g = torch.Generator().manual_seed(8)
+    mk = lambda: dict(dof_state=torch.randn(N, 4, 2, generator=torch.Generator().manual_seed(1)),
+                      root_states=torch.randn(N, 13, generator=torch.Generator().manual_seed(2)),
+                      actions=torch.randn(N, 4, generator=torch.Generator().manual_seed(3)))
+    origins = torch.randn(N, 3, generator=g)
+    ids, push = torch.arange(0, N, 3), torch.arange(1, N, 4)
+    cfg = dict(RESET_CFG, randomize_yaw=randomize_yaw)
+    a, b = mk(), mk()
+    H.reference_hopper_trajectory_reset(a, ids, origins, cfg, seed=4, event=9, push_idx=push)
+    hopper_traj_reset(b, ids.numpy(), origins, cfg, seed=4, event=9)
+    hopper_traj_push(b, push.numpy(), cfg, seed=4, event=9)
+    for k in a:
+        assert_exact(b[k], a[k], k)
+    q = a["root_states"][ids, 3:7]
+    assert float((q.norm(dim=1) - 1).abs().max()) < 1e-5
