@@ -27,4 +27,8 @@ cap sliding_window 'sliding_window_kernel' 1
 timeout 240 ncu --set full --clock-control none --import-source on -k "regex:post_physics_kernel" -s 4 -c 1 -f -o $O/prof_${R}_post_physics_flat $B > $O/ncu_${R}_pp_flat.log 2>&1
 timeout 240 ncu --set full --clock-control none --import-source on -k "regex:pd_torques_kernel" -s 8 -c 1 -f -o $O/prof_${R}_pd_torques $B > $O/ncu_${R}_pd.log 2>&1
 timeout 240 ncu --set full --clock-control none --import-source on -k "regex:mlp_forward_h4" -s 2 -c 1 -f -o $O/prof_${R}_mlp_forward python tools/run_mlp_once.py 1048576 > $O/ncu_${R}_mlp.log 2>&1
+# the generic rom-family kernels and the Hopper kernels (own drivers, 1 M envs)
+timeout 240 ncu --set full --clock-control none --import-source on -k "regex:fam_step_tile" -c 6 -f -o $O/prof_${R}_romfam_step python tools/run_romfam_once.py > $O/ncu_${R}_romfam_step.log 2>&1
+timeout 240 ncu --set full --clock-control none --import-source on -k "regex:fam_reset" -c 1 -f -o $O/prof_${R}_romfam_reset python tools/run_romfam_once.py > $O/ncu_${R}_romfam_reset.log 2>&1
+timeout 240 ncu --set full --clock-control none --import-source on -k "regex:hopper" -c 6 -f -o $O/prof_${R}_hopper python tools/run_hopper_once.py > $O/ncu_${R}_hopper.log 2>&1
 ls -la $O | tail -20
