@@ -16,6 +16,33 @@ CASES = {"shipped": (192, 3, "orientation_spindown", 2.6, {}),
          "small_angles": (128, 6, "orientation_spindown", 0.02, dict(torque_limits=[9000.0, 80.0, 80.0, 80.0]))}
 
 
+def hopper_trajectory_inputs(N=96, W=10):
+    """Seeded inputs shared by the golden writer and the tests that replay it."""
+    import torch
+    from oracle.port_hopper import obs_case
+    case = obs_case(N, seed=6)
+    g = torch.Generator().manual_seed(2)
+    traj = torch.randn(N, W, 2, generator=g) * 0.5 + case["root_states"][:, None, :2]
+    scale = torch.tensor([2.0, 2.0])[None, :].repeat(W, 1)
+    vdes = torch.randn(N, 2, generator=g) * 0.2
+    state = dict(dof_state=torch.randn(N, 4, 2, generator=torch.Generator().manual_seed(1)),
+                 root_states=torch.randn(N, 13, generator=torch.Generator().manual_seed(2)),
+                 actions=torch.randn(N, 4, generator=torch.Generator().manual_seed(3)))
+    origins = torch.randn(N, 3, generator=g)
+    return case, traj, scale, vdes, state, origins, torch.arange(0, N, 3), torch.arange(1, N, 4)
+
+
+def hopper_trajectory_golden():
+    from oracle.port_controllers import GAINS
+    from oracle.port_hopper import OBS_CFG, RESET_CFG
+    case, traj, scale, vdes, state, origins, ids, push = hopper_trajectory_inputs()
+    obs, nv, raib = H.reference_hopper_trajectory_observations(case, OBS_CFG, traj, scale, GAINS, vdes, seed=5, event=7)
+    H.reference_hopper_trajectory_reset(state, ids, origins, RESET_CFG, seed=4, event=9, push_idx=push)
+    out = dict(obs=obs.numpy(), noise_scale_vec=nv.numpy(), raibert=raib.numpy())
+    out.update({f"reset_{k}": v.numpy() for k, v in state.items()})
+    return out
+
+
 def main():
     out = {}
     for name, (N, seed, ct, ang, over) in CASES.items():
@@ -28,6 +55,9 @@ def main():
     for tag, cfg in (("noise", OBS_CFG), ("plain", dict(OBS_CFG, add_noise=False, clip_observations=1.5))):
         obs, nv, terms = H.reference_hopper_observations(case, cfg, seed=5, event=7)
         out[f"obs_{tag}"], out["noise_scale_vec"], out["reward_terms"] = obs.numpy(), nv.numpy(), terms.numpy()
+    # HopperTrajectory groundwork (no kernel yet): trajectory-block observations, _reward_raibert, reset + push, from the unmodified methods
+    for k, v in hopper_trajectory_golden().items():
+        out[f"ht_{k}"] = v
     path = os.path.join(ROOT, "tests", "golden", "hopper_torques_reference.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

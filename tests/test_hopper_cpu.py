@@ -208,3 +208,20 @@ def test_hopper_trajectory_reset_and_push_ports_equal_reference(randomize_yaw):
         assert_exact(b[k], a[k], k)
     q = a["root_states"][ids, 3:7]
     assert float((q.norm(dim=1) - 1).abs().max()) < 1e-5
+
+
+def test_hopper_trajectory_groundwork_ports_match_reference_golden():
+    """The same ports against outputs the unmodified HopperTrajectory methods wrote into the fixture (runs without /root/reference)."""
+    from oracle.make_golden_hopper import hopper_trajectory_inputs
+    from oracle.port_controllers import GAINS
+    from oracle.port_hopper import (OBS_CFG, RESET_CFG, hopper_reward_raibert, hopper_traj_noise_scale_vec, hopper_traj_observations, hopper_traj_push,
+                                    hopper_traj_reset)
+    g = np.load(GOLD)
+    case, traj, scale, vdes, state, origins, ids, push = hopper_trajectory_inputs()
+    assert_exact(hopper_traj_noise_scale_vec(20), g["ht_noise_scale_vec"], "noise_scale_vec")
+    assert_close(hopper_traj_observations(case, traj, scale, OBS_CFG, seed=5, event=7), g["ht_obs"], 1.0, "observations")
+    assert_close(hopper_reward_raibert(case, traj[:, 0], vdes, GAINS), g["ht_raibert"], 1.0, "_reward_raibert")
+    hopper_traj_reset(state, ids.numpy(), origins, RESET_CFG, seed=4, event=9)
+    hopper_traj_push(state, push.numpy(), RESET_CFG, seed=4, event=9)
+    for k, v in state.items():
+        assert_close(v, g[f"ht_reset_{k}"], 1.0, f"reset {k}")
