@@ -45,7 +45,8 @@ def test_bench_touches_the_oracle_only_in_its_cpu_baseline():
 
 def test_importing_the_package_does_not_load_the_oracle():
     code = ("import sys; sys.path.insert(0, %r); import legged_gym_dev_b200, legged_gym_dev_b200.legged_robot, legged_gym_dev_b200.rom, "
-            "legged_gym_dev_b200.ppo, legged_gym_dev_b200.mlp, legged_gym_dev_b200.datasets, legged_gym_dev_b200.task_registry; "
+            "legged_gym_dev_b200.ppo, legged_gym_dev_b200.mlp, legged_gym_dev_b200.datasets, legged_gym_dev_b200.task_registry, legged_gym_dev_b200.hopper, "
+            "legged_gym_dev_b200.legged_robot_trajectory; "
             "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.') or m == 'legged_case']; print(bad); "
             "sys.exit(1 if bad else 0)") % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
