@@ -32,9 +32,9 @@ def one(rep):
         cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
         agg = {hdr[i][6:]: 0 for i in cols}
         for r in rows[rows.index(hdr) + 1:]:
-            if len(r) == len(hdr):
+            if len(r) == len(hdr) and r[0] != "Address":      # a report with several launches repeats the header per function
                 for i in cols:
-                    agg[hdr[i][6:]] += int(r[i] or 0)
+                    agg[hdr[i][6:]] += int(r[i] or 0) if (r[i] or "0").lstrip("-").isdigit() else 0
         tot = max(1, sum(agg.values()))
         d["top stalls"] = ", ".join(f"{k} {100 * v / tot:.0f}%" for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:4])
     return d
