@@ -399,6 +399,66 @@ int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const float* wpa
 int b200gym_debug_mlp_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------------
+ * PPO.update training contractions (rsl_rl ppo.py: `loss.backward()` through ActorCritic.actor / .critic)
+ * on the tcgen05 tensor cores: ONE grouped fp16 GEMM kernel (fp32 accumulation in TMEM) in three modes.  All matrices are
+ * row-major fp16 with leading dimensions that are multiples of 8; m/n/k below are the PADDED extents (multiples of 16 except
+ * the row count of FWD/DGRAD and k of WGRAD), *_real the extents that exist in the fp32 parameter / gradient buffers.
+ *   FWD    out[m,n]  = act(a[m,k] . b[n,k]^T + bias)      a = activations, b = packed weights W_l [n,k]; bias fp32 [n_real];
+ *                                                           flags & 1: ELU, flags & 2: fp32 output (else fp16), ldo in elements
+ *   DGRAD  out[m,n]  = (a[m,k] . b[k,n]) * elu'(aux[m,n])  a = dZ_l, b = the SAME packed W_l [k,n] (read MN-major), aux = H_{l-1}
+ *                                                           (fp16, elu' = h > 0 ? 1 : h + 1); aux NULL: no derivative factor
+ *   WGRAD  out[m,n] += scale * a[k,m]^T . b[k,n]           a = dZ_l [rows,m], b = H_{l-1} [rows,n], k = rows (split over `splits`
+ *                                                           CTAs); out fp32 [m_real, n_real] with ldo, accumulated with red.add;
+ *                                                           bias (fp32 [m_real], may be NULL) += scale * column sums of a
+ * Up to B200GYM_GEMM_MAX_PROBLEMS problems per launch (the actor and the critic layer of the same depth, or every
+ * weight-gradient GEMM of an update, share one launch). */
+#define B200GYM_GEMM_FWD 0
+#define B200GYM_GEMM_DGRAD 1
+#define B200GYM_GEMM_WGRAD 2
+#define B200GYM_GEMM_MAX_PROBLEMS 8
+typedef struct B200GemmProblem {
+    const void* a;
+    const void* b;
+    void* out;
+    const void* aux;
+    float* bias;
+    int32_t mode, flags;
+    int32_t m, n, k;
+    int32_t lda, ldb, ldo, ldaux;
+    int32_t m_real, n_real;
+    int32_t splits;
+    float scale;
+} B200GemmProblem;
+int b200gym_gemm_f16(const B200GemmProblem* problems, int32_t n_problems, void* stream);
+
+/* dst[i, 0:dst_ld] (fp16) = src[idx ? idx[i] : i, 0:cols] (fp32, row stride src_ld), zero padded to dst_ld (a multiple of 8):
+ * the observation gather of RolloutStorage.mini_batch_generator fused with the operand conversion of the first layer. */
+int b200gym_rows_to_f16(const float* src, int64_t src_ld, int32_t cols, const int64_t* idx, void* dst, int32_t dst_ld, int64_t n_rows,
+                        void* stream);
+/* b200gym_ppo_loss with (a) the per-sample storage columns read through the minibatch indices idx (NULL = identity) straight
+ * from the [T*N, .] storage tensors, (b) mu / value read from the fp32 outputs of the last FWD GEMMs (row strides ld_mu /
+ * ld_value, value in column 0), (c) the gradients written as the fp16 [batch, 16] dZ operands of the backward GEMMs, WITHOUT
+ * the 1/batch factor (pass it as `scale` of the WGRAD problems); d_std and scalars as in b200gym_ppo_loss. */
+int b200gym_ppo_loss_gathered(const B200PpoLossParams* p, const int64_t* idx, const float* mu_out, int32_t ld_mu, const float* value_out,
+                              int32_t ld_value, const float* std, const float* actions, const float* old_log_prob, const float* advantages,
+                              const float* returns, const float* old_values, const float* old_mu, const float* old_sigma, void* dz_actor,
+                              void* dz_critic, float* d_std, double* scalars, void* stream);
+/* fp32 master parameters (one flat buffer) -> fp16 operand copies, every layer in one launch.  Entry e copies the [rows, cols]
+ * matrix at flat[src_off] to dst[dst_off] (in halves) as layout 0: row-major with leading dimension ld, or layout 1: the
+ * chunk-major [cols/8][ld][8] form of b200gym_mlp_forward's fp16 section.  elem_end = running total of rows*cols. */
+#define B200GYM_PACK_MAX 16
+typedef struct B200PackEntry {
+    int64_t src_off, dst_off, elem_end;
+    int32_t rows, cols, ld, layout;
+} B200PackEntry;
+typedef struct B200PackTable {
+    B200PackEntry e[B200GYM_PACK_MAX];
+    int64_t total;
+    int32_t n, pad;
+} B200PackTable;
+int b200gym_pack_params_f16(const float* flat, const B200PackTable* table, void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Tube-dataset construction from the rollout logs (deep_tube_learning/datasets.py:60-71,
  * deep_tube_learning/evaluation/evaluate_tube_simple.py:28-46) — SURVEY.md §8f row 2
  * ---------------------------------------------------------------------------------------------- */

@@ -125,6 +125,25 @@ class PpoLossParamsPOD(C.Structure):
                 ("clip_param", f32), ("value_loss_coef", f32), ("entropy_coef", f32), ("inv_global_batch", f32)]
 
 
+class GemmProblemPOD(C.Structure):
+    _fields_ = [("a", vp), ("b", vp), ("out", vp), ("aux", vp), ("bias", vp), ("mode", i32), ("flags", i32),
+                ("m", i32), ("n", i32), ("k", i32), ("lda", i32), ("ldb", i32), ("ldo", i32), ("ldaux", i32),
+                ("m_real", i32), ("n_real", i32), ("splits", i32), ("scale", f32)]
+
+
+GEMM_FWD, GEMM_DGRAD, GEMM_WGRAD = 0, 1, 2
+PACK_MAX = 16
+
+
+class PackEntryPOD(C.Structure):
+    _fields_ = [("src_off", C.c_int64), ("dst_off", C.c_int64), ("elem_end", C.c_int64), ("rows", i32), ("cols", i32), ("ld", i32),
+                ("layout", i32)]
+
+
+class PackTablePOD(C.Structure):
+    _fields_ = [("e", PackEntryPOD * PACK_MAX), ("total", C.c_int64), ("n", i32), ("pad", i32)]
+
+
 class PeerPtrsPOD(C.Structure):
     _fields_ = [("ptr", vp * 16)]
 
@@ -205,8 +224,14 @@ def lib():
     L.b200gym_sliding_window.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.b200gym_tube_error.restype = L.b200gym_sliding_window.restype = C.c_int
     L.b200gym_mlp_forward.restype = C.c_int
+    L.b200gym_gemm_f16.argtypes = [C.POINTER(GemmProblemPOD), C.c_int32, vp]
+    L.b200gym_gemm_f16.restype = C.c_int
+    L.b200gym_rows_to_f16.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, C.c_int32, C.c_int64, vp]
+    L.b200gym_ppo_loss_gathered.argtypes = [C.POINTER(PpoLossParamsPOD), vp, vp, C.c_int32, vp, C.c_int32] + [vp] * 13
+    L.b200gym_pack_params_f16.argtypes = [vp, C.POINTER(PackTablePOD), vp, vp]
+    L.b200gym_rows_to_f16.restype = L.b200gym_ppo_loss_gathered.restype = L.b200gym_pack_params_f16.restype = C.c_int
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
-                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD),
+                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD), ("B200GemmProblem", GemmProblemPOD), ("B200PackTable", PackTablePOD),
                       ("B200RomFamilyParams", RomFamilyParamsPOD), ("B200HopperTorqueParams", HopperTorqueParamsPOD),
                       ("B200HopperTorqueBuffers", HopperTorqueBuffersPOD), ("B200HopperObsParams", HopperObsParamsPOD)):
         n = L.b200gym_sizeof(name.encode())
