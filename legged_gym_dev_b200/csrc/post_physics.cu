@@ -1017,8 +1017,6 @@ extern "C" int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedB
         B200_REQUIRE(q != nullptr, B200GYM_EINVAL, "post_physics: null buffer");
         B200_REQUIRE(b200_aligned16(q), B200GYM_EALIGN, "post_physics: buffers must be 16-byte aligned");
     }
-    B200_REQUIRE(p->num_sum_rows == 0 || (b->episode_sums && b200_aligned16(b->episode_sums) && (p->num_envs % 4 == 0 || p->num_envs < 64)),
-                 B200GYM_EALIGN, "post_physics: episode_sums rows must be 16-byte aligned (num_envs %% 4 == 0)");
     const int do_push = (p->push_robots && p->push_time > 0 && (step % static_cast<uint64_t>(p->push_time) == 0)) ? 1 : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static int tile = 0;   // tuning knob (profiles/): envs per CTA
@@ -1026,6 +1024,11 @@ extern "C" int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedB
         const char* t = getenv("B200GYM_TILE");
         tile = t ? atoi(t) : 32;
     }
+    // full tiles move the episode_sums rows [K, N] with 16-byte bulk copies: every row start k*N must be 16-byte aligned unless
+    // the only CTA is a partial tile (cooperative copies) — checked against the tile size actually launched
+    const int tile_used = traj ? 32 : (tile == 32 || tile == 16 ? tile : 64);
+    B200_REQUIRE(p->num_sum_rows == 0 || (b->episode_sums && b200_aligned16(b->episode_sums) && (p->num_envs % 4 == 0 || p->num_envs < tile_used)),
+                 B200GYM_EALIGN, "post_physics: episode_sums rows must be 16-byte aligned (num_envs %% 4 == 0 once num_envs >= %d)", tile_used);
     if (traj) {
         if (rough) return launch_post_physics<32, true, true>(*p, *b, step, env_id_offset, 0, st);
         return launch_post_physics<32, false, true>(*p, *b, step, env_id_offset, 0, st);

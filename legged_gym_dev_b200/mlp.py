@@ -1,6 +1,7 @@
 """Fused ActorCritic MLP forward on the tcgen05 tensor cores (csrc/mlp.cu): packing of nn.Sequential(Linear, ELU, ...)
 weights into the kernel's operand layout and the call wrapper.  Used for the no-grad forward passes of the rollout
-(`PPO.act`) and of `get_inference_policy`; the training forward/backward still goes through autograd."""
+(`PPO.act`) and of `get_inference_policy` when the whole weight set fits in shared memory (`FusedMLP.fits`); larger nets
+and the training step run layer by layer through the grouped GEMM (legged_gym_dev_b200/train_mlp.py)."""
 import torch
 import torch.nn as nn
 
@@ -12,6 +13,18 @@ def _pad(n, m):
 
 
 class FusedMLP:
+    @staticmethod
+    def fits(seq: nn.Sequential) -> bool:
+        """True when the weights-resident one-launch kernel can take this Linear/ELU stack."""
+        lin = [m for m in seq if isinstance(m, nn.Linear)]
+        acts = [m for m in seq if not isinstance(m, nn.Linear)]
+        if not lin or len(lin) > 6 or len(acts) != len(lin) - 1 or not all(isinstance(a, nn.ELU) for a in acts):
+            return False
+        dims = [_pad(lin[0].in_features, 16)] + [_pad(l.out_features, 16) for l in lin]
+        wtot = sum(dims[i] * dims[i + 1] for i in range(len(lin)))
+        smem = (128 * max(dims[:-1]) + wtot + sum(dims[1:])) * 4 + 64
+        return max(dims[1:]) <= 256 and smem <= 227 * 1024
+
     def __init__(self, seq: nn.Sequential):
         self.linears = [m for m in seq if isinstance(m, nn.Linear)]
         acts = [m for m in seq if not isinstance(m, nn.Linear)]

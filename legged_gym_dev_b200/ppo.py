@@ -11,9 +11,12 @@ network outputs (one launch), grad-norm + clip + Adam over ONE flat parameter bu
 KL-adaptive learning rate kept on the device — no host sync inside update().  Across GPUs (envs sharded, one process
 per GPU) the only collectives are one all-reduce of the 3 advantage statistics per iteration and one all-reduce of the
 flat gradient buffer (+ KL sum/count piggy-backed) per minibatch.
-The no-grad MLP forward passes (rollout `act` / `evaluate`, `get_inference_policy`) run as one tcgen05 (TF32, TMEM)
-launch per net (legged_gym_dev_b200/mlp.py, csrc/mlp.cu); the training forward/backward still goes through autograd
-(cuBLAS) — a tcgen05 backward is the next step.
+Every contraction runs on the tcgen05 tensor cores in hand-written kernels: the no-grad forward passes (rollout `act` /
+`evaluate`, `get_inference_policy`) as one fused launch per net when the weights fit in shared memory
+(legged_gym_dev_b200/mlp.py, csrc/mlp.cu: fp16 operands, fp32 accumulation in TMEM) or layer by layer through the grouped
+GEMM otherwise (the 512-256-128 rough nets), and the training forward / backward / weight gradients of PPO.update through
+the grouped GEMM kernel (legged_gym_dev_b200/train_mlp.py, csrc/gemm.cu).  There is no autograd, no cuBLAS and no eager
+fallback on these paths: a net the kernels cannot take raises.
 """
 import ctypes as C
 import os
@@ -138,8 +141,8 @@ class ActorCritic(nn.Module):
     def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=(256, 256, 256),
                  critic_hidden_dims=(256, 256, 256), activation="elu", init_noise_std=1.0, fused_inference=True, **kwargs):
         super().__init__()
-        self._want_fused = bool(fused_inference) and activation == "elu"
-        self._fused_actor = self._fused_critic = None
+        self._want_fused = activation == "elu"
+        self._fused_actor = self._fused_critic = self._trainer = None
         acts = {"elu": nn.ELU, "selu": nn.SELU, "relu": nn.ReLU, "lrelu": nn.LeakyReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}
         if activation not in acts:
             raise ValueError(f"invalid activation function {activation}")
@@ -178,26 +181,46 @@ class ActorCritic(nn.Module):
         return self
 
     def enable_fused_inference(self):
-        """No-grad forward passes (rollout `act`, `evaluate`, `act_inference`) run as ONE tcgen05 launch per net when the
-        net fits the weights-resident kernel (csrc/mlp.cu); the training forward stays on autograd."""
-        self._fused_actor = self._fused_critic = None
-        if not self._want_fused or next(self.parameters()).device.type != "cuda":
+        """Builds the tensor-core paths: `TensorCoreTrainer` (grouped GEMM: training step, and the forward of nets too large
+        for shared memory) and, for nets whose weights fit in shared memory, the one-launch fused forward (csrc/mlp.cu).
+        Raises for nets the kernels cannot take (non-ELU activations, > 16 outputs): there is no eager fallback."""
+        self._fused_actor = self._fused_critic = self._trainer = None
+        if next(self.parameters()).device.type != "cuda":
             return
+        if not self._want_fused:
+            raise ValueError("the b200gym ActorCritic runs Linear/ELU stacks on its tensor-core kernels only (activation='elu')")
         from .mlp import FusedMLP
-        try:
-            self._fused_actor, self._fused_critic = FusedMLP(self.actor), FusedMLP(self.critic)
-        except ValueError:
-            self._fused_actor = self._fused_critic = None
+        from .train_mlp import TensorCoreTrainer
+        self._trainer = TensorCoreTrainer(self)
+        for which, net in (("_fused_actor", self.actor), ("_fused_critic", self.critic)):
+            if FusedMLP.fits(net):
+                setattr(self, which, FusedMLP(net))
 
     def repack_fused(self):
-        if self._fused_actor is not None:
-            self._fused_actor.repack()
-            self._fused_critic.repack()
+        """Refreshes every fp16 / packed weight copy from the fp32 master parameters (after an optimiser step or a load)."""
+        if self._trainer is not None:
+            self._trainer.pack()
+        for f in (self._fused_actor, self._fused_critic):
+            if f is not None:
+                f.repack()
 
-    def _forward(self, net, fused, x):
-        if fused is not None and not torch.is_grad_enabled() and x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1:
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        if self.flat_param is not None:
+            self.repack_fused()
+        return out
+
+    def _forward(self, which, x):
+        """Forward of the actor (0) / critic (1) on the tensor-core kernels; the result carries no autograd graph (the
+        training gradients are produced by PPO.update's kernels, not by autograd)."""
+        if self._trainer is None:
+            raise RuntimeError("ActorCritic: call flatten_parameters() on a CUDA device first (the b200gym path has no CPU / eager fallback)")
+        if not (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1):
+            raise RuntimeError("ActorCritic: expected a float32 CUDA tensor of shape [batch, num_obs] with unit inner stride")
+        fused = self._fused_actor if which == 0 else self._fused_critic
+        if fused is not None:
             return fused(x)
-        return net(x)
+        return self._trainer.forward_net(which, x)
 
     def reset(self, dones=None):
         pass
@@ -215,7 +238,7 @@ class ActorCritic(nn.Module):
         return self.distribution.entropy().sum(dim=-1)
 
     def update_distribution(self, observations):
-        mean = self._forward(self.actor, self._fused_actor, observations)
+        mean = self._forward(0, observations)
         self.distribution = torch.distributions.Normal(mean, mean * 0.0 + self.std)
 
     def act(self, observations, **kwargs):
@@ -226,10 +249,10 @@ class ActorCritic(nn.Module):
         return self.distribution.log_prob(actions).sum(dim=-1)
 
     def act_inference(self, observations):
-        return self._forward(self.actor, self._fused_actor, observations)
+        return self._forward(0, observations)
 
     def evaluate(self, critic_observations, **kwargs):
-        return self._forward(self.critic, self._fused_critic, critic_observations)
+        return self._forward(1, critic_observations)
 
 
 class PPO:
@@ -266,7 +289,6 @@ class PPO:
         self._klsum = torch.zeros(2, dtype=torch.double, device=self.device)
         self._mb_cache = {}
         self.use_graph = os.environ.get("B200GYM_PPO_GRAPH", "1") != "0"
-        self.tf32_matmul = os.environ.get("B200GYM_PPO_TF32", "1") != "0"
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
@@ -283,7 +305,19 @@ class PPO:
         tr.values = ac.evaluate(critic_obs).detach()
         tr.actions_log_prob = ac.get_actions_log_prob(tr.actions).detach()
         tr.action_mean, tr.action_sigma = ac.action_mean.detach(), ac.action_std.detach()
-        tr.observations, tr.critic_observations = obs, critic_obs
+        # rsl_rl keeps references because its env returns a fresh obs tensor every step (legged_robot.py:211); the fused env
+        # rewrites ONE persistent obs_buf in place, so the transition must hold the observation the action was computed from
+        s = self.storage.step if self.storage is not None else None
+        if s is not None and s < self.storage.num_transitions_per_env:
+            self.storage.observations[s].copy_(obs)
+            tr.observations = self.storage.observations[s]
+            if self.storage.privileged_observations is not None:
+                self.storage.privileged_observations[s].copy_(critic_obs)
+                tr.critic_observations = self.storage.privileged_observations[s]
+            else:
+                tr.critic_observations = tr.observations
+        else:
+            tr.observations, tr.critic_observations = obs.clone(), critic_obs.clone()
         return tr.actions
 
     def process_env_step(self, rewards, dones, infos):
@@ -301,33 +335,24 @@ class PPO:
         self.storage.compute_returns(last_values, self.gamma, self.lam)
 
     def _minibatch_step(self, mb, world):
-        """One minibatch of PPO.update on the static buffers `mb` (gather target tensors): forward, fused loss + gradient,
-        backward, gradient all-reduce, KL-adaptive LR, clip + Adam.  No host synchronisation: capturable in a CUDA graph."""
+        """One minibatch of PPO.update for the row indices in the static tensor mb["idx"]: observation gather + forward (tcgen05
+        GEMMs), fused loss + gradient w.r.t. the network outputs, input- and weight-gradient GEMMs, gradient exchange,
+        KL-adaptive LR, clip + Adam, fp16 weight refresh.  No host synchronisation: capturable in a CUDA graph."""
         ac, ptr, st = self.actor_critic, _lib.ptr, _lib.stream_ptr(self.device)
-        obs, cobs, act, old_v, ret, old_logp, adv, old_mu, old_sigma = mb["tensors"]
-        B = obs.shape[0]
+        idx = mb["idx"]
+        B = idx.numel()
         std_off, _ = ac._slices["std"]
         lp = _lib.PpoLossParamsPOD()
         lp.num_actions, lp.use_clipped_value_loss = ac.std.numel(), int(self.use_clipped_value_loss)
         lp.clip_param, lp.value_loss_coef, lp.entropy_coef = self.clip_param, self.value_loss_coef, self.entropy_coef
         lp.batch, lp.inv_global_batch = B, 1.0 / (B * world)
-        # the training contractions run on the tensor cores in TF32 (SURVEY.md §8a G4: not under the 1e-5 contract);
-        # the flag is read when the GEMMs are enqueued (forward here, backward below) and restored afterwards
-        tf32_was = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = self.tf32_matmul
-        mu = ac.actor(obs)
-        value = ac.critic(cobs)
-        d_mu, d_value = mb["d_mu"], mb["d_value"]
         ac.flat_grad.zero_()
         sc = self._scalars[4:8]
         sc.zero_()
-        _lib.check(self.lib.b200gym_ppo_loss(lp, ptr(mu), ptr(ac.std), ptr(value), ptr(act), ptr(old_logp), ptr(adv), ptr(ret),
-                                             ptr(old_v), ptr(old_mu), ptr(old_sigma), ptr(d_mu), ptr(d_value),
-                                             C.c_void_p(ac.flat_grad.data_ptr() + 4 * std_off), ptr(sc), st), "ppo_loss")
-        torch.autograd.backward([mu, value], [d_mu, d_value.view(-1, 1)])
-        torch.backends.cuda.matmul.allow_tf32 = tf32_was
+        ac._trainer.minibatch_forward_backward(self.storage, idx, lp, ac.std, C.c_void_p(ac.flat_grad.data_ptr() + 4 * std_off), sc,
+                                               self.storage.privileged_observations is None)
         self._scalars[0:4] += sc
-        # one all-reduce: gradients + (sum kl, count) piggy-backed in the spare tail of the flat buffer
+        # one exchange: gradients + (sum kl, count) piggy-backed in the spare tail of the flat buffer
         tail = ac.flat_grad[ac.num_flat:ac.num_flat + 2]
         tail[0:1].copy_(sc[0:1])
         tail[1:2].fill_(float(B))
@@ -345,36 +370,22 @@ class PPO:
             _lib.check(self.lib.b200gym_adaptive_lr(ptr(self._klsum), float(B * world), self.desired_kl, ptr(self.optimizer.lr), st),
                        "adaptive_lr")
         self.optimizer.step(self.max_grad_norm, grad=grad)
+        ac._trainer.pack()
 
     def _static_minibatch(self, B):
-        """Persistent gather targets of one minibatch + the captured CUDA graph of `_minibatch_step` on them."""
+        """Static index tensor of one minibatch + the captured CUDA graph of `_minibatch_step` on it."""
         key = (B, self.storage.observations.data_ptr())
         mb = self._mb_cache.get(key)
         if mb is not None:
             return mb
-        st, dev = self.storage, self.device
-        crit = st.privileged_observations if st.privileged_observations is not None else st.observations
-        srcs = [st.observations, crit, st.actions, st.values, st.returns, st.actions_log_prob, st.advantages, st.mu, st.sigma]
-        flat = [t.flatten(0, 1) for t in srcs]
-        n = len(flat)
-        mb = dict(tensors=[torch.empty(B, *f.shape[1:], dtype=f.dtype, device=dev) for f in flat],
-                  idx=torch.zeros(B, dtype=torch.int64, device=dev), d_mu=torch.empty(B, self.actor_critic.std.numel(), device=dev),
-                  d_value=torch.empty(B, device=dev), graph=None)
-        mb["row_bytes"] = (C.c_int32 * n)(*[f.shape[1] * f.element_size() for f in flat])
-        mb["src_ptrs"] = (C.c_void_p * n)(*[f.data_ptr() for f in flat])
-        mb["dst_ptrs"] = (C.c_void_p * n)(*[o.data_ptr() for o in mb["tensors"]])
-        mb["n"] = n
+        mb = dict(idx=torch.zeros(B, dtype=torch.int64, device=self.device), graph=None)
         self._mb_cache = {key: mb}
         return mb
 
-    def _gather(self, mb):
-        _lib.check(self.lib.b200gym_gather_rows(mb["dst_ptrs"], mb["src_ptrs"], mb["row_bytes"], mb["n"], _lib.ptr(mb["idx"]),
-                                                mb["idx"].numel(), _lib.stream_ptr(self.device)), "gather_rows")
-
     def update(self, plan=None):
-        """rsl_rl PPO.update.  The body of one minibatch (gather -> forward -> loss -> backward -> all-reduce -> Adam) is
-        captured ONCE as a CUDA graph and replayed for every minibatch of every epoch; only the row indices change
-        (copied into a static index tensor).  B200GYM_PPO_GRAPH=0 runs the same body eagerly."""
+        """rsl_rl PPO.update.  The body of one minibatch (gather -> forward -> loss -> backward -> gradient exchange -> Adam
+        -> weight repack) is captured ONCE as a CUDA graph and replayed for every minibatch of every epoch; only the row
+        indices change (copied into a static index tensor).  B200GYM_PPO_GRAPH=0 runs the same body eagerly."""
         ac = self.actor_critic
         world = 1
         if _dist_ready():
@@ -396,7 +407,6 @@ class PPO:
                 mb = self._static_minibatch(idx.numel())
             mb["idx"].copy_(idx, non_blocking=True)
             if not use_graph:
-                self._gather(mb)
                 self._minibatch_step(mb, world)
             else:
                 if mb["graph"] is None:
@@ -411,24 +421,23 @@ class PPO:
         return s[2], s[1]   # mean_value_loss, mean_surrogate_loss (device scalars)
 
     def _capture(self, mb, world):
-        """Warm-up on a side stream (cuBLAS workspaces, autograd buffers), restore the optimiser state, then capture."""
+        """Warm-up on a side stream (buffer allocation, kernel attributes), restore the optimiser state, then capture."""
         ac, opt = self.actor_critic, self.optimizer
         keep = [t.clone() for t in (ac.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.lr, opt.step_dev, self._scalars)]
         steps = opt.steps
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(3):
-                self._gather(mb)
+            for _ in range(2):
                 self._minibatch_step(mb, world)
         torch.cuda.current_stream(self.device).wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._gather(mb)
             self._minibatch_step(mb, world)
         for t, k in zip((ac.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.lr, opt.step_dev, self._scalars), keep):
             t.copy_(k)
         opt.steps = steps
+        ac._trainer.pack()
         mb["graph"] = g
 
 

@@ -64,3 +64,30 @@ def test_actor_critic_uses_fused_forward_without_grad():
     ac.repack_fused()
     with torch.no_grad():
         assert (ac.act_inference(x) - ac.actor(x)).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("batch", [4096, 100])
+def test_rough_nets_forward_on_grouped_gemm(batch):
+    """235 -> 512 -> 256 -> 128 -> 12 / 1 (legged_robot_config.py:242-243) does not fit the weights-resident kernel: the forward runs
+    layer by layer on the grouped tcgen05 GEMM (fp16 operands, fp32 accumulation), never on torch."""
+    from legged_gym_dev_b200.ppo import ActorCritic, PPO
+    torch.manual_seed(2)
+    ac = ActorCritic(235, 235, 12, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128])
+    PPO(ac, device="cuda")
+    assert ac._fused_actor is None and ac._trainer is not None
+    x = torch.randn(batch, 235, device="cuda").clamp(-5, 5)
+    with torch.no_grad():
+        mu, v = ac.act_inference(x), ac.evaluate(x)
+        mu_ref, v_ref = ac.actor(x), ac.critic(x)
+    assert mu.shape == mu_ref.shape and v.shape == v_ref.shape
+    assert (mu - mu_ref).abs().max().item() < 1e-2 and (mu - mu_ref).abs().mean().item() < 2e-3
+    assert (v - v_ref).abs().max().item() < 1e-2
+    both = ac._trainer.forward_both(x, x)
+    assert torch.equal(both[0], mu) and torch.equal(both[1], v)
+
+
+def test_unsupported_activation_raises():
+    from legged_gym_dev_b200.ppo import ActorCritic, PPO
+    ac = ActorCritic(48, 48, 12, actor_hidden_dims=[32], critic_hidden_dims=[32], activation="tanh")
+    with pytest.raises(ValueError):
+        PPO(ac, device="cuda")

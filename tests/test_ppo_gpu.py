@@ -1,6 +1,7 @@
 """Group G parity on the GPU: storage / PPO kernels vs the restated rsl_rl arithmetic (oracle/port_ppo.py; parity
-unpinned by the reference, see that file's header).  returns / advantages: 1e-5 (S = 1); update: 1e-3 as per
-SURVEY.md §8d cfg 5 (the MLP contraction is a library GEMM on both sides), identical LR-schedule decisions."""
+unpinned by the reference, see that file's header).  returns / advantages: 1e-5 (S = 1); update: losses / KL / gradient norm
+to 1e-3 as per SURVEY.md §8d cfg 5 (the contractions run in fp16 on the tcgen05 tensor cores with fp32 accumulation; the
+oracle is fp32 torch), identical LR-schedule decisions."""
 import copy
 
 import pytest
@@ -134,32 +135,100 @@ def test_ppo_loss_gradients_match_autograd():
     assert_close(sc[3].cpu() / B, ent.mean().detach().double(), 1.0, "entropy", rtol=1e-4)
 
 
-@pytest.mark.parametrize("graph", [True, False])
-def test_ppo_update_tracks_oracle(graph):
-    """cfg 5 shape: flat nets [128,64,32], 4 minibatches; identical LR decisions, parameters within 1e-3.  graph=True: the
-    minibatch step replayed from one captured CUDA graph (the default), graph=False: the same body launched eagerly."""
-    ref, alg = _oracle_and_fused()
-    alg.use_graph, alg.tf32_matmul = graph, False     # fp32 library GEMMs on both sides: parameter-level parity
-    T, N = 24, 512
-    store = _fill(alg, ref, T, N, 48)
-    plan = O.mini_batch_indices(T, N, 4, 2, generator=torch.Generator().manual_seed(3))
+def _update_pair(num_obs, hidden, T, N, epochs=2, graph=True, seed=1):
+    ref, alg = _oracle_and_fused(num_obs, hidden, seed=seed)
+    alg.use_graph, alg.num_learning_epochs = graph, epochs
+    store = _fill(alg, ref, T, N, num_obs)
+    plan = O.mini_batch_indices(T, N, 4, epochs, generator=torch.Generator().manual_seed(3))
     opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
     lr, stats = O.ppo_update(ref, opt, store, plan, 1e-3, desired_kl=0.01, max_grad_norm=1.0, schedule="adaptive", clip_param=0.2,
                              value_loss_coef=1.0, entropy_coef=0.01, use_clipped_value_loss=True)
-    alg.update(plan=[p.cuda() for p in plan])
+    v_loss, s_loss = alg.update(plan=[p.cuda() for p in plan])
+    return ref, alg, plan, lr, stats, float(v_loss), float(s_loss)
+
+
+def _check_update(ref, alg, plan, lr, stats, v_loss, s_loss):
+    """SURVEY.md §8d cfg 5 contract for the tensor-core path: losses to 1e-3 relative and identical LR-schedule decisions.  Adam's
+    sign-like first steps make a parameter-level 1e-3 bound meaningless at 10-bit operand mantissas (a flipped 1e-7 gradient moves
+    a weight by 2 lr): parameters are bounded by 10 lr in the worst element and 0.5 lr on average."""
     assert alg.optimizer.steps == len(plan) and int(alg.optimizer.step_dev) == len(plan)
     assert abs(float(alg.optimizer.lr) - lr) <= 1e-9 + 1e-6 * lr, (float(alg.optimizer.lr), lr, [s["lr"] for s in stats])
+    want_v = sum(s["value_loss"] for s in stats) / len(stats)
+    want_s = sum(s["surrogate"] for s in stats) / len(stats)
+    assert abs(v_loss - want_v) <= 1e-3 * abs(want_v) + 1e-6, (v_loss, want_v)
+    assert abs(s_loss - want_s) <= 1e-3 * max(abs(want_s), 0.05), (s_loss, want_s)
     sd = alg.actor_critic.state_dict()
-    for k, v in ref.state_dict().items():
-        assert_close(sd[k].cpu(), v, 1.0, f"parameter {k} after update", rtol=1e-3)
+    lr_max = max(s["lr"] for s in stats)
+    worst = max((sd[k].cpu() - v).abs().max().item() for k, v in ref.state_dict().items())
+    mean = sum((sd[k].cpu() - v).abs().sum().item() for k, v in ref.state_dict().items()) / sum(v.numel() for v in ref.state_dict().values())
+    assert worst <= 10 * lr_max and mean <= 0.5 * lr_max, (worst, mean, lr_max)
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_ppo_update_tracks_oracle(graph):
+    """cfg 5 shape: flat nets [128,64,32], 4 minibatches.  graph=True: the minibatch step replayed from one captured CUDA graph
+    (the default), graph=False: the same body launched eagerly."""
+    _check_update(*_update_pair(48, (128, 64, 32), 24, 512, graph=graph))
+
+
+def test_ppo_update_cfg5_full_size():
+    """BASELINE.json configs[4] at its stated size: 4096 envs x 24 steps, 4 minibatches of 24 576 samples."""
+    _check_update(*_update_pair(48, (128, 64, 32), 24, 4096, epochs=2))
+
+
+def test_ppo_update_rough_nets():
+    """The base LeggedRobotCfgPPO policy (legged_robot_config.py:242-243): 235 -> 512 -> 256 -> 128 -> 12 / 1, weights streamed
+    through shared memory by the grouped GEMM (they do not fit the weights-resident forward kernel)."""
+    _check_update(*_update_pair(235, (512, 256, 128), 24, 256, epochs=1))
+
+
+@pytest.mark.parametrize("num_obs,hidden,B", [(48, (128, 64, 32), 6144), (235, (512, 256, 128), 3000), (48, (128, 64, 32), 100)])
+def test_minibatch_gradients_match_autograd(num_obs, hidden, B):
+    """flat_grad after one forward/backward of the tcgen05 path vs torch autograd (fp32) of the restated loss on the same
+    minibatch: gradient norm to 1e-3 relative, gradient vector to 5e-3 of its norm (fp16 operands, fp32 accumulation)."""
+    from legged_gym_dev_b200 import _lib
+    import ctypes as C
+    ref, alg = _oracle_and_fused(num_obs, hidden)
+    T, N = 8, 1024
+    store = _fill(alg, ref, T, N, num_obs)
+    with torch.no_grad():                       # move the policy away from the rollout policy: ratios != 1, clips engage
+        for p in ref.parameters():
+            p.add_(0.03 * torch.randn_like(p))
+    ac = alg.actor_critic
+    ac.load_state_dict(copy.deepcopy(ref.state_dict()))
+    idx = torch.randperm(T * N, generator=torch.Generator().manual_seed(4))[:B]
+    batch = {k: v[idx] for k, v in store.items()}
+    loss, info = O.ppo_loss(ref, batch, clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.01, use_clipped_value_loss=True)
+    loss.backward()
+    lp = _lib.PpoLossParamsPOD()
+    lp.batch, lp.num_actions, lp.use_clipped_value_loss = B, 12, 1
+    lp.clip_param, lp.value_loss_coef, lp.entropy_coef, lp.inv_global_batch = 0.2, 1.0, 0.01, 1.0 / B
+    ac.flat_grad.zero_()
+    sc = torch.zeros(4, dtype=torch.double, device="cuda")
+    std_off, _ = ac._slices["std"]
+    ac._trainer.minibatch_forward_backward(alg.storage, idx.cuda(), lp, ac.std, C.c_void_p(ac.flat_grad.data_ptr() + 4 * std_off), sc, True)
+    torch.cuda.synchronize()
+    got = {name: ac.flat_grad[o:o + k].cpu().view_as(p) for (name, p), (o, k) in
+           ((it, ac._slices[it[0]]) for it in ac.named_parameters())}
+    want = {name: p.grad for name, p in ref.named_parameters()}
+    gn_got = sum(float((g.double() ** 2).sum()) for g in got.values()) ** 0.5
+    gn_want = sum(float((g.double() ** 2).sum()) for g in want.values()) ** 0.5
+    assert abs(gn_got - gn_want) <= 1e-3 * gn_want, (gn_got, gn_want)
+    diff = sum(float(((got[k] - want[k]).double() ** 2).sum()) for k in want) ** 0.5
+    per = {k: float((got[k] - want[k]).abs().max() / (want[k].abs().max() + 1e-12)) for k in want}
+    assert diff <= 5e-3 * gn_want, (diff, gn_want, per)
+    assert abs(float(sc[0]) / B - float(info["kl_mean"])) <= 1e-3 * float(info["kl_mean"]) + 1e-6
+    assert abs(float(sc[1]) / B - float(info["surrogate_loss"])) <= 1e-3 * max(abs(float(info["surrogate_loss"])), 0.05)
+    assert abs(float(sc[2]) / B - float(info["value_loss"])) <= 1e-3 * float(info["value_loss"]) + 1e-6
 
 
 def test_graph_and_eager_updates_agree_over_two_iterations():
-    """Second update() reuses the captured graph (new indices, advanced Adam step): must match the eager path closely."""
+    """Second update() reuses the captured graph (new indices, advanced Adam step): must match the eager path closely (the
+    weight-gradient split-K sums are fp32 red.add in arrival order, so the two runs are not bit-identical)."""
     outs = []
     for graph in (True, False):
         ref, alg = _oracle_and_fused(seed=5)
-        alg.use_graph, alg.tf32_matmul = graph, False
+        alg.use_graph = graph
         T, N = 8, 256
         for it in range(2):
             _fill(alg, ref, T, N, 48, seed=7 + it)
@@ -169,30 +238,26 @@ def test_graph_and_eager_updates_agree_over_two_iterations():
         outs.append((alg.actor_critic.flat_param.clone(), float(alg.optimizer.lr), alg.optimizer.steps))
     assert outs[0][2] == outs[1][2] == 16
     assert outs[0][1] == outs[1][1]
-    assert_close(outs[0][0].cpu(), outs[1][0].cpu(), 1.0, "flat parameters graph vs eager", rtol=2e-4)
+    d = (outs[0][0] - outs[1][0]).abs()
+    assert d.max().item() <= 5e-3 and d.mean().item() <= 2e-5, (d.max().item(), d.mean().item())
 
 
-def test_ppo_update_tf32_contractions():
-    """Default mode: the training GEMMs run in TF32 on the tensor cores.  SURVEY.md §8d cfg 5 contract for that path:
-    losses to 1e-3 relative and identical LR-schedule decisions (Adam's sign-like first steps make a parameter-level
-    1e-3 bound meaningless at TF32: a flipped 1e-7 gradient moves a weight by 2 lr); parameters are checked at 5 lr."""
+def test_update_launches_no_library_gemm():
+    """The update path contains no cuBLAS / cutlass / autograd kernel: every launch of one update() is one of ours."""
+    from torch.profiler import profile, ProfilerActivity
     ref, alg = _oracle_and_fused()
-    assert alg.tf32_matmul and alg.use_graph
-    T, N = 24, 512
-    store = _fill(alg, ref, T, N, 48)
-    plan = O.mini_batch_indices(T, N, 4, 2, generator=torch.Generator().manual_seed(3))
-    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
-    lr, stats = O.ppo_update(ref, opt, store, plan, 1e-3, desired_kl=0.01, max_grad_norm=1.0, schedule="adaptive", clip_param=0.2,
-                             value_loss_coef=1.0, entropy_coef=0.01, use_clipped_value_loss=True)
-    v_loss, s_loss = alg.update(plan=[p.cuda() for p in plan])
-    assert abs(float(alg.optimizer.lr) - lr) <= 1e-9 + 1e-6 * lr, (float(alg.optimizer.lr), lr, [s["lr"] for s in stats])
-    want_v = sum(s["value_loss"] for s in stats) / len(stats)
-    want_s = sum(s["surrogate"] for s in stats) / len(stats)
-    assert abs(float(v_loss) - want_v) <= 1e-3 * abs(want_v) + 1e-6, (float(v_loss), want_v)
-    assert abs(float(s_loss) - want_s) <= 1e-3 * max(abs(want_s), 0.05), (float(s_loss), want_s)
-    sd = alg.actor_critic.state_dict()
-    worst = max((sd[k].cpu() - v).abs().max().item() for k, v in ref.state_dict().items())
-    assert worst <= 10 * max(s["lr"] for s in stats), worst
+    alg.use_graph = False
+    _fill(alg, ref, 8, 256, 48)
+    alg.update()
+    alg.storage.step = 8
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        alg.update()
+        torch.cuda.synchronize()
+    names = {e.key for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA}
+    bad = [n for n in names if "gemm_f16_kernel" not in n and
+           any(t in n.lower() for t in ("sgemm", "cutlass", "cublas", "gemv", "ampere", "sm90", "xmma", "nvjet"))]
+    assert not bad, bad
+    assert any("gemm_f16_kernel" in n for n in names), names
 
 
 @pytest.mark.parametrize("world", [1, 2, 5, 8])
