@@ -431,6 +431,29 @@ typedef struct B200GemmProblem {
 } B200GemmProblem;
 int b200gym_gemm_f16(const B200GemmProblem* problems, int32_t n_problems, void* stream);
 
+/* Forward + loss + input-gradient chain of one PPO minibatch in ONE launch, for nets whose 128-row activation tiles fit in
+ * shared memory (every layer output <= 128 wide: the 48-128-64-32 flat nets).  Per net (actor, critic) and layer l:
+ * kp[l] / np[l] = padded input / output width (multiples of 16, kp[l+1] == np[l], np[last] == 16), n_real[l] = real output
+ * width, w_off[l] = offset (halves) of the row-major fp16 copy [np[l], kp[l]] in w16, b_off[l] = offset (floats) of the bias
+ * in flat_param.  x: fp16 [batch, ldx] input rows (b200gym_rows_to_f16).  Written: h[l] fp16 [batch, np[l]] (l < last),
+ * dz[l] fp16 [batch, np[l]] (all l; unscaled, as in b200gym_ppo_loss_gathered), out (optional fp32 [batch, 16]), d_std and
+ * scalars as in b200gym_ppo_loss.  Follow with WGRAD problems of b200gym_gemm_f16 over (dz[l], h[l-1] | x). */
+#define B200GYM_CHAIN_MAX_LAYERS 6
+typedef struct B200ChainNet {
+    const void* x;
+    const void* w16;
+    const float* flat_param;
+    void* h[B200GYM_CHAIN_MAX_LAYERS];
+    void* dz[B200GYM_CHAIN_MAX_LAYERS];
+    float* out;
+    int64_t w_off[B200GYM_CHAIN_MAX_LAYERS], b_off[B200GYM_CHAIN_MAX_LAYERS];
+    int32_t kp[B200GYM_CHAIN_MAX_LAYERS], np[B200GYM_CHAIN_MAX_LAYERS], n_real[B200GYM_CHAIN_MAX_LAYERS];
+    int32_t num_layers, ldx;
+} B200ChainNet;
+int b200gym_ppo_chain(const B200ChainNet* actor, const B200ChainNet* critic, const B200PpoLossParams* lp, const int64_t* idx,
+                      const float* std, const float* actions, const float* old_log_prob, const float* advantages,
+                      const float* returns, const float* old_values, const float* old_mu, const float* old_sigma, float* d_std,
+                      double* scalars, void* stream);
 /* dst[i, 0:dst_ld] (fp16) = src[idx ? idx[i] : i, 0:cols] (fp32, row stride src_ld), zero padded to dst_ld (a multiple of 8):
  * the observation gather of RolloutStorage.mini_batch_generator fused with the operand conversion of the first layer. */
 int b200gym_rows_to_f16(const float* src, int64_t src_ld, int32_t cols, const int64_t* idx, void* dst, int32_t dst_ld, int64_t n_rows,
@@ -457,6 +480,21 @@ typedef struct B200PackTable {
     int32_t n, pad;
 } B200PackTable;
 int b200gym_pack_params_f16(const float* flat, const B200PackTable* table, void* dst, void* stream);
+/* Everything of a PPO minibatch step after the backward pass in ONE launch (rsl_rl PPO.update: adaptive-KL schedule,
+ * clip_grad_norm_, Adam.step) + the fp16 operand copies of the updated weights (b200gym_pack_params_f16's table) + the
+ * clearing of grad[0 .. n+8) and of the per-minibatch sums for the next minibatch.  mb_scalars[0..3] = this minibatch's
+ * {sum kl, sum surrogate, sum value loss, sum entropy} (b200gym_ppo_chain / _ppo_loss_gathered), added to totals[0..3] and
+ * zeroed; totals[4] = squared gradient norm of this step.  count = minibatch samples (KL mean denominator).  lr and the step
+ * count live on the device.  workspace: 16 zero-initialised bytes, owned by the call sequence (reset on exit). */
+typedef struct B200OptParams {
+    int64_t n;
+    double count;
+    int32_t adaptive, pad;
+    float desired_kl, max_grad_norm, beta1, beta2, eps, pad2;
+} B200OptParams;
+int b200gym_ppo_optimizer_step(const B200OptParams* p, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* lr,
+                               int32_t* step_dev, double* mb_scalars, double* totals, void* workspace, const B200PackTable* table, void* w16,
+                               void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Tube-dataset construction from the rollout logs (deep_tube_learning/datasets.py:60-71,

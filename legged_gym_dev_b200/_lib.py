@@ -135,6 +135,21 @@ GEMM_FWD, GEMM_DGRAD, GEMM_WGRAD = 0, 1, 2
 PACK_MAX = 16
 
 
+CHAIN_MAX_LAYERS = 6
+
+
+class ChainNetPOD(C.Structure):
+    _fields_ = [("x", vp), ("w16", vp), ("flat_param", vp), ("h", vp * CHAIN_MAX_LAYERS), ("dz", vp * CHAIN_MAX_LAYERS), ("out", vp),
+                ("w_off", C.c_int64 * CHAIN_MAX_LAYERS), ("b_off", C.c_int64 * CHAIN_MAX_LAYERS),
+                ("kp", i32 * CHAIN_MAX_LAYERS), ("np", i32 * CHAIN_MAX_LAYERS), ("n_real", i32 * CHAIN_MAX_LAYERS),
+                ("num_layers", i32), ("ldx", i32)]
+
+
+class OptParamsPOD(C.Structure):
+    _fields_ = [("n", C.c_int64), ("count", C.c_double), ("adaptive", i32), ("pad", i32), ("desired_kl", f32), ("max_grad_norm", f32),
+                ("beta1", f32), ("beta2", f32), ("eps", f32), ("pad2", f32)]
+
+
 class PackEntryPOD(C.Structure):
     _fields_ = [("src_off", C.c_int64), ("dst_off", C.c_int64), ("elem_end", C.c_int64), ("rows", i32), ("cols", i32), ("ld", i32),
                 ("layout", i32)]
@@ -229,9 +244,13 @@ def lib():
     L.b200gym_rows_to_f16.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, C.c_int32, C.c_int64, vp]
     L.b200gym_ppo_loss_gathered.argtypes = [C.POINTER(PpoLossParamsPOD), vp, vp, C.c_int32, vp, C.c_int32] + [vp] * 13
     L.b200gym_pack_params_f16.argtypes = [vp, C.POINTER(PackTablePOD), vp, vp]
+    L.b200gym_ppo_chain.argtypes = [C.POINTER(ChainNetPOD), C.POINTER(ChainNetPOD), C.POINTER(PpoLossParamsPOD)] + [vp] * 12
+    L.b200gym_ppo_chain.restype = C.c_int
+    L.b200gym_ppo_optimizer_step.argtypes = [C.POINTER(OptParamsPOD)] + [vp] * 9 + [C.POINTER(PackTablePOD), vp, vp]
+    L.b200gym_ppo_optimizer_step.restype = C.c_int
     L.b200gym_rows_to_f16.restype = L.b200gym_ppo_loss_gathered.restype = L.b200gym_pack_params_f16.restype = C.c_int
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
-                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD), ("B200GemmProblem", GemmProblemPOD), ("B200PackTable", PackTablePOD),
+                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD), ("B200GemmProblem", GemmProblemPOD), ("B200PackTable", PackTablePOD), ("B200ChainNet", ChainNetPOD), ("B200OptParams", OptParamsPOD),
                       ("B200RomFamilyParams", RomFamilyParamsPOD), ("B200HopperTorqueParams", HopperTorqueParamsPOD),
                       ("B200HopperTorqueBuffers", HopperTorqueBuffersPOD), ("B200HopperObsParams", HopperObsParamsPOD)):
         n = L.b200gym_sizeof(name.encode())

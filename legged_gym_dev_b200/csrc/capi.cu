@@ -33,6 +33,8 @@ int b200gym_sizeof(const char* name) {
     if (!strcmp(name, "B200PeerPtrs")) return (int)sizeof(B200PeerPtrs);
     if (!strcmp(name, "B200GemmProblem")) return (int)sizeof(B200GemmProblem);
     if (!strcmp(name, "B200PackTable")) return (int)sizeof(B200PackTable);
+    if (!strcmp(name, "B200ChainNet")) return (int)sizeof(B200ChainNet);
+    if (!strcmp(name, "B200OptParams")) return (int)sizeof(B200OptParams);
     return -1;
 }
 

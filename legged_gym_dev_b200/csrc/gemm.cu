@@ -89,6 +89,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_f16_kernel(const __grid_
         mbar_init(accum, 1);
         fence_mbar_init();
     }
+    // WGRAD: the dZ tile is [rows x 128 columns] whatever the layer width; columns beyond the layer's width are zero and never change,
+    // so they are written once here instead of being re-issued as zero-fill copies in every stage
+    const int a_chunks = mode == B200GYM_GEMM_WGRAD ? min(TM / 8, (P.m - tile_m * TM + 7) / 8) : 0;
+    if (mode == B200GYM_GEMM_WGRAD && a_chunks < TM / 8 && warp >= 4 && warp < 8) {
+        const int t = tid - 128, nz = TM / 8 - a_chunks;
+        for (int q = t; q < NSTAGE * nz * KC; q += 128) {
+            const int s = q / (nz * KC), rem = q - s * (nz * KC), c = a_chunks + rem / KC, r = rem % KC;
+            *reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + c * CH_ROWSKC + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async();
+    }
     if (ones_block && warp >= 4 && warp < 8) {
         // the bias gradient rides the weight-gradient MMA: a constant [1,0,...,0] block of 16 columns behind the H tile
         const int t = tid - 128;
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_f16_kernel(const __grid_
             const int kc_eff = min(KC, ktot - it * KC);
             const int k0 = k_begin + it * KC;
             if (mode == B200GYM_GEMM_WGRAD) {
-                load_tile(at, CH_ROWSKC, A, P.lda, k0, tile_m * TM, kc_eff, TM / 8, k_end, P.m, t);
+                load_tile(at, CH_ROWSKC, A, P.lda, k0, tile_m * TM, kc_eff, a_chunks, k_end, P.m, t);
                 load_tile(bt, CH_ROWSKC, B, P.ldb, k0, tile_n * BN, kc_eff, bn_eff / 8, k_end, P.n, t);
             } else {
                 load_tile(at, CH_ROWS128, A, P.lda, tile_m * TM, k0, TM, kc_eff / 8, P.m, P.k, t);
@@ -176,11 +187,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_f16_kernel(const __grid_
                 uint32_t r[16];
                 tc::ld16_issue(taddr + n0, r);
                 tc::ld16_wait(r);
-                float v[16];
+                float v[16], bv[16];
+                const int c0 = gcol0 + n0;
+                if (bias != nullptr && c0 + 16 <= P.n_real && (reinterpret_cast<uintptr_t>(bias + c0) & 15) == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
+                        bv[4 * q] = b4.x, bv[4 * q + 1] = b4.y, bv[4 * q + 2] = b4.z, bv[4 * q + 3] = b4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) bv[j] = (bias != nullptr && c0 + j < P.n_real) ? __ldg(bias + c0 + j) : 0.0f;
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int c = gcol0 + n0 + j;
-                    float x = __uint_as_float(r[j]) + ((bias != nullptr && c < P.n_real) ? __ldg(bias + c) : 0.0f);
+                    const float x = __uint_as_float(r[j]) + bv[j];
                     v[j] = elu ? tc::elu_fast(x) : x;
                 }
                 if (live) {

@@ -1,0 +1,415 @@
+// ppo_chain_kernel — forward, loss and input-gradient chain of one PPO minibatch for nets whose per-tile activations fit in
+// shared memory (the 48-128-64-32 flat nets; rsl_rl PPO.update: ActorCritic forward, surrogate / value / entropy loss,
+// loss.backward() down to the first layer's pre-activations).  One CTA owns (net, 128-row tile) and runs
+//     FWD layer 0 .. L-1  ->  loss on the last layer's TMEM rows  ->  DGRAD layer L-1 .. 1
+// back to back: every layer is a tcgen05.mma chain (kind::f16, fp32 accumulators in TMEM) whose A operand is the previous
+// epilogue's output, kept in shared memory in the chunk layout of tc.cuh; weights stream through a 2-stage cp.async ring and are
+// read K-major (forward) or MN-major (backward) from the same packed copy.  The loss separates per net — the actor CTA computes
+// the clipped surrogate / KL / entropy terms and d(loss)/d(mu), the critic CTA the clipped value loss and d(loss)/d(value) — so
+// no launch sits between forward and backward.  Activations H_l and gradients dZ_l also go to HBM (fp16): they are the operands
+// of the weight-gradient GEMM (gemm.cu, WGRAD), the only other contraction launch of the minibatch step.
+// Two CTAs per SM (108 KB of shared memory, 128 TMEM columns each): one CTA's epilogue overlaps the other's MMAs.
+#include "tc.cuh"
+#include "../../include/b200gym.h"
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int KC = 64;
+constexpr int WST = 2;                          // weight ring stages
+constexpr int CH128 = TM * 16 + 16;             // chunk stride of 128-row tiles (activations, K-major weight tiles)
+constexpr int CHKC = KC * 16 + 16;              // chunk stride of KC-row tiles (MN-major weight tiles)
+constexpr int W_STAGE = 16 * CHKC;              // 16640 >= 8 * CH128
+constexpr int CHAIN_THREADS = 288;
+constexpr uint32_t TMEM_COLS = 128;
+constexpr int MAXA = 16;
+static_assert(8 * CH128 <= W_STAGE, "weight stage too small");
+
+struct ChainArgs {
+    B200ChainNet net[2];
+    B200PpoLossParams lp;
+    const long long* idx;
+    const float *stdv, *actions, *old_logp, *adv, *ret, *old_v, *old_mu, *old_sigma;
+    float* d_std;
+    double* scalars;
+    int tiles;
+    int act_bytes[2];
+};
+
+__device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void load_tile(unsigned char* dst, int chunk_stride, const __half* base, long long ld, int row0, int col0, int nrows,
+                                          int nchunks, int row_lim, int col_lim, int t) {
+    const int pieces = nrows * nchunks;
+    for (int q = t; q < pieces; q += 128) {
+        const int r = q / nchunks, c = q - r * nchunks;
+        const int gr = row0 + r, gc = col0 + 8 * c;
+        const bool ok = gr < row_lim && gc < col_lim;
+        const __half* src = ok ? base + static_cast<long long>(gr) * ld + gc : base;
+        tc::cp_async16(dst + c * chunk_stride + r * 16, src, ok ? 16u : 0u);
+    }
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __grid_constant__ ChainArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int which = static_cast<int>(blockIdx.x) / a.tiles, tile = static_cast<int>(blockIdx.x) - which * a.tiles;
+    const B200ChainNet& net = a.net[which];
+    const int L = net.num_layers;
+    const int batch = a.lp.batch;
+
+    // shared memory: activation regions act[0..L-1] (act[l] = A operand of layer l), dz_last (2 chunks), weight ring, barriers
+    __shared__ int act_off[B200GYM_CHAIN_MAX_LAYERS + 1];   // act_off[MAX] = end of the regions = dz_last
+    if (tid == 0) {
+        int o = 0;
+        for (int l = 0; l < B200GYM_CHAIN_MAX_LAYERS; ++l) {
+            act_off[l] = o;
+            if (l < L) o += (net.kp[l] >> 3) * CH128;
+        }
+        act_off[B200GYM_CHAIN_MAX_LAYERS] = o;
+    }
+    __syncthreads();
+    unsigned char* dz_last = smem + act_off[B200GYM_CHAIN_MAX_LAYERS];
+    unsigned char* ring = dz_last + 2 * CH128;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + WST * W_STAGE);
+    uint64_t* empty = full + WST;
+    uint64_t* accum = empty + WST;
+    uint64_t* aready = accum + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + 1);
+    float* s_red = reinterpret_cast<float*>(tmem_slot + 2);   // [16] d_std partials, then 4 doubles
+    double* s_sc = reinterpret_cast<double*>(s_red + 16);
+
+    if (warp == 0) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (tid == 32) {
+        for (int s = 0; s < WST; ++s) {
+            mbar_init(full + s, 128);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(accum, 1);
+        mbar_init(aready, 128);
+        fence_mbar_init();
+    }
+    if (tid < 16) s_red[tid] = 0.0f;
+    if (tid >= 16 && tid < 20) s_sc[tid - 16] = 0.0;
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int nsteps = 2 * L - 1;   // L forward layers, then DGRAD of layers L-1 .. 1
+
+    if (warp == 8) {
+        // ------------------------------ MMA issue ------------------------------
+        int it = 0;
+        for (int step = 0; step < nsteps; ++step) {
+            const bool fwd = step < L;
+            const int l = fwd ? step : 2 * L - 1 - step;
+            const int ktot = fwd ? net.kp[l] : net.np[l];
+            const int n = fwd ? net.np[l] : net.kp[l];
+            const unsigned char* abase = smem + (fwd ? act_off[l] : (l == L - 1 ? act_off[B200GYM_CHAIN_MAX_LAYERS] : act_off[l + 1]));
+            const uint32_t idesc = tc::idesc_f16(n, false, !fwd);
+            tc::mbar_wait_spin(aready, step & 1);
+            tc::fence_after();
+            const int ns = (ktot + KC - 1) / KC;
+            for (int j = 0; j < ns; ++j, ++it) {
+                const int s = it % WST;
+                tc::mbar_wait_spin(full + s, (it / WST) & 1);
+                tc::fence_after();
+                if (tc::elect_one()) {
+                    const unsigned char* bt = ring + s * W_STAGE;
+                    uint64_t da = tc::smem_desc(abase + (8 * j) * CH128, CH128, 128);
+                    uint64_t db = fwd ? tc::smem_desc(bt, CH128, 128) : tc::smem_desc(bt, 128, CHKC);
+                    const uint32_t b_step = fwd ? ((2u * CH128) >> 4) : (256u >> 4);
+                    const int nk = min(KC, ktot - j * KC) >> 4;
+                    for (int q = 0; q < nk; ++q) {
+                        tc::mma_f16(tmem, da, db, idesc, (j | q) != 0 ? 1u : 0u);
+                        da += (2u * CH128) >> 4;
+                        db += b_step;
+                    }
+                    tc::commit(empty + s);
+                    if (j == ns - 1) tc::commit(accum);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------ loaders: the input tile, then the weight tiles of every step ------------------------------
+        const int t = tid - 128;
+        load_tile(smem + act_off[0], CH128, static_cast<const __half*>(net.x), net.ldx, tile * TM, 0, TM, net.kp[0] >> 3, batch, net.kp[0], t);
+        tc::cp_async_commit();
+        const __half* w16 = static_cast<const __half*>(net.w16);
+        int it = 0;
+        for (int step = 0; step < nsteps; ++step) {
+            const bool fwd = step < L;
+            const int l = fwd ? step : 2 * L - 1 - step;
+            const int ktot = fwd ? net.kp[l] : net.np[l];
+            const __half* W = w16 + net.w_off[l];   // row-major [np[l], kp[l]]
+            const int ns = (ktot + KC - 1) / KC;
+            for (int j = 0; j < ns; ++j, ++it) {
+                const int s = it % WST;
+                tc::mbar_wait_sleep(empty + s, ((it / WST) & 1) ^ 1);
+                unsigned char* bt = ring + s * W_STAGE;
+                const int kc_eff = min(KC, ktot - j * KC);
+                if (fwd) load_tile(bt, CH128, W, net.kp[l], 0, j * KC, net.np[l], kc_eff >> 3, net.np[l], net.kp[l], t);       // [n rows x k cols], K-major
+                else load_tile(bt, CHKC, W, net.kp[l], j * KC, 0, kc_eff, net.kp[l] >> 3, net.np[l], net.kp[l], t);            // [n rows = K x k cols = N], MN-major
+                tc::cp_async_commit();
+                tc::cp_async_wait<1>();   // everything before this stage has landed: publish it to the tensor-core proxy
+                fence_proxy_async();
+                if (it == 0) tc::mbar_arrive(aready);   // the input tile = step 0's A operand
+                else tc::mbar_arrive(full + (it - 1) % WST);
+            }
+        }
+        tc::cp_async_wait<0>();
+        fence_proxy_async();
+        tc::mbar_arrive(full + (it - 1) % WST);
+    } else {
+        // ------------------------------ epilogue warps: TMEM lane = tile row ------------------------------
+        const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        const int grow = tile * TM + tid;
+        const bool live = grow < batch;
+        const int A = a.lp.num_actions;
+        // per-sample storage columns of this row, fetched through the minibatch index while the first layers run
+        const long long srow = live ? (a.idx ? a.idx[grow] : grow) : 0;
+        float4 act4[3], omu4[3], osg4[3];
+        float s_adv = 0.f, s_logp = 0.f, s_ret = 0.f, s_oldv = 0.f;
+        if (which == 0) {
+            if (A == 12) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    act4[q] = __ldg(reinterpret_cast<const float4*>(a.actions + srow * 12) + q);
+                    omu4[q] = __ldg(reinterpret_cast<const float4*>(a.old_mu + srow * 12) + q);
+                    osg4[q] = __ldg(reinterpret_cast<const float4*>(a.old_sigma + srow * 12) + q);
+                }
+            }
+            s_adv = __ldg(a.adv + srow), s_logp = __ldg(a.old_logp + srow);
+        } else {
+            s_ret = __ldg(a.ret + srow), s_oldv = __ldg(a.old_v + srow);
+        }
+        for (int step = 0; step < nsteps; ++step) {
+            const bool fwd = step < L;
+            const int l = fwd ? step : 2 * L - 1 - step;
+            tc::mbar_wait_sleep(accum, step & 1);
+            tc::fence_after();
+            if (fwd && l < L - 1) {
+                // bias + ELU -> fp16: A operand of layer l+1 (shared memory) and H_l (HBM, operand of the weight-gradient GEMM)
+                const int n = net.np[l];
+                const float* bias = net.flat_param + net.b_off[l];
+                unsigned char* dst = smem + act_off[l + 1] + tid * 16;
+                __half* hg = static_cast<__half*>(net.h[l]) + static_cast<size_t>(grow) * n;
+                for (int n0 = 0; n0 < n; n0 += 16) {
+                    uint32_t r[16];
+                    tc::ld16_issue(taddr + n0, r);
+                    tc::ld16_wait(r);
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        v[j] = tc::elu_fast(__uint_as_float(r[j]) + (n0 + j < net.n_real[l] ? __ldg(bias + n0 + j) : 0.0f));
+                    const uint4 p0 = make_uint4(tc::pack_h2(v[0], v[1]), tc::pack_h2(v[2], v[3]), tc::pack_h2(v[4], v[5]), tc::pack_h2(v[6], v[7]));
+                    const uint4 p1 = make_uint4(tc::pack_h2(v[8], v[9]), tc::pack_h2(v[10], v[11]), tc::pack_h2(v[12], v[13]), tc::pack_h2(v[14], v[15]));
+                    *reinterpret_cast<uint4*>(dst + (n0 >> 3) * CH128) = p0;
+                    *reinterpret_cast<uint4*>(dst + ((n0 >> 3) + 1) * CH128) = p1;
+                    if (live) {
+                        reinterpret_cast<uint4*>(hg + n0)[0] = p0;
+                        reinterpret_cast<uint4*>(hg + n0)[1] = p1;
+                    }
+                }
+            } else if (fwd) {
+                // last layer: 16 output columns of this row -> loss terms and d(loss)/d(output), unscaled (1/batch lives in the WGRAD epilogue)
+                uint32_t r[16];
+                tc::ld16_issue(taddr, r);
+                tc::ld16_wait(r);
+                const float* bias = net.flat_param + net.b_off[l];
+                float o[16], dz[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    o[j] = __uint_as_float(r[j]) + (j < net.n_real[l] ? __ldg(bias + j) : 0.0f);
+                    dz[j] = 0.0f;
+                }
+                if (net.out != nullptr && live) {
+                    float4* op = reinterpret_cast<float4*>(net.out + static_cast<size_t>(grow) * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) op[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                }
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                float dstd[MAXA];
+#pragma unroll
+                for (int j = 0; j < MAXA; ++j) dstd[j] = 0.0f;
+                if (which == 0 && live) {
+                    const float LOG_SQRT_2PI = 0.91893853320467274178f;
+                    float logp = 0.0f, ent = 0.0f, kl = 0.0f, diff[MAXA];
+                    const float av[12] = {act4[0].x, act4[0].y, act4[0].z, act4[0].w, act4[1].x, act4[1].y, act4[1].z, act4[1].w, act4[2].x, act4[2].y, act4[2].z, act4[2].w};
+                    const float mv[12] = {omu4[0].x, omu4[0].y, omu4[0].z, omu4[0].w, omu4[1].x, omu4[1].y, omu4[1].z, omu4[1].w, omu4[2].x, omu4[2].y, omu4[2].z, omu4[2].w};
+                    const float gv[12] = {osg4[0].x, osg4[0].y, osg4[0].z, osg4[0].w, osg4[1].x, osg4[1].y, osg4[1].z, osg4[1].w, osg4[2].x, osg4[2].y, osg4[2].z, osg4[2].w};
+#pragma unroll
+                    for (int j = 0; j < MAXA; ++j) {
+                        diff[j] = 0.0f;
+                        if (j < A) {
+                            const float sg = __ldg(a.stdv + j), m = o[j];
+                            const float x = A == 12 ? av[j < 12 ? j : 0] : __ldg(a.actions + srow * A + j);
+                            const float om = A == 12 ? mv[j < 12 ? j : 0] : __ldg(a.old_mu + srow * A + j);
+                            const float os = A == 12 ? gv[j < 12 ? j : 0] : __ldg(a.old_sigma + srow * A + j);
+                            const float ls = logf(sg);
+                            diff[j] = x - m;
+                            logp += -(diff[j] * diff[j]) / (2.0f * sg * sg) - ls - LOG_SQRT_2PI;
+                            ent += 0.5f + LOG_SQRT_2PI + ls;
+                            const float dm = om - m;
+                            kl += logf(sg / os + 1.e-5f) + (os * os + dm * dm) / (2.0f * sg * sg) - 0.5f;
+                        }
+                    }
+                    const float ratio = expf(logp - s_logp);
+                    const float lo = 1.0f - a.lp.clip_param, hi = 1.0f + a.lp.clip_param;
+                    const float s1 = -s_adv * ratio, s2 = -s_adv * fminf(fmaxf(ratio, lo), hi);
+                    const bool inside = ratio >= lo && ratio <= hi;
+                    const float g_ratio = s1 > s2 ? -s_adv : (s1 == s2 ? (inside ? -s_adv : -0.5f * s_adv) : 0.0f);   // torch.max splits ties
+                    const float dlogp = g_ratio * ratio;
+#pragma unroll
+                    for (int j = 0; j < MAXA; ++j) {
+                        if (j < A) {
+                            const float sg = __ldg(a.stdv + j), inv2 = 1.0f / (sg * sg);
+                            dz[j] = dlogp * diff[j] * inv2;
+                            dstd[j] = (dlogp * (diff[j] * diff[j] * inv2 / sg - 1.0f / sg) - a.lp.entropy_coef / sg) * a.lp.inv_global_batch;
+                        }
+                    }
+                    acc[0] = kl, acc[1] = fmaxf(s1, s2), acc[3] = ent;
+                } else if (which == 1 && live) {
+                    const float v = o[0], R = s_ret;
+                    float vloss, dv;
+                    if (a.lp.use_clipped_value_loss) {
+                        const float dvo = v - s_oldv;
+                        const float vc = s_oldv + fminf(fmaxf(dvo, -a.lp.clip_param), a.lp.clip_param);
+                        const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+                        const bool pass = dvo >= -a.lp.clip_param && dvo <= a.lp.clip_param;
+                        vloss = fmaxf(l1, l2);
+                        const float g1 = 2.0f * (v - R), g2 = pass ? 2.0f * (vc - R) : 0.0f;
+                        dv = l1 > l2 ? g1 : (l1 == l2 ? 0.5f * (g1 + g2) : g2);
+                    } else {
+                        vloss = (R - v) * (R - v);
+                        dv = 2.0f * (v - R);
+                    }
+                    dz[0] = a.lp.value_loss_coef * dv;
+                    acc[2] = vloss;
+                }
+                const uint4 p0 = make_uint4(tc::pack_h2(dz[0], dz[1]), tc::pack_h2(dz[2], dz[3]), tc::pack_h2(dz[4], dz[5]), tc::pack_h2(dz[6], dz[7]));
+                const uint4 p1 = make_uint4(tc::pack_h2(dz[8], dz[9]), tc::pack_h2(dz[10], dz[11]), tc::pack_h2(dz[12], dz[13]), tc::pack_h2(dz[14], dz[15]));
+                *reinterpret_cast<uint4*>(dz_last + tid * 16) = p0;
+                *reinterpret_cast<uint4*>(dz_last + CH128 + tid * 16) = p1;
+                if (live) {
+                    uint4* zg = reinterpret_cast<uint4*>(static_cast<__half*>(net.dz[l]) + static_cast<size_t>(grow) * 16);
+                    zg[0] = p0, zg[1] = p1;
+                }
+                // CTA-level sums: warp shuffles, shared-memory atomics, one global atomic per value per CTA
+                const int lane = tid & 31;
+                if (which == 0) {
+#pragma unroll
+                    for (int j = 0; j < MAXA; ++j) {
+                        if (j < A) {
+                            float x = dstd[j];
+#pragma unroll
+                            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                            if (lane == 0) atomicAdd(s_red + j, x);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double x = acc[k];
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                    if (lane == 0 && x != 0.0) atomicAdd(s_sc + k, x);
+                }
+                bar_epilogue();
+                if (tid < 4 && s_sc[tid] != 0.0) atomicAdd(a.scalars + tid, s_sc[tid]);
+                if (which == 0 && tid >= 32 && tid < 32 + A) atomicAdd(a.d_std + tid - 32, s_red[tid - 32]);
+            } else {
+                // DGRAD of layer l: dZ_{l-1} = (dZ_l . W_l) * ELU'(H_{l-1}); H_{l-1} sits in act[l] and is overwritten in place by dZ_{l-1}
+                const int n = net.kp[l];
+                unsigned char* hs = smem + act_off[l] + tid * 16;
+                __half* zg = static_cast<__half*>(net.dz[l - 1]) + static_cast<size_t>(grow) * n;
+                for (int n0 = 0; n0 < n; n0 += 16) {
+                    uint32_t r[16];
+                    tc::ld16_issue(taddr + n0, r);
+                    const uint4 h0 = *reinterpret_cast<const uint4*>(hs + (n0 >> 3) * CH128), h1 = *reinterpret_cast<const uint4*>(hs + ((n0 >> 3) + 1) * CH128);
+                    tc::ld16_wait(r);
+                    const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                    uint32_t o[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float2 h = tc::unpack_h2(hw[q]);
+                        const float d0 = h.x > 0.0f ? 1.0f : h.x + 1.0f, d1 = h.y > 0.0f ? 1.0f : h.y + 1.0f;
+                        o[q] = tc::pack_h2(__uint_as_float(r[2 * q]) * d0, __uint_as_float(r[2 * q + 1]) * d1);
+                    }
+                    const uint4 p0 = make_uint4(o[0], o[1], o[2], o[3]), p1 = make_uint4(o[4], o[5], o[6], o[7]);
+                    *reinterpret_cast<uint4*>(hs + (n0 >> 3) * CH128) = p0;
+                    *reinterpret_cast<uint4*>(hs + ((n0 >> 3) + 1) * CH128) = p1;
+                    if (live) {
+                        reinterpret_cast<uint4*>(zg + n0)[0] = p0;
+                        reinterpret_cast<uint4*>(zg + n0)[1] = p1;
+                    }
+                }
+            }
+            // this thread's part of the next A operand is written and its accumulator reads are done
+            fence_proxy_async();
+            tc::fence_before();
+            if (step + 1 < nsteps) tc::mbar_arrive(aready);
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc::fence_after();
+        tc::tmem_dealloc<TMEM_COLS>(tmem);
+    }
+}
+
+size_t chain_smem(const B200ChainNet& n) {
+    size_t chunks = 2;
+    for (int l = 0; l < n.num_layers; ++l) chunks += static_cast<size_t>(n.kp[l] >> 3);
+    return chunks * CH128 + static_cast<size_t>(WST) * W_STAGE + 256;
+}
+
+}  // namespace
+
+extern "C" int b200gym_ppo_chain(const B200ChainNet* actor, const B200ChainNet* critic, const B200PpoLossParams* lp, const int64_t* idx,
+                                 const float* std, const float* actions, const float* old_log_prob, const float* advantages,
+                                 const float* returns, const float* old_values, const float* old_mu, const float* old_sigma, float* d_std,
+                                 double* scalars, void* stream) {
+    B200_REQUIRE(actor && critic && lp && std && actions && old_log_prob && advantages && returns && old_values && old_mu && old_sigma &&
+                     d_std && scalars,
+                 B200GYM_EINVAL, "ppo_chain: null argument");
+    B200_REQUIRE(lp->batch > 0 && lp->num_actions > 0 && lp->num_actions <= MAXA, B200GYM_EINVAL, "ppo_chain: batch > 0, 1..%d actions", MAXA);
+    ChainArgs a;
+    size_t smem = 0;
+    const B200ChainNet* nets[2] = {actor, critic};
+    for (int w = 0; w < 2; ++w) {
+        const B200ChainNet& n = *nets[w];
+        B200_REQUIRE(n.num_layers >= 2 && n.num_layers <= B200GYM_CHAIN_MAX_LAYERS, B200GYM_EINVAL, "ppo_chain: 2..%d layers", B200GYM_CHAIN_MAX_LAYERS);
+        B200_REQUIRE(n.x && n.w16 && n.flat_param && b200_aligned16(n.x) && b200_aligned16(n.w16) && n.ldx % 8 == 0 && n.ldx >= n.kp[0], B200GYM_EALIGN,
+                     "ppo_chain: x / w16 must be 16-byte aligned, ldx %% 8 == 0");
+        for (int l = 0; l < n.num_layers; ++l) {
+            B200_REQUIRE(n.kp[l] % 16 == 0 && n.np[l] % 16 == 0 && n.np[l] >= 16 && n.np[l] <= 128 && n.kp[l] >= 16 && n.n_real[l] <= n.np[l],
+                         B200GYM_EINVAL, "ppo_chain: layer %d is %d -> %d; widths must be multiples of 16, outputs <= 128", l, n.kp[l], n.np[l]);
+            B200_REQUIRE(l == 0 || (n.kp[l] == n.np[l - 1] && n.kp[l] <= 128), B200GYM_EINVAL, "ppo_chain: layer %d input %d != previous output %d", l, n.kp[l],
+                         n.np[l - 1]);
+            B200_REQUIRE(n.w_off[l] % 8 == 0 && n.dz[l] && b200_aligned16(n.dz[l]) && (l == n.num_layers - 1 || (n.h[l] && b200_aligned16(n.h[l]))),
+                         B200GYM_EALIGN, "ppo_chain: layer %d buffers missing or misaligned", l);
+        }
+        B200_REQUIRE(n.np[n.num_layers - 1] == 16, B200GYM_EINVAL, "ppo_chain: the last layer must be padded to 16 outputs");
+        a.net[w] = n;
+        const size_t s = chain_smem(n);
+        smem = s > smem ? s : smem;
+    }
+    B200_REQUIRE(smem <= 227 * 1024, B200GYM_EINVAL, "ppo_chain: %zu B of shared memory needed per CTA: use the layered GEMM path for this net", smem);
+    a.lp = *lp;
+    a.idx = reinterpret_cast<const long long*>(idx);
+    a.stdv = std, a.actions = actions, a.old_logp = old_log_prob, a.adv = advantages, a.ret = returns, a.old_v = old_values;
+    a.old_mu = old_mu, a.old_sigma = old_sigma, a.d_std = d_std, a.scalars = scalars;
+    a.tiles = (lp->batch + TM - 1) / TM;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(ppo_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "ppo_chain: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+        configured = smem;
+    }
+    ppo_chain_kernel<<<2 * a.tiles, CHAIN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    B200_LAUNCH_CHECK("ppo_chain");
+    return B200GYM_OK;
+}

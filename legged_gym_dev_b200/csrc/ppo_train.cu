@@ -163,6 +163,102 @@ __global__ void __launch_bounds__(256) pack_params_f16_kernel(const float* __res
     dst[o] = __float2half_rn(w);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// ppo_optimizer_step_kernel — everything of a PPO minibatch step that follows the backward pass, in ONE launch:
+//   clip_grad_norm_ (squared norm over the flat gradient buffer) -> KL-adaptive learning rate -> Adam -> fp16 operand
+//   copies of the updated weights -> gradient buffer and per-minibatch loss sums cleared for the next minibatch.
+// (rsl_rl PPO.update: the `if self.desired_kl ...` schedule, nn.utils.clip_grad_norm_, optimizer.step(); replaces
+// adam_prepare + grad_sumsq + adaptive_lr + clip_adam_dev + pack_params_f16 + four torch fill / copy launches.)
+// The grid is at most one CTA per SM, so all CTAs are co-resident and a device-wide barrier between the norm and the
+// update is safe: ws[0] = squared norm, counters (arrive, depart) behind it; the last CTA to leave resets them.
+// ------------------------------------------------------------------------------------------------------------------
+struct OptWs {
+    double sumsq;
+    unsigned int arrive, depart;
+};
+
+__global__ void __launch_bounds__(512) ppo_optimizer_step_kernel(const __grid_constant__ B200OptParams p, float* __restrict__ param,
+                                                                 float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+                                                                 float* __restrict__ lr, int* __restrict__ step, double* __restrict__ mb,
+                                                                 double* __restrict__ totals, OptWs* __restrict__ ws,
+                                                                 const __grid_constant__ B200PackTable tab, __half* __restrict__ w16) {
+    __shared__ double sh[16];
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- phase 1: squared gradient norm ----
+    double acc = 0.0;
+    for (long long i = i0; i < p.n; i += stride) {
+        const double g = grad[i];
+        acc += g * g;
+    }
+    acc = warp_sum_d(acc);
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
+        atomicAdd(&ws->sumsq, t);
+        __threadfence();
+        atomicAdd(&ws->arrive, 1u);
+        while (atomicAdd(&ws->arrive, 0u) < gridDim.x) __nanosleep(32);   // all CTAs are resident (grid <= SM count)
+        __threadfence();
+    }
+    __syncthreads();
+    // ---- phase 2: schedule, clip, Adam, fp16 copies ----
+    const double sumsq = *reinterpret_cast<volatile double*>(&ws->sumsq);
+    float l = *lr;
+    if (p.adaptive) {   // ppo.py: adaptive schedule on the KL of THIS minibatch, before the optimiser step
+        const float kl_mean = static_cast<float>(mb[0] / p.count);
+        if (kl_mean > p.desired_kl * 2.0f) l = fmaxf(1e-5f, l / 1.5f);
+        else if (kl_mean < p.desired_kl / 2.0f && kl_mean > 0.0f) l = fminf(1e-2f, l * 1.5f);
+    }
+    const float st = static_cast<float>(*step + 1);
+    const float bc1 = 1.0f - powf(p.beta1, st), bc2_sqrt = sqrtf(1.0f - powf(p.beta2, st));
+    const float total = static_cast<float>(sqrt(sumsq));
+    const float coef = fminf(p.max_grad_norm / (total + 1e-6f), 1.0f);   // clip_grad_norm_
+    const float step_size = l / bc1;
+    for (long long i = i0; i < p.n; i += stride) {
+        const float gi = grad[i] * coef;
+        const float mi = p.beta1 * m[i] + (1.0f - p.beta1) * gi;
+        const float vi = p.beta2 * v[i] + (1.0f - p.beta2) * gi * gi;
+        m[i] = mi, v[i] = vi;
+        const float w = param[i] - step_size * mi / (sqrtf(vi) / bc2_sqrt + p.eps);
+        param[i] = w;
+        grad[i] = 0.0f;
+        for (int e = 0; e < tab.n; ++e) {
+            const B200PackEntry& t = tab.e[e];
+            const long long local = i - t.src_off;
+            if (local >= 0 && local < static_cast<long long>(t.rows) * t.cols) {
+                const unsigned r = static_cast<unsigned>(local) / static_cast<unsigned>(t.cols), k = static_cast<unsigned>(local) - r * static_cast<unsigned>(t.cols);
+                const long long o = t.layout == 0 ? t.dst_off + static_cast<long long>(r) * t.ld + k
+                                                  : t.dst_off + (static_cast<long long>(k >> 3) * t.ld + r) * 8 + (k & 7);
+                w16[o] = __float2half_rn(w);
+                break;
+            }
+        }
+    }
+    for (long long i = p.n + i0; i < p.n + 8; i += stride) grad[i] = 0.0f;   // spare tail of the flat buffer
+    // ---- leave: the last CTA publishes the scalars and resets the workspace ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ws->depart, 1u) == gridDim.x - 1) {
+            *lr = l;
+            *step += 1;
+            for (int k = 0; k < 4; ++k) {
+                totals[k] += mb[k];
+                mb[k] = 0.0;
+            }
+            totals[4] = sumsq;   // last gradient norm^2 (FlatAdam.grad_norm)
+            ws->sumsq = 0.0;
+            ws->arrive = 0u;
+            ws->depart = 0u;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -202,6 +298,27 @@ int b200gym_pack_params_f16(const float* flat, const B200PackTable* table, void*
     pack_params_f16_kernel<<<static_cast<unsigned>((table->total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         flat, *table, static_cast<__half*>(dst));
     B200_LAUNCH_CHECK("pack_params_f16");
+    return B200GYM_OK;
+}
+
+int b200gym_ppo_optimizer_step(const B200OptParams* p, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* lr,
+                               int32_t* step_dev, double* mb_scalars, double* totals, void* workspace, const B200PackTable* table, void* w16,
+                               void* stream) {
+    B200_REQUIRE(p && param && grad && exp_avg && exp_avg_sq && lr && step_dev && mb_scalars && totals && workspace && table && w16,
+                 B200GYM_EINVAL, "ppo_optimizer_step: null argument");
+    B200_REQUIRE(p->n > 0 && p->count > 0 && table->n >= 0 && table->n <= B200GYM_PACK_MAX, B200GYM_EINVAL, "ppo_optimizer_step: bad argument");
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // small nets (the 34 K-parameter flat nets): ONE CTA, no device-wide barrier on the critical path; otherwise ~8 parameters per thread
+    long long grid = p->n <= 65536 ? 1 : (p->n + 512 * 8 - 1) / (512 * 8);
+    grid = grid < 1 ? 1 : (grid > sms ? sms : grid);     // never more CTAs than SMs: the device-wide barrier needs co-residency
+    ppo_optimizer_step_kernel<<<static_cast<unsigned>(grid), 512, 0, static_cast<cudaStream_t>(stream)>>>(
+        *p, param, grad, exp_avg, exp_avg_sq, lr, step_dev, mb_scalars, totals, static_cast<OptWs*>(workspace), *table, static_cast<__half*>(w16));
+    B200_LAUNCH_CHECK("ppo_optimizer_step");
     return B200GYM_OK;
 }
 

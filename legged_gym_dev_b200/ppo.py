@@ -284,7 +284,8 @@ class PPO:
         self.value_loss_coef, self.entropy_coef, self.gamma, self.lam = value_loss_coef, entropy_coef, gamma, lam
         self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
         self.lib = _lib.lib()
-        self._scalars = torch.zeros(8, dtype=torch.double, device=self.device)
+        # [0:4] sums over the update {kl, surrogate, value loss, entropy}, [4] last squared gradient norm, [8:12] sums of the current minibatch
+        self._scalars = torch.zeros(16, dtype=torch.double, device=self.device)
         self._sumsq = torch.zeros(1, dtype=torch.double, device=self.device)
         self._klsum = torch.zeros(2, dtype=torch.double, device=self.device)
         self._mb_cache = {}
@@ -346,8 +347,15 @@ class PPO:
         lp.num_actions, lp.use_clipped_value_loss = ac.std.numel(), int(self.use_clipped_value_loss)
         lp.clip_param, lp.value_loss_coef, lp.entropy_coef = self.clip_param, self.value_loss_coef, self.entropy_coef
         lp.batch, lp.inv_global_batch = B, 1.0 / (B * world)
+        sc = self._scalars[8:12]
+        if world == 1:
+            # single GPU: the gradient buffer and `sc` were cleared by the previous optimiser launch (or by update())
+            ac._trainer.minibatch_forward_backward(self.storage, idx, lp, ac.std, C.c_void_p(ac.flat_grad.data_ptr() + 4 * std_off), sc,
+                                                   self.storage.privileged_observations is None)
+            self.optimizer.fused_step(self.max_grad_norm, sc, self._scalars, float(B),
+                                      self.desired_kl if (self.desired_kl is not None and self.schedule == "adaptive") else None)
+            return
         ac.flat_grad.zero_()
-        sc = self._scalars[4:8]
         sc.zero_()
         ac._trainer.minibatch_forward_backward(self.storage, idx, lp, ac.std, C.c_void_p(ac.flat_grad.data_ptr() + 4 * std_off), sc,
                                                self.storage.privileged_observations is None)
@@ -357,12 +365,12 @@ class PPO:
         tail[0:1].copy_(sc[0:1])
         tail[1:2].fill_(float(B))
         grad = None
-        if world > 1 and self._peer is not None:
+        if self._peer is not None:
             # ONE kernel over peer-mapped memory: rank-ordered sum of all ranks' buffers + squared norm (graph-capturable)
             self.optimizer.prepare()
             grad = self._peer.reduce(ac.num_flat, self.optimizer._sumsq)
             tail = grad[ac.num_flat:ac.num_flat + 2]
-        elif world > 1:
+        else:
             import torch.distributed as dist
             dist.all_reduce(ac.flat_grad)
         if self.desired_kl is not None and self.schedule == "adaptive":
@@ -398,6 +406,7 @@ class PPO:
             plan = [perm[i * B:(i + 1) * B] for _ in range(self.num_learning_epochs) for i in range(self.num_mini_batches)]
         mb = self._static_minibatch(B)
         self._scalars.zero_()
+        ac.flat_grad.zero_()
         # Across ranks the minibatch body runs eagerly: it is GPU-bound either way (graph replay and eager launch measure the
         # same), and keeping the NCCL all-reduce out of stream capture avoids depending on capture support in the process group.
         use_graph = self.use_graph and (world == 1 or self._peer is not None) and all(p.numel() == B for p in plan)
@@ -423,7 +432,8 @@ class PPO:
     def _capture(self, mb, world):
         """Warm-up on a side stream (buffer allocation, kernel attributes), restore the optimiser state, then capture."""
         ac, opt = self.actor_critic, self.optimizer
-        keep = [t.clone() for t in (ac.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.lr, opt.step_dev, self._scalars)]
+        state = (ac.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.lr, opt.step_dev, self._scalars, ac.flat_grad)
+        keep = [t.clone() for t in state]
         steps = opt.steps
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -434,7 +444,7 @@ class PPO:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._minibatch_step(mb, world)
-        for t, k in zip((ac.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.lr, opt.step_dev, self._scalars), keep):
+        for t, k in zip(state, keep):
             t.copy_(k)
         opt.steps = steps
         ac._trainer.pack()
@@ -453,6 +463,8 @@ class FlatAdam:
         self.steps = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._sumsq = torch.zeros(1, dtype=torch.double, device=dev)
+        self._ws = torch.zeros(2, dtype=torch.double, device=dev)   # fused_step workspace: squared norm + the two barrier counters
+        self._last_sumsq = None
         self.lib = _lib.lib()
 
     def prepare(self):
@@ -474,8 +486,23 @@ class FlatAdam:
                                                   ac.num_flat, 1.0, ptr(self._sumsq), max_grad_norm, ptr(self.lr), self.betas[0],
                                                   self.betas[1], self.eps, ptr(self.step_dev), st), "clip_adam_dev")
 
+    def fused_step(self, max_grad_norm, mb_scalars, totals, count, desired_kl):
+        """Single-GPU minibatch tail in ONE launch (csrc/ppo_train.cu ppo_optimizer_step_kernel): squared gradient norm, KL-adaptive
+        learning rate, clip + Adam, fp16 operand copies of the new weights, gradient buffer and minibatch sums cleared."""
+        ac, ptr = self.ac, _lib.ptr
+        self.steps += 1
+        p = _lib.OptParamsPOD()
+        p.n, p.count, p.adaptive = ac.num_flat, count, int(desired_kl is not None)
+        p.desired_kl, p.max_grad_norm = (desired_kl or 0.0), max_grad_norm
+        p.beta1, p.beta2, p.eps = self.betas[0], self.betas[1], self.eps
+        tr = ac._trainer
+        _lib.check(self.lib.b200gym_ppo_optimizer_step(p, ptr(ac.flat_param), ptr(ac.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                                       ptr(self.lr), ptr(self.step_dev), ptr(mb_scalars), ptr(totals), ptr(self._ws),
+                                                       tr._tab, ptr(tr.w16), _lib.stream_ptr(ac.flat_param.device)), "ppo_optimizer_step")
+        self._last_sumsq = totals[4:5]
+
     def grad_norm(self):
-        return torch.sqrt(self._sumsq[0])
+        return torch.sqrt(self._last_sumsq[0] if self._last_sumsq is not None else self._sumsq[0])
 
     def state_dict(self):
         return dict(lr=self.lr.clone(), exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(), steps=self.steps)

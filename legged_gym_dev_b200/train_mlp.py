@@ -13,6 +13,7 @@ The same FWD launches serve the no-grad rollout / inference forward of nets that
 fused kernel (the 512-256-128 rough nets).
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -74,6 +75,11 @@ class TensorCoreTrainer:
         tab.n, tab.total = e, end
         self._tab = tab
         self._bufs = {}
+        # nets whose 128-row activation tiles fit in shared memory run forward + loss + input gradients as ONE launch (csrc/ppo_chain.cu)
+        def chain_fits(net):
+            smem = (2 + sum(k // 8 for k in net.Kp)) * (128 * 16 + 16) + 2 * 16 * (64 * 16 + 16) + 256
+            return 2 <= net.L <= _lib.CHAIN_MAX_LAYERS and max(net.Np) <= 128 and max(net.Kp[1:]) <= 128 and smem <= 227 * 1024
+        self.use_chain = all(chain_fits(n) for n in self.nets) and os.environ.get("B200GYM_PPO_CHAIN", "1") != "0"
         self.pack()
 
     # ------------------------------------------------------------------------------------------------------------
@@ -100,6 +106,8 @@ class TensorCoreTrainer:
         b["fwd"] = self._fwd_launches(b, B)
         if train:
             b["dgrad"] = self._dgrad_launches(b, B)
+            if self.use_chain:
+                b["chain"] = [self._chain_net(b, i) for i in range(2)]
         if len(self._bufs) > 8:
             self._bufs.clear()
         self._bufs[key] = b
@@ -131,6 +139,17 @@ class TensorCoreTrainer:
             ps = [per_net[i][l] for i, net in enumerate(self.nets) if l < net.L]
             launches.append(((_lib.GemmProblemPOD * len(ps))(*ps), len(ps)))
         return launches
+
+    def _chain_net(self, b, i):
+        net, c = self.nets[i], _lib.ChainNetPOD()
+        c.x, c.w16, c.flat_param, c.out = b["x"][i].data_ptr(), self.w16.data_ptr(), self.ac.flat_param.data_ptr(), b["out"][i].data_ptr()
+        c.num_layers, c.ldx = net.L, b["x"][i].stride(0)
+        for l in range(net.L):
+            c.kp[l], c.np[l], c.n_real[l], c.w_off[l], c.b_off[l] = net.Kp[l], net.Np[l], net.N[l], net.w16_off[l], net.b_off[l]
+            c.dz[l] = b["dz"][i][l].data_ptr()
+            if l < net.L - 1:
+                c.h[l] = b["h"][i][l].data_ptr()
+        return c
 
     def _dgrad_launches(self, b, B):
         launches = []
@@ -201,12 +220,18 @@ class TensorCoreTrainer:
         self._convert(obs, idx, b["x"][0], B)
         if not shared_obs:
             self._convert(flat(storage.privileged_observations), idx, b["x"][1], B)
-        self._run(b["fwd"])
-        _lib.check(self.lib.b200gym_ppo_loss_gathered(
-            lp, ptr(idx), ptr(b["out"][0]), 16, ptr(b["out"][1]), 16, ptr(std), ptr(storage.actions), ptr(storage.actions_log_prob),
-            ptr(storage.advantages), ptr(storage.returns), ptr(storage.values), ptr(storage.mu), ptr(storage.sigma),
-            ptr(b["dz"][0][-1]), ptr(b["dz"][1][-1]), d_std_ptr, ptr(scalars), st), "ppo_loss_gathered")
-        self._run(b["dgrad"])
+        if self.use_chain:
+            _lib.check(self.lib.b200gym_ppo_chain(
+                b["chain"][0], b["chain"][1], lp, ptr(idx), ptr(std), ptr(storage.actions), ptr(storage.actions_log_prob),
+                ptr(storage.advantages), ptr(storage.returns), ptr(storage.values), ptr(storage.mu), ptr(storage.sigma), d_std_ptr,
+                ptr(scalars), st), "ppo_chain")
+        else:
+            self._run(b["fwd"])
+            _lib.check(self.lib.b200gym_ppo_loss_gathered(
+                lp, ptr(idx), ptr(b["out"][0]), 16, ptr(b["out"][1]), 16, ptr(std), ptr(storage.actions), ptr(storage.actions_log_prob),
+                ptr(storage.advantages), ptr(storage.returns), ptr(storage.values), ptr(storage.mu), ptr(storage.sigma),
+                ptr(b["dz"][0][-1]), ptr(b["dz"][1][-1]), d_std_ptr, ptr(scalars), st), "ppo_loss_gathered")
+            self._run(b["dgrad"])
         key = ("wgrad", lp.inv_global_batch)
         if key not in b:
             b[key] = self._wgrad_launches(b, B, lp.inv_global_batch)

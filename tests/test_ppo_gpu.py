@@ -182,8 +182,10 @@ def test_ppo_update_rough_nets():
     _check_update(*_update_pair(235, (512, 256, 128), 24, 256, epochs=1))
 
 
-@pytest.mark.parametrize("num_obs,hidden,B", [(48, (128, 64, 32), 6144), (235, (512, 256, 128), 3000), (48, (128, 64, 32), 100)])
-def test_minibatch_gradients_match_autograd(num_obs, hidden, B):
+@pytest.mark.parametrize("num_obs,hidden,B,chain", [(48, (128, 64, 32), 6144, True), (48, (128, 64, 32), 6144, False),
+                                                     (235, (512, 256, 128), 3000, False), (48, (128, 64, 32), 100, True),
+                                                     (235, (128, 64), 1000, True), (40, (64, 128, 32, 32), 777, True)])
+def test_minibatch_gradients_match_autograd(num_obs, hidden, B, chain):
     """flat_grad after one forward/backward of the tcgen05 path vs torch autograd (fp32) of the restated loss on the same
     minibatch: gradient norm to 1e-3 relative, gradient vector to 5e-3 of its norm (fp16 operands, fp32 accumulation)."""
     from legged_gym_dev_b200 import _lib
@@ -196,6 +198,8 @@ def test_minibatch_gradients_match_autograd(num_obs, hidden, B):
             p.add_(0.03 * torch.randn_like(p))
     ac = alg.actor_critic
     ac.load_state_dict(copy.deepcopy(ref.state_dict()))
+    assert ac._trainer.use_chain or not chain      # flat-sized nets take the one-launch chain kernel by default
+    ac._trainer.use_chain = chain                  # chain=False: the layered GEMM path (what the rough nets use)
     idx = torch.randperm(T * N, generator=torch.Generator().manual_seed(4))[:B]
     batch = {k: v[idx] for k, v in store.items()}
     loss, info = O.ppo_loss(ref, batch, clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.01, use_clipped_value_loss=True)

@@ -58,7 +58,10 @@ def run(num_obs, hidden, N=4096, T=24, reps=5, profile=True):
 
 if __name__ == "__main__":
     res = []
+    prof = "--no-profile" not in sys.argv
+    reps = 1 if "--once" in sys.argv else 5
     if "--rough-only" not in sys.argv:
-        res.append(run(48, (128, 64, 32)))
-    res.append(run(235, (512, 256, 128)))
+        res.append(run(48, (128, 64, 32), profile=prof, reps=reps))
+    if "--flat-only" not in sys.argv:
+        res.append(run(235, (512, 256, 128), profile=prof, reps=reps))
     print(json.dumps(res, indent=1))
