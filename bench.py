@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python API instead of CUDA-graph replays of tape cycles")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 4096..1M envs sweep (extra key, not the headline)")
     ap.add_argument("--no-extra", action="store_true", help="skip the timings of configs 1, 3, 4, 5 (extra key)")
+    ap.add_argument("--no-multi", action="store_true", help="skip the sharded configs 4 / 2 (1M envs total) / 5 (multi_gpu key, every N)")
     return ap.parse_args()
 
 
@@ -321,12 +322,20 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        del env
+        env = tape = graphed = None
         torch.cuda.empty_cache()
         esteps = max(5, min(args.steps, 30 if N <= 262144 else 12))
         dt, h2d, d2h = e2e_run(N, 2 if N > 262144 else min(args.frames, 4), esteps, 3, device, rank, world)
         e2e = {"value": world * N * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": esteps, "note": "LeggedRobot.step through the C ABI with pinned-host physics frames + actions in, obs/rew/reset out"}
+
+    multi = None
+    if not args.no_multi:   # every rank: the sharded configurations of BASELINE.json (strong scaling), N = 1 included
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_multigpu
+        env = tape = graphed = None
+        torch.cuda.empty_cache()
+        multi = bench_multigpu.run_all(rank, world, device)
 
     sweep = None
     extra = None
@@ -383,6 +392,8 @@ def main():
             line["sweep"] = sweep
         if extra:
             line["extra_configs"] = extra
+        if multi:
+            line["multi_gpu"] = multi
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -496,6 +496,41 @@ int b200gym_ppo_optimizer_step(const B200OptParams* p, float* param, float* grad
                                int32_t* step_dev, double* mb_scalars, double* totals, void* workspace, const B200PackTable* table, void* w16,
                                void* stream);
 
+/* The data-parallel form of b200gym_ppo_optimizer_step (replaces rsl_rl-style DDP: NCCL all-reduce of the
+ * gradients + clip_grad_norm_ + Adam.step): ONE launch per rank exchanges the flat gradient buffers over NVLink peer memory
+ * (push into every rank's symmetric buffer, flag signalling, no host / torch barrier), sums them in rank order (bit-identical on
+ * every rank), and performs the step.  peers->base[r] = rank r's mapping of its symmetric buffer of 2 * world * n_pad floats
+ * (slots [parity][source rank][n_pad]) followed by world uint32 flags, all zero-initialised before the first call;
+ * n_pad = multiple of 4 in [n + 2, n + 8]; grad: this rank's LOCAL flat gradients (n + 8 floats, cleared on exit);
+ * grad_sum: n_pad floats of scratch that receive the summed gradients (+ {sum kl, count} at [n], [n + 1]); the KL mean of the
+ * adaptive schedule is the GLOBAL one.  workspace: B200GYM_PEER_WS_BYTES zero-initialised bytes owned by the call sequence
+ * (holds the exchange number: every rank must make the same sequence of calls).  ctas: 0 = pick from n.  A rank that waits
+ * more than 4 s for a peer sets workspace word 4 (error) instead of hanging. */
+#define B200GYM_OPT_MAX_CTAS 160
+#define B200GYM_PEER_WS_BYTES (32 + 8 * B200GYM_OPT_MAX_CTAS)
+typedef struct B200PeerBases {
+    float* base[B200GYM_MAX_PEERS];
+} B200PeerBases;
+int b200gym_ppo_optimizer_step_peers(const B200OptParams* p, const B200PeerBases* peers, int32_t world, int32_t rank, int64_t n_pad, float* param,
+                                     float* grad, float* grad_sum, float* exp_avg, float* exp_avg_sq, float* lr, int32_t* step_dev,
+                                     double* mb_scalars, double* totals, void* workspace, const B200PackTable* table, void* w16, int32_t ctas,
+                                     void* stream);
+
+/* Everything of rsl_rl PPO.act after the actor / critic forward, in ONE launch (rsl_rl/algorithms/ppo.py act(): Normal(mu, std)
+ * .sample(), get_actions_log_prob, and the transition fields; rsl_rl/storage/rollout_storage.py add_transitions' copies): the
+ * action sample (Philox4x32-10, site POLICY_SAMPLE, counter = (env_id_offset + env, event); Box-Muller, specification
+ * oracle/port_ppo.py sample_actions), its summed log-prob, and observations / critic observations / actions / values / log-prob /
+ * mu / sigma written to the storage ROW pointers st_* (row `step` of the [T, N, .] tensors).  mu_out [n_envs, ld_mu] and
+ * value_out [n_envs, ld_value] are the MLP outputs; st_critic_obs may be NULL (no privileged observations). */
+int b200gym_ppo_act_store(int32_t n_envs, int32_t num_actions, int32_t num_obs, int32_t num_critic_obs, const float* mu_out, int32_t ld_mu,
+                          const float* value_out, int32_t ld_value, const float* std, const float* obs, int64_t ld_obs, const float* critic_obs,
+                          int64_t ld_critic_obs, uint64_t seed, uint64_t event, uint64_t env_id_offset, float* st_obs, float* st_critic_obs,
+                          float* st_actions, float* st_values, float* st_log_prob, float* st_mu, float* st_sigma, void* stream);
+/* PPO.process_env_step -> add_transitions: rewards / dones / time-out flags (byte tensors; time_outs may be NULL = none) of one env
+ * step into the storage row pointers. */
+int b200gym_ppo_store_step(int32_t n_envs, const float* rewards, const uint8_t* dones, const uint8_t* time_outs, float* st_rewards,
+                           uint8_t* st_dones, uint8_t* st_time_outs, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Tube-dataset construction from the rollout logs (deep_tube_learning/datasets.py:60-71,
  * deep_tube_learning/evaluation/evaluate_tube_simple.py:28-46) — SURVEY.md §8f row 2

@@ -163,6 +163,14 @@ class PeerPtrsPOD(C.Structure):
     _fields_ = [("ptr", vp * 16)]
 
 
+class PeerBasesPOD(C.Structure):
+    _fields_ = [("base", vp * 16)]
+
+
+OPT_MAX_CTAS = 160
+PEER_WS_BYTES = 32 + 8 * OPT_MAX_CTAS
+
+
 _lib = None
 
 
@@ -248,9 +256,16 @@ def lib():
     L.b200gym_ppo_chain.restype = C.c_int
     L.b200gym_ppo_optimizer_step.argtypes = [C.POINTER(OptParamsPOD)] + [vp] * 9 + [C.POINTER(PackTablePOD), vp, vp]
     L.b200gym_ppo_optimizer_step.restype = C.c_int
+    L.b200gym_ppo_optimizer_step_peers.argtypes = ([C.POINTER(OptParamsPOD), C.POINTER(PeerBasesPOD), C.c_int32, C.c_int32, C.c_int64] + [vp] * 10
+                                                   + [C.POINTER(PackTablePOD), vp, C.c_int32, vp])
+    L.b200gym_ppo_optimizer_step_peers.restype = C.c_int
+    u64 = C.c_uint64
+    L.b200gym_ppo_act_store.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, C.c_int64, vp, C.c_int64, u64, u64, u64] + [vp] * 8
+    L.b200gym_ppo_store_step.argtypes = [i32] + [vp] * 7
+    L.b200gym_ppo_act_store.restype = L.b200gym_ppo_store_step.restype = C.c_int
     L.b200gym_rows_to_f16.restype = L.b200gym_ppo_loss_gathered.restype = L.b200gym_pack_params_f16.restype = C.c_int
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
-                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD), ("B200GemmProblem", GemmProblemPOD), ("B200PackTable", PackTablePOD), ("B200ChainNet", ChainNetPOD), ("B200OptParams", OptParamsPOD),
+                      ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD), ("B200PeerBases", PeerBasesPOD), ("B200GemmProblem", GemmProblemPOD), ("B200PackTable", PackTablePOD), ("B200ChainNet", ChainNetPOD), ("B200OptParams", OptParamsPOD),
                       ("B200RomFamilyParams", RomFamilyParamsPOD), ("B200HopperTorqueParams", HopperTorqueParamsPOD),
                       ("B200HopperTorqueBuffers", HopperTorqueBuffersPOD), ("B200HopperObsParams", HopperObsParamsPOD)):
         n = L.b200gym_sizeof(name.encode())

@@ -31,6 +31,7 @@ int b200gym_sizeof(const char* name) {
     if (!strcmp(name, "B200HopperTorqueBuffers")) return (int)sizeof(B200HopperTorqueBuffers);
     if (!strcmp(name, "B200HopperObsParams")) return (int)sizeof(B200HopperObsParams);
     if (!strcmp(name, "B200PeerPtrs")) return (int)sizeof(B200PeerPtrs);
+    if (!strcmp(name, "B200PeerBases")) return (int)sizeof(B200PeerBases);
     if (!strcmp(name, "B200GemmProblem")) return (int)sizeof(B200GemmProblem);
     if (!strcmp(name, "B200PackTable")) return (int)sizeof(B200PackTable);
     if (!strcmp(name, "B200ChainNet")) return (int)sizeof(B200ChainNet);

@@ -13,7 +13,9 @@ enum Site : uint32_t {
     ROM_SIN_MAG = 23, ROM_SIN_MEAN = 24, ROM_SIN_FREQ = 25, ROM_SIN_OFF = 26, ROM_TFINAL = 27, ROM_WEIGHTS = 28,
     ROM_STATIONARY = 29,
     // HopperTrajectory reset / push (oracle/philox.py; reserved, no kernel draws from them yet)
-    HOP_DOF_POS = 32, HOP_DOF_VEL = 33, HOP_ROOT_POS = 34, HOP_YAW = 35, HOP_ROOT_VEL = 36, HOP_PUSH = 37
+    HOP_DOF_POS = 32, HOP_DOF_VEL = 33, HOP_ROOT_POS = 34, HOP_YAW = 35, HOP_ROOT_VEL = 36, HOP_PUSH = 37,
+    // PPO.act: Normal(mu, std).sample(), event = the runner's act counter (csrc/ppo_rollout.cu)
+    POLICY_SAMPLE = 48
 };
 
 __device__ __forceinline__ uint4 block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {

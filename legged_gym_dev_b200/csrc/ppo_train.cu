@@ -9,6 +9,7 @@
 //                             weight-gradient epilogue, so fp16 never sees 1e-5-sized values
 //   pack_params_f16_kernel    fp32 master weights (one flat buffer) -> the fp16 operand copies, all layers in one launch
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/b200gym.h"
 
@@ -164,6 +165,50 @@ __global__ void __launch_bounds__(256) pack_params_f16_kernel(const float* __res
 }
 
 
+// clip + Adam + fp16 operand copies over the flat buffers, elements i0, i0 + stride, ...; the loads of four elements are issued
+// together (one CTA of the 34 K-parameter nets walks 66 elements per thread: a serial load -> store chain would cost ~1 us each).
+// g_src: summed gradients (read through L2: another CTA may have written them); g_clear: buffer to zero behind the read, or null.
+__device__ __forceinline__ void adam_pack_pass(const B200OptParams& p, const B200PackTable& tab, long long i0, long long stride,
+                                               const float* __restrict__ g_src, float* __restrict__ g_clear, float coef, float step_size,
+                                               float bc2_sqrt, float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
+                                               __half* __restrict__ w16) {
+    constexpr int U = 4;
+    for (long long base = i0; base < p.n; base += U * stride) {
+        float g[U], mm[U], vv[U], w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + u * stride;
+            const bool ok = i < p.n;
+            g[u] = ok ? __ldcg(g_src + i) : 0.0f;
+            mm[u] = ok ? m[i] : 0.0f;
+            vv[u] = ok ? v[i] : 0.0f;
+            w[u] = ok ? param[i] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + u * stride;
+            if (i >= p.n) break;
+            const float gi = g[u] * coef;
+            const float mi = p.beta1 * mm[u] + (1.0f - p.beta1) * gi;
+            const float vi = p.beta2 * vv[u] + (1.0f - p.beta2) * gi * gi;
+            m[i] = mi, v[i] = vi;
+            const float wn = w[u] - step_size * mi / (sqrtf(vi) / bc2_sqrt + p.eps);
+            param[i] = wn;
+            if (g_clear) g_clear[i] = 0.0f;
+            int e = 0;
+            while (e < tab.n && !(i >= tab.e[e].src_off && i - tab.e[e].src_off < static_cast<long long>(tab.e[e].rows) * tab.e[e].cols)) ++e;
+            if (e < tab.n) {
+                const B200PackEntry& t = tab.e[e];
+                const unsigned local = static_cast<unsigned>(i - t.src_off);
+                const unsigned r = local / static_cast<unsigned>(t.cols), k = local - r * static_cast<unsigned>(t.cols);
+                const long long o = t.layout == 0 ? t.dst_off + static_cast<long long>(r) * t.ld + k
+                                                  : t.dst_off + (static_cast<long long>(k >> 3) * t.ld + r) * 8 + (k & 7);
+                w16[o] = __float2half_rn(wn);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // ppo_optimizer_step_kernel — everything of a PPO minibatch step that follows the backward pass, in ONE launch:
 //   clip_grad_norm_ (squared norm over the flat gradient buffer) -> KL-adaptive learning rate -> Adam -> fp16 operand
@@ -189,6 +234,7 @@ __global__ void __launch_bounds__(512) ppo_optimizer_step_kernel(const __grid_co
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // ---- phase 1: squared gradient norm ----
     double acc = 0.0;
+#pragma unroll 4
     for (long long i = i0; i < p.n; i += stride) {
         const double g = grad[i];
         acc += g * g;
@@ -219,26 +265,7 @@ __global__ void __launch_bounds__(512) ppo_optimizer_step_kernel(const __grid_co
     const float total = static_cast<float>(sqrt(sumsq));
     const float coef = fminf(p.max_grad_norm / (total + 1e-6f), 1.0f);   // clip_grad_norm_
     const float step_size = l / bc1;
-    for (long long i = i0; i < p.n; i += stride) {
-        const float gi = grad[i] * coef;
-        const float mi = p.beta1 * m[i] + (1.0f - p.beta1) * gi;
-        const float vi = p.beta2 * v[i] + (1.0f - p.beta2) * gi * gi;
-        m[i] = mi, v[i] = vi;
-        const float w = param[i] - step_size * mi / (sqrtf(vi) / bc2_sqrt + p.eps);
-        param[i] = w;
-        grad[i] = 0.0f;
-        for (int e = 0; e < tab.n; ++e) {
-            const B200PackEntry& t = tab.e[e];
-            const long long local = i - t.src_off;
-            if (local >= 0 && local < static_cast<long long>(t.rows) * t.cols) {
-                const unsigned r = static_cast<unsigned>(local) / static_cast<unsigned>(t.cols), k = static_cast<unsigned>(local) - r * static_cast<unsigned>(t.cols);
-                const long long o = t.layout == 0 ? t.dst_off + static_cast<long long>(r) * t.ld + k
-                                                  : t.dst_off + (static_cast<long long>(k >> 3) * t.ld + r) * 8 + (k & 7);
-                w16[o] = __float2half_rn(w);
-                break;
-            }
-        }
-    }
+    adam_pack_pass(p, tab, i0, stride, grad, grad, coef, step_size, bc2_sqrt, param, m, v, w16);
     for (long long i = p.n + i0; i < p.n + 8; i += stride) grad[i] = 0.0f;   // spare tail of the flat buffer
     // ---- leave: the last CTA publishes the scalars and resets the workspace ----
     __syncthreads();
@@ -255,6 +282,161 @@ __global__ void __launch_bounds__(512) ppo_optimizer_step_kernel(const __grid_co
             ws->sumsq = 0.0;
             ws->arrive = 0u;
             ws->depart = 0u;
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// ppo_optimizer_step_peers_kernel — the data-parallel form of the launch above ("NCCL gradient allreduce"):
+// gradient exchange over NVLink peer memory + rank-ordered sum + clip + KL schedule + Adam + fp16 copies in ONE launch per
+// rank, with no host-side or torch barrier.
+//   A  push   every rank stores its local gradients (+ {sum kl, count} in the tail) into slot [parity][rank] of EVERY rank's
+//             symmetric buffer (posted NVLink writes), clears its local gradient buffer, then publishes the exchange number in
+//             flags[rank] of every rank with a system-scope release store
+//   B  wait   acquire-poll the LOCAL flags until every rank has published this exchange (bounded: a dead peer sets ws->error)
+//   C  sum    slots [parity][0..world) summed in rank order -> bit-identical totals on all ranks; per-CTA partial squared
+//             norms combined in CTA order after a device-wide barrier (deterministic: identical clip factor everywhere)
+//   D  step   as the single-GPU kernel
+// Slots are double-buffered by the parity of the exchange number: a rank can only overwrite parity q two exchanges later, i.e.
+// after it has seen the flag of the exchange in between, which its owner publishes after finishing its reads of q.
+// ------------------------------------------------------------------------------------------------------------------
+struct PeerWs {
+    unsigned int arrive, arrive2, depart, epoch, error, pad[3];
+    double partial[B200GYM_OPT_MAX_CTAS];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(512) ppo_optimizer_step_peers_kernel(const __grid_constant__ B200OptParams p, const __grid_constant__ B200PeerBases peers,
+                                                                       int world, int rank, long long n_pad, float* __restrict__ param,
+                                                                       float* __restrict__ grad, float* __restrict__ gsum, float* __restrict__ m,
+                                                                       float* __restrict__ v, float* __restrict__ lr, int* __restrict__ step,
+                                                                       double* __restrict__ mb, double* __restrict__ totals, PeerWs* __restrict__ ws,
+                                                                       const __grid_constant__ B200PackTable tab, __half* __restrict__ w16) {
+    __shared__ double sh[17];
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(&ws->epoch) + 1u;   // rewritten only after every CTA has passed barrier C
+    const long long slot0 = static_cast<long long>(epoch & 1u) * world * n_pad;
+    const long long n4 = n_pad >> 2;
+    // ---- A: push ----
+    for (long long i = i0; i < n4; i += stride) {
+        float4 g = reinterpret_cast<const float4*>(grad)[i];
+        const long long e = i << 2;
+        if (e + 3 >= p.n) {   // the float4 that holds the piggy-backed tail: [n] = sum kl of this minibatch, [n + 1] = its sample count
+            float t[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (e + j == p.n) t[j] = static_cast<float>(mb[0]);
+                else if (e + j == p.n + 1) t[j] = static_cast<float>(p.count);
+                else if (e + j > p.n + 1) t[j] = 0.0f;
+            }
+            g = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.base[r] + slot0 + static_cast<long long>(rank) * n_pad)[i] = g;
+        reinterpret_cast<float4*>(grad)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    for (long long i = n_pad + i0; i < p.n + 8; i += stride) grad[i] = 0.0f;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&ws->arrive, 1u);
+        if (blockIdx.x == 0) {
+            while (atomicAdd(&ws->arrive, 0u) < gridDim.x) __nanosleep(32);   // all CTAs are resident (grid <= SM count)
+            __threadfence_system();
+        }
+    }
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        if (threadIdx.x < world)
+            st_release_sys(reinterpret_cast<unsigned int*>(peers.base[threadIdx.x] + 2ll * world * n_pad) + rank, epoch);
+    }
+    // ---- B: wait for every rank's publication of this exchange ----
+    if (threadIdx.x < world) {
+        const unsigned int* flag = reinterpret_cast<const unsigned int*>(peers.base[rank] + 2ll * world * n_pad) + threadIdx.x;
+        const unsigned long long t0 = globaltimer_ns();
+        while (static_cast<int>(ld_acquire_sys(flag) - epoch) < 0) {
+            __nanosleep(64);
+            if (globaltimer_ns() - t0 > 4000000000ull) {   // 4 s: a peer never arrived; flag it instead of hanging the device
+                ws->error = 1u;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- C: rank-ordered sum + squared norm ----
+    const float* mine = peers.base[rank] + slot0;
+    double acc = 0.0;
+    for (long long i = i0; i < n4; i += stride) {
+        float4 s = __ldcg(reinterpret_cast<const float4*>(mine) + i);
+        for (int r = 1; r < world; ++r) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(mine + static_cast<long long>(r) * n_pad) + i);
+            s.x = __fadd_rn(s.x, a.x), s.y = __fadd_rn(s.y, a.y), s.z = __fadd_rn(s.z, a.z), s.w = __fadd_rn(s.w, a.w);
+        }
+        reinterpret_cast<float4*>(gsum)[i] = s;
+        const long long e = i << 2;
+        const float t[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (e + j < p.n) acc += static_cast<double>(t[j]) * t[j];
+    }
+    acc = warp_sum_d(acc);
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
+        ws->partial[blockIdx.x] = t;
+        __threadfence();
+        atomicAdd(&ws->arrive2, 1u);
+        while (atomicAdd(&ws->arrive2, 0u) < gridDim.x) __nanosleep(32);
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned int c = 0; c < gridDim.x; ++c) tot += __ldcg(&ws->partial[c]);   // CTA order: the same total on every rank
+        sh[16] = tot;
+    }
+    __syncthreads();
+    // ---- D: schedule, clip, Adam, fp16 copies ----
+    const double sumsq = sh[16];
+    float l = *lr;
+    if (p.adaptive) {   // KL mean over the GLOBAL minibatch (all ranks), from the summed tail
+        const float kl_mean = __ldcg(gsum + p.n) / __ldcg(gsum + p.n + 1);
+        if (kl_mean > p.desired_kl * 2.0f) l = fmaxf(1e-5f, l / 1.5f);
+        else if (kl_mean < p.desired_kl / 2.0f && kl_mean > 0.0f) l = fminf(1e-2f, l * 1.5f);
+    }
+    const float st = static_cast<float>(*step + 1);
+    const float bc1 = 1.0f - powf(p.beta1, st), bc2_sqrt = sqrtf(1.0f - powf(p.beta2, st));
+    const float total = static_cast<float>(sqrt(sumsq));
+    const float coef = fminf(p.max_grad_norm / (total + 1e-6f), 1.0f);
+    const float step_size = l / bc1;
+    adam_pack_pass(p, tab, i0, stride, gsum, nullptr, coef, step_size, bc2_sqrt, param, m, v, w16);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ws->depart, 1u) == gridDim.x - 1) {
+            *lr = l;
+            *step += 1;
+            for (int k = 0; k < 4; ++k) {
+                totals[k] += mb[k];
+                mb[k] = 0.0;
+            }
+            totals[4] = sumsq;
+            ws->arrive = 0u;
+            ws->arrive2 = 0u;
+            ws->depart = 0u;
+            ws->epoch = epoch;
         }
     }
 }
@@ -313,12 +495,40 @@ int b200gym_ppo_optimizer_step(const B200OptParams* p, float* param, float* grad
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    // small nets (the 34 K-parameter flat nets): ONE CTA, no device-wide barrier on the critical path; otherwise ~8 parameters per thread
-    long long grid = p->n <= 65536 ? 1 : (p->n + 512 * 8 - 1) / (512 * 8);
+    // ~4 parameters per thread (one batch of adam_pack_pass); B200GYM_OPT_CTAS overrides (A/B)
+    static const int forced = getenv("B200GYM_OPT_CTAS") ? atoi(getenv("B200GYM_OPT_CTAS")) : 0;
+    long long grid = forced > 0 ? forced : (p->n + 512 * 4 - 1) / (512 * 4);
     grid = grid < 1 ? 1 : (grid > sms ? sms : grid);     // never more CTAs than SMs: the device-wide barrier needs co-residency
     ppo_optimizer_step_kernel<<<static_cast<unsigned>(grid), 512, 0, static_cast<cudaStream_t>(stream)>>>(
         *p, param, grad, exp_avg, exp_avg_sq, lr, step_dev, mb_scalars, totals, static_cast<OptWs*>(workspace), *table, static_cast<__half*>(w16));
     B200_LAUNCH_CHECK("ppo_optimizer_step");
+    return B200GYM_OK;
+}
+
+int b200gym_ppo_optimizer_step_peers(const B200OptParams* p, const B200PeerBases* peers, int32_t world, int32_t rank, int64_t n_pad, float* param,
+                                     float* grad, float* grad_sum, float* exp_avg, float* exp_avg_sq, float* lr, int32_t* step_dev,
+                                     double* mb_scalars, double* totals, void* workspace, const B200PackTable* table, void* w16, int32_t ctas,
+                                     void* stream) {
+    B200_REQUIRE(p && peers && param && grad && grad_sum && exp_avg && exp_avg_sq && lr && step_dev && mb_scalars && totals && workspace && table && w16,
+                 B200GYM_EINVAL, "ppo_optimizer_step_peers: null argument");
+    B200_REQUIRE(p->n > 0 && p->count > 0 && table->n >= 0 && table->n <= B200GYM_PACK_MAX, B200GYM_EINVAL, "ppo_optimizer_step_peers: bad argument");
+    B200_REQUIRE(world >= 1 && world <= B200GYM_MAX_PEERS && rank >= 0 && rank < world, B200GYM_EINVAL,
+                 "ppo_optimizer_step_peers: 1..%d ranks, 0 <= rank < world (got %d of %d)", B200GYM_MAX_PEERS, rank, world);
+    B200_REQUIRE(n_pad % 4 == 0 && n_pad >= p->n + 2 && n_pad <= p->n + 8, B200GYM_EINVAL,
+                 "ppo_optimizer_step_peers: n_pad must be a multiple of 4 in [n + 2, n + 8]");
+    for (int r = 0; r < world; ++r)
+        B200_REQUIRE(peers->base[r] != nullptr && b200_aligned16(peers->base[r]), B200GYM_EALIGN, "ppo_optimizer_step_peers: peer %d has no 16-byte aligned buffer", r);
+    B200_REQUIRE(b200_aligned16(grad) && b200_aligned16(grad_sum), B200GYM_EALIGN, "ppo_optimizer_step_peers: grad / grad_sum must be 16-byte aligned");
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = ctas > 0 ? ctas : (p->n + 512 * 4 - 1) / (512 * 4);
+    const long long cap = sms < B200GYM_OPT_MAX_CTAS ? sms : B200GYM_OPT_MAX_CTAS;
+    grid = grid < 1 ? 1 : (grid > cap ? cap : grid);   // co-residency of the device-wide barriers
+    ppo_optimizer_step_peers_kernel<<<static_cast<unsigned>(grid), 512, 0, static_cast<cudaStream_t>(stream)>>>(
+        *p, *peers, world, rank, n_pad, param, grad, grad_sum, exp_avg, exp_avg_sq, lr, step_dev, mb_scalars, totals,
+        static_cast<PeerWs*>(workspace), *table, static_cast<__half*>(w16));
+    B200_LAUNCH_CHECK("ppo_optimizer_step_peers");
     return B200GYM_OK;
 }
 

@@ -267,17 +267,22 @@ class PPO:
         if self.actor_critic.flat_param is None or self.actor_critic.flat_param.device != self.device:
             self.actor_critic.flatten_parameters()
         self.storage = None
-        # multi-GPU: gradients in peer-mapped memory, summed by our own kernel over NVLink (peer_reduce.py); B200GYM_P2P_GRADS=0 or a
-        # failed rendezvous falls back to the NCCL all-reduce of the same flat buffer
-        self._peer = None
-        if _dist_ready() and os.environ.get("B200GYM_P2P_GRADS", "1") != "0":
-            try:
+        # multi-GPU gradient exchange (B200GYM_GRAD_EXCHANGE): "fused" (default) = push + flags + rank-ordered sum inside the optimiser
+        # kernel (peer_reduce.PeerExchange); "peer" = round-1 barrier / reduce kernel / barrier; "nccl" = all-reduce of the flat buffer.
+        # The last two are A/B baselines selected explicitly — nothing falls back on its own: a failed rendezvous raises.
+        self._peer = self._xchg = None
+        self.exchange = "none"
+        if _dist_ready():
+            self.exchange = os.environ.get("B200GYM_GRAD_EXCHANGE", "nccl" if os.environ.get("B200GYM_P2P_GRADS") == "0" else "fused")
+            if self.exchange == "fused":
+                from .peer_reduce import PeerExchange
+                self._xchg = PeerExchange(self.actor_critic.num_flat, self.device)
+            elif self.exchange == "peer":
                 from .peer_reduce import PeerGradReducer
                 self._peer = PeerGradReducer(self.actor_critic.num_flat + 8, self.device)
                 self.actor_critic.flatten_parameters(grad_buffer=self._peer.buf)
-            except Exception as e:   # noqa: BLE001 — symmetric memory needs NVLink/P2P between the ranks
-                print(f"[b200gym] peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
-                self._peer = None
+            elif self.exchange != "nccl":
+                raise ValueError(f"B200GYM_GRAD_EXCHANGE={self.exchange!r}: expected fused, peer or nccl")
         self.optimizer = FlatAdam(self.actor_critic, lr=learning_rate)
         self.transition = RolloutStorage.Transition()
         self.clip_param, self.num_learning_epochs, self.num_mini_batches = clip_param, num_learning_epochs, num_mini_batches
@@ -289,6 +294,8 @@ class PPO:
         self._sumsq = torch.zeros(1, dtype=torch.double, device=self.device)
         self._klsum = torch.zeros(2, dtype=torch.double, device=self.device)
         self._mb_cache = {}
+        # PPO.act's sample: Philox stream keyed by (seed, global env id, act counter); torch.manual_seed controls it like rsl_rl's sampling
+        self.seed, self.env_id_offset, self._act_event = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, 0, 0
         self.use_graph = os.environ.get("B200GYM_PPO_GRAPH", "1") != "0"
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
@@ -301,33 +308,45 @@ class PPO:
         self.actor_critic.train()
 
     def act(self, obs, critic_obs):
-        tr, ac = self.transition, self.actor_critic
-        tr.actions = ac.act(obs).detach()
-        tr.values = ac.evaluate(critic_obs).detach()
-        tr.actions_log_prob = ac.get_actions_log_prob(tr.actions).detach()
-        tr.action_mean, tr.action_sigma = ac.action_mean.detach(), ac.action_std.detach()
-        # rsl_rl keeps references because its env returns a fresh obs tensor every step (legged_robot.py:211); the fused env
-        # rewrites ONE persistent obs_buf in place, so the transition must hold the observation the action was computed from
-        s = self.storage.step if self.storage is not None else None
-        if s is not None and s < self.storage.num_transitions_per_env:
-            self.storage.observations[s].copy_(obs)
-            tr.observations = self.storage.observations[s]
-            if self.storage.privileged_observations is not None:
-                self.storage.privileged_observations[s].copy_(critic_obs)
-                tr.critic_observations = self.storage.privileged_observations[s]
-            else:
-                tr.critic_observations = tr.observations
-        else:
-            tr.observations, tr.critic_observations = obs.clone(), critic_obs.clone()
+        """rsl_rl PPO.act: two MLP forwards (tcgen05) + ONE launch for Normal(mu, std).sample(), its log-prob and the transition
+        written straight into row `storage.step` (csrc/ppo_rollout.cu).  rsl_rl keeps references to obs in the transition because
+        its env returns a fresh tensor every step (legged_robot.py:211); the fused env rewrites ONE persistent obs_buf in place, so
+        the observations are stored here, at act time.  The transition fields are views of the storage row."""
+        tr, ac, st = self.transition, self.actor_critic, self.storage
+        if st is None:
+            raise RuntimeError("PPO.act: call init_storage() first (the transition is written straight into the rollout storage)")
+        if st.step >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        s, ptr = st.step, _lib.ptr
+        mu, val = ac._forward(0, obs), ac._forward(1, critic_obs)
+        self._act_event += 1
+        priv = st.privileged_observations
+        _lib.check(self.lib.b200gym_ppo_act_store(
+            obs.shape[0], ac.std.numel(), obs.shape[1], critic_obs.shape[1], ptr(mu), mu.stride(0), ptr(val), val.stride(0), ptr(ac.std),
+            ptr(obs), obs.stride(0), ptr(critic_obs), critic_obs.stride(0), self.seed, self._act_event, int(self.env_id_offset),
+            ptr(st.observations[s]), ptr(priv[s]) if priv is not None else None, ptr(st.actions[s]), ptr(st.values[s]),
+            ptr(st.actions_log_prob[s]), ptr(st.mu[s]), ptr(st.sigma[s]), _lib.stream_ptr(self.device)), "ppo_act_store")
+        tr.observations = st.observations[s]
+        tr.critic_observations = priv[s] if priv is not None else tr.observations
+        tr.actions, tr.values, tr.actions_log_prob = st.actions[s], st.values[s], st.actions_log_prob[s, :, 0]
+        tr.action_mean, tr.action_sigma = st.mu[s], st.sigma[s]
         return tr.actions
 
     def process_env_step(self, rewards, dones, infos):
-        """The time-out bootstrap (rewards += gamma * values * time_outs) is deferred into the GAE kernel: the storage keeps
-        the raw reward plus the time-out flag, and compute_returns applies it in place before the scan."""
-        tr = self.transition
-        tr.rewards, tr.dones = rewards.clone(), dones
-        tr.time_outs = infos["time_outs"] if "time_outs" in infos else None
-        self.storage.add_transitions(tr)
+        """rsl_rl PPO.process_env_step + RolloutStorage.add_transitions for the fields the env step produced: ONE launch.  The
+        time-out bootstrap (rewards += gamma * values * time_outs) is deferred into the GAE kernel: the storage keeps the raw reward
+        plus the time-out flag, and compute_returns applies it in place before the scan."""
+        tr, st = self.transition, self.storage
+        if st.step >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        s, ptr = st.step, _lib.ptr
+        to = infos["time_outs"] if "time_outs" in infos else None
+        as_u8 = lambda t: t.view(torch.uint8) if t.dtype == torch.bool else (t if t.dtype == torch.uint8 else (t != 0).view(torch.uint8))
+        rewards = rewards if (rewards.dtype == torch.float32 and rewards.is_contiguous()) else rewards.float().contiguous()
+        _lib.check(self.lib.b200gym_ppo_store_step(rewards.numel(), ptr(rewards), ptr(as_u8(dones).contiguous()),
+                                                   ptr(as_u8(to).contiguous()) if to is not None else None, ptr(st.rewards[s]),
+                                                   ptr(st.dones[s]), ptr(st.time_outs[s]), _lib.stream_ptr(self.device)), "ppo_store_step")
+        st.step += 1
         tr.clear()
         self.actor_critic.reset(dones)
 
@@ -335,12 +354,11 @@ class PPO:
         last_values = self.actor_critic.evaluate(last_critic_obs).detach()
         self.storage.compute_returns(last_values, self.gamma, self.lam)
 
-    def _minibatch_step(self, mb, world):
-        """One minibatch of PPO.update for the row indices in the static tensor mb["idx"]: observation gather + forward (tcgen05
+    def _minibatch_step(self, idx, world):
+        """One minibatch of PPO.update for the row indices in the static tensor `idx`: observation gather + forward (tcgen05
         GEMMs), fused loss + gradient w.r.t. the network outputs, input- and weight-gradient GEMMs, gradient exchange,
         KL-adaptive LR, clip + Adam, fp16 weight refresh.  No host synchronisation: capturable in a CUDA graph."""
         ac, ptr, st = self.actor_critic, _lib.ptr, _lib.stream_ptr(self.device)
-        idx = mb["idx"]
         B = idx.numel()
         std_off, _ = ac._slices["std"]
         lp = _lib.PpoLossParamsPOD()
@@ -348,12 +366,13 @@ class PPO:
         lp.clip_param, lp.value_loss_coef, lp.entropy_coef = self.clip_param, self.value_loss_coef, self.entropy_coef
         lp.batch, lp.inv_global_batch = B, 1.0 / (B * world)
         sc = self._scalars[8:12]
-        if world == 1:
-            # single GPU: the gradient buffer and `sc` were cleared by the previous optimiser launch (or by update())
+        adaptive_kl = self.desired_kl if (self.desired_kl is not None and self.schedule == "adaptive") else None
+        if world == 1 or self._xchg is not None:
+            # the gradient buffer and `sc` were cleared by the previous optimiser launch (or by update()); across ranks the same ONE
+            # launch also carries the exchange (push over NVLink, flags, rank-ordered sum): csrc/ppo_train.cu
             ac._trainer.minibatch_forward_backward(self.storage, idx, lp, ac.std, C.c_void_p(ac.flat_grad.data_ptr() + 4 * std_off), sc,
                                                    self.storage.privileged_observations is None)
-            self.optimizer.fused_step(self.max_grad_norm, sc, self._scalars, float(B),
-                                      self.desired_kl if (self.desired_kl is not None and self.schedule == "adaptive") else None)
+            self.optimizer.fused_step(self.max_grad_norm, sc, self._scalars, float(B), adaptive_kl, xchg=self._xchg)
             return
         ac.flat_grad.zero_()
         sc.zero_()
@@ -366,34 +385,35 @@ class PPO:
         tail[1:2].fill_(float(B))
         grad = None
         if self._peer is not None:
-            # ONE kernel over peer-mapped memory: rank-ordered sum of all ranks' buffers + squared norm (graph-capturable)
+            # round-1 form: barrier, ONE reduce kernel over peer-mapped memory (rank-ordered sum + squared norm), barrier
             self.optimizer.prepare()
             grad = self._peer.reduce(ac.num_flat, self.optimizer._sumsq)
             tail = grad[ac.num_flat:ac.num_flat + 2]
         else:
             import torch.distributed as dist
             dist.all_reduce(ac.flat_grad)
-        if self.desired_kl is not None and self.schedule == "adaptive":
+        if adaptive_kl is not None:
             self._klsum.copy_(tail)
             _lib.check(self.lib.b200gym_adaptive_lr(ptr(self._klsum), float(B * world), self.desired_kl, ptr(self.optimizer.lr), st),
                        "adaptive_lr")
         self.optimizer.step(self.max_grad_norm, grad=grad)
         ac._trainer.pack()
 
-    def _static_minibatch(self, B):
-        """Static index tensor of one minibatch + the captured CUDA graph of `_minibatch_step` on it."""
-        key = (B, self.storage.observations.data_ptr())
-        mb = self._mb_cache.get(key)
-        if mb is not None:
-            return mb
-        mb = dict(idx=torch.zeros(B, dtype=torch.int64, device=self.device), graph=None)
-        self._mb_cache = {key: mb}
-        return mb
+    def _static_plan(self, B, n_mb, n_epochs):
+        """Static permutation buffer of one update + the captured CUDA graph of ALL its minibatch steps."""
+        key = (B, n_mb, n_epochs, self.storage.observations.data_ptr())
+        sp = self._mb_cache.get(key)
+        if sp is None:
+            sp = dict(perm=torch.zeros(n_mb * B, dtype=torch.int64, device=self.device), graph=None)
+            sp["slices"] = [sp["perm"][i * B:(i + 1) * B] for _ in range(n_epochs) for i in range(n_mb)]
+            self._mb_cache = {key: sp}
+        return sp
 
     def update(self, plan=None):
-        """rsl_rl PPO.update.  The body of one minibatch (gather -> forward -> loss -> backward -> gradient exchange -> Adam
-        -> weight repack) is captured ONCE as a CUDA graph and replayed for every minibatch of every epoch; only the row
-        indices change (copied into a static index tensor).  B200GYM_PPO_GRAPH=0 runs the same body eagerly."""
+        """rsl_rl PPO.update.  The bodies of ALL minibatches of the update (gather -> forward -> loss -> backward -> gradient
+        exchange -> Adam -> weight repack, epochs x minibatches times) are captured ONCE as a CUDA graph over a static permutation
+        buffer and replayed with one launch per update; only the permutation changes (copied into the static buffer).  A `plan`
+        (explicit list of index tensors: tests) or B200GYM_PPO_GRAPH=0 runs the same bodies eagerly."""
         ac = self.actor_critic
         world = 1
         if _dist_ready():
@@ -401,35 +421,40 @@ class PPO:
             world = dist.get_world_size()
         T, N = self.storage.num_transitions_per_env, self.storage.num_envs
         B = T * N // self.num_mini_batches
-        if plan is None:
-            perm = torch.randperm(self.num_mini_batches * B, device=self.device)
-            plan = [perm[i * B:(i + 1) * B] for _ in range(self.num_learning_epochs) for i in range(self.num_mini_batches)]
-        mb = self._static_minibatch(B)
         self._scalars.zero_()
         ac.flat_grad.zero_()
-        # Across ranks the minibatch body runs eagerly: it is GPU-bound either way (graph replay and eager launch measure the
-        # same), and keeping the NCCL all-reduce out of stream capture avoids depending on capture support in the process group.
-        use_graph = self.use_graph and (world == 1 or self._peer is not None) and all(p.numel() == B for p in plan)
-        n_updates = 0
-        for idx in plan:
-            if idx.numel() != B:      # ragged plan (tests): fresh buffers, eager
-                mb = self._static_minibatch(idx.numel())
-            mb["idx"].copy_(idx, non_blocking=True)
-            if not use_graph:
-                self._minibatch_step(mb, world)
-            else:
-                if mb["graph"] is None:
-                    self._capture(mb, world)
-                mb["graph"].replay()
-                self.optimizer.steps += 1
-            n_updates += 1
+        # The NCCL baseline runs eagerly: keeping the process-group collective out of stream capture avoids depending on capture
+        # support in the process group.
+        use_graph = self.use_graph and (world == 1 or self._xchg is not None or self._peer is not None)
+        sp = None
+        if plan is None:
+            # rsl_rl: ONE permutation per update, re-used by every epoch (rollout_storage.py mini_batch_generator)
+            sp = self._static_plan(B, self.num_mini_batches, self.num_learning_epochs)
+            torch.randperm(self.num_mini_batches * B, device=self.device, out=sp["perm"])
+            plan = sp["slices"]
+        elif use_graph and len(plan) == self.num_mini_batches * self.num_learning_epochs and all(p.numel() == B for p in plan):
+            # an explicit plan of rsl_rl's shape (tests): epochs x the same minibatches -> the static buffer takes the first epoch
+            M = self.num_mini_batches
+            if all(plan[k] is plan[k % M] or torch.equal(plan[k], plan[k % M]) for k in range(M, len(plan))):
+                sp = self._static_plan(B, M, self.num_learning_epochs)
+                sp["perm"].copy_(torch.cat([p.to(self.device, torch.int64) for p in plan[:M]]))
+        use_graph = use_graph and sp is not None
+        n_updates = len(plan)
+        if use_graph:
+            if sp["graph"] is None:
+                self._capture(sp, world)
+            sp["graph"].replay()
+            self.optimizer.steps += n_updates
+        else:
+            for idx in plan:
+                self._minibatch_step(idx.to(self.device, torch.int64).contiguous(), world)
         self.storage.clear()
         ac.repack_fused()
         s = (self._scalars[0:4] / (n_updates * B))
         self.learning_rate = self.optimizer.lr   # device scalar; float(self.learning_rate) syncs on demand
         return s[2], s[1]   # mean_value_loss, mean_surrogate_loss (device scalars)
 
-    def _capture(self, mb, world):
+    def _capture(self, sp, world):
         """Warm-up on a side stream (buffer allocation, kernel attributes), restore the optimiser state, then capture."""
         ac, opt = self.actor_critic, self.optimizer
         state = (ac.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.lr, opt.step_dev, self._scalars, ac.flat_grad)
@@ -438,17 +463,18 @@ class PPO:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(2):
-                self._minibatch_step(mb, world)
+            for idx in sp["slices"][:2]:
+                self._minibatch_step(idx, world)
         torch.cuda.current_stream(self.device).wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._minibatch_step(mb, world)
+            for idx in sp["slices"]:
+                self._minibatch_step(idx, world)
         for t, k in zip(state, keep):
             t.copy_(k)
         opt.steps = steps
         ac._trainer.pack()
-        mb["graph"] = g
+        sp["graph"] = g
 
 
 class FlatAdam:
@@ -486,9 +512,10 @@ class FlatAdam:
                                                   ac.num_flat, 1.0, ptr(self._sumsq), max_grad_norm, ptr(self.lr), self.betas[0],
                                                   self.betas[1], self.eps, ptr(self.step_dev), st), "clip_adam_dev")
 
-    def fused_step(self, max_grad_norm, mb_scalars, totals, count, desired_kl):
-        """Single-GPU minibatch tail in ONE launch (csrc/ppo_train.cu ppo_optimizer_step_kernel): squared gradient norm, KL-adaptive
-        learning rate, clip + Adam, fp16 operand copies of the new weights, gradient buffer and minibatch sums cleared."""
+    def fused_step(self, max_grad_norm, mb_scalars, totals, count, desired_kl, xchg=None):
+        """Minibatch tail in ONE launch (csrc/ppo_train.cu ppo_optimizer_step[_peers]_kernel): [gradient exchange over peer memory,]
+        squared gradient norm, KL-adaptive learning rate, clip + Adam, fp16 operand copies of the new weights, gradient buffer and
+        minibatch sums cleared."""
         ac, ptr = self.ac, _lib.ptr
         self.steps += 1
         p = _lib.OptParamsPOD()
@@ -496,9 +523,17 @@ class FlatAdam:
         p.desired_kl, p.max_grad_norm = (desired_kl or 0.0), max_grad_norm
         p.beta1, p.beta2, p.eps = self.betas[0], self.betas[1], self.eps
         tr = ac._trainer
-        _lib.check(self.lib.b200gym_ppo_optimizer_step(p, ptr(ac.flat_param), ptr(ac.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                                       ptr(self.lr), ptr(self.step_dev), ptr(mb_scalars), ptr(totals), ptr(self._ws),
-                                                       tr._tab, ptr(tr.w16), _lib.stream_ptr(ac.flat_param.device)), "ppo_optimizer_step")
+        st = _lib.stream_ptr(ac.flat_param.device)
+        if xchg is None:
+            _lib.check(self.lib.b200gym_ppo_optimizer_step(p, ptr(ac.flat_param), ptr(ac.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                                           ptr(self.lr), ptr(self.step_dev), ptr(mb_scalars), ptr(totals), ptr(self._ws),
+                                                           tr._tab, ptr(tr.w16), st), "ppo_optimizer_step")
+        else:
+            _lib.check(self.lib.b200gym_ppo_optimizer_step_peers(p, xchg.peers, xchg.world, xchg.rank, xchg.n_pad, ptr(ac.flat_param),
+                                                                 ptr(ac.flat_grad), ptr(xchg.grad_sum), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                                                 ptr(self.lr), ptr(self.step_dev), ptr(mb_scalars), ptr(totals), ptr(xchg.ws),
+                                                                 tr._tab, ptr(tr.w16), int(os.environ.get("B200GYM_OPT_CTAS", "0")), st),
+                       "ppo_optimizer_step_peers")
         self._last_sumsq = totals[4:5]
 
     def grad_norm(self):
@@ -526,6 +561,7 @@ class OnPolicyRunner:
         self.alg = PPO(ac, device=self.device, **self.alg_cfg)
         self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
         self.alg.init_storage(env.num_envs, self.num_steps_per_env, [env.num_obs], [env.num_privileged_obs], [env.num_actions])
+        self.alg.env_id_offset = int(getattr(env, "env_id_offset", 0))   # env shards draw distinct action noise
         self.tot_timesteps, self.tot_time, self.current_learning_iteration = 0, 0, 0
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):

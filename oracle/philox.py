@@ -100,3 +100,4 @@ SITE_HOP_ROOT_POS = 34    # cols 0..4 = z, qx, qy, qz, qw offsets              (
 SITE_HOP_YAW = 35         # col 0                                              (hopper_trajectory.py:343)
 SITE_HOP_ROOT_VEL = 36    # cols 0..5                                          (hopper_trajectory.py:351-354)
 SITE_HOP_PUSH = 37        # cols 0..5                                          (hopper_trajectory.py:366-367)
+SITE_POLICY_SAMPLE = 48   # cols 0..num_actions-1: Box-Muller pairs, event = act counter  (rsl_rl PPO.act -> Normal.sample)

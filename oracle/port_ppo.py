@@ -115,3 +115,27 @@ def ppo_update(ac, optimizer, storage, plan, lr, desired_kl=0.01, max_grad_norm=
         stats.append(dict(loss=float(loss), kl=float(info["kl_mean"]), grad_norm=float(gn), lr=lr,
                           surrogate=float(info["surrogate_loss"]), value_loss=float(info["value_loss"])))
     return lr, stats
+
+
+def sample_actions(mu, std, seed, env_ids, event):
+    """Specification of the action sample of the fused PPO.act (legged_gym_dev_b200/csrc/ppo_rollout.cu): rsl_rl draws
+    Normal(mu, std).sample() from torch's global generator; here the standard normals come from the library's Philox stream
+    (site POLICY_SAMPLE, counter = (global env id, act event)) through Box-Muller — per Philox block (w0, w1, w2, w3):
+    columns 4b + {0, 1} = sqrt(-2 ln u(w0)) * {cos, sin}(2 pi u(w1)), columns 4b + {2, 3} likewise from (w2, w3), with
+    u(w) = ((w >> 8) + 0.5) 2^-24 under the logarithm and (w >> 8) 2^-24 in the angle.  Returns (actions, summed log-prob) as
+    float32 tensors, computed with torch's Normal.log_prob formula."""
+    import numpy as np
+    from . import philox
+    A = mu.shape[1]
+    nb = (A + 3) // 4
+    w = philox._words(seed, env_ids, event, philox.SITE_POLICY_SAMPLE, nb * 4).reshape(-1, nb, 4)
+    f = np.float32
+    ulog = ((w[..., 0::2] >> np.uint32(8)).astype(f) + f(0.5)) * f(2.0 ** -24)
+    uang = (w[..., 1::2] >> np.uint32(8)).astype(f) * f(2.0 ** -24)
+    r = np.sqrt(f(-2.0) * np.log(ulog)).astype(f)
+    ang = (f(6.283185307179586) * uang).astype(f)
+    z = np.stack((r * np.cos(ang), r * np.sin(ang)), axis=-1).astype(f).reshape(-1, nb * 4)[:, :A]
+    z = torch.from_numpy(z)
+    actions = mu + std * z
+    logp = torch.distributions.Normal(mu, mu * 0.0 + std).log_prob(actions).sum(dim=-1)
+    return actions, logp

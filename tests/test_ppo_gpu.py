@@ -287,3 +287,115 @@ def test_grad_reduce_peers_kernel(world):
     assert abs(float(sumsq) - ref) <= 1e-12 * ref
     with pytest.raises(RuntimeError):
         _lib.check(L.b200gym_grad_reduce_peers(peers, 17, _lib.ptr(out), n, n_params, _lib.ptr(sumsq), _lib.stream_ptr("cuda")))
+
+
+def test_act_store_matches_oracle():
+    """PPO.act (two tcgen05 forwards + ONE act/store launch) against the sampling specification oracle/port_ppo.py
+    sample_actions: actions and summed log-prob to 1e-5 (S = max(1, |value|)), the transition row of the storage exact."""
+    from legged_gym_dev_b200.ppo import ActorCritic, PPO
+    torch.manual_seed(3)
+    N, T, A = 1000, 4, 12
+    ac = ActorCritic(48, 235, A, actor_hidden_dims=(128, 64, 32), critic_hidden_dims=(128, 64, 32), init_noise_std=0.7)
+    alg = PPO(ac, device="cuda")
+    alg.init_storage(N, T, [48], [235], [A])
+    alg.env_id_offset = 5000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    zs = []
+    for s in range(3):
+        obs = torch.randn(N, 48, device="cuda", generator=g)
+        cobs = torch.randn(N, 235, device="cuda", generator=g)
+        act = alg.act(obs, cobs)
+        st = alg.storage
+        assert act.data_ptr() == st.actions[s].data_ptr()
+        assert torch.equal(st.observations[s], obs) and torch.equal(st.privileged_observations[s], cobs)
+        mu, val = ac.act_inference(obs), ac.evaluate(cobs)
+        assert torch.equal(st.mu[s], mu) and torch.equal(st.values[s], val)
+        assert torch.equal(st.sigma[s], ac.std.detach().expand(N, A))
+        want_a, want_lp = O.sample_actions(mu.cpu(), ac.std.detach().cpu(), alg.seed, 5000 + torch.arange(N).numpy(), s + 1)
+        assert_close(st.actions[s].cpu(), want_a, 1.0, f"actions step {s}", rtol=1e-5)
+        assert_close(st.actions_log_prob[s, :, 0].cpu(), want_lp, 1.0, f"log-prob step {s}", rtol=1e-5)
+        assert torch.equal(alg.transition.actions_log_prob, st.actions_log_prob[s, :, 0])
+        zs.append(((st.actions[s] - mu) / ac.std.detach()).flatten())
+        alg.process_env_step(torch.full((N,), 0.25 + s, device="cuda"), torch.arange(N, device="cuda") % 7 == s,
+                             {"time_outs": torch.arange(N, device="cuda") % 14 == s})
+        assert st.step == s + 1
+        assert torch.equal(st.rewards[s, :, 0], torch.full((N,), 0.25 + s, device="cuda"))
+        assert torch.equal(st.dones[s, :, 0].bool(), torch.arange(N, device="cuda") % 7 == s)
+        assert torch.equal(st.time_outs[s].bool(), torch.arange(N, device="cuda") % 14 == s)
+    z = torch.cat(zs)
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02, "the sample is not a standard normal"
+    assert not torch.equal(zs[0], zs[1])
+    # long `dones` (the reference's reset_buf dtype at allocation, base_task.py:72) and no time-out entry
+    alg.act(obs, cobs)
+    alg.process_env_step(torch.ones(N, device="cuda"), torch.ones(N, dtype=torch.long, device="cuda"), {})
+    assert bool(alg.storage.dones[3].all()) and not bool(alg.storage.time_outs[3].any())
+    with pytest.raises(AssertionError):
+        alg.act(obs, cobs)
+
+
+@pytest.mark.parametrize("world,n", [(2, 33657), (4, 33657), (3, 1001), (2, 590000)])
+def test_optimizer_step_peers_emulated_ranks(world, n):
+    """b200gym_ppo_optimizer_step_peers with `world` emulated ranks on ONE GPU: every rank's launch runs on its own stream with
+    local tensors standing in for the symmetric buffers, so the push / flag / wait / rank-ordered-sum protocol runs for real
+    (the kernels wait for each other).  Two consecutive exchanges (both slot parities).  All ranks must hold bit-identical
+    parameters equal to clip_grad_norm_ + Adam on the rank-ordered gradient sum; the 2+ GPU wiring is tools/ddp_train_check.py."""
+    from legged_gym_dev_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    n_pad = (n + 2 + 3) // 4 * 4
+    g = torch.Generator(device="cuda").manual_seed(world)
+    p0 = torch.randn(n, generator=g, device=dev) * 0.1
+    sym = [torch.zeros(2 * world * n_pad + 32, device=dev) for _ in range(world)]
+    peers = _lib.PeerBasesPOD()
+    for r in range(world):
+        peers.base[r] = sym[r].data_ptr()
+    tab = _lib.PackTablePOD()
+    tab.n, tab.total = 1, n
+    tab.e[0].src_off, tab.e[0].dst_off, tab.e[0].elem_end, tab.e[0].rows, tab.e[0].cols, tab.e[0].ld, tab.e[0].layout = 0, 0, n, 1, n, n, 0
+    R = [dict(param=p0.clone(), grad=torch.zeros(n + 8, device=dev), gsum=torch.zeros(n_pad, device=dev), m=torch.zeros(n, device=dev),
+              v=torch.zeros(n, device=dev), lr=torch.tensor([1e-3], device=dev), step=torch.zeros(1, dtype=torch.int32, device=dev),
+              mb=torch.zeros(4, dtype=torch.double, device=dev), tot=torch.zeros(8, dtype=torch.double, device=dev),
+              ws=torch.zeros(_lib.PEER_WS_BYTES // 4, dtype=torch.int32, device=dev), w16=torch.zeros(n, dtype=torch.float16, device=dev),
+              stream=torch.cuda.Stream()) for _ in range(world)]
+    ref_p, ref_m, ref_v, lr = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev), 1e-3
+    op = _lib.OptParamsPOD()
+    op.n, op.count, op.adaptive, op.desired_kl, op.max_grad_norm, op.beta1, op.beta2, op.eps = n, 100.0, 1, 0.01, 1.0, 0.9, 0.999, 1e-8
+    for it in range(2):
+        grads = [torch.randn(n, generator=g, device=dev) * (0.01 if it == 0 else 1e-4) for _ in range(world)]
+        kls = [0.05 * (r + 1) * 100.0 if it == 0 else 0.0001 * 100.0 for r in range(world)]
+        for r in range(world):
+            R[r]["grad"][:n].copy_(grads[r])
+            R[r]["mb"][0] = kls[r]
+        torch.cuda.synchronize()
+        for r in range(world):
+            d = R[r]
+            with torch.cuda.stream(d["stream"]):
+                _lib.check(L.b200gym_ppo_optimizer_step_peers(op, peers, world, r, n_pad, *[_lib.ptr(d[k]) for k in
+                                                              ("param", "grad", "gsum", "m", "v", "lr", "step", "mb", "tot", "ws")],
+                                                              tab, _lib.ptr(d["w16"]), 0, d["stream"].cuda_stream), "ppo_optimizer_step_peers")
+        torch.cuda.synchronize()
+        # reference: rank-ordered fp32 sum, KL schedule on the global mean, clip_grad_norm_, torch Adam arithmetic
+        tot = grads[0].clone()
+        for r in range(1, world):
+            tot = tot + grads[r]
+        kl_mean = sum(kls) / (100.0 * world)
+        if kl_mean > 0.02:
+            lr = max(1e-5, lr / 1.5)
+        elif 0.0 < kl_mean < 0.005:
+            lr = min(1e-2, lr * 1.5)
+        norm = float(torch.sqrt((tot.double() ** 2).sum()))
+        gc = tot * min(1.0 / (norm + 1e-6), 1.0)
+        ref_m = 0.9 * ref_m + 0.1 * gc
+        ref_v = 0.999 * ref_v + 0.001 * gc * gc
+        t = it + 1
+        ref_p = ref_p - (lr / (1 - 0.9 ** t)) * ref_m / (ref_v.sqrt() / (1 - 0.999 ** t) ** 0.5 + 1e-8)
+        for r in range(world):
+            d = R[r]
+            assert int(d["ws"][4]) == 0, "a rank timed out waiting for its peers"
+            assert torch.equal(d["gsum"][:n], tot), f"rank {r}: summed gradients differ from the rank-ordered sum"
+            assert torch.equal(d["param"], R[0]["param"]) and torch.equal(d["m"], R[0]["m"]), f"rank {r} diverged from rank 0"
+            assert float(d["grad"].abs().max()) == 0.0 and int(d["step"]) == t and float(d["mb"][0]) == 0.0
+            assert abs(float(d["lr"]) - lr) <= 1e-9
+            assert abs(float(d["tot"][4]) - norm * norm) <= 1e-9 * norm * norm
+            assert torch.equal(d["w16"], d["param"].half())
+        assert_close(R[0]["param"].cpu(), ref_p.cpu(), 1.0, f"parameters after exchange {it}", rtol=2e-6)

@@ -27,3 +27,34 @@ def test_train_call_sequence():
     policy = runner.get_inference_policy(device=env.device)
     assert policy(env.get_observations()).shape == (N, 12)
     assert set(env.extras) >= {"episode", "time_outs"}
+
+
+def test_storage_holds_the_observation_each_action_was_computed_from():
+    """rsl_rl stores references to the obs tensors its env returns; the fused env rewrites ONE obs_buf in place, so PPO.act must
+    store the observation at act time: storage.observations[t] == obs fed to act at step t, and observations[t + 1] == the obs
+    returned by step t."""
+    from types import SimpleNamespace
+    from legged_gym_dev_b200 import synthetic as S
+    from legged_gym_dev_b200.physics import ReplayPhysics
+    from legged_gym_dev_b200.task_registry import task_registry
+    N = 256
+    tape = S.make_state_tape(N, frames=8, seed=1, device="cuda")
+    args = SimpleNamespace(num_envs=N, sim_device="cuda", headless=True, physics_engine=None)
+    env, _ = task_registry.make_env("anymal_c_flat_b200", args=args, physics=ReplayPhysics(tape, device="cuda"))
+    runner, _ = task_registry.make_alg_runner(env, name="anymal_c_flat_b200", args=args)
+    alg = runner.alg
+    obs = env.get_observations()
+    fed, returned = [], []
+    for t in range(6):
+        fed.append(obs.clone())
+        actions = alg.act(obs, obs)
+        mu = alg.actor_critic.act_inference(fed[-1])
+        assert torch.equal(alg.storage.mu[t], mu), "mu was not computed from the stored observation"
+        obs, _, rew, dones, infos = env.step(actions)
+        returned.append(obs.clone())
+        alg.process_env_step(rew, dones, infos)
+        assert torch.equal(alg.storage.rewards[t, :, 0], rew) and torch.equal(alg.storage.dones[t, :, 0].bool(), dones)
+    for t in range(6):
+        assert torch.equal(alg.storage.observations[t], fed[t])
+        if t + 1 < 6:
+            assert torch.equal(alg.storage.observations[t + 1], returned[t])

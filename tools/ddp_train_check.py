@@ -27,7 +27,34 @@ torch.manual_seed(1)                                                            
 runner, _ = task_registry.make_alg_runner(env, name="anymal_c_flat_b200", args=args)
 p0 = runner.alg.actor_critic.flat_param.clone()
 alg = runner.alg
-mode = "peer-memory kernel" if getattr(alg, "_peer", None) is not None else "NCCL all-reduce"
+mode = alg.exchange
+if world > 1 and getattr(alg, "_xchg", None) is not None:
+    # unit check of the in-kernel exchange against NCCL on random gradients: after one fused step grad_sum holds the rank-ordered sum
+    ac, x = alg.actor_critic, alg._xchg
+    state = [t.clone() for t in (ac.flat_param, alg.optimizer.exp_avg, alg.optimizer.exp_avg_sq, alg.optimizer.lr, alg.optimizer.step_dev, alg._scalars)]
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    ac.flat_grad[:ac.num_flat].copy_(torch.randn(ac.num_flat, generator=g, device=dev))
+    want = ac.flat_grad[:ac.num_flat].clone()
+    dist.all_reduce(want)
+    alg._scalars[8] = 0.25 * (rank + 1)
+    alg.optimizer.fused_step(1.0, alg._scalars[8:12], alg._scalars, 100.0, 0.01, xchg=x)
+    torch.cuda.synchronize()
+    got = x.grad_sum[:ac.num_flat].clone()
+    err = float((got - want).abs().max())
+    tail = x.grad_sum[ac.num_flat:ac.num_flat + 2].tolist()
+    allg = [torch.empty_like(x.grad_sum) for _ in range(world)]
+    dist.all_gather(allg, x.grad_sum)
+    same_sum = all(torch.equal(allg[0], t) for t in allg)
+    cleared = float(ac.flat_grad.abs().max()) == 0.0
+    if rank == 0:
+        print(f"fused exchange vs NCCL: max |diff| {err:.2e}, tail {tail} (want {[0.25 * world * (world + 1) / 2, 100.0 * world]}), "
+              f"bit-identical across ranks: {same_sum}, local grads cleared: {cleared}, error flag: {x.error()}")
+    assert err < 1e-5 and same_sum and cleared and not x.error()
+    assert abs(tail[0] - 0.25 * world * (world + 1) / 2) < 1e-5 and tail[1] == 100.0 * world
+    for t, k in zip((ac.flat_param, alg.optimizer.exp_avg, alg.optimizer.exp_avg_sq, alg.optimizer.lr, alg.optimizer.step_dev, alg._scalars), state):
+        t.copy_(k)
+    alg.optimizer.steps = 0
+    ac.repack_fused()
 if world > 1 and getattr(alg, "_peer", None) is not None:
     # unit check of the peer-memory reduction against NCCL on random buffers
     pr = alg._peer
