@@ -142,6 +142,15 @@ int b200gym_debug_set_lstm_variant(int variant);
 int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedBuffers* b, uint64_t step, int64_t env_id_offset,
                          void* stream);
 
+/* LeggedRobot.reset_idx(env_ids) as an EXTERNAL call (legged_robot.py:147-187, anymal.py:56-60; BaseTask.reset, base_task.py:111-119)
+ * for the envs flagged in reset_mask (uint8 [N]): terrain curriculum, dof / root state redraw, command resample, last_actions /
+ * last_dof_vel / feet_air_time / episode_length_buf cleared, reset_buf set, episode_sums folded into extras_out (means over the
+ * reset envs / max_episode_length_s, terrain-level mean over all envs) and cleared, actuator LSTM state zeroed.  time_out_buf,
+ * obs_buf and rew_buf are left alone, as in the reference.  `event` keys the Philox draws (sites as in b200gym_post_physics); pass
+ * a value no env step uses (the Python mirror: (number of external resets << 40) | common_step_counter).  Not for traj_mode. */
+int b200gym_legged_reset_idx(const B200LeggedParams* p, const B200LeggedBuffers* b, const uint8_t* reset_mask, uint64_t event,
+                             int64_t env_id_offset, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Group M — reduced-order-model rollout (trajopt/rom_dynamics.py, deep_tube_learning/custom_sim.py,
  * deep_tube_learning/controllers.py, deep_tube_learning/data_collection_trajectory.py)

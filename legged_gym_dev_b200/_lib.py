@@ -192,6 +192,8 @@ def lib():
     L.b200gym_set_actuator_net.argtypes = [vp] * 10 + [f32, f32, f32]
     L.b200gym_lstm_torques.argtypes = [pp, vp, vp, vp, vp, vp, vp, vp]
     L.b200gym_post_physics.argtypes = [pp, C.POINTER(LeggedBuffersPOD), C.c_uint64, C.c_int64, vp]
+    L.b200gym_legged_reset_idx.argtypes = [pp, C.POINTER(LeggedBuffersPOD), vp, C.c_uint64, C.c_int64, vp]
+    L.b200gym_legged_reset_idx.restype = C.c_int
     for name in ("b200gym_pd_torques", "b200gym_set_actuator_net", "b200gym_lstm_torques", "b200gym_post_physics"):
         getattr(L, name).restype = C.c_int
     rp, rs = C.POINTER(RomParamsPOD), C.POINTER(RomStatePOD)

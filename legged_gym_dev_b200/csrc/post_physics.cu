@@ -936,6 +936,100 @@ __global__ void extras_finalize_kernel(const __grid_constant__ B200LeggedParams 
 }
 #endif
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// reset_idx_kernel — LeggedRobot.reset_idx(env_ids) called from OUTSIDE step() (legged_robot.py:147-187, anymal.py:56-60;
+// BaseTask.reset, base_task.py:111-119): the same draws and buffer updates as the in-step reset branch of phase S, for the
+// envs flagged in `mask`, with no termination / time-out flag touched and no observation recomputed (the reference leaves
+// obs_buf alone until the next step).  One thread per env of the shard; every env contributes its terrain level to the
+// extras["episode"]["terrain_level"] mean (:181).  The random draws are keyed by `event` (the host passes a number that no
+// env step uses: the external-reset count in the high bits, common_step_counter below — oracle/port_legged.py reset_idx).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) reset_idx_kernel(const __grid_constant__ B200LeggedParams p, const __grid_constant__ B200LeggedBuffers b,
+                                                        const uint8_t* __restrict__ mask, unsigned long long event, long long env_off,
+                                                        const SqThr thr) {
+    const int N = p.num_envs, K = p.num_sum_rows;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_acc[B200GYM_NUM_REWARD_TERMS + 2];
+    if (threadIdx.x < K + 2) s_acc[threadIdx.x] = 0.0;
+    __syncthreads();
+    const bool valid = e < N;
+    const bool hit = valid && mask[e] != 0;
+    long long level = (valid && p.terrain_curriculum) ? b.terrain_levels[e] : 0;
+    if (hit) {
+        const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<unsigned long long>(env_off + e), event);
+        float c0 = b.commands[e * 4 + 0], c1 = b.commands[e * 4 + 1], c2 = b.commands[e * 4 + 2], c3 = b.commands[e * 4 + 3];
+        float ox = b.env_origins[e * 3 + 0], oy = b.env_origins[e * 3 + 1], oz = b.env_origins[e * 3 + 2];
+        if (p.terrain_curriculum) {   // legged_robot.py:463-486
+            const float dist = norm2_rn(sub_rn(b.root_states[e * 13 + 0], ox), sub_rn(b.root_states[e * 13 + 1], oy));
+            const bool up = dist > p.half_env_length;
+            const bool down = (dist < mul_rn(mul_rn(norm2_rn(c0, c1), p.max_episode_length_s), 0.5f)) && !up;
+            level += (up ? 1 : 0) - (down ? 1 : 0);
+            if (level >= p.max_terrain_level)
+                level = philox::bounded(rng.words(philox::TERRAIN, 0).x, static_cast<uint32_t>(p.max_terrain_level));
+            else if (level < 0)
+                level = 0;
+            const float* og = b.terrain_origins + (level * p.terrain_num_cols + b.terrain_types[e]) * 3;
+            ox = og[0], oy = og[1], oz = og[2];
+            b.terrain_levels[e] = level;
+            b.env_origins[e * 3 + 0] = ox, b.env_origins[e * 3 + 1] = oy, b.env_origins[e * 3 + 2] = oz;
+        }
+        for (int blk = 0; blk < 3; ++blk) {   // dofs: q = q0 * U(0.5, 1.5), qd = 0 (:423-425)
+            const uint4 w = rng.words(philox::RESET_DOF, blk);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int d = 4 * blk + i;
+                const float q = mul_rn(p.default_dof_pos[d], affine_rn(1.0f, philox::u01(philox::word(w, i)), 0.5f));
+                reinterpret_cast<float2*>(b.dof_state)[e * ND + d] = make_float2(q, 0.0f);
+                b.last_actions[e * ND + d] = 0.0f;
+                b.last_dof_vel[e * ND + d] = 0.0f;
+            }
+        }
+        float nr[13];   // root (:441-449)
+#pragma unroll
+        for (int k = 0; k < 13; ++k) nr[k] = p.base_init_state[k];
+        nr[0] = add_rn(nr[0], ox), nr[1] = add_rn(nr[1], oy), nr[2] = add_rn(nr[2], oz);
+        if (p.custom_origins) {
+            const uint4 w = rng.words(philox::RESET_XY, 0);
+            nr[0] = add_rn(nr[0], affine_rn(2.0f, philox::u01(w.x), -1.0f));
+            nr[1] = add_rn(nr[1], affine_rn(2.0f, philox::u01(w.y), -1.0f));
+        }
+        const uint4 w0 = rng.words(philox::RESET_VEL, 0), w1 = rng.words(philox::RESET_VEL, 1);
+        nr[7] = affine_rn(1.0f, philox::u01(w0.x), -0.5f), nr[8] = affine_rn(1.0f, philox::u01(w0.y), -0.5f);
+        nr[9] = affine_rn(1.0f, philox::u01(w0.z), -0.5f), nr[10] = affine_rn(1.0f, philox::u01(w0.w), -0.5f);
+        nr[11] = affine_rn(1.0f, philox::u01(w1.x), -0.5f), nr[12] = affine_rn(1.0f, philox::u01(w1.y), -0.5f);
+#pragma unroll
+        for (int k = 0; k < 13; ++k) b.root_states[e * 13 + k] = nr[k];
+        resample_commands(p, thr, rng, philox::CMD_RESET, c0, c1, c2, c3);
+        *reinterpret_cast<float4*>(b.commands + e * 4) = make_float4(c0, c1, c2, c3);
+        *reinterpret_cast<float4*>(b.feet_air_time + e * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<long long*>(b.episode_length_buf)[e] = 0;
+        b.reset_buf[e] = 1;
+        for (int k = 0; k < K; ++k) {   // extras["episode"] statistics (:175-179)
+            atomicAdd(&s_acc[k], static_cast<double>(b.episode_sums[static_cast<size_t>(k) * N + e]));
+            b.episode_sums[static_cast<size_t>(k) * N + e] = 0.0f;
+        }
+        atomicAdd(&s_acc[K + 1], 1.0);
+        if (p.zero_lstm_on_reset) {
+            const size_t M8 = static_cast<size_t>(N) * ND * 8;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int l = 0; l < 2; ++l) {
+                float4* hp = reinterpret_cast<float4*>(b.lstm_h + l * M8 + static_cast<size_t>(e) * ND * 8);
+                float4* cp = reinterpret_cast<float4*>(b.lstm_c + l * M8 + static_cast<size_t>(e) * ND * 8);
+                for (int k = 0; k < 24; ++k) hp[k] = z4, cp[k] = z4;
+            }
+        }
+    }
+    if (p.terrain_curriculum) {
+        long long lv = valid ? level : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[K], static_cast<double>(lv));
+    }
+    __syncthreads();
+    if (threadIdx.x < K + 2 && s_acc[threadIdx.x] != 0.0) atomicAdd(&b.ws_sums[threadIdx.x], s_acc[threadIdx.x]);
+}
+
 // largest y with sqrtf(y) <= t  (so sqrtf(x) > t <=> x > y) and smallest y with sqrtf(y) >= t (sqrtf(x) < t <=> x < y)
 static float sq_gt(float t) {
     float y = t * t;
@@ -1043,4 +1137,35 @@ extern "C" int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedB
     }
     if (rough) return launch_post_physics<64, true>(*p, *b, step, env_id_offset, do_push, st);
     return launch_post_physics<64, false>(*p, *b, step, env_id_offset, do_push, st);
+}
+
+
+extern "C" int b200gym_legged_reset_idx(const B200LeggedParams* p, const B200LeggedBuffers* b, const uint8_t* reset_mask, uint64_t event,
+                                        int64_t env_id_offset, void* stream) {
+    B200_REQUIRE(p && b && reset_mask, B200GYM_EINVAL, "legged_reset_idx: null argument");
+    B200_REQUIRE(p->num_envs > 0 && p->num_sum_rows >= 0 && p->num_sum_rows <= B200GYM_NUM_REWARD_TERMS, B200GYM_EINVAL, "legged_reset_idx: bad sizes");
+    B200_REQUIRE(p->traj_mode == 0, B200GYM_EINVAL, "legged_reset_idx: the trajectory env resets through its own generator path");
+    B200_REQUIRE(!p->terrain_curriculum || (b->terrain_levels && b->terrain_types && b->terrain_origins), B200GYM_EINVAL,
+                 "legged_reset_idx: terrain curriculum buffers missing");
+    B200_REQUIRE(!p->zero_lstm_on_reset || (b->lstm_h && b->lstm_c), B200GYM_EINVAL, "legged_reset_idx: LSTM state buffers missing");
+    const void* must[] = {b->root_states, b->dof_state, b->last_actions, b->last_dof_vel, b->commands, b->feet_air_time, b->episode_length_buf,
+                          b->reset_buf, b->env_origins, b->extras_out, b->ws_sums};
+    for (const void* q : must) {
+        B200_REQUIRE(q != nullptr, B200GYM_EINVAL, "legged_reset_idx: null buffer");
+        B200_REQUIRE(b200_aligned16(q), B200GYM_EALIGN, "legged_reset_idx: buffers must be 16-byte aligned");
+    }
+    B200_REQUIRE(p->num_sum_rows == 0 || b->episode_sums, B200GYM_EINVAL, "legged_reset_idx: episode_sums missing");
+    static const SqThr thr = {sq_gt(1.0f), sq_gt(0.1f), sq_gt(0.2f), sq_lt(0.1f)};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    reset_idx_kernel<<<(p->num_envs + 127) / 128, 128, 0, st>>>(*p, *b, reset_mask, event, env_id_offset, thr);
+    B200_LAUNCH_CHECK("legged_reset_idx");
+#if PP_FINALIZE_KERNEL
+    B200LeggedBuffers b2 = *b;
+    b2.step_counter = nullptr;   // the means are finalised like a step's, but no env step has happened
+    extras_finalize_kernel<<<1, 32, 0, st>>>(*p, b2);
+    B200_LAUNCH_CHECK("legged_reset_idx finalize");
+#else
+#error "legged_reset_idx needs the stand-alone extras finaliser (PP_FINALIZE_KERNEL)"
+#endif
+    return B200GYM_OK;
 }

@@ -314,16 +314,37 @@ class LeggedRobot:
         return self.privileged_obs_buf
 
     def reset_idx(self, env_ids):
-        """External resets (legged_robot.py:147-187).  The per-step resets happen inside the fused kernel; this
-        entry point forces `env_ids` to terminate on the next step by saturating their episode counters, which
-        reproduces the reference's BaseTask.reset() sequence (reset_idx(all); step(0))."""
+        """LeggedRobot.reset_idx called from outside step() (legged_robot.py:147-187): ONE masked launch that redraws the dof / root
+        state, resamples commands, clears the per-episode buffers, folds episode_sums into extras["episode"] and sets reset_buf —
+        immediately, with time_out_buf untouched, as the reference does.  (The per-step resets live in the fused step kernel.)
+        Draws are keyed by an event no env step uses: (external reset count << 40) | common_step_counter."""
         if len(env_ids) == 0:
             return
-        self.episode_length_buf[env_ids] = int(self.max_episode_length) + 1
+        if self.params.traj_mode:
+            # LeggedRobotTrajectory.reset_idx also resets the generators from the new roots: that sequence runs inside the fused
+            # step (legged_robot_trajectory.py), so an external reset of the trajectory env is deferred to the next step
+            self.episode_length_buf[env_ids] = int(self.max_episode_length) + 1
+            return
+        if getattr(self, "_reset_mask", None) is None:
+            self._reset_mask = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            self._ext_resets = 0
+        self._reset_mask.zero_()
+        self._reset_mask[env_ids] = 1
+        self._ext_resets += 1
+        step = self.common_step_counter if getattr(self, "_step_dev", None) is None else int(self._step_dev.item()) - 1
+        rc = self.lib.b200gym_legged_reset_idx(self._pod, self._buffers(), self._reset_mask.data_ptr(), (self._ext_resets << 40) | int(step),
+                                               self.env_id_offset, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "legged_reset_idx")
+        self.physics.commit_resets(self._reset_mask.view(torch.bool))
 
     def reset(self):
-        self.reset_idx(torch.arange(self.num_envs, device=self.device))
+        """BaseTask.reset of the fork (base_task.py:111-119): reset_idx(all), a zero-action step, and both once more."""
+        ids = torch.arange(self.num_envs, device=self.device)
         zero = torch.zeros(self.num_envs, self.num_actions, device=self.device)
+        self.reset_idx(ids)
+        self.step(zero)
+        self.reset_idx(ids)
         obs, priv, _, _, _ = self.step(zero)
         return obs, priv
 

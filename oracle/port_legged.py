@@ -97,7 +97,12 @@ class LeggedPort:
         if self.rng == "torch":
             return torch.rand(n, ncols)
         ids = env_ids.numpy() + self.off
-        return torch.from_numpy(P.uniform01(self.p.seed, ids, self.common_step_counter, site, ncols))
+        return torch.from_numpy(P.uniform01(self.p.seed, ids, self._event(), site, ncols))
+
+    def _event(self):
+        """Philox event of the current draw: common_step_counter inside a step, or the external-reset event (reset_idx)."""
+        ev = getattr(self, "_ext_event", None)
+        return self.common_step_counter if ev is None else ev
 
     def _uniform(self, lo, hi, site, env_ids, ncols, col=None):
         u = self._u(site, env_ids, ncols)
@@ -294,7 +299,7 @@ class LeggedPort:
             if self.rng == "torch":
                 rnd = torch.randint_like(self.terrain_levels[ids], p.max_terrain_level)
             else:
-                rnd = torch.from_numpy(P.randint(p.seed, ids.numpy() + self.off, self.common_step_counter,
+                rnd = torch.from_numpy(P.randint(p.seed, ids.numpy() + self.off, self._event(),
                                                  P.SITE_TERRAIN, 1, p.max_terrain_level)).squeeze(1)
             self.terrain_levels[ids] = torch.where(self.terrain_levels[ids] >= p.max_terrain_level, rnd,
                                                    torch.clip(self.terrain_levels[ids], 0))
@@ -323,6 +328,31 @@ class LeggedPort:
             D = p.num_dof
             self.sea_hidden_state.view(2, self.N, D, 8)[:, ids] = 0.0
             self.sea_cell_state.view(2, self.N, D, 8)[:, ids] = 0.0
+
+    def reset_idx(self, ids):
+        """LeggedRobot.reset_idx called from OUTSIDE step() (legged_robot.py:147-187; BaseTask.reset base_task.py:111-119).  Same
+        body as the in-step reset plus `reset_buf[env_ids] = 1` (:170); its draws are keyed by the event
+        (external reset count << 40) | common_step_counter, which no env step uses."""
+        ids = torch.as_tensor(ids, dtype=torch.long)
+        if len(ids) == 0:
+            return
+        self._ext_resets = getattr(self, "_ext_resets", 0) + 1
+        self._ext_event = (self._ext_resets << 40) | self.common_step_counter
+        try:
+            self._reset_idx(ids)
+        finally:
+            self._ext_event = None
+        self.reset_buf = self.reset_buf.clone()
+        self.reset_buf[ids] = True
+
+    def reset(self, physics):
+        """BaseTask.reset of the fork (base_task.py:111-119): reset_idx(all) + zero-action step, twice."""
+        ids, zero = torch.arange(self.N), torch.zeros(self.N, self.p.num_dof)
+        self.reset_idx(ids)
+        self.step(zero, physics)
+        self.reset_idx(ids)
+        obs, priv, _, _, _ = self.step(zero.clone(), physics)
+        return obs, priv
 
     def _compute_observations(self):                                      # legged_robot.py:208-226
         p = self.p

@@ -431,31 +431,49 @@ def _install_legged_wrappers(ref):
     rng_shim.install()
     all_ids = lambda s: np.arange(s.num_envs)
 
+    # draw event: common_step_counter inside a step; an EXTERNAL reset_idx (BaseTask.reset, user code) keys its draws with
+    # (external reset count << 40) | common_step_counter so that they never coincide with a step's (oracle/port_legged.py reset_idx)
+    ev = lambda s: getattr(s, "_shim_event", None) or s.common_step_counter
+
     def cmd_ctx(self, env_ids):
         site = P.SITE_CMD_RESET if getattr(self, "_in_reset", False) else P.SITE_CMD_PERIODIC
-        return (env_ids, self.common_step_counter, [(site, 0), (site, 1), (site, 2)])
+        return (env_ids, ev(self), [(site, 0), (site, 1), (site, 2)])
 
     _wrap(LR, "_resample_commands", cmd_ctx)
-    _wrap(LR, "_push_robots", lambda s: (all_ids(s), s.common_step_counter, [(P.SITE_PUSH, 0)]))
+    _wrap(LR, "_push_robots", lambda s: (all_ids(s), ev(s), [(P.SITE_PUSH, 0)]))
     _wrap(LR, "_update_terrain_curriculum",
-          lambda s, env_ids: (env_ids, s.common_step_counter, [(P.SITE_TERRAIN, 0)]))
-    _wrap(LR, "_reset_dofs", lambda s, env_ids: (env_ids, s.common_step_counter, [(P.SITE_RESET_DOF, 0)]))
+          lambda s, env_ids: (env_ids, ev(s), [(P.SITE_TERRAIN, 0)]))
+    _wrap(LR, "_reset_dofs", lambda s, env_ids: (env_ids, ev(s), [(P.SITE_RESET_DOF, 0)]))
     _wrap(LR, "_reset_root_states",
-          lambda s, env_ids: (env_ids, s.common_step_counter,
+          lambda s, env_ids: (env_ids, ev(s),
                               [(P.SITE_RESET_XY, 0), (P.SITE_RESET_VEL, 0)] if s.custom_origins
                               else [(P.SITE_RESET_VEL, 0)]))
-    _wrap(LR, "compute_observations", lambda s: (all_ids(s), s.common_step_counter, [(P.SITE_OBS_NOISE, 0)]))
+    _wrap(LR, "compute_observations", lambda s: (all_ids(s), ev(s), [(P.SITE_OBS_NOISE, 0)]))
     if (LR, "reset_idx") not in _wrapped:
         _wrapped.add((LR, "reset_idx"))
         orig = LR.reset_idx
+        orig_pps = LR.post_physics_step
+
+        def post_physics_step(self):
+            self._in_pps = True
+            try:
+                return orig_pps(self)
+            finally:
+                self._in_pps = False
 
         def reset_idx(self, env_ids):
+            external = not getattr(self, "_in_pps", False) and hasattr(self, "_shim_seed") and len(env_ids) > 0
+            if external:
+                self._ext_resets = getattr(self, "_ext_resets", 0) + 1
+                self._shim_event = (self._ext_resets << 40) | int(self.common_step_counter)
             self._in_reset = True
             try:
                 return orig(self, env_ids)
             finally:
                 self._in_reset = False
+                self._shim_event = None
         LR.reset_idx = reset_idx
+        LR.post_physics_step = post_physics_step
 
 
 # --------------------------------------------------------------------------------------------

@@ -241,6 +241,40 @@ def test_tensor_core_lstm_variant_meets_the_torque_contract():
         L.b200gym_debug_set_lstm_variant(0)
 
 
+@pytest.mark.parametrize("name,N", [("flat_pd_upstream", 1000), ("rough_lstm_allterms", 516), ("flat_heading_nonoise", 68), ("rough_pd_shipped", 20)])
+def test_external_reset_matches_oracle(name, N):
+    """reset_idx(env_ids) / reset() called from outside step() (legged_robot.py:147-187, base_task.py:111-119) against the port
+    (pinned to the reference's own methods by tests/test_oracle_cpu.py::test_port_external_reset_tracks_unmodified_reference):
+    the masked reset launch acts immediately, leaves time_out_buf alone and keys its draws with the external-reset event."""
+    case = LC.build_case(name, N)
+    port, phys = LC.make_port(case)
+    env = LC.make_fused(case)
+    for s in range(4):
+        a = case.tape.actions[s % case.tape.frames]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+    ids = torch.arange(1, N, 3)
+    port.reset_idx(ids)
+    env.reset_idx(ids.cuda())
+    LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} partial reset: ")
+    assert bool(env.reset_buf[ids.cuda()].all()) and int(env.episode_length_buf[ids.cuda()].abs().sum()) == 0
+    for s in range(4, 7):
+        a = case.tape.actions[s % case.tape.frames]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} step {s} after the partial reset: ")
+    o_port, _ = port.reset(phys)
+    o_env, _ = env.reset()
+    LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} reset(): ")
+    assert not bool(env.time_out_buf.any()), "BaseTask.reset must not leave time-out flags behind"
+    env.reset_idx(torch.arange(0, device="cuda"))
+    for s in range(7, 10):
+        a = case.tape.actions[s % case.tape.frames]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} step {s} after reset(): ")
+
+
 def test_trajectory_env_reset_then_steps_are_finite():
     """AnymalTrajectory.reset() (BaseTask.reset: reset all, one zero-action step) followed by steps never produces NaNs — the
     generators are reset before the first generator step (a never-reset generator evaluates 0/0, rom_dynamics.py:552)."""

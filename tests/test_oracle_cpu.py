@@ -132,6 +132,66 @@ def test_port_tracks_unmodified_reference(name):
 
 
 @pytest.mark.reference
+@pytest.mark.parametrize("name", ["flat_pd_upstream", "rough_lstm_allterms"])
+def test_port_external_reset_tracks_unmodified_reference(name):
+    """LeggedRobot.reset_idx / BaseTask.reset called from outside step() (legged_robot.py:147-187, base_task.py:111-119): the
+    port's external reset against the reference's own methods — state right after the reset and over the steps that follow."""
+    from oracle import ref_harness as H
+    N = 96
+    case = LC.build_case(name, N)
+    task, rs, cr, lstm, over = LC.CASES[name]
+    env = H.make_reference_anymal(task, N, case.tape, seed=case.seed, reward_scales=rs, command_ranges=cr, use_actuator_network=lstm,
+                                  heightfield=case.terrain["height_samples"] if case.rough else None,
+                                  terrain_origins=case.terrain["terrain_origins"] if case.rough else None,
+                                  episode_lengths=case.ep, overrides=over)
+    if case.rough:
+        env.terrain_levels[:] = case.terrain["terrain_levels"]
+        env.terrain_types[:] = case.terrain["terrain_types"]
+        env.env_origins[:] = case.terrain["env_origins"]
+    port, phys = LC.make_port(case)
+
+    def check(tag):
+        assert_exact(port.reset_buf, env.reset_buf.bool(), tag + "reset")
+        assert_exact(port.time_out_buf, env.time_out_buf.bool(), tag + "time_out")
+        assert_exact(port.episode_length_buf, env.episode_length_buf, tag + "ep_len")
+        for k in ("commands", "root_states", "dof_state", "feet_air_time", "last_actions", "last_dof_vel", "obs_buf", "rew_buf"):
+            assert_close(getattr(port, k), getattr(env, k), 1.0, tag + k)
+        for k in env.episode_sums:
+            assert_close(port.episode_sums[k], env.episode_sums[k], 1.0, tag + "sum_" + k)
+        assert list(env.extras["episode"]) == list(port.extras["episode"])
+        for k in env.extras["episode"]:
+            assert_close(port.extras["episode"][k], env.extras["episode"][k], 1.0, tag + "extras " + k)
+        if case.rough:
+            assert_exact(port.terrain_levels, env.terrain_levels, tag + "levels")
+            assert_close(port.env_origins, env.env_origins, 1.0, tag + "origins")
+        if lstm:
+            assert_close(port.sea_hidden_state, env.sea_hidden_state, 1.0, tag + "h")
+
+    for s in range(5):
+        a = case.tape.actions[s % case.tape.frames]
+        env.step(a.clone())
+        port.step(a.clone(), phys)
+    ids = torch.arange(0, N, 3)
+    env.reset_idx(ids)
+    port.reset_idx(ids)
+    check("partial reset: ")
+    assert bool(port.reset_buf[ids].all())
+    for s in range(5, 8):
+        a = case.tape.actions[s % case.tape.frames]
+        env.step(a.clone())
+        port.step(a.clone(), phys)
+        check(f"step {s} after the partial reset: ")
+    o1, _ = env.reset()
+    o2, _ = port.reset(phys)
+    assert_close(o2, o1, 1.0, "reset() obs")
+    check("reset(): ")
+    assert not bool(env.time_out_buf.any()), "BaseTask.reset leaves no time-out flag behind"
+    env.reset_idx(torch.arange(0))
+    port.reset_idx(torch.arange(0))
+    check("empty reset: ")
+
+
+@pytest.mark.reference
 @pytest.mark.parametrize("over", [{}, dict(prob_stationary=0.05, t_low=0.2, t_high=0.5), dict(randomize_rom_distance=False)])
 def test_rom_port_tracks_unmodified_reference(over):
     """oracle/port_rom.py vs the reference's CustomSim/TrajectoryGenerator/DoubleSingleTracking, every step."""
