@@ -47,6 +47,10 @@ typedef struct B200LeggedParams {
     float noise_lin_vel, noise_ang_vel, noise_gravity, noise_dof_pos, noise_dof_vel, noise_height;
     int32_t heading_command, resample_steps;
     float cmd_lo[4], cmd_span[4]; /* lin_vel_x, lin_vel_y, ang_vel_yaw, heading: lower and (upper - lower) */
+    /* the ranges the RESET resample of this launch draws from: equal to cmd_lo / cmd_span except on the step on which the
+     * command curriculum advances (legged_robot.py:360-363 runs between the periodic resample and reset_idx); max_command_x =
+     * extras["episode"]["max_command_x"] (:183-184), written to extras_out[num_sum_rows + 2] when an env reset */
+    float cmd_lo_reset[4], cmd_span_reset[4], max_command_x;
     int32_t push_robots, push_time;
     float push_lo, push_span;
     float max_episode_length, max_episode_length_s;
@@ -115,6 +119,10 @@ typedef struct B200LeggedBuffers {
     const float* trajectory;     /* [N, horizon, n] self.trajectory = traj_gen.get_trajectory() of this step (:410) */
     float* prev_error;           /* [N, n] */
     float* time_until_next_push; /* [N] */
+    /* optional [num_sum_rows + 2] doubles: the RAW statistics behind extras_out of this step — per-term sums over the envs that reset,
+     * sum of terrain levels over all envs, number of resets (0 when none) — so that env shards can all-reduce (sum, count) pairs and
+     * log the same means a single process over all envs would (legged_robot.py:175-182) */
+    double* extras_raw;
 } B200LeggedBuffers;
 
 /* LeggedRobot._compute_torques (legged_robot.py:389-413), optionally fused with the action clip of

@@ -31,7 +31,7 @@ class LeggedParamsPOD(C.Structure):
         ("noise_lin_vel", f32), ("noise_ang_vel", f32), ("noise_gravity", f32), ("noise_dof_pos", f32),
         ("noise_dof_vel", f32), ("noise_height", f32),
         ("heading_command", i32), ("resample_steps", i32),
-        ("cmd_lo", f32 * 4), ("cmd_span", f32 * 4),
+        ("cmd_lo", f32 * 4), ("cmd_span", f32 * 4), ("cmd_lo_reset", f32 * 4), ("cmd_span_reset", f32 * 4), ("max_command_x", f32),
         ("push_robots", i32), ("push_time", i32), ("push_lo", f32), ("push_span", f32),
         ("max_episode_length", f32), ("max_episode_length_s", f32),
         ("reward_scale", f32 * NUM_TERMS), ("sum_row", i32 * NUM_TERMS),
@@ -56,7 +56,7 @@ _BUF_FIELDS = ["root_states", "dof_state", "contact_forces", "actions", "torques
                "time_out_buf", "rew_buf", "episode_sums", "obs_buf", "base_lin_vel", "base_ang_vel",
                "projected_gravity", "measured_heights", "height_samples", "env_origins", "terrain_levels",
                "terrain_types", "terrain_origins", "lstm_h", "lstm_c", "extras_out", "ws_sums", "ws_counter", "step_counter",
-               "trajectory", "prev_error", "time_until_next_push"]
+               "trajectory", "prev_error", "time_until_next_push", "extras_raw"]
 
 
 class LeggedBuffersPOD(C.Structure):
@@ -339,6 +339,8 @@ def fill_params(p, num_sum_rows, sum_row, zero_lstm_on_reset=False) -> LeggedPar
     s.heading_command, s.resample_steps = int(p.heading_command), p.resample_steps
     for i, r in enumerate((p.cmd_lin_vel_x, p.cmd_lin_vel_y, p.cmd_ang_vel_yaw, p.cmd_heading)):
         s.cmd_lo[i], s.cmd_span[i] = r[0], r[1] - r[0]
+        s.cmd_lo_reset[i], s.cmd_span_reset[i] = r[0], r[1] - r[0]
+    s.max_command_x = p.cmd_lin_vel_x[1]
     s.push_robots, s.push_time = int(p.push_robots), int(p.push_time)
     s.push_lo, s.push_span = -p.max_push_vel, p.max_push_vel - (-p.max_push_vel)
     s.max_episode_length, s.max_episode_length_s = p.max_episode_length, p.max_episode_length_s

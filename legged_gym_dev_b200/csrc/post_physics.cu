@@ -121,12 +121,14 @@ __device__ __forceinline__ void resample_commands(const B200LeggedParams& p, con
                                                   float& c0, float& c1, float& c2, float& c3) {
     // legged_robot.py:365-387
     const uint4 w = rng.words(site, 0);
-    c0 = affine_rn(p.cmd_span[0], philox::u01(w.x), p.cmd_lo[0]);
-    c1 = affine_rn(p.cmd_span[1], philox::u01(w.y), p.cmd_lo[1]);
+    const float* lo = site == philox::CMD_RESET ? p.cmd_lo_reset : p.cmd_lo;       // differ only while the command curriculum advances
+    const float* span = site == philox::CMD_RESET ? p.cmd_span_reset : p.cmd_span;
+    c0 = affine_rn(span[0], philox::u01(w.x), lo[0]);
+    c1 = affine_rn(span[1], philox::u01(w.y), lo[1]);
     if (p.heading_command)
-        c3 = affine_rn(p.cmd_span[3], philox::u01(w.z), p.cmd_lo[3]);
+        c3 = affine_rn(span[3], philox::u01(w.z), lo[3]);
     else
-        c2 = affine_rn(p.cmd_span[2], philox::u01(w.z), p.cmd_lo[2]);
+        c2 = affine_rn(span[2], philox::u01(w.z), lo[2]);
 #if PP_SQNORM
     const float m = sq2_rn(c0, c1) > thr.gt02 ? 1.0f : 0.0f;
 #else
@@ -931,6 +933,8 @@ __global__ void extras_finalize_kernel(const __grid_constant__ B200LeggedParams 
     if (tid < K && cnt > 0.0) b.extras_out[tid] = static_cast<float>(mine / cnt) / p.max_episode_length_s;
     if (tid == K && cnt > 0.0) b.extras_out[K] = static_cast<float>(mine / static_cast<double>(p.num_envs));
     if (tid == K + 1) b.extras_out[K + 1] = static_cast<float>(cnt);
+    if (tid == K + 2 && cnt > 0.0) b.extras_out[K + 2] = p.max_command_x;   // legged_robot.py:183-184
+    if (b.extras_raw && tid < K + 2) b.extras_raw[tid] = mine;
     if (tid < K + 2) b.ws_sums[tid] = 0.0;
     if (tid == 0 && b.step_counter) *b.step_counter += 1;
 }

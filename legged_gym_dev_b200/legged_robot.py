@@ -98,6 +98,34 @@ class LeggedRobot:
         self.custom_origins = p.custom_origins
         self.command_ranges = dict(lin_vel_x=p.cmd_lin_vel_x, lin_vel_y=p.cmd_lin_vel_y, ang_vel_yaw=p.cmd_ang_vel_yaw,
                                    heading=p.cmd_heading)
+        # the fork's command curriculum (legged_robot.py:822-833): nominal ranges scaled by curriculum.commands[state]
+        self.nominal_command_ranges = {k: list(v) for k, v in self.command_ranges.items()}
+        self.nominal_push_time, self.nominal_max_push_vel = p.push_time, p.max_push_vel
+        self.curriculum_state = 0
+        if p.use_curriculum:
+            self.update_command_curriculum()
+
+    def _curriculum_ranges(self, ind):
+        c = self.params.curriculum_commands[ind]
+        return {k: [v * c if k != "heading" else v for v in val] for k, val in self.nominal_command_ranges.items()}   # :502-503
+
+    def update_command_curriculum(self):                                  # legged_robot.py:488-506
+        p, ind = self.params, self.curriculum_state
+        self.command_ranges = self._curriculum_ranges(ind)
+        r = self.command_ranges
+        p.cmd_lin_vel_x, p.cmd_lin_vel_y, p.cmd_ang_vel_yaw, p.cmd_heading = r["lin_vel_x"], r["lin_vel_y"], r["ang_vel_yaw"], r["heading"]
+        self.push_time = self.nominal_push_time * p.curriculum_push_time[ind]                       # :505 (pushes cannot run: params.py)
+        pod = getattr(self, "_pod", None)
+        if pod is not None:
+            self._write_command_ranges(pod, r, reset_only=False)
+
+    @staticmethod
+    def _write_command_ranges(pod, r, reset_only):
+        for i, k in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw", "heading")):
+            pod.cmd_lo_reset[i], pod.cmd_span_reset[i] = r[k][0], r[k][1] - r[k][0]
+            if not reset_only:
+                pod.cmd_lo[i], pod.cmd_span[i] = r[k][0], r[k][1] - r[k][0]
+        pod.max_command_x = r["lin_vel_x"][1]
 
     # ------------------------------------------------------------------ buffers (base_task.py:70-79, legged_robot.py:533-603)
     def _init_buffers(self):
@@ -168,8 +196,9 @@ class LeggedRobot:
         sum_row = [-1] * len(REWARD_TERMS)
         for i, n in enumerate(p.active_terms):
             sum_row[TERM_ID[n]] = i
-        self._extras_out = torch.zeros(K + 2, dtype=torch.float, device=self.device)
+        self._extras_out = torch.zeros(K + 3, dtype=torch.float, device=self.device)
         self._ws_sums = torch.zeros(K + 2, dtype=torch.double, device=self.device)
+        self._extras_raw = torch.zeros(K + 2, dtype=torch.double, device=self.device)   # (sums over reset envs, level sum, reset count) of the last step
         self._ws_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         self._pod = _lib.fill_params(p, K, sum_row, zero_lstm_on_reset=self._has_actuator_state())
         self._ptr_actions, self._ptr_torques = self.actions.data_ptr(), self.torques.data_ptr()
@@ -178,6 +207,8 @@ class LeggedRobot:
         ep = {"rew_" + n: self._extras_out[i] for i, n in enumerate(p.active_terms)}
         if p.terrain_curriculum:
             ep["terrain_level"] = self._extras_out[K]
+        if p.use_curriculum:
+            ep["max_command_x"] = self._extras_out[K + 2]                 # legged_robot.py:183-184
         self.extras["episode"] = ep
         self.extras["num_resets"] = self._extras_out[K + 1]
         if p.send_timeouts:
@@ -261,7 +292,7 @@ class LeggedRobot:
                      height_samples=self.height_samples, env_origins=self.env_origins, terrain_levels=self.terrain_levels,
                      terrain_types=self.terrain_types, terrain_origins=self.terrain_origins,
                      lstm_h=getattr(self, "sea_hidden_state", None), lstm_c=getattr(self, "sea_cell_state", None),
-                     extras_out=self._extras_out, ws_sums=self._ws_sums, ws_counter=self._ws_counter)
+                     extras_out=self._extras_out, ws_sums=self._ws_sums, ws_counter=self._ws_counter, extras_raw=self._extras_raw)
             for k, v in t.items():
                 if v is not None:
                     _lib.require_cuda(v, k)
@@ -275,17 +306,29 @@ class LeggedRobot:
     def post_physics_step(self):                                          # legged_robot.py:106-134, fused
         self.physics.refresh()
         self.common_step_counter += 1
+        p = self.params
+        advance = (p.use_curriculum and self.curriculum_state < len(p.curriculum_steps) and
+                   self.common_step_counter % p.curriculum_steps[self.curriculum_state] == 0)                 # legged_robot.py:360-363
+        if advance:
+            # the callback advances the curriculum AFTER this step's periodic resample and BEFORE its reset_idx: inside the fused
+            # launch only the reset resample (and extras["episode"]["max_command_x"]) sees the new ranges
+            self.curriculum_state += 1
+            self._write_command_ranges(self._pod, self._curriculum_ranges(self.curriculum_state), reset_only=True)
         ev = self._event_start()
         st = self._stream if self._stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         rc = self.lib.b200gym_post_physics(self._pod, self._buffers(), self.common_step_counter, self.env_id_offset, st)
         if rc:
             _lib.check(rc, "post_physics")
         self._event_end("post_physics", ev)
+        if advance:
+            self.update_command_curriculum()
         self.physics.commit_resets(self.reset_buf)
 
     def use_device_step_counter(self):
         """Keeps the step counter the kernels see in device memory (advanced by the kernels themselves), so that a
         sequence of env steps can be captured in a CUDA graph and replayed (legged_gym_dev_b200.graphs)."""
+        if self.params.use_curriculum:
+            raise RuntimeError("the command curriculum advances on the host (legged_robot.py:360-363): its steps cannot be replayed from a CUDA graph")
         if getattr(self, "_step_dev", None) is None:
             self._step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._step_dev.fill_(self.common_step_counter + 1)
@@ -350,6 +393,18 @@ class LeggedRobot:
 
     def render(self, sync_frame_time=True):
         return None
+
+    # ------------------------------------------------------------------ reward statistics across env shards
+    def episode_stats_from_raw(self, raw, total_envs=None):
+        """extras["episode"] (legged_robot.py:175-182) from RAW per-step statistics `raw` [..., K + 2] = (per-term sums over the envs
+        that reset, sum of terrain levels, number of resets), e.g. `_extras_raw` rows summed over the ranks by ONE all-reduce: the
+        means a single process over all envs would log.  Rows without a reset give NaN (nothing to average)."""
+        p, K = self.params, len(self.params.active_terms)
+        cnt = raw[..., K + 1]
+        out = {"rew_" + n: raw[..., i] / cnt / p.max_episode_length_s for i, n in enumerate(p.active_terms)}
+        if p.terrain_curriculum:
+            out["terrain_level"] = raw[..., K] / float(total_envs if total_envs is not None else self.num_envs)
+        return out
 
 
 def cfg_num_commands(cfg):

@@ -162,7 +162,7 @@ class LeggedRobotTrajectory(LeggedRobot):
         rc = self.lib.b200gym_post_physics(self._pod, self._buffers(), self.common_step_counter, self.env_id_offset, st)
         if rc:
             _lib.check(rc, "post_physics")
-        K = self._extras_out.numel() - 2
+        K = self._extras_out.numel() - 3
         rc = self.lib.b200gym_rom_reset_from_root(g._p, g._s, self.reset_buf.data_ptr(), self.physics.root_states.data_ptr(), 13,
                                                   self._extras_out[K + 1:].data_ptr(), self.env_id_offset, st)   # :224, :248-253
         if rc:

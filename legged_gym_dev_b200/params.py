@@ -91,6 +91,12 @@ class LeggedParams:
     cmd_lin_vel_y: List[float] = field(default_factory=lambda: [0.0, 0.0])
     cmd_ang_vel_yaw: List[float] = field(default_factory=lambda: [0.0, 0.0])
     cmd_heading: List[float] = field(default_factory=lambda: [0.0, 0.0])
+    # command / push curriculum of the fork's base env (legged_robot.py:360-363, 488-506; legged_robot_config.py:178-185)
+    use_curriculum: bool = False
+    curriculum_steps: List[int] = field(default_factory=list)
+    curriculum_commands: List[float] = field(default_factory=list)
+    curriculum_push_magnitude: List[float] = field(default_factory=list)
+    curriculum_push_time: List[float] = field(default_factory=list)
     # pushes
     push_robots: bool = True
     push_time: int = 750
@@ -211,7 +217,20 @@ def flatten_legged_cfg(cfg, sim_dt, dof_names, num_envs=None, feet_indices=None,
         r = c.ranges
         p.cmd_lin_vel_x, p.cmd_lin_vel_y = [float(v) for v in r.lin_vel_x], [float(v) for v in r.lin_vel_y]
         p.cmd_ang_vel_yaw, p.cmd_heading = [float(v) for v in r.ang_vel_yaw], [float(v) for v in r.heading]
-        p.max_push_vel = float(getattr(d, "max_push_vel", getattr(d, "max_push_vel_xy", 1.0)))
+        mv = getattr(d, "max_push_vel", getattr(d, "max_push_vel_xy", 1.0))
+        p.max_push_vel = float(mv[0] if isinstance(mv, (list, tuple)) else mv)   # a list only with the curriculum (:504), where pushes cannot run
+        cur = getattr(cfg, "curriculum", None)
+        p.use_curriculum = bool(getattr(cur, "use_curriculum", False))   # annotation-only in the fork's base cfg (:179): absent = off
+        if p.use_curriculum:
+            p.curriculum_steps = [int(v) for v in cur.curriculum_steps]
+            p.curriculum_commands = [float(v) for v in cur.commands]
+            p.curriculum_push_magnitude = [float(v) for v in cur.push.magnitude]
+            p.curriculum_push_time = [float(v) for v in cur.push.time]
+            if p.push_robots:
+                # update_command_curriculum turns max_push_vel into a list (:504) and _push_robots negates it (:459): the reference
+                # raises this TypeError on its first push; raised here at construction instead of mid-run
+                raise TypeError("bad operand type for unary -: 'list' (legged_robot.py:459: curriculum.use_curriculum with "
+                                "domain_rand.push_robots cannot run in the reference; set push_robots = False)")
     else:   # LeggedRobotTrajectoryCfg has no `commands`; pushes use max_push_vel_xy and per-env timers
         p.traj_mode = True
         p.heading_command, p.resample_steps = False, 1

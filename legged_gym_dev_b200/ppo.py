@@ -563,6 +563,7 @@ class OnPolicyRunner:
         self.alg.init_storage(env.num_envs, self.num_steps_per_env, [env.num_obs], [env.num_privileged_obs], [env.num_actions])
         self.alg.env_id_offset = int(getattr(env, "env_id_offset", 0))   # env shards draw distinct action noise
         self.tot_timesteps, self.tot_time, self.current_learning_iteration = 0, 0, 0
+        self.log_episode_stats = False
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
         env = self.env
@@ -573,16 +574,26 @@ class OnPolicyRunner:
         critic_obs = priv if priv is not None else obs
         self.alg.actor_critic.train()
         infos_out = []
+        # reward statistics (rsl_rl's ep_infos, logged when a log_dir / callback is given): the RAW (sum, count) rows of every env step
+        # are kept on the device and summed over the env shards by ONE all-reduce per iteration, so every rank logs the means a single
+        # process over all envs would (legged_robot.py:175-182; SURVEY.md 8e "reward statistics")
+        raw = getattr(env, "_extras_raw", None)
+        log_stats = raw is not None and (self.log_dir is not None or self.wandb_callback is not None or self.log_episode_stats)
+        hist = torch.zeros(self.num_steps_per_env, raw.numel(), dtype=torch.double, device=self.device) if log_stats else None
         for it in range(self.current_learning_iteration, self.current_learning_iteration + num_learning_iterations):
             with torch.inference_mode():
-                for _ in range(self.num_steps_per_env):
+                for t in range(self.num_steps_per_env):
                     actions = self.alg.act(obs, critic_obs)
                     obs, priv, rewards, dones, infos = env.step(actions)
                     critic_obs = priv if priv is not None else obs
                     self.alg.process_env_step(rewards, dones, infos)
+                    if log_stats:
+                        hist[t].copy_(raw)
                 self.alg.compute_returns(critic_obs)
             mean_value_loss, mean_surrogate_loss = self.alg.update()
             infos_out.append(dict(it=it, mean_value_loss=mean_value_loss, mean_surrogate_loss=mean_surrogate_loss))
+            if log_stats:
+                infos_out[-1]["episode"] = self._episode_stats(hist)
             if self.wandb_callback is not None:
                 self.wandb_callback(dict(mean_value_loss=float(mean_value_loss), mean_surrogate_loss=float(mean_surrogate_loss), it=it),
                                     float(self.alg.learning_rate), self.alg.actor_critic.std.mean().item(),
@@ -591,6 +602,19 @@ class OnPolicyRunner:
                 self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
         self.current_learning_iteration += num_learning_iterations
         return infos_out
+
+    def _episode_stats(self, hist):
+        """Mean over the env steps of the rollout that saw a reset of the per-step means over the reset envs (rsl_rl's logger:
+        torch.mean over the collected ep_infos), with the (sum, count) rows all-reduced over the env shards first."""
+        total = self.env.num_envs
+        if _dist_ready():
+            import torch.distributed as dist
+            hist = hist.clone()
+            dist.all_reduce(hist)
+            total *= dist.get_world_size()
+        stats = self.env.episode_stats_from_raw(hist, total_envs=total)
+        seen = hist[:, -1] > 0
+        return {k: (v[seen].mean() if k != "terrain_level" else v.mean()) for k, v in stats.items()}
 
     def save(self, path, infos=None):
         torch.save({"model_state_dict": self.alg.actor_critic.state_dict(), "optimizer_state_dict": self.alg.optimizer.state_dict(),

@@ -86,10 +86,20 @@ class LeggedPort:
             self.height_points[:, :, 1] = gy.flatten()
         self.noise_scale_vec = nv
         self.commands_scale = t([p.obs_lin_vel, p.obs_lin_vel, p.obs_ang_vel])
+        # command curriculum of the fork (legged_robot.py:822-833, 488-506)
+        self.nominal_command_ranges = dict(lin_vel_x=list(p.cmd_lin_vel_x), lin_vel_y=list(p.cmd_lin_vel_y),
+                                           ang_vel_yaw=list(p.cmd_ang_vel_yaw), heading=list(p.cmd_heading))
+        self.command_ranges, self.curriculum_state = self.nominal_command_ranges, 0
+        if getattr(p, "use_curriculum", False):
+            self.update_command_curriculum()
         if lstm is not None:                                              # anymal.py:62-69
             self.lstm = {k: torch.as_tensor(v, **f32) for k, v in lstm.items()}
             self.sea_hidden_state = torch.zeros(2, N * D, 8, **f32)
             self.sea_cell_state = torch.zeros(2, N * D, 8, **f32)
+
+    def update_command_curriculum(self):                                  # legged_robot.py:488-506
+        c = self.p.curriculum_commands[self.curriculum_state]
+        self.command_ranges = {k: [v * c if k != "heading" else v for v in val] for k, val in self.nominal_command_ranges.items()}
 
     # ---- randomness -----------------------------------------------------------------------------
     def _u(self, site, env_ids, ncols):
@@ -165,6 +175,10 @@ class LeggedPort:
         if p.push_robots and self.common_step_counter % p.push_time == 0:
             all_ids = torch.arange(self.N)
             self.root_states[:, 7:9] = self._uniform(-p.max_push_vel, p.max_push_vel, P.SITE_PUSH, all_ids, 2)
+        if getattr(p, "use_curriculum", False) and self.curriculum_state < len(p.curriculum_steps) and \
+                self.common_step_counter % p.curriculum_steps[self.curriculum_state] == 0:                   # :360-363
+            self.curriculum_state += 1
+            self.update_command_curriculum()
         # termination (:139-145)
         f = torch.norm(self.contact_forces[:, self.term, :], dim=-1)
         self.reset_buf = torch.any(f > 1.0, dim=1)
@@ -187,14 +201,15 @@ class LeggedPort:
         p = self.p
         if len(ids) == 0 and self.rng == "philox":
             return
-        rx, ry = p.cmd_lin_vel_x, p.cmd_lin_vel_y
+        cr = self.command_ranges
+        rx, ry = cr["lin_vel_x"], cr["lin_vel_y"]
         self.commands[ids, 0] = self._uniform(rx[0], rx[1], site, ids, 3, 0).squeeze(1)
         self.commands[ids, 1] = self._uniform(ry[0], ry[1], site, ids, 3, 1).squeeze(1)
         if p.heading_command:
-            r = p.cmd_heading
+            r = cr["heading"]
             self.commands[ids, 3] = self._uniform(r[0], r[1], site, ids, 3, 2).squeeze(1)
         else:
-            r = p.cmd_ang_vel_yaw
+            r = cr["ang_vel_yaw"]
             self.commands[ids, 2] = self._uniform(r[0], r[1], site, ids, 3, 2).squeeze(1)
         self.commands[ids, :2] *= (torch.norm(self.commands[ids, :2], dim=1) > 0.2).unsqueeze(1)
 
@@ -322,6 +337,8 @@ class LeggedPort:
             self.episode_sums[k][ids] = 0.0
         if p.terrain_curriculum:
             self.extras["episode"]["terrain_level"] = torch.mean(self.terrain_levels.float())
+        if getattr(p, "use_curriculum", False):
+            self.extras["episode"]["max_command_x"] = self.command_ranges["lin_vel_x"][1]                     # :183-184
         if p.send_timeouts:
             self.extras["time_outs"] = self.time_out_buf
         if p.use_actuator_network:

@@ -26,6 +26,11 @@ CASES = {
     "rough_lstm_allterms": ("anymal_c_rough", ALL_REWARD_SCALES, configs.UPSTREAM_COMMAND_RANGES, True,
                             {"rewards.only_positive_rewards": False, "domain_rand.push_interval_s": 0.1}),
     "rough_pd_shipped": ("anymal_c_rough", None, None, False, {}),
+    # the fork's command curriculum of the base env (legged_robot.py:360-363, 488-506): advances at steps 5 and 9; pushes off (the
+    # reference's _push_robots cannot run with it, :459 negates a list)
+    "flat_cmd_curriculum": ("anymal_c_flat", configs.UPSTREAM_REWARD_SCALES, configs.UPSTREAM_COMMAND_RANGES, False,
+                            {"curriculum.use_curriculum": True, "curriculum.curriculum_steps": [5, 9], "domain_rand.push_robots": False,
+                             "domain_rand.max_push_vel": [1.0, 1.0], "commands.resampling_time": 0.1}),
     # AnymalTrajectory (legged_robot_trajectory.py); frequent per-env pushes so the timers fire in a short test
     "traj_flat_allterms": ("anymal_c_flat_trajectory", configs.TRAJECTORY_ALL_REWARD_SCALES, None, False,
                            {"domain_rand.time_between_pushes": [0.05, 0.3]}),

@@ -81,7 +81,7 @@ def test_cfg_tables_match_reference_objects():
 
 @pytest.mark.reference
 @pytest.mark.parametrize("name", ["flat_pd_upstream", "flat_lstm_shipped", "flat_allterms_v", "flat_heading_nonoise",
-                                  "rough_lstm_allterms", "rough_pd_shipped"])
+                                  "rough_lstm_allterms", "rough_pd_shipped", "flat_cmd_curriculum"])
 def test_port_tracks_unmodified_reference(name):
     """The travelling restatement vs the reference's own code, every step, same Philox stream."""
     from oracle import ref_harness as H

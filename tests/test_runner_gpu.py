@@ -58,3 +58,36 @@ def test_storage_holds_the_observation_each_action_was_computed_from():
         assert torch.equal(alg.storage.observations[t], fed[t])
         if t + 1 < 6:
             assert torch.equal(alg.storage.observations[t + 1], returned[t])
+
+
+def test_runner_episode_statistics_match_the_per_step_extras():
+    """OnPolicyRunner's logged reward statistics (rsl_rl: mean over the rollout's ep_infos) are rebuilt from the RAW (sum, count) rows
+    the step kernel leaves behind — the quantity the env shards all-reduce.  Single rank: they must equal the mean over the steps that
+    saw a reset of extras["episode"] itself."""
+    from types import SimpleNamespace
+    from legged_gym_dev_b200 import synthetic as S
+    from legged_gym_dev_b200.physics import ReplayPhysics
+    from legged_gym_dev_b200.task_registry import task_registry
+    N = 512
+    tape = S.make_state_tape(N, frames=8, seed=3, device="cuda")
+    args = SimpleNamespace(num_envs=N, sim_device="cuda", headless=True, physics_engine=None)
+    env, _ = task_registry.make_env("anymal_c_flat_b200", args=args, physics=ReplayPhysics(tape, device="cuda"))
+    env.episode_length_buf.copy_(S.make_episode_lengths(N, seed=1, device="cuda"))
+    runner, _ = task_registry.make_alg_runner(env, name="anymal_c_flat_b200", args=args)
+    runner.log_episode_stats = True
+    seen = []
+    orig_step = env.step
+
+    def step(a):
+        out = orig_step(a)
+        if float(env.extras["num_resets"]) > 0:
+            seen.append({k: float(v) for k, v in env.extras["episode"].items()})
+        return out
+    env.step = step
+    infos = runner.learn(num_learning_iterations=1)
+    assert seen, "no env reset during the rollout: the test tape must produce resets"
+    ep = infos[0]["episode"]
+    assert set(ep) == set(seen[0])
+    for k in ep:
+        want = sum(s[k] for s in seen) / len(seen)
+        assert abs(float(ep[k]) - want) <= 1e-5 * max(1.0, abs(want)), (k, float(ep[k]), want)

@@ -73,7 +73,17 @@ if world > 1 and getattr(alg, "_peer", None) is not None:
         print(f"peer reduce vs NCCL: max |diff| {err:.2e}, sumsq rel err {nerr:.1e}, bit-identical across ranks: {same_sum}")
     assert err < 1e-5 and nerr < 1e-12 and same_sum
     pr.buf.zero_()
+runner.log_episode_stats = True
 infos = runner.learn(num_learning_iterations=2, init_at_random_ep_len=True)
+if world > 1:
+    # reward statistics: every rank must log the same (all-reduced) means
+    ep = {k: float(v) for k, v in infos[-1]["episode"].items()}
+    allep = [None] * world
+    dist.all_gather_object(allep, ep)
+    if rank == 0:
+        same_stats = all(all(a[k] == allep[0][k] or (a[k] != a[k] and allep[0][k] != allep[0][k]) for k in ep) for a in allep)
+        print("episode statistics identical on all ranks:", same_stats, {k: round(v, 6) for k, v in list(ep.items())[:3]})
+        assert same_stats
 # time the update alone (rollout data of the last iteration is gone: refill the storage with one more rollout inside learn)
 torch.cuda.synchronize()
 import time
