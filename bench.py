@@ -248,25 +248,55 @@ def e2e_run(num_envs, frames, steps, warmup, device, rank, world):
     return dt, h2d, d2h
 
 
-def cpu_baseline(num_envs, steps, warmup=3):
-    """The oracle port (reference's torch ops, torch.rand like the reference) on the host cores."""
+def cpu_baseline(num_envs, steps, warmup=3, port_too=True):
+    """The reference's own LeggedRobot.step (unmodified sources staged in oracle/_ref by __graft_entry__.build(), driven through
+    oracle/ref_harness.py with the replay tape standing in for Isaac Gym and its stock torch.rand draws) on the host cores:
+    kind "reference".  The oracle port (oracle/port_legged.py) is timed beside it (`port_value`), and alone when no reference tree
+    is present (kind "port")."""
     import legged_case as LC
     torch.set_num_threads(os.cpu_count() or 1)
     case = LC.build_case("flat_pd_upstream", num_envs, frames=4, base_contact_prob=0.002)
-    port, phys = LC.make_port(case, rng="torch")
-    for s in range(warmup):
-        port.step(case.tape.actions[s % 4], phys)
-    t0 = time.perf_counter()
-    n = 0
-    while n < steps:
-        port.step(case.tape.actions[n % 4], phys)
-        n += 1
-        if time.perf_counter() - t0 > 60.0:
-            break
-    dt = time.perf_counter() - t0
-    return dict(value=num_envs * n / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"oracle/port_legged.py (torch CPU restatement of the reference), anymal_c_flat PD + upstream rewards, "
-                       f"{num_envs} envs x {n} steps, {dt:.2f} s", ms_per_step=1e3 * dt / n)
+
+    def timed(step):
+        for s in range(warmup):
+            step(case.tape.actions[s % 4])
+        t0 = time.perf_counter()
+        n = 0
+        while n < steps:
+            step(case.tape.actions[n % 4])
+            n += 1
+            if time.perf_counter() - t0 > 45.0:
+                break
+        return n, time.perf_counter() - t0
+
+    out, ref_err = None, None
+    try:
+        from oracle import ref_harness as H
+        if H.reference_available():
+            task, rs, cr, lstm, over = LC.CASES["flat_pd_upstream"]
+            env = H.make_reference_anymal(task, num_envs, case.tape, seed=case.seed, reward_scales=rs, command_ranges=cr,
+                                          use_actuator_network=lstm, episode_lengths=case.ep, overrides=over)
+            del env._shim_seed                      # stock code path: the reference draws from torch.rand itself
+            n, dt = timed(lambda a: env.step(a.clone()))
+            out = dict(value=num_envs * n / dt, unit=UNIT, cores=torch.get_num_threads(), kind="reference",
+                       sample=f"the reference's own LeggedRobot.step (legged_gym/envs/base/legged_robot.py:80-104, staged unmodified in "
+                              f"oracle/_ref), anymal_c_flat PD + upstream rewards, {num_envs} envs x {n} steps, {dt:.2f} s",
+                       ms_per_step=1e3 * dt / n)
+    except Exception as e:   # noqa: BLE001 — the port below still gives a CPU figure
+        ref_err = f"{type(e).__name__}: {e}"
+    if out is None or port_too:
+        port, phys = LC.make_port(case, rng="torch")
+        n, dt = timed(lambda a: port.step(a, phys))
+        pv = dict(value=num_envs * n / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                  sample=f"oracle/port_legged.py (torch CPU restatement of the reference), anymal_c_flat PD + upstream rewards, "
+                         f"{num_envs} envs x {n} steps, {dt:.2f} s", ms_per_step=1e3 * dt / n)
+        if out is None:
+            out = pv
+            if ref_err:
+                out["reference_error"] = ref_err
+        else:
+            out["port_value"] = pv["value"]
+    return out
 
 
 def main():
@@ -278,13 +308,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_baseline(args.cpu_envs, max(1, min(args.steps, 200)), warmup=max(3, min(args.warmup, 10)))
+        cb = cpu_baseline(args.cpu_envs, max(1, min(args.steps, 200)), warmup=max(3, min(args.warmup, 10)), port_too=False)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"anymal_c_flat env.step (4x PD torques + post_physics_step), upstream reward table, "
-                                       f"replayed synthetic state; reference's torch CPU path on a bounded sample of {args.cpu_envs} envs"},
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                                       f"replayed synthetic state; reference's torch CPU path ({cb['kind']}) on a bounded sample of {args.cpu_envs} envs"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "reference_error") if k in cb},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -387,7 +417,11 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if cb:
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "port_value", "reference_error") if k in cb}
+            if sweep and str(args.cpu_envs) in sweep:   # the GPU arm at the CPU arm's own size: a same-config ratio
+                g = sweep[str(args.cpu_envs)]
+                line["cpu_baseline"]["gpu_value_at_same_envs"] = g["graph_env_steps_per_s"]
+                line["cpu_baseline"]["same_config_ratio"] = g["graph_env_steps_per_s"] / cb["value"]
         if sweep:
             line["sweep"] = sweep
         if extra:

@@ -1,9 +1,10 @@
 """Executes the UNMODIFIED reference (/root/reference) as the pinning oracle.  TEST INFRASTRUCTURE.
 
-Container-only: /root/reference does not exist on the GPU box, so nothing imported by `-m gpu`
-tests, smoke() or bench.py may import this module.  It is used by oracle/make_golden.py (to write
-tests/golden/*.npz) and by tests/test_oracle_cpu.py (to validate the travelling restatements in
-oracle/port_*.py), both `-m "not gpu"` and both skipped when /root/reference is absent.
+/root/reference does not exist on the GPU box; there the byte-identical copy staged into the git-ignored oracle/_ref/ by
+oracle/stage_reference.py (run by __graft_entry__.build() in the container) is imported instead.  Users: oracle/make_golden.py
+(writes tests/golden/*.npz), tests/test_oracle_cpu.py (validates the travelling restatements in oracle/port_*.py; `-m "not gpu"`,
+skipped when no tree is present) and bench.py's CPU arm (`--impl reference`, `cpu_baseline`), which times the reference's own
+LeggedRobot.step.  No `-m gpu` test, smoke() or product module imports it.
 
 How: the absent heavy dependencies are replaced in sys.modules by mocks, except
 `isaacgym.torch_utils`, which is the restatement in oracle/isaacgym_restated.py; `Anymal.__init__` is
@@ -24,7 +25,9 @@ import torch
 from . import philox as P
 from . import rng_shim, isaacgym_restated
 
-REF_ROOT = "/root/reference"
+# the tree itself in the build container; on the GPU box the byte-identical copy staged by oracle/stage_reference.py (git-ignored)
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF_ROOT = "/root/reference" if os.path.isdir("/root/reference/legged_gym") else _STAGED
 
 
 def reference_available():
