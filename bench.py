@@ -202,6 +202,50 @@ def kernel_time(env, actions, steps, device):
     return sum(pp) / len(pp), sum(pd) / len(pd)
 
 
+def graph_kernel_times(env, actions, reps=20):
+    """Average duration of pd_torques and of the fused post-physics pass over BACK-TO-BACK launches replayed from a CUDA graph
+    (4 F torque launches, resp. F post-physics passes over the tape frames): the per-launch figure without the ~5 us of host
+    launch gap that event-bracketing a single eager launch includes — what matters below ~256 K envs per GPU."""
+    dev, F = env.device, len(actions)
+    ph = env.physics
+    env.use_device_step_counter()
+    out = {}
+    for name in ("pd_torques", "post_physics"):
+        def body():
+            for f in range(F):
+                if name == "pd_torques":
+                    for i in range(env.params.decimation):
+                        env._compute_torques(actions[f], write_clipped=(i == 0))
+                        ph.simulate(env.torques)
+                    ph.refresh()
+                else:
+                    env.post_physics_step()
+        c0, f0 = env.common_step_counter, ph.frame
+        env._stream = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        env.common_step_counter, ph.frame, ph.sub = c0, f0, 0
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize(dev)
+        n_launch = reps * F * (env.params.decimation if name == "pd_torques" else 1)
+        out[name + "_ms"] = a.elapsed_time(b) / n_launch
+    return out
+
+
 def e2e_run(num_envs, frames, steps, warmup, device, rank, world):
     """Public-API step with HOST-resident inputs: every sub-step's dof_state, the root/contact frame and the
     actions come from pinned host memory; obs/rew/reset are read back to pinned host memory every step."""
@@ -378,10 +422,15 @@ def main():
             tpp, tpd = kernel_time(e2, a2, 30, device)
             from legged_gym_dev_b200.graphs import GraphedReplay
             m3 = time_steps(e2, a2, 96, 8, 1, device, graphed=GraphedReplay(e2, a2))
+            gk = graph_kernel_times(e2, a2)   # back-to-back launches replayed from a graph: no host launch gap in the figure
             sweep[str(n)] = {"env_steps_per_s": n * 100 / (m2 * 1e-3), "ms_per_step": m2 / 100, "graph_ms_per_step": m3 / 96,
                              "graph_env_steps_per_s": n * 96 / (m3 * 1e-3), "post_physics_ms": tpp,
                              "post_physics_frac": ab["post_physics"] * n / (tpp * 1e-3) / 1e9 / peak,
-                             "pd_torques_ms": tpd, "pd_torques_frac": ab["pd_torques"] * n / (tpd * 1e-3) / 1e9 / peak}
+                             "pd_torques_ms": tpd, "pd_torques_frac": ab["pd_torques"] * n / (tpd * 1e-3) / 1e9 / peak,
+                             "post_physics_graph_ms": gk["post_physics_ms"], "pd_torques_graph_ms": gk["pd_torques_ms"],
+                             "post_physics_graph_frac": ab["post_physics"] * n / (gk["post_physics_ms"] * 1e-3) / 1e9 / peak,
+                             "pd_torques_graph_frac": ab["pd_torques"] * n / (gk["pd_torques_ms"] * 1e-3) / 1e9 / peak,
+                             "step_frac": ab["step"] * n * 96 / (m3 * 1e-3) / 1e9 / peak}
             del e2, tp2, a2
             torch.cuda.empty_cache()
     if world == 1 and not args.no_extra:
