@@ -39,6 +39,13 @@ class TaskRegistry:
         if args is not None and getattr(args, "num_envs", None) is not None:
             env_cfg.env.num_envs = args.num_envs                        # helpers.py:208-231 (update_cfg_from_args)
         device = getattr(args, "sim_device", None) or env_kwargs.pop("sim_device", "cuda")
+        # task_registry.py:89 set_seed(env_cfg.seed): the configured seed keys the env's Philox streams and torch's generator
+        # (policy initialisation; PPO.act's sample stream is keyed by torch.initial_seed())
+        seed = getattr(env_cfg, "seed", None)
+        if seed is not None and "seed" not in env_kwargs:
+            env_kwargs["seed"] = int(seed)
+            import torch
+            torch.manual_seed(int(seed))
         sim_params = SimpleNamespace(dt=env_cfg.sim.dt, use_gpu_pipeline=True)
         env = task_class(cfg=env_cfg, sim_params=sim_params, physics_engine=getattr(args, "physics_engine", None),
                          sim_device=device, headless=getattr(args, "headless", True), physics=physics, **env_kwargs)

@@ -396,6 +396,180 @@ def _install_trajectory_wrappers(ref, ltmod):
         LT.reset_traj = reset_traj
 
 
+
+# --------------------------------------------------------------------------------------------
+# HopperTrajectory as a whole env (hopper_trajectory.py), the only Hopper class of the fork that can run a full step
+# --------------------------------------------------------------------------------------------
+class _HopperReplayGym:
+    """`self.gym` of HopperTrajectory.step: simulate() + the three refresh calls of one sub-step replay a per-sub-step tape."""
+
+    def __init__(self, env, tape):
+        self.env, self.tape, self.frame, self.sub = env, tape, 0, 0
+
+    def simulate(self, sim):
+        t, f = self.tape, self.frame % self.tape.frames
+        self.env.dof_state.copy_(t.dof[f, self.sub].reshape(self.env.dof_state.shape))
+        self.env.root_states.copy_(t.root[f, self.sub])
+        self.env.contact_forces.copy_(t.contact[f, self.sub])
+        self.sub += 1
+        if self.sub == t.decimation:
+            self.sub, self.frame = 0, self.frame + 1
+
+    def __getattr__(self, name):
+        return lambda *a, **k: None
+
+
+def make_reference_hopper_trajectory(hp, dr, tape, time_until_next_push, episode_lengths=None):
+    """The reference's HopperTrajectory (hopper_trajectory.py) without Isaac Gym, configured from the port's parameter namespace `hp`
+    (oracle/port_hopper_env.hopper_env_params): the constructor is bypassed as for the ANYmal classes, its body is replayed by hand
+    with the reference's own methods (`_parse_cfg`, `_init_rom`, `_init_trajectory_generator`, `_init_buffers`,
+    `_prepare_reward_function`), the asset loader's outputs and the construction-time random multipliers (`_update_envs`) are inputs."""
+    ref = import_reference()
+    import legged_gym.envs.base.legged_robot_trajectory as ltmod
+    import legged_gym.envs.hopper.hopper_trajectory as ht
+    from legged_gym.envs.hopper.flat_trajectory.hopper_trajectory_config import HopperRoughTrajectoryCfg
+    from .port_hopper_env import TERMS
+    N = hp.num_envs
+    cfg = HopperRoughTrajectoryCfg()
+    cfg.env.num_envs, cfg.env.num_observations, cfg.env.episode_length_s = N, 14 + hp.generator["N"] * 2 + 4, hp.episode_length_s
+    for name in TERMS:
+        setattr(cfg.rewards.scales, name, hp.scales.get(name, 0.0))
+    rw = cfg.rewards
+    rw.only_positive_rewards, rw.tracking_sigma, rw.base_height_target = hp.only_positive_rewards, hp.tracking_sigma, hp.base_height_target
+    rw.soft_dof_vel_limit, rw.soft_torque_limit, rw.max_contact_force = hp.soft_dof_vel_limit, hp.soft_torque_limit, hp.max_contact_force
+    rw.reward_weighting = SimpleNamespace(position=hp.reward_weighting[0])
+    rw.differential_error.neg_slope, rw.differential_error.pos_slope = hp.diff_neg_slope, hp.diff_pos_slope
+    g = hp.raibert
+    rw.raibert.Kp, rw.raibert.Kv, rw.raibert.Kff = g["Kp"], g["Kv"], g["K_ff"]
+    rw.raibert.clip_pos, rw.raibert.clip_vel, rw.raibert.clip_ang = g["clip_pos"], g["clip_vel"], g["clip_ang"]
+    cfg.control.control_type, cfg.control.action_scale, cfg.control.decimation = hp.control_type, hp.action_scale, hp.decimation
+    cfg.control.zero_action = list(hp.reset["zero_action"])
+    cfg.normalization.clip_actions, cfg.normalization.clip_observations = hp.clip_actions, hp.obs["clip_observations"]
+    cfg.normalization.obs_scales.trajectory = list(hp.trajectory_scale)
+    cfg.noise.add_noise = hp.obs["add_noise"]
+    d = cfg.domain_rand
+    d.push_robots, d.time_between_pushes, d.max_push_vel = hp.push_robots, list(hp.time_between_pushes), list(hp.reset["max_push_vel"])
+    tgc = hp.generator
+    d.randomize_rom_distance, d.max_rom_dist, d.zero_rom_distance_likelihood = tgc["randomize_rom_distance"], list(tgc["max_rom_distance"]), tgc["zero_rom_dist_llh"]
+    cfg.curriculum.use_curriculum = False
+    cfg.rom.dt, cfg.rom.v_min, cfg.rom.v_max = tgc["rom_dt"], [-tgc["vel_max_rom"]] * 2, [tgc["vel_max_rom"]] * 2
+    tg = cfg.trajectory_generator
+    tg.weight_samp_cls, tg.N, tg.dN, tg.DN = tgc["weight_sampler"], tgc["N"], tgc["dN"], tgc["dN"]
+    tg.t_low, tg.t_high, tg.freq_low, tg.freq_high = tgc["t_low"], tgc["t_high"], tgc["freq_low"], tgc["freq_high"]
+    tg.prob_stationary, tg.seed = tgc["prob_stationary"], tgc["seed"]
+    isl, rc = cfg.init_state, hp.reset
+    isl.pos, isl.rot = list(rc["base_init_state"][:3]), list(rc["base_init_state"][3:7])
+    isl.lin_vel, isl.ang_vel = list(rc["base_init_state"][7:10]), list(rc["base_init_state"][10:13])
+    isl.randomize_yaw = rc["randomize_yaw"]
+    isl.default_dof_pos_noise_lower, isl.default_dof_pos_noise_upper = list(rc["dof_pos_noise"][0]), list(rc["dof_pos_noise"][1])
+    isl.default_dof_vel_noise_lower, isl.default_dof_vel_noise_upper = list(rc["dof_vel_noise"][0]), list(rc["dof_vel_noise"][1])
+    isl.default_root_pos_noise_lower, isl.default_root_pos_noise_upper = list(rc["root_pos_noise"][0]), list(rc["root_pos_noise"][1])
+    isl.default_root_vel_noise_lower, isl.default_root_vel_noise_upper = list(rc["root_vel_noise"][0]), list(rc["root_vel_noise"][1])
+    dof_names = ["foot_slide", "wheel1_rotation", "wheel2_rotation", "wheel3_rotation"]
+    isl.default_joint_angles = dict(zip(dof_names, rc["default_dof_pos"]))
+    cfg.control.stiffness = dict(zip(dof_names, hp.p_gains))
+    cfg.control.damping = dict(zip(dof_names, hp.d_gains))
+    cfg.control.wheel_spindown = dict(zip(dof_names[1:], hp.kd_spindown))
+    cfg.asset.wheel_speed_bounds = dict(zip(dof_names[1:], hp.wheel_speed_limits))
+    cfg.asset.rot_actuator, cfg.asset.torque_speed_bound_ratio = [list(r) for r in hp.rot_actuator], hp.torque_speed_bound_ratio
+
+    HT = ht.HopperTrajectory
+    env = HT.__new__(HT)
+    # --- head of HopperTrajectory.__init__ (:46-58) ---
+    env.nominal_spring_stiffness, env.nominal_spring_damping = cfg.asset.spring_stiffness, cfg.asset.spring_damping
+    env.nominal_spring_setpoint = cfg.control.foot_pos_des
+    env.zero_action = torch.repeat_interleave(torch.tensor(cfg.control.zero_action).reshape((1, -1)), N, 0).float()
+    # --- LeggedRobotTrajectory.__init__ (:65-88) with BaseTask.__init__ / create_sim replaced by their outputs ---
+    env.cfg = cfg
+    env.sim_params = SimpleNamespace(dt=hp.sim_dt, use_gpu_pipeline=False)
+    env.height_samples, env.debug_viz, env.init_done = None, False, False
+    env._parse_cfg(cfg)                                                   # reference code
+    env.device, env.headless, env.viewer, env.enable_viewer_sync, env.sim = "cpu", True, None, False, None
+    env.num_envs, env.num_obs = N, cfg.env.num_observations
+    env.num_privileged_obs, env.num_actions = None, 4
+    env.obs_buf = torch.zeros(N, env.num_obs, dtype=torch.float)
+    env.rew_buf = torch.zeros(N, dtype=torch.float)
+    env.reset_buf = torch.ones(N, dtype=torch.long)
+    env.episode_length_buf = torch.zeros(N, dtype=torch.long)
+    env.time_out_buf = torch.zeros(N, dtype=torch.bool)
+    env.privileged_obs_buf, env.extras, env.up_axis_idx = None, {}, 2
+    env.num_dof = env.num_dofs = 4
+    env.num_bodies, env.dof_names = hp.num_bodies, dof_names
+    env.feet_indices = torch.tensor([hp.foot_body], dtype=torch.long)
+    env.penalised_contact_indices = torch.tensor(hp.penalised_bodies, dtype=torch.long)
+    env.termination_contact_indices = torch.tensor(hp.termination_bodies, dtype=torch.long)
+    env.dof_pos_limits = torch.tensor(hp.dof_pos_limits, dtype=torch.float)
+    env.dof_vel_limits, env.torque_limits = torch.tensor(hp.dof_vel_limits), torch.tensor(hp.torque_limits)
+    env.base_init_state = torch.tensor(isl.pos + isl.rot + isl.lin_vel + isl.ang_vel, dtype=torch.float)
+    env._get_env_origins()                                                # reference code (plane: a grid)
+    env.max_rom_distance = torch.tensor(env.nominal_max_rom_distance)
+    env.zero_rom_dist_llh = env.nominal_zero_rom_distance_likelihood
+    for name in ("UniformWeightSamplerNoRamp", "UniformWeightSamplerNoExtreme"):
+        base = getattr(ref.dtl_utils, name)
+        cpu_cls = type(name, (base,), {"__init__": (lambda b: lambda self, dim=4, seed=42, device="cpu":
+                                                    b.__init__(self, dim=dim, seed=seed, device="cpu"))(base)})
+        setattr(ltmod, name, cpu_cls)
+    _install_rom_wrappers(ref)
+    holder = SimpleNamespace(seed=int(tg.seed), ctr=np.zeros(N, dtype=np.int64))
+    env._init_rom()                                                       # reference code
+    ref.rom_dynamics.TrajectoryGenerator._pending_holder = holder
+    try:
+        env._init_trajectory_generator()                                  # reference code
+    finally:
+        ref.rom_dynamics.TrajectoryGenerator._pending_holder = None
+    env.traj_gen._shim = holder
+    env._traj_shim = holder
+    handed = iter([tape.root[0, 0].clone(), tape.dof[0, 0].reshape(N * 4, 2).clone(), tape.contact[0, 0].reshape(N * hp.num_bodies, 3).clone()])
+    ltmod.gymtorch.wrap_tensor = lambda _t: next(handed)
+    env.gym = MagicMock()
+    env._init_buffers()                                                   # reference code (HopperTrajectory's, :415-434)
+    env._prepare_reward_function()                                        # reference code
+    env.init_done = True
+    env.time_until_next_push = time_until_next_push.clone().reshape(N, 1)   # the torch_rand_float draw of :85-88 as an input
+    # --- tail of HopperTrajectory.__init__ (:59-100) ---
+    env.raibert_Kp, env.raibert_Kv, env.raibert_Kff = rw.raibert.Kp, rw.raibert.Kv, rw.raibert.Kff
+    env.raibert_clip_pos, env.raibert_clip_vel, env.raibert_clip_ang = rw.raibert.clip_pos, rw.raibert.clip_vel, rw.raibert.clip_ang
+    env.use_raibert = False
+    env.foot_joint_index = torch.tensor([0])
+    env.wxyz_quat_inds = torch.tensor([6, 3, 4, 5])
+    env.wheel_joint_indices = torch.tensor([1, 2, 3])
+    env.actuator_transform = sys.modules["pytorch3d.transforms"].Rotate(torch.tensor(cfg.asset.rot_actuator), device="cpu")
+    env.torque_speed_bound_ratio = cfg.asset.torque_speed_bound_ratio
+    t = lambda v: torch.tensor(v, dtype=torch.float)
+    env.default_dof_pos_noise_lower, env.default_dof_pos_noise_upper = t(isl.default_dof_pos_noise_lower), t(isl.default_dof_pos_noise_upper)
+    env.default_dof_vel_noise_lower, env.default_dof_vel_noise_upper = t(isl.default_dof_vel_noise_lower), t(isl.default_dof_vel_noise_upper)
+    env.default_root_pos_noise_lower, env.default_root_pos_noise_upper = t(isl.default_root_pos_noise_lower), t(isl.default_root_pos_noise_upper)
+    env.default_root_vel_noise_lower, env.default_root_vel_noise_upper = t(isl.default_root_vel_noise_lower), t(isl.default_root_vel_noise_upper)
+    env.max_vel = t(d.max_push_vel)
+    for k, v in dr.items():                                               # what _update_envs (:372-413) draws at construction
+        setattr(env, k, v.clone())
+    env.gym = _HopperReplayGym(env, tape)
+    if episode_lengths is not None:
+        env.episode_length_buf[:] = episode_lengths
+    env._shim_seed = hp.seed
+    _install_trajectory_wrappers(ref, ltmod)
+    _install_hopper_wrappers(ht)
+    return env
+
+
+def _install_hopper_wrappers(ht):
+    HT = ht.HopperTrajectory
+    rng_shim.install()
+    all_ids = lambda s: np.arange(s.num_envs)
+    _wrap(HT, "_push_robots", lambda s, push_idx: (push_idx, s.common_step_counter, [(P.SITE_HOP_PUSH, 0)]))
+    _wrap(HT, "_reset_dofs", lambda s, env_ids: (env_ids, s.common_step_counter, [(P.SITE_HOP_DOF_POS, 0), (P.SITE_HOP_DOF_VEL, 0)]))
+    _wrap(HT, "_reset_root_states",
+          lambda s, env_ids: (env_ids, s.common_step_counter,
+                              [(P.SITE_HOP_ROOT_POS, 0)] + ([(P.SITE_HOP_YAW, 0)] if s.cfg.init_state.randomize_yaw else []) + [(P.SITE_HOP_ROOT_VEL, 0)]))
+    _wrap(HT, "compute_observations", lambda s: (all_ids(s), s.common_step_counter, [(P.SITE_OBS_NOISE, 0)]))
+
+    def pps_ctx(self):   # the push-timer redraw is inline in post_physics_step (:156-159): rows = the envs whose timer ran out, in order
+        ids = lambda call, hist: (self.time_until_next_push <= 0).reshape(-1).nonzero().flatten().numpy()
+        ev = lambda call, hist: self.common_step_counter
+        return (ids, ev, [(P.SITE_PUSH_TIMER, 0)])
+    _wrap(HT, "post_physics_step", pps_ctx)
+
+
 def synthetic_dof_limits():
     """The URDF carries effort/velocity limits (80 N m, 20 rad/s: anymal_c.urdf:540) but no position
     limits; synthetic +-(HAA 0.72, HFE/KFE 9.42*0.1...) style limits make the limit rewards non-trivial."""

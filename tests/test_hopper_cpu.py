@@ -225,3 +225,72 @@ def test_hopper_trajectory_groundwork_ports_match_reference_golden():
     hopper_traj_push(state, push.numpy(), RESET_CFG, seed=4, event=9)
     for k, v in state.items():
         assert_close(v, g[f"ht_reset_{k}"], 1.0, f"reset {k}")
+
+
+HOPPER_ALL_SCALES = dict(termination=-500.0, tracking_rom=6.0, ang_vel_xy=-0.01, orientation=-80.0, torques=-1e-6, dof_acc=-2.5e-8, unit_quat=-0.01,
+                         collision=-1.0, action_rate=-0.01, differential_error=10.0, raibert=-0.1, base_height=-1.0, dof_pos_limits=-10.0,
+                         dof_vel=-1e-6, dof_vel_limits=-0.5, feet_air_time=1.0, feet_contact_forces=-0.01, lin_vel_z=-2.0, stumble=-0.3,
+                         torque_limits=-0.02)
+HOPPER_ENV_CASES = {
+    "yaml_table": {},                                                                   # hopper_single_int.yaml's reward table
+    "all_terms_spindown": dict(scales=HOPPER_ALL_SCALES, control_type="orientation_spindown", penalised_bodies=[1, 2, 3], only_positive_rewards=True),
+    "nonoise_nopush": dict(obs=dict(add_noise=False), push_robots=False, reset=dict(randomize_yaw=False)),
+}
+
+
+def build_hopper_env_case(name, N, seed=3):
+    from oracle import port_hopper_env as E
+    hp = E.hopper_env_params(N, seed=seed, **HOPPER_ENV_CASES[name])
+    tape = E.make_hopper_tape(N, frames=8, seed=1)
+    dr = E.make_domain_rand(N, hp, seed=2)
+    g = torch.Generator().manual_seed(5)
+    tpush = 0.15 * torch.rand(N, generator=g)
+    ep = torch.randint(0, 1002, (N,), generator=g)
+    return hp, tape, dr, tpush, ep
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("name", list(HOPPER_ENV_CASES))
+def test_hopper_env_port_tracks_unmodified_reference(name):
+    """The whole HopperTrajectory env (hopper_trajectory.py: reset, step, post_physics_step with pushes, resets, rewards, observations)
+    executed UNMODIFIED through oracle/ref_harness.make_reference_hopper_trajectory against oracle/port_hopper_env.HopperTrajPort, every
+    step, same Philox streams."""
+    from oracle import ref_harness as H
+    from oracle import port_hopper_env as E
+    N = 64
+    hp, tape, dr, tpush, ep = build_hopper_env_case(name, N)
+    env = H.make_reference_hopper_trajectory(hp, dr, tape, tpush, episode_lengths=ep)
+    port = E.HopperTrajPort(hp, dr, tape, tpush, episode_length_buf=ep, env_origins=env.env_origins)
+    phys = E.HopperTapePhysics(tape)
+    assert [n for n in port.active if n != "termination"] == env.reward_names
+    o1, _ = env.reset()
+    o2, _ = port.reset(phys)
+    assert_close(o2, o1, 1.0, "reset() obs")
+    resets = pushes = 0
+    for s in range(24):
+        a = tape.actions[s % 8] * (300.0 if s == 3 else 1.0)
+        before = env.time_until_next_push.clone()
+        o1, _, r1, d1, x1 = env.step(a.clone())
+        o2, _, r2, d2, x2 = port.step(a.clone(), phys)
+        pushes += int((env.time_until_next_push.reshape(-1) > before.reshape(-1)).sum())
+        resets += int(d1.sum())
+        tag = f"{name} step {s}: "
+        assert_exact(d2, d1.bool(), tag + "reset")
+        assert_exact(port.time_out_buf, env.time_out_buf, tag + "time_out")
+        assert_exact(port.episode_length_buf, env.episode_length_buf, tag + "ep_len")
+        assert_exact(port.last_contacts, env.last_contacts, tag + "last_contacts")
+        assert_close(o2, o1, 1.0, tag + "obs")
+        assert_close(r2, r1, 1.0, tag + "rew")
+        assert_close(port.torques, env.torques, 300.0, tag + "torques")
+        for k in ("root_states", "trajectory", "prev_error", "last_actions", "last_dof_vel", "last_root_vel", "base_ang_vel", "base_lin_vel",
+                  "feet_air_time", "actions"):
+            assert_close(getattr(port, k), getattr(env, k), 1.0, tag + k)
+        assert_close(port.time_until_next_push, env.time_until_next_push.reshape(-1), 1.0, tag + "time_until_next_push")
+        assert_close(port.dof_state, env.dof_state.view(N, 4, 2), 1.0, tag + "dof_state")
+        for k in env.episode_sums:
+            assert_close(port.episode_sums[k], env.episode_sums[k], 1.0, tag + "sum_" + k)
+        if "episode" in x1:
+            assert list(x1["episode"]) == list(x2["episode"])
+            for k in x1["episode"]:
+                assert_close(x2["episode"][k], x1["episode"][k], 1.0, tag + "extras " + k)
+    assert resets > 0 and (pushes > 0 or not hp.push_robots)
