@@ -300,6 +300,10 @@ typedef struct B200HopperTorqueParams {
     float kd_spindown[3], wheel_speed_limits[3];       /* hopper.py:390-403 */
     float torque_limits[4];                            /* asset effort limits */
     float rot_actuator[9];                             /* cfg.asset.rot_actuator, row-major; tau = local_tau @ R (pytorch3d Rotate, :67,:221) */
+    /* 1: base_ang_vel = quat_rotate_inverse(root quaternion, root_states[:, 10:13]) is formed in the kernel from the root state the
+     * previous sub-step left (the refresh of hopper_trajectory.py:124-126) instead of being read from the buffer; the env's first
+     * sub-step of a step reads the buffer (it holds the pre-reset value, as in the reference) */
+    int32_t ang_vel_from_root, pad;
 } B200HopperTorqueParams;
 
 typedef struct B200HopperTorqueBuffers {
@@ -336,6 +340,61 @@ int b200gym_hopper_observations(const B200HopperObsParams* p, const float* root_
  * _reward_dof_acc = sum ((last_dof_vel - dof_vel) / dt)^2 over the wheels, _reward_unit_quat = (1 - |actions|)^2). */
 int b200gym_hopper_reward_terms(int32_t num_envs, float dt, const float* torques, const float* dof_state, const float* last_dof_vel,
                                 const float* actions, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY 8f row 3 — HopperTrajectory.post_physics_step (legged_gym/envs/hopper/hopper_trajectory.py:135-182) with the inherited
+ * check_termination / compute_reward / reset_idx of legged_gym/envs/base/legged_robot_trajectory.py (:194-272), the Hopper's
+ * _reset_dofs / _reset_root_states / _push_robots (:298-370), compute_observations (:255-282) + the observation clip of step
+ * (:128-129).  The caller runs the trajectory generator around it as for the ANYmal trajectory env: b200gym_rom_step before (the
+ * callback, legged_robot_trajectory.py:409-410), b200gym_rom_reset_from_root with reset_buf after (reset_traj, :248-253).
+ * Specification pinned to the unmodified class: oracle/port_hopper_env.py.
+ * ---------------------------------------------------------------------------------------------- */
+#define B200GYM_HOPPER_NUM_TERMS 20     /* alphabetical: action_rate, ang_vel_xy, base_height, collision, differential_error, dof_acc,
+                                           dof_pos_limits, dof_vel, dof_vel_limits, feet_air_time, feet_contact_forces, lin_vel_z, orientation,
+                                           raibert, stumble, torque_limits, torques, tracking_rom, unit_quat; termination last */
+#define B200GYM_HOPPER_TRAJ_NUM_OBS (14 + B200GYM_TRAJ_WIDTH + 4)
+typedef struct B200HopperEnvParams {
+    int32_t num_envs, num_bodies, foot_body, num_term, num_pen, num_sum_rows;
+    int32_t term_idx[8], pen_idx[8];
+    int32_t push_robots, only_positive, add_noise, randomize_yaw;
+    float dt, push_dt, max_episode_length, max_episode_length_s; /* push_dt = decimation * sim_dt (:148) */
+    float push_t_lo, push_t_span, max_push_vel[6];               /* time_between_pushes (:156-159), cfg.domain_rand.max_push_vel (:99) */
+    float reward_scale[B200GYM_HOPPER_NUM_TERMS];                 /* cfg scale * dt; 0 = inactive */
+    int32_t sum_row[B200GYM_HOPPER_NUM_TERMS];                    /* row of episode_sums [K, N] (alphabetical over the active names) or -1 */
+    float tracking_sigma, soft_dof_vel_limit, base_height_target, max_contact_force, traj_weight[2], diff_neg_slope, diff_pos_slope;
+    float raibert[6];                                             /* Kp, Kv, Kff, clip_pos, clip_vel, clip_ang (cfg.rewards.raibert) */
+    float dof_pos_lo[4], dof_pos_hi[4], dof_vel_limits[4];
+    float default_dof_pos[4], dof_pos_noise_lo[4], dof_pos_noise_span[4], dof_vel_noise_lo[4], dof_vel_noise_span[4]; /* span = fp32(upper) - fp32(lower) */
+    float base_init_state[13], root_pos_noise_lo[5], root_pos_noise_span[5], root_vel_noise_lo[6], root_vel_noise_span[6]; /* columns 2..6 / 7..12 */
+    float zero_action[4];
+    float z_pos_scale, lin_vel_scale, ang_vel_scale, dof_vel_scale, clip_obs, traj_scale[2], noise_scale_vec[14];
+    uint32_t seed_lo, seed_hi;
+} B200HopperEnvParams;
+typedef struct B200HopperEnvBuffers {
+    float* root_states;           /* [N, 13] in/out (pushes, resets) */
+    float* dof_state;             /* [N, 4, 2] in/out (resets) */
+    const float* contact_forces;  /* [N, num_bodies, 3] */
+    float* actions;               /* [N, 4] the clipped actions of this step; zero_action written for envs that reset (:314) */
+    const float* torques;         /* [N, 4] the limit-clipped torques of the last sub-step (self.torques after :112) */
+    float *last_actions, *last_dof_vel, *last_root_vel; /* [N, 4], [N, 4], [N, 6] */
+    float *base_lin_vel, *base_ang_vel, *projected_gravity; /* [N, 3] out */
+    float* feet_air_time;         /* [N] */
+    uint8_t* last_contacts;       /* [N] */
+    int64_t* episode_length_buf;  /* [N] */
+    uint8_t *reset_buf, *time_out_buf; /* [N] out */
+    float* rew_buf;               /* [N] out */
+    float* episode_sums;          /* [K, N] */
+    float* obs_buf;               /* [N, B200GYM_HOPPER_TRAJ_NUM_OBS] out */
+    const float* trajectory;      /* [N, 10, 2] traj_gen.get_trajectory() after this step's generator step */
+    const float* gen_v;           /* [N, 2] traj_gen.v */
+    float* prev_error;            /* [N, 2] */
+    float* time_until_next_push;  /* [N] */
+    const float* env_origins;     /* [N, 3] */
+    float* extras_out;            /* [K + 2]: means of episode_sums over the envs that reset / max_episode_length_s; [K + 1] = reset count */
+    double* ws_sums;              /* [K + 2] zero-initialised workspace */
+    uint32_t* push_flag;          /* 1 word, zero-initialised */
+} B200HopperEnvBuffers;
+int b200gym_hopper_post_physics(const B200HopperEnvParams* p, const B200HopperEnvBuffers* b, uint64_t step, int64_t env_id_offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Group G — rsl_rl rollout storage + PPO update (rsl_rl v1.0.2, a fork of which the reference imports at

@@ -89,12 +89,42 @@ class RomFamilyParamsPOD(C.Structure):
 class HopperTorqueParamsPOD(C.Structure):
     _fields_ = [("num_envs", i32), ("num_bodies", i32), ("foot_body", i32), ("spindown", i32), ("action_scale", f32),
                 ("torque_speed_bound_ratio", f32), ("p_gains", f32 * 4), ("d_gains", f32 * 4), ("kd_spindown", f32 * 3),
-                ("wheel_speed_limits", f32 * 3), ("torque_limits", f32 * 4), ("rot_actuator", f32 * 9)]
+                ("wheel_speed_limits", f32 * 3), ("torque_limits", f32 * 4), ("rot_actuator", f32 * 9), ("ang_vel_from_root", i32), ("pad", i32)]
 
 
 class HopperObsParamsPOD(C.Structure):
     _fields_ = [("num_envs", i32), ("add_noise", i32), ("z_pos_scale", f32), ("lin_vel_scale", f32), ("ang_vel_scale", f32), ("dof_vel_scale", f32),
                 ("clip_observations", f32), ("commands_scale", f32 * 3), ("noise_scale_vec", f32 * 21), ("seed_lo", u32), ("seed_hi", u32)]
+
+
+HOPPER_NUM_TERMS = 20
+
+
+class HopperEnvParamsPOD(C.Structure):
+    _fields_ = [("num_envs", i32), ("num_bodies", i32), ("foot_body", i32), ("num_term", i32), ("num_pen", i32), ("num_sum_rows", i32),
+                ("term_idx", i32 * 8), ("pen_idx", i32 * 8), ("push_robots", i32), ("only_positive", i32), ("add_noise", i32), ("randomize_yaw", i32),
+                ("dt", f32), ("push_dt", f32), ("max_episode_length", f32), ("max_episode_length_s", f32),
+                ("push_t_lo", f32), ("push_t_span", f32), ("max_push_vel", f32 * 6),
+                ("reward_scale", f32 * HOPPER_NUM_TERMS), ("sum_row", i32 * HOPPER_NUM_TERMS),
+                ("tracking_sigma", f32), ("soft_dof_vel_limit", f32), ("base_height_target", f32), ("max_contact_force", f32), ("traj_weight", f32 * 2),
+                ("diff_neg_slope", f32), ("diff_pos_slope", f32), ("raibert", f32 * 6),
+                ("dof_pos_lo", f32 * 4), ("dof_pos_hi", f32 * 4), ("dof_vel_limits", f32 * 4),
+                ("default_dof_pos", f32 * 4), ("dof_pos_noise_lo", f32 * 4), ("dof_pos_noise_span", f32 * 4), ("dof_vel_noise_lo", f32 * 4),
+                ("dof_vel_noise_span", f32 * 4),
+                ("base_init_state", f32 * 13), ("root_pos_noise_lo", f32 * 5), ("root_pos_noise_span", f32 * 5), ("root_vel_noise_lo", f32 * 6),
+                ("root_vel_noise_span", f32 * 6), ("zero_action", f32 * 4),
+                ("z_pos_scale", f32), ("lin_vel_scale", f32), ("ang_vel_scale", f32), ("dof_vel_scale", f32), ("clip_obs", f32), ("traj_scale", f32 * 2),
+                ("noise_scale_vec", f32 * 14), ("seed_lo", u32), ("seed_hi", u32)]
+
+
+_HOPPER_ENV_FIELDS = ["root_states", "dof_state", "contact_forces", "actions", "torques", "last_actions", "last_dof_vel", "last_root_vel", "base_lin_vel",
+                      "base_ang_vel", "projected_gravity", "feet_air_time", "last_contacts", "episode_length_buf", "reset_buf", "time_out_buf", "rew_buf",
+                      "episode_sums", "obs_buf", "trajectory", "gen_v", "prev_error", "time_until_next_push", "env_origins", "extras_out", "ws_sums",
+                      "push_flag"]
+
+
+class HopperEnvBuffersPOD(C.Structure):
+    _fields_ = [(n, vp) for n in _HOPPER_ENV_FIELDS]
 
 
 _HOPPER_FIELDS = ["actions", "dof_state", "contact_forces", "root_states", "base_ang_vel", "p_gain_random", "d_gain_random", "torque_limit_random",
@@ -194,6 +224,8 @@ def lib():
     L.b200gym_post_physics.argtypes = [pp, C.POINTER(LeggedBuffersPOD), C.c_uint64, C.c_int64, vp]
     L.b200gym_legged_reset_idx.argtypes = [pp, C.POINTER(LeggedBuffersPOD), vp, C.c_uint64, C.c_int64, vp]
     L.b200gym_legged_reset_idx.restype = C.c_int
+    L.b200gym_hopper_post_physics.argtypes = [C.POINTER(HopperEnvParamsPOD), C.POINTER(HopperEnvBuffersPOD), C.c_uint64, C.c_int64, vp]
+    L.b200gym_hopper_post_physics.restype = C.c_int
     for name in ("b200gym_pd_torques", "b200gym_set_actuator_net", "b200gym_lstm_torques", "b200gym_post_physics"):
         getattr(L, name).restype = C.c_int
     rp, rs = C.POINTER(RomParamsPOD), C.POINTER(RomStatePOD)
@@ -269,7 +301,8 @@ def lib():
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),
                       ("B200RomParams", RomParamsPOD), ("B200RomState", RomStatePOD), ("B200PeerPtrs", PeerPtrsPOD), ("B200PeerBases", PeerBasesPOD), ("B200GemmProblem", GemmProblemPOD), ("B200PackTable", PackTablePOD), ("B200ChainNet", ChainNetPOD), ("B200OptParams", OptParamsPOD),
                       ("B200RomFamilyParams", RomFamilyParamsPOD), ("B200HopperTorqueParams", HopperTorqueParamsPOD),
-                      ("B200HopperTorqueBuffers", HopperTorqueBuffersPOD), ("B200HopperObsParams", HopperObsParamsPOD)):
+                      ("B200HopperTorqueBuffers", HopperTorqueBuffersPOD), ("B200HopperObsParams", HopperObsParamsPOD),
+                      ("B200HopperEnvParams", HopperEnvParamsPOD), ("B200HopperEnvBuffers", HopperEnvBuffersPOD)):
         n = L.b200gym_sizeof(name.encode())
         if n != C.sizeof(cls):
             raise RuntimeError(f"ABI mismatch: sizeof({name}) is {n} in the library, {C.sizeof(cls)} in the binding")

@@ -28,7 +28,7 @@ def _tree(d):
     return Cfg(**{k: _tree(v) if isinstance(v, dict) and k not in _DICT_LEAVES else copy.deepcopy(v) for k, v in d.items()})
 
 
-_DICT_LEAVES = {"default_joint_angles", "stiffness", "damping", "terrain_kwargs"}
+_DICT_LEAVES = {"default_joint_angles", "stiffness", "damping", "terrain_kwargs", "wheel_spindown", "wheel_speed_bounds"}
 
 _GRID_X = [round(-0.8 + 0.1 * i, 1) for i in range(17)]      # legged_robot_config.py:55-57
 _GRID_Y = [round(-0.5 + 0.1 * i, 1) for i in range(11)]
@@ -191,6 +191,64 @@ def anymal_c_flat_trajectory_cfg_ppo():
 
 def anymal_c_rough_trajectory_cfg_ppo():
     return _tree(_merge(_PPO, {"runner": dict(experiment_name="rough_anymal_trajectory_c")}))
+
+
+# ---- HopperRoughTrajectoryCfg (legged_gym/envs/hopper/flat_trajectory/hopper_trajectory_config.py:3-260), the configuration of the only
+# Hopper class of the fork that can run a full step (HopperTrajectory).  Values the shipped class leaves undefined or unusable are taken from
+# the training yaml (deep_tube_learning/configs/rl/hopper_single_int.yaml) and flagged.
+_HOPPER_TRAJ = _merge(_TRAJ_BASE, {
+    "env": dict(num_envs=4096 * 4, num_observations=38, num_actions=4),                            # :4-7
+    "terrain": dict(mesh_type="plane", measure_heights=False, curriculum=False),                   # :9-13
+    "init_state": dict(pos=[0.0, 0.0, 0.3], rot=[0.0, 0.0, 0.0, 1.0], lin_vel=[0.0, 0.0, 0.0], ang_vel=[0.0, 0.0, 0.0],
+                       default_joint_angles={"foot_slide": 0.0, "wheel1_rotation": 0.0, "wheel2_rotation": 0.0, "wheel3_rotation": 0.0},
+                       randomize_yaw=True, default_dof_pos_noise_lower=[-0.02, 0, 0, 0], default_dof_pos_noise_upper=[0.02, 0, 0, 0],
+                       default_dof_vel_noise_lower=[-0.1, -100.0, -100.0, -100.0], default_dof_vel_noise_upper=[0.1, 100.0, 100.0, 100.0],
+                       default_root_pos_noise_lower=[-0.0, -0.0, -0.05, -0.03, -0.03, -0.03, -0.03],
+                       default_root_pos_noise_upper=[0.0, 0.0, 0.05, 0.03, 0.03, 0.03, 0.03],
+                       default_root_vel_noise_lower=[-0.05, -0.05, -0.05, -0.2, -0.2, -0.2],
+                       default_root_vel_noise_upper=[0.05, 0.05, 0.05, 0.2, 0.2, 0.2]),               # :15-31
+    "control": dict(stiffness={"foot_slide": 400.0, "wheel1_rotation": 15.0, "wheel2_rotation": 15.0, "wheel3_rotation": 15.0},
+                    damping={"foot_slide": 40.0, "wheel1_rotation": 3.0, "wheel2_rotation": 3.0, "wheel3_rotation": 3.0},
+                    wheel_spindown={"wheel1_rotation": 0.1, "wheel2_rotation": 0.1, "wheel3_rotation": 0.1}, foot_pos_des=0.03, action_scale=1,
+                    decimation=4, control_type="orientation", zero_action=[1.0, 0.0, 0.0, 0.0], use_actuator_network=False),   # :33-58
+    "asset": dict(name="hopper_flat_trajectory", foot_name="foot", penalize_contacts_on=[], terminate_after_contacts_on=["wheel", "torso"],
+                  spring_stiffness=11732, spring_damping=50,
+                  rot_actuator=[[-0.8165, 0.2511, 0.2511], [-0.0, -0.7643, 0.7643], [-0.5773, -0.5939, -0.5939]],
+                  wheel_speed_bounds={"wheel1_rotation": 600, "wheel2_rotation": 600, "wheel3_rotation": 600}, torque_speed_bound_ratio=6),   # :60-90
+    "normalization": dict(obs_scales=dict(lin_vel=0.5, ang_vel=0.25, dof_vel=0.01, z_pos=1.0, trajectory=[1.0, 1.0], height_measurements=5.0),
+                          clip_observations=100.0, clip_actions=100.0),                             # :92-103
+    "noise": dict(add_noise=True, noise_level=1.0, noise_scales=dict(dof_vel=1.5, lin_vel=0.1, ang_vel=0.2, gravity=0.05, z_pos=0.02, quat=0.05,
+                                                                     height_measurements=0.1)),     # :105-116
+    "domain_rand": dict(push_robots=True, randomize_rom_distance=False, max_rom_dist=[1.0, 1.0],    # max_rom_dist: None as shipped (:131), yaml value
+                        zero_rom_distance_likelihood=0.25,
+                        spring_properties=dict(randomize_stiffness=True, stiffness_range=[0.9, 1.1], randomize_damping=True, damping_range=[0.9, 1.1],
+                                               randomize_setpoint=True, setpoint_range=[0.75, 1.25]),
+                        pd_gain_properties=dict(randomize_p_gain=True, p_gain_range=[0.9, 1.1], randomize_d_gain=True, d_gain_range=[0.9, 1.1]),
+                        torque_speed_properties=dict(randomize_max_torque=True, max_torque_range=[0.95, 1.05], randomize_max_speed=True,
+                                                     max_speed_range=[0.9, 1.1], randomize_slope=True, slope_range=[0.9, 1.1])),   # :118-170
+    "rewards": dict(scales=dict(termination=-0.5, collision=-1.0), only_positive_rewards=False, base_height_target=0.55, max_contact_force=100.0,
+                    tracking_sigma=0.25, reward_weighting=dict(position=1.0),                        # tracking_sigma / weighting: yaml
+                    raibert=dict(Kp=-0.3, Kv=-0.9, Kff=0.0, clip_pos=0.5, clip_vel=1.0, clip_ang=0.2),
+                    differential_error=dict(pos_slope=4, neg_slope=1)),                            # :172-190
+    "trajectory_generator": dict(weight_samp_cls="UniformWeightSamplerNoRamp"),                    # yaml; the shipped class name does not exist
+    "curriculum": dict(use_curriculum=False, curriculum_steps=[2500, 5000]),                       # :214-216
+})
+# the reward table the Hopper is trained with (deep_tube_learning/configs/rl/hopper_single_int.yaml)
+HOPPER_YAML_REWARD_SCALES = dict(termination=-500.0, tracking_rom=6.0, ang_vel_xy=-0.01, orientation=-80.0, torques=-1e-6, dof_acc=-2.5e-8,
+                                 unit_quat=-0.01, collision=-1.0, action_rate=-0.01, differential_error=10.0, raibert=-0.1)
+HOPPER_DOF_NAMES = ["foot_slide", "wheel1_rotation", "wheel2_rotation", "wheel3_rotation"]
+# what the asset loader would report for resources/robots/hopper/urdf/hopper.urdf (bodies: torso, wheel1-3, foot)
+HOPPER_ASSET = dict(num_bodies=5, foot_body=4, termination_bodies=[0, 1, 2, 3], penalised_bodies=[], torque_limits=[300.0, 1.5, 1.5, 1.5],
+                    dof_pos_limits=[[-0.03, 0.1], [-1e4, 1e4], [-1e4, 1e4], [-1e4, 1e4]], dof_vel_limits=[5.0, 600.0, 600.0, 600.0])
+
+
+def hopper_flat_trajectory_cfg():
+    return _tree(_HOPPER_TRAJ)
+
+
+def hopper_flat_trajectory_cfg_ppo():
+    return _tree(_merge(_PPO, {"policy": dict(actor_hidden_dims=[128, 64, 32], critic_hidden_dims=[128, 64, 32]),
+                               "algorithm": dict(entropy_coef=0.01), "runner": dict(experiment_name="hopper_flat_trajectory", max_iterations=1500)}))
 
 
 def anymal_c_rough_cfg():

@@ -29,6 +29,8 @@ int b200gym_sizeof(const char* name) {
     if (!strcmp(name, "B200RomFamilyParams")) return (int)sizeof(B200RomFamilyParams);
     if (!strcmp(name, "B200HopperTorqueParams")) return (int)sizeof(B200HopperTorqueParams);
     if (!strcmp(name, "B200HopperTorqueBuffers")) return (int)sizeof(B200HopperTorqueBuffers);
+    if (!strcmp(name, "B200HopperEnvParams")) return (int)sizeof(B200HopperEnvParams);
+    if (!strcmp(name, "B200HopperEnvBuffers")) return (int)sizeof(B200HopperEnvBuffers);
     if (!strcmp(name, "B200HopperObsParams")) return (int)sizeof(B200HopperObsParams);
     if (!strcmp(name, "B200PeerPtrs")) return (int)sizeof(B200PeerPtrs);
     if (!strcmp(name, "B200PeerBases")) return (int)sizeof(B200PeerBases);

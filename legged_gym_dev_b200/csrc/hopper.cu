@@ -82,9 +82,20 @@ __global__ void __launch_bounds__(256) hopper_torques_kernel(const __grid_consta
         const float phi_sin = sinf(phi);
         const float factor = fabsf(phi_sin) > 5e-5f ? div_rn(phi, mul_rn(2.0f, phi_sin)) : add_rn(0.5f, mul_rn(mul_rn(phi, phi), 1.0f / 12));
         const float lg[3] = {mul_rn(factor, sub_rn(R21, R12)), mul_rn(factor, sub_rn(R02, R20)), mul_rn(factor, sub_rn(R10, R01))};
+        float bav[3];
+        if (p.ang_vel_from_root) {   // the refresh of the previous sub-step (hopper_trajectory.py:124-126): quat_rotate_inverse(base_quat, root[:, 10:13])
+            const float vx = rs[10], vy = rs[11], vz = rs[12];
+            const float k = sub_rn(mul_rn(mul_rn(2.0f, bw), bw), 1.0f), w2 = mul_rn(bw, 2.0f);
+            const float d = add_rn(add_rn(mul_rn(bx, vx), mul_rn(by, vy)), mul_rn(bz, vz));
+            bav[0] = add_rn(sub_rn(mul_rn(vx, k), mul_rn(sub_rn(mul_rn(by, vz), mul_rn(bz, vy)), w2)), mul_rn(mul_rn(bx, d), 2.0f));
+            bav[1] = add_rn(sub_rn(mul_rn(vy, k), mul_rn(sub_rn(mul_rn(bz, vx), mul_rn(bx, vz)), w2)), mul_rn(mul_rn(by, d), 2.0f));
+            bav[2] = add_rn(sub_rn(mul_rn(vz, k), mul_rn(sub_rn(mul_rn(bx, vy), mul_rn(by, vx)), w2)), mul_rn(mul_rn(bz, d), 2.0f));
+        } else {
+            bav[0] = b.base_ang_vel[i * 3], bav[1] = b.base_ang_vel[i * 3 + 1], bav[2] = b.base_ang_vel[i * 3 + 2];
+        }
         float lt[3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) lt[j] = sub_rn(mul_rn(-pg[1 + j], lg[j]), mul_rn(dg[1 + j], b.base_ang_vel[i * 3 + j]));   // :219
+        for (int j = 0; j < 3; ++j) lt[j] = sub_rn(mul_rn(-pg[1 + j], lg[j]), mul_rn(dg[1 + j], bav[j]));   // :219
         // Rotate(rot_actuator).transform_points: row vector times matrix
 #pragma unroll
         for (int j = 0; j < 3; ++j) tq[1 + j] = fmaf(lt[2], p.rot_actuator[6 + j], fmaf(lt[1], p.rot_actuator[3 + j], mul_rn(lt[0], p.rot_actuator[j])));

@@ -428,50 +428,12 @@ def make_reference_hopper_trajectory(hp, dr, tape, time_until_next_push, episode
     import legged_gym.envs.base.legged_robot_trajectory as ltmod
     import legged_gym.envs.hopper.hopper_trajectory as ht
     from legged_gym.envs.hopper.flat_trajectory.hopper_trajectory_config import HopperRoughTrajectoryCfg
-    from .port_hopper_env import TERMS
+    from .port_hopper_env import apply_params_to_cfg
     N = hp.num_envs
     cfg = HopperRoughTrajectoryCfg()
-    cfg.env.num_envs, cfg.env.num_observations, cfg.env.episode_length_s = N, 14 + hp.generator["N"] * 2 + 4, hp.episode_length_s
-    for name in TERMS:
-        setattr(cfg.rewards.scales, name, hp.scales.get(name, 0.0))
-    rw = cfg.rewards
-    rw.only_positive_rewards, rw.tracking_sigma, rw.base_height_target = hp.only_positive_rewards, hp.tracking_sigma, hp.base_height_target
-    rw.soft_dof_vel_limit, rw.soft_torque_limit, rw.max_contact_force = hp.soft_dof_vel_limit, hp.soft_torque_limit, hp.max_contact_force
-    rw.reward_weighting = SimpleNamespace(position=hp.reward_weighting[0])
-    rw.differential_error.neg_slope, rw.differential_error.pos_slope = hp.diff_neg_slope, hp.diff_pos_slope
-    g = hp.raibert
-    rw.raibert.Kp, rw.raibert.Kv, rw.raibert.Kff = g["Kp"], g["Kv"], g["K_ff"]
-    rw.raibert.clip_pos, rw.raibert.clip_vel, rw.raibert.clip_ang = g["clip_pos"], g["clip_vel"], g["clip_ang"]
-    cfg.control.control_type, cfg.control.action_scale, cfg.control.decimation = hp.control_type, hp.action_scale, hp.decimation
-    cfg.control.zero_action = list(hp.reset["zero_action"])
-    cfg.normalization.clip_actions, cfg.normalization.clip_observations = hp.clip_actions, hp.obs["clip_observations"]
-    cfg.normalization.obs_scales.trajectory = list(hp.trajectory_scale)
-    cfg.noise.add_noise = hp.obs["add_noise"]
-    d = cfg.domain_rand
-    d.push_robots, d.time_between_pushes, d.max_push_vel = hp.push_robots, list(hp.time_between_pushes), list(hp.reset["max_push_vel"])
-    tgc = hp.generator
-    d.randomize_rom_distance, d.max_rom_dist, d.zero_rom_distance_likelihood = tgc["randomize_rom_distance"], list(tgc["max_rom_distance"]), tgc["zero_rom_dist_llh"]
-    cfg.curriculum.use_curriculum = False
-    cfg.rom.dt, cfg.rom.v_min, cfg.rom.v_max = tgc["rom_dt"], [-tgc["vel_max_rom"]] * 2, [tgc["vel_max_rom"]] * 2
-    tg = cfg.trajectory_generator
-    tg.weight_samp_cls, tg.N, tg.dN, tg.DN = tgc["weight_sampler"], tgc["N"], tgc["dN"], tgc["dN"]
-    tg.t_low, tg.t_high, tg.freq_low, tg.freq_high = tgc["t_low"], tgc["t_high"], tgc["freq_low"], tgc["freq_high"]
-    tg.prob_stationary, tg.seed = tgc["prob_stationary"], tgc["seed"]
-    isl, rc = cfg.init_state, hp.reset
-    isl.pos, isl.rot = list(rc["base_init_state"][:3]), list(rc["base_init_state"][3:7])
-    isl.lin_vel, isl.ang_vel = list(rc["base_init_state"][7:10]), list(rc["base_init_state"][10:13])
-    isl.randomize_yaw = rc["randomize_yaw"]
-    isl.default_dof_pos_noise_lower, isl.default_dof_pos_noise_upper = list(rc["dof_pos_noise"][0]), list(rc["dof_pos_noise"][1])
-    isl.default_dof_vel_noise_lower, isl.default_dof_vel_noise_upper = list(rc["dof_vel_noise"][0]), list(rc["dof_vel_noise"][1])
-    isl.default_root_pos_noise_lower, isl.default_root_pos_noise_upper = list(rc["root_pos_noise"][0]), list(rc["root_pos_noise"][1])
-    isl.default_root_vel_noise_lower, isl.default_root_vel_noise_upper = list(rc["root_vel_noise"][0]), list(rc["root_vel_noise"][1])
+    apply_params_to_cfg(cfg, hp)
+    rw, d, tg, isl = cfg.rewards, cfg.domain_rand, cfg.trajectory_generator, cfg.init_state
     dof_names = ["foot_slide", "wheel1_rotation", "wheel2_rotation", "wheel3_rotation"]
-    isl.default_joint_angles = dict(zip(dof_names, rc["default_dof_pos"]))
-    cfg.control.stiffness = dict(zip(dof_names, hp.p_gains))
-    cfg.control.damping = dict(zip(dof_names, hp.d_gains))
-    cfg.control.wheel_spindown = dict(zip(dof_names[1:], hp.kd_spindown))
-    cfg.asset.wheel_speed_bounds = dict(zip(dof_names[1:], hp.wheel_speed_limits))
-    cfg.asset.rot_actuator, cfg.asset.torque_speed_bound_ratio = [list(r) for r in hp.rot_actuator], hp.torque_speed_bound_ratio
 
     HT = ht.HopperTrajectory
     env = HT.__new__(HT)

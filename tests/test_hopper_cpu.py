@@ -241,7 +241,7 @@ HOPPER_ENV_CASES = {
 def build_hopper_env_case(name, N, seed=3):
     from oracle import port_hopper_env as E
     hp = E.hopper_env_params(N, seed=seed, **HOPPER_ENV_CASES[name])
-    tape = E.make_hopper_tape(N, frames=8, seed=1)
+    tape = E.make_hopper_tape(N, frames=8, seed=1, origins=E.grid_origins(N))
     dr = E.make_domain_rand(N, hp, seed=2)
     g = torch.Generator().manual_seed(5)
     tpush = 0.15 * torch.rand(N, generator=g)

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from legged_gym_dev_b200.hopper import HopperActuation
-from oracle.compare import assert_close, max_err
+from oracle.compare import assert_close, assert_exact, max_err
 from oracle.make_golden_hopper import CASES
 from oracle.port_hopper import hopper_case, hopper_torques
 
@@ -150,3 +150,99 @@ def test_observations_shard_invariance_1m():
     plain = make_obs_env(case, dict(OBS_CFG, add_noise=False)).compute_observations()
     assert torch.equal(plain[:, 1:5], case["root_states"][:, 3:7].cuda()) and torch.equal(plain[:, 14:], whole[:, 14:])
     assert float((whole - plain)[:, :14].abs().max()) <= 0.0501 and float((whole - plain)[:, :14].abs().max()) > 0.04
+
+
+# ---- the whole HopperTrajectory env step against oracle/port_hopper_env.HopperTrajPort, which is pinned step by step to the
+# unmodified reference class (tests/test_hopper_cpu.py::test_hopper_env_port_tracks_unmodified_reference) --------------------------------------
+HOPPER_ALL_SCALES = dict(termination=-500.0, tracking_rom=6.0, ang_vel_xy=-0.01, orientation=-80.0, torques=-1e-6, dof_acc=-2.5e-8, unit_quat=-0.01,
+                         collision=-1.0, action_rate=-0.01, differential_error=10.0, raibert=-0.1, base_height=-1.0, dof_pos_limits=-10.0,
+                         dof_vel=-1e-6, dof_vel_limits=-0.5, feet_air_time=1.0, feet_contact_forces=-0.01, lin_vel_z=-2.0, stumble=-0.3,
+                         torque_limits=-0.02)
+HOPPER_ENV_CASES = {
+    "yaml_table": {},
+    "all_terms_spindown": dict(scales=HOPPER_ALL_SCALES, control_type="orientation_spindown", penalised_bodies=[1, 2, 3], only_positive_rewards=True),
+    "nonoise_nopush": dict(obs=dict(add_noise=False), push_robots=False, reset=dict(randomize_yaw=False)),
+}
+
+
+def _hopper_env_pair(name, N, seed=3, env_id_offset=0, lo=0, hi=None):
+    from oracle import port_hopper_env as E
+    from legged_gym_dev_b200 import configs
+    from legged_gym_dev_b200.hopper_trajectory import HopperTrajectory, HopperReplayPhysics
+    from types import SimpleNamespace
+    hi = N if hi is None else hi
+    hp_all = E.hopper_env_params(N, seed=seed, **HOPPER_ENV_CASES[name])
+    tape = E.make_hopper_tape(N, frames=8, seed=1, origins=E.grid_origins(N))
+    dr = E.make_domain_rand(N, hp_all, seed=2)
+    g = torch.Generator().manual_seed(5)
+    tpush = 0.15 * torch.rand(N, generator=g)
+    ep = torch.randint(0, 1002, (N,), generator=g)
+    n = hi - lo
+    hp = E.hopper_env_params(n, seed=seed, **HOPPER_ENV_CASES[name])
+    cut = SimpleNamespace(dof=tape.dof[:, :, lo:hi].contiguous(), root=tape.root[:, :, lo:hi].contiguous(), contact=tape.contact[:, :, lo:hi].contiguous(),
+                          actions=tape.actions[:, lo:hi].contiguous(), num_envs=n, frames=tape.frames, decimation=tape.decimation)
+    dr_cut = {k: v[lo:hi].contiguous() for k, v in dr.items()}
+    cfg = E.apply_params_to_cfg(configs.hopper_flat_trajectory_cfg(), hp)
+    asset = dict(num_bodies=hp.num_bodies, foot_body=hp.foot_body, termination_bodies=hp.termination_bodies, penalised_bodies=hp.penalised_bodies,
+                 torque_limits=hp.torque_limits, dof_pos_limits=hp.dof_pos_limits, dof_vel_limits=hp.dof_vel_limits)
+    env = HopperTrajectory(cfg, SimpleNamespace(dt=hp.sim_dt), None, "cuda", True, physics=HopperReplayPhysics(cut, device="cuda"), asset=asset,
+                           domain_rand_values=dr_cut, seed=seed, env_id_offset=env_id_offset + lo)
+    env.time_until_next_push.copy_(tpush[lo:hi].reshape(-1, 1))
+    env.episode_length_buf.copy_(ep[lo:hi])
+    port = E.HopperTrajPort(hp, dr_cut, cut, tpush[lo:hi], episode_length_buf=ep[lo:hi], env_origins=env.env_origins.cpu(), env_id_offset=env_id_offset + lo)
+    return hp, cut, env, port, E.HopperTapePhysics(cut)
+
+
+def _compare_hopper_env(env, port, tag):
+    N = port.N
+    assert_exact(env.reset_buf.cpu(), port.reset_buf, tag + "reset")
+    assert_exact(env.time_out_buf.cpu(), port.time_out_buf, tag + "time_out")
+    assert_exact(env.episode_length_buf.cpu(), port.episode_length_buf, tag + "ep_len")
+    assert_exact(env.last_contacts.cpu(), port.last_contacts, tag + "last_contacts")
+    assert_close(env.obs_buf.cpu(), port.obs_buf, 1.0, tag + "obs")
+    assert_close(env.rew_buf.cpu(), port.rew_buf, 1.0, tag + "rew")
+    assert_close(env.torques.cpu(), port.torques, 300.0, tag + "torques")
+    for k in ("root_states", "trajectory", "prev_error", "last_actions", "last_dof_vel", "last_root_vel", "base_ang_vel", "base_lin_vel",
+              "projected_gravity", "feet_air_time", "actions"):
+        assert_close(getattr(env, k).cpu(), getattr(port, k), 1.0, tag + k)
+    assert_close(env.time_until_next_push.cpu().reshape(-1), port.time_until_next_push, 1.0, tag + "time_until_next_push")
+    assert_close(env.dof_state.cpu().view(N, 4, 2), port.dof_state, 1.0, tag + "dof_state")
+    assert list(env.episode_sums) == list(port.episode_sums)
+    for k in port.episode_sums:
+        assert_close(env.episode_sums[k].cpu(), port.episode_sums[k], 1.0, tag + "sum_" + k)
+    for k, v in port.extras.get("episode", {}).items():
+        assert_close(env.extras["episode"][k].cpu(), v, 1.0, tag + "extras " + k)
+
+
+@pytest.mark.parametrize("name,N", [("yaml_table", 1000), ("all_terms_spindown", 516), ("nonoise_nopush", 67), ("yaml_table", 3)])
+def test_hopper_env_step_parity(name, N):
+    """HopperTrajectory.step on the fused path (4 x torque law + generator step + prologue / post-physics / finaliser + generator reset) against
+    the port, every step: flags and counters exact, everything else to 1e-5 (S = 1; 300 for torques = the foot's torque limit)."""
+    hp, tape, env, port, phys = _hopper_env_pair(name, N)
+    ids = torch.arange(N)
+    port.gen.reset_traj(ids, port.proj_z())          # the generators start next to the robots on both sides (a never-reset generator evaluates 0/0)
+    env.reset_traj_all()
+    resets = 0
+    for s in range(24):
+        a = tape.actions[s % 8] * (300.0 if s == 3 else 1.0)
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        resets += int(port.reset_buf.sum())
+        _compare_hopper_env(env, port, f"{name} N={N} step {s}: ")
+    assert resets > 0
+
+
+def test_hopper_env_shard_invariance():
+    """Per-env results do not depend on the split over ranks, except for the reference's env-0 push quirk (local env 0 of every process rides
+    along with every push of its process): compared on a case without pushes."""
+    N, half = 128, 64
+    _, tape, env, _, _ = _hopper_env_pair("nonoise_nopush", N)
+    _, tape_b, env_b, _, _ = _hopper_env_pair("nonoise_nopush", N, lo=half, hi=N)
+    env_b.env_origins.copy_(env.env_origins[half:])   # the shard keeps the origins of its global env ids (a per-process input)
+    env.reset_traj_all()
+    env_b.reset_traj_all()
+    for s in range(10):
+        env.step(tape.actions[s % 8].cuda())
+        env_b.step(tape_b.actions[s % 8].cuda())
+        assert torch.equal(env.obs_buf[half:], env_b.obs_buf) and torch.equal(env.rew_buf[half:], env_b.rew_buf)
+        assert torch.equal(env.reset_buf[half:], env_b.reset_buf) and torch.equal(env.root_states[half:], env_b.root_states)
