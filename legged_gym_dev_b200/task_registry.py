@@ -78,6 +78,9 @@ def _register_defaults():
                            configs.anymal_c_rough_trajectory_cfg_ppo())
     task_registry.register("anymal_c_flat_trajectory_b200", AnymalTrajectory, configs.anymal_c_flat_trajectory_cfg(),
                            configs.anymal_c_flat_trajectory_cfg_ppo())
+    from .hopper_trajectory import HopperTrajectory                      # legged_gym/envs/__init__.py: "hopper_flat_trajectory"
+    task_registry.register("hopper_flat_trajectory_b200", HopperTrajectory, configs.hopper_flat_trajectory_cfg(),
+                           configs.hopper_flat_trajectory_cfg_ppo())
 
 
 _register_defaults()

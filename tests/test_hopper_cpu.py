@@ -294,3 +294,25 @@ def test_hopper_env_port_tracks_unmodified_reference(name):
             for k in x1["episode"]:
                 assert_close(x2["episode"][k], x1["episode"][k], 1.0, tag + "extras " + k)
     assert resets > 0 and (pushes > 0 or not hp.push_robots)
+
+
+@pytest.mark.parametrize("name", ["yaml_table", "all_terms_spindown"])
+def test_hopper_env_port_replays_reference_golden(name):
+    """The travelling Hopper env port against tests/golden/hopper_env_reference.npz (outputs of the unmodified reference class, written by
+    oracle/make_golden_hopper_env.py): runs without the reference tree, as on the GPU box."""
+    from oracle import port_hopper_env as E
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hopper_env_reference.npz"))
+    N = gold[f"{name}/obs"].shape[1]
+    hp, tape, dr, tpush, ep = build_hopper_env_case(name, N)
+    port = E.HopperTrajPort(hp, dr, tape, tpush, episode_length_buf=ep, env_origins=E.grid_origins(N))
+    phys = E.HopperTapePhysics(tape)
+    port.gen.reset_traj(torch.arange(N), port.proj_z())
+    for s in range(gold[f"{name}/obs"].shape[0]):
+        port.step(tape.actions[s % 8].clone(), phys)
+        g = lambda k: torch.from_numpy(gold[f"{name}/{k}"][s])
+        tag = f"golden {name} step {s}: "
+        assert_exact(port.reset_buf, g("reset"), tag + "reset")
+        assert_close(port.obs_buf, g("obs"), 1.0, tag + "obs")
+        assert_close(port.rew_buf, g("rew"), 1.0, tag + "rew")
+        assert_close(port.root_states, g("root_states"), 1.0, tag + "root_states")
+        assert_close(port.torques, g("torques"), 300.0, tag + "torques")

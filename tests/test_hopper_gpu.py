@@ -246,3 +246,27 @@ def test_hopper_env_shard_invariance():
         env_b.step(tape_b.actions[s % 8].cuda())
         assert torch.equal(env.obs_buf[half:], env_b.obs_buf) and torch.equal(env.rew_buf[half:], env_b.rew_buf)
         assert torch.equal(env.reset_buf[half:], env_b.reset_buf) and torch.equal(env.root_states[half:], env_b.root_states)
+
+
+@pytest.mark.parametrize("name", ["yaml_table", "all_terms_spindown"])
+def test_hopper_env_replays_reference_golden(name):
+    """The fused Hopper env against outputs of the UNMODIFIED reference class itself (tests/golden/hopper_env_reference.npz, written by
+    oracle/make_golden_hopper_env.py in the build container): observations, rewards, flags, root state, torques, prev_error, push timers."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hopper_env_reference.npz")
+    gold = np.load(path)
+    N = gold[f"{name}/obs"].shape[1]
+    hp, tape, env, port, phys = _hopper_env_pair(name, N)
+    env.reset_traj_all()
+    for s in range(gold[f"{name}/obs"].shape[0]):
+        env.step(tape.actions[s % 8].cuda())
+        tag = f"golden {name} step {s}: "
+        g = lambda k: torch.from_numpy(gold[f"{name}/{k}"][s])
+        assert_exact(env.reset_buf.cpu(), g("reset"), tag + "reset")
+        assert_exact(env.time_out_buf.cpu(), g("time_out"), tag + "time_out")
+        assert_close(env.obs_buf.cpu(), g("obs"), 1.0, tag + "obs")
+        assert_close(env.rew_buf.cpu(), g("rew"), 1.0, tag + "rew")
+        assert_close(env.torques.cpu(), g("torques"), 300.0, tag + "torques")
+        assert_close(env.root_states.cpu(), g("root_states"), 1.0, tag + "root_states")
+        assert_close(env.prev_error.cpu(), g("prev_error"), 1.0, tag + "prev_error")
+        assert_close(env.trajectory.cpu(), g("trajectory"), 1.0, tag + "trajectory")
+        assert_close(env.time_until_next_push.cpu().reshape(-1), g("time_until_next_push"), 1.0, tag + "time_until_next_push")

@@ -351,8 +351,8 @@ def gae_update(num_envs=4096, T=24, device="cuda", peak=6535.7):
                 T=T, gae_ms=ms_gae, gae_env_steps_per_s=num_envs * T / (ms_gae * 1e-3),
                 gae_gbs=604 * num_envs / (ms_gae * 1e-3) / 1e9, gae_frac=604 * num_envs / (ms_gae * 1e-3) / 1e9 / peak,
                 update_ms=ms_upd, update_samples_per_s=5 * T * num_envs / (ms_upd * 1e-3),
-                note="GAE at 4096 envs moves 2.5 MB: launch-latency bound; update = 20 replays of one captured minibatch graph "
-                     "(fused gather/loss/clip+Adam kernels + TF32 cuBLAS GEMMs for the training forward/backward)")
+                note="GAE at 4096 envs moves 2.5 MB: launch-latency bound; update = ONE replay of a captured graph of all 20 minibatch steps "
+                     "(row gather -> chained tcgen05 forward / loss / dgrad -> grouped wgrad GEMM -> fused clip + Adam + fp16 repack)")
 
 
 def cpu_port_baselines(quick=False):
@@ -457,6 +457,58 @@ def hopper_torques(num_envs=1 << 20, steps=50, device="cuda", peak=6535.7):
                 algorithmic_bytes_per_env=188, achieved_gbs=188 * num_envs / ms / 1e6, frac=188 * num_envs / ms / 1e6 / peak)
 
 
+def hopper_env_step(num_envs=1 << 20, steps=32, device="cuda", peak=6535.7):
+    """HopperTrajectory.step = 4 x torque law + generator step + prologue / fused post-physics / finaliser + generator reset,
+    yaml reward table (11 terms).  Synthetic per-sub-step state generated on the device.  Algorithmic bytes per env: 4 x 188 (torque law)
+    + 682 (post-physics, csrc/hopper_env.cu header) + generator step."""
+    from legged_gym_dev_b200 import configs
+    from legged_gym_dev_b200.hopper_trajectory import HopperTrajectory
+    cfg = configs.hopper_flat_trajectory_cfg()
+    cfg.env.num_envs = num_envs
+    for k, v in configs.HOPPER_YAML_REWARD_SCALES.items():
+        setattr(cfg.rewards.scales, k, v)
+
+    class DevicePhysics:   # fixed random state tensors: the kernels' traffic does not depend on the values
+        def __init__(self):
+            g = torch.Generator(device=device).manual_seed(0)
+            self.root_states = torch.randn(num_envs, 13, device=device, generator=g)
+            self.root_states[:, 3:7] = torch.nn.functional.normalize(self.root_states[:, 3:7] + torch.tensor([0, 0, 0, 3.0], device=device), dim=-1)
+            self.dof_state = torch.randn(num_envs, 4, 2, device=device, generator=g)
+            self.contact_forces = torch.zeros(num_envs, 5, 3, device=device)
+            self.contact_forces[:, 4, 2] = 100.0 * (torch.rand(num_envs, device=device, generator=g) > 0.5)
+
+        def simulate(self, torques):
+            pass
+
+        def commit_resets(self, reset_buf):
+            pass
+    env = HopperTrajectory(cfg, SimpleNamespace(dt=0.005), None, device, True, physics=DevicePhysics(), seed=0)
+    env.episode_length_buf.copy_(torch.randint(0, 1000, (num_envs,), device=device))
+    env.reset_traj_all()
+    act = torch.randn(num_envs, 4, device=device) * 0.2 + torch.tensor([1.0, 0, 0, 0], device=device)
+    for _ in range(4):
+        env.step(act)
+    torch.cuda.synchronize()
+    a, b = _events()
+    a.record()
+    for _ in range(steps):
+        env.step(act)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    a.record()
+    for _ in range(steps):
+        env.post_physics_step()
+    b.record()
+    torch.cuda.synchronize()
+    ms_pp = a.elapsed_time(b) / steps
+    per_pp = 682 + 2 * (88 + 80 + 4 * 4 + 16 + 9 * 8 + 4 + 1 + 4) + 80
+    return dict(workload=f"HopperTrajectory.step, yaml reward table, {num_envs} envs", ms_per_step=ms, env_steps_per_s=num_envs / ms * 1e3,
+                post_physics_ms=ms_pp, post_physics_bytes_per_env=per_pp, post_physics_frac=per_pp * num_envs / ms_pp / 1e6 / peak,
+                step_bytes_per_env=4 * 188 + per_pp, step_frac=(4 * 188 + per_pp) * num_envs / ms / 1e6 / peak,
+                finite=bool(torch.isfinite(env.obs_buf).all()) and bool(torch.isfinite(env.rew_buf).all()))
+
+
 def run_all(device="cuda", peak=6535.7, quick=False):
     out = {}
     for name, fn, kw in (("cfg1_rom_per_call", rom_per_call, dict(device=device, loop_steps=200 if quick else 1000)),
@@ -469,7 +521,8 @@ def run_all(device="cuda", peak=6535.7, quick=False):
                          ("cfg4b_tube_dataset", tube_dataset, dict(device=device, peak=peak, num_envs=16384 if quick else 262144)),
                          ("cfg5_gae_update", gae_update, dict(device=device, peak=peak)),
                          ("next4_rom_family_step", rom_family_step, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20))),
-                         ("next3_hopper_torques", hopper_torques, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20)))):
+                         ("next3_hopper_torques", hopper_torques, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20))),
+                         ("next3_hopper_env_step", hopper_env_step, dict(device=device, peak=peak, num_envs=(1 << 17) if quick else (1 << 20)))):
         try:
             out[name] = fn(**kw)
         except Exception as e:   # an extra must never take the headline line down
