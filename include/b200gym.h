@@ -597,15 +597,17 @@ int b200gym_ppo_optimizer_step_peers(const B200OptParams* p, const B200PeerBases
  * action sample (Philox4x32-10, site POLICY_SAMPLE, counter = (env_id_offset + env, event); Box-Muller, specification
  * oracle/port_ppo.py sample_actions), its summed log-prob, and observations / critic observations / actions / values / log-prob /
  * mu / sigma written to the storage ROW pointers st_* (row `step` of the [T, N, .] tensors).  mu_out [n_envs, ld_mu] and
- * value_out [n_envs, ld_value] are the MLP outputs; st_critic_obs may be NULL (no privileged observations). */
+ * value_out [n_envs, ld_value] are the MLP outputs; st_critic_obs may be NULL (no privileged observations).  event_dev (optional):
+ * the act counter in device memory, read instead of `event` and advanced by b200gym_ppo_store_step — a whole rollout can then be
+ * captured in a CUDA graph and replayed with fresh draws. */
 int b200gym_ppo_act_store(int32_t n_envs, int32_t num_actions, int32_t num_obs, int32_t num_critic_obs, const float* mu_out, int32_t ld_mu,
                           const float* value_out, int32_t ld_value, const float* std, const float* obs, int64_t ld_obs, const float* critic_obs,
-                          int64_t ld_critic_obs, uint64_t seed, uint64_t event, uint64_t env_id_offset, float* st_obs, float* st_critic_obs,
-                          float* st_actions, float* st_values, float* st_log_prob, float* st_mu, float* st_sigma, void* stream);
+                          int64_t ld_critic_obs, uint64_t seed, uint64_t event, const uint64_t* event_dev, uint64_t env_id_offset, float* st_obs,
+                          float* st_critic_obs, float* st_actions, float* st_values, float* st_log_prob, float* st_mu, float* st_sigma, void* stream);
 /* PPO.process_env_step -> add_transitions: rewards / dones / time-out flags (byte tensors; time_outs may be NULL = none) of one env
  * step into the storage row pointers. */
 int b200gym_ppo_store_step(int32_t n_envs, const float* rewards, const uint8_t* dones, const uint8_t* time_outs, float* st_rewards,
-                           uint8_t* st_dones, uint8_t* st_time_outs, void* stream);
+                           uint8_t* st_dones, uint8_t* st_time_outs, uint64_t* event_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Tube-dataset construction from the rollout logs (deep_tube_learning/datasets.py:60-71,

@@ -294,8 +294,8 @@ def lib():
                                                    + [C.POINTER(PackTablePOD), vp, C.c_int32, vp])
     L.b200gym_ppo_optimizer_step_peers.restype = C.c_int
     u64 = C.c_uint64
-    L.b200gym_ppo_act_store.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, C.c_int64, vp, C.c_int64, u64, u64, u64] + [vp] * 8
-    L.b200gym_ppo_store_step.argtypes = [i32] + [vp] * 7
+    L.b200gym_ppo_act_store.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, C.c_int64, vp, C.c_int64, u64, u64, vp, u64] + [vp] * 8
+    L.b200gym_ppo_store_step.argtypes = [i32] + [vp] * 8
     L.b200gym_ppo_act_store.restype = L.b200gym_ppo_store_step.restype = C.c_int
     L.b200gym_rows_to_f16.restype = L.b200gym_ppo_loss_gathered.restype = L.b200gym_pack_params_f16.restype = C.c_int
     for name, cls in (("B200MlpParams", MlpParamsPOD), ("B200PpoLossParams", PpoLossParamsPOD), ("B200LeggedParams", LeggedParamsPOD), ("B200LeggedBuffers", LeggedBuffersPOD),

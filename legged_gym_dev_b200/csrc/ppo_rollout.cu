@@ -24,11 +24,12 @@ __global__ void __launch_bounds__(256) ppo_act_store_kernel(int n_envs, int num_
                                                             int ld_mu, const float* __restrict__ value_out, int ld_value,
                                                             const float* __restrict__ stdv, const float* __restrict__ obs, long long ld_obs,
                                                             const float* __restrict__ critic_obs, long long ld_cobs, uint32_t seed_lo,
-                                                            uint32_t seed_hi, unsigned long long event, unsigned long long env_id_offset,
-                                                            float* __restrict__ st_obs, float* __restrict__ st_cobs, float* __restrict__ st_actions,
+                                                            uint32_t seed_hi, unsigned long long event, const unsigned long long* __restrict__ event_dev,
+                                                            unsigned long long env_id_offset, float* __restrict__ st_obs, float* __restrict__ st_cobs, float* __restrict__ st_actions,
                                                             float* __restrict__ st_values, float* __restrict__ st_logp, float* __restrict__ st_mu,
                                                             float* __restrict__ st_sigma) {
     const int A = num_actions;
+    if (event_dev) event = *event_dev;   // graph-replayable mode: the act counter lives in device memory (advanced by ppo_store_step_kernel)
     const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
     if (tid < n_envs) {
@@ -86,8 +87,10 @@ __global__ void __launch_bounds__(256) ppo_act_store_kernel(int n_envs, int num_
 
 __global__ void __launch_bounds__(256) ppo_store_step_kernel(int n_envs, const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
                                                              const uint8_t* __restrict__ time_outs, float* __restrict__ st_rewards,
-                                                             uint8_t* __restrict__ st_dones, uint8_t* __restrict__ st_time_outs) {
+                                                             uint8_t* __restrict__ st_dones, uint8_t* __restrict__ st_time_outs,
+                                                             unsigned long long* __restrict__ event_dev) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0 && event_dev) *event_dev += 1;   // the next PPO.act draws from the next event
     if (e >= n_envs) return;
     st_rewards[e] = rewards[e];
     st_dones[e] = dones[e] ? 1 : 0;
@@ -100,8 +103,8 @@ extern "C" {
 
 int b200gym_ppo_act_store(int32_t n_envs, int32_t num_actions, int32_t num_obs, int32_t num_critic_obs, const float* mu_out, int32_t ld_mu,
                           const float* value_out, int32_t ld_value, const float* std, const float* obs, int64_t ld_obs, const float* critic_obs,
-                          int64_t ld_critic_obs, uint64_t seed, uint64_t event, uint64_t env_id_offset, float* st_obs, float* st_critic_obs,
-                          float* st_actions, float* st_values, float* st_log_prob, float* st_mu, float* st_sigma, void* stream) {
+                          int64_t ld_critic_obs, uint64_t seed, uint64_t event, const uint64_t* event_dev, uint64_t env_id_offset, float* st_obs,
+                          float* st_critic_obs, float* st_actions, float* st_values, float* st_log_prob, float* st_mu, float* st_sigma, void* stream) {
     B200_REQUIRE(mu_out && value_out && std && obs && st_obs && st_actions && st_values && st_log_prob && st_mu && st_sigma, B200GYM_EINVAL,
                  "ppo_act_store: null argument");
     B200_REQUIRE(n_envs > 0 && num_actions > 0 && num_actions <= MAXA && num_obs > 0 && ld_mu >= num_actions && ld_value >= 1 && ld_obs >= num_obs,
@@ -115,17 +118,19 @@ int b200gym_ppo_act_store(int32_t n_envs, int32_t num_actions, int32_t num_obs, 
     if (blocks < min_blocks) blocks = min_blocks;
     ppo_act_store_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         n_envs, num_actions, num_obs, num_critic_obs, mu_out, ld_mu, value_out, ld_value, std, obs, ld_obs, critic_obs, ld_critic_obs,
-        static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), event, env_id_offset, st_obs, st_critic_obs, st_actions, st_values,
+        static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), event, reinterpret_cast<const unsigned long long*>(event_dev), env_id_offset,
+        st_obs, st_critic_obs, st_actions, st_values,
         st_log_prob, st_mu, st_sigma);
     B200_LAUNCH_CHECK("ppo_act_store");
     return B200GYM_OK;
 }
 
 int b200gym_ppo_store_step(int32_t n_envs, const float* rewards, const uint8_t* dones, const uint8_t* time_outs, float* st_rewards,
-                           uint8_t* st_dones, uint8_t* st_time_outs, void* stream) {
+                           uint8_t* st_dones, uint8_t* st_time_outs, uint64_t* event_dev, void* stream) {
     B200_REQUIRE(n_envs > 0 && rewards && dones && st_rewards && st_dones && st_time_outs, B200GYM_EINVAL, "ppo_store_step: bad argument");
     ppo_store_step_kernel<<<(n_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(n_envs, rewards, dones, time_outs, st_rewards,
-                                                                                              st_dones, st_time_outs);
+                                                                                              st_dones, st_time_outs,
+                                                                                              reinterpret_cast<unsigned long long*>(event_dev));
     B200_LAUNCH_CHECK("ppo_store_step");
     return B200GYM_OK;
 }

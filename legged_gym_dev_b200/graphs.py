@@ -40,3 +40,38 @@ class GraphedReplay:
         self.graph.replay()
         self.env.common_step_counter += self.F
         self.env.physics.frame += self.F
+
+
+class GraphedRollout:
+    """One PPO rollout — T x [PPO.act, env.step, PPO.process_env_step] of an OnPolicyRunner — captured ONCE as a CUDA graph and replayed per
+    training iteration (rsl_rl OnPolicyRunner.learn's inner loop; ~10 launches per env step become one graph launch per rollout).  Needs an
+    env whose step is graph-capturable: here a LeggedRobot on a replayed tape whose length divides T.  Both counters the kernels key their
+    random draws with (env step, act event) live in device memory and are advanced by the kernels, so every replay draws fresh numbers."""
+
+    def __init__(self, runner, rollout_fn):
+        env, alg, T = runner.env, runner.alg, runner.num_steps_per_env
+        ph = env.physics
+        F = getattr(ph, "frames", None)
+        if F is None or T % F or ph.frame % F:
+            raise ValueError("GraphedRollout needs a replayed tape whose length divides the rollout length, at the start of a tape cycle")
+        if alg.storage.step != 0:
+            raise ValueError("GraphedRollout: capture at the start of a rollout")
+        self.runner, self.T = runner, T
+        env.use_device_step_counter()
+        alg.use_device_act_counter()
+        env._stream = None
+        state = (env.common_step_counter, ph.frame, ph.sub, alg._act_event)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            rollout_fn()
+        env.common_step_counter, ph.frame, ph.sub, alg._act_event = state     # capture executed nothing
+        alg.storage.step = 0
+        env._stream = None
+
+    def replay(self):
+        env, alg = self.runner.env, self.runner.alg
+        self.graph.replay()
+        env.common_step_counter += self.T
+        env.physics.frame += self.T
+        alg._act_event += self.T
+        alg.storage.step = self.T

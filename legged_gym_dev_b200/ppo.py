@@ -296,6 +296,7 @@ class PPO:
         self._mb_cache = {}
         # PPO.act's sample: Philox stream keyed by (seed, global env id, act counter); torch.manual_seed controls it like rsl_rl's sampling
         self.seed, self.env_id_offset, self._act_event = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, 0, 0
+        self._act_event_dev = None
         self.use_graph = os.environ.get("B200GYM_PPO_GRAPH", "1") != "0"
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
@@ -323,7 +324,8 @@ class PPO:
         priv = st.privileged_observations
         _lib.check(self.lib.b200gym_ppo_act_store(
             obs.shape[0], ac.std.numel(), obs.shape[1], critic_obs.shape[1], ptr(mu), mu.stride(0), ptr(val), val.stride(0), ptr(ac.std),
-            ptr(obs), obs.stride(0), ptr(critic_obs), critic_obs.stride(0), self.seed, self._act_event, int(self.env_id_offset),
+            ptr(obs), obs.stride(0), ptr(critic_obs), critic_obs.stride(0), self.seed, self._act_event,
+            ptr(self._act_event_dev) if self._act_event_dev is not None else None, int(self.env_id_offset),
             ptr(st.observations[s]), ptr(priv[s]) if priv is not None else None, ptr(st.actions[s]), ptr(st.values[s]),
             ptr(st.actions_log_prob[s]), ptr(st.mu[s]), ptr(st.sigma[s]), _lib.stream_ptr(self.device)), "ppo_act_store")
         tr.observations = st.observations[s]
@@ -331,6 +333,14 @@ class PPO:
         tr.actions, tr.values, tr.actions_log_prob = st.actions[s], st.values[s], st.actions_log_prob[s, :, 0]
         tr.action_mean, tr.action_sigma = st.mu[s], st.sigma[s]
         return tr.actions
+
+    def use_device_act_counter(self):
+        """Keeps the act counter (Philox event of PPO.act's sample) in device memory, advanced by the store kernel, so that a sequence of
+        act / env.step / process_env_step calls can be captured in a CUDA graph and replayed (legged_gym_dev_b200.graphs.GraphedRollout)."""
+        if self._act_event_dev is None:
+            self._act_event_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._act_event_dev.fill_(self._act_event + 1)
+        return self._act_event_dev
 
     def process_env_step(self, rewards, dones, infos):
         """rsl_rl PPO.process_env_step + RolloutStorage.add_transitions for the fields the env step produced: ONE launch.  The
@@ -345,7 +355,9 @@ class PPO:
         rewards = rewards if (rewards.dtype == torch.float32 and rewards.is_contiguous()) else rewards.float().contiguous()
         _lib.check(self.lib.b200gym_ppo_store_step(rewards.numel(), ptr(rewards), ptr(as_u8(dones).contiguous()),
                                                    ptr(as_u8(to).contiguous()) if to is not None else None, ptr(st.rewards[s]),
-                                                   ptr(st.dones[s]), ptr(st.time_outs[s]), _lib.stream_ptr(self.device)), "ppo_store_step")
+                                                   ptr(st.dones[s]), ptr(st.time_outs[s]),
+                                                   ptr(self._act_event_dev) if self._act_event_dev is not None else None,
+                                                   _lib.stream_ptr(self.device)), "ppo_store_step")
         st.step += 1
         tr.clear()
         self.actor_critic.reset(dones)
@@ -564,6 +576,10 @@ class OnPolicyRunner:
         self.alg.env_id_offset = int(getattr(env, "env_id_offset", 0))   # env shards draw distinct action noise
         self.tot_timesteps, self.tot_time, self.current_learning_iteration = 0, 0, 0
         self.log_episode_stats = False
+        # opt-in: replay the T-step rollout (act / env.step / process_env_step) from ONE captured CUDA graph — for envs whose step is
+        # graph-capturable (a replayed tape, a GPU-resident simulator); the first iteration runs eagerly and is the capture warm-up
+        self.graph_rollout = False
+        self._rollout_graph = None
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
         env = self.env
@@ -580,15 +596,26 @@ class OnPolicyRunner:
         raw = getattr(env, "_extras_raw", None)
         log_stats = raw is not None and (self.log_dir is not None or self.wandb_callback is not None or self.log_episode_stats)
         hist = torch.zeros(self.num_steps_per_env, raw.numel(), dtype=torch.double, device=self.device) if log_stats else None
+        def rollout():
+            nonlocal obs, critic_obs
+            for t in range(self.num_steps_per_env):
+                actions = self.alg.act(obs, critic_obs)
+                obs, priv, rewards, dones, infos = env.step(actions)
+                critic_obs = priv if priv is not None else obs
+                self.alg.process_env_step(rewards, dones, infos)
+                if log_stats:
+                    hist[t].copy_(raw)
+
         for it in range(self.current_learning_iteration, self.current_learning_iteration + num_learning_iterations):
             with torch.inference_mode():
-                for t in range(self.num_steps_per_env):
-                    actions = self.alg.act(obs, critic_obs)
-                    obs, priv, rewards, dones, infos = env.step(actions)
-                    critic_obs = priv if priv is not None else obs
-                    self.alg.process_env_step(rewards, dones, infos)
-                    if log_stats:
-                        hist[t].copy_(raw)
+                if self.graph_rollout and self._rollout_graph is not None:
+                    self._rollout_graph.replay()
+                elif self.graph_rollout and it > self.current_learning_iteration:
+                    from .graphs import GraphedRollout
+                    self._rollout_graph = GraphedRollout(self, rollout)   # captures (nothing runs), then replays once
+                    self._rollout_graph.replay()
+                else:
+                    rollout()
                 self.alg.compute_returns(critic_obs)
             mean_value_loss, mean_surrogate_loss = self.alg.update()
             infos_out.append(dict(it=it, mean_value_loss=mean_value_loss, mean_surrogate_loss=mean_surrogate_loss))

@@ -91,3 +91,57 @@ def test_runner_episode_statistics_match_the_per_step_extras():
     for k in ep:
         want = sum(s[k] for s in seen) / len(seen)
         assert abs(float(ep[k]) - want) <= 1e-5 * max(1.0, abs(want)), (k, float(ep[k]), want)
+
+
+def test_graphed_rollout_matches_eager_rollout():
+    """GraphedRollout (T x [act, env.step, process_env_step] replayed from one CUDA graph, step and act counters in device memory) fills
+    the rollout storage bit-identically to the eager loop, replay after replay, and OnPolicyRunner.learn runs with it."""
+    from types import SimpleNamespace
+    from legged_gym_dev_b200 import synthetic as S
+    from legged_gym_dev_b200.graphs import GraphedRollout
+    from legged_gym_dev_b200.physics import ReplayPhysics
+    from legged_gym_dev_b200.task_registry import task_registry
+    N = 384
+
+    def collect(graph):
+        tape = S.make_state_tape(N, frames=4, seed=2, device="cuda")
+        args = SimpleNamespace(num_envs=N, sim_device="cuda", headless=True, physics_engine=None)
+        env, _ = task_registry.make_env("anymal_c_flat_b200", args=args, physics=ReplayPhysics(tape, device="cuda"))
+        env.episode_length_buf.copy_(S.make_episode_lengths(N, seed=1, device="cuda"))
+        runner, _ = task_registry.make_alg_runner(env, name="anymal_c_flat_b200", args=args)
+        alg, obs = runner.alg, env.get_observations()
+
+        def rollout():
+            for _ in range(runner.num_steps_per_env):
+                actions = alg.act(obs, obs)
+                _, _, rew, dones, infos = env.step(actions)
+                alg.process_env_step(rew, dones, infos)
+        out = []
+        with torch.inference_mode():
+            rollout()
+            alg.storage.clear()
+            g = GraphedRollout(runner, rollout) if graph else None
+            for _ in range(2):
+                g.replay() if graph else rollout()
+                st = alg.storage
+                out.append({k: getattr(st, k).clone() for k in ("observations", "actions", "rewards", "dones", "values", "actions_log_prob", "time_outs")})
+                assert st.step == runner.num_steps_per_env
+                st.clear()
+        return out, env.common_step_counter, alg._act_event
+
+    a, ca, ea = collect(False)
+    b, cb, eb = collect(True)
+    assert ca == cb == 72 and ea == eb == 72
+    for ra, rb in zip(a, b):
+        for k in ra:
+            assert torch.equal(ra[k], rb[k]), f"storage.{k} differs between the eager and the graph-replayed rollout"
+    assert not torch.equal(a[0]["actions"], a[1]["actions"])
+    # end to end through the runner
+    tape = S.make_state_tape(N, frames=4, seed=2, device="cuda")
+    args = SimpleNamespace(num_envs=N, sim_device="cuda", headless=True, physics_engine=None)
+    env, _ = task_registry.make_env("anymal_c_flat_b200", args=args, physics=ReplayPhysics(tape, device="cuda"))
+    runner, _ = task_registry.make_alg_runner(env, name="anymal_c_flat_b200", args=args)
+    runner.graph_rollout = True
+    infos = runner.learn(num_learning_iterations=4)
+    assert runner._rollout_graph is not None and env.common_step_counter == 4 * 24
+    assert all(torch.isfinite(i["mean_value_loss"]) for i in infos)

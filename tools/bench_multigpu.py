@@ -100,6 +100,11 @@ def train_iteration(rank, world, device, total=4096, iters=5):
     alg = runner.alg
     runner.learn(num_learning_iterations=2, init_at_random_ep_len=True)      # warm-up: allocations, graph capture
     ms_iter = _timed(lambda: runner.learn(num_learning_iterations=1), device, world, reps=iters)
+    # the same iteration with the rollout replayed from one CUDA graph (the replay tape makes the env step capturable)
+    runner.graph_rollout = True
+    runner.learn(num_learning_iterations=2)
+    ms_iter_g = _timed(lambda: runner.learn(num_learning_iterations=1), device, world, reps=iters)
+    runner.graph_rollout = False
     # the update alone, on the storage of the last rollout (update() only resets the write cursor)
     T = alg.storage.num_transitions_per_env
 
@@ -122,6 +127,7 @@ def train_iteration(rank, world, device, total=4096, iters=5):
     return dict(config="anymal_c_flat PPO training iteration: 24 env steps (act + env.step + storage) + GAE + update of 5 epochs x 4 "
                        "minibatches, nets 48-128-64-32; 4096 envs TOTAL sharded over the ranks",
                 total_envs=total, envs_per_gpu=n, ms_per_iteration=ms_iter, update_ms=ms_upd, rollout_ms=ms_iter - ms_upd,
+                ms_per_iteration_graphed_rollout=ms_iter_g, rollout_ms_graphed=ms_iter_g - ms_upd,
                 samples_per_s=total * T / (ms_iter * 1e-3), gradient_exchange=alg.exchange, params_bit_identical_across_ranks=same,
                 launches_per_minibatch=4, scaling="strong")
 
