@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) hopper_prologue_kernel(const __grid_const
     b.time_until_next_push[i] = t_out;
 }
 
-__global__ void __launch_bounds__(128) hopper_post_physics_kernel(const __grid_constant__ B200HopperEnvParams p,
+__global__ void __launch_bounds__(128, 5) hopper_post_physics_kernel(const __grid_constant__ B200HopperEnvParams p,
                                                                   const __grid_constant__ B200HopperEnvBuffers b, unsigned long long step,
                                                                   long long env_off) {
     const int N = p.num_envs, K = p.num_sum_rows, B = p.num_bodies;
@@ -127,13 +127,17 @@ __global__ void __launch_bounds__(128) hopper_post_physics_kernel(const __grid_c
         const bool reset = term | time_out;
 
         // rewards (legged_robot_trajectory.py:255-272), alphabetical order of the active terms
+        // the per-term values stay in registers; the episode_sums rows are read-modify-written once, after every load of the step has
+        // been issued (a global store per term in between would order the remaining loads behind it: 72 % long-scoreboard stalls)
         const float* rs = p.reward_scale;
         float rew = 0.0f;
+        float tv[B200GYM_HOPPER_NUM_TERMS];
+#pragma unroll
+        for (int k = 0; k < B200GYM_HOPPER_NUM_TERMS; ++k) tv[k] = 0.0f;
         auto add_term = [&](int k, float val) {
             const float rr = mul_rn(val, rs[k]);
             rew = add_rn(rew, rr);
-            float* sp = b.episode_sums + static_cast<size_t>(p.sum_row[k]) * N + i;
-            *sp = add_rn(*sp, rr);
+            tv[k] = rr;
         };
         const float ex = sub_rn(R[0], tr0x), ey = sub_rn(R[1], tr0y);
         const float te0 = mul_rn(ex, ex), te1 = mul_rn(ey, ey);   // square(proj_z(root) - trajectory[:, 0])
@@ -303,12 +307,21 @@ __global__ void __launch_bounds__(128) hopper_post_physics_kernel(const __grid_c
             for (int k = 0; k < 13; ++k) b.root_states[i * 13 + k] = R[k];
             fat = 0.0f;
             ep = 0;
-            for (int k = 0; k < K; ++k) {   // extras["episode"] (:235-239)
-                float* sp = b.episode_sums + static_cast<size_t>(k) * N + i;
-                atomicAdd(&s_acc[k], static_cast<double>(*sp));
-                *sp = 0.0f;
-            }
             atomicAdd(&s_acc[K + 1], 1.0);
+        }
+        // episode_sums += term (compute_reward) and, for an env that reset, extras["episode"] partial sums + clear (:235-239)
+#pragma unroll
+        for (int k = 0; k < B200GYM_HOPPER_NUM_TERMS; ++k) {
+            const int row = p.sum_row[k];
+            if (row >= 0) {
+                float* sp = b.episode_sums + static_cast<size_t>(row) * N + i;
+                float v = add_rn(*sp, tv[k]);
+                if (reset) {
+                    atomicAdd(&s_acc[row], static_cast<double>(v));
+                    v = 0.0f;
+                }
+                *sp = v;
+            }
         }
 
         // observations (hopper_trajectory.py:255-282) + clip (:128-129)

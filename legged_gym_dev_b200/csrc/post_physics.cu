@@ -17,8 +17,10 @@
 //   phase S  1 thread per env: body-frame vectors, commands, termination, reward assembly, in-place reset,
 //            first 12 observation columns — scalar work executed exactly once per env
 //   phase H' (rough only) height observations redone for the (rare) envs that reset: they use the post-reset height
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "philox.cuh"
 #include "../../include/b200gym.h"
@@ -44,6 +46,11 @@ constexpr int LPE = 4;     // lanes per env in phase W
 struct SqThr { float gt1, gt01, gt02, lt01; };
 constexpr int ND = B200GYM_NUM_DOF;
 constexpr int HPAD = 192;  // padded per-env stride of the raw height tile (>= 187)
+// Terrain window of one env staged by ONE 2-D TMA box load (cp.async.bulk.tensor.2d, SASS UTMALDG.2D): the 17 x 11 sample grid lies within
+// 0.95 m of the base, i.e. within +-10 cells at the shipped 0.1 m resolution; 22 rows (+1 for the min-of-3 neighbour) x 32 columns (the
+// window's first column is rounded down to a multiple of 8: the box origin of the innermost dimension must be 16-byte aligned — an
+// unaligned origin raises "illegal instruction", tools/probes/tma_probe_bisect.cu) = 1408 B = 11 x 128 B.
+constexpr int HW_ROWS = 22, HW_COLS = 32, HW_ELEMS = HW_ROWS * HW_COLS, HW_HALF = 10;
 // LeggedRobotTrajectory (legged_robot_trajectory.py:274-287): the 3 command columns become the N x rom.n trajectory block
 constexpr int TRAJ_W = B200GYM_TRAJ_WIDTH;
 template <bool TRAJ> struct ObsLayout {
@@ -87,8 +94,9 @@ __device__ __forceinline__ float sq3_rn(float x, float y, float z) { return add_
 // operation a separately rounded fp32 mul/add exactly as torch evaluates it, issued as packed f32x2 instructions:
 //   t = 2 * cross(q_yaw.xyz, p) = (-2 qz hy, 2 qz hx);  w = p + qw t + cross(q_yaw.xyz, t);  cell = trunc((w + base + border) / hs)
 struct HeightConsts { float2 border, neg_hs, rcp_hs; };
+template <bool PACKED>
 __device__ __forceinline__ void height_cells2(float2 hx, float2 hy, float qz, float qw, float bx, float by, const HeightConsts& c,
-                                              int rows, int cols, int& off0, int& off1) {
+                                              int rows, int cols, int& pk0, int& pk1) {
     const float2 qz2 = make_float2(qz, qz), nqz2 = make_float2(-qz, -qz), qw2 = make_float2(qw, qw);
     const float2 tx = __fmul2_rn(__fmul2_rn(qz2, hy), make_float2(-2.0f, -2.0f));   // == (-(qz*hy)) * 2
     const float2 ty = __fmul2_rn(__fmul2_rn(qz2, hx), make_float2(2.0f, 2.0f));
@@ -104,8 +112,13 @@ __device__ __forceinline__ void height_cells2(float2 hx, float2 hy, float qz, fl
     // .long() truncation + clip (legged_robot.py:903-907); the saturating conversion keeps huge values clipped
     const int ix0 = min(max(__float2int_rz(wx.x), 0), rows - 2), iy0 = min(max(__float2int_rz(wy.x), 0), cols - 2);
     const int ix1 = min(max(__float2int_rz(wx.y), 0), rows - 2), iy1 = min(max(__float2int_rz(wy.y), 0), cols - 2);
-    off0 = ix0 * cols + iy0;
-    off1 = ix1 * cols + iy1;
+    if (PACKED) {   // (row, column) of the cell, 16 bits each (the launcher checks rows, cols < 32768): the TMA path indexes a window
+        pk0 = (ix0 << 16) | iy0;
+        pk1 = (ix1 << 16) | iy1;
+    } else {        // element offset into the field: the gather path
+        pk0 = ix0 * cols + iy0;
+        pk1 = ix1 * cols + iy1;
+    }
 }
 
 __device__ __forceinline__ float wrap_to_pi(float a) {
@@ -169,13 +182,15 @@ struct TileSmem {
     float *bh, *zpost, *stage, *hsum, *unoise;
     float *traj, *perr, *tpush;
     float2 *pts, *yaw;
+    int16_t* hwin;     // [warps][2][HW_ROWS][HW_COLS] terrain windows of the env pair a warp is scanning (TMA destination, 128-byte aligned)
+    uint64_t* hbar;    // one mbarrier per warp
     double* acc;
     int* nreset;
     size_t bytes;
 };
 
 template <int TILE, bool ROUGH, bool TRAJ>
-__device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K, bool need_hpart) {
+__device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K, bool need_hpart, bool tma_heights = false) {
     Carver c{base, 0};
     TileSmem s;
     s.bar = c.take<uint64_t>(2);
@@ -219,7 +234,14 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
         s.hsum = need_hpart ? c.take<float>(TILE) : nullptr;
         s.unoise = c.take<float>(static_cast<size_t>(TILE * LPE / 32) * 2 * HPAD);   // per warp: noise uniforms of an env pair
         s.pts = c.take<float2>(HPAD);
+        s.hwin = nullptr, s.hbar = nullptr;
+        if (tma_heights) {
+            s.hbar = c.take<uint64_t>(TILE * LPE / 32);
+            c.off = (c.off + 127) & ~static_cast<size_t>(127);
+            s.hwin = c.take<int16_t>(static_cast<size_t>(TILE * LPE / 32) * 2 * HW_ELEMS);
+        }
     } else {
+        s.hwin = nullptr, s.hbar = nullptr;
         s.hraw = nullptr;
         s.bh = s.zpost = s.stage = s.hsum = s.unoise = nullptr;
         s.pts = nullptr;
@@ -234,14 +256,15 @@ __device__ __forceinline__ void coop_copy(T* dst, const T* src, int n) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
-template <int TILE, bool ROUGH, bool TRAJ>
+template <int TILE, bool ROUGH, bool TRAJ, bool HTMA = false>
 __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) post_physics_kernel(const __grid_constant__ B200LeggedParams p,
                                                                                const __grid_constant__ B200LeggedBuffers b,
                                                                                uint64_t step, long long env_off, int do_push,
-                                                                               const SqThr thr) {
+                                                                               const SqThr thr, const __grid_constant__ CUtensorMap hmap) {
+    constexpr int use_hmap = (ROUGH && HTMA) ? 1 : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int B = p.num_bodies, K = p.num_sum_rows, N = p.num_envs, O = p.num_obs;
-    const TileSmem s = carve_tile<TILE, ROUGH, TRAJ>(smem_raw, B, K, p.reward_scale[T_BASE_HEIGHT] != 0.0f);
+    const TileSmem s = carve_tile<TILE, ROUGH, TRAJ>(smem_raw, B, K, p.reward_scale[T_BASE_HEIGHT] != 0.0f, use_hmap != 0);
     const int tid = threadIdx.x;
     const int tile0 = blockIdx.x * TILE;
     const int nvalid = min(TILE, N - tile0);
@@ -254,6 +277,8 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
     pdl_wait();   // everything below reads what the torque kernels / the previous step wrote (incl. the device step counter)
     if (tid == 0) {
         mbar_init(s.bar, 1);
+        if (ROUGH && use_hmap)
+            for (int w = 0; w < TILE * LPE / 32; ++w) mbar_init(s.hbar + w, 1);
         fence_mbar_init();
         s.nreset[0] = 0;
         s.nreset[1] = do_push;
@@ -342,8 +367,36 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
         constexpr int NW = TILE * LPE / 32, RND = HPAD / 32;
         const int warp = tid >> 5, lane = tid & 31;
         float* un = s.unoise + warp * 2 * HPAD;
+        constexpr bool tma_h = use_hmap != 0;   // the launcher selects HTMA only for a heightfield (never mesh_plane)
+        int16_t* win = tma_h ? s.hwin + warp * 2 * HW_ELEMS : nullptr;
+        uint32_t hphase = 0;
         for (int e0 = 2 * warp; e0 < nvalid; e0 += 2 * NW) {
             const int ne = min(2, nvalid - e0);
+            int wx0[2] = {0, 0}, wy0[2] = {0, 0};
+            if (tma_h) {
+                // terrain windows of the pair: one 2-D box per env around the base cell, issued before the noise draws so that the
+                // copy overlaps them; rows / columns outside the field are zero-filled by the TMA unit and never addressed (the cell
+                // indices are clipped to the field, legged_robot.py:905-907)
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (k < ne) {
+                        const float* R = s.root + (e0 + k) * 13;
+                        wx0[k] = __float2int_rd(mul_rn(add_rn(R[0], p.border_size), inv_hs)) - HW_HALF;
+                        wy0[k] = (__float2int_rd(mul_rn(add_rn(R[1], p.border_size), inv_hs)) - HW_HALF) & ~7;
+                    }
+                }
+                fence_proxy_async();   // the previous pair's generic-proxy reads of the windows precede the async-proxy writes
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(s.hbar + warp, static_cast<uint32_t>(ne) * HW_ELEMS * 2);
+                __syncwarp();
+                if (lane < ne) {
+                    const int cy = lane == 0 ? wy0[0] : wy0[1], cx = lane == 0 ? wx0[0] : wx0[1];
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                                     smem_u32(win + lane * HW_ELEMS)),
+                                 "l"(reinterpret_cast<uint64_t>(&hmap)), "r"(cy), "r"(cx), "r"(smem_u32(s.hbar + warp))
+                                 : "memory");
+                }
+            }
             if (p.add_noise) {
                 // the Q (= 47) Philox blocks of an env hold the noise of its 4Q points: lane L draws block L of both envs, then
                 // the tails (blocks 32..Q-1) of the two envs share one more round (lanes 0-15 / 16-31); uniforms go through a
@@ -368,16 +421,36 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) po
 #pragma unroll
                 for (int r = 0; r < RND; ++r) raw[r] = 0;
                 if (!p.mesh_plane) {
-                    int off[RND];
+                    int pk[RND];
 #pragma unroll
                     for (int r = 0; r < RND; r += 2) {   // two points (rounds r, r+1) per packed instruction
                         const float2 pa = s.pts[32 * r + lane], pb = s.pts[32 * (r + 1) + lane];
-                        height_cells2(make_float2(pa.x, pb.x), make_float2(pa.y, pb.y), yw.x, yw.y, R[0], R[1], hc, rows, cols, off[r], off[r + 1]);
+                        height_cells2<tma_h>(make_float2(pa.x, pb.x), make_float2(pa.y, pb.y), yw.x, yw.y, R[0], R[1], hc, rows, cols, pk[r], pk[r + 1]);
                     }
+                    if (tma_h) {
+                        if (k == 0) {
+                            mbar_wait(s.hbar + warp, hphase);
+                            hphase ^= 1u;
+                        }
+                        const int16_t* w = win + k * HW_ELEMS;
+                        const int ox = wx0[k], oy = wy0[k];
 #pragma unroll
-                    for (int r = 0; r < RND; ++r) {   // 18 gathers issued together; padding points read a valid (unused) cell
-                        const int16_t* h = b.height_samples + off[r];
-                        raw[r] = min(min(static_cast<int>(__ldg(h)), static_cast<int>(__ldg(h + cols))), static_cast<int>(__ldg(h + 1)));
+                        for (int r = 0; r < RND; ++r) {   // samples from the staged window; a cell outside it (robot off the field: its
+                            const int lx = (pk[r] >> 16) - ox, ly = (pk[r] & 0xffff) - oy;   // clipped cells are far from the base) reads the field itself
+                            if (static_cast<unsigned>(lx) <= static_cast<unsigned>(HW_ROWS - 2) && static_cast<unsigned>(ly) <= static_cast<unsigned>(HW_COLS - 2)) {
+                                const int16_t* h = w + lx * HW_COLS + ly;
+                                raw[r] = min(min(static_cast<int>(h[0]), static_cast<int>(h[HW_COLS])), static_cast<int>(h[1]));
+                            } else {
+                                const int16_t* h = b.height_samples + (pk[r] >> 16) * cols + (pk[r] & 0xffff);
+                                raw[r] = min(min(static_cast<int>(__ldg(h)), static_cast<int>(__ldg(h + cols))), static_cast<int>(__ldg(h + 1)));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < RND; ++r) {   // 18 gathers issued together; padding points read a valid (unused) cell
+                            const int16_t* h = b.height_samples + pk[r];
+                            raw[r] = min(min(static_cast<int>(__ldg(h)), static_cast<int>(__ldg(h + cols))), static_cast<int>(__ldg(h + 1)));
+                        }
                     }
                 }
                 float* mh_out = b.measured_heights + static_cast<size_t>(tile0 + e) * H + lane;
@@ -1048,13 +1121,45 @@ static float sq_lt(float t) {
     return y;
 }
 
-template <int TILE, bool ROUGH, bool TRAJ = false>
-int launch_post_physics(const B200LeggedParams& p, const B200LeggedBuffers& b, uint64_t step, long long env_off, int do_push,
-                        cudaStream_t stream) {
-    const size_t smem = carve_tile<TILE, ROUGH, TRAJ>(nullptr, p.num_bodies, p.num_sum_rows, p.reward_scale[T_BASE_HEIGHT] != 0.0f).bytes;
+// Tensor map of the int16 heightfield [rows, cols] (cuTensorMapEncodeTiled through the runtime's driver entry point: no link against
+// libcuda), box = one env window; cached per (pointer, rows, cols).  Returns false when the field cannot be described (row pitch not a
+// multiple of 16 bytes, misaligned base, no driver entry point): the kernel then gathers from the field directly.
+static bool height_tensor_map(const int16_t* field, int rows, int cols, CUtensorMap* out) {
+    struct Entry { const int16_t* f; int r, c; CUtensorMap m; bool ok; };
+    static Entry cache[8];
+    static int used = 0;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].f == field && cache[i].r == rows && cache[i].c == cols) {
+            *out = cache[i].m;
+            return cache[i].ok;
+        }
+    Entry e{field, rows, cols, {}, false};
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if ((cols % 8) == 0 && b200_aligned16(field) && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn &&
+        q == cudaDriverEntryPointSuccess) {
+        const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+        const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cols) * 2};
+        const cuuint32_t box[2] = {HW_COLS, HW_ROWS};
+        const cuuint32_t es[2] = {1, 1};
+        e.ok = reinterpret_cast<EncodeFn>(fn)(&e.m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t*>(field), gdim, gstr, box, es,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    cache[used < 8 ? used++ : 7] = e;
+    *out = e.m;
+    return e.ok;
+}
+
+template <int TILE, bool ROUGH, bool TRAJ, bool HTMA>
+int launch_post_physics_impl(const B200LeggedParams& p, const B200LeggedBuffers& b, uint64_t step, long long env_off, int do_push,
+                             cudaStream_t stream, const CUtensorMap& hmap) {
+    const size_t smem = carve_tile<TILE, ROUGH, TRAJ>(nullptr, p.num_bodies, p.num_sum_rows, p.reward_scale[T_BASE_HEIGHT] != 0.0f, HTMA).bytes;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(post_physics_kernel<TILE, ROUGH, TRAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(post_physics_kernel<TILE, ROUGH, TRAJ, HTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
         B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "post_physics: cannot reserve %zu B of shared memory: %s", smem,
                      cudaGetErrorString(e));
@@ -1062,13 +1167,34 @@ int launch_post_physics(const B200LeggedParams& p, const B200LeggedBuffers& b, u
     }
     const int grid = (p.num_envs + TILE - 1) / TILE;
     static const SqThr thr = {sq_gt(1.0f), sq_gt(0.1f), sq_gt(0.2f), sq_lt(0.1f)};
-    b200_launch_pdl(p.num_envs, post_physics_kernel<TILE, ROUGH, TRAJ>, dim3(grid), dim3(TILE * LPE), smem, stream, p, b, step, env_off, do_push, thr);
+    b200_launch_pdl(p.num_envs, post_physics_kernel<TILE, ROUGH, TRAJ, HTMA>, dim3(grid), dim3(TILE * LPE), smem, stream, p, b, step, env_off, do_push,
+                    thr, hmap);
     B200_LAUNCH_CHECK("post_physics");
 #if PP_FINALIZE_KERNEL
     b200_launch_pdl(p.num_envs, extras_finalize_kernel, dim3(1), dim3(32), 0, stream, p, b);
     B200_LAUNCH_CHECK("extras_finalize");
 #endif
     return B200GYM_OK;
+}
+
+template <int TILE, bool ROUGH, bool TRAJ = false>
+int launch_post_physics(const B200LeggedParams& p, const B200LeggedBuffers& b, uint64_t step, long long env_off, int do_push,
+                        cudaStream_t stream) {
+    // rough envs on a heightfield: the terrain window of every env is staged in shared memory by a 2-D TMA box load (B200GYM_HEIGHT_TMA=0:
+    // per-point gathers from the field, the round-1 path — A/B in profiles/)
+    static int want_tma = -1;
+    if (want_tma < 0) {
+        const char* t = getenv("B200GYM_HEIGHT_TMA");
+        want_tma = t ? atoi(t) : 1;
+    }
+    CUtensorMap hmap;
+    memset(&hmap, 0, sizeof(hmap));
+    const bool within = p.horizontal_scale > 0.0f && 0.95f / p.horizontal_scale <= static_cast<float>(HW_HALF) - 0.5f;   // the scan fits the window
+    const int use_hmap = (ROUGH && want_tma && !p.mesh_plane && within && p.terrain_rows < 32768 && p.terrain_cols < 32768 && height_tensor_map(b.height_samples, p.terrain_rows, p.terrain_cols, &hmap)) ? 1 : 0;
+    if constexpr (ROUGH) {
+        if (use_hmap) return launch_post_physics_impl<TILE, true, TRAJ, true>(p, b, step, env_off, do_push, stream, hmap);
+    }
+    return launch_post_physics_impl<TILE, ROUGH, TRAJ, false>(p, b, step, env_off, do_push, stream, hmap);
 }
 
 }  // namespace
@@ -1104,6 +1230,8 @@ extern "C" int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedB
     B200_REQUIRE(!rough || b->measured_heights, B200GYM_EINVAL, "post_physics: measured_heights buffer missing");
     B200_REQUIRE(!rough || p->mesh_plane || (b->height_samples && p->terrain_rows >= 2 && p->terrain_cols >= 2), B200GYM_EINVAL,
                  "post_physics: height_samples missing");
+    B200_REQUIRE(!rough || p->mesh_plane || (p->terrain_rows < 32768 && p->terrain_cols < 32768), B200GYM_EINVAL,
+                 "post_physics: heightfields of up to 32767 x 32767 cells (cell coordinates are packed 16 + 16 bits)");
     B200_REQUIRE(!p->terrain_curriculum || (b->terrain_levels && b->terrain_types && b->terrain_origins), B200GYM_EINVAL,
                  "post_physics: terrain curriculum buffers missing");
     B200_REQUIRE(!p->zero_lstm_on_reset || (b->lstm_h && b->lstm_c), B200GYM_EINVAL, "post_physics: LSTM state buffers missing");
