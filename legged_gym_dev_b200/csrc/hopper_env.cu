@@ -81,20 +81,40 @@ __global__ void __launch_bounds__(256) hopper_prologue_kernel(const __grid_const
     b.time_until_next_push[i] = t_out;
 }
 
-__global__ void __launch_bounds__(128, 5) hopper_post_physics_kernel(const __grid_constant__ B200HopperEnvParams p,
-                                                                  const __grid_constant__ B200HopperEnvBuffers b, unsigned long long step,
-                                                                  long long env_off) {
+// The row-strided tensors of a CTA's 128 envs (root [., 13], contacts [., B, 3], trajectory [., 20] in; observations [., 38] out) are contiguous
+// byte ranges: they move between HBM and shared memory with coalesced cooperative copies (odd row strides in shared memory: conflict-free
+// per-env access), the [., 4] tensors are read as one float4 per thread.  (First version: every thread walked its own rows in global memory —
+// 13 + 15 + 20 strided loads and 38 strided stores per env, 40 % of HBM.)
+constexpr int HT_TILE = 128, HS_TRAJ = B200GYM_TRAJ_WIDTH + 1, HS_OBS = B200GYM_HOPPER_TRAJ_NUM_OBS + 1;
+
+__global__ void __launch_bounds__(HT_TILE, 4) hopper_post_physics_kernel(const __grid_constant__ B200HopperEnvParams p,
+                                                                        const __grid_constant__ B200HopperEnvBuffers b, unsigned long long step,
+                                                                        long long env_off) {
     const int N = p.num_envs, K = p.num_sum_rows, B = p.num_bodies;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tile0 = blockIdx.x * HT_TILE, t = threadIdx.x;
+    const int e = tile0 + t, nvalid = min(HT_TILE, N - tile0);
+    extern __shared__ __align__(16) float hsm[];
+    float* s_root = hsm;                                   // [128][13]
+    float* s_contact = s_root + HT_TILE * 13;              // [128][3B]
+    float* s_traj = s_contact + HT_TILE * 3 * B;           // [128][21]
+    float* s_obs = s_traj + HT_TILE * HS_TRAJ;             // [128][39]
     __shared__ double s_acc[B200GYM_HOPPER_NUM_TERMS + 2];
-    if (threadIdx.x < K + 2) s_acc[threadIdx.x] = 0.0;
+    if (t < K + 2) s_acc[t] = 0.0;
+    {
+        const float* g = b.root_states + static_cast<size_t>(tile0) * 13;
+        for (int q = t; q < nvalid * 13; q += HT_TILE) s_root[q] = g[q];
+        g = b.contact_forces + static_cast<size_t>(tile0) * 3 * B;
+        for (int q = t; q < nvalid * 3 * B; q += HT_TILE) s_contact[q] = g[q];
+        g = b.trajectory + static_cast<size_t>(tile0) * B200GYM_TRAJ_WIDTH;
+        for (int q = t; q < nvalid * B200GYM_TRAJ_WIDTH; q += HT_TILE) s_traj[(q / B200GYM_TRAJ_WIDTH) * HS_TRAJ + q % B200GYM_TRAJ_WIDTH] = g[q];
+    }
     __syncthreads();
     if (e < N) {
         const size_t i = static_cast<size_t>(e);
         const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<unsigned long long>(env_off) + i, step);
         float R[13];
 #pragma unroll
-        for (int k = 0; k < 13; ++k) R[k] = b.root_states[i * 13 + k];
+        for (int k = 0; k < 13; ++k) R[k] = s_root[t * 13 + k];
         if (e == 0 && p.push_robots && *b.push_flag != 0u) {   // the [N, 1]-mask quirk: env 0 rides along with every push of the process
             push_draw(p, rng, R);
 #pragma unroll
@@ -112,9 +132,9 @@ __global__ void __launch_bounds__(128, 5) hopper_post_physics_kernel(const __gri
         const float blv[3] = {b.base_lin_vel[i * 3], b.base_lin_vel[i * 3 + 1], b.base_lin_vel[i * 3 + 2]};
         const float bav[3] = {b.base_ang_vel[i * 3], b.base_ang_vel[i * 3 + 1], b.base_ang_vel[i * 3 + 2]};
         const float pg[3] = {b.projected_gravity[i * 3], b.projected_gravity[i * 3 + 1], b.projected_gravity[i * 3 + 2]};
-        const float* traj = b.trajectory + i * (B200GYM_TRAJ_WIDTH);
+        const float* traj = s_traj + t * HS_TRAJ;
         const float tr0x = traj[0], tr0y = traj[1];
-        const float* cf = b.contact_forces + i * B * 3;
+        const float* cf = s_contact + t * B * 3;
         long long ep = reinterpret_cast<long long*>(b.episode_length_buf)[i] + 1;
 
         // termination (legged_robot_trajectory.py:194-202)
@@ -325,7 +345,7 @@ __global__ void __launch_bounds__(128, 5) hopper_post_physics_kernel(const __gri
         }
 
         // observations (hopper_trajectory.py:255-282) + clip (:128-129)
-        float* o = b.obs_buf + i * B200GYM_HOPPER_TRAJ_NUM_OBS;
+        float* o = s_obs + t * HS_OBS;
         float head[14] = {mul_rn(R[2], p.z_pos_scale), R[3], R[4], R[5], R[6], mul_rn(blv[0], p.lin_vel_scale), mul_rn(blv[1], p.lin_vel_scale),
                           mul_rn(blv[2], p.lin_vel_scale), mul_rn(bav[0], p.ang_vel_scale), mul_rn(bav[1], p.ang_vel_scale), mul_rn(bav[2], p.ang_vel_scale),
                           mul_rn(qd[1], p.dof_vel_scale), mul_rn(qd[2], p.dof_vel_scale), mul_rn(qd[3], p.dof_vel_scale)};
@@ -368,7 +388,12 @@ __global__ void __launch_bounds__(128, 5) hopper_post_physics_kernel(const __gri
         b.time_out_buf[i] = time_out ? 1 : 0;
     }
     __syncthreads();
-    if (threadIdx.x < K + 2 && s_acc[threadIdx.x] != 0.0) atomicAdd(&b.ws_sums[threadIdx.x], s_acc[threadIdx.x]);
+    {
+        float* g = b.obs_buf + static_cast<size_t>(tile0) * B200GYM_HOPPER_TRAJ_NUM_OBS;
+        for (int q = t; q < nvalid * B200GYM_HOPPER_TRAJ_NUM_OBS; q += HT_TILE)
+            g[q] = s_obs[(q / B200GYM_HOPPER_TRAJ_NUM_OBS) * HS_OBS + q % B200GYM_HOPPER_TRAJ_NUM_OBS];
+    }
+    if (t < K + 2 && s_acc[t] != 0.0) atomicAdd(&b.ws_sums[t], s_acc[t]);
 }
 
 __global__ void hopper_extras_finalize_kernel(const __grid_constant__ B200HopperEnvParams p, const __grid_constant__ B200HopperEnvBuffers b) {
@@ -405,7 +430,14 @@ extern "C" int b200gym_hopper_post_physics(const B200HopperEnvParams* p, const B
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     hopper_prologue_kernel<<<(p->num_envs + 255) / 256, 256, 0, st>>>(*p, *b, step, env_id_offset);
     B200_LAUNCH_CHECK("hopper_prologue");
-    hopper_post_physics_kernel<<<(p->num_envs + 127) / 128, 128, 0, st>>>(*p, *b, step, env_id_offset);
+    const size_t smem = static_cast<size_t>(HT_TILE) * (13 + 3 * p->num_bodies + HS_TRAJ + HS_OBS) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(hopper_post_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "hopper_post_physics: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+        configured = smem;
+    }
+    hopper_post_physics_kernel<<<(p->num_envs + HT_TILE - 1) / HT_TILE, HT_TILE, smem, st>>>(*p, *b, step, env_id_offset);
     B200_LAUNCH_CHECK("hopper_post_physics");
     hopper_extras_finalize_kernel<<<1, 32, 0, st>>>(*p, *b);
     B200_LAUNCH_CHECK("hopper_extras_finalize");

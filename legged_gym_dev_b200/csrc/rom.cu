@@ -522,6 +522,9 @@ __global__ void raibert_policy_kernel(const float* __restrict__ obs, int stride,
 }
 
 // ---- persistent rollout: one data-collection epoch ---------------------------------------------------
+#ifndef ROLLOUT_MINBLOCKS
+#define ROLLOUT_MINBLOCKS 4   // resident CTAs per SM the register allocation must allow (A/B: profiles/r2_rom_rollout_occupancy.txt)
+#endif
 constexpr int RB = 128;   // envs (threads) per CTA
 constexpr int TB = 8;     // timesteps staged per flush
 
@@ -536,7 +539,7 @@ __device__ __forceinline__ void flush_rows(float* __restrict__ dst, const float*
 }
 
 template <int W>
-__global__ void __launch_bounds__(RB) rom_rollout_kernel(const __grid_constant__ B200RomParams p, const __grid_constant__ B200RomState s,
+__global__ void __launch_bounds__(RB, ROLLOUT_MINBLOCKS) rom_rollout_kernel(const __grid_constant__ B200RomParams p, const __grid_constant__ B200RomState s,
                                                          float* __restrict__ obs_io, int T, float* __restrict__ lx, float* __restrict__ lz,
                                                          float* __restrict__ lpz, float* __restrict__ lv, uint8_t* __restrict__ ldone,
                                                          long long env_off) {
