@@ -293,7 +293,10 @@ __global__ void rom_init_kernel(const __grid_constant__ B200RomParams p, const _
 }
 
 template <int RN, int W>
-__global__ void __launch_bounds__(128) rom_step_kernel(const __grid_constant__ B200RomParams p, const __grid_constant__ B200RomState s,
+#ifndef ROM_STEP_MINBLOCKS
+#define ROM_STEP_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, ROM_STEP_MINBLOCKS) rom_step_kernel(const __grid_constant__ B200RomParams p, const __grid_constant__ B200RomState s,
                                                        const float* __restrict__ action, const uint8_t* __restrict__ mask,
                                                        long long env_off) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
