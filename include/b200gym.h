@@ -155,7 +155,9 @@ int b200gym_post_physics(const B200LeggedParams* p, const B200LeggedBuffers* b, 
  * last_dof_vel / feet_air_time / episode_length_buf cleared, reset_buf set, episode_sums folded into extras_out (means over the
  * reset envs / max_episode_length_s, terrain-level mean over all envs) and cleared, actuator LSTM state zeroed.  time_out_buf,
  * obs_buf and rew_buf are left alone, as in the reference.  `event` keys the Philox draws (sites as in b200gym_post_physics); pass
- * a value no env step uses (the Python mirror: (number of external resets << 40) | common_step_counter).  Not for traj_mode. */
+ * a value no env step uses (the Python mirror: (number of external resets << 40) | common_step_counter).  traj_mode
+ * (LeggedRobotTrajectory.reset_idx, legged_robot_trajectory.py:204-246): no command resample; prev_error is rewritten from the
+ * trajectory buffer and the new root (:233); the caller then resets the generators (b200gym_rom_reset_from_root with the same mask). */
 int b200gym_legged_reset_idx(const B200LeggedParams* p, const B200LeggedBuffers* b, const uint8_t* reset_mask, uint64_t event,
                              int64_t env_id_offset, void* stream);
 

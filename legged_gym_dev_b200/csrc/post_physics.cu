@@ -1077,8 +1077,13 @@ __global__ void __launch_bounds__(128) reset_idx_kernel(const __grid_constant__ 
         nr[11] = affine_rn(1.0f, philox::u01(w1.x), -0.5f), nr[12] = affine_rn(1.0f, philox::u01(w1.y), -0.5f);
 #pragma unroll
         for (int k = 0; k < 13; ++k) b.root_states[e * 13 + k] = nr[k];
-        resample_commands(p, thr, rng, philox::CMD_RESET, c0, c1, c2, c3);
-        *reinterpret_cast<float4*>(b.commands + e * 4) = make_float4(c0, c1, c2, c3);
+        if (!p.traj_mode) {
+            resample_commands(p, thr, rng, philox::CMD_RESET, c0, c1, c2, c3);
+            *reinterpret_cast<float4*>(b.commands + e * 4) = make_float4(c0, c1, c2, c3);
+        } else {   // legged_robot_trajectory.py:233: prev_error from the (stale) trajectory clone and the NEW root; the caller resets the generator
+            const float d0 = b.trajectory[static_cast<size_t>(e) * TRAJ_W] - nr[0], d1 = b.trajectory[static_cast<size_t>(e) * TRAJ_W + 1] - nr[1];
+            b.prev_error[e * 2] = d0 * d0, b.prev_error[e * 2 + 1] = d1 * d1;
+        }
         *reinterpret_cast<float4*>(b.feet_air_time + e * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         reinterpret_cast<long long*>(b.episode_length_buf)[e] = 0;
         b.reset_buf[e] = 1;
@@ -1276,7 +1281,8 @@ extern "C" int b200gym_legged_reset_idx(const B200LeggedParams* p, const B200Leg
                                         int64_t env_id_offset, void* stream) {
     B200_REQUIRE(p && b && reset_mask, B200GYM_EINVAL, "legged_reset_idx: null argument");
     B200_REQUIRE(p->num_envs > 0 && p->num_sum_rows >= 0 && p->num_sum_rows <= B200GYM_NUM_REWARD_TERMS, B200GYM_EINVAL, "legged_reset_idx: bad sizes");
-    B200_REQUIRE(p->traj_mode == 0, B200GYM_EINVAL, "legged_reset_idx: the trajectory env resets through its own generator path");
+    B200_REQUIRE(p->traj_mode == 0 || (b->trajectory && b->prev_error && !p->terrain_curriculum), B200GYM_EINVAL,
+                 "legged_reset_idx: traj_mode needs the trajectory / prev_error buffers (and has no terrain curriculum)");
     B200_REQUIRE(!p->terrain_curriculum || (b->terrain_levels && b->terrain_types && b->terrain_origins), B200GYM_EINVAL,
                  "legged_reset_idx: terrain curriculum buffers missing");
     B200_REQUIRE(!p->zero_lstm_on_reset || (b->lstm_h && b->lstm_c), B200GYM_EINVAL, "legged_reset_idx: LSTM state buffers missing");

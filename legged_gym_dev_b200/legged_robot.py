@@ -363,11 +363,6 @@ class LeggedRobot:
         Draws are keyed by an event no env step uses: (external reset count << 40) | common_step_counter."""
         if len(env_ids) == 0:
             return
-        if self.params.traj_mode:
-            # LeggedRobotTrajectory.reset_idx also resets the generators from the new roots: that sequence runs inside the fused
-            # step (legged_robot_trajectory.py), so an external reset of the trajectory env is deferred to the next step
-            self.episode_length_buf[env_ids] = int(self.max_episode_length) + 1
-            return
         if getattr(self, "_reset_mask", None) is None:
             self._reset_mask = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
             self._ext_resets = 0
@@ -379,6 +374,8 @@ class LeggedRobot:
                                                self.env_id_offset, torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             _lib.check(rc, "legged_reset_idx")
+        if self.params.traj_mode:                                          # legged_robot_trajectory.py:225 (after the root redraw)
+            self.reset_traj(env_ids)
         self.physics.commit_resets(self._reset_mask.view(torch.bool))
 
     def reset(self):

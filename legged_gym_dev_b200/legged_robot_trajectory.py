@@ -170,14 +170,6 @@ class LeggedRobotTrajectory(LeggedRobot):
         self._event_end("post_physics", ev)
         self.physics.commit_resets(self.reset_buf)
 
-    def reset(self):
-        """BaseTask.reset (base_task.py:108-112): reset_idx(all envs), then one zero-action step.  The per-step resets live in the
-        fused kernel, so the forced reset rides on that first step; the generators are reset at the robots' current positions
-        first, because a never-initialised generator evaluates 0/0 in its ramp input (rom_dynamics.py:552 with
-        t_final == ramp_t_start == 0) — a state the reference never steps from, its reset_idx resets the generator first."""
-        self.reset_traj(torch.arange(self.num_envs, device=self.device))
-        return super().reset()
-
     def reset_traj(self, env_ids):                                        # :248-253 (stand-alone use)
         mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         mask[env_ids] = True

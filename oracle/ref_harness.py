@@ -362,13 +362,16 @@ def _install_trajectory_wrappers(ref, ltmod):
     LT = ltmod.LeggedRobotTrajectory
     rng_shim.install()
     all_ids = lambda s: np.arange(s.num_envs)
-    _wrap(LT, "_push_robots", lambda s, push_idx: (push_idx.nonzero().flatten(), s.common_step_counter, [(P.SITE_PUSH, 0)]))
-    _wrap(LT, "_reset_dofs", lambda s, env_ids: (env_ids, s.common_step_counter, [(P.SITE_RESET_DOF, 0)]))
+    # draw event: common_step_counter inside a step; an EXTERNAL reset_idx keys its draws with (external reset count << 40) | step, as for
+    # the base env (oracle/port_legged.py reset_idx)
+    ev = lambda s: getattr(s, "_shim_event", None) or s.common_step_counter
+    _wrap(LT, "_push_robots", lambda s, push_idx: (push_idx.nonzero().flatten(), ev(s), [(P.SITE_PUSH, 0)]))
+    _wrap(LT, "_reset_dofs", lambda s, env_ids: (env_ids, ev(s), [(P.SITE_RESET_DOF, 0)]))
     _wrap(LT, "_reset_root_states",
-          lambda s, env_ids: (env_ids, s.common_step_counter,
+          lambda s, env_ids: (env_ids, ev(s),
                               [(P.SITE_RESET_XY, 0), (P.SITE_RESET_VEL, 0)] if s.custom_origins
                               else [(P.SITE_RESET_VEL, 0)]))
-    _wrap(LT, "compute_observations", lambda s: (all_ids(s), s.common_step_counter, [(P.SITE_OBS_NOISE, 0)]))
+    _wrap(LT, "compute_observations", lambda s: (all_ids(s), ev(s), [(P.SITE_OBS_NOISE, 0)]))
 
     # the push-timer redraw is inline in post_physics_step (:175-178): an outer context resolved at draw time
     def pps_ctx(self):
@@ -376,6 +379,28 @@ def _install_trajectory_wrappers(ref, ltmod):
         ev = lambda call, hist: self.common_step_counter
         return (ids, ev, [(P.SITE_PUSH_TIMER, 0)])
     _wrap(LT, "post_physics_step", pps_ctx)
+    if (LT, "reset_idx") not in _wrapped:
+        _wrapped.add((LT, "reset_idx"))
+        orig_reset, orig_pps = LT.reset_idx, LT.post_physics_step
+
+        def post_physics_step(self):
+            self._in_pps = True
+            try:
+                return orig_pps(self)
+            finally:
+                self._in_pps = False
+
+        def reset_idx(self, env_ids):
+            external = not getattr(self, "_in_pps", False) and hasattr(self, "_shim_seed") and len(env_ids) > 0
+            if external:
+                self._ext_resets = getattr(self, "_ext_resets", 0) + 1
+                self._shim_event = (self._ext_resets << 40) | int(self.common_step_counter)
+            try:
+                return orig_reset(self, env_ids)
+            finally:
+                self._shim_event = None
+        LT.reset_idx = reset_idx
+        LT.post_physics_step = post_physics_step
 
     if (LT, "reset_traj") not in _wrapped:
         _wrapped.add((LT, "reset_traj"))

@@ -275,17 +275,33 @@ def test_external_reset_matches_oracle(name, N):
         LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} step {s} after reset(): ")
 
 
-def test_trajectory_env_reset_then_steps_are_finite():
-    """AnymalTrajectory.reset() (BaseTask.reset: reset all, one zero-action step) followed by steps never produces NaNs — the
-    generators are reset before the first generator step (a never-reset generator evaluates 0/0, rom_dynamics.py:552)."""
-    case = LC.build_case("traj_flat_allterms", 512)
+@pytest.mark.parametrize("name,N", [("traj_flat_allterms", 512), ("traj_rough_lstm_allterms", 260)])
+def test_trajectory_env_external_reset_matches_oracle(name, N):
+    """AnymalTrajectory.reset() / reset_idx(env_ids) from outside step() (legged_robot_trajectory.py:204-246 + base_task.py:111-119) against
+    the trajectory port (pinned to the reference by test_trajectory_port_external_reset_tracks_unmodified_reference): masked reset launch +
+    generator reset from the new roots, immediate, generator state included; reset() starts the generators, so nothing is ever NaN."""
+    case = LC.build_case(name, N)
+    port, phys = LC.make_port(case)
     env = LC.make_fused(case)
+    port.reset(phys)
     obs, _ = env.reset()
-    assert torch.isfinite(obs).all() and bool(env.reset_buf.all())
-    for s in range(12):
-        obs, _, rew, dones, extras = env.step(case.tape.actions[s % 8].cuda())
-        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
-        assert torch.isfinite(env.prev_error).all() and torch.isfinite(env.trajectory).all()
+    assert torch.isfinite(obs).all()
+    LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} reset(): ")
+    for s in range(4):
+        a = case.tape.actions[s % case.tape.frames]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} step {s} after reset(): ")
+    ids = torch.arange(2, N, 3)
+    port.reset_idx(ids)
+    env.reset_idx(ids.cuda())
+    LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} partial reset: ")
+    for s in range(4, 12):
+        a = case.tape.actions[s % case.tape.frames]
+        port.step(a.clone(), phys)
+        obs, _, rew, _, _ = env.step(a.cuda())
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and torch.isfinite(env.prev_error).all()
+        LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"{name} step {s} after the partial reset: ")
     assert float(env.traj_gen.k.min()) >= 0
 
 

@@ -301,6 +301,60 @@ def test_trajectory_port_tracks_unmodified_reference(name):
     assert resets > N // 2 and pushes > 0
 
 
+@pytest.mark.reference
+@pytest.mark.parametrize("name", ["traj_flat_allterms", "traj_rough_lstm_allterms"])
+def test_trajectory_port_external_reset_tracks_unmodified_reference(name):
+    """LeggedRobotTrajectory.reset_idx / BaseTask.reset called from outside step() (legged_robot_trajectory.py:204-246, base_task.py:111-119):
+    the trajectory port's external reset against the reference's own methods, generator state included."""
+    from oracle import ref_harness as H
+    N = 96
+    case = LC.build_case(name, N)
+    task, rs, _, lstm, over = LC.CASES[name]
+    env = H.make_reference_anymal_trajectory(task, N, case.tape, seed=case.seed, reward_scales=rs, use_actuator_network=lstm,
+                                             heightfield=case.terrain["height_samples"] if case.rough else None,
+                                             terrain_origins=case.terrain["terrain_origins"] if case.rough else None,
+                                             episode_lengths=case.ep, time_until_next_push=case.tpush, overrides=over)
+    if case.rough:
+        env.env_origins[:] = case.terrain["env_origins"]
+    port, phys = LC.make_port(case)
+
+    def check(tag):
+        tg, g = env.traj_gen, port.gen
+        assert_exact(port.reset_buf, env.reset_buf.bool(), tag + "reset")
+        assert_exact(port.time_out_buf, env.time_out_buf.bool(), tag + "time_out")
+        assert_exact(port.episode_length_buf, env.episode_length_buf, tag + "ep_len")
+        assert_exact(g.k, tg.k, tag + "gen k")
+        for k in ("root_states", "dof_state", "feet_air_time", "last_actions", "last_dof_vel", "obs_buf", "rew_buf", "trajectory", "prev_error"):
+            assert_close(getattr(port, k), getattr(env, k), 1.0, tag + k)
+        assert_close(g.traj, tg.trajectory, 1.0, tag + "gen trajectory")
+        assert_close(g.v, tg.v, 1.0, tag + "gen v")
+        for k in env.episode_sums:
+            assert_close(port.episode_sums[k], env.episode_sums[k], 1.0, tag + "sum_" + k)
+        if "episode" in env.extras:
+            for k in env.extras["episode"]:
+                assert_close(port.extras["episode"][k], env.extras["episode"][k], 1.0, tag + "extras " + k)
+
+    o1, _ = env.reset()
+    o2, _ = port.reset(phys)
+    assert_close(o2, o1, 1.0, "reset() obs")
+    check("reset(): ")
+    for s in range(4):
+        a = case.tape.actions[s % case.tape.frames]
+        env.step(a.clone())
+        port.step(a.clone(), phys)
+        check(f"step {s} after reset(): ")
+    ids = torch.arange(0, N, 3)
+    env.reset_idx(ids)
+    port.reset_idx(ids)
+    check("partial reset: ")
+    for s in range(4, 8):
+        a = case.tape.actions[s % case.tape.frames]
+        env.step(a.clone())
+        port.step(a.clone(), phys)
+        check(f"step {s} after the partial reset: ")
+    assert np.array_equal(port.gen.ctr, env._traj_shim.ctr)
+
+
 def test_trajectory_cfg_tables_match_reference_objects():
     """configs.py's anymal trajectory tables == the reference's cfg classes (+ the documented completion) after flattening."""
     if not os.path.isdir("/root/reference/legged_gym"):
