@@ -396,12 +396,10 @@ class LeggedRobot:
         """extras["episode"] (legged_robot.py:175-182) from RAW per-step statistics `raw` [..., K + 2] = (per-term sums over the envs
         that reset, sum of terrain levels, number of resets), e.g. `_extras_raw` rows summed over the ranks by ONE all-reduce: the
         means a single process over all envs would log.  Rows without a reset give NaN (nothing to average)."""
-        p, K = self.params, len(self.params.active_terms)
-        cnt = raw[..., K + 1]
-        out = {"rew_" + n: raw[..., i] / cnt / p.max_episode_length_s for i, n in enumerate(p.active_terms)}
-        if p.terrain_curriculum:
-            out["terrain_level"] = raw[..., K] / float(total_envs if total_envs is not None else self.num_envs)
-        return out
+        from .sharding import combine_episode_stats
+        p = self.params
+        return combine_episode_stats(raw, p.active_terms, p.max_episode_length_s, total_envs if total_envs is not None else self.num_envs,
+                                     terrain_level=p.terrain_curriculum)
 
 
 def cfg_num_commands(cfg):

@@ -22,6 +22,18 @@ def combine_advantage_stats(stats):
     return mean, torch.sqrt(var)
 
 
+def combine_episode_stats(raw, term_names, max_episode_length_s, total_envs, terrain_level=False):
+    """extras["episode"] (legged_robot.py:175-182) from RAW per-step rows `raw` [..., K + 2] = (per-term sums over the envs that reset, sum of
+    terrain levels over all envs, number of resets) — the rows the step kernel leaves in `extras_raw`, summed over the env shards by ONE
+    all-reduce: the means a single process over all envs would log.  Rows without a reset give NaN (nothing to average)."""
+    K = len(term_names)
+    cnt = raw[..., K + 1]
+    out = {"rew_" + n: raw[..., i] / cnt / max_episode_length_s for i, n in enumerate(term_names)}
+    if terrain_level:
+        out["terrain_level"] = raw[..., K] / float(total_envs)
+    return out
+
+
 def init_distributed(device=None):
     """Reads RANK / LOCAL_RANK / WORLD_SIZE (torchrun) and sets up NCCL over NVLink; returns (rank, local_rank, world)."""
     import os

