@@ -397,6 +397,11 @@ typedef struct B200HopperEnvBuffers {
     uint32_t* push_flag;          /* 1 word, zero-initialised */
 } B200HopperEnvBuffers;
 int b200gym_hopper_post_physics(const B200HopperEnvParams* p, const B200HopperEnvBuffers* b, uint64_t step, int64_t env_id_offset, void* stream);
+/* LeggedRobotTrajectory.reset_idx(env_ids) as an external call for the Hopper (legged_robot_trajectory.py:204-246 with the Hopper's _reset_* methods;
+ * HopperTrajectory.reset, hopper_trajectory.py:286-296) for the envs flagged in reset_mask (uint8 [N]); draws keyed by `event` (the reference's own
+ * call sequence keys them with common_step_counter).  The caller then resets the generators: b200gym_rom_reset_from_root with the same mask. */
+int b200gym_hopper_reset_idx(const B200HopperEnvParams* p, const B200HopperEnvBuffers* b, const uint8_t* reset_mask, uint64_t event,
+                             int64_t env_id_offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Group G — rsl_rl rollout storage + PPO update (rsl_rl v1.0.2, a fork of which the reference imports at

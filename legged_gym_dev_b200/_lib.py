@@ -226,6 +226,8 @@ def lib():
     L.b200gym_legged_reset_idx.restype = C.c_int
     L.b200gym_hopper_post_physics.argtypes = [C.POINTER(HopperEnvParamsPOD), C.POINTER(HopperEnvBuffersPOD), C.c_uint64, C.c_int64, vp]
     L.b200gym_hopper_post_physics.restype = C.c_int
+    L.b200gym_hopper_reset_idx.argtypes = [C.POINTER(HopperEnvParamsPOD), C.POINTER(HopperEnvBuffersPOD), vp, C.c_uint64, C.c_int64, vp]
+    L.b200gym_hopper_reset_idx.restype = C.c_int
     for name in ("b200gym_pd_torques", "b200gym_set_actuator_net", "b200gym_lstm_torques", "b200gym_post_physics"):
         getattr(L, name).restype = C.c_int
     rp, rs = C.POINTER(RomParamsPOD), C.POINTER(RomStatePOD)
@@ -334,6 +336,27 @@ def ptr(t):
 
 def stream_ptr(device=None):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_bound_device = None
+
+
+def require_current_device(device):
+    """One process drives one GPU: the library keeps per-process state (constant-memory actuator net, kernel attributes, SM
+    count) for the device it first ran on.  Raises when an object is created for a device that is not the current CUDA device, or for a
+    second device in the same process, instead of computing with another device's constants."""
+    global _bound_device
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"b200gym runs on CUDA devices only (got {dev})")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        raise RuntimeError(f"b200gym: device cuda:{idx} is not the current CUDA device (cuda:{torch.cuda.current_device()}): call "
+                           "torch.cuda.set_device first — one process per GPU")
+    if _bound_device is None:
+        _bound_device = idx
+    elif _bound_device != idx:
+        raise RuntimeError(f"b200gym: this process already runs on cuda:{_bound_device}; one process per GPU (per-device kernel state is process-wide)")
 
 
 def require_cuda(t, name):

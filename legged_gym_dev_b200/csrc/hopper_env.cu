@@ -81,6 +81,68 @@ __global__ void __launch_bounds__(256) hopper_prologue_kernel(const __grid_const
     b.time_until_next_push[i] = t_out;
 }
 
+// HopperTrajectory._reset_dofs + _reset_root_states for env i (hopper_trajectory.py:298-358): dof / action / root redraw at the HOP_* Philox
+// sites, yaw randomisation through pytorch3d's euler -> matrix -> quaternion -> multiply chain; writes dof_state, actions, root_states and
+// leaves the new values in q / qd / act / R.  Shared by the in-step reset and the external reset_idx launch.
+__device__ __forceinline__ void hopper_reset_env(const B200HopperEnvParams& p, const B200HopperEnvBuffers& b, const philox::Stream& rng, size_t i,
+                                                 float (&q)[4], float (&qd)[4], float (&act)[4], float (&R)[13]) {
+    const uint4 wp = rng.words(philox::HOP_DOF_POS, 0), wv = rng.words(philox::HOP_DOF_VEL, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        q[k] = add_rn(p.default_dof_pos[k], affine_rn(p.dof_pos_noise_span[k], philox::u01(philox::word(wp, k)), p.dof_pos_noise_lo[k]));
+        qd[k] = affine_rn(p.dof_vel_noise_span[k], philox::u01(philox::word(wv, k)), p.dof_vel_noise_lo[k]);
+        act[k] = p.zero_action[k];                                                      // :314
+    }
+    *reinterpret_cast<float4*>(b.dof_state + i * 8) = make_float4(q[0], qd[0], q[1], qd[1]);
+    *reinterpret_cast<float4*>(b.dof_state + i * 8 + 4) = make_float4(q[2], qd[2], q[3], qd[3]);
+    *reinterpret_cast<float4*>(b.actions + i * 4) = make_float4(act[0], act[1], act[2], act[3]);
+#pragma unroll
+    for (int k = 0; k < 13; ++k) R[k] = p.base_init_state[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) R[k] = add_rn(R[k], b.env_origins[i * 3 + k]);
+    const uint4 w0 = rng.words(philox::HOP_ROOT_POS, 0), w1 = rng.words(philox::HOP_ROOT_POS, 1);
+    const float ur[5] = {philox::u01(w0.x), philox::u01(w0.y), philox::u01(w0.z), philox::u01(w0.w), philox::u01(w1.x)};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) R[2 + k] = add_rn(R[2 + k], affine_rn(p.root_pos_noise_span[k], ur[k], p.root_pos_noise_lo[k]));   // :338-341
+    const float nq = sqrtf(add_rn(add_rn(add_rn(mul_rn(R[3], R[3]), mul_rn(R[4], R[4])), mul_rn(R[5], R[5])), mul_rn(R[6], R[6])));
+#pragma unroll
+    for (int k = 3; k < 7; ++k) R[k] = div_rn(R[k], nq);
+    if (p.randomize_yaw) {   // :343-348, pytorch3d: euler_angles_to_matrix([0, 0, yaw], "XYZ") = Rz(yaw) -> matrix_to_quaternion -> multiply
+        const float pi = 3.14159265358979323846f;
+        const float yaw = affine_rn(sub_rn(pi, -pi), philox::u01(rng.words(philox::HOP_YAW, 0).x), -pi);
+        const float c = cosf(yaw), s = sinf(yaw);
+        const float a0 = add_rn(add_rn(add_rn(1.0f, c), c), 1.0f), a3 = add_rn(sub_rn(sub_rn(1.0f, c), c), 1.0f);
+        const float a1 = sub_rn(sub_rn(add_rn(1.0f, c), c), 1.0f), a2 = sub_rn(add_rn(sub_rn(1.0f, c), c), 1.0f);
+        const float q0 = a0 > 0.f ? sqrtf(a0) : 0.f, q1 = a1 > 0.f ? sqrtf(a1) : 0.f, q2 = a2 > 0.f ? sqrtf(a2) : 0.f, q3 = a3 > 0.f ? sqrtf(a3) : 0.f;
+        const float two_s = sub_rn(s, -s);   // m10 - m01
+        float yw, yx = 0.0f, yy = 0.0f, yz;
+        int best = 0;
+        float bq = q0;
+        if (q1 > bq) best = 1, bq = q1;
+        if (q2 > bq) best = 2, bq = q2;
+        if (q3 > bq) best = 3, bq = q3;
+        const float den = mul_rn(2.0f, fmaxf(bq, 0.1f));
+        if (best == 0) yw = div_rn(mul_rn(q0, q0), den), yz = div_rn(two_s, den);
+        else if (best == 3) yw = div_rn(two_s, den), yz = div_rn(mul_rn(q3, q3), den);
+        else if (best == 1) yw = 0.0f, yx = div_rn(mul_rn(q1, q1), den), yy = div_rn(add_rn(s, -s), den), yz = 0.0f;
+        else yw = 0.0f, yx = div_rn(add_rn(s, -s), den), yy = div_rn(mul_rn(q2, q2), den), yz = 0.0f;
+        if (yw < 0.0f) yw = -yw, yx = -yx, yy = -yy, yz = -yz;      // standardize_quaternion
+        const float aw = R[6], ax = R[3], ay = R[4], az = R[5];      // wxyz_quat_inds
+        float ow = sub_rn(sub_rn(sub_rn(mul_rn(aw, yw), mul_rn(ax, yx)), mul_rn(ay, yy)), mul_rn(az, yz));
+        float ox = sub_rn(add_rn(add_rn(mul_rn(aw, yx), mul_rn(ax, yw)), mul_rn(ay, yz)), mul_rn(az, yy));
+        float oy = add_rn(add_rn(sub_rn(mul_rn(aw, yy), mul_rn(ax, yz)), mul_rn(ay, yw)), mul_rn(az, yx));
+        float oz = add_rn(sub_rn(add_rn(mul_rn(aw, yz), mul_rn(ax, yy)), mul_rn(ay, yx)), mul_rn(az, yw));
+        if (ow < 0.0f) ow = -ow, ox = -ox, oy = -oy, oz = -oz;
+        R[3] = ox, R[4] = oy, R[5] = oz, R[6] = ow;
+    }
+    const uint4 v0 = rng.words(philox::HOP_ROOT_VEL, 0), v1 = rng.words(philox::HOP_ROOT_VEL, 1);
+    const float uv[6] = {philox::u01(v0.x), philox::u01(v0.y), philox::u01(v0.z), philox::u01(v0.w), philox::u01(v1.x), philox::u01(v1.y)};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) R[7 + k] = affine_rn(p.root_vel_noise_span[k], uv[k], p.root_vel_noise_lo[k]);
+#pragma unroll
+    for (int k = 0; k < 13; ++k) b.root_states[i * 13 + k] = R[k];
+}
+
 // The row-strided tensors of a CTA's 128 envs (root [., 13], contacts [., B, 3], trajectory [., 20] in; observations [., 38] out) are contiguous
 // byte ranges: they move between HBM and shared memory with coalesced cooperative copies (odd row strides in shared memory: conflict-free
 // per-env access), the [., 4] tensors are read as one float4 per thread.  (First version: every thread walked its own rows in global memory —
@@ -270,61 +332,7 @@ __global__ void __launch_bounds__(HT_TILE, 4) hopper_post_physics_kernel(const _
 
         // in-place reset (legged_robot_trajectory.py:204-246 with HopperTrajectory._reset_dofs / _reset_root_states :298-358)
         if (reset) {
-            const uint4 wp = rng.words(philox::HOP_DOF_POS, 0), wv = rng.words(philox::HOP_DOF_VEL, 0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                q[k] = add_rn(p.default_dof_pos[k], affine_rn(p.dof_pos_noise_span[k], philox::u01(philox::word(wp, k)), p.dof_pos_noise_lo[k]));
-                qd[k] = affine_rn(p.dof_vel_noise_span[k], philox::u01(philox::word(wv, k)), p.dof_vel_noise_lo[k]);
-                act[k] = p.zero_action[k];                                                      // :314
-            }
-            *reinterpret_cast<float4*>(b.dof_state + i * 8) = make_float4(q[0], qd[0], q[1], qd[1]);
-            *reinterpret_cast<float4*>(b.dof_state + i * 8 + 4) = make_float4(q[2], qd[2], q[3], qd[3]);
-            *reinterpret_cast<float4*>(b.actions + i * 4) = make_float4(act[0], act[1], act[2], act[3]);
-#pragma unroll
-            for (int k = 0; k < 13; ++k) R[k] = p.base_init_state[k];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) R[k] = add_rn(R[k], b.env_origins[i * 3 + k]);
-            const uint4 w0 = rng.words(philox::HOP_ROOT_POS, 0), w1 = rng.words(philox::HOP_ROOT_POS, 1);
-            const float ur[5] = {philox::u01(w0.x), philox::u01(w0.y), philox::u01(w0.z), philox::u01(w0.w), philox::u01(w1.x)};
-#pragma unroll
-            for (int k = 0; k < 5; ++k) R[2 + k] = add_rn(R[2 + k], affine_rn(p.root_pos_noise_span[k], ur[k], p.root_pos_noise_lo[k]));   // :338-341
-            const float nq = sqrtf(add_rn(add_rn(add_rn(mul_rn(R[3], R[3]), mul_rn(R[4], R[4])), mul_rn(R[5], R[5])), mul_rn(R[6], R[6])));
-#pragma unroll
-            for (int k = 3; k < 7; ++k) R[k] = div_rn(R[k], nq);
-            if (p.randomize_yaw) {   // :343-348, pytorch3d: euler_angles_to_matrix([0, 0, yaw], "XYZ") = Rz(yaw) -> matrix_to_quaternion -> multiply
-                const float pi = 3.14159265358979323846f;
-                const float yaw = affine_rn(sub_rn(pi, -pi), philox::u01(rng.words(philox::HOP_YAW, 0).x), -pi);
-                const float c = cosf(yaw), s = sinf(yaw);
-                const float a0 = add_rn(add_rn(add_rn(1.0f, c), c), 1.0f), a3 = add_rn(sub_rn(sub_rn(1.0f, c), c), 1.0f);
-                const float a1 = sub_rn(sub_rn(add_rn(1.0f, c), c), 1.0f), a2 = sub_rn(add_rn(sub_rn(1.0f, c), c), 1.0f);
-                const float q0 = a0 > 0.f ? sqrtf(a0) : 0.f, q1 = a1 > 0.f ? sqrtf(a1) : 0.f, q2 = a2 > 0.f ? sqrtf(a2) : 0.f, q3 = a3 > 0.f ? sqrtf(a3) : 0.f;
-                const float two_s = sub_rn(s, -s);   // m10 - m01
-                float yw, yx = 0.0f, yy = 0.0f, yz;
-                int best = 0;
-                float bq = q0;
-                if (q1 > bq) best = 1, bq = q1;
-                if (q2 > bq) best = 2, bq = q2;
-                if (q3 > bq) best = 3, bq = q3;
-                const float den = mul_rn(2.0f, fmaxf(bq, 0.1f));
-                if (best == 0) yw = div_rn(mul_rn(q0, q0), den), yz = div_rn(two_s, den);
-                else if (best == 3) yw = div_rn(two_s, den), yz = div_rn(mul_rn(q3, q3), den);
-                else if (best == 1) yw = 0.0f, yx = div_rn(mul_rn(q1, q1), den), yy = div_rn(add_rn(s, -s), den), yz = 0.0f;
-                else yw = 0.0f, yx = div_rn(add_rn(s, -s), den), yy = div_rn(mul_rn(q2, q2), den), yz = 0.0f;
-                if (yw < 0.0f) yw = -yw, yx = -yx, yy = -yy, yz = -yz;      // standardize_quaternion
-                const float aw = R[6], ax = R[3], ay = R[4], az = R[5];      // wxyz_quat_inds
-                float ow = sub_rn(sub_rn(sub_rn(mul_rn(aw, yw), mul_rn(ax, yx)), mul_rn(ay, yy)), mul_rn(az, yz));
-                float ox = sub_rn(add_rn(add_rn(mul_rn(aw, yx), mul_rn(ax, yw)), mul_rn(ay, yz)), mul_rn(az, yy));
-                float oy = add_rn(add_rn(sub_rn(mul_rn(aw, yy), mul_rn(ax, yz)), mul_rn(ay, yw)), mul_rn(az, yx));
-                float oz = add_rn(sub_rn(add_rn(mul_rn(aw, yz), mul_rn(ax, yy)), mul_rn(ay, yx)), mul_rn(az, yw));
-                if (ow < 0.0f) ow = -ow, ox = -ox, oy = -oy, oz = -oz;
-                R[3] = ox, R[4] = oy, R[5] = oz, R[6] = ow;
-            }
-            const uint4 v0 = rng.words(philox::HOP_ROOT_VEL, 0), v1 = rng.words(philox::HOP_ROOT_VEL, 1);
-            const float uv[6] = {philox::u01(v0.x), philox::u01(v0.y), philox::u01(v0.z), philox::u01(v0.w), philox::u01(v1.x), philox::u01(v1.y)};
-#pragma unroll
-            for (int k = 0; k < 6; ++k) R[7 + k] = affine_rn(p.root_vel_noise_span[k], uv[k], p.root_vel_noise_lo[k]);
-#pragma unroll
-            for (int k = 0; k < 13; ++k) b.root_states[i * 13 + k] = R[k];
+            hopper_reset_env(p, b, rng, i, q, qd, act, R);
             fat = 0.0f;
             ep = 0;
             atomicAdd(&s_acc[K + 1], 1.0);
@@ -396,6 +404,41 @@ __global__ void __launch_bounds__(HT_TILE, 4) hopper_post_physics_kernel(const _
     if (t < K + 2 && s_acc[t] != 0.0) atomicAdd(&b.ws_sums[t], s_acc[t]);
 }
 
+
+// LeggedRobotTrajectory.reset_idx(env_ids) called from OUTSIDE step() for the Hopper (legged_robot_trajectory.py:204-246 with the Hopper's
+// _reset_dofs / _reset_root_states; HopperTrajectory.reset, hopper_trajectory.py:286-296): the same redraw as the in-step reset for the envs
+// flagged in `mask`, buffers cleared, reset_buf set, prev_error from the (stale) trajectory buffer and the new root (:233), episode_sums folded
+// into the extras statistics; time_out_buf, obs_buf, rew_buf untouched.  The caller then resets the generators (b200gym_rom_reset_from_root).
+__global__ void __launch_bounds__(128) hopper_reset_idx_kernel(const __grid_constant__ B200HopperEnvParams p, const __grid_constant__ B200HopperEnvBuffers b,
+                                                               const uint8_t* __restrict__ mask, unsigned long long event, long long env_off) {
+    const int N = p.num_envs, K = p.num_sum_rows;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_acc[B200GYM_HOPPER_NUM_TERMS + 2];
+    if (threadIdx.x < K + 2) s_acc[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (e < N && mask[e] != 0) {
+        const size_t i = static_cast<size_t>(e);
+        const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<unsigned long long>(env_off) + i, event);
+        float q[4], qd[4], act[4], R[13];
+        hopper_reset_env(p, b, rng, i, q, qd, act, R);
+        *reinterpret_cast<float4*>(b.last_actions + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(b.last_dof_vel + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        b.feet_air_time[i] = 0.0f;
+        reinterpret_cast<long long*>(b.episode_length_buf)[i] = 0;
+        b.reset_buf[i] = 1;
+        const float d0 = sub_rn(b.trajectory[i * B200GYM_TRAJ_WIDTH], R[0]), d1 = sub_rn(b.trajectory[i * B200GYM_TRAJ_WIDTH + 1], R[1]);
+        b.prev_error[i * 2] = mul_rn(d0, d0), b.prev_error[i * 2 + 1] = mul_rn(d1, d1);
+        for (int k = 0; k < K; ++k) {
+            float* sp = b.episode_sums + static_cast<size_t>(k) * N + i;
+            atomicAdd(&s_acc[k], static_cast<double>(*sp));
+            *sp = 0.0f;
+        }
+        atomicAdd(&s_acc[K + 1], 1.0);
+    }
+    __syncthreads();
+    if (threadIdx.x < K + 2 && s_acc[threadIdx.x] != 0.0) atomicAdd(&b.ws_sums[threadIdx.x], s_acc[threadIdx.x]);
+}
+
 __global__ void hopper_extras_finalize_kernel(const __grid_constant__ B200HopperEnvParams p, const __grid_constant__ B200HopperEnvBuffers b) {
     const int K = p.num_sum_rows, tid = threadIdx.x;
     const double cnt = b.ws_sums[K + 1];
@@ -441,5 +484,23 @@ extern "C" int b200gym_hopper_post_physics(const B200HopperEnvParams* p, const B
     B200_LAUNCH_CHECK("hopper_post_physics");
     hopper_extras_finalize_kernel<<<1, 32, 0, st>>>(*p, *b);
     B200_LAUNCH_CHECK("hopper_extras_finalize");
+    return B200GYM_OK;
+}
+
+extern "C" int b200gym_hopper_reset_idx(const B200HopperEnvParams* p, const B200HopperEnvBuffers* b, const uint8_t* reset_mask, uint64_t event,
+                                        int64_t env_id_offset, void* stream) {
+    B200_REQUIRE(p && b && reset_mask, B200GYM_EINVAL, "hopper_reset_idx: null argument");
+    B200_REQUIRE(p->num_envs > 0 && p->num_sum_rows >= 0 && p->num_sum_rows <= B200GYM_HOPPER_NUM_TERMS, B200GYM_EINVAL, "hopper_reset_idx: bad sizes");
+    const void* must[] = {b->root_states, b->dof_state, b->actions, b->last_actions, b->last_dof_vel, b->feet_air_time, b->episode_length_buf, b->reset_buf,
+                          b->trajectory, b->prev_error, b->env_origins, b->extras_out, b->ws_sums};
+    for (const void* q : must) B200_REQUIRE(q != nullptr, B200GYM_EINVAL, "hopper_reset_idx: null buffer");
+    B200_REQUIRE(p->num_sum_rows == 0 || b->episode_sums, B200GYM_EINVAL, "hopper_reset_idx: episode_sums missing");
+    const void* vec[] = {b->dof_state, b->actions, b->last_actions, b->last_dof_vel};
+    for (const void* q : vec) B200_REQUIRE(b200_aligned16(q), B200GYM_EALIGN, "hopper_reset_idx: [N, 4] tensors must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    hopper_reset_idx_kernel<<<(p->num_envs + 127) / 128, 128, 0, st>>>(*p, *b, reset_mask, event, env_id_offset);
+    B200_LAUNCH_CHECK("hopper_reset_idx");
+    hopper_extras_finalize_kernel<<<1, 32, 0, st>>>(*p, *b);
+    B200_LAUNCH_CHECK("hopper_reset_idx finalize");
     return B200GYM_OK;
 }

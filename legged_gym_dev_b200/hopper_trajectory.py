@@ -63,6 +63,7 @@ class HopperTrajectory:
         self.device = torch.device(sim_device)
         if self.device.type != "cuda":
             raise RuntimeError("the b200gym Hopper env runs on CUDA devices only (no CPU fallback)")
+        _lib.require_current_device(self.device)
         self.lib = _lib.lib()
         from .configs import HOPPER_ASSET, HOPPER_DOF_NAMES
         a = dict(HOPPER_ASSET)
@@ -338,11 +339,19 @@ class HopperTrajectory:
         return self.privileged_obs_buf
 
     def reset_idx(self, env_ids):
-        """External reset: rides on the next step's in-kernel reset (the reset sequence — root redraw, generator reset from the new root —
-        lives in the fused step), by saturating the episode counters."""
+        """LeggedRobotTrajectory.reset_idx called from outside step() (legged_robot_trajectory.py:204-246 with the Hopper's _reset_* methods):
+        ONE masked launch (dof / action / root redraw, buffers cleared, reset_buf set, prev_error, extras) + the generator reset from the new
+        roots; immediate, time_out_buf untouched.  Draws keyed by common_step_counter, as in the reference's own call sequence."""
         if len(env_ids) == 0:
             return
-        self.episode_length_buf[env_ids] = int(self.max_episode_length) + 1
+        mask = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        mask[env_ids] = 1
+        g, st = self.traj_gen, _lib.stream_ptr(self.device)
+        _lib.check(self.lib.b200gym_hopper_reset_idx(self._pod, self._buffers(), mask.data_ptr(), int(self.common_step_counter), self.env_id_offset, st),
+                   "hopper_reset_idx")
+        _lib.check(self.lib.b200gym_rom_reset_from_root(g._p, g._s, mask.data_ptr(), self.physics.root_states.data_ptr(), 13, None,
+                                                        self.env_id_offset, st), "rom_reset_from_root")
+        self.physics.commit_resets(mask.view(torch.bool))
 
     def reset_traj_all(self):
         """reset_traj (legged_robot_trajectory.py:248-253) of every env at the robots' current positions: a never-reset generator evaluates
@@ -354,7 +363,6 @@ class HopperTrajectory:
 
     def reset(self):                                                      # hopper_trajectory.py:286-296
         ids = torch.arange(self.num_envs, device=self.device)
-        self.reset_traj_all()
         self.reset_idx(ids)
         self.step(self.zero_action.clone())
         self.reset_idx(ids)

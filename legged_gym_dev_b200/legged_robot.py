@@ -66,6 +66,7 @@ class LeggedRobot:
         self.env_id_offset = int(env_id_offset)
         self.seed = int(seed)
         self._terrain_in = terrain
+        _lib.require_current_device(self.device)
         self._parse_cfg(cfg)
         self._init_buffers()
         self._prepare_reward_function()

@@ -35,6 +35,7 @@ class FusedMLP:
         self.in_dim, self.out_dim = self.linears[0].in_features, self.linears[-1].out_features
         self.dims = [_pad(self.in_dim, 16)] + [_pad(l.out_features, 16) for l in self.linears]
         dev = self.linears[0].weight.device
+        _lib.require_current_device(dev)
         wtot = sum(self.dims[i] * self.dims[i + 1] for i in range(len(self.linears)))
         smem = (128 * max(self.dims[:-1]) + wtot + sum(self.dims[1:])) * 4 + 64
         if max(self.dims[1:]) > 256 or smem > 227 * 1024:

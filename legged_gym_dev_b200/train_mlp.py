@@ -51,6 +51,7 @@ class TensorCoreTrainer:
     def __init__(self, ac):
         self.ac = ac
         self.dev = ac.flat_param.device
+        _lib.require_current_device(self.dev)
         self.lib = _lib.lib()
         by_id = {id(p): ac._slices[name] for name, p in ac.named_parameters()}
         self.actor, self.critic = _Net(ac.actor, by_id), _Net(ac.critic, by_id)

@@ -270,3 +270,30 @@ def test_hopper_env_replays_reference_golden(name):
         assert_close(env.prev_error.cpu(), g("prev_error"), 1.0, tag + "prev_error")
         assert_close(env.trajectory.cpu(), g("trajectory"), 1.0, tag + "trajectory")
         assert_close(env.time_until_next_push.cpu().reshape(-1), g("time_until_next_push"), 1.0, tag + "time_until_next_push")
+
+
+@pytest.mark.parametrize("name,N", [("yaml_table", 300), ("all_terms_spindown", 67)])
+def test_hopper_env_external_reset_matches_oracle(name, N):
+    """HopperTrajectory.reset() / reset_idx(env_ids) from outside step() (hopper_trajectory.py:286-296, legged_robot_trajectory.py:204-246)
+    against the port, whose reset() is pinned to the reference's (tests/test_hopper_cpu.py): masked reset launch + generator reset, immediate."""
+    hp, tape, env, port, phys = _hopper_env_pair(name, N)
+    port.reset(phys)
+    obs, _ = env.reset()
+    assert torch.isfinite(obs).all()
+    _compare_hopper_env(env, port, f"{name} reset(): ")
+    assert not bool(env.time_out_buf.any())
+    for s in range(3):
+        a = tape.actions[s % 8]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        _compare_hopper_env(env, port, f"{name} step {s} after reset(): ")
+    ids = torch.arange(1, N, 3)
+    port.reset_idx(ids)
+    env.reset_idx(ids.cuda())
+    _compare_hopper_env(env, port, f"{name} partial reset: ")
+    assert bool(env.reset_buf[ids.cuda()].all())
+    for s in range(3, 8):
+        a = tape.actions[s % 8]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        _compare_hopper_env(env, port, f"{name} step {s} after the partial reset: ")
