@@ -2,6 +2,8 @@
 seconds, so the checks are identities that must hold for any N: shard invariance (results keyed by global env id), flag
 identities recomputed with plain torch ops from the same inputs, clip bounds, determinism of the persistent ROM rollout, and
 the sliding-window kernel against a torch gather of the same definition."""
+import os
+import sys
 from types import SimpleNamespace
 
 import pytest
@@ -162,3 +164,22 @@ def test_trajectory_env_at_1m_envs_shard_invariance_and_identities():
         assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
         assert float(obs.abs().max()) <= full.cfg.normalization.clip_observations
     assert int(full.reset_buf.sum()) > 0
+
+
+def test_rough_lstm_step_at_cfg3_size_matches_oracle():
+    """BASELINE.json configs[2] at its stated size: anymal_c_rough with the actuator-net torques, the 187-point height scan (terrain windows
+    staged by TMA) and every reward term, 16 384 envs x 10 steps, every tensor against the oracle port (flags / height cells exact, 1e-5 else)."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import legged_case as LC
+    N = 16384
+    case = LC.build_case("rough_lstm_allterms", N)
+    port, phys = LC.make_port(case)
+    env = LC.make_fused(case)
+    resets = 0
+    for s in range(10):
+        a = case.tape.actions[s % case.tape.frames]
+        port.step(a.clone(), phys)
+        env.step(a.cuda())
+        resets += int(port.reset_buf.sum())
+        LC.compare_snapshots(LC.snapshot_fused(env), LC.snapshot_port(port), tag=f"cfg3 size step {s}: ")
+    assert resets > 0

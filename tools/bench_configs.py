@@ -57,8 +57,28 @@ def rough_lstm(num_envs=16384, steps=50, warmup=5, device="cuda", peak=6535.7):
     t_pp, t_tq = sum(pp) / len(pp), sum(tq) / len(tq)
     K = len(env.params.active_terms)
     pp_bytes = 986 + 8 * K + 748 + 748
+    graph_ms = None
+    try:   # the 6 launches of a step (4 x LSTM torques, post-physics, finaliser; PDL between them) replayed from ONE CUDA graph per tape cycle
+        from legged_gym_dev_b200.graphs import GraphedReplay
+        env._timing = None
+        g = GraphedReplay(env, acts)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        a.record()
+        reps = max(1, steps // F)
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        graph_ms = a.elapsed_time(b) / (reps * F)
+    except Exception as e:   # noqa: BLE001
+        graph_ms = f"{type(e).__name__}: {e}"
+    step_bytes = 4 * (3264 + 48) + pp_bytes
     return dict(config="anymal_c_rough: 4x LSTM actuator torques + post_physics with 187-pt height scan, 235 obs",
-                num_envs=num_envs, ms_per_step=ms, env_steps_per_s=num_envs / (ms * 1e-3),
+                num_envs=num_envs, ms_per_step=ms, env_steps_per_s=num_envs / (ms * 1e-3), graph_ms_per_step=graph_ms,
+                graph_env_steps_per_s=(num_envs / (graph_ms * 1e-3) if isinstance(graph_ms, float) else None),
+                graph_step_frac=(step_bytes * num_envs / (graph_ms * 1e-3) / 1e9 / peak if isinstance(graph_ms, float) else None),
                 lstm_torques=dict(avg_launch_ms=t_tq, algorithmic_bytes_per_env=3264 + 48,
                                   achieved_gbs=(3264 + 48) * num_envs / (t_tq * 1e-3) / 1e9,
                                   frac=(3264 + 48) * num_envs / (t_tq * 1e-3) / 1e9 / peak),
