@@ -288,7 +288,7 @@ def e2e_run(num_envs, frames, steps, warmup, device, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     h2d = num_envs * (4 * 96 + 52 + 204 + 48)
-    d2h = num_envs * (env.num_obs * 4 + 4 + 1)
+    d2h = num_envs * (env.num_obs * 4 + 4 + 1 + 4 * 48)     # obs, rew, reset + the torques of the 4 sub-steps (what a host-side physics needs back)
     return dt, h2d, d2h
 
 
@@ -401,7 +401,7 @@ def main():
         esteps = max(5, min(args.steps, 30 if N <= 262144 else 12))
         dt, h2d, d2h = e2e_run(N, 2 if N > 262144 else min(args.frames, 4), esteps, 3, device, rank, world)
         e2e = {"value": world * N * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": esteps, "note": "LeggedRobot.step through the C ABI with pinned-host physics frames + actions in, obs/rew/reset out"}
+               "steps": esteps, "note": "LeggedRobot.step through the C ABI with pinned-host physics frames + actions in; obs / rew / reset and the 4 sub-steps' torques out"}
 
     multi = None
     if not args.no_multi:   # every rank: the sharded configurations of BASELINE.json (strong scaling), N = 1 included

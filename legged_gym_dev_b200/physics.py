@@ -74,9 +74,10 @@ class HostReplayPhysics(ReplayPhysics):
     stream into a second set of device buffers while step s computes (double buffering, like any input pipeline);
     every byte still moves inside the timed region."""
 
-    def __init__(self, tape, device="cuda"):
+    def __init__(self, tape, device="cuda", return_torques=True):
         self.tape, self.copy = tape, True
         dev = self.device = torch.device(device)
+        self.return_torques = return_torques
         self.root_frames = tape.root.pin_memory()
         self.dof_frames = tape.dof.pin_memory()
         self.contact_frames = tape.contact.reshape(tape.frames, tape.num_envs * tape.contact.shape[2], 3).pin_memory()
@@ -92,6 +93,15 @@ class HostReplayPhysics(ReplayPhysics):
         self.root_states = self.root_frames[0].to(dev)
         self.dof_state = self.dof_frames[0, 0].to(dev)
         self.contact_forces = self.contact_frames[0].to(dev)
+        # a host-side physics needs every sub-step's torques back: staged on the device (double-buffered by frame parity), read back to
+        # pinned host memory on a side stream while the next step's inputs arrive (PCIe is full duplex)
+        if return_torques:
+            nd = self.dof_frames.shape[2] // self.num_envs
+            self._tq_stage = [[torch.empty(self.num_envs, nd, device=dev) for _ in range(self.decimation)] for _ in range(2)]
+            self.torques_host = [torch.empty(self.num_envs, nd).pin_memory() for _ in range(self.decimation)]
+            self._out_stream = torch.cuda.Stream(device=dev)
+            self._tq_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._tq_read = [torch.cuda.Event(), torch.cuda.Event()]
         self._prefetch(0)
 
     def _prefetch(self, frame):
@@ -111,10 +121,22 @@ class HostReplayPhysics(ReplayPhysics):
         if self.sub == 0:
             torch.cuda.current_stream(self.device).wait_event(self._ready[b])
         self.dof_state = self._dof_d[b][self.sub]
+        if self.return_torques:
+            cur = torch.cuda.current_stream(self.device)
+            if self.sub == 0 and self.frame >= 2:
+                cur.wait_event(self._tq_read[b])          # the read-back of two steps ago has left this staging set
+            self._tq_stage[b][self.sub].copy_(torques, non_blocking=True)
         self.sub += 1
 
     def refresh(self):
         b = self.frame % 2
+        if self.return_torques:
+            self._tq_done[b].record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._out_stream):
+                self._out_stream.wait_event(self._tq_done[b])
+                for j in range(self.decimation):
+                    self.torques_host[j].copy_(self._tq_stage[b][j], non_blocking=True)
+                self._tq_read[b].record(self._out_stream)
         self.root_states, self.contact_forces = self._root_d[b], self._contact_d[b]
         self.frame += 1
         self.sub = 0

@@ -153,6 +153,8 @@ def test_host_replay_physics_matches_device_replay():
             continue   # torque evaluation 0 of the very first step sees the initial (unspecified) dof_state of each backend
         for k in ("obs_buf", "rew_buf", "reset_buf", "commands", "torques"):
             assert torch.equal(getattr(a, k), getattr(b, k)), f"step {s}: {k}"
+        # the last sub-step's torques, read back to pinned host memory (what a host-side physics consumes)
+        assert torch.equal(b.physics.torques_host[3], b.torques.cpu()), f"step {s}: torques read back to the host"
 
 
 def test_height_cells_exact_at_scale():
