@@ -85,7 +85,7 @@ def step_total_1m(rank, world, device, total=1 << 20, steps=96, frames=4):
     return out
 
 
-def train_iteration(rank, world, device, total=4096, iters=5):
+def train_iteration(rank, world, device, total=4096, iters=10):
     from legged_gym_dev_b200 import synthetic as S
     from legged_gym_dev_b200.physics import ReplayPhysics
     from legged_gym_dev_b200.sharding import env_shard
@@ -126,9 +126,12 @@ def train_iteration(rank, world, device, total=4096, iters=5):
             same = False
     return dict(config="anymal_c_flat PPO training iteration: 24 env steps (act + env.step + storage) + GAE + update of 5 epochs x 4 "
                        "minibatches, nets 48-128-64-32; 4096 envs TOTAL sharded over the ranks",
-                total_envs=total, envs_per_gpu=n, ms_per_iteration=ms_iter, update_ms=ms_upd, rollout_ms=ms_iter - ms_upd,
-                ms_per_iteration_graphed_rollout=ms_iter_g, rollout_ms_graphed=ms_iter_g - ms_upd,
-                samples_per_s=total * T / (ms_iter * 1e-3), gradient_exchange=alg.exchange, params_bit_identical_across_ranks=same,
+                total_envs=total, envs_per_gpu=n,
+                # headline: rollout replayed from one CUDA graph (GPU-bound); the eager-rollout figure (~10 Python-issued launches per env
+                # step, max over ranks) is host-launch bound and jitters with the host
+                ms_per_iteration=ms_iter_g, update_ms=ms_upd, rollout_ms=ms_iter_g - ms_upd,
+                ms_per_iteration_eager_rollout=ms_iter, rollout_ms_eager=ms_iter - ms_upd,
+                samples_per_s=total * T / (ms_iter_g * 1e-3), gradient_exchange=alg.exchange, params_bit_identical_across_ranks=same,
                 launches_per_minibatch=4, scaling="strong")
 
 
