@@ -477,6 +477,12 @@ typedef struct B200MlpParams {
     int32_t dims[B200GYM_MLP_MAX_LAYERS + 1];
 } B200MlpParams;
 int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const float* wpacked, const float* bias, float* out, void* stream);
+/* Two nets in ONE launch — rsl_rl PPO.act's actor_critic.act(obs) + actor_critic.evaluate(critic_obs) (rsl_rl algorithms/ppo.py,
+ * called from legged_gym/utils/task_registry.py's runner; not vendored under the reference tree).  CTAs [0, split) of the grid run
+ * net a, the rest net b; results are those of two b200gym_mlp_forward calls.  Both nets must be ones the fp16 four-slot kernel takes
+ * (every N_l <= 128, K_l %% 16 == 0, in_dim %% 8 == 0); B200GYM_EINVAL otherwise. */
+int b200gym_mlp_forward_pair(const B200MlpParams* pa, const float* xa, const float* wa, const float* ba, float* outa,
+                             const B200MlpParams* pb, const float* xb, const float* wb, const float* bb, float* outb, void* stream);
 /* Debug aid (tools/trace_mlp.py): buf = device buffer of 5*4096*2 uint64 that CTA 0 of the pipelined forward kernel fills
  * with (event, clock64) pairs; NULL switches tracing off again (the default). */
 int b200gym_debug_mlp_trace(void* buf);

@@ -283,6 +283,8 @@ def lib():
     L.b200gym_sliding_window.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.b200gym_tube_error.restype = L.b200gym_sliding_window.restype = C.c_int
     L.b200gym_mlp_forward.restype = C.c_int
+    L.b200gym_mlp_forward_pair.argtypes = [C.POINTER(MlpParamsPOD), vp, vp, vp, vp, C.POINTER(MlpParamsPOD), vp, vp, vp, vp, vp]
+    L.b200gym_mlp_forward_pair.restype = C.c_int
     L.b200gym_gemm_f16.argtypes = [C.POINTER(GemmProblemPOD), C.c_int32, vp]
     L.b200gym_gemm_f16.restype = C.c_int
     L.b200gym_rows_to_f16.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, C.c_int32, C.c_int64, vp]

@@ -596,9 +596,11 @@ __device__ __forceinline__ void h4_epilogue_chunk(const uint32_t (&r)[16], const
     }
 }
 
-__global__ void __launch_bounds__(H4_THREADS, 1) mlp_forward_h4_kernel(const __grid_constant__ B200MlpParams p, const H4Plan plan,
-                                                                        const float* __restrict__ x, const __half* __restrict__ wpacked16,
-                                                                        const float* __restrict__ bias, float* __restrict__ out) {
+// One CTA's share of one net's forward: CTA `cta` of the `G` CTAs assigned to this net (the pair kernel below gives each of
+// two nets its own contiguous range of the grid).
+__device__ __forceinline__ void mlp_forward_h4_body(const B200MlpParams& p, const H4Plan& plan, const float* __restrict__ x,
+                                                    const __half* __restrict__ wpacked16, const float* __restrict__ bias,
+                                                    float* __restrict__ out, const int cta, const int G) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int L = p.num_layers, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t buf_bytes = static_cast<size_t>(plan.buf_chunks) * CH16_BYTES;
@@ -647,7 +649,6 @@ __global__ void __launch_bounds__(H4_THREADS, 1) mlp_forward_h4_kernel(const __g
     const uint32_t tmem = *tmem_slot;
 
     const int ntiles = (p.batch + TM - 1) / TM;
-    const int G = gridDim.x;
     const int t = tid & (TM - 1);   // row within the tile (epilogue: TMEM lane = 32 * (warp % 4) + lane)
 
     if (warp == 24) {
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(H4_THREADS, 1) mlp_forward_h4_kernel(const __g
         int lay[NSLOT], tile_of[NSLOT];
         uint32_t nstep[NSLOT], nfull[NSLOT];
 #pragma unroll
-        for (int sl = 0; sl < NSLOT; ++sl) lay[sl] = 0, tile_of[sl] = static_cast<int>(blockIdx.x) + sl * G, nstep[sl] = 0, nfull[sl] = 0;
+        for (int sl = 0; sl < NSLOT; ++sl) lay[sl] = 0, tile_of[sl] = cta + sl * G, nstep[sl] = 0, nfull[sl] = 0;
         while (true) {
             bool any = false, progress = false;
 #pragma unroll
@@ -704,10 +705,10 @@ __global__ void __launch_bounds__(H4_THREADS, 1) mlp_forward_h4_kernel(const __g
         uint32_t ph[2] = {1, 1};   // the first wait on a fresh "empty" barrier falls through
         for (int it = 0;; ++it) {
             const int sl = g + 2 * (it & 1);
-            const int tile = static_cast<int>(blockIdx.x) + sl * G + (it >> 1) * NSLOT * G;
+            const int tile = cta + sl * G + (it >> 1) * NSLOT * G;
             // tiles of the two slots of this group interleave in increasing order; stop when both are exhausted
             if (tile >= ntiles) {
-                const int other = static_cast<int>(blockIdx.x) + (g + 2 * ((it + 1) & 1)) * G + ((it + 1) >> 1) * NSLOT * G;
+                const int other = cta + (g + 2 * ((it + 1) & 1)) * G + ((it + 1) >> 1) * NSLOT * G;
                 if (other >= ntiles) break;
                 continue;
             }
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(H4_THREADS, 1) mlp_forward_h4_kernel(const __g
         unsigned char* hrow = sH0 + slot * buf_bytes + t * 16;
         uint64_t *mma_done = bars + 2 * NSLOT + slot, *ready = bars + 3 * NSLOT + slot;
         uint32_t ph_mma = 0;
-        for (int tile = static_cast<int>(blockIdx.x) + slot * G; tile < ntiles; tile += NSLOT * G) {
+        for (int tile = cta + slot * G; tile < ntiles; tile += NSLOT * G) {
             const int row = tile * TM + t;
             const bool live = row < p.batch;
             float* orow = out + static_cast<size_t>(row) * p.out_dim;
@@ -804,6 +805,84 @@ __global__ void __launch_bounds__(H4_THREADS, 1) mlp_forward_h4_kernel(const __g
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+__global__ void __launch_bounds__(H4_THREADS, 1) mlp_forward_h4_kernel(const __grid_constant__ B200MlpParams p, const H4Plan plan,
+                                                                        const float* __restrict__ x, const __half* __restrict__ wpacked16,
+                                                                        const float* __restrict__ bias, float* __restrict__ out) {
+    mlp_forward_h4_body(p, plan, x, wpacked16, bias, out, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
+}
+
+// Two independent nets (PPO.act's actor and critic) in ONE launch: CTAs [0, split) run net 0, the rest net 1.  The choice is
+// CTA-uniform, so each CTA is exactly the single-net kernel on its own range of the grid.
+struct H4Net {
+    B200MlpParams p;
+    H4Plan plan;
+    const float* x;
+    const __half* w16;
+    const float* bias;
+    float* out;
+};
+struct H4Pair {
+    H4Net net[2];
+    int split;
+};
+
+__global__ void __launch_bounds__(H4_THREADS, 1) mlp_forward_h4_pair_kernel(const __grid_constant__ H4Pair pr) {
+    const int b = static_cast<int>(blockIdx.x);
+    const bool second = b >= pr.split;
+    const H4Net& n = pr.net[second ? 1 : 0];
+    mlp_forward_h4_body(n.p, n.plan, n.x, n.w16, n.bias, n.out, second ? b - pr.split : b,
+                        second ? static_cast<int>(gridDim.x) - pr.split : pr.split);
+}
+
+// Argument checks shared by the forward entries; fills the totals the plan needs.
+int mlp_check_params(const B200MlpParams* p, const char* who, size_t* wtot_out, size_t* btot_out) {
+    B200_REQUIRE(p->batch > 0 && p->num_layers >= 1 && p->num_layers <= B200GYM_MLP_MAX_LAYERS, B200GYM_EINVAL,
+                 "%s: batch > 0 and 1..%d layers", who, B200GYM_MLP_MAX_LAYERS);
+    size_t wtot = 0, btot = 0;
+    for (int l = 0; l < p->num_layers; ++l) {
+        const int K = p->dims[l], N = p->dims[l + 1];
+        B200_REQUIRE(K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && N <= 256, B200GYM_EINVAL,
+                     "%s: layer %d is %d -> %d; need K %% 8 == 0, N %% 16 == 0, N <= 256 (pad with zeros)", who, l, K, N);
+        wtot += static_cast<size_t>(K) * N;
+        btot += N;
+    }
+    B200_REQUIRE(p->in_dim > 0 && p->in_dim <= p->dims[0] && p->in_stride >= p->in_dim && p->out_dim > 0 &&
+                     p->out_dim <= p->dims[p->num_layers],
+                 B200GYM_EINVAL, "%s: inconsistent in_dim / out_dim", who);
+    *wtot_out = wtot, *btot_out = btot;
+    return B200GYM_OK;
+}
+
+// Shared-memory plan of the fp16 four-slot kernel; false when the net is outside what that kernel takes.
+bool h4_make_plan(const B200MlpParams* p, size_t wtot, size_t btot, H4Plan* plan, size_t* smem) {
+    const int L = p->num_layers;
+    int nmax = 0, hidden_late = 0, hidden_all = 0;
+    bool k16 = true;
+    for (int l = 0; l < L; ++l) {
+        nmax = p->dims[l + 1] > nmax ? p->dims[l + 1] : nmax;
+        k16 = k16 && (p->dims[l] % 16 == 0);
+    }
+    for (int j = 1; j <= L - 1; ++j) hidden_all = p->dims[j] > hidden_all ? p->dims[j] : hidden_all;
+    for (int j = 2; j <= L - 1; ++j) hidden_late = p->dims[j] > hidden_late ? p->dims[j] : hidden_late;
+    plan->x_off = hidden_late / 8;
+    plan->free_layer = L - 1 < 1 ? L - 1 : 1;
+    plan->buf_chunks = hidden_all / 8 > plan->x_off + p->dims[0] / 8 ? hidden_all / 8 : plan->x_off + p->dims[0] / 8;
+    plan->wtot = static_cast<int>(wtot), plan->btot = static_cast<int>(btot);
+    *smem = NSLOT * static_cast<size_t>(plan->buf_chunks) * CH16_BYTES + wtot * 2 + ((btot + 3) & ~size_t(3)) * 4 + 8 * 4 * NSLOT +
+            sizeof(LayerDesc) * B200GYM_MLP_MAX_LAYERS + 64;
+    return k16 && nmax <= 128 && (p->in_dim & 7) == 0 && (p->in_stride & 3) == 0 && (wtot & 7) == 0 && *smem <= 227 * 1024;
+}
+
+int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
 }  // namespace
 
 /* debug: registers (or clears, with NULL) a device buffer of 5 * 4096 * 2 uint64 that CTA 0 of the pipelined kernel fills
@@ -818,27 +897,11 @@ extern "C" int b200gym_debug_mlp_trace(void* buf) {
 extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const float* wpacked, const float* bias, float* out,
                                    void* stream) {
     B200_REQUIRE(p && x && wpacked && bias && out, B200GYM_EINVAL, "mlp_forward: null argument");
-    B200_REQUIRE(p->batch > 0 && p->num_layers >= 1 && p->num_layers <= B200GYM_MLP_MAX_LAYERS, B200GYM_EINVAL,
-                 "mlp_forward: batch > 0 and 1..%d layers", B200GYM_MLP_MAX_LAYERS);
     B200_REQUIRE(b200_aligned16(x) && b200_aligned16(wpacked), B200GYM_EALIGN, "mlp_forward: x / weights must be 16-byte aligned");
     size_t kmax = 0, wtot = 0, btot = 0;
-    for (int l = 0; l < p->num_layers; ++l) {
-        const int K = p->dims[l], N = p->dims[l + 1];
-        B200_REQUIRE(K >= 8 && K % 8 == 0 && N >= 16 && N % 16 == 0 && N <= 256, B200GYM_EINVAL,
-                     "mlp_forward: layer %d is %d -> %d; need K %% 8 == 0, N %% 16 == 0, N <= 256 (pad with zeros)", l, K, N);
-        kmax = K > (int)kmax ? K : kmax;
-        wtot += static_cast<size_t>(K) * N;
-        btot += N;
-    }
-    B200_REQUIRE(p->in_dim > 0 && p->in_dim <= p->dims[0] && p->in_stride >= p->in_dim && p->out_dim > 0 &&
-                     p->out_dim <= p->dims[p->num_layers],
-                 B200GYM_EINVAL, "mlp_forward: inconsistent in_dim / out_dim");
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    if (int rc = mlp_check_params(p, "mlp_forward", &wtot, &btot)) return rc;
+    for (int l = 0; l < p->num_layers; ++l) kmax = p->dims[l] > (int)kmax ? p->dims[l] : kmax;
+    const int sms = sm_count();
     const int ntiles = (p->batch + TM - 1) / TM;
     const int L = p->num_layers;
     static int variant = -1;   // 0: best available, 1: force the TF32 two-slot kernel, 2: force the serial kernel (A/B runs)
@@ -849,21 +912,8 @@ extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const
     // ---- fp16 four-slot kernel (weights: the fp16 section that follows the fp32 section of `wpacked`) --------------------
     {
         H4Plan plan;
-        int nmax = 0, hidden_late = 0, hidden_all = 0;
-        bool k16 = true;
-        for (int l = 0; l < L; ++l) {
-            nmax = p->dims[l + 1] > nmax ? p->dims[l + 1] : nmax;
-            k16 = k16 && (p->dims[l] % 16 == 0);
-        }
-        for (int j = 1; j <= L - 1; ++j) hidden_all = p->dims[j] > hidden_all ? p->dims[j] : hidden_all;
-        for (int j = 2; j <= L - 1; ++j) hidden_late = p->dims[j] > hidden_late ? p->dims[j] : hidden_late;
-        plan.x_off = hidden_late / 8;
-        plan.free_layer = L - 1 < 1 ? L - 1 : 1;
-        plan.buf_chunks = hidden_all / 8 > plan.x_off + p->dims[0] / 8 ? hidden_all / 8 : plan.x_off + p->dims[0] / 8;
-        plan.wtot = static_cast<int>(wtot), plan.btot = static_cast<int>(btot);
-        const size_t smem_h4 = NSLOT * static_cast<size_t>(plan.buf_chunks) * CH16_BYTES + wtot * 2 + ((btot + 3) & ~size_t(3)) * 4 +
-                               8 * 4 * NSLOT + sizeof(LayerDesc) * B200GYM_MLP_MAX_LAYERS + 64;
-        if (variant == 0 && k16 && nmax <= 128 && (p->in_dim & 7) == 0 && (p->in_stride & 3) == 0 && (wtot & 7) == 0 && smem_h4 <= 227 * 1024) {
+        size_t smem_h4 = 0;
+        if (h4_make_plan(p, wtot, btot, &plan, &smem_h4) && variant == 0) {
             static size_t configured_h4 = 0;
             if (smem_h4 > configured_h4) {
                 cudaError_t e = cudaFuncSetAttribute(mlp_forward_h4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_h4));
@@ -919,5 +969,52 @@ extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const
     }
     mlp_forward_serial_kernel<<<ntiles < sms ? ntiles : sms, TM, smem, static_cast<cudaStream_t>(stream)>>>(*p, x, wpacked, bias, out);
     B200_LAUNCH_CHECK("mlp_forward");
+    return B200GYM_OK;
+}
+
+/* Two nets in one launch (PPO.act: actor on obs, critic on critic obs).  Both must be nets the fp16 four-slot kernel takes
+ * (b200gym_mlp_forward's first variant); otherwise B200GYM_EINVAL and the caller issues two b200gym_mlp_forward calls. */
+extern "C" int b200gym_mlp_forward_pair(const B200MlpParams* pa, const float* xa, const float* wa, const float* ba, float* outa,
+                                        const B200MlpParams* pb, const float* xb, const float* wb, const float* bb, float* outb,
+                                        void* stream) {
+    B200_REQUIRE(pa && xa && wa && ba && outa && pb && xb && wb && bb && outb, B200GYM_EINVAL, "mlp_forward_pair: null argument");
+    B200_REQUIRE(b200_aligned16(xa) && b200_aligned16(wa) && b200_aligned16(xb) && b200_aligned16(wb), B200GYM_EALIGN,
+                 "mlp_forward_pair: x / weights must be 16-byte aligned");
+    H4Pair pr;
+    size_t smem = 0;
+    const B200MlpParams* ps[2] = {pa, pb};
+    const float* xs[2] = {xa, xb};
+    const float* ws[2] = {wa, wb};
+    const float* bs[2] = {ba, bb};
+    float* os[2] = {outa, outb};
+    int tiles[2];
+    for (int i = 0; i < 2; ++i) {
+        size_t wtot = 0, btot = 0, sm = 0;
+        if (int rc = mlp_check_params(ps[i], "mlp_forward_pair", &wtot, &btot)) return rc;
+        B200_REQUIRE(h4_make_plan(ps[i], wtot, btot, &pr.net[i].plan, &sm), B200GYM_EINVAL,
+                     "mlp_forward_pair: net %d is outside the fp16 four-slot kernel (K %% 16, N <= 128, in_dim %% 8, weights resident)", i);
+        pr.net[i].p = *ps[i];
+        pr.net[i].x = xs[i], pr.net[i].w16 = reinterpret_cast<const __half*>(ws[i] + wtot), pr.net[i].bias = bs[i], pr.net[i].out = os[i];
+        smem = sm > smem ? sm : smem;
+        tiles[i] = (ps[i]->batch + TM - 1) / TM;
+    }
+    // one CTA per tile while the grid fits one wave; beyond that the SMs are split in proportion to the tile counts
+    const int sms = sm_count();
+    int ga = tiles[0], gb = tiles[1];
+    if (ga + gb > sms) {
+        ga = static_cast<int>(static_cast<long long>(sms) * tiles[0] / (tiles[0] + tiles[1]));
+        ga = ga < 1 ? 1 : (ga > sms - 1 ? sms - 1 : ga);
+        gb = sms - ga;
+        ga = ga < tiles[0] ? ga : tiles[0], gb = gb < tiles[1] ? gb : tiles[1];
+    }
+    pr.split = ga;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_forward_h4_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "mlp_forward_pair: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+        configured = smem;
+    }
+    mlp_forward_h4_pair_kernel<<<ga + gb, H4_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(pr);
+    B200_LAUNCH_CHECK("mlp_forward_pair");
     return B200GYM_OK;
 }

@@ -62,15 +62,35 @@ class FusedMLP:
             woff += K * N
             boff += N
 
-    def __call__(self, x):
+    def _params(self, x):
         _lib.require_cuda(x, "x")
         if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.in_dim or x.stride(1) != 1:
             raise ValueError(f"expected a float32 [batch, {self.in_dim}] tensor with unit inner stride")
-        out = torch.empty(x.shape[0], self.out_dim, device=x.device)
         p = _lib.MlpParamsPOD()
         p.batch, p.num_layers, p.in_dim, p.in_stride, p.out_dim = x.shape[0], len(self.linears), self.in_dim, x.stride(0), self.out_dim
         for i, d in enumerate(self.dims):
             p.dims[i] = d
+        return p
+
+    def __call__(self, x):
+        p = self._params(x)
+        out = torch.empty(x.shape[0], self.out_dim, device=x.device)
         _lib.check(self.lib.b200gym_mlp_forward(p, x.data_ptr(), self.wpacked.data_ptr(), self.bias.data_ptr(), out.data_ptr(),
                                                 torch.cuda.current_stream(x.device).cuda_stream), "mlp_forward")
         return out
+
+    @property
+    def pairable(self) -> bool:
+        """True when this net runs on the fp16 four-slot kernel, the one b200gym_mlp_forward_pair launches for two nets at once."""
+        return (max(self.dims[1:]) <= 128 and all(d % 16 == 0 for d in self.dims[:-1]) and self.in_dim % 8 == 0 and self.wtot % 8 == 0)
+
+    @staticmethod
+    def forward_pair(a: "FusedMLP", xa, b: "FusedMLP", xb):
+        """a(xa), b(xb) in one launch (csrc/mlp.cu, mlp_forward_h4_pair_kernel)."""
+        pa, pb = a._params(xa), b._params(xb)
+        oa = torch.empty(xa.shape[0], a.out_dim, device=xa.device)
+        ob = torch.empty(xb.shape[0], b.out_dim, device=xb.device)
+        _lib.check(a.lib.b200gym_mlp_forward_pair(pa, xa.data_ptr(), a.wpacked.data_ptr(), a.bias.data_ptr(), oa.data_ptr(),
+                                                  pb, xb.data_ptr(), b.wpacked.data_ptr(), b.bias.data_ptr(), ob.data_ptr(),
+                                                  torch.cuda.current_stream(xa.device).cuda_stream), "mlp_forward_pair")
+        return oa, ob

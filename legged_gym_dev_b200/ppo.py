@@ -222,6 +222,16 @@ class ActorCritic(nn.Module):
             return fused(x)
         return self._trainer.forward_net(which, x)
 
+    def forward_both(self, obs, critic_obs):
+        """(actor(obs), critic(critic_obs)) — ONE launch when both nets run on the fp16 weights-resident kernel (flat nets), else
+        two launches of the same kernels."""
+        fa, fc = self._fused_actor, self._fused_critic
+        if (fa is not None and fc is not None and fa.pairable and fc.pairable and obs.stride(0) % 4 == 0 and critic_obs.stride(0) % 4 == 0
+                and os.environ.get("B200GYM_ACT_PAIR", "1") != "0"):
+            from .mlp import FusedMLP
+            return FusedMLP.forward_pair(fa, obs, fc, critic_obs)
+        return self._forward(0, obs), self._forward(1, critic_obs)
+
     def reset(self, dones=None):
         pass
 
@@ -309,7 +319,7 @@ class PPO:
         self.actor_critic.train()
 
     def act(self, obs, critic_obs):
-        """rsl_rl PPO.act: two MLP forwards (tcgen05) + ONE launch for Normal(mu, std).sample(), its log-prob and the transition
+        """rsl_rl PPO.act: the actor and critic forwards (tcgen05; one launch for flat nets) + ONE launch for Normal(mu, std).sample(), its log-prob and the transition
         written straight into row `storage.step` (csrc/ppo_rollout.cu).  rsl_rl keeps references to obs in the transition because
         its env returns a fresh tensor every step (legged_robot.py:211); the fused env rewrites ONE persistent obs_buf in place, so
         the observations are stored here, at act time.  The transition fields are views of the storage row."""
@@ -319,7 +329,7 @@ class PPO:
         if st.step >= st.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
         s, ptr = st.step, _lib.ptr
-        mu, val = ac._forward(0, obs), ac._forward(1, critic_obs)
+        mu, val = ac.forward_both(obs, critic_obs)
         self._act_event += 1
         priv = st.privileged_observations
         _lib.check(self.lib.b200gym_ppo_act_store(

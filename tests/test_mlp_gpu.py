@@ -40,6 +40,32 @@ def test_fused_mlp_matches_torch(num_obs, hidden, out, batch):
     assert (f(x) - want2).abs().max().item() < 5e-3
 
 
+@pytest.mark.parametrize("batch_a,batch_b", [(4096, 4096), (7, 1000), (24576, 4096), (131072, 131072)])
+def test_pair_launch_equals_two_single_launches(batch_a, batch_b):
+    """b200gym_mlp_forward_pair (actor + critic of PPO.act in one launch) is bit-identical to two b200gym_mlp_forward calls:
+    each CTA runs the single-net kernel body on its own range of the grid."""
+    from legged_gym_dev_b200.mlp import FusedMLP
+    torch.manual_seed(3)
+    actor, critic = FusedMLP(_net(48, (128, 64, 32), 12)), FusedMLP(_net(48, (128, 64, 32), 1))
+    assert actor.pairable and critic.pairable
+    xa, xb = torch.randn(batch_a, 48, device="cuda"), torch.randn(batch_b, 48, device="cuda")
+    oa, ob = FusedMLP.forward_pair(actor, xa, critic, xb)
+    torch.cuda.synchronize()
+    assert torch.equal(oa, actor(xa)) and torch.equal(ob, critic(xb))
+    # the same tensor as input of both nets (critic obs = obs on flat terrain)
+    oa2, ob2 = FusedMLP.forward_pair(actor, xa, critic, xa)
+    assert torch.equal(oa2, oa) and torch.equal(ob2, critic(xa))
+
+
+def test_pair_launch_rejects_nets_outside_the_fp16_kernel():
+    from legged_gym_dev_b200.mlp import FusedMLP
+    odd = FusedMLP(_net(30, (64, 48), 5))
+    ok = FusedMLP(_net(48, (128, 64, 32), 12))
+    assert not odd.pairable
+    with pytest.raises(RuntimeError):
+        FusedMLP.forward_pair(ok, torch.randn(64, 48, device="cuda"), odd, torch.randn(64, 30, device="cuda"))
+
+
 def test_fused_mlp_rejects_large_nets():
     from legged_gym_dev_b200.mlp import FusedMLP
     with pytest.raises(ValueError):
