@@ -526,7 +526,8 @@ int b200gym_gemm_f16(const B200GemmProblem* problems, int32_t n_problems, void* 
  * width, w_off[l] = offset (halves) of the row-major fp16 copy [np[l], kp[l]] in w16, b_off[l] = offset (floats) of the bias
  * in flat_param.  x: fp16 [batch, ldx] input rows (b200gym_rows_to_f16).  Written: h[l] fp16 [batch, np[l]] (l < last),
  * dz[l] fp16 [batch, np[l]] (all l; unscaled, as in b200gym_ppo_loss_gathered), out (optional fp32 [batch, 16]), d_std and
- * scalars as in b200gym_ppo_loss.  Follow with WGRAD problems of b200gym_gemm_f16 over (dz[l], h[l-1] | x). */
+ * scalars as in b200gym_ppo_loss.  Either follow with WGRAD problems of b200gym_gemm_f16 over (dz[l], h[l-1] | x), or pass
+ * flat_grad (below) and the whole of rsl_rl's loss.backward() for the minibatch is this launch. */
 #define B200GYM_CHAIN_MAX_LAYERS 6
 typedef struct B200ChainNet {
     const void* x;
@@ -538,11 +539,23 @@ typedef struct B200ChainNet {
     int64_t w_off[B200GYM_CHAIN_MAX_LAYERS], b_off[B200GYM_CHAIN_MAX_LAYERS];
     int32_t kp[B200GYM_CHAIN_MAX_LAYERS], np[B200GYM_CHAIN_MAX_LAYERS], n_real[B200GYM_CHAIN_MAX_LAYERS];
     int32_t num_layers, ldx;
+    /* optional: x32 != NULL gathers the input rows in the kernel — fp32 [*, ldx32] rows taken through idx, k_real[0] columns — instead
+     * of reading the fp16 copy x.  flat_grad != NULL also computes the weight and bias gradients in the kernel: per 128-row tile
+     * dW_l = dZ_l^T . H_{l-1} / batch is added (fp32 red) to flat_grad + w32_off[l] ([n_real[l], k_real[l]] row-major, k_real = real
+     * input width) and sum_rows dZ_l / batch to flat_grad + b_off[l]; h / dz may then be NULL (nothing but gradients leaves the SM). */
+    const float* x32;
+    float* flat_grad;
+    int64_t w32_off[B200GYM_CHAIN_MAX_LAYERS];
+    int32_t k_real[B200GYM_CHAIN_MAX_LAYERS];
+    int32_t ldx32, pad;
 } B200ChainNet;
 int b200gym_ppo_chain(const B200ChainNet* actor, const B200ChainNet* critic, const B200PpoLossParams* lp, const int64_t* idx,
                       const float* std, const float* actions, const float* old_log_prob, const float* advantages,
                       const float* returns, const float* old_values, const float* old_mu, const float* old_sigma, float* d_std,
                       double* scalars, void* stream);
+/* Debug aid (tools/trace_chain.py): buf = device buffer of 6*128*2 uint64 that the first and last CTA of the chain kernel fill with
+ * (event, clock64) pairs; NULL switches tracing off again (the default). */
+int b200gym_debug_chain_trace(void* buf);
 /* dst[i, 0:dst_ld] (fp16) = src[idx ? idx[i] : i, 0:cols] (fp32, row stride src_ld), zero padded to dst_ld (a multiple of 8):
  * the observation gather of RolloutStorage.mini_batch_generator fused with the operand conversion of the first layer. */
 int b200gym_rows_to_f16(const float* src, int64_t src_ld, int32_t cols, const int64_t* idx, void* dst, int32_t dst_ld, int64_t n_rows,

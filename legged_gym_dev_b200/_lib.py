@@ -172,7 +172,8 @@ class ChainNetPOD(C.Structure):
     _fields_ = [("x", vp), ("w16", vp), ("flat_param", vp), ("h", vp * CHAIN_MAX_LAYERS), ("dz", vp * CHAIN_MAX_LAYERS), ("out", vp),
                 ("w_off", C.c_int64 * CHAIN_MAX_LAYERS), ("b_off", C.c_int64 * CHAIN_MAX_LAYERS),
                 ("kp", i32 * CHAIN_MAX_LAYERS), ("np", i32 * CHAIN_MAX_LAYERS), ("n_real", i32 * CHAIN_MAX_LAYERS),
-                ("num_layers", i32), ("ldx", i32)]
+                ("num_layers", i32), ("ldx", i32), ("x32", vp), ("flat_grad", vp), ("w32_off", C.c_int64 * CHAIN_MAX_LAYERS),
+                ("k_real", i32 * CHAIN_MAX_LAYERS), ("ldx32", i32), ("pad", i32)]
 
 
 class OptParamsPOD(C.Structure):
@@ -276,7 +277,7 @@ def lib():
     L.b200gym_debug_set_lstm_variant.argtypes = [C.c_int]
     L.b200gym_debug_set_lstm_variant.restype = C.c_int
     for name in ("b200gym_gae_returns", "b200gym_adv_normalize", "b200gym_gather_rows", "b200gym_ppo_loss", "b200gym_grad_sumsq",
-                 "b200gym_clip_adam", "b200gym_adaptive_lr", "b200gym_adam_prepare", "b200gym_clip_adam_dev", "b200gym_debug_mlp_trace"):
+                 "b200gym_clip_adam", "b200gym_adaptive_lr", "b200gym_adam_prepare", "b200gym_clip_adam_dev", "b200gym_debug_mlp_trace", "b200gym_debug_chain_trace"):
         getattr(L, name).restype = C.c_int
     L.b200gym_mlp_forward.argtypes = [C.POINTER(MlpParamsPOD), vp, vp, vp, vp, vp]
     L.b200gym_tube_error.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp]

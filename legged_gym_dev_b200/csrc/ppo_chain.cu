@@ -6,9 +6,16 @@
 // epilogue's output, kept in shared memory in the chunk layout of tc.cuh; weights stream through a 2-stage cp.async ring and are
 // read K-major (forward) or MN-major (backward) from the same packed copy.  The loss separates per net — the actor CTA computes
 // the clipped surrogate / KL / entropy terms and d(loss)/d(mu), the critic CTA the clipped value loss and d(loss)/d(value) — so
-// no launch sits between forward and backward.  Activations H_l and gradients dZ_l also go to HBM (fp16): they are the operands
-// of the weight-gradient GEMM (gemm.cu, WGRAD), the only other contraction launch of the minibatch step.
-// Two CTAs per SM (108 KB of shared memory, 128 TMEM columns each): one CTA's epilogue overlaps the other's MMAs.
+// no launch sits between forward and backward.
+// Weight gradients (net.flat_grad != NULL): the operands of dW_l = dZ_l^T . H_{l-1} over the tile's 128 rows are the shared-memory
+// regions the chain already holds, read MN-major, so each backward step issues that MMA chain next to its input-gradient chain
+// (second accumulator, TMEM columns [128, 256)); the otherwise idle loader warps scale the tile's partial by 1/batch and add it to
+// the flat gradient buffer with red.global.add.v4.f32 while the next step runs.  One last step holds dW_0 = dZ_0^T . X and the bias
+// gradients of every layer (dZ_l^T against a constant [1,0,..] block).  The observation rows are gathered through the minibatch
+// index and converted to fp16 in the kernel (net.x32), so a minibatch's forward + backward is this ONE launch and nothing but the
+// gradient leaves the SM.  Without flat_grad the kernel is the round-2a form: H_l / dZ_l go to HBM (fp16) as the operands of the
+// weight-gradient GEMM (gemm.cu, WGRAD).
+// Two CTAs per SM (108 KB of shared memory, 256 TMEM columns each): one CTA's epilogue overlaps the other's MMAs.
 #include "tc.cuh"
 #include "../../include/b200gym.h"
 
@@ -21,7 +28,8 @@ constexpr int CH128 = TM * 16 + 16;             // chunk stride of 128-row tiles
 constexpr int CHKC = KC * 16 + 16;              // chunk stride of KC-row tiles (MN-major weight tiles)
 constexpr int W_STAGE = 16 * CHKC;              // 16640 >= 8 * CH128
 constexpr int CHAIN_THREADS = 288;
-constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t WG_COL = 128;              // first TMEM column of the weight-gradient accumulator
 constexpr int MAXA = 16;
 static_assert(8 * CH128 <= W_STAGE, "weight stage too small");
 
@@ -50,6 +58,26 @@ __device__ __forceinline__ void load_tile(unsigned char* dst, int chunk_stride, 
     }
 }
 
+// debug trace (tools/trace_chain.py): 6 regions of TRACE_EV (code, clock64) pairs — {epilogue thread 0, loader thread 128, MMA warp}
+// of CTA 0 and of the last CTA of the grid (one that starts when a first-round CTA has left)
+constexpr int TRACE_EV = 128;
+__device__ unsigned long long* g_chain_trace = nullptr;
+struct Trace {
+    unsigned long long* p = nullptr;
+    int n = 0;
+    __device__ __forceinline__ void operator()(int code) {
+        if (p != nullptr && n < TRACE_EV) {
+            p[2 * n] = static_cast<unsigned long long>(code);
+            p[2 * n + 1] = static_cast<unsigned long long>(clock64());
+            ++n;
+        }
+    }
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __grid_constant__ ChainArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -75,7 +103,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
     uint64_t* empty = full + WST;
     uint64_t* accum = empty + WST;
     uint64_t* aready = accum + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + 1);
+    uint64_t* wdone = aready + 1;    // tcgen05.commit after a weight-gradient MMA chain
+    uint64_t* wfree = wdone + 1;     // the loader warps have drained the weight-gradient accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfree + 1);
     float* s_red = reinterpret_cast<float*>(tmem_slot + 2);   // [16] d_std partials, then 4 doubles
     double* s_sc = reinterpret_cast<double*>(s_red + 16);
 
@@ -87,6 +117,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
         }
         mbar_init(accum, 1);
         mbar_init(aready, 128);
+        mbar_init(wdone, 1);
+        mbar_init(wfree, 128);
         fence_mbar_init();
     }
     if (tid < 16) s_red[tid] = 0.0f;
@@ -95,21 +127,29 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int nsteps = 2 * L - 1;   // L forward layers, then DGRAD of layers L-1 .. 1
+    const bool fuse = net.flat_grad != nullptr;
+    Trace tr;
+    if (g_chain_trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (tid == 0 || tid == 128 || tid == 256))
+        tr.p = g_chain_trace + static_cast<size_t>((blockIdx.x == 0 ? 0 : 3) + (tid >> 7)) * TRACE_EV * 2;
+    tr(0);
+    const int nsteps = 2 * L - 1 + (fuse ? 1 : 0);   // L forward layers, DGRAD of layers L-1 .. 1, then (fused) dW_0 + the bias gradients
 
     if (warp == 8) {
         // ------------------------------ MMA issue ------------------------------
         int it = 0;
         for (int step = 0; step < nsteps; ++step) {
-            const bool fwd = step < L;
+            const bool fwd = step < L, last = step == 2 * L - 1;
             const int l = fwd ? step : 2 * L - 1 - step;
             const int ktot = fwd ? net.kp[l] : net.np[l];
             const int n = fwd ? net.np[l] : net.kp[l];
-            const unsigned char* abase = smem + (fwd ? act_off[l] : (l == L - 1 ? act_off[B200GYM_CHAIN_MAX_LAYERS] : act_off[l + 1]));
+            const unsigned char* dzl = smem + (l == L - 1 ? act_off[B200GYM_CHAIN_MAX_LAYERS] : act_off[l + 1]);   // dZ_l once the backward pass is there
+            const unsigned char* abase = fwd ? smem + act_off[l] : dzl;
             const uint32_t idesc = tc::idesc_f16(n, false, !fwd);
+            const bool wg = fuse && !fwd;
             tc::mbar_wait_spin(aready, step & 1);
             tc::fence_after();
-            const int ns = (ktot + KC - 1) / KC;
+            tr(100 + step * 4);       // A operand ready
+            const int ns = last ? 0 : (ktot + KC - 1) / KC;
             for (int j = 0; j < ns; ++j, ++it) {
                 const int s = it % WST;
                 tc::mbar_wait_spin(full + s, (it / WST) & 1);
@@ -126,24 +166,116 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                         db += b_step;
                     }
                     tc::commit(empty + s);
-                    if (j == ns - 1) tc::commit(accum);
+                    if (j == ns - 1 && !wg) tc::commit(accum);
                 }
                 __syncwarp();
             }
+            tr(101 + step * 4);       // forward / input-gradient MMAs issued
+            if (wg) {
+                // dW_l = dZ_l^T . H_{l-1}: both operands are [128 rows x width] chunk regions, contracted over the rows (MN-major).
+                // Accumulator = 128 TMEM columns: layer 0's input may be wider (kp[0] <= 256 + ...), so it goes in blocks of 128 columns.
+                const int nblk = (net.kp[l] + 127) >> 7;
+                int s = 0;
+                for (int blk = 0; blk < nblk; ++blk) {
+                    const int jw = step - L + blk;
+                    if (jw > 0) {
+                        tc::mbar_wait_spin(wfree, (jw - 1) & 1);
+                        tc::fence_after();
+                    }
+                    if (last && blk == 0) {
+                        s = it % WST;
+                        tc::mbar_wait_spin(full + s, (it / WST) & 1);   // the constant block of the bias-gradient MMAs
+                        tc::fence_after();
+                        ++it;
+                    }
+                    if (tc::elect_one()) {
+                        const int ncols = min(128, net.kp[l] - 128 * blk);
+                        const uint32_t idw = tc::idesc_f16(ncols, true, true);
+                        uint64_t da = tc::smem_desc(dzl, 128, CH128), db = tc::smem_desc(smem + act_off[l] + 16 * blk * CH128, 128, CH128);
+                        for (int q = 0; q < TM / 16; ++q) {
+                            tc::mma_f16(tmem + WG_COL, da, db, idw, q != 0 ? 1u : 0u);
+                            da += 256u >> 4;
+                            db += 256u >> 4;
+                        }
+                        if (last && blk == 0) {
+                            const uint32_t idb = tc::idesc_f16(16, true, true);
+                            for (int m = 0; m < L; ++m) {
+                                uint64_t dam = tc::smem_desc(smem + (m == L - 1 ? act_off[B200GYM_CHAIN_MAX_LAYERS] : act_off[m + 1]), 128, CH128);
+                                uint64_t dbm = tc::smem_desc(ring + s * W_STAGE, 128, CH128);
+                                for (int q = 0; q < TM / 16; ++q) {
+                                    tc::mma_f16(tmem + 16 * m, dam, dbm, idb, q != 0 ? 1u : 0u);
+                                    dam += 256u >> 4;
+                                    dbm += 256u >> 4;
+                                }
+                            }
+                        }
+                        tc::commit(wdone);
+                        // also orders the weight-gradient reads of H_{l-1} before the epilogue overwrites it with dZ_{l-1}
+                        if (blk == 0) tc::commit(accum);
+                    }
+                    __syncwarp();
+                }
+                tr(102 + step * 4);   // weight-gradient MMAs issued
+            }
         }
     } else if (warp >= 4) {
-        // ------------------------------ loaders: the input tile, then the weight tiles of every step ------------------------------
+        // ------------------------------ loaders: the input tile, the weight tiles of every step, the weight-gradient drain -------------
         const int t = tid - 128;
-        load_tile(smem + act_off[0], CH128, static_cast<const __half*>(net.x), net.ldx, tile * TM, 0, TM, net.kp[0] >> 3, batch, net.kp[0], t);
-        tc::cp_async_commit();
+        if (net.x32 == nullptr) {
+            load_tile(smem + act_off[0], CH128, static_cast<const __half*>(net.x), net.ldx, tile * TM, 0, TM, net.kp[0] >> 3, batch, net.kp[0], t);
+            tc::cp_async_commit();
+            tc::cp_async_wait<0>();
+            fence_proxy_async();
+            tc::mbar_arrive(aready);   // the input tile = step 0's A operand
+        }
         const __half* w16 = static_cast<const __half*>(net.w16);
-        int it = 0;
+        const uint32_t taddr_w = tmem + WG_COL + (static_cast<uint32_t>((warp - 4) * 32) << 16);
+        // drains the jw-th weight-gradient accumulator (layer L-1-jw): TMEM lane = row of W_l, scaled by 1/batch, added to the flat gradient
+        auto drain = [&](int jw) {
+            const int l = jw < L - 1 ? L - 1 - jw : 0;
+            const int col0 = jw < L - 1 ? 0 : 128 * (jw - (L - 1));   // layer 0 goes in blocks of 128 input columns
+            tr(300 + jw * 4);
+            tc::mbar_wait_sleep(wdone, jw & 1);
+            tc::fence_after();
+            tr(301 + jw * 4);
+            const int kr = net.k_real[l];
+            if ((warp - 4) * 32 < net.n_real[l]) {   // warp-uniform: this warp owns live rows of W_l
+                const bool rowlive = t < net.n_real[l];
+                float* g = net.flat_grad + net.w32_off[l] + static_cast<size_t>(t) * kr;
+                const bool vec = (kr & 3) == 0 && (net.w32_off[l] & 3) == 0;
+                const float sc = a.lp.inv_global_batch;
+                for (int n0 = 0; n0 < 128 && col0 + n0 < kr; n0 += 16) {
+                    uint32_t r[16];
+                    tc::ld16_issue(taddr_w + n0, r);
+                    tc::ld16_wait(r);
+                    if (rowlive) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int c = col0 + n0 + 4 * q;
+                            if (vec && c + 4 <= kr) {
+                                red_add_v4(g + c, __uint_as_float(r[4 * q]) * sc, __uint_as_float(r[4 * q + 1]) * sc, __uint_as_float(r[4 * q + 2]) * sc,
+                                           __uint_as_float(r[4 * q + 3]) * sc);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (c + e < kr) atomicAdd(g + c + e, __uint_as_float(r[4 * q + e]) * sc);
+                            }
+                        }
+                    }
+                    __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge before the next one
+                }
+            }
+            tc::fence_before();
+            tc::mbar_arrive(wfree);
+            tr(302 + jw * 4);
+        };
+        int it = 0, pending = -1;   // pending: ring stage whose copies are committed but not yet published to the MMA warp
         for (int step = 0; step < nsteps; ++step) {
-            const bool fwd = step < L;
+            const bool fwd = step < L, last = step == 2 * L - 1;
             const int l = fwd ? step : 2 * L - 1 - step;
             const int ktot = fwd ? net.kp[l] : net.np[l];
             const __half* W = w16 + net.w_off[l];   // row-major [np[l], kp[l]]
-            const int ns = (ktot + KC - 1) / KC;
+            const int ns = last ? 0 : (ktot + KC - 1) / KC;
             for (int j = 0; j < ns; ++j, ++it) {
                 const int s = it % WST;
                 tc::mbar_wait_sleep(empty + s, ((it / WST) & 1) ^ 1);
@@ -152,15 +284,42 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                 if (fwd) load_tile(bt, CH128, W, net.kp[l], 0, j * KC, net.np[l], kc_eff >> 3, net.np[l], net.kp[l], t);       // [n rows x k cols], K-major
                 else load_tile(bt, CHKC, W, net.kp[l], j * KC, 0, kc_eff, net.kp[l] >> 3, net.np[l], net.kp[l], t);            // [n rows = K x k cols = N], MN-major
                 tc::cp_async_commit();
-                tc::cp_async_wait<1>();   // everything before this stage has landed: publish it to the tensor-core proxy
-                fence_proxy_async();
-                if (it == 0) tc::mbar_arrive(aready);   // the input tile = step 0's A operand
-                else tc::mbar_arrive(full + (it - 1) % WST);
+                if (pending >= 0) {   // everything before this stage has landed: publish it to the tensor-core proxy
+                    tc::cp_async_wait<1>();
+                    fence_proxy_async();
+                    tc::mbar_arrive(full + pending);
+                }
+                pending = s;
+                tr(200 + it);         // stage `it` issued, stage `it - 1` published
+            }
+            if (fuse && !fwd) {
+                if (pending >= 0) {
+                    tc::cp_async_wait<0>();
+                    fence_proxy_async();
+                    tc::mbar_arrive(full + pending);
+                    pending = -1;
+                }
+                if (last) {
+                    // constant block of the bias-gradient MMAs: 16 columns x 128 rows, column 0 = 1 (fp16), the rest 0
+                    const int s = it % WST;
+                    tc::mbar_wait_sleep(empty + s, ((it / WST) & 1) ^ 1);
+                    unsigned char* bt = ring + s * W_STAGE;
+                    *reinterpret_cast<uint4*>(bt + t * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(bt + CH128 + t * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    fence_proxy_async();
+                    tc::mbar_arrive(full + s);
+                    ++it;
+                }
+                if (step > L) drain(step - L - 1);   // the previous step's weight gradient, while this step's MMAs and epilogue run
             }
         }
-        tc::cp_async_wait<0>();
-        fence_proxy_async();
-        tc::mbar_arrive(full + (it - 1) % WST);
+        if (pending >= 0) {
+            tc::cp_async_wait<0>();
+            fence_proxy_async();
+            tc::mbar_arrive(full + pending);
+        }
+        if (fuse)
+            for (int blk = 0; blk < (net.kp[0] + 127) >> 7; ++blk) drain(L - 1 + blk);
     } else {
         // ------------------------------ epilogue warps: TMEM lane = tile row ------------------------------
         const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
@@ -184,11 +343,45 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
         } else {
             s_ret = __ldg(a.ret + srow), s_oldv = __ldg(a.old_v + srow);
         }
+        if (net.x32 != nullptr) {
+            // this thread's observation row through the minibatch index, fp32 -> fp16, straight into the A operand of layer 0
+            // (the loader warps are fetching the first weight tiles meanwhile)
+            const int chunks0 = net.kp[0] >> 3, kr0 = net.k_real[0];
+            const float* src = net.x32 + static_cast<size_t>(srow) * net.ldx32;
+            unsigned char* dst = smem + act_off[0] + tid * 16;
+            if ((kr0 & 7) == 0 && (net.ldx32 & 3) == 0) {
+                for (int c0 = 0; c0 < chunks0; c0 += 6) {
+                    float4 v[12];
+#pragma unroll
+                    for (int u = 0; u < 12; ++u)
+                        v[u] = (live && 8 * c0 + 4 * u < kr0) ? __ldg(reinterpret_cast<const float4*>(src + 8 * c0) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 6; ++u)
+                        if (c0 + u < chunks0)
+                            *reinterpret_cast<uint4*>(dst + (c0 + u) * CH128) =
+                                make_uint4(tc::pack_h2(v[2 * u].x, v[2 * u].y), tc::pack_h2(v[2 * u].z, v[2 * u].w), tc::pack_h2(v[2 * u + 1].x, v[2 * u + 1].y),
+                                           tc::pack_h2(v[2 * u + 1].z, v[2 * u + 1].w));
+                }
+            } else {
+                for (int c = 0; c < chunks0; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = (live && 8 * c + e < kr0) ? __ldg(src + 8 * c + e) : 0.0f;
+                    *reinterpret_cast<uint4*>(dst + c * CH128) =
+                        make_uint4(tc::pack_h2(v[0], v[1]), tc::pack_h2(v[2], v[3]), tc::pack_h2(v[4], v[5]), tc::pack_h2(v[6], v[7]));
+                }
+            }
+            fence_proxy_async();
+            tc::mbar_arrive(aready);   // the input tile = step 0's A operand
+            tr(399);
+        }
         for (int step = 0; step < nsteps; ++step) {
             const bool fwd = step < L;
             const int l = fwd ? step : 2 * L - 1 - step;
+            tr(400 + step * 4);
             tc::mbar_wait_sleep(accum, step & 1);
             tc::fence_after();
+            tr(401 + step * 4);       // accumulator ready
             if (fwd && l < L - 1) {
                 // bias + ELU -> fp16: A operand of layer l+1 (shared memory) and H_l (HBM, operand of the weight-gradient GEMM)
                 const int n = net.np[l];
@@ -207,7 +400,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                     const uint4 p1 = make_uint4(tc::pack_h2(v[8], v[9]), tc::pack_h2(v[10], v[11]), tc::pack_h2(v[12], v[13]), tc::pack_h2(v[14], v[15]));
                     *reinterpret_cast<uint4*>(dst + (n0 >> 3) * CH128) = p0;
                     *reinterpret_cast<uint4*>(dst + ((n0 >> 3) + 1) * CH128) = p1;
-                    if (live) {
+                    if (live && net.h[l] != nullptr) {
                         reinterpret_cast<uint4*>(hg + n0)[0] = p0;
                         reinterpret_cast<uint4*>(hg + n0)[1] = p1;
                     }
@@ -292,7 +485,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                 const uint4 p1 = make_uint4(tc::pack_h2(dz[8], dz[9]), tc::pack_h2(dz[10], dz[11]), tc::pack_h2(dz[12], dz[13]), tc::pack_h2(dz[14], dz[15]));
                 *reinterpret_cast<uint4*>(dz_last + tid * 16) = p0;
                 *reinterpret_cast<uint4*>(dz_last + CH128 + tid * 16) = p1;
-                if (live) {
+                if (live && net.dz[l] != nullptr) {
                     uint4* zg = reinterpret_cast<uint4*>(static_cast<__half*>(net.dz[l]) + static_cast<size_t>(grow) * 16);
                     zg[0] = p0, zg[1] = p1;
                 }
@@ -319,6 +512,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                 bar_epilogue();
                 if (tid < 4 && s_sc[tid] != 0.0) atomicAdd(a.scalars + tid, s_sc[tid]);
                 if (which == 0 && tid >= 32 && tid < 32 + A) atomicAdd(a.d_std + tid - 32, s_red[tid - 32]);
+            } else if (step == 2 * L - 1) {
+                // bias gradients: column 16 m of the accumulator = sum over the tile's rows of dZ_m[:, lane]
+                for (int m = 0; m < L; ++m) {
+                    if (warp * 32 < net.n_real[m]) {   // warp-uniform
+                        uint32_t r[16];
+                        tc::ld16_issue(taddr + 16 * m, r);
+                        tc::ld16_wait(r);
+                        if (tid < net.n_real[m]) atomicAdd(net.flat_grad + net.b_off[m] + tid, __uint_as_float(r[0]) * a.lp.inv_global_batch);
+                        __syncwarp();
+                    }
+                }
             } else {
                 // DGRAD of layer l: dZ_{l-1} = (dZ_l . W_l) * ELU'(H_{l-1}); H_{l-1} sits in act[l] and is overwritten in place by dZ_{l-1}
                 const int n = net.kp[l];
@@ -340,7 +544,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                     const uint4 p0 = make_uint4(o[0], o[1], o[2], o[3]), p1 = make_uint4(o[4], o[5], o[6], o[7]);
                     *reinterpret_cast<uint4*>(hs + (n0 >> 3) * CH128) = p0;
                     *reinterpret_cast<uint4*>(hs + ((n0 >> 3) + 1) * CH128) = p1;
-                    if (live) {
+                    if (live && net.dz[l - 1] != nullptr) {
                         reinterpret_cast<uint4*>(zg + n0)[0] = p0;
                         reinterpret_cast<uint4*>(zg + n0)[1] = p1;
                     }
@@ -350,8 +554,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
             fence_proxy_async();
             tc::fence_before();
             if (step + 1 < nsteps) tc::mbar_arrive(aready);
+            tr(402 + step * 4);       // epilogue done
         }
     }
+    tr(999);
     tc::fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -382,15 +588,27 @@ extern "C" int b200gym_ppo_chain(const B200ChainNet* actor, const B200ChainNet* 
     for (int w = 0; w < 2; ++w) {
         const B200ChainNet& n = *nets[w];
         B200_REQUIRE(n.num_layers >= 2 && n.num_layers <= B200GYM_CHAIN_MAX_LAYERS, B200GYM_EINVAL, "ppo_chain: 2..%d layers", B200GYM_CHAIN_MAX_LAYERS);
-        B200_REQUIRE(n.x && n.w16 && n.flat_param && b200_aligned16(n.x) && b200_aligned16(n.w16) && n.ldx % 8 == 0 && n.ldx >= n.kp[0], B200GYM_EALIGN,
-                     "ppo_chain: x / w16 must be 16-byte aligned, ldx %% 8 == 0");
+        B200_REQUIRE(n.w16 && n.flat_param && b200_aligned16(n.w16), B200GYM_EALIGN, "ppo_chain: w16 must be 16-byte aligned");
+        if (n.x32 != nullptr)
+            B200_REQUIRE(b200_aligned16(n.x32) && n.ldx32 >= n.k_real[0] && n.k_real[0] > 0 && n.k_real[0] <= n.kp[0], B200GYM_EALIGN,
+                         "ppo_chain: x32 must be 16-byte aligned with 0 < k_real[0] <= ldx32, kp[0]");
+        else
+            B200_REQUIRE(n.x && b200_aligned16(n.x) && n.ldx % 8 == 0 && n.ldx >= n.kp[0], B200GYM_EALIGN,
+                         "ppo_chain: x must be 16-byte aligned, ldx %% 8 == 0");
+        B200_REQUIRE(n.flat_grad == nullptr || b200_aligned16(n.flat_grad), B200GYM_EALIGN, "ppo_chain: flat_grad must be 16-byte aligned");
         for (int l = 0; l < n.num_layers; ++l) {
             B200_REQUIRE(n.kp[l] % 16 == 0 && n.np[l] % 16 == 0 && n.np[l] >= 16 && n.np[l] <= 128 && n.kp[l] >= 16 && n.n_real[l] <= n.np[l],
                          B200GYM_EINVAL, "ppo_chain: layer %d is %d -> %d; widths must be multiples of 16, outputs <= 128", l, n.kp[l], n.np[l]);
             B200_REQUIRE(l == 0 || (n.kp[l] == n.np[l - 1] && n.kp[l] <= 128), B200GYM_EINVAL, "ppo_chain: layer %d input %d != previous output %d", l, n.kp[l],
                          n.np[l - 1]);
-            B200_REQUIRE(n.w_off[l] % 8 == 0 && n.dz[l] && b200_aligned16(n.dz[l]) && (l == n.num_layers - 1 || (n.h[l] && b200_aligned16(n.h[l]))),
-                         B200GYM_EALIGN, "ppo_chain: layer %d buffers missing or misaligned", l);
+            B200_REQUIRE(n.w_off[l] % 8 == 0 && b200_aligned16(n.dz[l]) && b200_aligned16(n.h[l]), B200GYM_EALIGN,
+                         "ppo_chain: layer %d buffers misaligned", l);
+            if (n.flat_grad == nullptr)
+                B200_REQUIRE(n.dz[l] && (l == n.num_layers - 1 || n.h[l]), B200GYM_EINVAL,
+                             "ppo_chain: layer %d: without flat_grad the h / dz operand buffers of the weight-gradient GEMM are required", l);
+            else
+                B200_REQUIRE(n.k_real[l] > 0 && n.k_real[l] <= n.kp[l] && n.w32_off[l] >= 0, B200GYM_EINVAL,
+                             "ppo_chain: layer %d: 0 < k_real <= kp and w32_off >= 0 are required with flat_grad", l);
         }
         B200_REQUIRE(n.np[n.num_layers - 1] == 16, B200GYM_EINVAL, "ppo_chain: the last layer must be padded to 16 outputs");
         a.net[w] = n;
@@ -411,5 +629,14 @@ extern "C" int b200gym_ppo_chain(const B200ChainNet* actor, const B200ChainNet* 
     }
     ppo_chain_kernel<<<2 * a.tiles, CHAIN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
     B200_LAUNCH_CHECK("ppo_chain");
+    return B200GYM_OK;
+}
+
+/* debug: registers (or clears, with NULL) a device buffer of 6 * 128 * 2 uint64 that the first and the last CTA of ppo_chain_kernel
+ * fill with (event code, clock64) pairs — tools/trace_chain.py prints the per-step budget. */
+extern "C" int b200gym_debug_chain_trace(void* buf) {
+    unsigned long long* p = static_cast<unsigned long long*>(buf);
+    cudaError_t e = cudaMemcpyToSymbol(g_chain_trace, &p, sizeof(p));
+    B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "debug_chain_trace: %s", cudaGetErrorString(e));
     return B200GYM_OK;
 }

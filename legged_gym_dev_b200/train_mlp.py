@@ -81,6 +81,9 @@ class TensorCoreTrainer:
             smem = (2 + sum(k // 8 for k in net.Kp)) * (128 * 16 + 16) + 2 * 16 * (64 * 16 + 16) + 256
             return 2 <= net.L <= _lib.CHAIN_MAX_LAYERS and max(net.Np) <= 128 and max(net.Kp[1:]) <= 128 and smem <= 227 * 1024
         self.use_chain = all(chain_fits(n) for n in self.nets) and os.environ.get("B200GYM_PPO_CHAIN", "1") != "0"
+        # ... and the weight / bias gradients and the observation gather in the same launch (B200GYM_CHAIN_WGRAD=0: A/B against the
+        # round-2a form, chain + row-gather launch + grouped weight-gradient GEMM)
+        self.fuse_wgrad = self.use_chain and os.environ.get("B200GYM_CHAIN_WGRAD", "1") != "0"
         self.pack()
 
     # ------------------------------------------------------------------------------------------------------------
@@ -150,6 +153,7 @@ class TensorCoreTrainer:
             c.dz[l] = b["dz"][i][l].data_ptr()
             if l < net.L - 1:
                 c.h[l] = b["h"][i][l].data_ptr()
+            c.k_real[l], c.w32_off[l] = net.K[l], net.w_off[l]
         return c
 
     def _dgrad_launches(self, b, B):
@@ -220,10 +224,17 @@ class TensorCoreTrainer:
         ptr, st = _lib.ptr, _lib.stream_ptr(self.dev)
         flat = lambda t: t.flatten(0, 1)
         obs = flat(storage.observations)
-        self._convert(obs, idx, b["x"][0], B)
-        if not shared_obs:
-            self._convert(flat(storage.privileged_observations), idx, b["x"][1], B)
+        fuse = self.use_chain and self.fuse_wgrad
+        if not fuse:
+            self._convert(obs, idx, b["x"][0], B)
+            if not shared_obs:
+                self._convert(flat(storage.privileged_observations), idx, b["x"][1], B)
         if self.use_chain:
+            srcs = (obs, obs if shared_obs else flat(storage.privileged_observations))
+            for c, src in zip(b["chain"], srcs):
+                # fused: rows gathered in the kernel from the fp32 storage, gradients added to the flat buffer, no operand copies in HBM
+                c.x32, c.ldx32 = (src.data_ptr(), src.stride(0)) if fuse else (None, 0)
+                c.flat_grad = self.ac.flat_grad.data_ptr() if fuse else None
             _lib.check(self.lib.b200gym_ppo_chain(
                 b["chain"][0], b["chain"][1], lp, ptr(idx), ptr(std), ptr(storage.actions), ptr(storage.actions_log_prob),
                 ptr(storage.advantages), ptr(storage.returns), ptr(storage.values), ptr(storage.mu), ptr(storage.sigma), d_std_ptr,
@@ -235,6 +246,8 @@ class TensorCoreTrainer:
                 ptr(storage.advantages), ptr(storage.returns), ptr(storage.values), ptr(storage.mu), ptr(storage.sigma),
                 ptr(b["dz"][0][-1]), ptr(b["dz"][1][-1]), d_std_ptr, ptr(scalars), st), "ppo_loss_gathered")
             self._run(b["dgrad"])
+        if fuse:
+            return
         key = ("wgrad", lp.inv_global_batch)
         if key not in b:
             b[key] = self._wgrad_launches(b, B, lp.inv_global_batch)

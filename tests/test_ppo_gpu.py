@@ -261,7 +261,12 @@ def test_update_launches_no_library_gemm():
     bad = [n for n in names if "gemm_f16_kernel" not in n and
            any(t in n.lower() for t in ("sgemm", "cutlass", "cublas", "gemv", "ampere", "sm90", "xmma", "nvjet"))]
     assert not bad, bad
-    assert any("gemm_f16_kernel" in n for n in names), names
+    # flat nets: forward + loss + backward (weight gradients included) is the chain kernel, then the optimiser kernel
+    assert any("ppo_chain_kernel" in n for n in names), names
+    ours = [n for n in names if "ppo_chain_kernel" in n or "ppo_optimizer_step" in n]
+    mb = [e for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA and e.key in ours]
+    assert sorted(e.count for e in mb) == [alg.num_learning_epochs * alg.num_mini_batches] * 2, [(e.key, e.count) for e in mb]
+    assert not any("gemm_f16_kernel" in n or "rows_to_f16" in n for n in names), names
 
 
 @pytest.mark.parametrize("world", [1, 2, 5, 8])
