@@ -553,7 +553,7 @@ int b200gym_ppo_chain(const B200ChainNet* actor, const B200ChainNet* critic, con
                       const float* std, const float* actions, const float* old_log_prob, const float* advantages,
                       const float* returns, const float* old_values, const float* old_mu, const float* old_sigma, float* d_std,
                       double* scalars, void* stream);
-/* Debug aid (tools/trace_chain.py): buf = device buffer of 6*128*2 uint64 that the first and last CTA of the chain kernel fill with
+/* Debug aid (tools/trace_chain.py): buf = device buffer of 6*256*2 uint64 that the first and last CTA of the chain kernel fill with
  * (event, clock64) pairs; NULL switches tracing off again (the default). */
 int b200gym_debug_chain_trace(void* buf);
 /* dst[i, 0:dst_ld] (fp16) = src[idx ? idx[i] : i, 0:cols] (fp32, row stride src_ld), zero padded to dst_ld (a multiple of 8):

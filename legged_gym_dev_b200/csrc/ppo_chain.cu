@@ -27,7 +27,8 @@ constexpr int WST = 2;                          // weight ring stages
 constexpr int CH128 = TM * 16 + 16;             // chunk stride of 128-row tiles (activations, K-major weight tiles)
 constexpr int CHKC = KC * 16 + 16;              // chunk stride of KC-row tiles (MN-major weight tiles)
 constexpr int W_STAGE = 16 * CHKC;              // 16640 >= 8 * CH128
-constexpr int CHAIN_THREADS = 288;
+// EH = epilogue warps per TMEM lane quadrant (1 or 2): warps [0, 4 EH) epilogue, the next four loaders / gradient drain, then the MMA warp
+__host__ __device__ constexpr int chain_threads(int eh) { return 128 * eh + 160; }
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t WG_COL = 128;              // first TMEM column of the weight-gradient accumulator
 constexpr int MAXA = 16;
@@ -44,8 +45,6 @@ struct ChainArgs {
     int act_bytes[2];
 };
 
-__device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
 __device__ __forceinline__ void load_tile(unsigned char* dst, int chunk_stride, const __half* base, long long ld, int row0, int col0, int nrows,
                                           int nchunks, int row_lim, int col_lim, int t) {
     const int pieces = nrows * nchunks;
@@ -58,9 +57,10 @@ __device__ __forceinline__ void load_tile(unsigned char* dst, int chunk_stride, 
     }
 }
 
-// debug trace (tools/trace_chain.py): 6 regions of TRACE_EV (code, clock64) pairs — {epilogue thread 0, loader thread 128, MMA warp}
+// debug trace (-DB200GYM_CHAIN_TRACE, tools/trace_chain.py): 6 regions of TRACE_EV (code, clock64) pairs — {epilogue thread 0, loader thread 128, MMA warp}
 // of CTA 0 and of the last CTA of the grid (one that starts when a first-round CTA has left)
-constexpr int TRACE_EV = 128;
+#ifdef B200GYM_CHAIN_TRACE
+constexpr int TRACE_EV = 256;
 __device__ unsigned long long* g_chain_trace = nullptr;
 struct Trace {
     unsigned long long* p = nullptr;
@@ -73,14 +73,25 @@ struct Trace {
         }
     }
 };
+#else
+struct Trace {   // the production build carries no trace code
+    __device__ __forceinline__ void operator()(int) const {}
+};
+#endif
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __grid_constant__ ChainArgs a) {
+template <int EH>
+__global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const __grid_constant__ ChainArgs a) {
+    constexpr int CHAIN_THREADS = chain_threads(EH), LOADER_WARP0 = 4 * EH, MMA_WARP = 4 * EH + 4, LOADER_TID0 = 128 * EH;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef B200GYM_CHAIN_TRACE
+    unsigned long long t_entry;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
+#endif
     const int which = static_cast<int>(blockIdx.x) / a.tiles, tile = static_cast<int>(blockIdx.x) - which * a.tiles;
     const B200ChainNet& net = a.net[which];
     const int L = net.num_layers;
@@ -88,7 +99,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
 
     // shared memory: activation regions act[0..L-1] (act[l] = A operand of layer l), dz_last (2 chunks), weight ring, barriers
     __shared__ int act_off[B200GYM_CHAIN_MAX_LAYERS + 1];   // act_off[MAX] = end of the regions = dz_last
-    if (tid == 0) {
+    int act_end = 0, nsum = 0;   // every thread sums the layer widths itself: one block-wide barrier in the whole set-up
+    for (int l = 0; l < L; ++l) act_end += (net.kp[l] >> 3) * CH128, nsum += net.np[l];
+    if (tid == 64) {
         int o = 0;
         for (int l = 0; l < B200GYM_CHAIN_MAX_LAYERS; ++l) {
             act_off[l] = o;
@@ -96,8 +109,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
         }
         act_off[B200GYM_CHAIN_MAX_LAYERS] = o;
     }
-    __syncthreads();
-    unsigned char* dz_last = smem + act_off[B200GYM_CHAIN_MAX_LAYERS];
+    unsigned char* dz_last = smem + act_end;
     unsigned char* ring = dz_last + 2 * CH128;
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + WST * W_STAGE);
     uint64_t* empty = full + WST;
@@ -106,8 +118,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
     uint64_t* wdone = aready + 1;    // tcgen05.commit after a weight-gradient MMA chain
     uint64_t* wfree = wdone + 1;     // the loader warps have drained the weight-gradient accumulator
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfree + 1);
-    float* s_red = reinterpret_cast<float*>(tmem_slot + 2);   // [16] d_std partials, then 4 doubles
-    double* s_sc = reinterpret_cast<double*>(s_red + 16);
+    float* s_red = reinterpret_cast<float*>(tmem_slot + 2);   // CTA sums: [0, 16) d_std partials, [16, 20) {kl, surrogate, value loss, entropy}
+    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_red + 20) + 15) & ~static_cast<uintptr_t>(15));   // the biases of every layer, each zero padded to np[l], back to back
+    float* s_std = s_bias + nsum;   // per-action constants of the Gaussian policy (np[l] are multiples of 16: the block stays 16-byte aligned)
 
     if (warp == 0) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
     if (tid == 32) {
@@ -116,25 +129,35 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
             mbar_init(empty + s, 1);
         }
         mbar_init(accum, 1);
-        mbar_init(aready, 128);
+        mbar_init(aready, 128 * EH);
         mbar_init(wdone, 1);
         mbar_init(wfree, 128);
         fence_mbar_init();
     }
-    if (tid < 16) s_red[tid] = 0.0f;
-    if (tid >= 16 && tid < 20) s_sc[tid - 16] = 0.0;
+    if (tid < 20) s_red[tid] = 0.0f;
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = *tmem_slot;
     const bool fuse = net.flat_grad != nullptr;
     Trace tr;
-    if (g_chain_trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (tid == 0 || tid == 128 || tid == 256))
-        tr.p = g_chain_trace + static_cast<size_t>((blockIdx.x == 0 ? 0 : 3) + (tid >> 7)) * TRACE_EV * 2;
+#ifdef B200GYM_CHAIN_TRACE
+    // CTA Gantt chart: (globaltimer at start, at end, SM id) of every CTA behind the six event regions
+    unsigned long long* gantt = g_chain_trace != nullptr ? g_chain_trace + 6 * TRACE_EV * 2 + 4 * static_cast<size_t>(blockIdx.x) : nullptr;
+    if (gantt != nullptr && tid == 0) {
+        unsigned long long t;
+        unsigned int smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        gantt[0] = t_entry, gantt[2] = smid, gantt[3] = t;
+    }
+    if (g_chain_trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (tid == 0 || tid == LOADER_TID0 || tid == 32 * MMA_WARP))
+        tr.p = g_chain_trace + static_cast<size_t>((blockIdx.x == 0 ? 0 : 3) + (tid == 0 ? 0 : tid == LOADER_TID0 ? 1 : 2)) * TRACE_EV * 2;
+#endif
     tr(0);
     const int nsteps = 2 * L - 1 + (fuse ? 1 : 0);   // L forward layers, DGRAD of layers L-1 .. 1, then (fused) dW_0 + the bias gradients
 
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         // ------------------------------ MMA issue ------------------------------
         int it = 0;
         for (int step = 0; step < nsteps; ++step) {
@@ -146,7 +169,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
             const unsigned char* abase = fwd ? smem + act_off[l] : dzl;
             const uint32_t idesc = tc::idesc_f16(n, false, !fwd);
             const bool wg = fuse && !fwd;
-            tc::mbar_wait_spin(aready, step & 1);
+            tc::mbar_wait_sleep(aready, step & 1);   // long wait: leave the issue slots to the epilogue warps of this SM sub-partition
             tc::fence_after();
             tr(100 + step * 4);       // A operand ready
             const int ns = last ? 0 : (ktot + KC - 1) / KC;
@@ -179,7 +202,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                 for (int blk = 0; blk < nblk; ++blk) {
                     const int jw = step - L + blk;
                     if (jw > 0) {
-                        tc::mbar_wait_spin(wfree, (jw - 1) & 1);
+                        tc::mbar_wait_sleep(wfree, (jw - 1) & 1);
                         tc::fence_after();
                     }
                     if (last && blk == 0) {
@@ -218,9 +241,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                 tr(102 + step * 4);   // weight-gradient MMAs issued
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= LOADER_WARP0) {
         // ------------------------------ loaders: the input tile, the weight tiles of every step, the weight-gradient drain -------------
-        const int t = tid - 128;
+        const int t = tid - LOADER_TID0;
         if (net.x32 == nullptr) {
             load_tile(smem + act_off[0], CH128, static_cast<const __half*>(net.x), net.ldx, tile * TM, 0, TM, net.kp[0] >> 3, batch, net.kp[0], t);
             tc::cp_async_commit();
@@ -229,7 +252,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
             tc::mbar_arrive(aready);   // the input tile = step 0's A operand
         }
         const __half* w16 = static_cast<const __half*>(net.w16);
-        const uint32_t taddr_w = tmem + WG_COL + (static_cast<uint32_t>((warp - 4) * 32) << 16);
+        const uint32_t taddr_w = tmem + WG_COL + (static_cast<uint32_t>((warp - LOADER_WARP0) * 32) << 16);
         // drains the jw-th weight-gradient accumulator (layer L-1-jw): TMEM lane = row of W_l, scaled by 1/batch, added to the flat gradient
         auto drain = [&](int jw) {
             const int l = jw < L - 1 ? L - 1 - jw : 0;
@@ -239,7 +262,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
             tc::fence_after();
             tr(301 + jw * 4);
             const int kr = net.k_real[l];
-            if ((warp - 4) * 32 < net.n_real[l]) {   // warp-uniform: this warp owns live rows of W_l
+            if ((warp - LOADER_WARP0) * 32 < net.n_real[l]) {   // warp-uniform: this warp owns live rows of W_l
                 const bool rowlive = t < net.n_real[l];
                 float* g = net.flat_grad + net.w32_off[l] + static_cast<size_t>(t) * kr;
                 const bool vec = (kr & 3) == 0 && (net.w32_off[l] & 3) == 0;
@@ -279,6 +302,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
             for (int j = 0; j < ns; ++j, ++it) {
                 const int s = it % WST;
                 tc::mbar_wait_sleep(empty + s, ((it / WST) & 1) ^ 1);
+                tr(250 + it);
                 unsigned char* bt = ring + s * W_STAGE;
                 const int kc_eff = min(KC, ktot - j * KC);
                 if (fwd) load_tile(bt, CH128, W, net.kp[l], 0, j * KC, net.np[l], kc_eff >> 3, net.np[l], net.kp[l], t);       // [n rows x k cols], K-major
@@ -321,49 +345,54 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
         if (fuse)
             for (int blk = 0; blk < (net.kp[0] + 127) >> 7; ++blk) drain(L - 1 + blk);
     } else {
-        // ------------------------------ epilogue warps: TMEM lane = tile row ------------------------------
-        const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-        const int grow = tile * TM + tid;
+        // ------------------------------ epilogue warps: TMEM lane = tile row; two warps per lane quadrant, each takes half of the
+        // accumulator's 16-column blocks (a lone warp per scheduler issues at ~0.25 IPC: the chain is bound by this role) --------------
+        const int row = tid & 127, half = EH == 2 ? tid >> 7 : 0;
+        const uint32_t taddr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const int grow = tile * TM + row;
         const bool live = grow < batch;
         const int A = a.lp.num_actions;
-        // per-sample storage columns of this row, fetched through the minibatch index while the first layers run
+        // per-sample storage columns of this row (half 0 computes the loss), fetched through the minibatch index while the first layers run
         const long long srow = live ? (a.idx ? a.idx[grow] : grow) : 0;
-        float4 act4[3], omu4[3], osg4[3];
+        // (no L1 to speak of next to 2 x 113 KB of shared memory: every global or local access is an L2 round trip, so the loss step
+        // takes its 38 per-row values in one batch of loads when it gets there, from lines prefetched into L2 here)
         float s_adv = 0.f, s_logp = 0.f, s_ret = 0.f, s_oldv = 0.f;
-        if (which == 0) {
-            if (A == 12) {
+        if (half == 0 && live) {
+            if (which == 0) {
+                const float* rows[3] = {a.actions + srow * A, a.old_mu + srow * A, a.old_sigma + srow * A};
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                    act4[q] = __ldg(reinterpret_cast<const float4*>(a.actions + srow * 12) + q);
-                    omu4[q] = __ldg(reinterpret_cast<const float4*>(a.old_mu + srow * 12) + q);
-                    osg4[q] = __ldg(reinterpret_cast<const float4*>(a.old_sigma + srow * 12) + q);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rows[q]));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rows[q] + A - 1));
                 }
+                s_adv = __ldg(a.adv + srow), s_logp = __ldg(a.old_logp + srow);
+            } else {
+                s_ret = __ldg(a.ret + srow), s_oldv = __ldg(a.old_v + srow);
             }
-            s_adv = __ldg(a.adv + srow), s_logp = __ldg(a.old_logp + srow);
-        } else {
-            s_ret = __ldg(a.ret + srow), s_oldv = __ldg(a.old_v + srow);
         }
         if (net.x32 != nullptr) {
-            // this thread's observation row through the minibatch index, fp32 -> fp16, straight into the A operand of layer 0
+            // this thread's half of its observation row through the minibatch index, fp32 -> fp16, straight into the A operand of layer 0
             // (the loader warps are fetching the first weight tiles meanwhile)
             const int chunks0 = net.kp[0] >> 3, kr0 = net.k_real[0];
+            const int c_lo = half ? (chunks0 + 1) >> 1 : 0, c_hi = (EH == 1 || half) ? chunks0 : (chunks0 + 1) >> 1;
             const float* src = net.x32 + static_cast<size_t>(srow) * net.ldx32;
-            unsigned char* dst = smem + act_off[0] + tid * 16;
+            unsigned char* dst = smem + act_off[0] + row * 16;
             if ((kr0 & 7) == 0 && (net.ldx32 & 3) == 0) {
-                for (int c0 = 0; c0 < chunks0; c0 += 6) {
-                    float4 v[12];
+                for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
+                    float4 v[8];
 #pragma unroll
-                    for (int u = 0; u < 12; ++u)
-                        v[u] = (live && 8 * c0 + 4 * u < kr0) ? __ldg(reinterpret_cast<const float4*>(src + 8 * c0) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int u = 0; u < 8; ++u)
+                        v[u] = (live && c0 + (u >> 1) < c_hi && 8 * c0 + 4 * u < kr0) ? __ldg(reinterpret_cast<const float4*>(src + 8 * c0) + u)
+                                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int u = 0; u < 6; ++u)
-                        if (c0 + u < chunks0)
+                    for (int u = 0; u < 4; ++u)
+                        if (c0 + u < c_hi)
                             *reinterpret_cast<uint4*>(dst + (c0 + u) * CH128) =
                                 make_uint4(tc::pack_h2(v[2 * u].x, v[2 * u].y), tc::pack_h2(v[2 * u].z, v[2 * u].w), tc::pack_h2(v[2 * u + 1].x, v[2 * u + 1].y),
                                            tc::pack_h2(v[2 * u + 1].z, v[2 * u + 1].w));
                 }
             } else {
-                for (int c = 0; c < chunks0; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float v[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) v[e] = (live && 8 * c + e < kr0) ? __ldg(src + 8 * c + e) : 0.0f;
@@ -374,7 +403,20 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
             fence_proxy_async();
             tc::mbar_arrive(aready);   // the input tile = step 0's A operand
             tr(399);
+        } else if (EH == 2 && half == 1) {
+            tc::mbar_arrive(aready);   // fp16 input copied by the 128 loader threads: make up the barrier's 256 arrivals
         }
+        // biases and policy constants into shared memory while step 0's MMAs run (only these warps read them): sigma, log sigma,
+        // 1/(2 sigma^2), 1/sigma^2, 1/sigma are computed once per CTA instead of once per row
+        for (int l = 0, o = 0; l < L; o += net.np[l], ++l)
+            for (int c = tid; c < net.np[l]; c += 128 * EH) s_bias[o + c] = c < net.n_real[l] ? __ldg(net.flat_param + net.b_off[l] + c) : 0.0f;
+        if (tid < MAXA) {
+            const float sg = tid < a.lp.num_actions ? __ldg(a.stdv + tid) : 1.0f;
+            s_std[tid] = sg, s_std[MAXA + tid] = logf(sg), s_std[2 * MAXA + tid] = 1.0f / (2.0f * sg * sg), s_std[3 * MAXA + tid] = 1.0f / (sg * sg);
+            s_std[4 * MAXA + tid] = 1.0f / sg;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EH) : "memory");
+        int sboff = 0;   // offset of layer l's bias in s_bias (forward steps visit the layers in order)
         for (int step = 0; step < nsteps; ++step) {
             const bool fwd = step < L;
             const int l = fwd ? step : 2 * L - 1 - step;
@@ -383,38 +425,49 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
             tc::fence_after();
             tr(401 + step * 4);       // accumulator ready
             if (fwd && l < L - 1) {
-                // bias + ELU -> fp16: A operand of layer l+1 (shared memory) and H_l (HBM, operand of the weight-gradient GEMM)
-                const int n = net.np[l];
-                const float* bias = net.flat_param + net.b_off[l];
-                unsigned char* dst = smem + act_off[l + 1] + tid * 16;
+                // bias + ELU -> fp16: A operand of layer l+1 (shared memory) and, in the unfused form, H_l (HBM, operand of the weight-gradient GEMM)
+                const int n = net.np[l], nb = n >> 4;
+                const int b_lo = half ? (nb + 1) >> 1 : 0, b_hi = (EH == 1 || half) ? nb : (nb + 1) >> 1;
+                const float* sb = s_bias + sboff;
+                unsigned char* dst = smem + act_off[l + 1] + row * 16;
                 __half* hg = static_cast<__half*>(net.h[l]) + static_cast<size_t>(grow) * n;
-                for (int n0 = 0; n0 < n; n0 += 16) {
+                for (int n0 = 16 * b_lo; n0 < 16 * b_hi; n0 += 16) {
                     uint32_t r[16];
+                    if (step == 0) tr(500 + n0);
                     tc::ld16_issue(taddr + n0, r);
+                    float bv[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(sb + n0 + 4 * q);
+                        bv[4 * q] = b4.x, bv[4 * q + 1] = b4.y, bv[4 * q + 2] = b4.z, bv[4 * q + 3] = b4.w;
+                    }
                     tc::ld16_wait(r);
+                    if (step == 0) tr(501 + n0);
                     float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        v[j] = tc::elu_fast(__uint_as_float(r[j]) + (n0 + j < net.n_real[l] ? __ldg(bias + n0 + j) : 0.0f));
+                    for (int j = 0; j < 16; ++j) v[j] = tc::elu_fast(__uint_as_float(r[j]) + bv[j]);
                     const uint4 p0 = make_uint4(tc::pack_h2(v[0], v[1]), tc::pack_h2(v[2], v[3]), tc::pack_h2(v[4], v[5]), tc::pack_h2(v[6], v[7]));
                     const uint4 p1 = make_uint4(tc::pack_h2(v[8], v[9]), tc::pack_h2(v[10], v[11]), tc::pack_h2(v[12], v[13]), tc::pack_h2(v[14], v[15]));
                     *reinterpret_cast<uint4*>(dst + (n0 >> 3) * CH128) = p0;
                     *reinterpret_cast<uint4*>(dst + ((n0 >> 3) + 1) * CH128) = p1;
+                    if (step == 0) tr(502 + n0);
                     if (live && net.h[l] != nullptr) {
                         reinterpret_cast<uint4*>(hg + n0)[0] = p0;
                         reinterpret_cast<uint4*>(hg + n0)[1] = p1;
                     }
                 }
-            } else if (fwd) {
-                // last layer: 16 output columns of this row -> loss terms and d(loss)/d(output), unscaled (1/batch lives in the WGRAD epilogue)
+                sboff += n;
+            } else if (fwd && half == 0) {
+                // last layer: 16 output columns of this row -> loss terms and d(loss)/d(output), unscaled (1/batch lives in the gradient drain)
                 uint32_t r[16];
                 tc::ld16_issue(taddr, r);
                 tc::ld16_wait(r);
-                const float* bias = net.flat_param + net.b_off[l];
+                tr(601);
+                const float* sb = s_bias + sboff;
                 float o[16], dz[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    o[j] = __uint_as_float(r[j]) + (j < net.n_real[l] ? __ldg(bias + j) : 0.0f);
+                    o[j] = __uint_as_float(r[j]) + sb[j];
                     dz[j] = 0.0f;
                 }
                 if (net.out != nullptr && live) {
@@ -422,31 +475,43 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
 #pragma unroll
                     for (int q = 0; q < 4; ++q) op[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
                 }
-                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                tr(602);
+                float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 float dstd[MAXA];
 #pragma unroll
                 for (int j = 0; j < MAXA; ++j) dstd[j] = 0.0f;
                 if (which == 0 && live) {
                     const float LOG_SQRT_2PI = 0.91893853320467274178f;
                     float logp = 0.0f, ent = 0.0f, kl = 0.0f, diff[MAXA];
-                    const float av[12] = {act4[0].x, act4[0].y, act4[0].z, act4[0].w, act4[1].x, act4[1].y, act4[1].z, act4[1].w, act4[2].x, act4[2].y, act4[2].z, act4[2].w};
-                    const float mv[12] = {omu4[0].x, omu4[0].y, omu4[0].z, omu4[0].w, omu4[1].x, omu4[1].y, omu4[1].z, omu4[1].w, omu4[2].x, omu4[2].y, omu4[2].z, omu4[2].w};
-                    const float gv[12] = {osg4[0].x, osg4[0].y, osg4[0].z, osg4[0].w, osg4[1].x, osg4[1].y, osg4[1].z, osg4[1].w, osg4[2].x, osg4[2].y, osg4[2].z, osg4[2].w};
 #pragma unroll
-                    for (int j = 0; j < MAXA; ++j) {
-                        diff[j] = 0.0f;
-                        if (j < A) {
-                            const float sg = __ldg(a.stdv + j), m = o[j];
-                            const float x = A == 12 ? av[j < 12 ? j : 0] : __ldg(a.actions + srow * A + j);
-                            const float om = A == 12 ? mv[j < 12 ? j : 0] : __ldg(a.old_mu + srow * A + j);
-                            const float os = A == 12 ? gv[j < 12 ? j : 0] : __ldg(a.old_sigma + srow * A + j);
-                            const float ls = logf(sg);
-                            diff[j] = x - m;
-                            logp += -(diff[j] * diff[j]) / (2.0f * sg * sg) - ls - LOG_SQRT_2PI;
-                            ent += 0.5f + LOG_SQRT_2PI + ls;
-                            const float dm = om - m;
-                            kl += logf(sg / os + 1.e-5f) + (os * os + dm * dm) / (2.0f * sg * sg) - 0.5f;
+                    for (int j = 0; j < MAXA; ++j) diff[j] = 0.0f;
+                    auto term = [&](int j, float x, float om, float os) {
+                        const float sg = s_std[j], ls = s_std[MAXA + j], iden = s_std[2 * MAXA + j], m = o[j];
+                        diff[j] = x - m;
+                        logp += -(diff[j] * diff[j]) * iden - ls - LOG_SQRT_2PI;
+                        ent += 0.5f + LOG_SQRT_2PI + ls;
+                        const float dm = om - m;
+                        kl += logf(__fdividef(sg, os) + 1.e-5f) + (os * os + dm * dm) * iden - 0.5f;
+                    };
+                    if (A == 12) {
+                        float4 x4[3], m4[3], g4[3];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            x4[q] = __ldg(reinterpret_cast<const float4*>(a.actions + srow * 12) + q);
+                            m4[q] = __ldg(reinterpret_cast<const float4*>(a.old_mu + srow * 12) + q);
+                            g4[q] = __ldg(reinterpret_cast<const float4*>(a.old_sigma + srow * 12) + q);
                         }
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            term(4 * q, x4[q].x, m4[q].x, g4[q].x);
+                            term(4 * q + 1, x4[q].y, m4[q].y, g4[q].y);
+                            term(4 * q + 2, x4[q].z, m4[q].z, g4[q].z);
+                            term(4 * q + 3, x4[q].w, m4[q].w, g4[q].w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < MAXA; ++j)
+                            if (j < A) term(j, __ldg(a.actions + srow * A + j), __ldg(a.old_mu + srow * A + j), __ldg(a.old_sigma + srow * A + j));
                     }
                     const float ratio = expf(logp - s_logp);
                     const float lo = 1.0f - a.lp.clip_param, hi = 1.0f + a.lp.clip_param;
@@ -457,9 +522,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
 #pragma unroll
                     for (int j = 0; j < MAXA; ++j) {
                         if (j < A) {
-                            const float sg = __ldg(a.stdv + j), inv2 = 1.0f / (sg * sg);
+                            const float inv2 = s_std[3 * MAXA + j], isg = s_std[4 * MAXA + j];
                             dz[j] = dlogp * diff[j] * inv2;
-                            dstd[j] = (dlogp * (diff[j] * diff[j] * inv2 / sg - 1.0f / sg) - a.lp.entropy_coef / sg) * a.lp.inv_global_batch;
+                            dstd[j] = (dlogp * (diff[j] * diff[j] * inv2 * isg - isg) - a.lp.entropy_coef * isg) * a.lp.inv_global_batch;
                         }
                     }
                     acc[0] = kl, acc[1] = fmaxf(s1, s2), acc[3] = ent;
@@ -481,54 +546,72 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                     dz[0] = a.lp.value_loss_coef * dv;
                     acc[2] = vloss;
                 }
+                tr(603 + (__float_as_uint(dz[0]) == 0x7fc12345u));
                 const uint4 p0 = make_uint4(tc::pack_h2(dz[0], dz[1]), tc::pack_h2(dz[2], dz[3]), tc::pack_h2(dz[4], dz[5]), tc::pack_h2(dz[6], dz[7]));
                 const uint4 p1 = make_uint4(tc::pack_h2(dz[8], dz[9]), tc::pack_h2(dz[10], dz[11]), tc::pack_h2(dz[12], dz[13]), tc::pack_h2(dz[14], dz[15]));
-                *reinterpret_cast<uint4*>(dz_last + tid * 16) = p0;
-                *reinterpret_cast<uint4*>(dz_last + CH128 + tid * 16) = p1;
+                *reinterpret_cast<uint4*>(dz_last + row * 16) = p0;
+                *reinterpret_cast<uint4*>(dz_last + CH128 + row * 16) = p1;
                 if (live && net.dz[l] != nullptr) {
                     uint4* zg = reinterpret_cast<uint4*>(static_cast<__half*>(net.dz[l]) + static_cast<size_t>(grow) * 16);
                     zg[0] = p0, zg[1] = p1;
                 }
-                // CTA-level sums: warp shuffles, shared-memory atomics, one global atomic per value per CTA
+                tr(605);
+                // CTA-level sums.  16 values per lane (d_std[0..12), the four loss sums) are reduced over the warp by exchanging half of the
+                // remaining values per step (8 + 4 + 2 + 1 + 1 shuffles instead of 16 x 5); lane 2 k ends up with the warp sum of value
+                // bitrev4(k), which it adds to the CTA's shared-memory sums.  More than 12 actions: a second pass for d_std[12..16).
                 const int lane = tid & 31;
-                if (which == 0) {
+                auto warp_sum16 = [&](float (&v)[16]) -> float {
 #pragma unroll
-                    for (int j = 0; j < MAXA; ++j) {
-                        if (j < A) {
-                            float x = dstd[j];
+                    for (int w = 8, d = 16; w >= 1; w >>= 1, d >>= 1) {
+                        const bool up = (lane & d) != 0;
 #pragma unroll
-                            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-                            if (lane == 0) atomicAdd(s_red + j, x);
+                        for (int i = 0; i < w; ++i) {
+                            const float send = up ? v[i] : v[i + w], keep = up ? v[i + w] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
                         }
                     }
-                }
+                    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+                };
+                const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);   // value index this lane ends up with
+                {
+                    float v[16];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    double x = acc[k];
+                    for (int j = 0; j < 12; ++j) v[j] = dstd[j];
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-                    if (lane == 0 && x != 0.0) atomicAdd(s_sc + k, x);
+                    for (int k = 0; k < 4; ++k) v[12 + k] = acc[k];
+                    const float sum = warp_sum16(v);
+                    if ((lane & 1) == 0 && sum != 0.0f) atomicAdd(s_red + (slot < 12 ? slot : slot + 4), sum);
                 }
-                bar_epilogue();
-                if (tid < 4 && s_sc[tid] != 0.0) atomicAdd(a.scalars + tid, s_sc[tid]);
-                if (which == 0 && tid >= 32 && tid < 32 + A) atomicAdd(a.d_std + tid - 32, s_red[tid - 32]);
+                if (A > 12) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = j < 4 ? dstd[12 + j] : 0.0f;
+                    const float sum = warp_sum16(v);
+                    if ((lane & 1) == 0 && slot < 4 && sum != 0.0f) atomicAdd(s_red + 12 + slot, sum);
+                }
+                tr(606);
+                // the CTA's sums go to global memory at the very end of the kernel: every CTA of a wave reaches this step at the same time,
+                // and the proxy fence below would wait for ~300 same-address atomics to be acknowledged (measured: 12 us of a 40 us CTA)
+            } else if (fwd) {
+                // half 1 has no part in the 16-column loss step
             } else if (step == 2 * L - 1) {
-                // bias gradients: column 16 m of the accumulator = sum over the tile's rows of dZ_m[:, lane]
-                for (int m = 0; m < L; ++m) {
-                    if (warp * 32 < net.n_real[m]) {   // warp-uniform
+                // bias gradients: column 16 m of the accumulator = sum over the tile's rows of dZ_m[:, lane]; layers alternate between the halves
+                for (int m = half; m < L; m += EH) {
+                    if ((warp & 3) * 32 < net.n_real[m]) {   // warp-uniform
                         uint32_t r[16];
                         tc::ld16_issue(taddr + 16 * m, r);
                         tc::ld16_wait(r);
-                        if (tid < net.n_real[m]) atomicAdd(net.flat_grad + net.b_off[m] + tid, __uint_as_float(r[0]) * a.lp.inv_global_batch);
+                        if (row < net.n_real[m]) atomicAdd(net.flat_grad + net.b_off[m] + row, __uint_as_float(r[0]) * a.lp.inv_global_batch);
                         __syncwarp();
                     }
                 }
             } else {
                 // DGRAD of layer l: dZ_{l-1} = (dZ_l . W_l) * ELU'(H_{l-1}); H_{l-1} sits in act[l] and is overwritten in place by dZ_{l-1}
-                const int n = net.kp[l];
-                unsigned char* hs = smem + act_off[l] + tid * 16;
+                const int n = net.kp[l], nb = n >> 4;
+                const int b_lo = half ? (nb + 1) >> 1 : 0, b_hi = (EH == 1 || half) ? nb : (nb + 1) >> 1;
+                unsigned char* hs = smem + act_off[l] + row * 16;
                 __half* zg = static_cast<__half*>(net.dz[l - 1]) + static_cast<size_t>(grow) * n;
-                for (int n0 = 0; n0 < n; n0 += 16) {
+                for (int n0 = 16 * b_lo; n0 < 16 * b_hi; n0 += 16) {
                     uint32_t r[16];
                     tc::ld16_issue(taddr + n0, r);
                     const uint4 h0 = *reinterpret_cast<const uint4*>(hs + (n0 >> 3) * CH128), h1 = *reinterpret_cast<const uint4*>(hs + ((n0 >> 3) + 1) * CH128);
@@ -551,7 +634,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
                 }
             }
             // this thread's part of the next A operand is written and its accumulator reads are done
+            if (step == 0 || step == L - 1) tr(598);
             fence_proxy_async();
+            if (step == L - 1) tr(599);
             tc::fence_before();
             if (step + 1 < nsteps) tc::mbar_arrive(aready);
             tr(402 + step * 4);       // epilogue done
@@ -560,6 +645,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
     tr(999);
     tc::fence_before();
     __syncthreads();
+    if (tid < 4 && s_red[16 + tid] != 0.0f) atomicAdd(a.scalars + tid, static_cast<double>(s_red[16 + tid]));
+    if (which == 0 && tid >= 32 && tid < 32 + a.lp.num_actions) atomicAdd(a.d_std + tid - 32, s_red[tid - 32]);
+#ifdef B200GYM_CHAIN_TRACE
+    if (gantt != nullptr && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        gantt[1] = t;
+    }
+#endif
     if (warp == 0) {
         tc::fence_after();
         tc::tmem_dealloc<TMEM_COLS>(tmem);
@@ -569,7 +663,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) ppo_chain_kernel(const __gri
 size_t chain_smem(const B200ChainNet& n) {
     size_t chunks = 2;
     for (int l = 0; l < n.num_layers; ++l) chunks += static_cast<size_t>(n.kp[l] >> 3);
-    return chunks * CH128 + static_cast<size_t>(WST) * W_STAGE + 256;
+    size_t nsum = 0;
+    for (int l = 0; l < n.num_layers; ++l) nsum += static_cast<size_t>(n.np[l]);
+    return chunks * CH128 + static_cast<size_t>(WST) * W_STAGE + 256 + nsum * 4 + 5 * MAXA * 4;
 }
 
 }  // namespace
@@ -621,22 +717,37 @@ extern "C" int b200gym_ppo_chain(const B200ChainNet* actor, const B200ChainNet* 
     a.stdv = std, a.actions = actions, a.old_logp = old_log_prob, a.adv = advantages, a.ret = returns, a.old_v = old_values;
     a.old_mu = old_mu, a.old_sigma = old_sigma, a.d_std = d_std, a.scalars = scalars;
     a.tiles = (lp->batch + TM - 1) / TM;
+    static int eh = 0;   // epilogue warps per lane quadrant: 2 by default, B200GYM_CHAIN_EPI=1 for the A/B
+    if (!eh) {
+        const char* e = getenv("B200GYM_CHAIN_EPI");
+        eh = (e && e[0] == '1') ? 1 : 2;
+    }
+    auto kern = eh == 1 ? ppo_chain_kernel<1> : ppo_chain_kernel<2>;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(ppo_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "ppo_chain: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+        // two CTAs per SM need the whole unified L1 / shared memory as shared memory: say so up front
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "ppo_chain: carve-out preference: %s", cudaGetErrorString(e));
         configured = smem;
     }
-    ppo_chain_kernel<<<2 * a.tiles, CHAIN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    kern<<<2 * a.tiles, chain_threads(eh), smem, static_cast<cudaStream_t>(stream)>>>(a);
     B200_LAUNCH_CHECK("ppo_chain");
     return B200GYM_OK;
 }
 
-/* debug: registers (or clears, with NULL) a device buffer of 6 * 128 * 2 uint64 that the first and the last CTA of ppo_chain_kernel
+/* debug: registers (or clears, with NULL) a device buffer of 6 * 256 * 2 uint64 that the first and the last CTA of ppo_chain_kernel
  * fill with (event code, clock64) pairs — tools/trace_chain.py prints the per-step budget. */
 extern "C" int b200gym_debug_chain_trace(void* buf) {
+#ifdef B200GYM_CHAIN_TRACE
     unsigned long long* p = static_cast<unsigned long long*>(buf);
     cudaError_t e = cudaMemcpyToSymbol(g_chain_trace, &p, sizeof(p));
     B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "debug_chain_trace: %s", cudaGetErrorString(e));
     return B200GYM_OK;
+#else
+    (void)buf;
+    B200_REQUIRE(false, B200GYM_EINVAL, "debug_chain_trace: this library was built without -DB200GYM_CHAIN_TRACE (tools/trace_chain.py builds its own)");
+    return B200GYM_EINVAL;
+#endif
 }

@@ -78,7 +78,7 @@ class TensorCoreTrainer:
         self._bufs = {}
         # nets whose 128-row activation tiles fit in shared memory run forward + loss + input gradients as ONE launch (csrc/ppo_chain.cu)
         def chain_fits(net):
-            smem = (2 + sum(k // 8 for k in net.Kp)) * (128 * 16 + 16) + 2 * 16 * (64 * 16 + 16) + 256
+            smem = (2 + sum(k // 8 for k in net.Kp)) * (128 * 16 + 16) + 2 * 16 * (64 * 16 + 16) + 256 + 4 * sum(net.Np) + 320
             return 2 <= net.L <= _lib.CHAIN_MAX_LAYERS and max(net.Np) <= 128 and max(net.Kp[1:]) <= 128 and smem <= 227 * 1024
         self.use_chain = all(chain_fits(n) for n in self.nets) and os.environ.get("B200GYM_PPO_CHAIN", "1") != "0"
         # ... and the weight / bias gradients and the observation gather in the same launch (B200GYM_CHAIN_WGRAD=0: A/B against the
@@ -235,6 +235,11 @@ class TensorCoreTrainer:
                 # fused: rows gathered in the kernel from the fp32 storage, gradients added to the flat buffer, no operand copies in HBM
                 c.x32, c.ldx32 = (src.data_ptr(), src.stride(0)) if fuse else (None, 0)
                 c.flat_grad = self.ac.flat_grad.data_ptr() if fuse else None
+            for i, (c, net) in enumerate(zip(b["chain"], self.nets)):
+                for l in range(net.L):      # the fp16 H_l / dZ_l copies in HBM are the operands of the separate weight-gradient GEMM only
+                    c.dz[l] = None if fuse else b["dz"][i][l].data_ptr()
+                    if l < net.L - 1:
+                        c.h[l] = None if fuse else b["h"][i][l].data_ptr()
             _lib.check(self.lib.b200gym_ppo_chain(
                 b["chain"][0], b["chain"][1], lp, ptr(idx), ptr(std), ptr(storage.actions), ptr(storage.actions_log_prob),
                 ptr(storage.advantages), ptr(storage.returns), ptr(storage.values), ptr(storage.mu), ptr(storage.sigma), d_std_ptr,
