@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
     uint64_t* wfree = wdone + 1;     // the loader warps have drained the weight-gradient accumulator
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfree + 1);
     float* s_red = reinterpret_cast<float*>(tmem_slot + 2);   // CTA sums: [0, 16) d_std partials, [16, 20) {kl, surrogate, value loss, entropy}
-    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_red + 20) + 15) & ~static_cast<uintptr_t>(15));   // the biases of every layer, each zero padded to np[l], back to back
+    // the biases of every layer, each zero padded to np[l], back to back; 192 bytes behind the (16-byte aligned) barrier block, by plain
+    // pointer arithmetic so that the compiler keeps the shared address space (an integer round trip turns the reads into generic LD)
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full) + 192);
     float* s_std = s_bias + nsum;   // per-action constants of the Gaussian policy (np[l] are multiples of 16: the block stays 16-byte aligned)
 
     if (warp == 0) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -139,6 +141,10 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = *tmem_slot;
+    // programmatic dependent launch: the set-up above ran while the optimiser kernel of the previous minibatch was draining; weights,
+    // biases and the cleared gradient buffer are its output, so every role waits here before touching global memory
+    pdl_launch_dependents();
+    pdl_wait();
     const bool fuse = net.flat_grad != nullptr;
     Trace tr;
 #ifdef B200GYM_CHAIN_TRACE
@@ -301,6 +307,13 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
             const int ns = last ? 0 : (ktot + KC - 1) / KC;
             for (int j = 0; j < ns; ++j, ++it) {
                 const int s = it % WST;
+                if (pending >= 0 && !tc::mbar_try(empty + s, ((it / WST) & 1) ^ 1)) {
+                    // about to block on the ring: hand the stage already in flight to the MMA warp first
+                    tc::cp_async_wait<0>();
+                    fence_proxy_async();
+                    tc::mbar_arrive(full + pending);
+                    pending = -1;
+                }
                 tc::mbar_wait_sleep(empty + s, ((it / WST) & 1) ^ 1);
                 tr(250 + it);
                 unsigned char* bt = ring + s * W_STAGE;
@@ -431,6 +444,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
                 const float* sb = s_bias + sboff;
                 unsigned char* dst = smem + act_off[l + 1] + row * 16;
                 __half* hg = static_cast<__half*>(net.h[l]) + static_cast<size_t>(grow) * n;
+                const bool keep_h = live && net.h[l] != nullptr;
                 for (int n0 = 16 * b_lo; n0 < 16 * b_hi; n0 += 16) {
                     uint32_t r[16];
                     if (step == 0) tr(500 + n0);
@@ -451,7 +465,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
                     *reinterpret_cast<uint4*>(dst + (n0 >> 3) * CH128) = p0;
                     *reinterpret_cast<uint4*>(dst + ((n0 >> 3) + 1) * CH128) = p1;
                     if (step == 0) tr(502 + n0);
-                    if (live && net.h[l] != nullptr) {
+                    if (keep_h) {
                         reinterpret_cast<uint4*>(hg + n0)[0] = p0;
                         reinterpret_cast<uint4*>(hg + n0)[1] = p1;
                     }
@@ -611,6 +625,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
                 const int b_lo = half ? (nb + 1) >> 1 : 0, b_hi = (EH == 1 || half) ? nb : (nb + 1) >> 1;
                 unsigned char* hs = smem + act_off[l] + row * 16;
                 __half* zg = static_cast<__half*>(net.dz[l - 1]) + static_cast<size_t>(grow) * n;
+                const bool keep_dz = live && net.dz[l - 1] != nullptr;
                 for (int n0 = 16 * b_lo; n0 < 16 * b_hi; n0 += 16) {
                     uint32_t r[16];
                     tc::ld16_issue(taddr + n0, r);
@@ -627,7 +642,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
                     const uint4 p0 = make_uint4(o[0], o[1], o[2], o[3]), p1 = make_uint4(o[4], o[5], o[6], o[7]);
                     *reinterpret_cast<uint4*>(hs + (n0 >> 3) * CH128) = p0;
                     *reinterpret_cast<uint4*>(hs + ((n0 >> 3) + 1) * CH128) = p1;
-                    if (live && net.dz[l - 1] != nullptr) {
+                    if (keep_dz) {
                         reinterpret_cast<uint4*>(zg + n0)[0] = p0;
                         reinterpret_cast<uint4*>(zg + n0)[1] = p1;
                     }
@@ -732,7 +747,7 @@ extern "C" int b200gym_ppo_chain(const B200ChainNet* actor, const B200ChainNet* 
         B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "ppo_chain: carve-out preference: %s", cudaGetErrorString(e));
         configured = smem;
     }
-    kern<<<2 * a.tiles, chain_threads(eh), smem, static_cast<cudaStream_t>(stream)>>>(a);
+    b200_launch_pdl(0, kern, dim3(2 * a.tiles), dim3(chain_threads(eh)), smem, static_cast<cudaStream_t>(stream), a);
     B200_LAUNCH_CHECK("ppo_chain");
     return B200GYM_OK;
 }

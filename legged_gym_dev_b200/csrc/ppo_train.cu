@@ -229,6 +229,10 @@ __global__ void __launch_bounds__(512) ppo_optimizer_step_kernel(const __grid_co
                                                                  double* __restrict__ totals, OptWs* __restrict__ ws,
                                                                  const __grid_constant__ B200PackTable tab, __half* __restrict__ w16) {
     __shared__ double sh[16];
+    // programmatic dependent launch: this grid is scheduled while the minibatch kernel drains and lets the next minibatch kernel be
+    // scheduled behind it; everything it reads was written by the launches before it, so wait first
+    pdl_launch_dependents();
+    pdl_wait();
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -325,6 +329,8 @@ __global__ void __launch_bounds__(512) ppo_optimizer_step_peers_kernel(const __g
                                                                        double* __restrict__ mb, double* __restrict__ totals, PeerWs* __restrict__ ws,
                                                                        const __grid_constant__ B200PackTable tab, __half* __restrict__ w16) {
     __shared__ double sh[17];
+    pdl_launch_dependents();   // as in ppo_optimizer_step_kernel
+    pdl_wait();
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -499,8 +505,8 @@ int b200gym_ppo_optimizer_step(const B200OptParams* p, float* param, float* grad
     static const int forced = getenv("B200GYM_OPT_CTAS") ? atoi(getenv("B200GYM_OPT_CTAS")) : 0;
     long long grid = forced > 0 ? forced : (p->n + 512 * 4 - 1) / (512 * 4);
     grid = grid < 1 ? 1 : (grid > sms ? sms : grid);     // never more CTAs than SMs: the device-wide barrier needs co-residency
-    ppo_optimizer_step_kernel<<<static_cast<unsigned>(grid), 512, 0, static_cast<cudaStream_t>(stream)>>>(
-        *p, param, grad, exp_avg, exp_avg_sq, lr, step_dev, mb_scalars, totals, static_cast<OptWs*>(workspace), *table, static_cast<__half*>(w16));
+    b200_launch_pdl(0, ppo_optimizer_step_kernel, dim3(static_cast<unsigned>(grid)), dim3(512), 0, static_cast<cudaStream_t>(stream), *p, param, grad,
+                    exp_avg, exp_avg_sq, lr, step_dev, mb_scalars, totals, static_cast<OptWs*>(workspace), *table, static_cast<__half*>(w16));
     B200_LAUNCH_CHECK("ppo_optimizer_step");
     return B200GYM_OK;
 }
@@ -525,9 +531,9 @@ int b200gym_ppo_optimizer_step_peers(const B200OptParams* p, const B200PeerBases
     long long grid = ctas > 0 ? ctas : (p->n + 512 * 4 - 1) / (512 * 4);
     const long long cap = sms < B200GYM_OPT_MAX_CTAS ? sms : B200GYM_OPT_MAX_CTAS;
     grid = grid < 1 ? 1 : (grid > cap ? cap : grid);   // co-residency of the device-wide barriers
-    ppo_optimizer_step_peers_kernel<<<static_cast<unsigned>(grid), 512, 0, static_cast<cudaStream_t>(stream)>>>(
-        *p, *peers, world, rank, n_pad, param, grad, grad_sum, exp_avg, exp_avg_sq, lr, step_dev, mb_scalars, totals,
-        static_cast<PeerWs*>(workspace), *table, static_cast<__half*>(w16));
+    b200_launch_pdl(0, ppo_optimizer_step_peers_kernel, dim3(static_cast<unsigned>(grid)), dim3(512), 0, static_cast<cudaStream_t>(stream), *p, *peers,
+                    world, rank, n_pad, param, grad, grad_sum, exp_avg, exp_avg_sq, lr, step_dev, mb_scalars, totals,
+                    static_cast<PeerWs*>(workspace), *table, static_cast<__half*>(w16));
     B200_LAUNCH_CHECK("ppo_optimizer_step_peers");
     return B200GYM_OK;
 }
