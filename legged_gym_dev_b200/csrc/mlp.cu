@@ -612,9 +612,6 @@ __device__ __forceinline__ void mlp_forward_h4_body(const B200MlpParams& p, cons
     LayerDesc* sL = reinterpret_cast<LayerDesc*>(bars + 4 * NSLOT);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sL + B200GYM_MLP_MAX_LAYERS);
 
-    for (int i = tid * 8; i < plan.wtot; i += H4_THREADS * 8)
-        *reinterpret_cast<uint4*>(sW + i) = *reinterpret_cast<const uint4*>(wpacked16 + i);
-    for (int i = tid; i < plan.btot; i += H4_THREADS) sB[i] = bias[i];
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -628,6 +625,13 @@ __device__ __forceinline__ void mlp_forward_h4_body(const B200MlpParams& p, cons
         }
         fence_mbar_init();
     }
+    // programmatic dependent launch: TMEM allocation and barrier set-up above overlap the previous kernel's tail; weights, biases
+    // and observations are other kernels' output, so nothing in global memory is touched before this point
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int i = tid * 8; i < plan.wtot; i += H4_THREADS * 8)
+        *reinterpret_cast<uint4*>(sW + i) = *reinterpret_cast<const uint4*>(wpacked16 + i);
+    for (int i = tid; i < plan.btot; i += H4_THREADS) sB[i] = bias[i];
     if (tid >= 64 && tid < 64 + L) {
         const int l = tid - 64;
         int woff = 0;
@@ -920,8 +924,8 @@ extern "C" int b200gym_mlp_forward(const B200MlpParams* p, const float* x, const
                 B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "mlp_forward: cannot reserve %zu B of shared memory: %s", smem_h4, cudaGetErrorString(e));
                 configured_h4 = smem_h4;
             }
-            mlp_forward_h4_kernel<<<ntiles < sms ? ntiles : sms, H4_THREADS, smem_h4, static_cast<cudaStream_t>(stream)>>>(
-                *p, plan, x, reinterpret_cast<const __half*>(wpacked + wtot), bias, out);
+            b200_launch_pdl(0, mlp_forward_h4_kernel, dim3(ntiles < sms ? ntiles : sms), dim3(H4_THREADS), smem_h4, static_cast<cudaStream_t>(stream),
+                            *p, plan, x, reinterpret_cast<const __half*>(wpacked + wtot), bias, out);
             B200_LAUNCH_CHECK("mlp_forward (fp16, 4 slots)");
             return B200GYM_OK;
         }
@@ -1014,7 +1018,7 @@ extern "C" int b200gym_mlp_forward_pair(const B200MlpParams* pa, const float* xa
         B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "mlp_forward_pair: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
         configured = smem;
     }
-    mlp_forward_h4_pair_kernel<<<ga + gb, H4_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(pr);
+    b200_launch_pdl(0, mlp_forward_h4_pair_kernel, dim3(ga + gb), dim3(H4_THREADS), smem, static_cast<cudaStream_t>(stream), pr);
     B200_LAUNCH_CHECK("mlp_forward_pair");
     return B200GYM_OK;
 }

@@ -29,43 +29,50 @@ __global__ void __launch_bounds__(256) ppo_act_store_kernel(int n_envs, int num_
                                                             float* __restrict__ st_values, float* __restrict__ st_logp, float* __restrict__ st_mu,
                                                             float* __restrict__ st_sigma) {
     const int A = num_actions;
+    pdl_launch_dependents();   // programmatic dependent launch (common.cuh): scheduled while the policy forward drains
+    pdl_wait();
     if (event_dev) event = *event_dev;   // graph-replayable mode: the act counter lives in device memory (advanced by ppo_store_step_kernel)
     const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-    if (tid < n_envs) {
-        const long long e = tid;
-        const philox::Stream rng(seed_lo, seed_hi, env_id_offset + static_cast<unsigned long long>(e), event);
-        const float LOG_SQRT_2PI = 0.91893853320467274178f, TWO_PI = 6.283185307179586f;
+    // four lanes per env: lane blk draws the Philox block of actions 4 blk .. 4 blk + 3 (one thread per env left 16 CTAs doing ~3000
+    // serial instructions each at 4096 envs); the log-probability is summed over the four lanes
+    {
+        const long long e = tid >> 2;
+        const int blk = static_cast<int>(tid & 3);
+        const bool on = e < n_envs;
         float logp = 0.0f;
+        if (on && blk * 4 < A) {
+            const philox::Stream rng(seed_lo, seed_hi, env_id_offset + static_cast<unsigned long long>(e), event);
+            const float LOG_SQRT_2PI = 0.91893853320467274178f, TWO_PI = 6.283185307179586f;
+            const uint4 w = rng.words(philox::POLICY_SAMPLE, blk);
+            // two Box-Muller pairs per block: (w.x, w.y) -> columns 4 blk + {0, 1}, (w.z, w.w) -> columns 4 blk + {2, 3}
+            const float u0 = (static_cast<float>(w.x >> 8) + 0.5f) * 5.9604644775390625e-08f, u1 = philox::u01(w.y);
+            const float u2 = (static_cast<float>(w.z >> 8) + 0.5f) * 5.9604644775390625e-08f, u3 = philox::u01(w.w);
+            const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+            float s0, c0, s1, c1;
+            sincosf(TWO_PI * u1, &s0, &c0);
+            sincosf(TWO_PI * u3, &s1, &c1);
+            const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
 #pragma unroll
-        for (int blk = 0; blk < MAXA / 4; ++blk) {
-            if (blk * 4 < A) {
-                const uint4 w = rng.words(philox::POLICY_SAMPLE, blk);
-                // two Box-Muller pairs per block: (w.x, w.y) -> columns 4 blk + {0, 1}, (w.z, w.w) -> columns 4 blk + {2, 3}
-                const float u0 = (static_cast<float>(w.x >> 8) + 0.5f) * 5.9604644775390625e-08f, u1 = philox::u01(w.y);
-                const float u2 = (static_cast<float>(w.z >> 8) + 0.5f) * 5.9604644775390625e-08f, u3 = philox::u01(w.w);
-                const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
-                float s0, c0, s1, c1;
-                sincosf(TWO_PI * u1, &s0, &c0);
-                sincosf(TWO_PI * u3, &s1, &c1);
-                const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int a = blk * 4 + j;
-                    if (a < A) {
-                        const float sg = stdv[a], m = mu_out[e * ld_mu + a];
-                        const float x = __fadd_rn(m, __fmul_rn(sg, z[j]));          // torch.normal: mean + std * eps
-                        const float d = x - m;
-                        logp += -(d * d) / (2.0f * sg * sg) - logf(sg) - LOG_SQRT_2PI;   // Normal.log_prob, summed over the action dim
-                        st_actions[e * A + a] = x;
-                        st_mu[e * A + a] = m;
-                        st_sigma[e * A + a] = sg;
-                    }
+            for (int j = 0; j < 4; ++j) {
+                const int a = blk * 4 + j;
+                if (a < A) {
+                    const float sg = stdv[a], m = mu_out[e * ld_mu + a];
+                    const float x = __fadd_rn(m, __fmul_rn(sg, z[j]));          // torch.normal: mean + std * eps
+                    const float d = x - m;
+                    logp += -(d * d) / (2.0f * sg * sg) - logf(sg) - LOG_SQRT_2PI;   // Normal.log_prob, summed over the action dim
+                    st_actions[e * A + a] = x;
+                    st_mu[e * A + a] = m;
+                    st_sigma[e * A + a] = sg;
                 }
             }
         }
-        st_logp[e] = logp;
-        st_values[e] = value_out[e * ld_value];
+        logp += __shfl_xor_sync(0xffffffffu, logp, 1);
+        logp += __shfl_xor_sync(0xffffffffu, logp, 2);
+        if (on && blk == 0) {
+            st_logp[e] = logp;
+            st_values[e] = value_out[e * ld_value];
+        }
     }
     // the observations the action was computed from (the env rewrites its obs_buf in place on the next step)
     const long long n_o = static_cast<long long>(n_envs) * num_obs;
@@ -90,6 +97,8 @@ __global__ void __launch_bounds__(256) ppo_store_step_kernel(int n_envs, const f
                                                              uint8_t* __restrict__ st_dones, uint8_t* __restrict__ st_time_outs,
                                                              unsigned long long* __restrict__ event_dev) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (e == 0 && event_dev) *event_dev += 1;   // the next PPO.act draws from the next event
     if (e >= n_envs) return;
     st_rewards[e] = rewards[e];
@@ -113,10 +122,10 @@ int b200gym_ppo_act_store(int32_t n_envs, int32_t num_actions, int32_t num_obs, 
                  "ppo_act_store: critic observations need a source, a width and a leading dimension");
     const long long work = static_cast<long long>(n_envs) * ((num_obs + (st_critic_obs ? num_critic_obs : 0) + 3) / 4);
     long long blocks = ((work > n_envs ? work : n_envs) + 255) / 256;
-    const long long min_blocks = (n_envs + 255) / 256;
+    const long long min_blocks = (4LL * n_envs + 255) / 256;   // four lanes per env
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < min_blocks) blocks = min_blocks;
-    ppo_act_store_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    b200_launch_pdl(0, ppo_act_store_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream),
         n_envs, num_actions, num_obs, num_critic_obs, mu_out, ld_mu, value_out, ld_value, std, obs, ld_obs, critic_obs, ld_critic_obs,
         static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), event, reinterpret_cast<const unsigned long long*>(event_dev), env_id_offset,
         st_obs, st_critic_obs, st_actions, st_values,
@@ -128,9 +137,8 @@ int b200gym_ppo_act_store(int32_t n_envs, int32_t num_actions, int32_t num_obs, 
 int b200gym_ppo_store_step(int32_t n_envs, const float* rewards, const uint8_t* dones, const uint8_t* time_outs, float* st_rewards,
                            uint8_t* st_dones, uint8_t* st_time_outs, uint64_t* event_dev, void* stream) {
     B200_REQUIRE(n_envs > 0 && rewards && dones && st_rewards && st_dones && st_time_outs, B200GYM_EINVAL, "ppo_store_step: bad argument");
-    ppo_store_step_kernel<<<(n_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(n_envs, rewards, dones, time_outs, st_rewards,
-                                                                                              st_dones, st_time_outs,
-                                                                                              reinterpret_cast<unsigned long long*>(event_dev));
+    b200_launch_pdl(0, ppo_store_step_kernel, dim3((n_envs + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), n_envs, rewards, dones,
+                    time_outs, st_rewards, st_dones, st_time_outs, reinterpret_cast<unsigned long long*>(event_dev));
     B200_LAUNCH_CHECK("ppo_store_step");
     return B200GYM_OK;
 }
