@@ -132,7 +132,7 @@ def train_iteration(rank, world, device, total=4096, iters=10):
                 ms_per_iteration=ms_iter_g, update_ms=ms_upd, rollout_ms=ms_iter_g - ms_upd,
                 ms_per_iteration_eager_rollout=ms_iter, rollout_ms_eager=ms_iter - ms_upd,
                 samples_per_s=total * T / (ms_iter_g * 1e-3), gradient_exchange=alg.exchange, params_bit_identical_across_ranks=same,
-                launches_per_minibatch=4, scaling="strong")
+                launches_per_minibatch=2, scaling="strong")
 
 
 def run_all(rank, world, device):
