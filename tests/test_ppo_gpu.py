@@ -57,11 +57,11 @@ def test_gather_rows_matches_indexing():
         assert torch.equal(sig, flat(st.sigma)[idx])
 
 
-def _oracle_and_fused(num_obs=48, hidden=(128, 64, 32), seed=1):
+def _oracle_and_fused(num_obs=48, hidden=(128, 64, 32), seed=1, num_actions=12):
     from legged_gym_dev_b200.ppo import ActorCritic, PPO
     torch.manual_seed(seed)
-    ref = O.ActorCritic(num_obs, num_obs, 12, list(hidden), list(hidden), init_noise_std=1.0)
-    ac = ActorCritic(num_obs, num_obs, 12, actor_hidden_dims=hidden, critic_hidden_dims=hidden, init_noise_std=1.0)
+    ref = O.ActorCritic(num_obs, num_obs, num_actions, list(hidden), list(hidden), init_noise_std=1.0)
+    ac = ActorCritic(num_obs, num_obs, num_actions, actor_hidden_dims=hidden, critic_hidden_dims=hidden, init_noise_std=1.0)
     ac.load_state_dict(copy.deepcopy(ref.state_dict()))
     alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
               entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
@@ -75,12 +75,13 @@ def _fill(alg, ref, T, N, num_obs, seed=2):
     obs = torch.randn(T, N, num_obs, generator=g)
     with torch.no_grad():
         d = ref.dist(obs)
-        actions = d.mean + d.stddev * torch.randn(T, N, 12, generator=g)
+        A = ref.std.numel()
+        actions = d.mean + d.stddev * torch.randn(T, N, A, generator=g)
         logp = d.log_prob(actions).sum(-1, keepdim=True)
         values = ref.critic(obs)
     rewards, _, dones, time_outs, last_values = make_storage_inputs(T, N, seed)
     if alg.storage is None or (alg.storage.num_envs, alg.storage.num_transitions_per_env) != (N, T):
-        alg.init_storage(N, T, [num_obs], [None], [12])
+        alg.init_storage(N, T, [num_obs], [None], [ref.std.numel()])
     st = alg.storage
     for name, t in dict(observations=obs, actions=actions, actions_log_prob=logp, values=values, mu=d.mean, sigma=d.stddev,
                         rewards=rewards, dones=dones, time_outs=time_outs).items():
@@ -183,15 +184,17 @@ def test_ppo_update_rough_nets():
     _check_update(*_update_pair(235, (512, 256, 128), 24, 256, epochs=1))
 
 
-@pytest.mark.parametrize("num_obs,hidden,B,chain", [(48, (128, 64, 32), 6144, True), (48, (128, 64, 32), 6144, False),
-                                                     (235, (512, 256, 128), 3000, False), (48, (128, 64, 32), 100, True),
-                                                     (235, (128, 64), 1000, True), (40, (64, 128, 32, 32), 777, True)])
-def test_minibatch_gradients_match_autograd(num_obs, hidden, B, chain):
+@pytest.mark.parametrize("num_obs,hidden,B,chain,A", [(48, (128, 64, 32), 6144, True, 12), (48, (128, 64, 32), 6144, False, 12),
+                                                       (235, (512, 256, 128), 3000, False, 12), (48, (128, 64, 32), 100, True, 12),
+                                                       (235, (128, 64), 1000, True, 12), (40, (64, 128, 32, 32), 777, True, 12),
+                                                       (38, (128, 64, 32), 2000, True, 4), (48, (128, 64, 32), 1500, True, 16),
+                                                       (38, (128, 64, 32), 2000, False, 4)])
+def test_minibatch_gradients_match_autograd(num_obs, hidden, B, chain, A):
     """flat_grad after one forward/backward of the tcgen05 path vs torch autograd (fp32) of the restated loss on the same
     minibatch: gradient norm to 1e-3 relative, gradient vector to 5e-3 of its norm (fp16 operands, fp32 accumulation)."""
     from legged_gym_dev_b200 import _lib
     import ctypes as C
-    ref, alg = _oracle_and_fused(num_obs, hidden)
+    ref, alg = _oracle_and_fused(num_obs, hidden, num_actions=A)   # A = 4: the Hopper's action width; 16: the second reduction pass
     T, N = 8, 1024
     store = _fill(alg, ref, T, N, num_obs)
     with torch.no_grad():                       # move the policy away from the rollout policy: ratios != 1, clips engage
@@ -206,7 +209,7 @@ def test_minibatch_gradients_match_autograd(num_obs, hidden, B, chain):
     loss, info = O.ppo_loss(ref, batch, clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.01, use_clipped_value_loss=True)
     loss.backward()
     lp = _lib.PpoLossParamsPOD()
-    lp.batch, lp.num_actions, lp.use_clipped_value_loss = B, 12, 1
+    lp.batch, lp.num_actions, lp.use_clipped_value_loss = B, A, 1
     lp.clip_param, lp.value_loss_coef, lp.entropy_coef, lp.inv_global_batch = 0.2, 1.0, 0.01, 1.0 / B
     ac.flat_grad.zero_()
     sc = torch.zeros(4, dtype=torch.double, device="cuda")
