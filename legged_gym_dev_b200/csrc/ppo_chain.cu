@@ -141,10 +141,11 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = *tmem_slot;
-    // programmatic dependent launch: the set-up above ran while the optimiser kernel of the previous minibatch was draining; weights,
-    // biases and the cleared gradient buffer are its output, so every role waits here before touching global memory
+    // programmatic dependent launch: this grid is scheduled while the optimiser kernel of the previous minibatch runs.  Weights, biases
+    // and the cleared gradient buffer are that kernel's output: every role executes pdl_wait() before it touches them.  The rollout
+    // storage and the minibatch index were written before the update started, so the epilogue warps gather their observation rows (two
+    // dependent L2 / HBM round trips) BEFORE the wait, under the optimiser kernel.
     pdl_launch_dependents();
-    pdl_wait();
     const bool fuse = net.flat_grad != nullptr;
     Trace tr;
 #ifdef B200GYM_CHAIN_TRACE
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
 
     if (warp == MMA_WARP) {
         // ------------------------------ MMA issue ------------------------------
+        pdl_wait();
         int it = 0;
         for (int step = 0; step < nsteps; ++step) {
             const bool fwd = step < L, last = step == 2 * L - 1;
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
     } else if (warp >= LOADER_WARP0) {
         // ------------------------------ loaders: the input tile, the weight tiles of every step, the weight-gradient drain -------------
         const int t = tid - LOADER_TID0;
+        pdl_wait();   // the fp16 weights are the previous optimiser kernel's output
         if (net.x32 == nullptr) {
             load_tile(smem + act_off[0], CH128, static_cast<const __half*>(net.x), net.ldx, tile * TM, 0, TM, net.kp[0] >> 3, batch, net.kp[0], t);
             tc::cp_async_commit();
@@ -419,6 +422,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
         } else if (EH == 2 && half == 1) {
             tc::mbar_arrive(aready);   // fp16 input copied by the 128 loader threads: make up the barrier's 256 arrivals
         }
+        pdl_wait();   // from here on: parameters of the previous optimiser step, and (at the end) the gradient buffer it cleared
         // biases and policy constants into shared memory while step 0's MMAs run (only these warps read them): sigma, log sigma,
         // 1/(2 sigma^2), 1/sigma^2, 1/sigma are computed once per CTA instead of once per row
         for (int l = 0, o = 0; l < L; o += net.np[l], ++l)
