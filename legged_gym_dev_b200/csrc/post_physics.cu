@@ -31,6 +31,9 @@
 #ifndef PP_ALIAS_OBS
 #define PP_ALIAS_OBS 1     // the observation tile reuses the contact-force tile (dead after the contact pass of phase W)
 #endif
+#ifndef PP_MINBLOCKS_FLAT
+#define PP_MINBLOCKS_FLAT 10   // flat, non-trajectory kernel: 48 registers (no spills) and 22.0 KB of shared memory -> 10 CTAs per SM
+#endif
 #ifndef PP_MINBLOCKS
 #define PP_MINBLOCKS 9     // register cap so that 9 CTAs of 128 threads are resident per SM (A/B: profiles/r1_post_physics_ab.txt)
 #endif
@@ -215,11 +218,15 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
     s.traj = TRAJ ? c.take<float>(TILE * TRAJ_W) : nullptr;
     s.perr = TRAJ ? c.take<float>(TILE * 2) : nullptr;
     s.tpush = TRAJ ? c.take<float>(TILE) : nullptr;
-    s.blv = c.take<float>(TILE * 3);
-    s.bav = c.take<float>(TILE * 3);
-    s.pg = c.take<float>(TILE * 3);
-    s.lrv = c.take<float>(TILE * 6);
-    s.rew = c.take<float>(TILE);
+    // The torque and last-action tiles are only read in phase W; the per-env outputs of phase S (behind the barrier that ends phase W)
+    // are staged on top of them: 64 B per env less, which is what lets a 10th CTA of the flat kernel fit on an SM (131 072 envs = 4096
+    // tiles then take 3 rounds of 1480 resident CTAs instead of 4 rounds of 1332)
+    static_assert((TILE * 3 * sizeof(float)) % 16 == 0 && (TILE * sizeof(float)) % 16 == 0, "aliased output tiles must stay 16-byte aligned");
+    s.blv = s.tq;
+    s.bav = s.tq + TILE * 3;
+    s.pg = s.tq + TILE * 6;
+    s.rew = s.tq + TILE * 9;
+    s.lrv = s.lact;
     s.part = c.take<float>(NUM_PARTS * TILE);
     s.reset = c.take<uint8_t>(TILE);
     s.tout = c.take<uint8_t>(TILE);
@@ -257,7 +264,7 @@ __device__ __forceinline__ void coop_copy(T* dst, const T* src, int n) {
 }
 
 template <int TILE, bool ROUGH, bool TRAJ, bool HTMA = false>
-__global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? PP_MINBLOCKS : 1)) post_physics_kernel(const __grid_constant__ B200LeggedParams p,
+__global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? ((ROUGH || TRAJ) ? PP_MINBLOCKS : PP_MINBLOCKS_FLAT) : 1)) post_physics_kernel(const __grid_constant__ B200LeggedParams p,
                                                                                const __grid_constant__ B200LeggedBuffers b,
                                                                                uint64_t step, long long env_off, int do_push,
                                                                                const SqThr thr, const __grid_constant__ CUtensorMap hmap) {
