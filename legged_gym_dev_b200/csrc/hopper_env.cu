@@ -147,9 +147,12 @@ __device__ __forceinline__ void hopper_reset_env(const B200HopperEnvParams& p, c
 // byte ranges: they move between HBM and shared memory with coalesced cooperative copies (odd row strides in shared memory: conflict-free
 // per-env access), the [., 4] tensors are read as one float4 per thread.  (First version: every thread walked its own rows in global memory —
 // 13 + 15 + 20 strided loads and 38 strided stores per env, 40 % of HBM.)
+#ifndef HOPPER_MINBLOCKS
+#define HOPPER_MINBLOCKS 5   // resident CTAs per SM the register allocation aims at: 90 registers, no spills; 45.6 KB of shared memory still fit 5 (A/B: profiles/r2_hopper_occupancy.txt)
+#endif
 constexpr int HT_TILE = 128, HS_TRAJ = B200GYM_TRAJ_WIDTH + 1, HS_OBS = B200GYM_HOPPER_TRAJ_NUM_OBS + 1;
 
-__global__ void __launch_bounds__(HT_TILE, 4) hopper_post_physics_kernel(const __grid_constant__ B200HopperEnvParams p,
+__global__ void __launch_bounds__(HT_TILE, HOPPER_MINBLOCKS) hopper_post_physics_kernel(const __grid_constant__ B200HopperEnvParams p,
                                                                         const __grid_constant__ B200HopperEnvBuffers b, unsigned long long step,
                                                                         long long env_off) {
     const int N = p.num_envs, K = p.num_sum_rows, B = p.num_bodies;
