@@ -115,6 +115,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_f16_kernel(const __grid_
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = *tmem_slot;
+    // programmatic dependent launch: TMEM allocation and barrier set-up above overlap the previous launch's tail; operands and the
+    // accumulation target are other kernels' output
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 8) {
         // ------------------------------ MMA issue ------------------------------
@@ -312,7 +316,7 @@ extern "C" int b200gym_gemm_f16(const B200GemmProblem* problems, int32_t n_probl
         B200_REQUIRE(e == cudaSuccess, B200GYM_ECUDA, "gemm_f16: cannot reserve %zu B of shared memory: %s", GEMM_SMEM, cudaGetErrorString(e));
         configured = true;
     }
-    gemm_f16_kernel<<<ctas, GEMM_THREADS, GEMM_SMEM, static_cast<cudaStream_t>(stream)>>>(batch);
+    b200_launch_pdl(0, gemm_f16_kernel, dim3(ctas), dim3(GEMM_THREADS), GEMM_SMEM, static_cast<cudaStream_t>(stream), batch);
     B200_LAUNCH_CHECK("gemm_f16");
     return B200GYM_OK;
 }

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(256) rows_to_f16_kernel(const float* __restric
                                                           __half* __restrict__ dst, int dst_ld, long long n_rows) {
     const int pieces = dst_ld >> 3;
     const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    pdl_launch_dependents();   // programmatic dependent launch (common.cuh)
+    pdl_wait();
     if (q >= n_rows * pieces) return;
     const long long row = q / pieces;
     const int c0 = static_cast<int>(q - row * pieces) * 8;
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(256) ppo_loss_gathered_kernel(const __grid_con
     const int A = p.num_actions;
     __shared__ float s_dstd[MAXA];
     __shared__ double s_acc[4][8];
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x < MAXA) s_dstd[threadIdx.x] = 0.0f;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,8 +461,8 @@ int b200gym_rows_to_f16(const float* src, int64_t src_ld, int32_t cols, const in
     B200_REQUIRE(dst_ld % 8 == 0 && dst_ld >= cols && src_ld >= cols && b200_aligned16(dst), B200GYM_EALIGN,
                  "rows_to_f16: dst must be 16-byte aligned with dst_ld %% 8 == 0, dst_ld >= cols");
     const long long total = n_rows * (dst_ld / 8);
-    rows_to_f16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, src_ld, cols, reinterpret_cast<const long long*>(idx), static_cast<__half*>(dst), dst_ld, n_rows);
+    b200_launch_pdl(0, rows_to_f16_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, src_ld,
+                    cols, reinterpret_cast<const long long*>(idx), static_cast<__half*>(dst), dst_ld, n_rows);
     B200_LAUNCH_CHECK("rows_to_f16");
     return B200GYM_OK;
 }
@@ -473,9 +477,9 @@ int b200gym_ppo_loss_gathered(const B200PpoLossParams* p, const int64_t* idx, co
     B200_REQUIRE(p->batch > 0 && p->num_actions > 0 && p->num_actions <= MAXA && ld_mu >= p->num_actions && ld_value >= 1, B200GYM_EINVAL,
                  "ppo_loss_gathered: batch > 0, 1..%d actions", MAXA);
     B200_REQUIRE(b200_aligned16(dz_actor) && b200_aligned16(dz_critic), B200GYM_EALIGN, "ppo_loss_gathered: dZ buffers must be 16-byte aligned");
-    ppo_loss_gathered_kernel<<<(p->batch + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        *p, reinterpret_cast<const long long*>(idx), mu_out, ld_mu, value_out, ld_value, std, actions, old_log_prob, advantages, returns,
-        old_values, old_mu, old_sigma, static_cast<__half*>(dz_actor), static_cast<__half*>(dz_critic), d_std, scalars);
+    b200_launch_pdl(0, ppo_loss_gathered_kernel, dim3((p->batch + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), *p,
+                    reinterpret_cast<const long long*>(idx), mu_out, ld_mu, value_out, ld_value, std, actions, old_log_prob, advantages, returns,
+                    old_values, old_mu, old_sigma, static_cast<__half*>(dz_actor), static_cast<__half*>(dz_critic), d_std, scalars);
     B200_LAUNCH_CHECK("ppo_loss_gathered");
     return B200GYM_OK;
 }

@@ -173,7 +173,9 @@ class TensorCoreTrainer:
     def _wgrad_launches(self, b, B, scale):
         fg = self.ac.flat_grad
         tiles = sum(((net.Np[l] + 127) // 128) * ((net.Kp[l] + 127) // 128) for net in self.nets for l in range(net.L))
-        splits = max(1, min((B + 255) // 256, round(192 / tiles)))   # A/B at 24 576 rows x 8 tiles: 24 splits 2.35 ms / 37: 2.41 / 16: 2.50 / 48: 2.45
+        # A/B at 24 576 rows (B200): 8 tiles (flat nets, unfused form): 24 splits 2.35 ms / 37: 2.41 / 16: 2.50 / 48: 2.45; 38 tiles (rough
+        # nets): 8 splits = 304 CTAs = one wave of 2 CTAs per SM 11.8 ms / 5: 13.0 / 6: 12.4 / 10: 13.0 / 12: 12.7 / 16: 12.4
+        splits = max(1, min((B + 255) // 256, round(192 / tiles) if tiles <= 8 else round(296 / tiles)))
         if os.environ.get("B200GYM_WGRAD_SPLITS"):      # A/B knob (profiles/): batch-row splits of every weight-gradient problem
             splits = max(1, min((B + 127) // 128, int(os.environ["B200GYM_WGRAD_SPLITS"])))
         ps = []
