@@ -271,6 +271,19 @@ __global__ void __launch_bounds__(128) fam_reset_kernel(const __grid_constant__ 
                  s.trajectory + i * (p.window + 1) * Rom<T>::n, s.v_trajectory + i * p.window * Rom<T>::m);
 }
 
+// LeggedRobotTrajectory's view of the generator (get_trajectory, rom_dynamics.py:607-612, written into env.trajectory [N, N_h, n]):
+// knot j of the horizon interpolated towards the next one by (t - (k-1) rom.dt) / rom.dt — the arithmetic of rom.cu's write_views
+template <int RN>
+__device__ __forceinline__ void write_env_window(const B200RomFamilyParams& p, const float* tr, float t, float k, float* et) {
+    const float sc = sub_rn(t, mul_rn(sub_rn(k, 1.0f), p.rom_dt));
+    const int horizon = p.window / p.dN;
+    for (int j = 0; j < horizon; ++j) {
+        const int a = j * p.dN * RN;
+#pragma unroll
+        for (int c = 0; c < RN; ++c) et[j * RN + c] = add_rn(tr[a + c], div_rn(mul_rn(sub_rn(tr[a + RN + c], tr[a + c]), sc), p.rom_dt));
+    }
+}
+
 template <int T>
 __global__ void __launch_bounds__(128) fam_step_kernel(const __grid_constant__ B200RomFamilyParams p, const __grid_constant__ B200RomState s,
                                                        const uint8_t* __restrict__ mask, long long env_off) {
@@ -313,6 +326,7 @@ __global__ void __launch_bounds__(128) fam_step_kernel(const __grid_constant__ B
     if (g.ctr != ctr0) store_params(s, i, g);
 #pragma unroll
     for (int c = 0; c < M; ++c) s.v[i * M + c] = g.v[c];
+    if (s.env_trajectory) write_env_window<RN>(p, tr, g.t, g.k, s.env_trajectory + i * (w / p.dN) * RN);
 }
 
 // The same step with the CTA's horizon windows staged through shared memory.  The windows of 128 consecutive envs are ONE contiguous
@@ -330,9 +344,10 @@ __global__ void __launch_bounds__(FT) fam_step_tile_kernel(const __grid_constant
     extern __shared__ __align__(128) float fam_smem[];
     __shared__ uint64_t bar;
     const int w = p.window;
-    const int rl = (w + 1) * RN, vl = w * M;   // floats per env in the two windows
+    const int rl = (w + 1) * RN, vl = w * M, hl = (w / p.dN) * RN;   // floats per env: the two windows, the env's interpolated view
     float* s_tr = fam_smem;
     float* s_vt = fam_smem + FT * rl;
+    float* s_et = s_vt + FT * vl;                                      // only carved / used with an attached env (s.env_trajectory)
     const int env0 = blockIdx.x * FT;
     const int nenv = min(FT, p.num_envs - env0);
     const int e = threadIdx.x;
@@ -348,22 +363,29 @@ __global__ void __launch_bounds__(FT) fam_step_tile_kernel(const __grid_constant
     const bool in_idx = valid && (mask == nullptr || mask[i] != 0);
     const bool due = in_idx && (g.t >= sub_rn(mul_rn(g.k, p.rom_dt), 1e-5f));
     const uint32_t bytes_tr = static_cast<uint32_t>(nenv) * rl * 4u, bytes_vt = static_cast<uint32_t>(nenv) * vl * 4u;
-    const bool tile_ok = ((bytes_tr | bytes_vt) & 15u) == 0 && ((reinterpret_cast<uintptr_t>(g_tr) | reinterpret_cast<uintptr_t>(g_vt)) & 15u) == 0;
-    const bool staged = __syncthreads_or(due) != 0 && tile_ok;
-    if (staged) {
+    const uint32_t bytes_et = static_cast<uint32_t>(nenv) * hl * 4u;
+    // an attached env reads the whole state window on EVERY call (its view is an interpolation over all knots), so that window is
+    // staged on every call and the view leaves as one bulk store; the input window still moves only when a knot is appended
+    float* g_et = s.env_trajectory ? s.env_trajectory + static_cast<size_t>(env0) * hl : nullptr;
+    const bool tile_ok = ((bytes_tr | bytes_vt | (g_et ? bytes_et : 0u)) & 15u) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(g_tr) | reinterpret_cast<uintptr_t>(g_vt) | reinterpret_cast<uintptr_t>(g_et)) & 15u) == 0;
+    const bool any_due = __syncthreads_or(due) != 0;
+    const bool staged = any_due && tile_ok;              // both windows in shared memory, written back
+    const bool staged_tr = tile_ok && (any_due || g_et != nullptr);
+    if (staged_tr) {
         if (e == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
         }
         __syncthreads();
         if (e == 0) {
-            mbar_expect_tx(&bar, bytes_tr + bytes_vt);
+            mbar_expect_tx(&bar, bytes_tr + (staged ? bytes_vt : 0u));
             bulk_g2s(s_tr, g_tr, bytes_tr, &bar);
-            bulk_g2s(s_vt, g_vt, bytes_vt, &bar);
+            if (staged) bulk_g2s(s_vt, g_vt, bytes_vt, &bar);
         }
         mbar_wait(&bar, 0);
     }
-    float* tr = staged ? s_tr + e * rl : s.trajectory + i * rl;
+    float* tr = staged_tr ? s_tr + e * rl : s.trajectory + i * rl;
     float* vt = staged ? s_vt + e * vl : s.v_trajectory + i * vl;
     const uint32_t ctr0 = g.ctr;
     if (valid) {
@@ -390,13 +412,17 @@ __global__ void __launch_bounds__(FT) fam_step_tile_kernel(const __grid_constant
         if (g.ctr != ctr0) store_params(s, i, g);
 #pragma unroll
         for (int c = 0; c < M; ++c) s.v[i * M + c] = g.v[c];
+        if (g_et) write_env_window<RN>(p, tr, g.t, g.k, staged_tr ? s_et + e * hl : s.env_trajectory + i * hl);
     }
-    if (staged) {
+    if (staged_tr) {
         fence_proxy_async();
         __syncthreads();
         if (e == 0) {
-            bulk_s2g(g_tr, s_tr, bytes_tr);
-            bulk_s2g(g_vt, s_vt, bytes_vt);
+            if (staged) {
+                bulk_s2g(g_tr, s_tr, bytes_tr);
+                bulk_s2g(g_vt, s_vt, bytes_vt);
+            }
+            if (g_et) bulk_s2g(g_et, s_et, bytes_et);
             bulk_commit();
             bulk_wait0();
         }
@@ -605,9 +631,10 @@ bool fam_tile_enabled() {
     static const bool on = []() { const char* e = getenv("B200GYM_ROMFAM_TILE"); return !(e && e[0] == '0'); }();
     return on;
 }
-size_t fam_tile_bytes(const B200RomFamilyParams* p) {   // both horizon windows of a CTA's 128 envs
+size_t fam_tile_bytes(const B200RomFamilyParams* p, bool env_view = false) {   // both horizon windows of a CTA's 128 envs (+ the env's view)
     const int n_of[B200GYM_ROM_NUM_TYPES] = {2, 4, 3, 3, 5, 6}, m_of[B200GYM_ROM_NUM_TYPES] = {2, 2, 2, 3, 2, 3};
-    return static_cast<size_t>(128) * ((p->window + 1) * n_of[p->rom_type] + p->window * m_of[p->rom_type]) * sizeof(float);
+    const int hl = env_view ? (p->window / (p->dN > 0 ? p->dN : 1)) * n_of[p->rom_type] : 0;
+    return static_cast<size_t>(128) * ((p->window + 1) * n_of[p->rom_type] + p->window * m_of[p->rom_type] + hl) * sizeof(float);
 }
 
 int check_rows(int32_t rom_type, int64_t n_rows, const char* what) {
@@ -697,7 +724,9 @@ int b200gym_romfam_gen_step(const B200RomFamilyParams* p, const B200RomState* s,
     const int grid = (p->num_envs + 127) / 128;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // windows staged through shared memory (TMA bulk tiles) unless they do not fit or B200GYM_ROMFAM_TILE=0 asks for the per-thread kernel
-    const size_t smem = fam_tile_bytes(p);
+    B200_REQUIRE(s->env_trajectory == nullptr || (p->dN > 0 && p->window % p->dN == 0), B200GYM_EINVAL,
+                 "romfam_gen_step: an attached env view needs window %% dN == 0");
+    const size_t smem = fam_tile_bytes(p, s->env_trajectory != nullptr);
     if (fam_tile_enabled() && smem <= 200 * 1024) {
         FAM_DISPATCH(p->rom_type, {
             static size_t granted = 0;   // per rom class: raise the dynamic shared-memory limit once per size, not on every call

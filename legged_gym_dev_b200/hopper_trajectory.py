@@ -323,7 +323,7 @@ class HopperTrajectory:
     def post_physics_step(self):                                          # hopper_trajectory.py:135-182
         self.common_step_counter += 1
         g, st = self.traj_gen, _lib.stream_ptr(self.device)
-        _lib.check(self.lib.b200gym_rom_step(g._p, g._s, None, None, self.env_id_offset, st), "rom_step")   # callback (base :409-410)
+        _lib.check(g.env_step(st), "rom_step")   # callback (base :409-410)
         _lib.check(self.lib.b200gym_hopper_post_physics(self._pod, self._buffers(), self.common_step_counter, self.env_id_offset, st),
                    "hopper_post_physics")
         K = self._extras_out.numel() - 2

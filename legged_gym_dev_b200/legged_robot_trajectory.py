@@ -156,7 +156,7 @@ class LeggedRobotTrajectory(LeggedRobot):
         ev = self._event_start()
         st = self._stream if self._stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         g = self.traj_gen
-        rc = self.lib.b200gym_rom_step(g._p, g._s, None, None, self.env_id_offset, st)          # :409-410
+        rc = g.env_step(st)                                                                      # :409-410
         if rc:
             _lib.check(rc, "rom_step")
         rc = self.lib.b200gym_post_physics(self._pod, self._buffers(), self.common_step_counter, self.env_id_offset, st)

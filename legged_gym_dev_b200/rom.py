@@ -19,6 +19,8 @@ reference evaluates with scipy on the host) and a stand-alone TrajectoryGenerato
 import ctypes as C
 import math
 
+import os
+
 import torch
 
 from . import _lib
@@ -383,11 +385,22 @@ class TrajectoryGenerator:
 
     def step_idx(self, idx):
         m, mp = self._mask_ptr(idx)
-        if self._family and not (self._s.env_trajectory or self._s.obs):     # attached views are refreshed by b200gym_rom_step only
+        # a CustomSim's observation view is refreshed by b200gym_rom_step only; a trajectory env's interpolated window (env_trajectory) is
+        # written by the window-staging kernel as well (one bulk store per 128 envs)
+        if self._family and not self._s.obs:
             _lib.check(self.lib.b200gym_romfam_gen_step(self._fp, self._s, mp, self.env_id_offset, _lib.stream_ptr(self.device)),
                        "romfam_gen_step")
             return
         _lib.check(self.lib.b200gym_rom_step(self._p, self._s, None, mp, self.env_id_offset, _lib.stream_ptr(self.device)), "rom_step")
+
+    def env_step(self, stream):
+        """The generator step of an attached trajectory env (legged_robot_trajectory.py:409-410): `traj_gen.step()` plus the refresh of the
+        env's interpolated window.  The random generator goes through the window-staging kernel (csrc/rom_family.cu: the state window
+        and the env's view move as bulk tiles, bit-identical to b200gym_rom_step); the Zero / Square / Circle generators and
+        B200GYM_ENV_GEN_TILE=0 through b200gym_rom_step.  Returns the C-ABI status."""
+        if self.kind == 0 and not self._s.obs and os.environ.get("B200GYM_ENV_GEN_TILE", "1") != "0":
+            return self.lib.b200gym_romfam_gen_step(self._fp, self._s, None, self.env_id_offset, stream)
+        return self.lib.b200gym_rom_step(self._p, self._s, None, None, self.env_id_offset, stream)
 
     def get_trajectory(self):                                             # rom_dynamics.py:607-612
         t0, t1 = self.trajectory[:, :-1, :], self.trajectory[:, 1:, :]
