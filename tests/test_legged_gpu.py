@@ -307,6 +307,32 @@ def test_trajectory_env_external_reset_matches_oracle(name, N):
     assert float(env.traj_gen.k.min()) >= 0
 
 
+@pytest.mark.parametrize("name,N", [("traj_flat_allterms", 1000), ("traj_rough_lstm_allterms", 132)])
+def test_trajectory_env_generator_step_kernels_are_bit_identical(name, N, monkeypatch):
+    """The trajectory env's generator step through the window-staging kernel (state window and the env's interpolated view moved as
+    bulk tiles, csrc/rom_family.cu) against b200gym_rom_step (B200GYM_ENV_GEN_TILE=0): every buffer of the env and of the generator
+    agrees bit for bit over a run with resets and new knots (N = 132: a 4-env tail CTA)."""
+    case = LC.build_case(name, N)
+    runs = {}
+    for tile in ("1", "0"):
+        monkeypatch.setenv("B200GYM_ENV_GEN_TILE", tile)
+        env = LC.make_fused(case)
+        env.reset_traj(torch.arange(N, device="cuda"))
+        snaps = []
+        for s in range(14):
+            env.step(case.tape.actions[s % case.tape.frames].cuda())
+            snap = LC.snapshot_fused(env)
+            snap["gen_v"], snap["gen_t"], snap["gen_k"] = env.traj_gen.v.clone(), env.traj_gen.t.clone(), env.traj_gen.k.clone()
+            snap["gen_traj"], snap["gen_vtraj"] = env.traj_gen.trajectory.clone(), env.traj_gen.v_trajectory.clone()
+            snaps.append(snap)
+        runs[tile] = snaps
+    for s in range(14):
+        for k, v in runs["1"][s].items():
+            w = runs["0"][s][k]
+            if torch.is_tensor(v):
+                assert torch.equal(v, w), (s, k)
+
+
 def test_trajectory_env_shard_invariance():
     """Per-env results of the trajectory env do not depend on the split over ranks (env and generator draws keyed by global id)."""
     N, half = 256, 128
