@@ -179,7 +179,7 @@ struct TileSmem {
     float *root, *dof, *contact, *act, *tq, *lact, *ldv, *cmd, *fat;
     uint8_t* lc;
     long long* ep;
-    float *sums, *obs, *blv, *bav, *pg, *lrv, *rew, *part;
+    float *sums, *obs, *blv, *bav, *pg, *lrv, *rew, *part, *part_b, *part_c;   // part rows 0-1 / 2-7 / 8-12 (see carve_tile)
     uint8_t *reset, *tout;
     int16_t* hraw;
     float *bh, *zpost, *stage, *hsum, *unoise;
@@ -191,6 +191,13 @@ struct TileSmem {
     int* nreset;
     size_t bytes;
 };
+
+// row k (compile-time) of the per-env partial sums, env e
+template <int TILE>
+__device__ __forceinline__ float& part_at(const TileSmem& s, int k, int e) {
+    return k < 2 ? s.part[k * TILE + e] : k < 8 ? s.part_b[(k - 2) * TILE + e] : s.part_c[(k - 8) * TILE + e];
+}
+#define PART(k) part_at<TILE>(s, (k), e)
 
 template <int TILE, bool ROUGH, bool TRAJ>
 __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K, bool need_hpart, bool tma_heights = false) {
@@ -227,7 +234,20 @@ __device__ __host__ inline TileSmem carve_tile(unsigned char* base, int B, int K
     s.pg = s.tq + TILE * 6;
     s.rew = s.tq + TILE * 9;
     s.lrv = s.lact;
-    s.part = c.take<float>(NUM_PARTS * TILE);
+    // Phase W's per-env partial sums (NUM_PARTS rows of TILE floats, written after the barrier that retires the contact tile, read in phase
+    // S).  Trajectory layout: they fit in what is dead by then and not claimed by the phase-S outputs above — the last 2 rows of the torque
+    // tile, the last 6 of the last-action tile and the 10 rows behind the 65-column observation tile in [dof | contact] — which brings
+    // the trajectory kernel from 8 to 9 resident CTAs per SM.  Otherwise one block of their own.
+    static_assert(NUM_PARTS == 13, "part rows are split 2 + 6 + 5");
+    if (PP_ALIAS_OBS && TRAJ && B * 3 < OW && 24 + B * 3 >= OW + 5) {
+        s.part = s.tq + TILE * 10;
+        s.part_b = s.lact + TILE * 6;
+        s.part_c = s.dof + TILE * OW;
+    } else {
+        s.part = c.take<float>(NUM_PARTS * TILE);
+        s.part_b = s.part + TILE * 2;
+        s.part_c = s.part + TILE * 8;
+    }
     s.reset = c.take<uint8_t>(TILE);
     s.tout = c.take<uint8_t>(TILE);
     s.acc = c.take<double>(B200GYM_NUM_REWARD_TERMS + 2);
@@ -598,16 +618,15 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? ((ROUGH || TRAJ) ? PP
         if (rs[T_TORQUE_LIMITS] != 0.f) ptq_lim = quad_sum(ptq_lim);
         if (rs[T_STUMBLE] != 0.f) p_stumble = quad_sum(p_stumble);
         if (rs[T_FEET_CONTACT_FORCES] != 0.f) p_fcf = quad_sum(p_fcf);
-        float* P = s.part + e;
         if (g == 0) {
-            P[P_ACTION_RATE * TILE] = pa_rate, P[P_DOF_ACC * TILE] = pd_acc, P[P_DOF_VEL * TILE] = pd_vel;
-            P[P_TORQUES * TILE] = ptq;
+            PART(P_ACTION_RATE) = pa_rate, PART(P_DOF_ACC) = pd_acc, PART(P_DOF_VEL) = pd_vel;
+            PART(P_TORQUES) = ptq;
         } else if (g == 1) {
-            P[P_POS_LIM * TILE] = ppos_lim, P[P_VEL_LIM * TILE] = pvel_lim, P[P_TQ_LIM * TILE] = ptq_lim;
+            PART(P_POS_LIM) = ppos_lim, PART(P_VEL_LIM) = pvel_lim, PART(P_TQ_LIM) = ptq_lim;
         } else if (g == 2) {
-            P[P_STAND * TILE] = pstand, P[P_AIR * TILE] = p_air, P[P_STUMBLE * TILE] = p_stumble;
+            PART(P_STAND) = pstand, PART(P_AIR) = p_air, PART(P_STUMBLE) = p_stumble;
         } else {
-            P[P_FCF * TILE] = p_fcf, P[P_COLL * TILE] = p_coll, P[P_TERM * TILE] = p_term;
+            PART(P_FCF) = p_fcf, PART(P_COLL) = p_coll, PART(P_TERM) = p_term;
         }
     }
     __syncthreads();
@@ -619,7 +638,6 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? ((ROUGH || TRAJ) ? PP
         const size_t ge = static_cast<size_t>(tile0 + e);
         const philox::Stream rng(p.seed_lo, p.seed_hi, static_cast<uint64_t>(env_off + tile0 + e), step);
         const float* R = s.root + e * 13;
-        const float* P = s.part + e;
         const float qx = R[3], qy = R[4], qz = R[5], qw = R[6];
 
         // R4: counters + body-frame vectors (legged_robot.py:114-121)
@@ -660,7 +678,7 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? ((ROUGH || TRAJ) ? PP
 
         // R8: termination (legged_robot.py:139-145)
         const bool time_out = static_cast<float>(ep) > p.max_episode_length;
-        const bool reset = (P[P_TERM * TILE] > 0.0f) | time_out;
+        const bool reset = (PART(P_TERM) > 0.0f) | time_out;
 
         // R9: reward assembly in the reference's (alphabetical) order (legged_robot.py:189-206)
 #if PP_SQNORM
@@ -677,7 +695,7 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? ((ROUGH || TRAJ) ? PP
             rew += r;
             sums[p.sum_row[k] * TILE] += r;
         };
-        if (rs[T_ACTION_RATE] != 0.f) add_term(T_ACTION_RATE, P[P_ACTION_RATE * TILE]);
+        if (rs[T_ACTION_RATE] != 0.f) add_term(T_ACTION_RATE, PART(P_ACTION_RATE));
         if (rs[T_ANG_VEL_XY] != 0.f) add_term(T_ANG_VEL_XY, bax * bax + bay * bay);
         if (rs[T_BASE_HEIGHT] != 0.f) {
             float bh = R[2];
@@ -686,7 +704,7 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? ((ROUGH || TRAJ) ? PP
             const float dh = bh - p.base_height_target;
             add_term(T_BASE_HEIGHT, dh * dh);
         }
-        if (rs[T_COLLISION] != 0.f) add_term(T_COLLISION, P[P_COLL * TILE]);
+        if (rs[T_COLLISION] != 0.f) add_term(T_COLLISION, PART(P_COLL));
         float te0 = 0.0f, te1 = 0.0f;   // square(proj_z(root) - trajectory[:, 0]) (legged_robot_trajectory.py:1064-1066, :1101-1103)
         if (TRAJ) {
             const float d0 = R[0] - s.traj[e * TRAJ_W], d1 = R[1] - s.traj[e * TRAJ_W + 1];
@@ -697,18 +715,18 @@ __global__ void __launch_bounds__(TILE* LPE, (TILE == 32 ? ((ROUGH || TRAJ) ? PP
                 add_term(T_DIFFERENTIAL_ERROR, (de < 0.0f ? p.diff_neg_slope : p.diff_pos_slope) * de);
             }
         }
-        if (rs[T_DOF_ACC] != 0.f) add_term(T_DOF_ACC, P[P_DOF_ACC * TILE]);
-        if (rs[T_DOF_POS_LIMITS] != 0.f) add_term(T_DOF_POS_LIMITS, P[P_POS_LIM * TILE]);
-        if (rs[T_DOF_VEL] != 0.f) add_term(T_DOF_VEL, P[P_DOF_VEL * TILE]);
-        if (rs[T_DOF_VEL_LIMITS] != 0.f) add_term(T_DOF_VEL_LIMITS, P[P_VEL_LIM * TILE]);
-        if (rs[T_FEET_AIR_TIME] != 0.f) add_term(T_FEET_AIR_TIME, TRAJ ? P[P_AIR * TILE] : P[P_AIR * TILE] * (cmd_gt01 ? 1.0f : 0.0f));
-        if (rs[T_FEET_CONTACT_FORCES] != 0.f) add_term(T_FEET_CONTACT_FORCES, P[P_FCF * TILE]);
+        if (rs[T_DOF_ACC] != 0.f) add_term(T_DOF_ACC, PART(P_DOF_ACC));
+        if (rs[T_DOF_POS_LIMITS] != 0.f) add_term(T_DOF_POS_LIMITS, PART(P_POS_LIM));
+        if (rs[T_DOF_VEL] != 0.f) add_term(T_DOF_VEL, PART(P_DOF_VEL));
+        if (rs[T_DOF_VEL_LIMITS] != 0.f) add_term(T_DOF_VEL_LIMITS, PART(P_VEL_LIM));
+        if (rs[T_FEET_AIR_TIME] != 0.f) add_term(T_FEET_AIR_TIME, TRAJ ? PART(P_AIR) : PART(P_AIR) * (cmd_gt01 ? 1.0f : 0.0f));
+        if (rs[T_FEET_CONTACT_FORCES] != 0.f) add_term(T_FEET_CONTACT_FORCES, PART(P_FCF));
         if (rs[T_LIN_VEL_Z] != 0.f) add_term(T_LIN_VEL_Z, blz * blz);
         if (rs[T_ORIENTATION] != 0.f) add_term(T_ORIENTATION, pgx * pgx + pgy * pgy);
-        if (rs[T_STAND_STILL] != 0.f) add_term(T_STAND_STILL, P[P_STAND * TILE] * (cmd_lt01 ? 1.0f : 0.0f));
-        if (rs[T_STUMBLE] != 0.f) add_term(T_STUMBLE, P[P_STUMBLE * TILE] > 0.0f ? 1.0f : 0.0f);
-        if (rs[T_TORQUE_LIMITS] != 0.f) add_term(T_TORQUE_LIMITS, P[P_TQ_LIM * TILE]);
-        if (rs[T_TORQUES] != 0.f) add_term(T_TORQUES, P[P_TORQUES * TILE]);
+        if (rs[T_STAND_STILL] != 0.f) add_term(T_STAND_STILL, PART(P_STAND) * (cmd_lt01 ? 1.0f : 0.0f));
+        if (rs[T_STUMBLE] != 0.f) add_term(T_STUMBLE, PART(P_STUMBLE) > 0.0f ? 1.0f : 0.0f);
+        if (rs[T_TORQUE_LIMITS] != 0.f) add_term(T_TORQUE_LIMITS, PART(P_TQ_LIM));
+        if (rs[T_TORQUES] != 0.f) add_term(T_TORQUES, PART(P_TORQUES));
         const float inv_sigma = 1.0f / p.tracking_sigma;
         if (rs[T_TRACKING_ANG_VEL] != 0.f) {
             const float er = c2 - baz;
