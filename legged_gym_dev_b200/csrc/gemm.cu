@@ -26,7 +26,7 @@ constexpr int B_STAGE = (BN / 8 + 2) * CH_ROWSKC;  // 18 chunks (BN + the 16-col
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
 constexpr int GEMM_THREADS = 288;
 constexpr uint32_t TMEM_COLS = 256;
-constexpr size_t GEMM_SMEM = static_cast<size_t>(NSTAGE) * STAGE_BYTES + 128;
+constexpr size_t GEMM_SMEM = static_cast<size_t>(NSTAGE) * STAGE_BYTES + 128 + BN * sizeof(float);   // stages, barriers, the tile's bias row
 static_assert(8 * CH_ROWS128 <= A_STAGE && 8 * CH_ROWS128 <= B_STAGE, "stage regions too small");
 
 struct GemmBatch {
@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_f16_kernel(const __grid_
     uint64_t* empty = full + NSTAGE;
     uint64_t* accum = empty + NSTAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    float* s_bias = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES + 128);
 
     // ---- which problem / tile / split is this CTA ----
     int pi = 0;
@@ -179,30 +180,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_f16_kernel(const __grid_
         tc::mbar_arrive(full + (nstages - 1) % NSTAGE);
     } else {
         // ------------------------------ epilogue: TMEM lane = tile row ------------------------------
-        tc::mbar_wait_sleep(accum, 0);
-        tc::fence_after();
+        // (two co-resident CTAs of 106 KB leave no L1: a global load in this role is an L2 round trip on the critical path, so
+        //  what the epilogue needs from global memory is fetched while the main loop runs)
         const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
         const int grow = tile_m * TM + tid;
         const int gcol0 = tile_n * BN;
+        uint4 aux_pre[8];   // DGRAD: the first 64 columns of this row's H (ELU derivative), in flight during the main loop
+        if (mode == B200GYM_GEMM_FWD) {
+            s_bias[tid] = (P.bias != nullptr && gcol0 + tid < P.n_real) ? __ldg(P.bias + gcol0 + tid) : 0.0f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        } else if (mode == B200GYM_GEMM_DGRAD) {
+            const __half* aux = static_cast<const __half*>(P.aux);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                aux_pre[q] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);   // h = 1 -> derivative 1
+                if (aux != nullptr && grow < P.m && 8 * q < bn_eff)
+                    aux_pre[q] = __ldg(reinterpret_cast<const uint4*>(aux + static_cast<size_t>(grow) * P.ldaux + gcol0) + q);
+            }
+        }
+        tc::mbar_wait_sleep(accum, 0);
+        tc::fence_after();
         if (mode == B200GYM_GEMM_FWD) {
             const bool live = grow < P.m, elu = (P.flags & 1) != 0, f32out = (P.flags & 2) != 0;
-            const float* bias = P.bias;
             for (int n0 = 0; n0 < bn_eff; n0 += 16) {
                 uint32_t r[16];
                 tc::ld16_issue(taddr + n0, r);
-                tc::ld16_wait(r);
-                float v[16], bv[16];
-                const int c0 = gcol0 + n0;
-                if (bias != nullptr && c0 + 16 <= P.n_real && (reinterpret_cast<uintptr_t>(bias + c0) & 15) == 0) {
+                float bv[16];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
-                        bv[4 * q] = b4.x, bv[4 * q + 1] = b4.y, bv[4 * q + 2] = b4.z, bv[4 * q + 3] = b4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) bv[j] = (bias != nullptr && c0 + j < P.n_real) ? __ldg(bias + c0 + j) : 0.0f;
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + 4 * q);
+                    bv[4 * q] = b4.x, bv[4 * q + 1] = b4.y, bv[4 * q + 2] = b4.z, bv[4 * q + 3] = b4.w;
                 }
+                tc::ld16_wait(r);
+                float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float x = __uint_as_float(r[j]) + bv[j];
@@ -223,14 +233,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_f16_kernel(const __grid_
         } else if (mode == B200GYM_GEMM_DGRAD) {
             const bool live = grow < P.m;
             const __half* aux = static_cast<const __half*>(P.aux);
-            for (int n0 = 0; n0 < bn_eff; n0 += 16) {
+#pragma unroll
+            for (int blk = 0; blk < BN / 16; ++blk) {
+                const int n0 = 16 * blk;
+                if (n0 >= bn_eff) break;
                 uint32_t r[16];
                 tc::ld16_issue(taddr + n0, r);
-                uint4 h0 = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u), h1 = h0;   // h = 1 -> derivative 1
-                if (aux != nullptr && live) {
-                    const uint4* hp = reinterpret_cast<const uint4*>(aux + static_cast<size_t>(grow) * P.ldaux + gcol0 + n0);
-                    h0 = __ldg(hp), h1 = __ldg(hp + 1);
+                if (blk == 4) {   // second half of the row: one batch of loads, issued together
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        aux_pre[q] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+                        if (aux != nullptr && live && 64 + 8 * q < bn_eff)
+                            aux_pre[q] = __ldg(reinterpret_cast<const uint4*>(aux + static_cast<size_t>(grow) * P.ldaux + gcol0 + 64) + q);
+                    }
                 }
+                const uint4 h0 = aux_pre[2 * (blk & 3)], h1 = aux_pre[2 * (blk & 3) + 1];
                 tc::ld16_wait(r);
                 const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                 uint32_t o[8];
