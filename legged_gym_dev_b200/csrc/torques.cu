@@ -154,6 +154,27 @@ __device__ __forceinline__ void lstm_cell(const float2 (&w_ih)[16][NIN], const f
     lstm_gates(gate, h, c);
 }
 
+// The same cell with scalar fma: each weight is a constant-bank OPERAND of its FFMA, where the packed form needs an LDC.64 into registers
+// first (ncu at 4096 envs: 22 % issue utilisation, short-scoreboard waits on those loads); here ptxas fetches the weights four at a time.
+// Twice the FMA-pipe issues, but measured faster at every size (profiles/r2_lstm_scalar_ab.txt), so it is the default; the packed
+// form stays selectable (B200GYM_LSTM_VARIANT=3).  Same products, same rounding: bit-identical.
+template <int NIN>
+__device__ __forceinline__ void lstm_cell_scalar(const float2 (&w_ih)[16][NIN], const float2 (&w_hh)[16][8], const float2 (&bi)[16],
+                                                 const float2 (&bh)[16], const float (&x)[NIN], float (&h)[8], float (&c)[8]) {
+    float2 gate[16];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+        float ax = bi[p].x, ay = bi[p].y, bx = bh[p].x, by = bh[p].y;
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) ax = __fmaf_rn(w_ih[p][k].x, x[k], ax), ay = __fmaf_rn(w_ih[p][k].y, x[k], ay);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bx = __fmaf_rn(w_hh[p][k].x, h[k], bx), by = __fmaf_rn(w_hh[p][k].y, h[k], by);
+        gate[p] = make_float2(__fadd_rn(ax, bx), __fadd_rn(ay, by));
+    }
+    lstm_gates(gate, h, c);
+}
+
+template <bool SCALAR>
 __global__ void __launch_bounds__(128, LSTM_MINBLOCKS) lstm_torques_kernel(const __grid_constant__ B200LeggedParams p,
                                                            const float* __restrict__ actions,
                                                            float* __restrict__ actions_clipped,
@@ -185,8 +206,13 @@ __global__ void __launch_bounds__(128, LSTM_MINBLOCKS) lstm_torques_kernel(const
     dst[4] = v.x, dst[5] = v.y, dst[6] = v.z, dst[7] = v.w;
     LD8(h0, hp) LD8(c0, cp) LD8(h1, hp1) LD8(c1, cp1)
 #undef LD8
-    lstm_cell<2>(c_net.w_ih0, c_net.w_hh0, c_net.b0, c_net.bh0, x, h0, c0);
-    lstm_cell<8>(c_net.w_ih1, c_net.w_hh1, c_net.b1, c_net.bh1, h0, h1, c1);
+    if (SCALAR) {
+        lstm_cell_scalar<2>(c_net.w_ih0, c_net.w_hh0, c_net.b0, c_net.bh0, x, h0, c0);
+        lstm_cell_scalar<8>(c_net.w_ih1, c_net.w_hh1, c_net.b1, c_net.bh1, h0, h1, c1);
+    } else {
+        lstm_cell<2>(c_net.w_ih0, c_net.w_hh0, c_net.b0, c_net.bh0, x, h0, c0);
+        lstm_cell<8>(c_net.w_ih1, c_net.w_hh1, c_net.b1, c_net.bh1, h0, h1, c1);
+    }
     float o = c_net.b_lin;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o = fmaf(c_net.w_lin[k], h1[k], o);
@@ -479,7 +505,7 @@ int b200gym_set_actuator_net(const float* w_ih0, const float* w_hh0, const float
 }
 
 static int g_lstm_variant = -1;
-/* debug / A-B aid: 0 = FFMA2 kernel (default), 1 = tcgen05 3xTF32 kernel, -1 = re-read B200GYM_LSTM_VARIANT */
+/* debug / A-B aid: 0 = scalar-fma kernel (default), 1 = tcgen05 3xTF32 kernel, 3 = packed FFMA2 kernel, -1 = re-read B200GYM_LSTM_VARIANT */
 int b200gym_debug_set_lstm_variant(int variant) {
     g_lstm_variant = variant;
     return B200GYM_OK;
@@ -492,8 +518,8 @@ int b200gym_lstm_torques(const B200LeggedParams* p, const float* actions, float*
     B200_REQUIRE(b200_aligned16(h) && b200_aligned16(c) && b200_aligned16(dof_state), B200GYM_EALIGN,
                  "lstm_torques: state pointers must be 16-byte aligned");
     const int m = p->num_envs * ND;
-    if (g_lstm_variant < 0) {   // 0 (default): FFMA2 kernel; 1: tcgen05 (3xTF32) gate mat-vecs — measured slower, see profiles/
-        const char* e = getenv("B200GYM_LSTM_VARIANT");
+    if (g_lstm_variant < 0) {   // 0 (default): scalar fma; 1: tcgen05 (3xTF32) gate mat-vecs — measured slower, see profiles/; 3: the packed
+        const char* e = getenv("B200GYM_LSTM_VARIANT");   // FFMA2 form of the default scalar-fma kernel
         g_lstm_variant = e ? atoi(e) : 0;
     }
     if (g_lstm_variant == 1) {
@@ -509,8 +535,12 @@ int b200gym_lstm_torques(const B200LeggedParams* p, const float* actions, float*
         B200_LAUNCH_CHECK("lstm_torques (tcgen05)");
         return B200GYM_OK;
     }
-    b200_launch_pdl(p->num_envs, lstm_torques_kernel, dim3((m + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), *p, actions, actions_clipped,
-                    reinterpret_cast<const float2*>(dof_state), h, c, torques, m);
+    if (g_lstm_variant != 3)   // scalar fma: 4-8 % faster than the packed form from 16 384 to 1 M envs, equal at 4096 (profiles/r2_lstm_scalar_ab.txt)
+        b200_launch_pdl(p->num_envs, lstm_torques_kernel<true>, dim3((m + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), *p, actions,
+                        actions_clipped, reinterpret_cast<const float2*>(dof_state), h, c, torques, m);
+    else
+        b200_launch_pdl(p->num_envs, lstm_torques_kernel<false>, dim3((m + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), *p, actions,
+                        actions_clipped, reinterpret_cast<const float2*>(dof_state), h, c, torques, m);
     B200_LAUNCH_CHECK("lstm_torques");
     return B200GYM_OK;
 }
