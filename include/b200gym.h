@@ -138,7 +138,8 @@ int b200gym_set_actuator_net(const float* w_ih0, const float* w_hh0, const float
                              const float* w_lin, const float* b_lin, float in_scale0, float in_scale1, float out_scale);
 int b200gym_lstm_torques(const B200LeggedParams* p, const float* actions, float* actions_clipped, const float* dof_state,
                          float* h, float* c, float* torques, void* stream);
-/* A/B aid: 0 = FFMA2 kernel (default), 1 = the gate mat-vecs on the tcgen05 tensor cores with the 3xTF32 operand split
+/* A/B aid: 0 = scalar-fma kernel (default), 3 = the same kernel with packed FFMA2 gate mat-vecs (bit-identical, 4-8 % slower),
+ * 1 = the gate mat-vecs on the tcgen05 tensor cores with the 3xTF32 operand split
  * ([A_hi | A_lo | A_hi] x [W_hi | W_hi | W_lo], fp32 accumulation in TMEM; meets the 1e-5 torque contract), -1 = re-read the
  * environment variable B200GYM_LSTM_VARIANT. */
 int b200gym_debug_set_lstm_variant(int variant);
