@@ -40,7 +40,8 @@ __device__ __forceinline__ void load_tile(unsigned char* dst, int chunk_stride, 
                                           int nchunks, int row_lim, int col_lim, int t) {
     const int pieces = nrows * nchunks;
     for (int q = t; q < pieces; q += 128) {
-        const int r = q / nchunks, c = q - r * nchunks;
+        // chunk counts are powers of two for every net in use (8 = one 64-column stage): shift / mask instead of an integer division
+        const int r = (nchunks & (nchunks - 1)) == 0 ? q >> (31 - __clz(nchunks)) : q / nchunks, c = q - r * nchunks;
         const int gr = row0 + r, gc = col0 + 8 * c;
         const bool ok = gr < row_lim && gc < col_lim;
         const __half* src = ok ? base + static_cast<size_t>(gr) * ld + gc : base;
