@@ -548,7 +548,9 @@ typedef struct B200ChainNet {
     float* flat_grad;
     int64_t w32_off[B200GYM_CHAIN_MAX_LAYERS];
     int32_t k_real[B200GYM_CHAIN_MAX_LAYERS];
-    int32_t ldx32, pad;
+    int32_t ldx32;
+    int32_t w_layout; /* layout of the fp16 weights in w16 (B200PackEntry.layout): 0 row-major [np, kp] (cp.async pieces), 1 chunk-major
+                       * [kp/8][np][8] (TMA bulk copies: a forward stage is 8 pieces of np*16 B, a backward stage kp/8 pieces of 1 KB) */
 } B200ChainNet;
 int b200gym_ppo_chain(const B200ChainNet* actor, const B200ChainNet* critic, const B200PpoLossParams* lp, const int64_t* idx,
                       const float* std, const float* actions, const float* old_log_prob, const float* advantages,

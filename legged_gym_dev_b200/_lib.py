@@ -173,7 +173,7 @@ class ChainNetPOD(C.Structure):
                 ("w_off", C.c_int64 * CHAIN_MAX_LAYERS), ("b_off", C.c_int64 * CHAIN_MAX_LAYERS),
                 ("kp", i32 * CHAIN_MAX_LAYERS), ("np", i32 * CHAIN_MAX_LAYERS), ("n_real", i32 * CHAIN_MAX_LAYERS),
                 ("num_layers", i32), ("ldx", i32), ("x32", vp), ("flat_grad", vp), ("w32_off", C.c_int64 * CHAIN_MAX_LAYERS),
-                ("k_real", i32 * CHAIN_MAX_LAYERS), ("ldx32", i32), ("pad", i32)]
+                ("k_real", i32 * CHAIN_MAX_LAYERS), ("ldx32", i32), ("pad", i32)]   # pad = w_layout (0 row-major, 1 chunk-major)
 
 
 class OptParamsPOD(C.Structure):

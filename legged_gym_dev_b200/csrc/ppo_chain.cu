@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
     if (warp == 0) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
     if (tid == 32) {
         for (int s = 0; s < WST; ++s) {
-            mbar_init(full + s, 128);
+            mbar_init(full + s, net.w_layout == 1 ? 1 : 128);   // TMA bulk copies: one arrive.expect_tx + the bytes; cp.async: every loader thread
             mbar_init(empty + s, 1);
         }
         mbar_init(accum, 1);
@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
             tc::mbar_arrive(aready);   // the input tile = step 0's A operand
         }
         const __half* w16 = static_cast<const __half*>(net.w16);
+        const bool wtma = net.w_layout == 1;
         const uint32_t taddr_w = tmem + WG_COL + (static_cast<uint32_t>((warp - LOADER_WARP0) * 32) << 16);
         // drains the jw-th weight-gradient accumulator (layer L-1-jw): TMEM lane = row of W_l, scaled by 1/batch, added to the flat gradient
         auto drain = [&](int jw) {
@@ -311,6 +312,31 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
             const int ns = last ? 0 : (ktot + KC - 1) / KC;
             for (int j = 0; j < ns; ++j, ++it) {
                 const int s = it % WST;
+                unsigned char* bt = ring + s * W_STAGE;
+                const int kc_eff = min(KC, ktot - j * KC);
+                if (wtma) {
+                    // chunk-major weights [kp/8][np][8]: the stage is a handful of contiguous pieces, moved by one thread as TMA bulk
+                    // copies that complete on the stage's barrier (no per-thread 16-byte cp.async, no publish step)
+                    if (t == 0) {
+                        tc::mbar_wait_sleep(empty + s, ((it / WST) & 1) ^ 1);
+                        const int np_l = net.np[l];
+                        if (fwd) {   // [np rows x kc_eff cols], K-major: chunk c of the stage = np_l * 16 contiguous bytes
+                            const int nch = kc_eff >> 3;
+                            const uint32_t piece = static_cast<uint32_t>(np_l) * 16u;
+                            mbar_expect_tx(full + s, piece * nch);
+                            for (int c = 0; c < nch; ++c)
+                                bulk_g2s(bt + c * CH128, W + (static_cast<size_t>(8 * j + c) * np_l) * 8, piece, full + s);
+                        } else {     // [kc_eff rows (of np) x kp cols], MN-major: chunk c = rows j*KC .. of column chunk c, kc_eff * 16 bytes
+                            const int nch = net.kp[l] >> 3;
+                            const uint32_t piece = static_cast<uint32_t>(kc_eff) * 16u;
+                            mbar_expect_tx(full + s, piece * nch);
+                            for (int c = 0; c < nch; ++c)
+                                bulk_g2s(bt + c * CHKC, W + (static_cast<size_t>(c) * np_l + j * KC) * 8, piece, full + s);
+                        }
+                    }
+                    tr(200 + it);
+                    continue;
+                }
                 if (pending >= 0 && !tc::mbar_try(empty + s, ((it / WST) & 1) ^ 1)) {
                     // about to block on the ring: hand the stage already in flight to the MMA warp first
                     tc::cp_async_wait<0>();
@@ -320,8 +346,6 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
                 }
                 tc::mbar_wait_sleep(empty + s, ((it / WST) & 1) ^ 1);
                 tr(250 + it);
-                unsigned char* bt = ring + s * W_STAGE;
-                const int kc_eff = min(KC, ktot - j * KC);
                 if (fwd) load_tile(bt, CH128, W, net.kp[l], 0, j * KC, net.np[l], kc_eff >> 3, net.np[l], net.kp[l], t);       // [n rows x k cols], K-major
                 else load_tile(bt, CHKC, W, net.kp[l], j * KC, 0, kc_eff, net.kp[l] >> 3, net.np[l], net.kp[l], t);            // [n rows = K x k cols = N], MN-major
                 tc::cp_async_commit();
@@ -348,7 +372,12 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
                     *reinterpret_cast<uint4*>(bt + t * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
                     *reinterpret_cast<uint4*>(bt + CH128 + t * 16) = make_uint4(0u, 0u, 0u, 0u);
                     fence_proxy_async();
-                    tc::mbar_arrive(full + s);
+                    if (wtma) {   // the stage barrier counts ONE arrival in this mode
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                        if (t == 0) tc::mbar_arrive(full + s);
+                    } else {
+                        tc::mbar_arrive(full + s);
+                    }
                     ++it;
                 }
                 if (step > L) drain(step - L - 1);   // the previous step's weight gradient, while this step's MMAs and epilogue run

@@ -62,29 +62,54 @@ class TensorCoreTrainer:
                 net.w16_off.append(off)
                 off += net.Np[l] * net.Kp[l]
         self.w16 = torch.zeros(off, dtype=torch.float16, device=self.dev)
-        tab = _lib.PackTablePOD()
-        e, end = 0, 0
-        for net in self.nets:
-            for l in range(net.L):
-                if e >= _lib.PACK_MAX:
-                    raise ValueError("too many layers for one pack launch")
-                end += net.N[l] * net.K[l]
-                t = tab.e[e]
-                t.src_off, t.dst_off, t.elem_end = net.w_off[l], net.w16_off[l], end
-                t.rows, t.cols, t.ld, t.layout = net.N[l], net.K[l], net.Kp[l], 0
-                e += 1
-        tab.n, tab.total = e, end
-        self._tab = tab
+        if sum(net.L for net in self.nets) > _lib.PACK_MAX:
+            raise ValueError("too many layers for one pack launch")
         self._bufs = {}
         # nets whose 128-row activation tiles fit in shared memory run forward + loss + input gradients as ONE launch (csrc/ppo_chain.cu)
         def chain_fits(net):
             smem = (2 + sum(k // 8 for k in net.Kp)) * (128 * 16 + 16) + 2 * 16 * (64 * 16 + 16) + 256 + 4 * sum(net.Np) + 320
             return 2 <= net.L <= _lib.CHAIN_MAX_LAYERS and max(net.Np) <= 128 and max(net.Kp[1:]) <= 128 and smem <= 227 * 1024
-        self.use_chain = all(chain_fits(n) for n in self.nets) and os.environ.get("B200GYM_PPO_CHAIN", "1") != "0"
+        self._use_chain = all(chain_fits(n) for n in self.nets) and os.environ.get("B200GYM_PPO_CHAIN", "1") != "0"
         # ... and the weight / bias gradients and the observation gather in the same launch (B200GYM_CHAIN_WGRAD=0: A/B against the
         # round-2a form, chain + row-gather launch + grouped weight-gradient GEMM)
-        self.fuse_wgrad = self.use_chain and os.environ.get("B200GYM_CHAIN_WGRAD", "1") != "0"
+        self.fuse_wgrad = self._use_chain and os.environ.get("B200GYM_CHAIN_WGRAD", "1") != "0"
+        # the chain kernel takes its weight tiles by TMA bulk copies from a CHUNK-MAJOR fp16 copy ([K/8][N][8]: a 64-column stage is 8
+        # contiguous pieces instead of 1024 16-byte ones); the layered GEMM path reads a row-major copy (B200GYM_CHAIN_TMA=0: row-major
+        # + cp.async in the chain kernel as well, for A/B)
+        self.chain_tma = os.environ.get("B200GYM_CHAIN_TMA", "1") != "0"
+        self._build_table()
         self.pack()
+
+    @property
+    def use_chain(self):
+        return self._use_chain
+
+    @use_chain.setter
+    def use_chain(self, on):
+        on = bool(on)
+        if on != self._use_chain:
+            self._use_chain = on
+            self._build_table()       # the two paths read different layouts of the fp16 copy
+            self.w16.zero_()
+            self.pack()
+
+    def _build_table(self):
+        self.w16_layout = 1 if (self._use_chain and self.chain_tma) else 0
+        tab = _lib.PackTablePOD()
+        e, end = 0, 0
+        for net in self.nets:
+            for l in range(net.L):
+                end += net.N[l] * net.K[l]
+                t = tab.e[e]
+                t.src_off, t.dst_off, t.elem_end = net.w_off[l], net.w16_off[l], end
+                t.rows, t.cols, t.layout = net.N[l], net.K[l], self.w16_layout
+                t.ld = net.Np[l] if self.w16_layout else net.Kp[l]     # chunk-major: rows per chunk; row-major: leading dimension
+                e += 1
+        tab.n, tab.total = e, end
+        self._tab = tab
+        for b in self._bufs.values():
+            for c in b.get("chain", ()):
+                c.pad = self.w16_layout
 
     # ------------------------------------------------------------------------------------------------------------
     def pack(self):
@@ -154,6 +179,7 @@ class TensorCoreTrainer:
             if l < net.L - 1:
                 c.h[l] = b["h"][i][l].data_ptr()
             c.k_real[l], c.w32_off[l] = net.K[l], net.w_off[l]
+        c.pad = self.w16_layout      # B200ChainNet.w_layout
         return c
 
     def _dgrad_launches(self, b, B):
