@@ -205,6 +205,8 @@ class LeggedRobot:
         self._ptr_actions, self._ptr_torques = self.actions.data_ptr(), self.torques.data_ptr()
         self._ptr_last_dof_vel = self.last_dof_vel.data_ptr()
         self._stream = None
+        # extras["episode"]: 0-d VIEWS of one persistent device buffer that every step rewrites in place (no allocation, no host sync).  A
+        # consumer that keeps them across steps must clone them — the runner logs from the per-step raw rows instead (ppo.py, _episode_stats).
         ep = {"rew_" + n: self._extras_out[i] for i, n in enumerate(p.active_terms)}
         if p.terrain_curriculum:
             ep["terrain_level"] = self._extras_out[K]
