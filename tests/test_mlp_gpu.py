@@ -1,5 +1,6 @@
-"""tcgen05 (TF32) fused MLP forward vs the plain fp32 torch forward of the same nn.Sequential.  TF32 keeps a 10-bit
-mantissa: tolerance 5e-3 absolute on O(1) outputs (SURVEY.md §8d cfg 5 allows TF32 for the G4 contraction)."""
+"""tcgen05 fused MLP forward (fp16 operands with fp32 accumulation in the default four-slot kernel, TF32 in the two-slot one) vs the
+plain fp32 torch forward of the same nn.Sequential.  Both keep a 10-bit mantissa: tolerance 5e-3 absolute on O(1) outputs (SURVEY.md
+§8d cfg 5 allows a tensor-core contraction for G4; the PPO update runs the same fp16 operand precision, so rollout and update agree)."""
 import pytest
 import torch
 import torch.nn as nn
