@@ -621,7 +621,8 @@ __device__ __forceinline__ void mlp_forward_h4_body(const B200MlpParams& p, cons
             mbar_init(bars + sl, TM);                  // full: every loader thread of the group arrives
             mbar_init(bars + NSLOT + sl, 1);           // empty: tcgen05.commit after the layer that last reads the X region
             mbar_init(bars + 2 * NSLOT + sl, 1);       // MMA completion (tcgen05.commit)
-            mbar_init(bars + 3 * NSLOT + sl, TM);      // ready: every epilogue thread of the slot arrives
+            // ready: every epilogue thread of the slot arrives (single-tile CTAs: all four warpgroups work on slot 0)
+            mbar_init(bars + 3 * NSLOT + sl, ((p.batch + TM - 1) / TM <= G && sl == 0) ? NSLOT * TM : TM);
         }
         fence_mbar_init();
     }
@@ -760,6 +761,39 @@ __device__ __forceinline__ void mlp_forward_h4_body(const B200MlpParams& p, cons
         }
     } else {
         // ------------------------------ epilogue warpgroup of slot warp / 4 ------------------------------
+        if (ntiles <= G) {
+            // Small batches (the rollout's 4096 envs = 32 tiles): a CTA holds at most ONE tile and three of its four epilogue warpgroups
+            // would idle while the layers run back to back, each waiting for a 128-thread epilogue.  Here the four warpgroups share the
+            // tile instead: warpgroup w takes the 16-column blocks w, w + 4, ... of every layer's accumulator (all four cover the 128
+            // TMEM lanes), so the per-layer epilogue is a quarter as long.  Same arithmetic per element: results bit-identical.
+            const int wg = warp >> 2;
+            const uint32_t my_taddr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+            unsigned char* hrow = sH0 + t * 16;
+            uint64_t *mma_done = bars + 2 * NSLOT, *ready = bars + 3 * NSLOT;
+            if (cta < ntiles) {
+                const int row = cta * TM + t;
+                const bool live = row < p.batch;
+                float* orow = out + static_cast<size_t>(row) * p.out_dim;
+                int boff = 0;
+                for (int l = 0; l < L; ++l) {
+                    const int N = p.dims[l + 1];
+                    mbar_wait(mma_done, l & 1);
+                    tc_fence_after();
+                    const float* sBl = sB + boff;
+                    for (int n0 = 16 * wg; n0 < N; n0 += 16 * NSLOT) {
+                        uint32_t ra[16];
+                        tmem_ld16_issue(my_taddr + n0, ra);
+                        tmem_ld16_wait(ra);
+                        if (l == L - 1) h4_epilogue_chunk<true>(ra, sBl, n0, hrow, orow, p.out_dim, live);
+                        else h4_epilogue_chunk<false>(ra, sBl, n0, hrow, orow, p.out_dim, live);
+                    }
+                    boff += N;
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(ready);
+                }
+            }
+        } else {
         const int slot = warp >> 2;
         const uint32_t my_taddr = tmem + static_cast<uint32_t>(slot * 128) + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         unsigned char* hrow = sH0 + slot * buf_bytes + t * 16;
@@ -801,6 +835,7 @@ __device__ __forceinline__ void mlp_forward_h4_body(const B200MlpParams& p, cons
                 tc_fence_before();
                 mbar_arrive(ready);
             }
+        }
         }
     }
     (void)lane;
