@@ -148,6 +148,9 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
     // dependent L2 / HBM round trips) BEFORE the wait, under the optimiser kernel.
     pdl_launch_dependents();
     const bool fuse = net.flat_grad != nullptr;
+    // The last step's dW_0 accumulator: when it fits (kp[0] <= 64 columns next to the L x 16 bias columns) it goes into the MAIN accumulator
+    // region, which is idle by then, so that step does not wait for the drain of dW_1 (5 K cycles for the 64 x 128 block of the flat nets)
+    const bool alt0 = net.kp[0] <= 64 && 16 * L <= 64;
     Trace tr;
 #ifdef B200GYM_CHAIN_TRACE
     // CTA Gantt chart: (globaltimer at start, at end, SM id) of every CTA behind the six event regions
@@ -210,7 +213,8 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
                 int s = 0;
                 for (int blk = 0; blk < nblk; ++blk) {
                     const int jw = step - L + blk;
-                    if (jw > 0) {
+                    const bool in_main = last && alt0;
+                    if (jw > 0 && !in_main) {
                         tc::mbar_wait_sleep(wfree, (jw - 1) & 1);
                         tc::fence_after();
                     }
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
                         const uint32_t idw = tc::idesc_f16(ncols, true, true);
                         uint64_t da = tc::smem_desc(dzl, 128, CH128), db = tc::smem_desc(smem + act_off[l] + 16 * blk * CH128, 128, CH128);
                         for (int q = 0; q < TM / 16; ++q) {
-                            tc::mma_f16(tmem + WG_COL, da, db, idw, q != 0 ? 1u : 0u);
+                            tc::mma_f16(tmem + (in_main ? 64u : WG_COL), da, db, idw, q != 0 ? 1u : 0u);
                             da += 256u >> 4;
                             db += 256u >> 4;
                         }
@@ -263,11 +267,12 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
         }
         const __half* w16 = static_cast<const __half*>(net.w16);
         const bool wtma = net.w_layout == 1;
-        const uint32_t taddr_w = tmem + WG_COL + (static_cast<uint32_t>((warp - LOADER_WARP0) * 32) << 16);
+        const uint32_t taddr_q = tmem + (static_cast<uint32_t>((warp - LOADER_WARP0) * 32) << 16);
         // drains the jw-th weight-gradient accumulator (layer L-1-jw): TMEM lane = row of W_l, scaled by 1/batch, added to the flat gradient
         auto drain = [&](int jw) {
             const int l = jw < L - 1 ? L - 1 - jw : 0;
             const int col0 = jw < L - 1 ? 0 : 128 * (jw - (L - 1));   // layer 0 goes in blocks of 128 input columns
+            const uint32_t taddr_w = taddr_q + ((alt0 && jw >= L - 1) ? 64u : WG_COL);
             tr(300 + jw * 4);
             tc::mbar_wait_sleep(wdone, jw & 1);
             tc::fence_after();
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
             fence_proxy_async();
             tc::mbar_arrive(full + pending);
         }
-        if (fuse)
+        if (fuse && !alt0)   // (alt0: the epilogue warps drain dW_0 from the main accumulator)
             for (int blk = 0; blk < (net.kp[0] + 127) >> 7; ++blk) drain(L - 1 + blk);
     } else {
         // ------------------------------ epilogue warps: TMEM lane = tile row; two warps per lane quadrant, each takes half of the
@@ -650,6 +655,34 @@ __global__ void __launch_bounds__(chain_threads(EH), 2) ppo_chain_kernel(const _
                         tc::ld16_issue(taddr + 16 * m, r);
                         tc::ld16_wait(r);
                         if (row < net.n_real[m]) atomicAdd(net.flat_grad + net.b_off[m] + row, __uint_as_float(r[0]) * a.lp.inv_global_batch);
+                        __syncwarp();
+                    }
+                }
+                if (alt0 && (warp & 3) * 32 < net.n_real[0]) {
+                    // dW_0 sits in columns [64, 64 + kp[0]) of this accumulator: the epilogue warps drain it (row = TMEM lane, the halves
+                    // alternate over the 16-column blocks) while the loader warps are still draining dW_1
+                    const int kr = net.k_real[0];
+                    float* g = net.flat_grad + net.w32_off[0] + static_cast<size_t>(row) * kr;
+                    const bool vec = (kr & 3) == 0 && (net.w32_off[0] & 3) == 0;
+                    const float sc = a.lp.inv_global_batch;
+                    for (int n0 = 16 * half; n0 < kr; n0 += 16 * EH) {
+                        uint32_t r[16];
+                        tc::ld16_issue(taddr + 64 + n0, r);
+                        tc::ld16_wait(r);
+                        if (row < net.n_real[0]) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int c = n0 + 4 * q;
+                                if (vec && c + 4 <= kr) {
+                                    red_add_v4(g + c, __uint_as_float(r[4 * q]) * sc, __uint_as_float(r[4 * q + 1]) * sc, __uint_as_float(r[4 * q + 2]) * sc,
+                                               __uint_as_float(r[4 * q + 3]) * sc);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (c + e < kr) atomicAdd(g + c + e, __uint_as_float(r[4 * q + e]) * sc);
+                                }
+                            }
+                        }
                         __syncwarp();
                     }
                 }
